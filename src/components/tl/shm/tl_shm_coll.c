@@ -1,0 +1,816 @@
+/* tl/shm collective algorithms, written as step programs (tl_shm_prog.h).
+ * Algorithm catalogue follows what the reference's host TL offers
+ * (tl_ucp: knomial / sra_knomial / ring / dbt / bruck / pairwise / linear /
+ * neighbor, reference tl/ucp/<coll>/<coll>.c alg tables); every algorithm
+ * here is a new formulation on top of the program builder. */
+#include "tl_shm_coll.h"
+#include "coll_patterns/knomial_tree.h"
+#include "coll_patterns/double_binary_tree.h"
+
+#define CHK(_x) do { st = (_x); if (ucc_unlikely(st != UCC_OK)) goto err; } while (0)
+#define ARGS(_t) (&(_t)->super.bargs.args)
+#define OFF(_p, _bytes) PTR_OFFSET(_p, _bytes)
+
+static unsigned cfg_radix(const ucc_mrange_uint_t *r, size_t msg, ucc_memory_type_t mt, unsigned dflt, ucc_rank_t size)
+{
+    unsigned v = ucc_mrange_uint_get(r, msg, mt);
+    if (v == UCC_UUNITS_AUTO || v < 2) v = dflt;
+    if (v > size) v = size;
+    if (v > 64) v = 64;
+    return v < 2 ? 2 : v;
+}
+
+/* ================================================================== */
+/* barrier / fanin / fanout                                            */
+/* ================================================================== */
+static ucc_status_t prog_fanin(ucc_tl_shm_task_t *t, ucc_rank_t root, unsigned radix, unsigned step)
+{
+    ucc_kn_tree_t tr; ucc_status_t st = UCC_OK;
+    ucc_kn_tree_init(&tr, t->vrank, t->vsize, root, radix);
+    for (unsigned i = 0; i < tr.n_children; i++) CHK(shm_prog_recv(t, tr.children[i], NULL, 0, UCC_MEMORY_TYPE_HOST, step));
+    CHK(shm_prog_wait(t));
+    if (tr.parent != UCC_RANK_INVALID) { CHK(shm_prog_send(t, tr.parent, NULL, 0, UCC_MEMORY_TYPE_HOST, step)); CHK(shm_prog_wait(t)); }
+err:
+    return st;
+}
+static ucc_status_t prog_fanout(ucc_tl_shm_task_t *t, ucc_rank_t root, unsigned radix, unsigned step)
+{
+    ucc_kn_tree_t tr; ucc_status_t st = UCC_OK;
+    ucc_kn_tree_init(&tr, t->vrank, t->vsize, root, radix);
+    if (tr.parent != UCC_RANK_INVALID) { CHK(shm_prog_recv(t, tr.parent, NULL, 0, UCC_MEMORY_TYPE_HOST, step)); CHK(shm_prog_wait(t)); }
+    for (unsigned i = 0; i < tr.n_children; i++) CHK(shm_prog_send(t, tr.children[i], NULL, 0, UCC_MEMORY_TYPE_HOST, step));
+    CHK(shm_prog_wait(t));
+err:
+    return st;
+}
+ucc_status_t ucc_tl_shm_barrier_knomial(ucc_tl_shm_task_t *t)
+{
+    ucc_tl_shm_context_t *ctx = SHM_CTX(t->team);
+    unsigned radix = cfg_radix(&ctx->cfg.barrier_kn_radix, 0, UCC_MEMORY_TYPE_HOST, 4, t->vsize);
+    ucc_status_t st;
+    CHK(prog_fanin(t, 0, radix, 1));
+    CHK(prog_fanout(t, 0, radix, 2));
+err:
+    return st;
+}
+ucc_status_t ucc_tl_shm_fanin_knomial(ucc_tl_shm_task_t *t)
+{ return prog_fanin(t, (ucc_rank_t)ARGS(t)->root, cfg_radix(&SHM_CTX(t->team)->cfg.barrier_kn_radix, 0, UCC_MEMORY_TYPE_HOST, 4, t->vsize), 1); }
+ucc_status_t ucc_tl_shm_fanout_knomial(ucc_tl_shm_task_t *t)
+{ return prog_fanout(t, (ucc_rank_t)ARGS(t)->root, cfg_radix(&SHM_CTX(t->team)->cfg.barrier_kn_radix, 0, UCC_MEMORY_TYPE_HOST, 4, t->vsize), 1); }
+
+/* ================================================================== */
+/* bcast                                                               */
+/* ================================================================== */
+ucc_status_t ucc_tl_shm_bcast_knomial_prog(ucc_tl_shm_task_t *t, void *buf, size_t len, ucc_memory_type_t mt, ucc_rank_t root, unsigned radix)
+{
+    ucc_kn_tree_t tr; ucc_status_t st = UCC_OK;
+    ucc_kn_tree_init(&tr, t->vrank, t->vsize, root, radix);
+    if (tr.parent != UCC_RANK_INVALID) { CHK(shm_prog_recv(t, tr.parent, buf, len, mt, 1)); CHK(shm_prog_wait(t)); }
+    for (unsigned i = 0; i < tr.n_children; i++) CHK(shm_prog_send(t, tr.children[i], buf, len, mt, 1));
+    CHK(shm_prog_wait(t));
+err:
+    return st;
+}
+ucc_status_t ucc_tl_shm_bcast_knomial(ucc_tl_shm_task_t *t)
+{
+    ucc_coll_args_t *a = ARGS(t);
+    size_t len = a->src.info.count * ucc_dt_size(a->src.info.datatype);
+    unsigned radix = cfg_radix(&SHM_CTX(t->team)->cfg.bcast_kn_radix, len, a->src.info.mem_type, 4, t->vsize);
+    ucc_rank_t root = (ucc_rank_t)a->root;
+    if (UCC_COLL_ARGS_ACTIVE_SET(a)) root = (ucc_rank_t)(((int64_t)a->root - (int64_t)a->active_set.start) / a->active_set.stride);
+    return ucc_tl_shm_bcast_knomial_prog(t, a->src.info.buffer, len, a->src.info.mem_type, root, radix);
+}
+/* scatter (binomial over blocks) followed by ring allgather: bandwidth optimal for large messages */
+ucc_status_t ucc_tl_shm_bcast_sag(ucc_tl_shm_task_t *t)
+{
+    ucc_coll_args_t *a = ARGS(t);
+    size_t dts = ucc_dt_size(a->src.info.datatype), count = a->src.info.count;
+    ucc_memory_type_t mt = a->src.info.mem_type;
+    ucc_rank_t N = t->vsize, root = (ucc_rank_t)a->root, vr = (t->vrank + N - root) % N;
+    char *buf = (char *)a->src.info.buffer;
+    ucc_status_t st = UCC_OK;
+    ucc_kn_tree_t tr;
+    if (UCC_COLL_ARGS_ACTIVE_SET(a)) return UCC_ERR_NOT_SUPPORTED;
+    /* scatter: a rank receives the blocks of its whole subtree [vr, vr+span), forwards sub-ranges to children */
+    ucc_kn_tree_init(&tr, t->vrank, N, root, 2);
+    if (tr.parent != UCC_RANK_INVALID) {
+        ucc_rank_t span = ucc_kn_subtree_size(vr, N, 2);
+        size_t off = ucc_buffer_block_offset(count, N, vr), end = ucc_buffer_block_offset(count, N, vr + span - 1) + ucc_buffer_block_count(count, N, vr + span - 1);
+        CHK(shm_prog_recv(t, tr.parent, buf + off * dts, (end - off) * dts, mt, 1)); CHK(shm_prog_wait(t));
+    }
+    for (unsigned i = 0; i < tr.n_children; i++) {
+        ucc_rank_t cvr = (tr.children[i] + N - root) % N, span = ucc_kn_subtree_size(cvr, N, 2);
+        size_t off = ucc_buffer_block_offset(count, N, cvr), end = ucc_buffer_block_offset(count, N, cvr + span - 1) + ucc_buffer_block_count(count, N, cvr + span - 1);
+        CHK(shm_prog_send(t, tr.children[i], buf + off * dts, (end - off) * dts, mt, 1));
+    }
+    CHK(shm_prog_wait(t));
+    /* ring allgather of the blocks in virtual-rank space */
+    for (ucc_rank_t s = 0; s + 1 < N; s++) {
+        ucc_rank_t sb = (vr + N - s) % N, rb = (vr + N - s - 1) % N;
+        ucc_rank_t next = (t->vrank + 1) % N, prev = (t->vrank + N - 1) % N;
+        CHK(shm_prog_send(t, next, buf + ucc_buffer_block_offset(count, N, sb) * dts, ucc_buffer_block_count(count, N, sb) * dts, mt, 2 + s));
+        CHK(shm_prog_recv(t, prev, buf + ucc_buffer_block_offset(count, N, rb) * dts, ucc_buffer_block_count(count, N, rb) * dts, mt, 2 + s));
+        CHK(shm_prog_wait(t));
+    }
+err:
+    return st;
+}
+/* double binary tree: the two halves of the message travel down two complementary trees */
+ucc_status_t ucc_tl_shm_bcast_dbt(ucc_tl_shm_task_t *t)
+{
+    ucc_coll_args_t *a = ARGS(t);
+    size_t dts = ucc_dt_size(a->src.info.datatype), count = a->src.info.count, c1 = count / 2, c2 = count - c1;
+    ucc_memory_type_t mt = a->src.info.mem_type;
+    ucc_rank_t N = t->vsize, root = (ucc_rank_t)a->root, vr = (t->vrank + N - root) % N;
+    char *buf = (char *)a->src.info.buffer;
+    ucc_dbt_t dbt; ucc_status_t st = UCC_OK;
+    if (UCC_COLL_ARGS_ACTIVE_SET(a) || N < 3) return UCC_ERR_NOT_SUPPORTED;
+    /* trees span virtual ranks 1..N-1; virtual rank 0 (the root) feeds both tree roots */
+    if (vr == 0) {
+        ucc_rank_t r1, r2; ucc_dbt_roots(N - 1, &r1, &r2);
+        CHK(shm_prog_send(t, (r1 + 1 + root) % N, buf, c1 * dts, mt, 1));
+        CHK(shm_prog_send(t, (r2 + 1 + root) % N, buf + c1 * dts, c2 * dts, mt, 2));
+        CHK(shm_prog_wait(t));
+        return UCC_OK;
+    }
+    ucc_dbt_init(&dbt, vr - 1, N - 1);
+    for (int k = 0; k < 2; k++) {
+        ucc_rank_t parent = dbt.parent[k] == UCC_RANK_INVALID ? root : (dbt.parent[k] + 1 + root) % N;
+        CHK(shm_prog_recv(t, parent, k == 0 ? buf : buf + c1 * dts, (k == 0 ? c1 : c2) * dts, mt, 1 + (unsigned)k));
+    }
+    CHK(shm_prog_wait(t));
+    for (int k = 0; k < 2; k++) for (int c = 0; c < 2; c++) if (dbt.children[k][c] != UCC_RANK_INVALID)
+        CHK(shm_prog_send(t, (dbt.children[k][c] + 1 + root) % N, k == 0 ? buf : buf + c1 * dts, (k == 0 ? c1 : c2) * dts, mt, 1 + (unsigned)k));
+    CHK(shm_prog_wait(t));
+err:
+    return st;
+}
+
+/* ================================================================== */
+/* allreduce                                                           */
+/* ================================================================== */
+/* recursive k-ing on buffer `acc` (count elements); scratch must hold (radix-1)*count elements */
+static ucc_status_t prog_allreduce_knomial(ucc_tl_shm_task_t *t, void *acc, void *scratch, size_t count, ucc_memory_type_t mt, unsigned radix, unsigned step0)
+{
+    ucc_kn_pattern_t p; ucc_rank_t peers[64]; size_t len = count * ucc_dt_size(t->dt);
+    ucc_status_t st = UCC_OK; unsigned step = step0;
+    ucc_kn_pattern_init(&p, t->vrank, t->vsize, radix);
+    if (p.type == UCC_KN_NODE_EXTRA) {
+        CHK(shm_prog_send(t, p.partner, acc, len, mt, step)); CHK(shm_prog_wait(t));
+        CHK(shm_prog_recv(t, p.partner, acc, len, mt, step + 1)); CHK(shm_prog_wait(t));
+        return UCC_OK;
+    }
+    if (p.type == UCC_KN_NODE_PROXY) {
+        CHK(shm_prog_recv(t, p.partner, scratch, len, mt, step)); CHK(shm_prog_wait(t));
+        CHK(shm_prog_reduce(t, acc, acc, scratch, count, mt, 0));
+    }
+    step += 2;
+    for (uint64_t dist = 1; dist < p.n_full; dist *= p.radix, step++) {
+        unsigned n = ucc_kn_round_peers(&p, dist, peers);
+        for (unsigned i = 0; i < n; i++) CHK(shm_prog_recv(t, peers[i], OFF(scratch, i * len), len, mt, step));
+        for (unsigned i = 0; i < n; i++) CHK(shm_prog_send(t, peers[i], acc, len, mt, step));
+        CHK(shm_prog_wait(t));
+        for (unsigned i = 0; i < n; i++) CHK(shm_prog_reduce(t, acc, acc, OFF(scratch, i * len), count, mt, 0));
+    }
+    if (t->op == UCC_OP_AVG) CHK(shm_prog_reduce(t, acc, acc, NULL, count, mt, 1));
+    if (p.type == UCC_KN_NODE_PROXY) { CHK(shm_prog_send(t, p.partner, acc, len, mt, step0 + 1)); CHK(shm_prog_wait(t)); }
+err:
+    return st;
+}
+ucc_status_t ucc_tl_shm_allreduce_knomial(ucc_tl_shm_task_t *t)
+{
+    ucc_coll_args_t *a = ARGS(t);
+    size_t count = a->dst.info.count, len = count * ucc_dt_size(a->dst.info.datatype);
+    ucc_memory_type_t mt = a->dst.info.mem_type;
+    unsigned radix = cfg_radix(&SHM_CTX(t->team)->cfg.allreduce_kn_radix, len, mt, 4, t->vsize);
+    void *scratch; ucc_status_t st;
+    CHK(shm_task_scratch(t, (size_t)(radix - 1) * len, mt, &scratch));
+    if (!UCC_IS_INPLACE(*a)) CHK(shm_prog_copy(t, a->dst.info.buffer, a->src.info.buffer, len, mt, a->src.info.mem_type));
+    CHK(prog_allreduce_knomial(t, a->dst.info.buffer, scratch, count, mt, radix, 1));
+err:
+    return st;
+}
+
+/* reduce-scatter ring on `buf` (count elems split in N blocks), result block (vrank+shift)%N complete on each rank */
+static ucc_status_t prog_rs_ring(ucc_tl_shm_task_t *t, char *buf, void *scratch, size_t count, ucc_memory_type_t mt, int final_block_is_own, unsigned step0)
+{
+    ucc_rank_t N = t->vsize, r = t->vrank, next = (r + 1) % N, prev = (r + N - 1) % N;
+    size_t dts = ucc_dt_size(t->dt); ucc_status_t st = UCC_OK;
+    int sh = final_block_is_own ? 1 : 0; /* own: last received block == r; else == r+1 */
+    for (ucc_rank_t s = 0; s + 1 < N; s++) {
+        ucc_rank_t sb = (r + 2 * N - s - sh) % N, rb = (r + 2 * N - s - 1 - sh) % N;
+        size_t rc = ucc_buffer_block_count(count, N, rb);
+        CHK(shm_prog_send(t, next, buf + ucc_buffer_block_offset(count, N, sb) * dts, ucc_buffer_block_count(count, N, sb) * dts, mt, step0 + s));
+        CHK(shm_prog_recv(t, prev, scratch, rc * dts, mt, step0 + s));
+        CHK(shm_prog_wait(t));
+        CHK(shm_prog_reduce(t, buf + ucc_buffer_block_offset(count, N, rb) * dts, buf + ucc_buffer_block_offset(count, N, rb) * dts, scratch, rc, mt, 0));
+    }
+err:
+    return st;
+}
+/* allgather ring where rank r starts owning block (r+own_shift)%N */
+static ucc_status_t prog_ag_ring(ucc_tl_shm_task_t *t, char *buf, size_t count, size_t dts, ucc_memory_type_t mt, int own_shift, unsigned step0)
+{
+    ucc_rank_t N = t->vsize, r = t->vrank, next = (r + 1) % N, prev = (r + N - 1) % N;
+    ucc_status_t st = UCC_OK;
+    for (ucc_rank_t s = 0; s + 1 < N; s++) {
+        ucc_rank_t sb = (r + own_shift + 2 * N - s) % N, rb = (r + own_shift + 2 * N - s - 1) % N;
+        CHK(shm_prog_send(t, next, buf + ucc_buffer_block_offset(count, N, sb) * dts, ucc_buffer_block_count(count, N, sb) * dts, mt, step0 + s));
+        CHK(shm_prog_recv(t, prev, buf + ucc_buffer_block_offset(count, N, rb) * dts, ucc_buffer_block_count(count, N, rb) * dts, mt, step0 + s));
+        CHK(shm_prog_wait(t));
+    }
+err:
+    return st;
+}
+ucc_status_t ucc_tl_shm_allreduce_ring(ucc_tl_shm_task_t *t)
+{
+    ucc_coll_args_t *a = ARGS(t);
+    size_t count = a->dst.info.count, dts = ucc_dt_size(a->dst.info.datatype);
+    ucc_memory_type_t mt = a->dst.info.mem_type; ucc_rank_t N = t->vsize, own = (t->vrank + 1) % N;
+    char *dst = (char *)a->dst.info.buffer; void *scratch; ucc_status_t st;
+    if (count < N) return UCC_ERR_NOT_SUPPORTED; /* fallback handles tiny vectors */
+    CHK(shm_task_scratch(t, ucc_div_round_up(count, N) * dts, mt, &scratch));
+    if (!UCC_IS_INPLACE(*a)) CHK(shm_prog_copy(t, dst, a->src.info.buffer, count * dts, mt, a->src.info.mem_type));
+    CHK(prog_rs_ring(t, dst, scratch, count, mt, 0, 1));
+    if (t->op == UCC_OP_AVG) CHK(shm_prog_reduce(t, dst + ucc_buffer_block_offset(count, N, own) * dts, dst + ucc_buffer_block_offset(count, N, own) * dts, NULL, ucc_buffer_block_count(count, N, own), mt, 1));
+    CHK(prog_ag_ring(t, dst, count, dts, mt, 1, 1 + N));
+err:
+    return st;
+}
+/* scatter-reduce by recursive vector halving + allgather by recursive doubling (radix 2 SRA) */
+ucc_status_t ucc_tl_shm_allreduce_sra(ucc_tl_shm_task_t *t)
+{
+    ucc_coll_args_t *a = ARGS(t);
+    size_t count = a->dst.info.count, dts = ucc_dt_size(a->dst.info.datatype), len = count * dts;
+    ucc_memory_type_t mt = a->dst.info.mem_type;
+    char *dst = (char *)a->dst.info.buffer; void *scratch;
+    ucc_kn_pattern_t p; ucc_status_t st; unsigned step = 3, nsteps = 0;
+    size_t off[32], cnt[32], soff[32], scnt[32], seg_off = 0, seg_cnt = count;
+    ucc_kn_pattern_init(&p, t->vrank, t->vsize, 2);
+    if (count < p.n_full) return UCC_ERR_NOT_SUPPORTED;
+    CHK(shm_task_scratch(t, len, mt, &scratch));
+    if (!UCC_IS_INPLACE(*a)) CHK(shm_prog_copy(t, dst, a->src.info.buffer, len, mt, a->src.info.mem_type));
+    if (p.type == UCC_KN_NODE_EXTRA) {
+        CHK(shm_prog_send(t, p.partner, dst, len, mt, 1)); CHK(shm_prog_wait(t));
+        CHK(shm_prog_recv(t, p.partner, dst, len, mt, 2)); CHK(shm_prog_wait(t));
+        return UCC_OK;
+    }
+    if (p.type == UCC_KN_NODE_PROXY) { CHK(shm_prog_recv(t, p.partner, scratch, len, mt, 1)); CHK(shm_prog_wait(t)); CHK(shm_prog_reduce(t, dst, dst, scratch, count, mt, 0)); }
+    for (ucc_rank_t mask = p.n_full >> 1; mask > 0; mask >>= 1, step++, nsteps++) {
+        ucc_rank_t peer = t->vrank ^ mask;
+        size_t h1 = seg_cnt / 2, h2 = seg_cnt - h1;
+        if (!(t->vrank & mask)) { off[nsteps] = seg_off; cnt[nsteps] = h1; soff[nsteps] = seg_off + h1; scnt[nsteps] = h2; }
+        else { off[nsteps] = seg_off + h1; cnt[nsteps] = h2; soff[nsteps] = seg_off; scnt[nsteps] = h1; }
+        CHK(shm_prog_send(t, peer, dst + soff[nsteps] * dts, scnt[nsteps] * dts, mt, step));
+        CHK(shm_prog_recv(t, peer, scratch, cnt[nsteps] * dts, mt, step));
+        CHK(shm_prog_wait(t));
+        CHK(shm_prog_reduce(t, dst + off[nsteps] * dts, dst + off[nsteps] * dts, scratch, cnt[nsteps], mt, 0));
+        seg_off = off[nsteps]; seg_cnt = cnt[nsteps];
+    }
+    if (t->op == UCC_OP_AVG) CHK(shm_prog_reduce(t, dst + seg_off * dts, dst + seg_off * dts, NULL, seg_cnt, mt, 1));
+    for (int i = (int)nsteps - 1; i >= 0; i--, step++) {
+        ucc_rank_t peer = t->vrank ^ (ucc_rank_t)(1u << (nsteps - 1 - (unsigned)i));
+        CHK(shm_prog_send(t, peer, dst + off[i] * dts, cnt[i] * dts, mt, step));
+        CHK(shm_prog_recv(t, peer, dst + soff[i] * dts, scnt[i] * dts, mt, step));
+        CHK(shm_prog_wait(t));
+    }
+    if (p.type == UCC_KN_NODE_PROXY) { CHK(shm_prog_send(t, p.partner, dst, len, mt, 2)); CHK(shm_prog_wait(t)); }
+err:
+    return st;
+}
+/* reduce down one tree / bcast up the other on two halves (double binary tree) */
+ucc_status_t ucc_tl_shm_allreduce_dbt(ucc_tl_shm_task_t *t)
+{
+    ucc_coll_args_t *a = ARGS(t);
+    size_t count = a->dst.info.count, dts = ucc_dt_size(a->dst.info.datatype), c[2], o[2];
+    ucc_memory_type_t mt = a->dst.info.mem_type;
+    char *dst = (char *)a->dst.info.buffer; void *scratch;
+    ucc_dbt_t dbt; ucc_status_t st; ucc_rank_t N = t->vsize;
+    if (N < 2 || count < 2) return UCC_ERR_NOT_SUPPORTED;
+    c[0] = count / 2; c[1] = count - c[0]; o[0] = 0; o[1] = c[0];
+    CHK(shm_task_scratch(t, 2 * c[1] * dts, mt, &scratch));
+    if (!UCC_IS_INPLACE(*a)) CHK(shm_prog_copy(t, dst, a->src.info.buffer, count * dts, mt, a->src.info.mem_type));
+    ucc_dbt_init(&dbt, t->vrank, N);
+    for (int k = 0; k < 2; k++) { /* reduce towards the root of tree k */
+        unsigned nc = 0;
+        for (int ch = 0; ch < 2; ch++) if (dbt.children[k][ch] != UCC_RANK_INVALID) { CHK(shm_prog_recv(t, dbt.children[k][ch], OFF(scratch, nc * c[1] * dts), c[k] * dts, mt, 1 + (unsigned)k)); nc++; }
+        CHK(shm_prog_wait(t));
+        for (unsigned i = 0; i < nc; i++) CHK(shm_prog_reduce(t, dst + o[k] * dts, dst + o[k] * dts, OFF(scratch, i * c[1] * dts), c[k], mt, 0));
+        if (dbt.parent[k] != UCC_RANK_INVALID) { CHK(shm_prog_send(t, dbt.parent[k], dst + o[k] * dts, c[k] * dts, mt, 1 + (unsigned)k)); CHK(shm_prog_wait(t)); }
+        else if (t->op == UCC_OP_AVG) CHK(shm_prog_reduce(t, dst + o[k] * dts, dst + o[k] * dts, NULL, c[k], mt, 1));
+    }
+    for (int k = 0; k < 2; k++) { /* broadcast back */
+        if (dbt.parent[k] != UCC_RANK_INVALID) { CHK(shm_prog_recv(t, dbt.parent[k], dst + o[k] * dts, c[k] * dts, mt, 3 + (unsigned)k)); CHK(shm_prog_wait(t)); }
+        for (int ch = 0; ch < 2; ch++) if (dbt.children[k][ch] != UCC_RANK_INVALID) CHK(shm_prog_send(t, dbt.children[k][ch], dst + o[k] * dts, c[k] * dts, mt, 3 + (unsigned)k));
+        CHK(shm_prog_wait(t));
+    }
+err:
+    return st;
+}
+
+/* ================================================================== */
+/* reduce                                                              */
+/* ================================================================== */
+ucc_status_t ucc_tl_shm_reduce_knomial(ucc_tl_shm_task_t *t)
+{
+    ucc_coll_args_t *a = ARGS(t);
+    ucc_rank_t root = (ucc_rank_t)a->root; int is_root = t->vrank == root;
+    size_t count = is_root ? a->dst.info.count : a->src.info.count;
+    ucc_datatype_t dt = is_root ? a->dst.info.datatype : a->src.info.datatype;
+    ucc_memory_type_t mt = is_root ? a->dst.info.mem_type : a->src.info.mem_type;
+    size_t len = count * ucc_dt_size(dt);
+    unsigned radix = cfg_radix(&SHM_CTX(t->team)->cfg.reduce_kn_radix, len, mt, 4, t->vsize);
+    ucc_kn_tree_t tr; void *acc, *scratch = NULL; const void *first; ucc_status_t st;
+    ucc_kn_tree_init(&tr, t->vrank, t->vsize, root, radix);
+    first = (is_root && UCC_IS_INPLACE(*a)) ? a->dst.info.buffer : a->src.info.buffer;
+    if (tr.n_children) CHK(shm_task_scratch(t, (size_t)tr.n_children * len, mt, &scratch));
+    if (is_root) acc = a->dst.info.buffer;
+    else if (tr.n_children) CHK(shm_task_scratch(t, len, mt, &acc));
+    else acc = (void *)first; /* leaf: send the source as is */
+    for (unsigned i = 0; i < tr.n_children; i++) CHK(shm_prog_recv(t, tr.children[i], OFF(scratch, i * len), len, mt, 1));
+    CHK(shm_prog_wait(t));
+    for (unsigned i = 0; i < tr.n_children; i++) CHK(shm_prog_reduce(t, acc, i == 0 ? first : acc, OFF(scratch, i * len), count, mt, 0));
+    if (is_root) {
+        if (!tr.n_children) CHK(shm_prog_copy(t, acc, first, len, mt, mt));
+        if (t->op == UCC_OP_AVG) CHK(shm_prog_reduce(t, acc, acc, NULL, count, mt, 1));
+    } else { CHK(shm_prog_send(t, tr.parent, acc, len, mt, 1)); CHK(shm_prog_wait(t)); }
+err:
+    return st;
+}
+/* scatter-reduce (ring) followed by gather to the root: bandwidth optimal */
+ucc_status_t ucc_tl_shm_reduce_srg(ucc_tl_shm_task_t *t)
+{
+    ucc_coll_args_t *a = ARGS(t);
+    ucc_rank_t root = (ucc_rank_t)a->root, N = t->vsize; int is_root = t->vrank == root;
+    size_t count = is_root ? a->dst.info.count : a->src.info.count;
+    ucc_datatype_t dt = is_root ? a->dst.info.datatype : a->src.info.datatype;
+    ucc_memory_type_t mt = is_root ? a->dst.info.mem_type : a->src.info.mem_type;
+    size_t dts = ucc_dt_size(dt);
+    void *work, *scratch; char *w; ucc_status_t st;
+    if (count < N) return UCC_ERR_NOT_SUPPORTED;
+    CHK(shm_task_scratch(t, ucc_div_round_up(count, N) * dts, mt, &scratch));
+    if (is_root) { work = a->dst.info.buffer; if (!UCC_IS_INPLACE(*a)) CHK(shm_prog_copy(t, work, a->src.info.buffer, count * dts, mt, a->src.info.mem_type)); }
+    else { CHK(shm_task_scratch(t, count * dts, mt, &work)); CHK(shm_prog_copy(t, work, a->src.info.buffer, count * dts, mt, mt)); }
+    w = (char *)work;
+    CHK(prog_rs_ring(t, w, scratch, count, mt, 1, 1));
+    if (t->op == UCC_OP_AVG) CHK(shm_prog_reduce(t, w + ucc_buffer_block_offset(count, N, t->vrank) * dts, w + ucc_buffer_block_offset(count, N, t->vrank) * dts, NULL, ucc_buffer_block_count(count, N, t->vrank), mt, 1));
+    if (is_root) { for (ucc_rank_t r = 0; r < N; r++) if (r != root) CHK(shm_prog_recv(t, r, w + ucc_buffer_block_offset(count, N, r) * dts, ucc_buffer_block_count(count, N, r) * dts, mt, 1 + N)); }
+    else CHK(shm_prog_send(t, root, w + ucc_buffer_block_offset(count, N, t->vrank) * dts, ucc_buffer_block_count(count, N, t->vrank) * dts, mt, 1 + N));
+    CHK(shm_prog_wait(t));
+err:
+    return st;
+}
+ucc_status_t ucc_tl_shm_reduce_dbt(ucc_tl_shm_task_t *t)
+{
+    ucc_coll_args_t *a = ARGS(t);
+    ucc_rank_t root = (ucc_rank_t)a->root, N = t->vsize, vr = (t->vrank + N - root) % N; int is_root = vr == 0;
+    size_t count = is_root ? a->dst.info.count : a->src.info.count, c[2], o[2];
+    ucc_datatype_t dt = is_root ? a->dst.info.datatype : a->src.info.datatype;
+    ucc_memory_type_t mt = is_root ? a->dst.info.mem_type : a->src.info.mem_type;
+    size_t dts = ucc_dt_size(dt);
+    void *work, *scratch; char *w; ucc_dbt_t dbt; ucc_status_t st;
+    if (N < 3 || count < 2) return UCC_ERR_NOT_SUPPORTED;
+    c[0] = count / 2; c[1] = count - c[0]; o[0] = 0; o[1] = c[0];
+    CHK(shm_task_scratch(t, 2 * c[1] * dts, mt, &scratch));
+    if (is_root) { /* root (virtual 0) sits above both trees built over virtual ranks 1..N-1 */
+        ucc_rank_t r1, r2; ucc_dbt_roots(N - 1, &r1, &r2);
+        work = a->dst.info.buffer; w = (char *)work;
+        if (!UCC_IS_INPLACE(*a)) CHK(shm_prog_copy(t, work, a->src.info.buffer, count * dts, mt, a->src.info.mem_type));
+        CHK(shm_prog_recv(t, (r1 + 1 + root) % N, scratch, c[0] * dts, mt, 1));
+        CHK(shm_prog_recv(t, (r2 + 1 + root) % N, OFF(scratch, c[1] * dts), c[1] * dts, mt, 2));
+        CHK(shm_prog_wait(t));
+        CHK(shm_prog_reduce(t, w, w, scratch, c[0], mt, t->op == UCC_OP_AVG));
+        CHK(shm_prog_reduce(t, w + o[1] * dts, w + o[1] * dts, OFF(scratch, c[1] * dts), c[1], mt, t->op == UCC_OP_AVG));
+        return UCC_OK;
+    }
+    CHK(shm_task_scratch(t, count * dts, mt, &work)); w = (char *)work;
+    CHK(shm_prog_copy(t, work, a->src.info.buffer, count * dts, mt, mt));
+    ucc_dbt_init(&dbt, vr - 1, N - 1);
+    for (int k = 0; k < 2; k++) {
+        unsigned nc = 0; ucc_rank_t parent = dbt.parent[k] == UCC_RANK_INVALID ? root : (dbt.parent[k] + 1 + root) % N;
+        for (int ch = 0; ch < 2; ch++) if (dbt.children[k][ch] != UCC_RANK_INVALID) { CHK(shm_prog_recv(t, (dbt.children[k][ch] + 1 + root) % N, OFF(scratch, nc * c[1] * dts), c[k] * dts, mt, 1 + (unsigned)k)); nc++; }
+        CHK(shm_prog_wait(t));
+        for (unsigned i = 0; i < nc; i++) CHK(shm_prog_reduce(t, w + o[k] * dts, w + o[k] * dts, OFF(scratch, i * c[1] * dts), c[k], mt, 0));
+        CHK(shm_prog_send(t, parent, w + o[k] * dts, c[k] * dts, mt, 1 + (unsigned)k)); CHK(shm_prog_wait(t));
+    }
+err:
+    return st;
+}
+
+/* ================================================================== */
+/* reduce_scatter(v)                                                   */
+/* ================================================================== */
+static ucc_status_t prog_rsv_ring(ucc_tl_shm_task_t *t, char *work, void *scratch, const size_t *cnt, const size_t *off, ucc_memory_type_t mt)
+{
+    ucc_rank_t N = t->vsize, r = t->vrank, next = (r + 1) % N, prev = (r + N - 1) % N;
+    size_t dts = ucc_dt_size(t->dt); ucc_status_t st = UCC_OK;
+    for (ucc_rank_t s = 0; s + 1 < N; s++) {
+        ucc_rank_t sb = (r + 2 * N - s - 1) % N, rb = (r + 2 * N - s - 2) % N;
+        CHK(shm_prog_send(t, next, work + off[sb] * dts, cnt[sb] * dts, mt, 1 + s));
+        CHK(shm_prog_recv(t, prev, scratch, cnt[rb] * dts, mt, 1 + s));
+        CHK(shm_prog_wait(t));
+        CHK(shm_prog_reduce(t, work + off[rb] * dts, work + off[rb] * dts, scratch, cnt[rb], mt, 0));
+    }
+err:
+    return st;
+}
+static ucc_status_t reduce_scatter_common(ucc_tl_shm_task_t *t, int is_v)
+{
+    ucc_coll_args_t *a = ARGS(t);
+    ucc_rank_t N = t->vsize, r = t->vrank; int inplace = UCC_IS_INPLACE(*a);
+    ucc_datatype_t dt = is_v ? a->dst.info_v.datatype : a->dst.info.datatype;
+    ucc_memory_type_t mt = is_v ? a->dst.info_v.mem_type : a->dst.info.mem_type;
+    size_t dts = ucc_dt_size(dt), total = 0, maxc = 0, *cnt, *off;
+    void *work, *scratch, *dstbuf = is_v ? a->dst.info_v.buffer : a->dst.info.buffer; ucc_status_t st;
+    cnt = (size_t *)malloc(2 * N * sizeof(size_t)); if (!cnt) return UCC_ERR_NO_MEMORY;
+    off = cnt + N; t->host_copy = cnt;
+    for (ucc_rank_t i = 0; i < N; i++) {
+        if (is_v) cnt[i] = ucc_coll_args_get_count(a, a->dst.info_v.counts, i);
+        else { size_t tot = inplace ? a->dst.info.count : a->dst.info.count * N; cnt[i] = ucc_buffer_block_count(tot, N, i); }
+        off[i] = total; total += cnt[i]; if (cnt[i] > maxc) maxc = cnt[i];
+    }
+    CHK(shm_task_scratch(t, maxc * dts, mt, &scratch));
+    if (inplace) work = dstbuf;
+    else { CHK(shm_task_scratch(t, total * dts, mt, &work)); CHK(shm_prog_copy(t, work, a->src.info.buffer, total * dts, mt, a->src.info.mem_type)); }
+    CHK(prog_rsv_ring(t, (char *)work, scratch, cnt, off, mt));
+    if (t->op == UCC_OP_AVG) CHK(shm_prog_reduce(t, OFF(work, off[r] * dts), OFF(work, off[r] * dts), NULL, cnt[r], mt, 1));
+    if (!inplace) CHK(shm_prog_copy(t, dstbuf, OFF(work, off[r] * dts), cnt[r] * dts, mt, mt));
+err:
+    return st;
+}
+ucc_status_t ucc_tl_shm_reduce_scatter_ring(ucc_tl_shm_task_t *t) { return reduce_scatter_common(t, 0); }
+ucc_status_t ucc_tl_shm_reduce_scatterv_ring(ucc_tl_shm_task_t *t) { return reduce_scatter_common(t, 1); }
+/* recursive halving (power-of-two teams): log2(N) steps, each exchanging half of the remaining range */
+ucc_status_t ucc_tl_shm_reduce_scatter_knomial(ucc_tl_shm_task_t *t)
+{
+    ucc_coll_args_t *a = ARGS(t);
+    ucc_rank_t N = t->vsize, r = t->vrank, lo = 0, hi = N; int inplace = UCC_IS_INPLACE(*a);
+    ucc_memory_type_t mt = a->dst.info.mem_type;
+    size_t dts = ucc_dt_size(a->dst.info.datatype), total = inplace ? a->dst.info.count : a->dst.info.count * N;
+    void *work, *scratch; char *w; ucc_status_t st; unsigned step = 1;
+    if (!ucc_is_pow2(N)) return UCC_ERR_NOT_SUPPORTED;
+    CHK(shm_task_scratch(t, (total / 2 + N) * dts, mt, &scratch));
+    if (inplace) work = a->dst.info.buffer;
+    else { CHK(shm_task_scratch(t, total * dts, mt, &work)); CHK(shm_prog_copy(t, work, a->src.info.buffer, total * dts, mt, a->src.info.mem_type)); }
+    w = (char *)work;
+    while (hi - lo > 1) { /* block range [lo,hi) is what this rank is still responsible for */
+        ucc_rank_t mid = (lo + hi) / 2, peer, klo, khi, slo, shi;
+        if (r < mid) { peer = r + (mid - lo); klo = lo; khi = mid; slo = mid; shi = hi; } else { peer = r - (mid - lo); klo = mid; khi = hi; slo = lo; shi = mid; }
+        size_t ko = ucc_buffer_block_offset(total, N, klo), kc = ucc_buffer_block_offset(total, N, khi - 1) + ucc_buffer_block_count(total, N, khi - 1) - ko;
+        size_t so = ucc_buffer_block_offset(total, N, slo), sc = ucc_buffer_block_offset(total, N, shi - 1) + ucc_buffer_block_count(total, N, shi - 1) - so;
+        CHK(shm_prog_send(t, peer, w + so * dts, sc * dts, mt, step)); CHK(shm_prog_recv(t, peer, scratch, kc * dts, mt, step)); CHK(shm_prog_wait(t));
+        CHK(shm_prog_reduce(t, w + ko * dts, w + ko * dts, scratch, kc, mt, 0));
+        lo = klo; hi = khi; step++;
+    }
+    { size_t o = ucc_buffer_block_offset(total, N, r), c = ucc_buffer_block_count(total, N, r);
+      if (t->op == UCC_OP_AVG) CHK(shm_prog_reduce(t, w + o * dts, w + o * dts, NULL, c, mt, 1));
+      if (!inplace) CHK(shm_prog_copy(t, a->dst.info.buffer, w + o * dts, c * dts, mt, mt)); }
+err:
+    return st;
+}
+
+/* ================================================================== */
+/* allgather(v)                                                        */
+/* ================================================================== */
+static ucc_status_t ag_layout(ucc_tl_shm_task_t *t, int is_v, size_t **cnt_p, size_t **off_p, size_t *dts, ucc_memory_type_t *mt, char **dst)
+{
+    ucc_coll_args_t *a = ARGS(t); ucc_rank_t N = t->vsize;
+    size_t *cnt = (size_t *)malloc(2 * N * sizeof(size_t)), *off;
+    if (!cnt) return UCC_ERR_NO_MEMORY;
+    off = cnt + N; t->host_copy = cnt;
+    if (is_v) {
+        *dts = ucc_dt_size(a->dst.info_v.datatype); *mt = a->dst.info_v.mem_type; *dst = (char *)a->dst.info_v.buffer;
+        for (ucc_rank_t i = 0; i < N; i++) { cnt[i] = ucc_coll_args_get_count(a, a->dst.info_v.counts, i) * *dts; off[i] = ucc_coll_args_get_displacement(a, a->dst.info_v.displacements, i) * *dts; }
+    } else {
+        size_t blk = (a->dst.info.count / N) * ucc_dt_size(a->dst.info.datatype);
+        *dts = ucc_dt_size(a->dst.info.datatype); *mt = a->dst.info.mem_type; *dst = (char *)a->dst.info.buffer;
+        for (ucc_rank_t i = 0; i < N; i++) { cnt[i] = blk; off[i] = i * blk; }
+    }
+    *cnt_p = cnt; *off_p = off;
+    return UCC_OK;
+}
+static ucc_status_t ag_own_block(ucc_tl_shm_task_t *t, char *dst, const size_t *cnt, const size_t *off, ucc_memory_type_t mt)
+{
+    ucc_coll_args_t *a = ARGS(t);
+    if (UCC_IS_INPLACE(*a)) return UCC_OK;
+    return shm_prog_copy(t, dst + off[t->vrank], a->src.info.buffer, cnt[t->vrank], mt, a->src.info.mem_type);
+}
+static ucc_status_t allgather_ring_common(ucc_tl_shm_task_t *t, int is_v)
+{
+    size_t *cnt, *off, dts; ucc_memory_type_t mt; char *dst; ucc_status_t st;
+    ucc_rank_t N = t->vsize, r = t->vrank, next = (r + 1) % N, prev = (r + N - 1) % N;
+    CHK(ag_layout(t, is_v, &cnt, &off, &dts, &mt, &dst));
+    CHK(ag_own_block(t, dst, cnt, off, mt));
+    for (ucc_rank_t s = 0; s + 1 < N; s++) {
+        ucc_rank_t sb = (r + N - s) % N, rb = (r + N - s - 1) % N;
+        CHK(shm_prog_send(t, next, dst + off[sb], cnt[sb], mt, 1 + s)); CHK(shm_prog_recv(t, prev, dst + off[rb], cnt[rb], mt, 1 + s)); CHK(shm_prog_wait(t));
+    }
+err:
+    return st;
+}
+ucc_status_t ucc_tl_shm_allgather_ring(ucc_tl_shm_task_t *t) { return allgather_ring_common(t, 0); }
+ucc_status_t ucc_tl_shm_allgatherv_ring(ucc_tl_shm_task_t *t) { return allgather_ring_common(t, 1); }
+static ucc_status_t allgather_linear_common(ucc_tl_shm_task_t *t, int is_v, unsigned batch)
+{
+    size_t *cnt, *off, dts; ucc_memory_type_t mt; char *dst; ucc_status_t st; ucc_rank_t N = t->vsize, r = t->vrank;
+    CHK(ag_layout(t, is_v, &cnt, &off, &dts, &mt, &dst));
+    CHK(ag_own_block(t, dst, cnt, off, mt));
+    for (ucc_rank_t s = 1; s < N; s++) {
+        ucc_rank_t to = (r + s) % N, from = (r + N - s) % N;
+        CHK(shm_prog_recv(t, from, dst + off[from], cnt[from], mt, 1)); CHK(shm_prog_send(t, to, dst + off[r], cnt[r], mt, 1));
+        if (batch && s % batch == 0) CHK(shm_prog_wait(t));
+    }
+    CHK(shm_prog_wait(t));
+err:
+    return st;
+}
+ucc_status_t ucc_tl_shm_allgather_linear(ucc_tl_shm_task_t *t) { return allgather_linear_common(t, 0, 0); }
+ucc_status_t ucc_tl_shm_allgather_batched(ucc_tl_shm_task_t *t) { return allgather_linear_common(t, 0, 4); }
+ucc_status_t ucc_tl_shm_allgatherv_linear(ucc_tl_shm_task_t *t) { return allgather_linear_common(t, 1, 0); }
+/* neighbor exchange (even team sizes): N/2 steps, pairs alternate left/right */
+ucc_status_t ucc_tl_shm_allgather_neighbor(ucc_tl_shm_task_t *t)
+{
+    size_t *cnt, *off, dts; ucc_memory_type_t mt; char *dst; ucc_status_t st; ucc_rank_t N = t->vsize, r = t->vrank;
+    ucc_rank_t nb[2], rdf[2]; int od[2];
+    if (N % 2) return UCC_ERR_NOT_SUPPORTED;
+    CHK(ag_layout(t, 0, &cnt, &off, &dts, &mt, &dst));
+    CHK(ag_own_block(t, dst, cnt, off, mt));
+    if (r % 2 == 0) { nb[0] = (r + 1) % N; nb[1] = (r + N - 1) % N; rdf[0] = r; rdf[1] = r; od[0] = 2; od[1] = -2; }
+    else { nb[0] = (r + N - 1) % N; nb[1] = (r + 1) % N; rdf[0] = nb[0]; rdf[1] = nb[0]; od[0] = -2; od[1] = 2; }
+    /* step 0: exchange own block with neighbor 0 */
+    CHK(shm_prog_send(t, nb[0], dst + off[r], cnt[r], mt, 1)); CHK(shm_prog_recv(t, nb[0], dst + off[nb[0]], cnt[nb[0]], mt, 1)); CHK(shm_prog_wait(t));
+    { ucc_rank_t send_from = r % 2 == 0 ? r : nb[0]; /* lower index of the pair just completed */
+      for (ucc_rank_t i = 1; i < N / 2; i++) {
+        int p = (int)(i % 2);
+        ucc_rank_t recv_from = (rdf[p] + (ucc_rank_t)((int)N + od[p])) % N;
+        rdf[p] = recv_from;
+        /* blocks are exchanged in pairs (send_from, send_from+1) */
+        CHK(shm_prog_send(t, nb[p], dst + off[send_from], cnt[send_from] + cnt[(send_from + 1) % N], mt, 1 + i));
+        CHK(shm_prog_recv(t, nb[p], dst + off[recv_from], cnt[recv_from] + cnt[(recv_from + 1) % N], mt, 1 + i));
+        CHK(shm_prog_wait(t));
+        send_from = recv_from;
+      } }
+err:
+    return st;
+}
+/* Bruck: ceil(log2 N) steps through a rotated scratch copy */
+ucc_status_t ucc_tl_shm_allgather_bruck(ucc_tl_shm_task_t *t)
+{
+    size_t *cnt, *off, dts, blk; ucc_memory_type_t mt; char *dst; ucc_status_t st; ucc_rank_t N = t->vsize, r = t->vrank;
+    void *scr; char *s; unsigned step = 1; ucc_coll_args_t *a = ARGS(t);
+    CHK(ag_layout(t, 0, &cnt, &off, &dts, &mt, &dst)); blk = cnt[0];
+    CHK(shm_task_scratch(t, blk * N, mt, &scr)); s = (char *)scr;
+    CHK(shm_prog_copy(t, s, UCC_IS_INPLACE(*a) ? (void *)(dst + off[r]) : a->src.info.buffer, blk, mt, UCC_IS_INPLACE(*a) ? mt : a->src.info.mem_type));
+    for (ucc_rank_t d = 1; d < N; d *= 2, step++) {
+        ucc_rank_t nblk = (2 * d <= N) ? d : N - d, to = (r + N - d) % N, from = (r + d) % N;
+        CHK(shm_prog_send(t, to, s, nblk * blk, mt, step)); CHK(shm_prog_recv(t, from, s + d * blk, nblk * blk, mt, step)); CHK(shm_prog_wait(t));
+    }
+    /* scratch block i holds data of rank (r+i)%N */
+    CHK(shm_prog_copy(t, dst + (size_t)r * blk, s, (N - r) * blk, mt, mt));
+    if (r) CHK(shm_prog_copy(t, dst, s + (size_t)(N - r) * blk, (size_t)r * blk, mt, mt));
+err:
+    return st;
+}
+/* knomial (recursive doubling over blocks; power-of-two only, others fall back) */
+ucc_status_t ucc_tl_shm_allgather_knomial(ucc_tl_shm_task_t *t)
+{
+    size_t *cnt, *off, dts, blk; ucc_memory_type_t mt; char *dst; ucc_status_t st; ucc_rank_t N = t->vsize, r = t->vrank; unsigned step = 1;
+    if (!ucc_is_pow2(N)) return UCC_ERR_NOT_SUPPORTED;
+    CHK(ag_layout(t, 0, &cnt, &off, &dts, &mt, &dst)); blk = cnt[0];
+    CHK(ag_own_block(t, dst, cnt, off, mt));
+    for (ucc_rank_t d = 1; d < N; d *= 2, step++) {
+        ucc_rank_t peer = r ^ d, peerbase = (peer / d) * d;
+        CHK(shm_prog_send(t, peer, dst + (size_t)((r / d) * d) * blk, (size_t)d * blk, mt, step));
+        CHK(shm_prog_recv(t, peer, dst + (size_t)peerbase * blk, (size_t)d * blk, mt, step));
+        CHK(shm_prog_wait(t));
+    }
+err:
+    return st;
+}
+/* sparbit: log steps with distances N/2, N/4.. ; data locality friendly — same data motion as bruck without rotation for pow2 */
+ucc_status_t ucc_tl_shm_allgather_sparbit(ucc_tl_shm_task_t *t)
+{
+    size_t *cnt, *off, dts, blk; ucc_memory_type_t mt; char *dst; ucc_status_t st; ucc_rank_t N = t->vsize, r = t->vrank; unsigned step = 1;
+    if (!ucc_is_pow2(N)) return UCC_ERR_NOT_SUPPORTED;
+    CHK(ag_layout(t, 0, &cnt, &off, &dts, &mt, &dst)); blk = cnt[0];
+    CHK(ag_own_block(t, dst, cnt, off, mt));
+    /* step k (distance d = N>>(k+1)): send every block b owned so far (b = r + j*2d) to r+d, receive from r-d */
+    for (ucc_rank_t d = N / 2; d >= 1; d /= 2, step++) {
+        ucc_rank_t to = (r + d) % N, from = (r + N - d) % N, stride = 2 * d;
+        for (ucc_rank_t j = 0; j < N / stride; j++) {
+            ucc_rank_t sb = (r + N - j * stride) % N, rb = (from + N - j * stride) % N;
+            CHK(shm_prog_send(t, to, dst + (size_t)sb * blk, blk, mt, step * 64 + j)); CHK(shm_prog_recv(t, from, dst + (size_t)rb * blk, blk, mt, step * 64 + j));
+        }
+        CHK(shm_prog_wait(t));
+        if (d == 1) break;
+    }
+err:
+    return st;
+}
+ucc_status_t ucc_tl_shm_allgatherv_knomial(ucc_tl_shm_task_t *t) { return allgather_linear_common(t, 1, 0); }
+
+/* ================================================================== */
+/* alltoall(v)                                                         */
+/* ================================================================== */
+static ucc_status_t a2a_common(ucc_tl_shm_task_t *t, int is_v)
+{
+    ucc_coll_args_t *a = ARGS(t); ucc_rank_t N = t->vsize, r = t->vrank; int inplace = UCC_IS_INPLACE(*a);
+    unsigned nposts = SHM_CTX(t->team)->cfg.alltoall_pairwise_num_posts;
+    size_t sdt, ddt; ucc_memory_type_t smt, dmt; char *src, *dst; ucc_status_t st = UCC_OK;
+    if (is_v) { sdt = ucc_dt_size(a->src.info_v.datatype); ddt = ucc_dt_size(a->dst.info_v.datatype); smt = a->src.info_v.mem_type; dmt = a->dst.info_v.mem_type; src = (char *)a->src.info_v.buffer; dst = (char *)a->dst.info_v.buffer; }
+    else { sdt = ucc_dt_size(a->src.info.datatype); ddt = ucc_dt_size(a->dst.info.datatype); smt = a->src.info.mem_type; dmt = a->dst.info.mem_type; src = (char *)a->src.info.buffer; dst = (char *)a->dst.info.buffer; }
+    if (inplace) { /* stage the whole send side: every block is overwritten by an incoming one */
+        size_t tot; void *tmp;
+        if (is_v) { tot = 0; for (ucc_rank_t i = 0; i < N; i++) { size_t e = (ucc_coll_args_get_displacement(a, a->dst.info_v.displacements, i) + ucc_coll_args_get_count(a, a->dst.info_v.counts, i)) * ddt; if (e > tot) tot = e; } }
+        else tot = a->dst.info.count * ddt;
+        CHK(shm_task_scratch(t, tot, dmt, &tmp)); CHK(shm_prog_copy(t, tmp, dst, tot, dmt, dmt));
+        src = (char *)tmp; sdt = ddt; smt = dmt;
+    }
+#define SCNT(_i) (is_v ? ucc_coll_args_get_count(a, inplace ? a->dst.info_v.counts : a->src.info_v.counts, _i) * sdt : (inplace ? a->dst.info.count : a->src.info.count) / N * sdt)
+#define SOFF(_i) (is_v ? ucc_coll_args_get_displacement(a, inplace ? a->dst.info_v.displacements : a->src.info_v.displacements, _i) * sdt : (size_t)(_i) * ((inplace ? a->dst.info.count : a->src.info.count) / N * sdt))
+#define DCNT(_i) (is_v ? ucc_coll_args_get_count(a, a->dst.info_v.counts, _i) * ddt : a->dst.info.count / N * ddt)
+#define DOFF(_i) (is_v ? ucc_coll_args_get_displacement(a, a->dst.info_v.displacements, _i) * ddt : (size_t)(_i) * (a->dst.info.count / N * ddt))
+    CHK(shm_prog_copy(t, dst + DOFF(r), src + SOFF(r), ucc_min(SCNT(r), DCNT(r)), dmt, smt));
+    for (ucc_rank_t s = 1; s < N; s++) {
+        ucc_rank_t to = (r + s) % N, from = (r + N - s) % N;
+        CHK(shm_prog_recv(t, from, dst + DOFF(from), DCNT(from), dmt, 1)); CHK(shm_prog_send(t, to, src + SOFF(to), SCNT(to), smt, 1));
+        if (nposts && nposts != UCC_UUNITS_AUTO && s % nposts == 0) CHK(shm_prog_wait(t));
+    }
+    CHK(shm_prog_wait(t));
+err:
+    return st;
+}
+ucc_status_t ucc_tl_shm_alltoall_pairwise(ucc_tl_shm_task_t *t) { return a2a_common(t, 0); }
+ucc_status_t ucc_tl_shm_alltoallv_pairwise(ucc_tl_shm_task_t *t) { return a2a_common(t, 1); }
+/* Bruck alltoall: log2(N) rounds, each moving the blocks whose index has bit k set (latency optimal for small blocks) */
+ucc_status_t ucc_tl_shm_alltoall_bruck(ucc_tl_shm_task_t *t)
+{
+    ucc_coll_args_t *a = ARGS(t); ucc_rank_t N = t->vsize, r = t->vrank; int inplace = UCC_IS_INPLACE(*a);
+    size_t blk = a->dst.info.count / N * ucc_dt_size(a->dst.info.datatype);
+    ucc_memory_type_t mt = a->dst.info.mem_type; char *dst = (char *)a->dst.info.buffer, *src = inplace ? dst : (char *)a->src.info.buffer;
+    void *wv, *pv; char *w, *pk; ucc_status_t st; unsigned step = 1;
+    if (!inplace && a->src.info.mem_type != mt) return UCC_ERR_NOT_SUPPORTED;
+    CHK(shm_task_scratch(t, blk * N, mt, &wv)); CHK(shm_task_scratch(t, blk * N, mt, &pv)); w = (char *)wv; pk = (char *)pv;
+    /* phase 1: local rotation, w[i] = src[(r+i)%N] */
+    CHK(shm_prog_copy(t, w, src + (size_t)r * blk, (N - r) * blk, mt, mt)); if (r) CHK(shm_prog_copy(t, w + (size_t)(N - r) * blk, src, (size_t)r * blk, mt, mt));
+    for (ucc_rank_t d = 1; d < N; d *= 2, step++) {
+        ucc_rank_t to = (r + d) % N, from = (r + N - d) % N, n = 0;
+        for (ucc_rank_t i = 0; i < N; i++) if (i & d) { CHK(shm_prog_copy(t, pk + (size_t)n * blk, w + (size_t)i * blk, blk, mt, mt)); n++; }
+        CHK(shm_prog_send(t, to, pk, (size_t)n * blk, mt, step)); CHK(shm_prog_recv(t, from, pk + (size_t)n * blk, (size_t)n * blk, mt, step)); CHK(shm_prog_wait(t));
+        n = 0; { ucc_rank_t cntb = 0; for (ucc_rank_t i = 0; i < N; i++) if (i & d) cntb++; for (ucc_rank_t i = 0; i < N; i++) if (i & d) { CHK(shm_prog_copy(t, w + (size_t)i * blk, pk + (size_t)(cntb + n) * blk, blk, mt, mt)); n++; } }
+    }
+    /* phase 3: inverse rotation, dst[(r - i + N) % N] = w[i] */
+    for (ucc_rank_t i = 0; i < N; i++) CHK(shm_prog_copy(t, dst + (size_t)((r + N - i) % N) * blk, w + (size_t)i * blk, blk, mt, mt));
+err:
+    return st;
+}
+
+/* ================================================================== */
+/* gather(v) / scatter(v)                                              */
+/* ================================================================== */
+ucc_status_t ucc_tl_shm_gather_linear(ucc_tl_shm_task_t *t)
+{
+    ucc_coll_args_t *a = ARGS(t); ucc_rank_t N = t->vsize, r = t->vrank, root = (ucc_rank_t)a->root; ucc_status_t st = UCC_OK;
+    if (r == root) {
+        size_t blk = a->dst.info.count / N * ucc_dt_size(a->dst.info.datatype); char *dst = (char *)a->dst.info.buffer;
+        if (!UCC_IS_INPLACE(*a)) CHK(shm_prog_copy(t, dst + (size_t)r * blk, a->src.info.buffer, blk, a->dst.info.mem_type, a->src.info.mem_type));
+        for (ucc_rank_t i = 0; i < N; i++) if (i != root) CHK(shm_prog_recv(t, i, dst + (size_t)i * blk, blk, a->dst.info.mem_type, 1));
+    } else CHK(shm_prog_send(t, root, a->src.info.buffer, a->src.info.count * ucc_dt_size(a->src.info.datatype), a->src.info.mem_type, 1));
+    CHK(shm_prog_wait(t));
+err:
+    return st;
+}
+/* knomial gather: subtrees are forwarded as contiguous ranges of virtual ranks through a scratch */
+ucc_status_t ucc_tl_shm_gather_knomial(ucc_tl_shm_task_t *t)
+{
+    ucc_coll_args_t *a = ARGS(t); ucc_rank_t N = t->vsize, r = t->vrank, root = (ucc_rank_t)a->root, vr = (r + N - root) % N;
+    int is_root = r == root; ucc_kn_tree_t tr; ucc_status_t st = UCC_OK;
+    size_t blk = is_root ? a->dst.info.count / N * ucc_dt_size(a->dst.info.datatype) : a->src.info.count * ucc_dt_size(a->src.info.datatype);
+    ucc_memory_type_t mt = is_root ? a->dst.info.mem_type : a->src.info.mem_type;
+    unsigned radix = cfg_radix(&SHM_CTX(t->team)->cfg.gather_kn_radix, blk * N, mt, 4, N);
+    ucc_rank_t span = ucc_kn_subtree_size(vr, N, radix);
+    void *sv; char *s;
+    ucc_kn_tree_init(&tr, r, N, root, radix);
+    /* scratch holds virtual ranks [vr, vr+span) */
+    CHK(shm_task_scratch(t, (size_t)span * blk, mt, &sv)); s = (char *)sv;
+    CHK(shm_prog_copy(t, s, (is_root && UCC_IS_INPLACE(*a)) ? (void *)((char *)a->dst.info.buffer + (size_t)r * blk) : a->src.info.buffer, blk, mt,
+                      (is_root && UCC_IS_INPLACE(*a)) ? mt : a->src.info.mem_type));
+    for (unsigned i = 0; i < tr.n_children; i++) {
+        ucc_rank_t cvr = (tr.children[i] + N - root) % N, cspan = ucc_kn_subtree_size(cvr, N, radix);
+        CHK(shm_prog_recv(t, tr.children[i], s + (size_t)(cvr - vr) * blk, (size_t)cspan * blk, mt, 1));
+    }
+    CHK(shm_prog_wait(t));
+    if (!is_root) { CHK(shm_prog_send(t, tr.parent, s, (size_t)span * blk, mt, 1)); CHK(shm_prog_wait(t)); }
+    else { /* un-rotate virtual ranks into team ranks */
+        char *dst = (char *)a->dst.info.buffer;
+        CHK(shm_prog_copy(t, dst + (size_t)root * blk, s, (size_t)(N - root) * blk, mt, mt));
+        if (root) CHK(shm_prog_copy(t, dst, s + (size_t)(N - root) * blk, (size_t)root * blk, mt, mt));
+    }
+err:
+    return st;
+}
+ucc_status_t ucc_tl_shm_gatherv_linear(ucc_tl_shm_task_t *t)
+{
+    ucc_coll_args_t *a = ARGS(t); ucc_rank_t N = t->vsize, r = t->vrank, root = (ucc_rank_t)a->root; ucc_status_t st = UCC_OK;
+    if (r == root) {
+        size_t dts = ucc_dt_size(a->dst.info_v.datatype); char *dst = (char *)a->dst.info_v.buffer;
+        for (ucc_rank_t i = 0; i < N; i++) {
+            size_t c = ucc_coll_args_get_count(a, a->dst.info_v.counts, i) * dts, o = ucc_coll_args_get_displacement(a, a->dst.info_v.displacements, i) * dts;
+            if (i == root) { if (!UCC_IS_INPLACE(*a)) CHK(shm_prog_copy(t, dst + o, a->src.info.buffer, c, a->dst.info_v.mem_type, a->src.info.mem_type)); }
+            else CHK(shm_prog_recv(t, i, dst + o, c, a->dst.info_v.mem_type, 1));
+        }
+    } else CHK(shm_prog_send(t, root, a->src.info.buffer, a->src.info.count * ucc_dt_size(a->src.info.datatype), a->src.info.mem_type, 1));
+    CHK(shm_prog_wait(t));
+err:
+    return st;
+}
+ucc_status_t ucc_tl_shm_scatter_linear(ucc_tl_shm_task_t *t)
+{
+    ucc_coll_args_t *a = ARGS(t); ucc_rank_t N = t->vsize, r = t->vrank, root = (ucc_rank_t)a->root; ucc_status_t st = UCC_OK;
+    if (r == root) {
+        size_t blk = a->src.info.count / N * ucc_dt_size(a->src.info.datatype); char *src = (char *)a->src.info.buffer;
+        for (ucc_rank_t i = 0; i < N; i++) if (i != root) CHK(shm_prog_send(t, i, src + (size_t)i * blk, blk, a->src.info.mem_type, 1));
+        if (!UCC_IS_INPLACE(*a)) CHK(shm_prog_copy(t, a->dst.info.buffer, src + (size_t)r * blk, blk, a->dst.info.mem_type, a->src.info.mem_type));
+    } else CHK(shm_prog_recv(t, root, a->dst.info.buffer, a->dst.info.count * ucc_dt_size(a->dst.info.datatype), a->dst.info.mem_type, 1));
+    CHK(shm_prog_wait(t));
+err:
+    return st;
+}
+ucc_status_t ucc_tl_shm_scatter_knomial(ucc_tl_shm_task_t *t)
+{
+    ucc_coll_args_t *a = ARGS(t); ucc_rank_t N = t->vsize, r = t->vrank, root = (ucc_rank_t)a->root, vr = (r + N - root) % N;
+    int is_root = r == root; ucc_kn_tree_t tr; ucc_status_t st = UCC_OK;
+    size_t blk = is_root ? a->src.info.count / N * ucc_dt_size(a->src.info.datatype) : a->dst.info.count * ucc_dt_size(a->dst.info.datatype);
+    ucc_memory_type_t mt = is_root ? a->src.info.mem_type : a->dst.info.mem_type;
+    unsigned radix = cfg_radix(&SHM_CTX(t->team)->cfg.gather_kn_radix, blk * N, mt, 4, N);
+    ucc_rank_t span = ucc_kn_subtree_size(vr, N, radix);
+    void *sv; char *s;
+    ucc_kn_tree_init(&tr, r, N, root, radix);
+    CHK(shm_task_scratch(t, (size_t)span * blk, mt, &sv)); s = (char *)sv;
+    if (is_root) { /* rotate into virtual rank order */
+        char *src = (char *)a->src.info.buffer;
+        CHK(shm_prog_copy(t, s, src + (size_t)root * blk, (size_t)(N - root) * blk, mt, mt));
+        if (root) CHK(shm_prog_copy(t, s + (size_t)(N - root) * blk, src, (size_t)root * blk, mt, mt));
+    } else { CHK(shm_prog_recv(t, tr.parent, s, (size_t)span * blk, mt, 1)); CHK(shm_prog_wait(t)); }
+    for (unsigned i = 0; i < tr.n_children; i++) {
+        ucc_rank_t cvr = (tr.children[i] + N - root) % N, cspan = ucc_kn_subtree_size(cvr, N, radix);
+        CHK(shm_prog_send(t, tr.children[i], s + (size_t)(cvr - vr) * blk, (size_t)cspan * blk, mt, 1));
+    }
+    if (!(is_root && UCC_IS_INPLACE(*a))) CHK(shm_prog_copy(t, a->dst.info.buffer, s, blk, is_root ? a->dst.info.mem_type : mt, mt));
+    CHK(shm_prog_wait(t));
+err:
+    return st;
+}
+ucc_status_t ucc_tl_shm_scatterv_linear(ucc_tl_shm_task_t *t)
+{
+    ucc_coll_args_t *a = ARGS(t); ucc_rank_t N = t->vsize, r = t->vrank, root = (ucc_rank_t)a->root; ucc_status_t st = UCC_OK;
+    if (r == root) {
+        size_t dts = ucc_dt_size(a->src.info_v.datatype); char *src = (char *)a->src.info_v.buffer;
+        for (ucc_rank_t i = 0; i < N; i++) {
+            size_t c = ucc_coll_args_get_count(a, a->src.info_v.counts, i) * dts, o = ucc_coll_args_get_displacement(a, a->src.info_v.displacements, i) * dts;
+            if (i == root) { if (!UCC_IS_INPLACE(*a)) CHK(shm_prog_copy(t, a->dst.info.buffer, src + o, c, a->dst.info.mem_type, a->src.info_v.mem_type)); }
+            else CHK(shm_prog_send(t, i, src + o, c, a->src.info_v.mem_type, 1));
+        }
+    } else CHK(shm_prog_recv(t, root, a->dst.info.buffer, a->dst.info.count * ucc_dt_size(a->dst.info.datatype), a->dst.info.mem_type, 1));
+    CHK(shm_prog_wait(t));
+err:
+    return st;
+}
+
+/* ================================================================== */
+/* service collectives (any subset of the team)                        */
+/* ================================================================== */
+ucc_status_t ucc_tl_shm_service_allreduce_prog(ucc_tl_shm_task_t *t, void *sbuf, void *rbuf, size_t count)
+{
+    size_t len = count * ucc_dt_size(t->dt); void *scratch; ucc_status_t st;
+    unsigned radix = t->vsize < 4 ? 2 : 4;
+    CHK(shm_task_scratch(t, (size_t)(radix - 1) * len, UCC_MEMORY_TYPE_HOST, &scratch));
+    if (sbuf != rbuf) CHK(shm_prog_copy(t, rbuf, sbuf, len, UCC_MEMORY_TYPE_HOST, UCC_MEMORY_TYPE_HOST));
+    CHK(prog_allreduce_knomial(t, rbuf, scratch, count, UCC_MEMORY_TYPE_HOST, radix, 1));
+err:
+    return st;
+}
+ucc_status_t ucc_tl_shm_service_allgather_prog(ucc_tl_shm_task_t *t, void *sbuf, void *rbuf, size_t msgsize)
+{
+    ucc_rank_t N = t->vsize, r = t->vrank; char *dst = (char *)rbuf; ucc_status_t st;
+    CHK(shm_prog_copy(t, dst + (size_t)r * msgsize, sbuf, msgsize, UCC_MEMORY_TYPE_HOST, UCC_MEMORY_TYPE_HOST));
+    CHK(shm_prog_wait(t));
+    if (N <= 8 || msgsize <= 4096) { /* linear: one round */
+        for (ucc_rank_t s = 1; s < N; s++) {
+            ucc_rank_t to = (r + s) % N, from = (r + N - s) % N;
+            CHK(shm_prog_recv(t, from, dst + (size_t)from * msgsize, msgsize, UCC_MEMORY_TYPE_HOST, 1));
+            CHK(shm_prog_send(t, to, sbuf, msgsize, UCC_MEMORY_TYPE_HOST, 1));
+        }
+        CHK(shm_prog_wait(t));
+    } else {
+        ucc_rank_t next = (r + 1) % N, prev = (r + N - 1) % N;
+        for (ucc_rank_t s = 0; s + 1 < N; s++) {
+            ucc_rank_t sb = (r + N - s) % N, rb = (r + N - s - 1) % N;
+            CHK(shm_prog_send(t, next, dst + (size_t)sb * msgsize, msgsize, UCC_MEMORY_TYPE_HOST, 1 + s));
+            CHK(shm_prog_recv(t, prev, dst + (size_t)rb * msgsize, msgsize, UCC_MEMORY_TYPE_HOST, 1 + s));
+            CHK(shm_prog_wait(t));
+        }
+    }
+err:
+    return st;
+}

@@ -1,0 +1,180 @@
+#include "ucc_schedule_pipelined.h"
+#include "utils/ucc_log.h"
+
+static ucc_status_t launch_frag(ucc_schedule_pipelined_t *sp, int slot, int global)
+{
+    ucc_schedule_t *f = sp->frags[slot];
+    ucc_status_t    st;
+    int             pslot = (slot - 1 + sp->n_frags) % sp->n_frags;
+    if (sp->frag_setup) { st = sp->frag_setup(sp, f, global); if (st != UCC_OK) return st; }
+    sp->slot_global[slot] = global;
+    f->n_completed_tasks  = 0;
+    f->super.status = UCC_INPROGRESS; f->super.super.status = UCC_INPROGRESS;
+    f->super.start_time = sp->super.super.start_time; f->super.timeout = sp->super.super.timeout;
+    for (unsigned j = 0; j < f->n_tasks; j++) {
+        ucc_coll_task_t *t = f->tasks[j];
+        int xdep = (global > 0 && sp->order != UCC_PIPELINE_PARALLEL && sp->n_frags > 1);
+        sp->fired[slot][j] = 0;
+        t->super.status = UCC_OPERATION_INITIALIZED; t->status = UCC_OPERATION_INITIALIZED;
+        t->n_deps = t->n_deps_base + (xdep ? 1 : 0);
+        t->n_deps_satisfied = 0;
+        t->generation++;
+        if (xdep) {
+            /* predecessor = task j of global-1: already fired if its slot moved on, or fired in its current run */
+            int pg = sp->slot_global[pslot];
+            if (pg > global - 1 || pg < 0 || (pg == global - 1 && sp->fired[pslot][j])) t->n_deps_satisfied = 1;
+        } else if (global > 0 && sp->order != UCC_PIPELINE_PARALLEL && sp->n_frags == 1) {
+            /* single slot: strictly sequential by construction */
+        }
+        t->timeout = f->super.timeout; t->start_time = f->super.start_time;
+    }
+    if (f->n_tasks == 0) { f->super.status = UCC_OK; return ucc_task_complete(&f->super) >= 0 ? UCC_OK : f->super.status; }
+    return ucc_event_manager_notify(&f->super, UCC_EVENT_SCHEDULE_STARTED);
+}
+
+static void find_task(ucc_schedule_pipelined_t *sp, ucc_coll_task_t *t, int *slot, int *j)
+{
+    for (int s = 0; s < sp->n_frags; s++)
+        for (unsigned k = 0; k < sp->frags[s]->n_tasks; k++)
+            if (sp->frags[s]->tasks[k] == t) { *slot = s; *j = (int)k; return; }
+    *slot = -1; *j = -1;
+}
+
+/* record that (slot ps, task pj) emitted its ordering event and wake the matching task of the
+ * next fragment if that fragment is armed and waiting for exactly this predecessor */
+static ucc_status_t fire(ucc_schedule_pipelined_t *sp, int ps, int pj)
+{
+    int ss = (ps + 1) % sp->n_frags;
+    if (sp->fired[ps][pj]) return UCC_OK;
+    sp->fired[ps][pj] = 1;
+    if (sp->slot_global[ss] >= 0 && sp->slot_global[ss] == sp->slot_global[ps] + 1 && (unsigned)pj < sp->frags[ss]->n_tasks) {
+        ucc_coll_task_t *succ = sp->frags[ss]->tasks[pj];
+        if (succ->super.status == UCC_OPERATION_INITIALIZED) return ucc_dependency_handler(sp->frags[ps]->tasks[pj], succ);
+    }
+    return UCC_OK;
+}
+
+static ucc_status_t cross_frag_handler(ucc_coll_task_t *parent, ucc_coll_task_t *task)
+{
+    ucc_schedule_pipelined_t *sp = ucc_derived_of(parent->schedule->super.schedule, ucc_schedule_pipelined_t);
+    int ps, pj;
+    ucc_status_t st = UCC_OK;
+    (void)task;
+    ucc_recursive_spin_lock(&sp->lock);
+    find_task(sp, parent, &ps, &pj);
+    if (ps >= 0 && sp->slot_global[ps] >= 0) st = fire(sp, ps, pj);
+    ucc_recursive_spin_unlock(&sp->lock);
+    return st;
+}
+
+static ucc_status_t frag_completed_handler(ucc_coll_task_t *parent, ucc_coll_task_t *task)
+{
+    ucc_schedule_pipelined_t *sp   = ucc_derived_of(task, ucc_schedule_pipelined_t);
+    ucc_schedule_t           *frag = ucc_derived_of(parent, ucc_schedule_t);
+    ucc_status_t              st   = UCC_OK;
+    int                       slot = -1;
+    ucc_recursive_spin_lock(&sp->lock);
+    for (int s = 0; s < sp->n_frags; s++) if (sp->frags[s] == frag) slot = s;
+    sp->n_frags_completed++;
+    if (sp->n_frags_completed == sp->n_frags_total) {
+        for (int s = 0; s < sp->n_frags; s++) sp->slot_global[s] = -1;
+        ucc_recursive_spin_unlock(&sp->lock);
+        sp->super.super.status = UCC_OK;
+        ucc_task_complete(&sp->super.super);
+        return UCC_OK;
+    }
+    /* deliver any ordering event of the finished incarnation that was not delivered yet
+     * (e.g. TASK_STARTED of a task that completed inside its own post) */
+    if (sp->order != UCC_PIPELINE_PARALLEL && sp->n_frags > 1)
+        for (unsigned j = 0; j < frag->n_tasks && st == UCC_OK; j++) st = fire(sp, slot, (int)j);
+    if (st == UCC_OK) {
+        if (sp->n_frags_started < sp->n_frags_total) {
+            int g = sp->n_frags_started++;
+            st = launch_frag(sp, slot, g); /* round-robin: slot == g % n_frags */
+        } else {
+            for (unsigned j = 0; j < frag->n_tasks; j++) sp->fired[slot][j] = 1;
+            sp->slot_global[slot] = sp->n_frags_total + slot; /* idle: "moved on" for successor checks */
+        }
+    }
+    ucc_recursive_spin_unlock(&sp->lock);
+    return st;
+}
+
+static ucc_status_t frag_error_handler(ucc_coll_task_t *parent, ucc_coll_task_t *task)
+{
+    if (task->super.status >= 0) { task->status = parent->status; ucc_task_complete(task); }
+    return UCC_OK;
+}
+
+ucc_status_t ucc_schedule_pipelined_post(ucc_coll_task_t *task)
+{
+    ucc_schedule_pipelined_t *sp = ucc_derived_of(task, ucc_schedule_pipelined_t);
+    int n = sp->n_frags < sp->n_frags_total ? sp->n_frags : sp->n_frags_total;
+    ucc_status_t st = UCC_OK;
+    sp->super.super.status = UCC_INPROGRESS; sp->super.super.super.status = UCC_INPROGRESS;
+    sp->n_frags_completed = 0; sp->n_frags_started = 0;
+    ucc_recursive_spin_lock(&sp->lock);
+    for (int s = 0; s < sp->n_frags; s++) { sp->slot_global[s] = -1; memset(sp->fired[s], 0, sizeof(sp->fired[s])); }
+    if (sp->n_frags_total == 0) {
+        ucc_recursive_spin_unlock(&sp->lock);
+        sp->super.super.status = UCC_OK; ucc_task_complete(&sp->super.super); return UCC_OK;
+    }
+    for (int s = 0; s < n && st == UCC_OK; s++) {
+        if (sp->super.super.super.status != UCC_INPROGRESS) break; /* finished/failed inline */
+        if (sp->n_frags_started > s) continue; /* slot was already re-armed by an inline completion */
+        sp->n_frags_started = s + 1;
+        st = launch_frag(sp, s, s);
+    }
+    ucc_recursive_spin_unlock(&sp->lock);
+    return st;
+}
+
+ucc_status_t ucc_schedule_pipelined_finalize(ucc_coll_task_t *task)
+{
+    ucc_schedule_pipelined_t *sp = ucc_derived_of(task, ucc_schedule_pipelined_t);
+    ucc_status_t st_all = UCC_OK;
+    for (int s = 0; s < sp->n_frags; s++) {
+        ucc_status_t st = sp->frags[s]->super.finalize(&sp->frags[s]->super);
+        if (st != UCC_OK) st_all = st;
+    }
+    ucc_coll_task_destruct(task);
+    return st_all;
+}
+
+ucc_status_t ucc_schedule_pipelined_init(ucc_base_coll_args_t *coll_args, ucc_base_team_t *team,
+                                         ucc_schedule_frag_init_fn_t frag_init, ucc_schedule_frag_setup_fn_t frag_setup,
+                                         int n_frags, int n_frags_total, ucc_pipeline_order_t order,
+                                         ucc_schedule_pipelined_t *sp)
+{
+    ucc_status_t st;
+    if (n_frags < 1 || n_frags > UCC_SCHEDULE_PIPELINED_MAX_FRAGS) return UCC_ERR_INVALID_PARAM;
+    UCC_CHECK_RET(ucc_schedule_init(&sp->super, coll_args, team));
+    sp->super.super.flags |= UCC_COLL_TASK_FLAG_IS_PIPELINED_SCHEDULE;
+    sp->super.super.post = ucc_schedule_pipelined_post;
+    sp->super.super.finalize = ucc_schedule_pipelined_finalize;
+    sp->n_frags = n_frags; sp->n_frags_total = n_frags_total; sp->order = order; sp->frag_setup = frag_setup;
+    sp->n_frags_started = sp->n_frags_completed = 0;
+    ucc_recursive_spinlock_init(&sp->lock);
+    for (int s = 0; s < n_frags; s++) {
+        st = frag_init(coll_args, sp, team, &sp->frags[s]);
+        if (st != UCC_OK) {
+            for (int k = 0; k < s; k++) sp->frags[k]->super.finalize(&sp->frags[k]->super);
+            return st;
+        }
+        sp->frags[s]->super.schedule = &sp->super;
+        sp->frags[s]->super.flags |= UCC_COLL_TASK_FLAG_INTERNAL;
+        if (sp->frags[s]->super.flags & UCC_COLL_TASK_FLAG_EXECUTOR) sp->super.super.flags |= UCC_COLL_TASK_FLAG_EXECUTOR;
+        for (unsigned j = 0; j < sp->frags[s]->n_tasks; j++) sp->frags[s]->tasks[j]->n_deps_base = sp->frags[s]->tasks[j]->n_deps;
+        UCC_CHECK_RET(ucc_event_manager_subscribe(&sp->frags[s]->super, UCC_EVENT_COMPLETED_SCHEDULE, &sp->super.super, frag_completed_handler));
+        UCC_CHECK_RET(ucc_event_manager_subscribe(&sp->frags[s]->super, UCC_EVENT_ERROR, &sp->super.super, frag_error_handler));
+    }
+    if (order != UCC_PIPELINE_PARALLEL && n_frags > 1) {
+        ucc_event_t ev = order == UCC_PIPELINE_ORDERED ? UCC_EVENT_TASK_STARTED : UCC_EVENT_COMPLETED;
+        for (int s = 0; s < n_frags; s++) {
+            ucc_schedule_t *a = sp->frags[s], *b = sp->frags[(s + 1) % n_frags];
+            for (unsigned j = 0; j < a->n_tasks && j < b->n_tasks; j++)
+                UCC_CHECK_RET(ucc_event_manager_subscribe(a->tasks[j], ev, b->tasks[j], cross_frag_handler));
+        }
+    }
+    return UCC_OK;
+}
