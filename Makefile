@@ -17,7 +17,7 @@ CFLAGS  := -O2 -g -std=gnu11 -fPIC -Wall -Wextra -Wno-unused-parameter -Wno-miss
 LDFLAGS := -shared -Wl,--no-undefined -lpthread -ldl -lrt -lm
 NVFLAGS := -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC \
            -Iinclude -Isrc -D_GNU_SOURCE --expt-relaxed-constexpr $(EXTRA_NVFLAGS)
-CUDA_LIBS := -L$(CUDA_HOME)/lib64 -lcudart -Wl,-rpath,$(CUDA_HOME)/lib64
+CUDA_LIBS := -L$(CUDA_HOME)/lib64 -lcudart -Xlinker -rpath,$(CUDA_HOME)/lib64
 
 CORE_DIRS := src/utils src/utils/arch src/utils/profile src/core src/schedule src/coll_score \
              src/components/base src/components/cl src/components/cl/basic src/components/cl/hier \
@@ -67,7 +67,7 @@ $(OUT)/libucc.so: $(CORE_OBJS)
 
 # ---- CUDA plugin modules: every .c / .cu of the component dir goes into one module ----
 define plugin_rule
-$(1)_SRCS := $$(wildcard $(2)/*.c) $$(wildcard $(2)/*.cu) $$(wildcard $(2)/kernels/*.cu)
+$(1)_SRCS := $$(wildcard $(2)/*.c) $$(wildcard $(2)/*.cu) $$(wildcard $(2)/kernels/*.cu) src/utils/cuda/ucc_cuda_util.c
 $(1)_OBJS := $$(patsubst %,$(BUILD)/%.o,$$($(1)_SRCS))
 $(MODDIR)/libucc_$(1).so: $$($(1)_OBJS) $(OUT)/libucc.so
 	@mkdir -p $(MODDIR)

@@ -48,7 +48,8 @@ typedef struct ucc_kn_pattern {
     unsigned   radix;
     ucc_rank_t size, rank, n_full; /* n_full = radix^p <= size */
     ucc_kn_node_type_t type;
-    ucc_rank_t partner;            /* proxy<->extra partner */
+    ucc_rank_t partner;            /* EXTRA: its proxy; PROXY: first extra */
+    unsigned   n_extras;           /* PROXY: extras served: rank + j*n_full, j = 1..n_extras (< radix) */
 } ucc_kn_pattern_t;
 
 static inline void ucc_kn_pattern_init(ucc_kn_pattern_t *p, ucc_rank_t rank, ucc_rank_t size, unsigned radix)
@@ -57,11 +58,16 @@ static inline void ucc_kn_pattern_init(ucc_kn_pattern_t *p, ucc_rank_t rank, ucc
     if (radix < 2) radix = 2;
     if (radix > size && size >= 2) radix = size;
     while (f * radix <= size) f *= radix;
-    p->radix = radix; p->size = size; p->rank = rank; p->n_full = (ucc_rank_t)f;
-    if (rank >= p->n_full) { p->type = UCC_KN_NODE_EXTRA; p->partner = rank - p->n_full; }
-    else if (rank + p->n_full < size) { p->type = UCC_KN_NODE_PROXY; p->partner = rank + p->n_full; }
-    else { p->type = UCC_KN_NODE_BASE; p->partner = UCC_RANK_INVALID; }
+    p->radix = radix; p->size = size; p->rank = rank; p->n_full = (ucc_rank_t)f; p->n_extras = 0;
+    /* size < radix * n_full, so every base rank serves at most radix-1 extras */
+    if (rank >= p->n_full) { p->type = UCC_KN_NODE_EXTRA; p->partner = rank % p->n_full; }
+    else {
+        for (uint64_t e = (uint64_t)rank + p->n_full; e < size; e += p->n_full) p->n_extras++;
+        if (p->n_extras) { p->type = UCC_KN_NODE_PROXY; p->partner = rank + p->n_full; }
+        else { p->type = UCC_KN_NODE_BASE; p->partner = UCC_RANK_INVALID; }
+    }
 }
+#define ucc_kn_extra(_p, _j) ((ucc_rank_t)((_p)->rank + ((_j) + 1) * (_p)->n_full))
 /* peers of `rank` in the round with digit weight `dist` (excluding itself); returns count */
 static inline unsigned ucc_kn_round_peers(const ucc_kn_pattern_t *p, uint64_t dist, ucc_rank_t *peers)
 {

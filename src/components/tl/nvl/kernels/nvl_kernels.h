@@ -1,0 +1,103 @@
+/* C launch interface of the tl/nvl device code (sm_100a).
+ *
+ * Every collective is ONE kernel that moves data between the team members'
+ * symmetric heaps over NVLink (plain ld/st on peer-mapped addresses or
+ * multimem.* on the NVLS multicast mapping), reduces in registers with the
+ * datatype/operator templates, and synchronises with flag words that live in
+ * the peers' heaps — no host involvement between phases, no separate reduce
+ * or copy kernel, no NCCL. */
+#ifndef UCC_TL_NVL_KERNELS_H_
+#define UCC_TL_NVL_KERNELS_H_
+#include <stdint.h>
+#include <stddef.h>
+#include <cuda_runtime_api.h>
+
+#define NVL_MAX_PEERS  16
+#define NVL_MAX_BLOCKS 128
+#define NVL_LL_MAX     (64 * 1024)          /* bytes per rank in the one-shot (latency) region */
+
+/* control block at offset 0 of every rank's heap */
+typedef struct nvl_ctrl {
+    uint32_t flags[NVL_MAX_BLOCKS][NVL_MAX_PEERS];    /* [block][src rank]: barrier signals written by peers */
+    uint32_t epoch;                                   /* barrier epoch of this rank (advanced by the last block of a kernel) */
+    uint32_t done_blocks;                             /* blocks of the running kernel that reached the end */
+    uint32_t rsvd[NVL_MAX_BLOCKS - 2];
+    uint32_t ll_flags[NVL_MAX_BLOCKS][NVL_MAX_PEERS]; /* one-shot arrival flags */
+    uint32_t ll_seq[NVL_MAX_BLOCKS];                  /* one-shot sequence (parity selects the buffer) */
+    uint32_t error;                                   /* set by a kernel whose spin timed out */
+    uint32_t pad[31];
+    uint64_t mc_arrive[NVL_MAX_BLOCKS];               /* NVLS barrier counters (incremented through the multicast mapping) */
+    uint64_t mc_epoch[NVL_MAX_BLOCKS];
+} nvl_ctrl_t;
+
+#define NVL_CTRL_SIZE  (64 * 1024)
+#define NVL_LL_OFFSET  NVL_CTRL_SIZE
+#define NVL_LL_SIZE    (2 * NVL_MAX_PEERS * NVL_LL_MAX)
+#define NVL_DATA_OFFSET (NVL_LL_OFFSET + NVL_LL_SIZE)
+
+typedef struct nvl_team_dev {
+    int      rank, size;
+    char    *heap[NVL_MAX_PEERS]; /* unicast mapping of every member's heap in my address space */
+    char    *mc_heap;             /* multicast mapping of the same offsets, or NULL */
+    size_t   data_size;           /* bytes of the data region */
+    uint64_t timeout_ns;          /* spin budget before a kernel gives up */
+    uint32_t *host_err;           /* host-mapped word: set when a spin timed out */
+} nvl_team_dev_t;
+
+typedef enum { NVL_DT_I8, NVL_DT_I16, NVL_DT_I32, NVL_DT_I64, NVL_DT_U8, NVL_DT_U16, NVL_DT_U32, NVL_DT_U64,
+               NVL_DT_F16, NVL_DT_F32, NVL_DT_F64, NVL_DT_BF16, NVL_DT_LAST } nvl_dt_t;
+typedef enum { NVL_OP_SUM, NVL_OP_PROD, NVL_OP_MAX, NVL_OP_MIN, NVL_OP_LAND, NVL_OP_LOR, NVL_OP_LXOR, NVL_OP_BAND, NVL_OP_BOR,
+               NVL_OP_BXOR, NVL_OP_AVG, NVL_OP_LAST } nvl_op_t;
+
+/* what the staged reduction kernel produces */
+typedef enum {
+    NVL_RED_ALLREDUCE,       /* every rank gets the whole reduced vector */
+    NVL_RED_REDUCE_SCATTER,  /* rank r gets block r (counts/offsets in elements) */
+    NVL_RED_REDUCE           /* only `root` gets the reduced vector */
+} nvl_red_kind_t;
+
+typedef struct nvl_red_args {
+    nvl_team_dev_t team;
+    const void    *src;
+    void          *dst;
+    size_t         count;       /* elements of the full input vector */
+    int            dt, op, kind, root;
+    int            use_nvls;    /* reduce in the switch (multimem.ld_reduce) instead of pulling */
+    size_t         rs_offset[NVL_MAX_PEERS]; /* REDUCE_SCATTER(V): element offset / count of each rank's block */
+    size_t         rs_count[NVL_MAX_PEERS];
+} nvl_red_args_t;
+
+/* generic staged exchange: allgather(v), alltoall(v), bcast, gather, scatter */
+#define NVL_XCHG_TABLE_BYTES 256 /* published offset table in front of the staged payload */
+#define NVL_XCHG_LOOKUP ((size_t)-1)
+typedef struct nvl_xchg_args {
+    nvl_team_dev_t team;
+    const void    *src;          /* local bytes staged into my heap (phase A) */
+    size_t         src_bytes;    /* how many bytes of src are staged (0: nothing to publish) */
+    size_t         stage_off[NVL_MAX_PEERS]; /* published table: byte offset of the block meant for peer p inside my staged data */
+    void          *dst;
+    /* phase B: from peer p copy pull_bytes[p] starting at pull_off[p] (offset inside p's staged data,
+     * or NVL_XCHG_LOOKUP: read it from p's published table at index `rank`) to dst + dst_off[p];
+     * the own block (p == rank) is copied straight from src + self_off */
+    size_t         pull_off[NVL_MAX_PEERS], pull_bytes[NVL_MAX_PEERS], dst_off[NVL_MAX_PEERS];
+    size_t         self_off;
+    int            publish_table;
+} nvl_xchg_args_t;
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+size_t       nvl_dt_size(int dt);
+int          nvl_dt_supports_op(int dt, int op);
+int          nvl_nvls_supports(int dt, int op);
+/* latency path: one-shot push allreduce, bytes <= NVL_LL_MAX */
+cudaError_t  nvl_launch_allreduce_oneshot(const nvl_red_args_t *a, int nblocks, int nthreads, cudaStream_t s);
+/* bandwidth path: staged two-shot (P2P pull or NVLS) for allreduce / reduce_scatter(v) / reduce */
+cudaError_t  nvl_launch_reduce_staged(const nvl_red_args_t *a, int nblocks, int nthreads, cudaStream_t s);
+cudaError_t  nvl_launch_exchange(const nvl_xchg_args_t *a, int nblocks, int nthreads, cudaStream_t s);
+cudaError_t  nvl_launch_barrier(const nvl_team_dev_t *t, cudaStream_t s);
+cudaError_t  nvl_launch_ctrl_init(void *heap_base, cudaStream_t s);
+#ifdef __cplusplus
+}
+#endif
+#endif

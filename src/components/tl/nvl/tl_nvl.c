@@ -1,0 +1,111 @@
+#include "tl_nvl.h"
+#include "core/ucc_global_opts.h"
+#include "utils/ucc_sys.h"
+#include <unistd.h>
+
+static ucc_config_field_t tl_nvl_lib_config_table[] = {
+    {"", "", NULL, ucc_offsetof(ucc_tl_nvl_lib_config_t, super), UCC_CONFIG_TYPE_TABLE(ucc_tl_lib_config_table)}, {NULL}};
+
+ucc_config_field_t ucc_tl_nvl_context_config_table[] = {
+    {"", "", NULL, ucc_offsetof(ucc_tl_nvl_context_config_t, super), UCC_CONFIG_TYPE_TABLE(ucc_tl_context_config_table)},
+    {"SYMMETRIC_SIZE", "128Mb", "Size of the data region of the per-team symmetric heap; larger messages are processed in rounds inside one kernel",
+     ucc_offsetof(ucc_tl_nvl_context_config_t, symmetric_size), UCC_CONFIG_TYPE_MEMUNITS},
+    {"NBLOCKS", "auto", "Thread blocks per collective kernel (auto: chosen from the message size)", ucc_offsetof(ucc_tl_nvl_context_config_t, nblocks), UCC_CONFIG_TYPE_UINT},
+    {"MAX_BLOCKS", "32", "Upper bound of thread blocks per collective kernel (all blocks of all ranks sharing a GPU must be co-resident)",
+     ucc_offsetof(ucc_tl_nvl_context_config_t, max_blocks), UCC_CONFIG_TYPE_UINT},
+    {"NTHREADS", "512", "Threads per block", ucc_offsetof(ucc_tl_nvl_context_config_t, nthreads), UCC_CONFIG_TYPE_UINT},
+    {"TIMEOUT", "10s", "Spin budget of a device-side wait before the kernel gives up and the collective fails with UCC_ERR_TIMED_OUT",
+     ucc_offsetof(ucc_tl_nvl_context_config_t, timeout), UCC_CONFIG_TYPE_TIME},
+    {"USE_NVLS", "try", "Use NVSwitch multicast / in-switch reduction (multimem.*) when the fabric supports it", ucc_offsetof(ucc_tl_nvl_context_config_t, use_nvls), UCC_CONFIG_TYPE_TERNARY},
+    {"USE_VMM", "try", "Allocate the heap with the CUDA virtual memory management API and share it as a POSIX fd (required for NVLS); otherwise cudaMalloc + cudaIpc",
+     ucc_offsetof(ucc_tl_nvl_context_config_t, use_vmm), UCC_CONFIG_TYPE_TERNARY},
+    {"ALLREDUCE_ONESHOT_THRESH", "32K", "Allreduce messages up to this size use the one-shot push kernel", ucc_offsetof(ucc_tl_nvl_context_config_t, oneshot_thresh), UCC_CONFIG_TYPE_MEMUNITS},
+    {"ALLREDUCE_NVLS_THRESH", "256K", "Allreduce messages of at least this size use NVLS when available", ucc_offsetof(ucc_tl_nvl_context_config_t, nvls_thresh), UCC_CONFIG_TYPE_MEMUNITS},
+    {"FD_VIA_PIDFD", "try", "Fetch peers' memory handles with pidfd_getfd before falling back to a unix socket", ucc_offsetof(ucc_tl_nvl_context_config_t, fd_via_pidfd), UCC_CONFIG_TYPE_TERNARY},
+    {NULL}};
+
+static ucc_status_t nvl_lib_init(const ucc_base_lib_params_t *p, const ucc_base_lib_config_t *config, ucc_base_lib_t **lib_p)
+{
+    ucc_tl_nvl_lib_t *lib = (ucc_tl_nvl_lib_t *)calloc(1, sizeof(*lib));
+    int n = 0;
+    (void)p;
+    if (!lib) return UCC_ERR_NO_MEMORY;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { (void)cudaGetLastError(); free(lib); return UCC_ERR_NO_RESOURCE; }
+    ucc_tl_lib_init_base(&lib->super, &ucc_tl_nvl, ucc_derived_of(config, ucc_tl_lib_config_t));
+    *lib_p = &lib->super.super;
+    return UCC_OK;
+}
+static void nvl_lib_finalize(ucc_base_lib_t *lib) { free(lib); }
+static ucc_status_t nvl_lib_get_attr(const ucc_base_lib_t *lib, ucc_base_lib_attr_t *attr)
+{ (void)lib; attr->attr.thread_mode = UCC_THREAD_MULTIPLE; attr->attr.coll_types = UCC_TL_NVL_SUPPORTED_COLLS; attr->flags = 0; attr->min_team_size = 2; attr->max_team_size = NVL_MAX_PEERS; return UCC_OK; }
+static ucc_status_t nvl_lib_get_properties(ucc_base_lib_properties_t *p) { p->default_team_size = 2; p->min_team_size = 2; p->max_team_size = NVL_MAX_PEERS; return UCC_OK; }
+
+static ucc_status_t nvl_ctx_create(const ucc_base_context_params_t *p, const ucc_base_ctx_config_t *config, ucc_base_context_t **ctx_p)
+{
+    static uint32_t seq = 0;
+    ucc_tl_nvl_context_t *ctx;
+    struct cudaDeviceProp prop;
+    int dev, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); tl_debug(config->lib, "no current CUDA device"); return UCC_ERR_NO_RESOURCE; }
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) { (void)cudaGetLastError(); return UCC_ERR_NO_RESOURCE; }
+    if (cudaFree(0) != cudaSuccess) { (void)cudaGetLastError(); return UCC_ERR_NO_RESOURCE; }
+    ctx = (ucc_tl_nvl_context_t *)calloc(1, sizeof(*ctx));
+    if (!ctx) return UCC_ERR_NO_MEMORY;
+    ctx->super.super.ucc_context = p->context; ctx->super.super.lib = config->lib; ctx->tm = p->thread_mode;
+    if (ucc_config_parser_clone_opts(config, &ctx->cfg, ucc_tl_nvl_context_config_table) != UCC_OK) { free(ctx); return UCC_ERR_NO_MEMORY; }
+    ctx->dev = dev; ctx->sm_count = prop.multiProcessorCount;
+    ctx->addr.host_hash = p->context->proc_info.host_hash; ctx->addr.pid = (int32_t)getpid(); ctx->addr.dev = dev;
+    ctx->addr.ep_id = ((uint64_t)(uint32_t)ctx->addr.pid << 32) | ucc_atomic_fadd32(&seq, 1);
+    ucc_cu_api_load();
+    ctx->addr.vmm_ok = 0; ctx->addr.mc_ok = 0;
+    if (ucc_cu.cuDeviceGetAttribute && ucc_cu.cuMemCreate) {
+        CUdevice cudev;
+        if (ucc_cu.cuDeviceGet(&cudev, dev) == CUDA_SUCCESS) {
+            if (ucc_cu.cuDeviceGetAttribute(&v, CU_DEVICE_ATTRIBUTE_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR_SUPPORTED, cudev) == CUDA_SUCCESS && v) ctx->addr.vmm_ok = 1;
+            v = 0;
+            if (ucc_cu.cuMulticastCreate && ucc_cu.cuDeviceGetAttribute(&v, CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED, cudev) == CUDA_SUCCESS && v) ctx->addr.mc_ok = 1;
+        }
+    }
+    if (ctx->cfg.use_vmm == UCC_NO) ctx->addr.vmm_ok = 0;
+    if (ctx->cfg.use_nvls == UCC_NO || !ctx->addr.vmm_ok) ctx->addr.mc_ok = 0;
+    if (ctx->cfg.oneshot_thresh > NVL_LL_MAX) ctx->cfg.oneshot_thresh = NVL_LL_MAX;
+    if (ctx->cfg.max_blocks > NVL_MAX_BLOCKS) ctx->cfg.max_blocks = NVL_MAX_BLOCKS;
+    if (ctx->cfg.max_blocks < 1) ctx->cfg.max_blocks = 1;
+    if (ctx->cfg.nthreads < 64) ctx->cfg.nthreads = 64;
+    if (ctx->cfg.nthreads > 1024) ctx->cfg.nthreads = 1024;
+    ucc_mpool_init(&ctx->task_mp, 0, sizeof(ucc_tl_nvl_task_t), 0, 64, 16, (unsigned)-1, NULL, p->thread_mode, "tl_nvl_tasks");
+    tl_debug(config->lib, "initialized tl context %p on device %d (%s, %d SMs): vmm %d multicast %d", (void *)ctx, dev, prop.name, ctx->sm_count, ctx->addr.vmm_ok, ctx->addr.mc_ok);
+    *ctx_p = &ctx->super.super;
+    return UCC_OK;
+}
+static void nvl_ctx_destroy(ucc_base_context_t *b)
+{
+    ucc_tl_nvl_context_t *ctx = ucc_derived_of(b, ucc_tl_nvl_context_t);
+    ucc_mpool_cleanup(&ctx->task_mp, 1);
+    ucc_config_parser_release_opts(&ctx->cfg, ucc_tl_nvl_context_config_table);
+    free(ctx);
+}
+static ucc_status_t nvl_ctx_get_attr(const ucc_base_context_t *b, ucc_base_ctx_attr_t *attr)
+{
+    const ucc_tl_nvl_context_t *ctx = ucc_derived_of(b, ucc_tl_nvl_context_t);
+    if (attr->attr.mask & UCC_CONTEXT_ATTR_FIELD_CTX_ADDR_LEN) attr->attr.ctx_addr_len = sizeof(ucc_tl_nvl_addr_t);
+    if (attr->attr.mask & UCC_CONTEXT_ATTR_FIELD_CTX_ADDR) memcpy(attr->attr.ctx_addr, &ctx->addr, sizeof(ctx->addr));
+    if (attr->attr.mask & UCC_CONTEXT_ATTR_FIELD_WORK_BUFFER_SIZE) attr->attr.global_work_buffer_size = 0;
+    attr->topo_required = 1;
+    return UCC_OK;
+}
+
+ucc_tl_iface_t ucc_tl_nvl = {
+    .super = {.name = "nvl", .score = UCC_TL_NVL_DEFAULT_SCORE},
+    .tl_lib_config = {"TL_NVL lib", "TL_NVL_", tl_nvl_lib_config_table, sizeof(ucc_tl_nvl_lib_config_t), {NULL, NULL}},
+    .tl_context_config = {"TL_NVL context", "TL_NVL_", ucc_tl_nvl_context_config_table, sizeof(ucc_tl_nvl_context_config_t), {NULL, NULL}},
+    .lib = {nvl_lib_init, nvl_lib_finalize, nvl_lib_get_attr, nvl_lib_get_properties},
+    .context = {nvl_ctx_create, NULL, nvl_ctx_destroy, nvl_ctx_get_attr, NULL, NULL, NULL},
+    .team = {ucc_tl_nvl_team_create_post, ucc_tl_nvl_team_create_test, ucc_tl_nvl_team_destroy, ucc_tl_nvl_team_get_scores},
+    .coll = {ucc_tl_nvl_coll_init},
+};
+static void UCC_CTOR tl_nvl_register(void)
+{
+    ucc_config_table_register(&ucc_tl_nvl.tl_lib_config); ucc_config_table_register(&ucc_tl_nvl.tl_context_config);
+    ucc_tl_nvl_register_alg_info();
+}

@@ -1,0 +1,128 @@
+/* tl/nvl: the NVLink 5 / NVSwitch transport (role of reference tl/cuda, 10.3 K LoC).
+ *
+ * Design (B200-first, not a port):
+ *   - one symmetric heap per team, mapped into every member's address space at team
+ *     creation (CUDA VMM handles passed as POSIX fds between processes, plain pointers
+ *     between contexts of one process) and, when the fabric offers it, additionally bound
+ *     to an NVLS multicast object;
+ *   - data plane AND synchronisation plane live on the GPU: every collective is one kernel
+ *     (kernels/nvl_kernels.cu) that signals peers with flag words in their heaps; the host only
+ *     enqueues the kernel and polls one CUDA event;
+ *   - no shared-memory control segment, no CPU step counters, no per-collective IPC handle
+ *     exchange, no executor round trips (compare reference tl_cuda_team.c:62-217,
+ *     reduce_scatterv_linear.c:229-328, alltoallv_ce.c:70-126).
+ */
+#ifndef UCC_TL_NVL_H_
+#define UCC_TL_NVL_H_
+#include "components/tl/ucc_tl.h"
+#include "components/mc/ucc_mc.h"
+#include "core/ucc_context.h"
+#include "core/ucc_team.h"
+#include "core/ucc_ee.h"
+#include "utils/ucc_mpool.h"
+#include "utils/cuda/ucc_cuda_util.h"
+#include "kernels/nvl_kernels.h"
+
+#define UCC_TL_NVL_DEFAULT_SCORE 40
+#define UCC_TL_NVL_SUPPORTED_COLLS UCC_COLL_TYPE_ALL
+
+typedef struct ucc_tl_nvl_lib_config { ucc_tl_lib_config_t super; } ucc_tl_nvl_lib_config_t;
+typedef struct ucc_tl_nvl_context_config {
+    ucc_tl_context_config_t super;
+    size_t   symmetric_size;   /* data region of the per-team heap */
+    unsigned nblocks;          /* CTAs per collective kernel (auto: by message size) */
+    unsigned max_blocks;
+    unsigned nthreads;
+    double   timeout;          /* device spin budget, seconds */
+    int      use_nvls;         /* ternary */
+    int      use_vmm;          /* ternary: VMM+fd export (needed for NVLS) or cudaMalloc+cudaIpc */
+    size_t   oneshot_thresh;   /* allreduce: one-shot push below, two-shot above */
+    size_t   nvls_thresh;      /* allreduce: use NVLS at or above this size */
+    int      fd_via_pidfd;     /* ternary: try pidfd_getfd before the unix socket */
+} ucc_tl_nvl_context_config_t;
+
+typedef struct ucc_tl_nvl_lib { ucc_tl_lib_t super; } ucc_tl_nvl_lib_t;
+
+typedef struct ucc_tl_nvl_addr { /* published through the core address exchange */
+    uint64_t host_hash; int32_t pid; int32_t dev; uint64_t ep_id; int32_t vmm_ok, mc_ok;
+} ucc_tl_nvl_addr_t;
+
+typedef struct ucc_tl_nvl_context {
+    ucc_tl_context_t            super;
+    ucc_tl_nvl_context_config_t cfg;
+    ucc_tl_nvl_addr_t           addr;
+    int                         dev;
+    int                         sm_count;
+    ucc_mpool_t                 task_mp;
+    ucc_thread_mode_t           tm;
+} ucc_tl_nvl_context_t;
+
+typedef enum { NVL_HEAP_LOCAL, NVL_HEAP_VMM, NVL_HEAP_IPC } nvl_heap_kind_t;
+/* what every rank tells the others about its heap */
+typedef struct nvl_rank_info {
+    int32_t  pid, dev, kind, fd, mc_fd;
+    int32_t  status;     /* UCC_OK or the error that makes this rank unusable */
+    uint64_t ptr;        /* LOCAL: device pointer valid inside that process */
+    uint64_t size;
+    cudaIpcMemHandle_t ipc;
+    char     sock[48];   /* abstract unix socket serving the fds */
+} nvl_rank_info_t;
+
+typedef enum { NVL_TEAM_INIT, NVL_TEAM_XCHG_INFO, NVL_TEAM_MAP, NVL_TEAM_SYNC1, NVL_TEAM_MC_CREATE, NVL_TEAM_MC_IMPORT,
+               NVL_TEAM_MC_ADDED, NVL_TEAM_MC_BOUND, NVL_TEAM_READY, NVL_TEAM_FAILED } nvl_team_state_t;
+
+typedef struct ucc_tl_nvl_team {
+    ucc_tl_team_t     super;
+    nvl_team_state_t  state;
+    ucc_team_oob_coll_t oob;
+    int               oob_internal;
+    void             *oob_req;
+    nvl_rank_info_t   my_info, *infos;
+    int32_t          *sync_vals, sync_send[4];
+    /* heap */
+    nvl_heap_kind_t   heap_kind;
+    size_t            heap_size;
+    char             *heap;                 /* my heap (device VA) */
+    CUmemGenericAllocationHandle mem_handle;/* VMM */
+    int               heap_fd;
+    char             *peer_va[NVL_MAX_PEERS];
+    CUmemGenericAllocationHandle peer_handle[NVL_MAX_PEERS];
+    /* NVLS */
+    int               nvls;                 /* multicast mapping is live */
+    CUmemGenericAllocationHandle mc_handle;
+    int               mc_fd;
+    char             *mc_va;
+    size_t            mc_size;
+    /* fd server */
+    int               srv_sock; void *srv_thread; volatile int srv_stop;
+    /* runtime */
+    nvl_team_dev_t    dev;
+    cudaStream_t      stream;
+    uint32_t         *host_err;             /* pinned, device mapped */
+    uint32_t          seq_num;
+} ucc_tl_nvl_team_t;
+
+typedef enum { NVL_TASK_REDUCE_ONESHOT, NVL_TASK_REDUCE_STAGED, NVL_TASK_XCHG, NVL_TASK_BARRIER } nvl_task_kind_t;
+typedef struct ucc_tl_nvl_task {
+    ucc_coll_task_t     super;
+    ucc_tl_nvl_team_t  *team;
+    nvl_task_kind_t     kind;
+    union { nvl_red_args_t red; nvl_xchg_args_t xchg; } u;
+    int                 nblocks, nthreads;
+    cudaEvent_t         event;
+    cudaStream_t        stream;     /* stream of the current post */
+    int                 captured;   /* posted into a capturing stream: completes immediately */
+} ucc_tl_nvl_task_t;
+
+#define NVL_CTX(_team) ucc_derived_of((_team)->super.super.context, ucc_tl_nvl_context_t)
+extern ucc_tl_iface_t ucc_tl_nvl;
+extern ucc_config_field_t ucc_tl_nvl_context_config_table[];
+
+ucc_status_t ucc_tl_nvl_team_create_post(ucc_base_context_t *ctx, const ucc_base_team_params_t *params, ucc_base_team_t **team);
+ucc_status_t ucc_tl_nvl_team_create_test(ucc_base_team_t *team);
+ucc_status_t ucc_tl_nvl_team_destroy(ucc_base_team_t *team);
+ucc_status_t ucc_tl_nvl_team_get_scores(ucc_base_team_t *team, ucc_coll_score_t **score);
+ucc_status_t ucc_tl_nvl_coll_init(ucc_base_coll_args_t *args, ucc_base_team_t *team, ucc_coll_task_t **task);
+ucc_status_t ucc_tl_nvl_alg_id_to_init(int alg_id, const char *alg_id_str, ucc_coll_type_t coll_type, ucc_memory_type_t mem_type, ucc_base_coll_init_fn_t *init);
+void         ucc_tl_nvl_register_alg_info(void);
+#endif

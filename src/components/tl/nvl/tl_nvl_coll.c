@@ -1,0 +1,374 @@
+/* tl/nvl collectives: argument translation, algorithm table, launch + completion.
+ * All 16 collective types map onto four kernels:
+ *   reduce family   -> nvl_allreduce_oneshot / nvl_reduce_staged (P2P or NVLS)
+ *   data movement   -> nvl_exchange (stage + pull)
+ *   synchronisation -> nvl_barrier                                                     */
+#include "tl_nvl.h"
+#include "core/ucc_progress_queue.h"
+#include "utils/profile/ucc_profile.h"
+#include "utils/ucc_string.h"
+#include <strings.h>
+
+#define NVL_LIB(_t) ((_t)->super.super.context->lib)
+
+static int to_nvl_dt(ucc_datatype_t dt)
+{
+    switch (dt) {
+    case UCC_DT_INT8: return NVL_DT_I8; case UCC_DT_INT16: return NVL_DT_I16; case UCC_DT_INT32: return NVL_DT_I32; case UCC_DT_INT64: return NVL_DT_I64;
+    case UCC_DT_UINT8: return NVL_DT_U8; case UCC_DT_UINT16: return NVL_DT_U16; case UCC_DT_UINT32: return NVL_DT_U32; case UCC_DT_UINT64: return NVL_DT_U64;
+    case UCC_DT_FLOAT16: return NVL_DT_F16; case UCC_DT_FLOAT32: return NVL_DT_F32; case UCC_DT_FLOAT64: return NVL_DT_F64; case UCC_DT_BFLOAT16: return NVL_DT_BF16;
+    default: return -1;
+    }
+}
+static int to_nvl_op(ucc_reduction_op_t op)
+{
+    switch (op) {
+    case UCC_OP_SUM: return NVL_OP_SUM; case UCC_OP_PROD: return NVL_OP_PROD; case UCC_OP_MAX: return NVL_OP_MAX; case UCC_OP_MIN: return NVL_OP_MIN;
+    case UCC_OP_LAND: return NVL_OP_LAND; case UCC_OP_LOR: return NVL_OP_LOR; case UCC_OP_LXOR: return NVL_OP_LXOR; case UCC_OP_BAND: return NVL_OP_BAND;
+    case UCC_OP_BOR: return NVL_OP_BOR; case UCC_OP_BXOR: return NVL_OP_BXOR; case UCC_OP_AVG: return NVL_OP_AVG;
+    default: return -1;
+    }
+}
+static inline int is_cuda(ucc_memory_type_t mt) { return mt == UCC_MEMORY_TYPE_CUDA; }
+
+/* ------------------------------------------------------------------ */
+/* task life cycle                                                     */
+/* ------------------------------------------------------------------ */
+static ucc_status_t nvl_launch(ucc_tl_nvl_task_t *t, cudaStream_t s)
+{
+    cudaError_t e;
+    switch (t->kind) {
+    case NVL_TASK_REDUCE_ONESHOT: e = nvl_launch_allreduce_oneshot(&t->u.red, t->nblocks, t->nthreads, s); break;
+    case NVL_TASK_REDUCE_STAGED: e = nvl_launch_reduce_staged(&t->u.red, t->nblocks, t->nthreads, s); break;
+    case NVL_TASK_XCHG: e = nvl_launch_exchange(&t->u.xchg, t->nblocks, t->nthreads, s); break;
+    default: e = nvl_launch_barrier(&t->team->dev, s); break;
+    }
+    if (e != cudaSuccess) { tl_error(NVL_LIB(t->team), "kernel launch failed: %s", cudaGetErrorString(e)); return UCC_ERR_NO_MESSAGE; }
+    return UCC_OK;
+}
+
+static void nvl_progress(ucc_coll_task_t *ct)
+{
+    ucc_tl_nvl_task_t *t = ucc_derived_of(ct, ucc_tl_nvl_task_t);
+    cudaError_t e;
+    if (t->captured) { ct->status = UCC_OK; return; }
+    e = cudaEventQuery(t->event);
+    if (e == cudaErrorNotReady) { (void)cudaGetLastError(); return; }
+    if (e != cudaSuccess) { (void)cudaGetLastError(); tl_error(NVL_LIB(t->team), "collective kernel failed: %s", cudaGetErrorString(e)); ct->status = UCC_ERR_NO_MESSAGE; return; }
+    if (ucc_unlikely(*(volatile uint32_t *)t->team->host_err)) {
+        tl_error(NVL_LIB(t->team), "device-side wait timed out (a peer did not arrive within TL_NVL_TIMEOUT)");
+        ct->status = UCC_ERR_TIMED_OUT; return;
+    }
+    ct->status = UCC_OK;
+}
+
+static ucc_status_t nvl_post_on(ucc_tl_nvl_task_t *t, cudaStream_t s)
+{
+    enum cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    ucc_status_t st;
+    UCC_PROFILE_REQUEST_EVENT(t, "nvl_coll_start", 0);
+    t->stream = s; t->captured = 0;
+    if (cudaStreamIsCapturing(s, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusActive) t->captured = 1;
+    st = nvl_launch(t, s);
+    if (st != UCC_OK) return st;
+    if (!t->captured) CUDA_CHECK(cudaEventRecord(t->event, s));
+    return ucc_progress_queue_enqueue(UCC_TL_CORE_CTX(t->team)->pq, &t->super);
+}
+static ucc_status_t nvl_post(ucc_coll_task_t *ct)
+{ ucc_tl_nvl_task_t *t = ucc_derived_of(ct, ucc_tl_nvl_task_t); return nvl_post_on(t, t->team->stream); }
+
+/* stream-ordered post: the kernel goes straight onto the user's stream (what PyTorch-style
+ * consumers use); no host-side dependency resolution is needed */
+static ucc_status_t nvl_triggered_post(ucc_ee_h ee, ucc_ev_t *ev, ucc_coll_task_t *ct)
+{
+    ucc_tl_nvl_task_t *t = ucc_derived_of(ct, ucc_tl_nvl_task_t);
+    ucc_ev_t post_event;
+    ucc_status_t st;
+    (void)ev;
+    if (ee->ee_type != UCC_EE_CUDA_STREAM) return UCC_ERR_NOT_SUPPORTED;
+    ct->ee = ee;
+    st = nvl_post_on(t, (cudaStream_t)ee->ee_context);
+    if (st != UCC_OK) return st;
+    post_event.ev_type = UCC_EVENT_COLLECTIVE_POST; post_event.ev_context = NULL; post_event.ev_context_size = 0; post_event.req = &ct->super;
+    ucc_ee_set_event_internal(ee, &post_event, &ee->event_out_queue);
+    return UCC_OK;
+}
+static ucc_status_t nvl_finalize(ucc_coll_task_t *ct)
+{
+    ucc_tl_nvl_task_t *t = ucc_derived_of(ct, ucc_tl_nvl_task_t);
+    if (t->event) cudaEventDestroy(t->event);
+    ucc_coll_task_destruct(ct);
+    ucc_mpool_put(t);
+    return UCC_OK;
+}
+
+static ucc_status_t task_alloc(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, ucc_tl_nvl_task_t **tp)
+{
+    ucc_tl_nvl_team_t *team = ucc_derived_of(b_team, ucc_tl_nvl_team_t);
+    ucc_tl_nvl_context_t *ctx = NVL_CTX(team);
+    ucc_tl_nvl_task_t *t = (ucc_tl_nvl_task_t *)ucc_mpool_get(&ctx->task_mp);
+    if (!t) return UCC_ERR_NO_MEMORY;
+    ucc_coll_task_init(&t->super, b, b_team);
+    t->team = team; t->event = NULL; t->captured = 0;
+    t->nthreads = (int)ctx->cfg.nthreads;
+    t->super.post = nvl_post; t->super.progress = nvl_progress; t->super.finalize = nvl_finalize; t->super.triggered_post = nvl_triggered_post;
+    if (cudaEventCreateWithFlags(&t->event, cudaEventDisableTiming) != cudaSuccess) { (void)cudaGetLastError(); ucc_mpool_put(t); return UCC_ERR_NO_RESOURCE; }
+    *tp = t;
+    return UCC_OK;
+}
+static int pick_blocks(ucc_tl_nvl_context_t *ctx, size_t bytes, size_t bytes_per_block)
+{
+    size_t nb;
+    if (ctx->cfg.nblocks != UCC_UUNITS_AUTO && ctx->cfg.nblocks > 0) return (int)ucc_min(ctx->cfg.nblocks, ctx->cfg.max_blocks);
+    nb = (bytes + bytes_per_block - 1) / bytes_per_block;
+    if (nb < 1) nb = 1;
+    if (nb > ctx->cfg.max_blocks) nb = ctx->cfg.max_blocks;
+    return (int)nb;
+}
+
+/* ------------------------------------------------------------------ */
+/* reduce family                                                       */
+/* ------------------------------------------------------------------ */
+typedef enum { RED_ALG_ONESHOT, RED_ALG_TWOSHOT, RED_ALG_NVLS } red_alg_t;
+
+static ucc_status_t red_init(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, ucc_coll_task_t **task_p, red_alg_t alg)
+{
+    ucc_tl_nvl_team_t *team = ucc_derived_of(b_team, ucc_tl_nvl_team_t);
+    ucc_tl_nvl_context_t *ctx = NVL_CTX(team);
+    ucc_coll_args_t *a = &b->args;
+    ucc_rank_t N = UCC_TL_TEAM_SIZE(team), me = UCC_TL_TEAM_RANK(team);
+    int inplace = UCC_IS_INPLACE(*a), root = (ucc_rank_t)a->root == me;
+    ucc_tl_nvl_task_t *t;
+    nvl_red_args_t *r;
+    ucc_datatype_t dt; ucc_memory_type_t smt, dmt;
+    const void *src; void *dst; size_t count, bytes;
+    int ndt, nop;
+    ucc_status_t st;
+    switch (a->coll_type) {
+    case UCC_COLL_TYPE_ALLREDUCE:
+        dt = a->dst.info.datatype; count = a->dst.info.count; dst = a->dst.info.buffer; dmt = a->dst.info.mem_type;
+        src = inplace ? dst : a->src.info.buffer; smt = inplace ? dmt : a->src.info.mem_type; break;
+    case UCC_COLL_TYPE_REDUCE:
+        if (root) { dt = a->dst.info.datatype; count = a->dst.info.count; dst = a->dst.info.buffer; dmt = a->dst.info.mem_type; src = inplace ? dst : a->src.info.buffer; smt = inplace ? dmt : a->src.info.mem_type; }
+        else { dt = a->src.info.datatype; count = a->src.info.count; src = a->src.info.buffer; smt = a->src.info.mem_type; dst = NULL; dmt = smt; }
+        break;
+    case UCC_COLL_TYPE_REDUCE_SCATTER:
+        dt = a->dst.info.datatype; dst = a->dst.info.buffer; dmt = a->dst.info.mem_type;
+        count = inplace ? a->dst.info.count : a->dst.info.count * N;
+        src = inplace ? dst : a->src.info.buffer; smt = inplace ? dmt : a->src.info.mem_type; break;
+    case UCC_COLL_TYPE_REDUCE_SCATTERV:
+        dt = a->dst.info_v.datatype; dst = a->dst.info_v.buffer; dmt = a->dst.info_v.mem_type;
+        count = ucc_coll_args_get_total_count(a, a->dst.info_v.counts, N);
+        src = inplace ? dst : a->src.info.buffer; smt = inplace ? dmt : a->src.info.mem_type; break;
+    default: return UCC_ERR_NOT_SUPPORTED;
+    }
+    if (!is_cuda(smt) || !is_cuda(dmt)) return UCC_ERR_NOT_SUPPORTED;
+    ndt = to_nvl_dt(dt); nop = to_nvl_op(a->op);
+    if (ndt < 0 || nop < 0 || !nvl_dt_supports_op(ndt, nop)) return UCC_ERR_NOT_SUPPORTED;
+    bytes = count * ucc_dt_size(dt);
+    if (alg == RED_ALG_ONESHOT && (a->coll_type != UCC_COLL_TYPE_ALLREDUCE || bytes > NVL_LL_MAX)) return UCC_ERR_NOT_SUPPORTED;
+    if (alg == RED_ALG_NVLS && (!team->nvls || !nvl_nvls_supports(ndt, nop))) return UCC_ERR_NOT_SUPPORTED;
+    st = task_alloc(b, b_team, &t);
+    if (st != UCC_OK) return st;
+    r = &t->u.red;
+    memset(r, 0, sizeof(*r));
+    r->team = team->dev; r->src = src; r->dst = dst; r->count = count; r->dt = ndt; r->op = nop; r->root = (int)a->root; r->use_nvls = (alg == RED_ALG_NVLS);
+    switch (a->coll_type) {
+    case UCC_COLL_TYPE_ALLREDUCE: r->kind = NVL_RED_ALLREDUCE; break;
+    case UCC_COLL_TYPE_REDUCE: r->kind = NVL_RED_REDUCE; break;
+    default:
+        r->kind = NVL_RED_REDUCE_SCATTER;
+        { size_t off = 0;
+          for (ucc_rank_t i = 0; i < N; i++) {
+              size_t c = a->coll_type == UCC_COLL_TYPE_REDUCE_SCATTERV ? ucc_coll_args_get_count(a, a->dst.info_v.counts, i) : ucc_buffer_block_count(count, N, i);
+              r->rs_offset[i] = off; r->rs_count[i] = c; off += c;
+          }
+          /* in-place: the result block stays at its offset inside the buffer */
+          if (inplace) r->dst = (char *)dst + r->rs_offset[me] * ucc_dt_size(dt); }
+        break;
+    }
+    if (alg == RED_ALG_ONESHOT) { t->kind = NVL_TASK_REDUCE_ONESHOT; t->nblocks = pick_blocks(ctx, bytes, 8192); if (t->nblocks > 8) t->nblocks = ucc_min(8u, ctx->cfg.max_blocks); }
+    else { t->kind = NVL_TASK_REDUCE_STAGED; t->nblocks = pick_blocks(ctx, bytes, 128 * 1024); }
+    *task_p = &t->super;
+    return UCC_OK;
+}
+static ucc_status_t red_init_oneshot(ucc_base_coll_args_t *b, ucc_base_team_t *t, ucc_coll_task_t **p) { return red_init(b, t, p, RED_ALG_ONESHOT); }
+static ucc_status_t red_init_twoshot(ucc_base_coll_args_t *b, ucc_base_team_t *t, ucc_coll_task_t **p) { return red_init(b, t, p, RED_ALG_TWOSHOT); }
+static ucc_status_t red_init_nvls(ucc_base_coll_args_t *b, ucc_base_team_t *t, ucc_coll_task_t **p) { return red_init(b, t, p, RED_ALG_NVLS); }
+
+/* ------------------------------------------------------------------ */
+/* data movement family                                                */
+/* ------------------------------------------------------------------ */
+static ucc_status_t xchg_init(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, ucc_coll_task_t **task_p)
+{
+    ucc_tl_nvl_team_t *team = ucc_derived_of(b_team, ucc_tl_nvl_team_t);
+    ucc_tl_nvl_context_t *ctx = NVL_CTX(team);
+    ucc_coll_args_t *a = &b->args;
+    ucc_rank_t N = UCC_TL_TEAM_SIZE(team), me = UCC_TL_TEAM_RANK(team);
+    int inplace = UCC_IS_INPLACE(*a), is_root = (ucc_rank_t)a->root == me;
+    size_t cap = ctx->cfg.symmetric_size > NVL_XCHG_TABLE_BYTES ? ctx->cfg.symmetric_size - NVL_XCHG_TABLE_BYTES : 0;
+    nvl_xchg_args_t x;
+    ucc_tl_nvl_task_t *t;
+    size_t moved = 0, dts;
+    ucc_status_t st;
+    memset(&x, 0, sizeof(x));
+    x.team = team->dev;
+    if (UCC_COLL_ARGS_ACTIVE_SET(a)) return UCC_ERR_NOT_SUPPORTED;
+    switch (a->coll_type) {
+    case UCC_COLL_TYPE_ALLGATHER: {
+        size_t blk = a->dst.info.count / N * ucc_dt_size(a->dst.info.datatype);
+        if (!is_cuda(a->dst.info.mem_type) || (!inplace && !is_cuda(a->src.info.mem_type))) return UCC_ERR_NOT_SUPPORTED;
+        x.dst = a->dst.info.buffer; x.src = inplace ? (char *)x.dst + me * blk : a->src.info.buffer; x.src_bytes = blk;
+        for (ucc_rank_t p = 0; p < N; p++) { x.pull_off[p] = 0; x.pull_bytes[p] = blk; x.dst_off[p] = p * blk; }
+        moved = blk * N; break; }
+    case UCC_COLL_TYPE_ALLGATHERV: {
+        dts = ucc_dt_size(a->dst.info_v.datatype);
+        if (!is_cuda(a->dst.info_v.mem_type) || (!inplace && !is_cuda(a->src.info.mem_type))) return UCC_ERR_NOT_SUPPORTED;
+        x.dst = a->dst.info_v.buffer;
+        for (ucc_rank_t p = 0; p < N; p++) { x.pull_off[p] = 0; x.pull_bytes[p] = ucc_coll_args_get_count(a, a->dst.info_v.counts, p) * dts; x.dst_off[p] = ucc_coll_args_get_displacement(a, a->dst.info_v.displacements, p) * dts; moved += x.pull_bytes[p]; }
+        x.src = inplace ? (char *)x.dst + x.dst_off[me] : a->src.info.buffer; x.src_bytes = x.pull_bytes[me];
+        break; }
+    case UCC_COLL_TYPE_ALLTOALL: {
+        size_t blk = a->dst.info.count / N * ucc_dt_size(a->dst.info.datatype);
+        if (inplace) return UCC_ERR_NOT_SUPPORTED; /* would need a full private copy: leave to the fallback TL */
+        if (!is_cuda(a->dst.info.mem_type) || !is_cuda(a->src.info.mem_type)) return UCC_ERR_NOT_SUPPORTED;
+        x.dst = a->dst.info.buffer; x.src = a->src.info.buffer; x.src_bytes = blk * N; x.self_off = me * blk;
+        for (ucc_rank_t p = 0; p < N; p++) { x.pull_off[p] = me * blk; x.pull_bytes[p] = blk; x.dst_off[p] = p * blk; }
+        moved = blk * N; break; }
+    case UCC_COLL_TYPE_ALLTOALLV: {
+        size_t sdt = ucc_dt_size(a->src.info_v.datatype), ddt = ucc_dt_size(a->dst.info_v.datatype), end = 0;
+        if (inplace) return UCC_ERR_NOT_SUPPORTED;
+        if (!is_cuda(a->dst.info_v.mem_type) || !is_cuda(a->src.info_v.mem_type)) return UCC_ERR_NOT_SUPPORTED;
+        x.dst = a->dst.info_v.buffer; x.src = a->src.info_v.buffer; x.publish_table = 1;
+        for (ucc_rank_t p = 0; p < N; p++) {
+            size_t so = ucc_coll_args_get_displacement(a, a->src.info_v.displacements, p) * sdt, sc = ucc_coll_args_get_count(a, a->src.info_v.counts, p) * sdt;
+            x.stage_off[p] = so; if (so + sc > end) end = so + sc;
+            x.pull_off[p] = NVL_XCHG_LOOKUP; x.pull_bytes[p] = ucc_coll_args_get_count(a, a->dst.info_v.counts, p) * ddt;
+            x.dst_off[p] = ucc_coll_args_get_displacement(a, a->dst.info_v.displacements, p) * ddt; moved += x.pull_bytes[p];
+        }
+        x.src_bytes = end; x.self_off = x.stage_off[me];
+        break; }
+    case UCC_COLL_TYPE_BCAST: {
+        size_t len = a->src.info.count * ucc_dt_size(a->src.info.datatype);
+        if (!is_cuda(a->src.info.mem_type)) return UCC_ERR_NOT_SUPPORTED;
+        x.dst = a->src.info.buffer; x.src = a->src.info.buffer; x.src_bytes = is_root ? len : 0;
+        if (!is_root) { x.pull_off[a->root] = 0; x.pull_bytes[a->root] = len; x.dst_off[a->root] = 0; }
+        moved = len; break; }
+    case UCC_COLL_TYPE_GATHER: {
+        size_t blk = is_root ? a->dst.info.count / N * ucc_dt_size(a->dst.info.datatype) : a->src.info.count * ucc_dt_size(a->src.info.datatype);
+        if (is_root ? !is_cuda(a->dst.info.mem_type) || (!inplace && !is_cuda(a->src.info.mem_type)) : !is_cuda(a->src.info.mem_type)) return UCC_ERR_NOT_SUPPORTED;
+        if (is_root) {
+            x.dst = a->dst.info.buffer; x.src = inplace ? (char *)x.dst + me * blk : a->src.info.buffer;
+            for (ucc_rank_t p = 0; p < N; p++) { x.pull_off[p] = 0; x.pull_bytes[p] = blk; x.dst_off[p] = p * blk; }
+        } else { x.src = a->src.info.buffer; x.src_bytes = blk; }
+        moved = blk * N; break; }
+    case UCC_COLL_TYPE_GATHERV: {
+        if (is_root ? !is_cuda(a->dst.info_v.mem_type) || (!inplace && !is_cuda(a->src.info.mem_type)) : !is_cuda(a->src.info.mem_type)) return UCC_ERR_NOT_SUPPORTED;
+        if (is_root) {
+            dts = ucc_dt_size(a->dst.info_v.datatype); x.dst = a->dst.info_v.buffer;
+            for (ucc_rank_t p = 0; p < N; p++) { x.pull_off[p] = 0; x.pull_bytes[p] = ucc_coll_args_get_count(a, a->dst.info_v.counts, p) * dts; x.dst_off[p] = ucc_coll_args_get_displacement(a, a->dst.info_v.displacements, p) * dts; moved += x.pull_bytes[p]; }
+            x.src = inplace ? (char *)x.dst + x.dst_off[me] : a->src.info.buffer;
+        } else { x.src = a->src.info.buffer; x.src_bytes = a->src.info.count * ucc_dt_size(a->src.info.datatype); moved = x.src_bytes * N; }
+        break; }
+    case UCC_COLL_TYPE_SCATTER: {
+        size_t blk = is_root ? a->src.info.count / N * ucc_dt_size(a->src.info.datatype) : a->dst.info.count * ucc_dt_size(a->dst.info.datatype);
+        if (is_root ? !is_cuda(a->src.info.mem_type) || (!inplace && !is_cuda(a->dst.info.mem_type)) : !is_cuda(a->dst.info.mem_type)) return UCC_ERR_NOT_SUPPORTED;
+        if (is_root) { x.src = a->src.info.buffer; x.src_bytes = blk * N; x.self_off = me * blk; if (!inplace) { x.dst = a->dst.info.buffer; x.pull_bytes[me] = blk; x.dst_off[me] = 0; } }
+        else { x.dst = a->dst.info.buffer; x.pull_off[a->root] = me * blk; x.pull_bytes[a->root] = blk; x.dst_off[a->root] = 0; }
+        moved = blk * N; break; }
+    case UCC_COLL_TYPE_SCATTERV: {
+        if (is_root ? !is_cuda(a->src.info_v.mem_type) || (!inplace && !is_cuda(a->dst.info.mem_type)) : !is_cuda(a->dst.info.mem_type)) return UCC_ERR_NOT_SUPPORTED;
+        if (is_root) {
+            size_t end = 0; dts = ucc_dt_size(a->src.info_v.datatype);
+            x.src = a->src.info_v.buffer; x.publish_table = 1;
+            for (ucc_rank_t p = 0; p < N; p++) { size_t so = ucc_coll_args_get_displacement(a, a->src.info_v.displacements, p) * dts, sc = ucc_coll_args_get_count(a, a->src.info_v.counts, p) * dts; x.stage_off[p] = so; if (so + sc > end) end = so + sc; }
+            x.src_bytes = end; x.self_off = x.stage_off[me]; moved = end;
+            if (!inplace) { x.dst = a->dst.info.buffer; x.pull_bytes[me] = ucc_coll_args_get_count(a, a->src.info_v.counts, me) * dts; x.dst_off[me] = 0; }
+        } else { x.dst = a->dst.info.buffer; x.pull_off[a->root] = NVL_XCHG_LOOKUP; x.pull_bytes[a->root] = a->dst.info.count * ucc_dt_size(a->dst.info.datatype); x.dst_off[a->root] = 0; moved = x.pull_bytes[a->root] * N; }
+        break; }
+    default: return UCC_ERR_NOT_SUPPORTED;
+    }
+    /* the staged payload must fit the heap (every rank evaluates the same bound for symmetric colls;
+     * v-variants that exceed it are rejected on the ranks that notice -> use a size hint via TUNE to avoid) */
+    if (x.src_bytes > cap) return UCC_ERR_NOT_SUPPORTED;
+    st = task_alloc(b, b_team, &t);
+    if (st != UCC_OK) return st;
+    t->kind = NVL_TASK_XCHG; t->u.xchg = x;
+    t->nblocks = pick_blocks(ctx, moved, 256 * 1024);
+    *task_p = &t->super;
+    return UCC_OK;
+}
+
+static ucc_status_t barrier_init(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, ucc_coll_task_t **task_p)
+{
+    ucc_tl_nvl_task_t *t;
+    ucc_status_t st = task_alloc(b, b_team, &t);
+    if (st != UCC_OK) return st;
+    t->kind = NVL_TASK_BARRIER; t->nblocks = 1;
+    *task_p = &t->super;
+    return UCC_OK;
+}
+
+/* ------------------------------------------------------------------ */
+/* algorithm table / scores                                            */
+/* ------------------------------------------------------------------ */
+typedef struct nvl_alg { const char *name; const char *desc; ucc_base_coll_init_fn_t init; } nvl_alg_t;
+static const nvl_alg_t algs_allreduce[] = {
+    {"twoshot", "stage + pull-reduce own slice over NVLink + push result to every peer, one kernel", red_init_twoshot},
+    {"oneshot", "push the whole vector to every peer and reduce locally (latency path, <= 64K)", red_init_oneshot},
+    {"nvls", "stage + multimem.ld_reduce / multimem.st through the NVSwitch (in-switch reduction)", red_init_nvls}, {NULL}};
+static const nvl_alg_t algs_red[] = {
+    {"twoshot", "stage + pull-reduce own slice over NVLink", red_init_twoshot},
+    {"nvls", "stage + multimem.ld_reduce own slice in the NVSwitch", red_init_nvls}, {NULL}};
+static const nvl_alg_t algs_xchg[] = {{"pull", "stage once, every peer pulls its part over NVLink", xchg_init}, {NULL}};
+static const nvl_alg_t algs_barrier[] = {{"flags", "flag exchange in peer memory", barrier_init}, {NULL}};
+static const nvl_alg_t *const nvl_algs[UCC_COLL_TYPE_NUM] = {
+    algs_xchg, algs_xchg, algs_allreduce, algs_xchg, algs_xchg, algs_barrier, algs_xchg, algs_barrier, algs_barrier,
+    algs_xchg, algs_xchg, algs_red, algs_red, algs_red, algs_xchg, algs_xchg};
+static ucc_base_coll_alg_info_t nvl_alg_info[UCC_COLL_TYPE_NUM][4];
+
+void ucc_tl_nvl_register_alg_info(void)
+{
+    for (int c = 0; c < UCC_COLL_TYPE_NUM; c++) {
+        int i;
+        for (i = 0; nvl_algs[c][i].name && i < 3; i++) { nvl_alg_info[c][i].id = (unsigned)i; nvl_alg_info[c][i].name = nvl_algs[c][i].name; nvl_alg_info[c][i].desc = nvl_algs[c][i].desc; }
+        nvl_alg_info[c][i].name = NULL;
+        ucc_tl_nvl.alg_info[c] = nvl_alg_info[c];
+    }
+}
+
+ucc_status_t ucc_tl_nvl_alg_id_to_init(int alg_id, const char *alg_id_str, ucc_coll_type_t coll_type, ucc_memory_type_t mem_type, ucc_base_coll_init_fn_t *init)
+{
+    int c = ucc_coll_type_index(coll_type), n = 0;
+    (void)mem_type;
+    while (nvl_algs[c][n].name) n++;
+    if (alg_id_str) { alg_id = -1; for (int i = 0; i < n; i++) if (!strcasecmp(alg_id_str, nvl_algs[c][i].name)) alg_id = i; }
+    if (alg_id < 0 || alg_id >= n) return alg_id_str ? UCC_ERR_NOT_SUPPORTED : UCC_ERR_INVALID_PARAM;
+    *init = nvl_algs[c][alg_id].init;
+    return UCC_OK;
+}
+
+ucc_status_t ucc_tl_nvl_coll_init(ucc_base_coll_args_t *b, ucc_base_team_t *team, ucc_coll_task_t **task)
+{ return nvl_algs[ucc_coll_type_index(b->args.coll_type)][0].init(b, team, task); }
+
+ucc_status_t ucc_tl_nvl_team_get_scores(ucc_base_team_t *b_team, ucc_coll_score_t **score_p)
+{
+    ucc_tl_nvl_team_t *team = ucc_derived_of(b_team, ucc_tl_nvl_team_t);
+    ucc_tl_nvl_context_t *ctx = NVL_CTX(team);
+    ucc_memory_type_t mt[1] = {UCC_MEMORY_TYPE_CUDA};
+    ucc_coll_score_team_info_t info = {UCC_TL_NVL_DEFAULT_SCORE, UCC_TL_TEAM_SIZE(team), UCC_TL_NVL_SUPPORTED_COLLS, mt, 1, ucc_tl_nvl_coll_init, ucc_tl_nvl_alg_id_to_init};
+    ucc_coll_score_t *score;
+    char sel[512], a[32], n[32];
+    ucc_status_t st = ucc_coll_score_build_default(b_team, UCC_TL_NVL_DEFAULT_SCORE, ucc_tl_nvl_coll_init, UCC_TL_NVL_SUPPORTED_COLLS, mt, 1, &score);
+    if (st != UCC_OK) return st;
+    ucc_memunits_to_str(ctx->cfg.oneshot_thresh, a, sizeof(a)); ucc_memunits_to_str(ctx->cfg.nvls_thresh, n, sizeof(n));
+    /* message-size driven defaults: latency kernel below the threshold, in-switch reduction for big
+     * messages when the multicast mapping is live (dt/op it cannot do fall back to twoshot through the
+     * score fallback chain because nvls init returns NOT_SUPPORTED) */
+    if (team->nvls) snprintf(sel, sizeof(sel), "allreduce:0-%s:@oneshot#allreduce:%s-inf:@nvls#reduce_scatter:%s-inf:@nvls#reduce_scatterv:%s-inf:@nvls#reduce:%s-inf:@nvls", a, n, n, n, n);
+    else snprintf(sel, sizeof(sel), "allreduce:0-%s:@oneshot", a);
+    st = ucc_tl_apply_tune(&team->super, score, &info, sel, ctx->cfg.super.super.score_str);
+    if (st != UCC_OK) { ucc_coll_score_free(score); return st; }
+    *score_p = score;
+    return UCC_OK;
+}

@@ -134,14 +134,16 @@ ucc_status_t ucc_tl_shm_bcast_dbt(ucc_tl_shm_task_t *t)
         return UCC_OK;
     }
     ucc_dbt_init(&dbt, vr - 1, N - 1);
+    /* one tree at a time: waiting for both parents before forwarding can dead-lock
+     * (x may be y's parent in one tree and y's child in the other) */
     for (int k = 0; k < 2; k++) {
         ucc_rank_t parent = dbt.parent[k] == UCC_RANK_INVALID ? root : (dbt.parent[k] + 1 + root) % N;
         CHK(shm_prog_recv(t, parent, k == 0 ? buf : buf + c1 * dts, (k == 0 ? c1 : c2) * dts, mt, 1 + (unsigned)k));
+        CHK(shm_prog_wait(t));
+        for (int c = 0; c < 2; c++) if (dbt.children[k][c] != UCC_RANK_INVALID)
+            CHK(shm_prog_send(t, (dbt.children[k][c] + 1 + root) % N, k == 0 ? buf : buf + c1 * dts, (k == 0 ? c1 : c2) * dts, mt, 1 + (unsigned)k));
+        CHK(shm_prog_wait(t));
     }
-    CHK(shm_prog_wait(t));
-    for (int k = 0; k < 2; k++) for (int c = 0; c < 2; c++) if (dbt.children[k][c] != UCC_RANK_INVALID)
-        CHK(shm_prog_send(t, (dbt.children[k][c] + 1 + root) % N, k == 0 ? buf : buf + c1 * dts, (k == 0 ? c1 : c2) * dts, mt, 1 + (unsigned)k));
-    CHK(shm_prog_wait(t));
 err:
     return st;
 }
@@ -160,9 +162,10 @@ static ucc_status_t prog_allreduce_knomial(ucc_tl_shm_task_t *t, void *acc, void
         CHK(shm_prog_recv(t, p.partner, acc, len, mt, step + 1)); CHK(shm_prog_wait(t));
         return UCC_OK;
     }
-    if (p.type == UCC_KN_NODE_PROXY) {
-        CHK(shm_prog_recv(t, p.partner, scratch, len, mt, step)); CHK(shm_prog_wait(t));
-        CHK(shm_prog_reduce(t, acc, acc, scratch, count, mt, 0));
+    if (p.type == UCC_KN_NODE_PROXY) { /* up to radix-1 extras fold their data into this rank first */
+        for (unsigned j = 0; j < p.n_extras; j++) CHK(shm_prog_recv(t, ucc_kn_extra(&p, j), OFF(scratch, j * len), len, mt, step));
+        CHK(shm_prog_wait(t));
+        for (unsigned j = 0; j < p.n_extras; j++) CHK(shm_prog_reduce(t, acc, acc, OFF(scratch, j * len), count, mt, 0));
     }
     step += 2;
     for (uint64_t dist = 1; dist < p.n_full; dist *= p.radix, step++) {
@@ -173,7 +176,10 @@ static ucc_status_t prog_allreduce_knomial(ucc_tl_shm_task_t *t, void *acc, void
         for (unsigned i = 0; i < n; i++) CHK(shm_prog_reduce(t, acc, acc, OFF(scratch, i * len), count, mt, 0));
     }
     if (t->op == UCC_OP_AVG) CHK(shm_prog_reduce(t, acc, acc, NULL, count, mt, 1));
-    if (p.type == UCC_KN_NODE_PROXY) { CHK(shm_prog_send(t, p.partner, acc, len, mt, step0 + 1)); CHK(shm_prog_wait(t)); }
+    if (p.type == UCC_KN_NODE_PROXY) {
+        for (unsigned j = 0; j < p.n_extras; j++) CHK(shm_prog_send(t, ucc_kn_extra(&p, j), acc, len, mt, step0 + 1));
+        CHK(shm_prog_wait(t));
+    }
 err:
     return st;
 }

@@ -45,6 +45,7 @@ ucc_status_t ucc_constructor(void)
     ucc_status_t st = UCC_OK;
     pthread_mutex_lock(&ucc_constructor_mutex);
     if (ucc_global_config.initialized) goto out;
+    { extern void ucc_debug_install_handlers(void); ucc_debug_install_handlers(); }
     st = ucc_config_parser_fill_opts_table(&ucc_global_config, ucc_global_config_table, "UCC_", "", 1);
     if (st != UCC_OK) { fprintf(stderr, "ucc: failed to parse global options\n"); goto out; }
     ucc_global_log_component.log_level = ucc_global_config.log_component.log_level;

@@ -1,4 +1,3 @@
-#define _GNU_SOURCE
 #include "ucc_sys.h"
 #include "ucc_log.h"
 #include "ucc_string.h"

@@ -1,0 +1,115 @@
+"""Every tl/shm algorithm forced through UCC_TL_SHM_TUNE (fresh job per algorithm, like the
+reference's algorithm-forced gtest variants, test/gtest/coll/test_allreduce.cc:290-660)."""
+import numpy as np
+import pytest
+
+from ucc_b200 import capi as U
+from ucc_b200.harness import UccJob, coll_args
+
+ALGS = {
+    "allreduce": ["knomial", "sra_knomial", "dbt", "ring"],
+    "allgather": ["knomial", "ring", "neighbor", "bruck", "sparbit", "linear", "batched"],
+    "allgatherv": ["ring", "knomial", "linear"],
+    "alltoall": ["pairwise", "bruck"],
+    "alltoallv": ["pairwise", "hybrid"],
+    "bcast": ["knomial", "sag_knomial", "dbt"],
+    "reduce": ["knomial", "dbt", "srg"],
+    "reduce_scatter": ["ring", "knomial"],
+    "gather": ["knomial", "linear"],
+    "scatter": ["knomial", "linear"],
+}
+SIZES = [2, 3, 4, 5, 6, 8, 11, 16]
+
+
+def run(team, args):
+    req = team.coll(args)
+    st = req.run()
+    req.finalize()
+    assert st == U.UCC_OK
+
+
+def check_coll(team, coll, n, count):
+    rng = np.random.default_rng(n * 1000 + count)
+    if coll == "allreduce":
+        for op in ("sum", "avg"):
+            src = [rng.random(count).astype(np.float64) for _ in range(n)]
+            dst = [np.zeros(count) for _ in range(n)]
+            run(team, [coll_args(coll, src[r], dst[r], dt="float64", op=op) for r in range(n)])
+            exp = np.sum(src, 0) / (n if op == "avg" else 1)
+            for r in range(n):
+                assert np.allclose(dst[r], exp), (r, op)
+    elif coll == "allgather":
+        src = [rng.integers(0, 1 << 30, count).astype(np.int32) for _ in range(n)]
+        dst = [np.zeros(count * n, np.int32) for _ in range(n)]
+        run(team, [coll_args(coll, src[r], dst[r], dt="int32") for r in range(n)])
+        for r in range(n):
+            assert np.array_equal(dst[r], np.concatenate(src)), r
+    elif coll == "allgatherv":
+        counts = [(count // 2) + r for r in range(n)]
+        displs = np.concatenate([[0], np.cumsum(counts)[:-1]])
+        src = [rng.integers(0, 100, counts[r]).astype(np.int32) for r in range(n)]
+        dst = [np.zeros(sum(counts), np.int32) for _ in range(n)]
+        run(team, [coll_args(coll, src[r], dst[r], dt="int32", dst_counts=counts, dst_displs=displs) for r in range(n)])
+        for r in range(n):
+            assert np.array_equal(dst[r], np.concatenate(src))
+    elif coll == "alltoall":
+        src = [rng.integers(0, 1 << 30, count * n).astype(np.int32) for _ in range(n)]
+        dst = [np.zeros(count * n, np.int32) for _ in range(n)]
+        run(team, [coll_args(coll, src[r], dst[r], dt="int32") for r in range(n)])
+        for r in range(n):
+            assert np.array_equal(dst[r], np.concatenate([src[p][r * count:(r + 1) * count] for p in range(n)])), r
+    elif coll == "alltoallv":
+        sc = [[(r + p) % 3 + 1 for p in range(n)] for r in range(n)]
+        rc = [[(p + r) % 3 + 1 for p in range(n)] for r in range(n)]
+        sd = [np.concatenate([[0], np.cumsum(c)[:-1]]) for c in sc]
+        rd = [np.concatenate([[0], np.cumsum(c)[:-1]]) for c in rc]
+        src = [rng.random(sum(sc[r])).astype(np.float32) for r in range(n)]
+        dst = [np.zeros(sum(rc[r]), np.float32) for r in range(n)]
+        run(team, [coll_args(coll, src[r], dst[r], src_counts=sc[r], src_displs=sd[r], dst_counts=rc[r], dst_displs=rd[r]) for r in range(n)])
+        for r in range(n):
+            assert np.array_equal(dst[r], np.concatenate([src[p][sd[p][r]:sd[p][r] + sc[p][r]] for p in range(n)]))
+    elif coll == "bcast":
+        for root in {0, n - 1, n // 2}:
+            bufs = [rng.random(count).astype(np.float32) if r == root else np.zeros(count, np.float32) for r in range(n)]
+            exp = bufs[root].copy()
+            run(team, [coll_args(coll, bufs[r], None, root=root) for r in range(n)])
+            for r in range(n):
+                assert np.array_equal(bufs[r], exp), (root, r)
+    elif coll == "reduce":
+        for root in {0, n - 1, n // 2}:
+            for op in ("sum", "avg"):
+                src = [rng.random(count) for _ in range(n)]
+                dst = np.zeros(count)
+                run(team, [coll_args(coll, src[r], dst if r == root else None, dt="float64", op=op, root=root, count_dst=count) for r in range(n)])
+                assert np.allclose(dst, np.sum(src, 0) / (n if op == "avg" else 1)), (root, op)
+    elif coll == "reduce_scatter":
+        src = [rng.random(count * n) for _ in range(n)]
+        dst = [np.zeros(count) for _ in range(n)]
+        run(team, [coll_args(coll, src[r], dst[r], dt="float64") for r in range(n)])
+        exp = np.sum(src, 0)
+        for r in range(n):
+            assert np.allclose(dst[r], exp[r * count:(r + 1) * count]), r
+    elif coll == "gather":
+        for root in {0, n - 1}:
+            src = [rng.integers(0, 1000, count).astype(np.int32) for _ in range(n)]
+            dst = np.zeros(count * n, np.int32)
+            run(team, [coll_args(coll, src[r], dst if r == root else None, dt="int32", root=root, count_dst=count * n) for r in range(n)])
+            assert np.array_equal(dst, np.concatenate(src)), root
+    elif coll == "scatter":
+        for root in {0, n - 1}:
+            big = rng.integers(0, 1000, count * n).astype(np.int32)
+            out = [np.zeros(count, np.int32) for _ in range(n)]
+            run(team, [coll_args(coll, big if r == root else None, out[r], dt="int32", root=root, count_src=count * n) for r in range(n)])
+            for r in range(n):
+                assert np.array_equal(out[r], big[r * count:(r + 1) * count]), (root, r)
+
+
+@pytest.mark.parametrize("coll,alg", [(c, a) for c, algs in ALGS.items() for a in algs])
+def test_forced_alg(coll, alg):
+    # score inf forces the algorithm; unsupported shapes fall back to the default via the fallback chain
+    with UccJob(16, env={"UCC_TL_SHM_TUNE": f"{coll}:inf:@{alg}"}) as job:
+        for n in SIZES:
+            team = job.create_team(range(n))
+            for count in (1, 24, 5000):
+                check_coll(team, coll, n, count)
+            team.destroy()

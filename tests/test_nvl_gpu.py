@@ -1,0 +1,272 @@
+"""tl/nvl kernels on a real GPU.  N emulated ranks share cuda:0 (one process, one stream per
+rank), so every kernel protocol (flags, epochs, slices, rounds) is exercised without needing
+several GPUs; the multi-GPU / multi-process path is covered by tests/test_dist_gpu.py.
+Numerics are compared against a plain PyTorch fp32/fp64 reference of the same op."""
+import os
+
+import numpy as np
+import pytest
+
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from ucc_b200 import capi as U  # noqa: E402
+from ucc_b200.harness import UccJob, coll_args  # noqa: E402
+
+CUDA = U.UCC_MEMORY_TYPE_CUDA
+TDT = {"float32": torch.float32, "float64": torch.float64, "float16": torch.float16, "bfloat16": torch.bfloat16,
+       "int32": torch.int32, "int64": torch.int64, "int8": torch.int8, "uint8": torch.uint8, "int16": torch.int16}
+ENV = {"UCC_TL_NVL_MAX_BLOCKS": "4", "UCC_TL_NVL_TIMEOUT": "5s", "UCC_TL_NVL_SYMMETRIC_SIZE": "8Mb"}
+
+
+def need_cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    torch.cuda.set_device(0)
+
+
+def cargs(coll, src, dst, dt, **kw):
+    return coll_args(coll, dt=dt, mem_type=CUDA, src_ptr=src.data_ptr() if src is not None else None,
+                     dst_ptr=dst.data_ptr() if dst is not None else None,
+                     count_src=src.numel() if src is not None else 0, count_dst=dst.numel() if dst is not None else 0, **kw)
+
+
+def run(team, args):
+    req = team.coll(args)
+    st = req.run()
+    req.finalize()
+    assert st == U.UCC_OK, U.status_str(st)
+    torch.cuda.synchronize()
+
+
+def gen(dt, n, seed):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    if TDT[dt].is_floating_point:
+        return (torch.rand(n, generator=g) + 0.5).to(TDT[dt]).cuda()
+    return torch.randint(1, 5, (n,), generator=g).to(TDT[dt]).cuda()
+
+
+def ref_reduce(op, xs):
+    a = torch.stack([x.double() if x.dtype.is_floating_point else x.long() for x in xs])
+    if op == "sum":
+        return a.sum(0)
+    if op == "avg":
+        return a.sum(0) / len(xs)
+    if op == "prod":
+        return a.prod(0)
+    if op == "max":
+        return a.max(0).values
+    if op == "min":
+        return a.min(0).values
+    raise ValueError(op)
+
+
+def assert_close(got, exp, dt):
+    if dt in ("bfloat16", "float16"):
+        assert torch.allclose(got.double(), exp.double(), rtol=2e-2, atol=2e-2)
+    elif TDT[dt].is_floating_point:
+        assert torch.allclose(got.double(), exp.double(), rtol=1e-5, atol=1e-6)
+    else:
+        assert torch.equal(got.long(), exp.long())
+
+
+@pytest.fixture(scope="module", params=["oneshot", "twoshot"])
+def alg_job(request):
+    need_cuda()
+    env = dict(ENV)
+    env["UCC_TL_NVL_TUNE"] = f"allreduce:cuda:inf:@{request.param}"
+    job = UccJob(8, env=env)
+    teams = {n: job.create_team(range(n)) for n in (2, 3, 4, 8)}
+    yield request.param, teams
+    job.cleanup()
+
+
+@pytest.mark.parametrize("n", [2, 3, 4, 8])
+@pytest.mark.parametrize("count", [1, 7, 1024, 4097, 16384])
+def test_allreduce_f32(alg_job, n, count):
+    alg, teams = alg_job
+    team = teams[n]
+    src = [gen("float32", count, r) for r in range(n)]
+    dst = [torch.zeros(count, device="cuda") for _ in range(n)]
+    run(team, [cargs("allreduce", src[r], dst[r], "float32") for r in range(n)])
+    exp = ref_reduce("sum", src)
+    for r in range(n):
+        assert_close(dst[r], exp, "float32")
+
+
+@pytest.mark.parametrize("dt,op", [("float32", "avg"), ("float64", "sum"), ("float16", "sum"), ("bfloat16", "sum"), ("bfloat16", "max"),
+                                   ("int32", "sum"), ("int64", "max"), ("int8", "min"), ("uint8", "sum"), ("int16", "prod")])
+def test_allreduce_dt_op(alg_job, dt, op):
+    alg, teams = alg_job
+    n, count = 4, 1000
+    team = teams[n]
+    src = [gen(dt, count, r + 11) for r in range(n)]
+    dst = [torch.zeros(count, dtype=TDT[dt], device="cuda") for _ in range(n)]
+    run(team, [cargs("allreduce", src[r], dst[r], dt, op=op) for r in range(n)])
+    exp = ref_reduce(op, src)
+    for r in range(n):
+        assert_close(dst[r], exp, dt)
+
+
+def test_allreduce_inplace_persistent_unaligned(alg_job):
+    alg, teams = alg_job
+    n, count = 4, 3001
+    team = teams[n]
+    base = [torch.zeros(count + 1, device="cuda") for _ in range(n)]
+    bufs = [b[1:] for b in base]  # 4-byte aligned only
+    req = team.coll([cargs("allreduce", None, bufs[r], "float32", inplace=True, persistent=True) for r in range(n)])
+    for it in range(3):
+        src = [gen("float32", count, 10 * it + r) for r in range(n)]
+        for r in range(n):
+            bufs[r].copy_(src[r])
+        torch.cuda.synchronize()
+        assert req.run() == U.UCC_OK
+        torch.cuda.synchronize()
+        exp = ref_reduce("sum", src)
+        for r in range(n):
+            assert_close(bufs[r], exp, "float32")
+    req.finalize()
+
+
+@pytest.fixture(scope="module")
+def job():
+    need_cuda()
+    j = UccJob(8, env=ENV)
+    teams = {n: j.create_team(range(n)) for n in (2, 3, 4, 8)}
+    yield teams
+    j.cleanup()
+
+
+@pytest.mark.parametrize("n", [2, 4, 8])
+def test_allreduce_multi_round(job, n):
+    # 8 MB heap / n ranks => several rounds inside one kernel
+    team = job[n]
+    count = 5 * 1024 * 1024 + 13
+    src = [gen("float32", count, r) for r in range(n)]
+    dst = [torch.zeros(count, device="cuda") for _ in range(n)]
+    run(team, [cargs("allreduce", src[r], dst[r], "float32") for r in range(n)])
+    exp = ref_reduce("sum", src)
+    for r in range(n):
+        assert_close(dst[r], exp, "float32")
+
+
+@pytest.mark.parametrize("n", [2, 3, 8])
+@pytest.mark.parametrize("inplace", [False, True])
+def test_reduce_scatter(job, n, inplace):
+    team = job[n]
+    blk = 1237
+    src = [gen("float32", blk * n, r) for r in range(n)]
+    exp = ref_reduce("sum", src)
+    if inplace:
+        bufs = [s.clone() for s in src]
+        run(team, [cargs("reduce_scatter", None, bufs[r], "float32", inplace=True) for r in range(n)])
+        for r in range(n):
+            assert_close(bufs[r][r * blk:(r + 1) * blk], exp[r * blk:(r + 1) * blk], "float32")
+    else:
+        dst = [torch.zeros(blk, device="cuda") for _ in range(n)]
+        run(team, [cargs("reduce_scatter", src[r], dst[r], "float32") for r in range(n)])
+        for r in range(n):
+            assert_close(dst[r], exp[r * blk:(r + 1) * blk], "float32")
+
+
+@pytest.mark.parametrize("n", [2, 4])
+def test_reduce_scatterv(job, n):
+    team = job[n]
+    counts = [100 + 33 * r for r in range(n)]
+    offs = np.concatenate([[0], np.cumsum(counts)[:-1]])
+    src = [gen("int32", sum(counts), r) for r in range(n)]
+    dst = [torch.zeros(counts[r], dtype=torch.int32, device="cuda") for r in range(n)]
+    run(team, [cargs("reduce_scatterv", src[r], dst[r], "int32", dst_counts=counts, dst_displs=offs) for r in range(n)])
+    exp = ref_reduce("sum", src)
+    for r in range(n):
+        assert_close(dst[r], exp[offs[r]:offs[r] + counts[r]], "int32")
+
+
+@pytest.mark.parametrize("n", [2, 4, 8])
+def test_reduce(job, n):
+    team = job[n]
+    count = 5000
+    for root in {0, n - 1}:
+        src = [gen("float32", count, r) for r in range(n)]
+        dst = torch.zeros(count, device="cuda")
+        run(team, [cargs("reduce", src[r], dst if r == root else None, "float32", root=root, count_dst=count) for r in range(n)])
+        assert_close(dst, ref_reduce("sum", src), "float32")
+
+
+@pytest.mark.parametrize("n", [2, 3, 8])
+@pytest.mark.parametrize("count", [1, 1000, 100001])
+def test_allgather(job, n, count):
+    team = job[n]
+    src = [gen("int32", count, r) for r in range(n)]
+    dst = [torch.zeros(count * n, dtype=torch.int32, device="cuda") for _ in range(n)]
+    run(team, [cargs("allgather", src[r], dst[r], "int32") for r in range(n)])
+    exp = torch.cat(src)
+    for r in range(n):
+        assert torch.equal(dst[r], exp)
+
+
+@pytest.mark.parametrize("n", [2, 4])
+def test_allgatherv(job, n):
+    team = job[n]
+    counts = [5 + 1000 * r for r in range(n)]
+    displs = np.concatenate([[0], np.cumsum(counts)[:-1]])
+    src = [gen("float32", counts[r], r) for r in range(n)]
+    dst = [torch.zeros(sum(counts), device="cuda") for _ in range(n)]
+    run(team, [cargs("allgatherv", src[r], dst[r], "float32", dst_counts=counts, dst_displs=displs) for r in range(n)])
+    for r in range(n):
+        assert torch.equal(dst[r], torch.cat(src))
+
+
+@pytest.mark.parametrize("n", [2, 3, 8])
+@pytest.mark.parametrize("count", [1, 333, 20000])
+def test_alltoall(job, n, count):
+    team = job[n]
+    src = [gen("float32", count * n, r) for r in range(n)]
+    dst = [torch.zeros(count * n, device="cuda") for _ in range(n)]
+    run(team, [cargs("alltoall", src[r], dst[r], "float32") for r in range(n)])
+    for r in range(n):
+        exp = torch.cat([src[p][r * count:(r + 1) * count] for p in range(n)])
+        assert torch.equal(dst[r], exp)
+
+
+@pytest.mark.parametrize("n", [2, 4, 8])
+def test_alltoallv_moe_skew(job, n):
+    team = job[n]
+    rng = np.random.default_rng(n)
+    # token-routing style skew: a few hot experts
+    m = rng.integers(0, 50, size=(n, n))
+    m[:, 0] += 400
+    sc = [list(m[r]) for r in range(n)]
+    rc = [list(m[:, r]) for r in range(n)]
+    sd = [np.concatenate([[0], np.cumsum(c)[:-1]]) for c in sc]
+    rd = [np.concatenate([[0], np.cumsum(c)[:-1]]) for c in rc]
+    src = [gen("bfloat16", int(sum(sc[r])), r) for r in range(n)]
+    dst = [torch.zeros(int(sum(rc[r])), dtype=torch.bfloat16, device="cuda") for r in range(n)]
+    run(team, [cargs("alltoallv", src[r], dst[r], "bfloat16", src_counts=sc[r], src_displs=sd[r], dst_counts=rc[r], dst_displs=rd[r]) for r in range(n)])
+    for r in range(n):
+        exp = torch.cat([src[p][sd[p][r]:sd[p][r] + sc[p][r]] for p in range(n)])
+        assert torch.equal(dst[r], exp)
+
+
+@pytest.mark.parametrize("n", [2, 4, 8])
+def test_bcast_gather_scatter_barrier(job, n):
+    team = job[n]
+    count = 7777
+    for root in {0, n - 1}:
+        bufs = [gen("float32", count, r) if r == root else torch.zeros(count, device="cuda") for r in range(n)]
+        exp = bufs[root].clone()
+        run(team, [cargs("bcast", bufs[r], None, "float32", root=root) for r in range(n)])
+        for r in range(n):
+            assert torch.equal(bufs[r], exp)
+        src = [gen("int32", 100, r) for r in range(n)]
+        dst = torch.zeros(100 * n, dtype=torch.int32, device="cuda")
+        run(team, [cargs("gather", src[r], dst if r == root else None, "int32", root=root, count_dst=100 * n) for r in range(n)])
+        assert torch.equal(dst, torch.cat(src))
+        big = gen("int32", 100 * n, 5)
+        out = [torch.zeros(100, dtype=torch.int32, device="cuda") for _ in range(n)]
+        run(team, [cargs("scatter", big if r == root else None, out[r], "int32", root=root, count_src=100 * n) for r in range(n)])
+        for r in range(n):
+            assert torch.equal(out[r], big[r * 100:(r + 1) * 100])
+    run(team, [coll_args("barrier") for _ in range(n)])

@@ -341,8 +341,11 @@ class UccJob:
     def __enter__(self):
         return self
 
-    def __exit__(self, *a):
-        self.cleanup()
+    def __exit__(self, exc_type, *a):
+        # after a failed test requests may still be in flight: tearing teams down under them
+        # would turn the assertion into a crash, so leak the job instead
+        if exc_type is None:
+            self.cleanup()
 
 
 # ----------------------------------------------------------------- args builders
