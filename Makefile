@@ -15,7 +15,7 @@ BUILD   := build
 CFLAGS  := -O2 -g -std=gnu11 -fPIC -Wall -Wextra -Wno-unused-parameter -Wno-missing-field-initializers -Wno-sign-compare \
            -Iinclude -Isrc -D_GNU_SOURCE $(EXTRA_CFLAGS)
 LDFLAGS := -shared -Wl,--no-undefined -lpthread -ldl -lrt -lm
-NVFLAGS := -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC \
+NVFLAGS := -O3 -std=c++17 --extended-lambda -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC \
            -Iinclude -Isrc -D_GNU_SOURCE --expt-relaxed-constexpr $(EXTRA_NVFLAGS)
 CUDA_LIBS := -L$(CUDA_HOME)/lib64 -lcudart -Xlinker -rpath,$(CUDA_HOME)/lib64
 

@@ -1,0 +1,70 @@
+"""Worker run under torchrun by test_dist_*.py: multi-process collectives through ucc_b200.dist."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from ucc_b200 import capi as U  # noqa: E402
+from ucc_b200.dist import Communicator, init_distributed  # noqa: E402
+
+
+def main():
+    use_cuda = len(sys.argv) > 1 and sys.argv[1] == "cuda"
+    rank, world, lrank = init_distributed("cpu:gloo,cuda:nccl" if use_cuda else "gloo")
+    dev = torch.device("cuda", torch.cuda.current_device()) if use_cuda else torch.device("cpu")
+    comm = Communicator()
+    ok = True
+    for count in (1, 1000, 100000, 3000001):
+        for dt in (torch.float32, torch.bfloat16, torch.int32):
+            g = torch.Generator().manual_seed(1234 + count)
+            alls = [(torch.rand(count, generator=g) * 4 + r).to(dt) for r in range(world)]
+            src = alls[rank].to(dev)
+            dst = torch.zeros(count, dtype=dt, device=dev)
+            req = comm.allreduce_init(src, dst)
+            if use_cuda:
+                req.post_on_stream()
+            else:
+                req.post()
+            req.wait()
+            req.finalize()
+            if use_cuda:
+                torch.cuda.synchronize()
+            exp = sum(a.double() for a in alls)
+            tol = 2e-2 * world if dt == torch.bfloat16 else 1e-5
+            if not torch.allclose(dst.cpu().double(), exp, rtol=tol, atol=tol):
+                print(f"rank {rank}: allreduce mismatch count {count} dt {dt}", flush=True)
+                ok = False
+    # allgather + alltoall + bcast + reduce_scatter
+    blk = 1000
+    src = torch.full((blk,), float(rank), device=dev)
+    dst = torch.zeros(blk * world, device=dev)
+    comm.run(comm.coll_init("allgather", src, dst))
+    if use_cuda:
+        torch.cuda.synchronize()
+    ok &= bool((dst.view(world, blk).cpu() == torch.arange(world, dtype=torch.float32)[:, None]).all())
+    src = torch.arange(blk * world, dtype=torch.float32, device=dev) + 1000 * rank
+    dst = torch.zeros(blk * world, device=dev)
+    comm.run(comm.coll_init("alltoall", src, dst))
+    exp = torch.cat([torch.arange(rank * blk, (rank + 1) * blk, dtype=torch.float32) + 1000 * p for p in range(world)])
+    ok &= bool(torch.equal(dst.cpu(), exp))
+    b = torch.full((5000,), 7.0 if rank == 0 else 0.0, device=dev)
+    comm.run(comm.coll_init("bcast", b, None, root=0))
+    ok &= bool((b.cpu() == 7.0).all())
+    src = torch.ones(blk * world, device=dev) * (rank + 1)
+    dst = torch.zeros(blk, device=dev)
+    comm.run(comm.coll_init("reduce_scatter", src, dst))
+    ok &= bool((dst.cpu() == world * (world + 1) / 2).all())
+    comm.barrier()
+    flag = torch.tensor([1 if ok else 0])
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    comm.destroy()
+    if rank == 0:
+        print("DIST_WORKER_OK" if flag.item() == 1 else "DIST_WORKER_FAIL", flush=True)
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()

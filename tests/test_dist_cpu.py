@@ -1,0 +1,18 @@
+"""Multi-process (gloo bootstrap, world_size 2 and 3) host collectives through ucc_b200.dist."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("n", [2, 3])
+def test_torchrun_host(n):
+    port = 29600 + n
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tests", "dist_worker.py"), "cpu"]
+    env = dict(os.environ, PYTHONPATH=ROOT, CUDA_VISIBLE_DEVICES="")
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert "DIST_WORKER_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]

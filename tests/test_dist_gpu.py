@@ -1,0 +1,41 @@
+"""Multi-process, one process per GPU: VMM heap exchange, NVLS binding and the fused kernels over real NVLink."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+torch = pytest.importorskip("torch")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+
+def _run(n, extra_env=None):
+    port = 29700 + n
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tests", "dist_worker.py"), "cuda"]
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    env.update(extra_env or {})
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+    assert "DIST_WORKER_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+
+
+def test_multiproc_all_gpus():
+    n = torch.cuda.device_count() if torch.cuda.is_available() else 0
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    _run(n)
+
+
+def test_multiproc_no_nvls():
+    n = torch.cuda.device_count() if torch.cuda.is_available() else 0
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    _run(n, {"UCC_TL_NVL_USE_NVLS": "n"})
+
+
+def test_multiproc_ipc_heap():
+    n = torch.cuda.device_count() if torch.cuda.is_available() else 0
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    _run(n, {"UCC_TL_NVL_USE_VMM": "n"})

@@ -28,9 +28,10 @@ def need_cuda():
 
 
 def cargs(coll, src, dst, dt, **kw):
+    kw.setdefault("count_src", src.numel() if src is not None else 0)
+    kw.setdefault("count_dst", dst.numel() if dst is not None else 0)
     return coll_args(coll, dt=dt, mem_type=CUDA, src_ptr=src.data_ptr() if src is not None else None,
-                     dst_ptr=dst.data_ptr() if dst is not None else None,
-                     count_src=src.numel() if src is not None else 0, count_dst=dst.numel() if dst is not None else 0, **kw)
+                     dst_ptr=dst.data_ptr() if dst is not None else None, **kw)
 
 
 def run(team, args):

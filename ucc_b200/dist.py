@@ -1,0 +1,218 @@
+"""One process per GPU: library / context / team bootstrap on top of torch.distributed.
+
+torch.distributed (gloo) only provides the out-of-band allgather used for wire-up, exactly the role
+MPI plays for the reference's ucc_perftest (tools/perf/ucc_pt_bootstrap_mpi.cc).  All collectives
+then run through libucc: tl/nvl kernels over NVLink for CUDA tensors, tl/shm for host tensors.
+"""
+import ctypes as C
+import itertools
+import os
+
+import torch
+import torch.distributed as dist
+
+from . import capi as U
+
+_TORCH_DT = {torch.int8: "int8", torch.int16: "int16", torch.int32: "int32", torch.int64: "int64", torch.uint8: "uint8",
+             torch.float16: "float16", torch.float32: "float32", torch.float64: "float64", torch.bfloat16: "bfloat16",
+             torch.complex64: "float32_complex", torch.complex128: "float64_complex"}
+for _n, _t in (("uint16", "uint16"), ("uint32", "uint32"), ("uint64", "uint64")):
+    if hasattr(torch, _n):
+        _TORCH_DT[getattr(torch, _n)] = _t
+
+
+def dt_of(t):
+    return _TORCH_DT[t.dtype]
+
+
+def mem_type_of(t):
+    return U.UCC_MEMORY_TYPE_CUDA if t.is_cuda else U.UCC_MEMORY_TYPE_HOST
+
+
+class _TorchOob:
+    """ucc_oob_coll_t whose allgather is a (blocking) gloo all_gather."""
+    _ids = itertools.count(1)
+
+    def __init__(self, group, rank, size):
+        self.group, self.rank, self.size = group, rank, size
+
+        def allgather(src, recv, nbytes, info, req_pp):
+            mine = torch.frombuffer(bytearray(C.string_at(src, nbytes)), dtype=torch.uint8).clone()
+            outs = [torch.empty(nbytes, dtype=torch.uint8) for _ in range(self.size)]
+            dist.all_gather(outs, mine, group=self.group)
+            flat = torch.cat(outs).contiguous()
+            C.memmove(recv, flat.data_ptr(), nbytes * self.size)
+            req_pp[0] = next(_TorchOob._ids)
+            return U.UCC_OK
+
+        self._ag = U.OOB_ALLGATHER_FN(allgather)
+        self._test = U.OOB_REQ_FN(lambda req: U.UCC_OK)
+        self._free = U.OOB_REQ_FN(lambda req: U.UCC_OK)
+
+    def struct(self):
+        o = U.ucc_oob_coll_t()
+        o.allgather, o.req_test, o.req_free = self._ag, self._test, self._free
+        o.coll_info = None
+        o.n_oob_eps, o.oob_ep = self.size, self.rank
+        return o
+
+
+class Request:
+    def __init__(self, comm, req, keep):
+        self.comm, self.req, self._keep = comm, req, keep
+
+    def post(self):
+        U.check(U.ucc_collective_post(self.req), "collective_post")
+        return self
+
+    def post_on_stream(self, stream=None):
+        """Stream-ordered post: the collective kernel is enqueued on `stream` (default: current)."""
+        ev = U.ucc_ev_t()
+        ev.ev_type = U.UCC_EVENT_COMPUTE_COMPLETE
+        ev.req = C.cast(self.req, C.c_void_p)
+        U.check(U.ucc_collective_triggered_post(self.comm.ee_for(stream), C.byref(ev)), "triggered_post")
+        return self
+
+    def test(self):
+        return self.req.contents.status
+
+    def wait(self):
+        while True:
+            st = self.req.contents.status
+            if st == U.UCC_OK:
+                return
+            if st < 0:
+                raise U.UccError(st, "collective")
+            U.ucc_context_progress(self.comm.ctx)
+
+    def finalize(self):
+        self.comm.drain_events()
+        U.check(U.ucc_collective_finalize(self.req), "collective_finalize")
+        self.req = None
+
+
+class Communicator:
+    """lib + context + one team spanning `group` (default: all ranks)."""
+
+    def __init__(self, group=None, thread_mode=U.UCC_THREAD_SINGLE, lib_modify=(), ctx_modify=()):
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed must be initialised (gloo is enough)")
+        self.rank = dist.get_rank(group)
+        self.size = dist.get_world_size(group)
+        self.oob = _TorchOob(group, self.rank, self.size)
+        cfg = U.handle()
+        U.check(U.ucc_lib_config_read(None, None, C.byref(cfg)), "lib_config_read")
+        for k, v in lib_modify:
+            U.check(U.ucc_lib_config_modify(cfg, k.encode(), v.encode()), "lib_config_modify")
+        p = U.ucc_lib_params_t()
+        p.mask, p.thread_mode = U.UCC_LIB_PARAM_FIELD_THREAD_MODE, thread_mode
+        self.lib = U.handle()
+        st = U.ucc_init_version(U.UCC_API_MAJOR, U.UCC_API_MINOR, C.byref(p), cfg, C.byref(self.lib))
+        U.ucc_lib_config_release(cfg)
+        U.check(st, "ucc_init")
+        ccfg = U.handle()
+        U.check(U.ucc_context_config_read(self.lib, None, C.byref(ccfg)), "context_config_read")
+        for comp, name, val in ctx_modify:
+            U.check(U.ucc_context_config_modify(ccfg, comp.encode() if comp else None, name.encode(), val.encode()), "ctx_modify")
+        cp = U.ucc_context_params_t()
+        if self.size > 1:
+            cp.mask = U.UCC_CONTEXT_PARAM_FIELD_OOB
+            cp.oob = self.oob.struct()
+        self.ctx = U.handle()
+        st = U.ucc_context_create(self.lib, C.byref(cp), ccfg, C.byref(self.ctx))
+        U.ucc_context_config_release(ccfg)
+        U.check(st, "context_create")
+        tp = U.ucc_team_params_t()
+        tp.mask = U.UCC_TEAM_PARAM_FIELD_EP | U.UCC_TEAM_PARAM_FIELD_EP_RANGE | U.UCC_TEAM_PARAM_FIELD_OOB
+        tp.ep, tp.ep_range = self.rank, U.UCC_COLLECTIVE_EP_RANGE_CONTIG
+        tp.oob = self.oob.struct()
+        self.team = U.handle()
+        ctxs = (U.handle * 1)(self.ctx)
+        U.check(U.ucc_team_create_post(ctxs, 1, C.byref(tp), C.byref(self.team)), "team_create_post")
+        while True:
+            st = U.ucc_team_create_test(self.team)
+            if st == U.UCC_OK:
+                break
+            U.check(st, "team_create_test")
+            U.ucc_context_progress(self.ctx)
+        self._ees = {}
+
+    # ------------------------------------------------------------------ streams
+    def ee_for(self, stream=None):
+        s = stream if stream is not None else torch.cuda.current_stream()
+        key = s.cuda_stream
+        if key not in self._ees:
+            ep = U.ucc_ee_params_t()
+            ep.ee_type, ep.ee_context, ep.ee_context_size = U.UCC_EE_CUDA_STREAM, key, C.sizeof(C.c_void_p)
+            ee = U.handle()
+            U.check(U.ucc_ee_create(self.team, C.byref(ep), C.byref(ee)), "ee_create")
+            self._ees[key] = ee
+        return self._ees[key]
+
+    def drain_events(self):
+        for ee in self._ees.values():
+            ev = C.POINTER(U.ucc_ev_t)()
+            while U.ucc_ee_get_event(ee, C.byref(ev)) == U.UCC_OK:
+                U.ucc_ee_ack_event(ee, ev)
+
+    def progress(self):
+        U.ucc_context_progress(self.ctx)
+
+    # ------------------------------------------------------------------ collectives
+    def init(self, args):
+        r = C.POINTER(U.ucc_coll_req_t)()
+        U.check(U.ucc_collective_init(C.byref(args), C.byref(r), self.team), "collective_init")
+        return Request(self, r, args)
+
+    def _args(self, coll, src=None, dst=None, op="sum", root=0, inplace=False, persistent=False, **kw):
+        from .harness import coll_args
+        ref = dst if dst is not None else src
+        if ref is None:  # barrier / fanin / fanout
+            return coll_args(coll, root=root, persistent=persistent)
+        return coll_args(coll, dt=dt_of(ref), op=op, root=root, inplace=inplace, persistent=persistent,
+                         src_ptr=src.data_ptr() if src is not None else None, dst_ptr=dst.data_ptr() if dst is not None else None,
+                         count_src=src.numel() if src is not None else 0, count_dst=dst.numel() if dst is not None else 0,
+                         mem_type=mem_type_of(ref), **kw)
+
+    def allreduce_init(self, src, dst, op="sum", persistent=False):
+        inplace = src is None or src.data_ptr() == dst.data_ptr()
+        return self.init(self._args("allreduce", None if inplace else src, dst, op=op, inplace=inplace, persistent=persistent))
+
+    def coll_init(self, coll, src=None, dst=None, **kw):
+        return self.init(self._args(coll, src, dst, **kw))
+
+    def run(self, req, stream=None):
+        """Convenience: post, wait (host), finalize."""
+        (req.post_on_stream(stream) if stream is not None else req.post()).wait()
+        req.finalize()
+
+    def barrier(self):
+        self.run(self.coll_init("barrier"))
+
+    def destroy(self):
+        for ee in self._ees.values():
+            U.ucc_ee_destroy(ee)
+        self._ees = {}
+        while True:
+            st = U.ucc_team_destroy(self.team)
+            if st != U.UCC_INPROGRESS:
+                break
+            U.ucc_context_progress(self.ctx)
+        U.ucc_context_destroy(self.ctx)
+        U.ucc_finalize(self.lib)
+
+
+def init_distributed(backend="cpu:gloo,cuda:nccl"):
+    """Initialise torch.distributed from the torchrun environment and bind this rank's GPU."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    lrank = int(os.environ.get("LOCAL_RANK", str(rank)))
+    if torch.cuda.is_available():
+        torch.cuda.set_device(lrank % torch.cuda.device_count())
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29555")
+    if not dist.is_initialized():
+        if not torch.cuda.is_available():
+            backend = "gloo"
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, world, lrank
