@@ -104,3 +104,4 @@ clean:
 	rm -rf $(BUILD) $(OUT) $(BINDIR)
 
 -include $(CORE_OBJS:.o=.d)
+-include $(shell find $(BUILD) -name '*.d' 2>/dev/null)

@@ -69,7 +69,11 @@ static ucc_config_field_t tl_nccl_context_config_table[] = {
 static ucc_status_t load_nccl(void)
 {
     if (nc.h) return UCC_OK;
-    nc.h = dlopen("libnccl.so.2", RTLD_LAZY | RTLD_GLOBAL);
+    /* never pull a second NCCL into a process that will load its own (PyTorch bundles one with the same
+     * soname): use the copy that is already mapped, else an explicit override, else the system library */
+    nc.h = dlopen("libnccl.so.2", RTLD_LAZY | RTLD_NOLOAD);
+    if (!nc.h && getenv("UCC_TL_NCCL_LIB")) nc.h = dlopen(getenv("UCC_TL_NCCL_LIB"), RTLD_LAZY | RTLD_LOCAL);
+    if (!nc.h && !getenv("UCC_TL_NCCL_NO_SYSTEM_LIB")) nc.h = dlopen("libnccl.so.2", RTLD_LAZY | RTLD_LOCAL);
     if (!nc.h) return UCC_ERR_NO_RESOURCE;
 #define SYM(_f) *(void **)&nc._f = dlsym(nc.h, "nccl" #_f)
     SYM(GetUniqueId); SYM(CommInitRank); SYM(CommDestroy); SYM(CommAbort); SYM(CommGetAsyncError); SYM(GetErrorString); SYM(AllReduce); SYM(Broadcast);

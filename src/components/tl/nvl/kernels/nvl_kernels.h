@@ -13,8 +13,8 @@
 #include <cuda_runtime_api.h>
 
 #define NVL_MAX_PEERS  16
-#define NVL_MAX_BLOCKS 128
-#define NVL_LL_MAX     (64 * 1024)          /* bytes per rank in the one-shot (latency) region */
+#define NVL_MAX_BLOCKS 320
+#define NVL_LL_MAX     (512 * 1024)          /* bytes per rank in the one-shot (latency) region */
 
 /* control block at offset 0 of every rank's heap */
 typedef struct nvl_ctrl {
@@ -30,7 +30,7 @@ typedef struct nvl_ctrl {
     uint64_t mc_epoch[NVL_MAX_BLOCKS];
 } nvl_ctrl_t;
 
-#define NVL_CTRL_SIZE  (64 * 1024)
+#define NVL_CTRL_SIZE  (128 * 1024)
 #define NVL_LL_OFFSET  NVL_CTRL_SIZE
 #define NVL_LL_SIZE    (2 * NVL_MAX_PEERS * NVL_LL_MAX)
 #define NVL_DATA_OFFSET (NVL_LL_OFFSET + NVL_LL_SIZE)

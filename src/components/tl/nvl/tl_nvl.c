@@ -11,7 +11,7 @@ ucc_config_field_t ucc_tl_nvl_context_config_table[] = {
     {"SYMMETRIC_SIZE", "128Mb", "Size of the data region of the per-team symmetric heap; larger messages are processed in rounds inside one kernel",
      ucc_offsetof(ucc_tl_nvl_context_config_t, symmetric_size), UCC_CONFIG_TYPE_MEMUNITS},
     {"NBLOCKS", "auto", "Thread blocks per collective kernel (auto: chosen from the message size)", ucc_offsetof(ucc_tl_nvl_context_config_t, nblocks), UCC_CONFIG_TYPE_UINT},
-    {"MAX_BLOCKS", "32", "Upper bound of thread blocks per collective kernel (all blocks of all ranks sharing a GPU must be co-resident)",
+    {"MAX_BLOCKS", "128", "Upper bound of thread blocks per collective kernel (all blocks of all ranks sharing a GPU must be co-resident)",
      ucc_offsetof(ucc_tl_nvl_context_config_t, max_blocks), UCC_CONFIG_TYPE_UINT},
     {"NTHREADS", "512", "Threads per block", ucc_offsetof(ucc_tl_nvl_context_config_t, nthreads), UCC_CONFIG_TYPE_UINT},
     {"TIMEOUT", "10s", "Spin budget of a device-side wait before the kernel gives up and the collective fails with UCC_ERR_TIMED_OUT",
@@ -19,8 +19,8 @@ ucc_config_field_t ucc_tl_nvl_context_config_table[] = {
     {"USE_NVLS", "try", "Use NVSwitch multicast / in-switch reduction (multimem.*) when the fabric supports it", ucc_offsetof(ucc_tl_nvl_context_config_t, use_nvls), UCC_CONFIG_TYPE_TERNARY},
     {"USE_VMM", "try", "Allocate the heap with the CUDA virtual memory management API and share it as a POSIX fd (required for NVLS); otherwise cudaMalloc + cudaIpc",
      ucc_offsetof(ucc_tl_nvl_context_config_t, use_vmm), UCC_CONFIG_TYPE_TERNARY},
-    {"ALLREDUCE_ONESHOT_THRESH", "32K", "Allreduce messages up to this size use the one-shot push kernel", ucc_offsetof(ucc_tl_nvl_context_config_t, oneshot_thresh), UCC_CONFIG_TYPE_MEMUNITS},
-    {"ALLREDUCE_NVLS_THRESH", "256K", "Allreduce messages of at least this size use NVLS when available", ucc_offsetof(ucc_tl_nvl_context_config_t, nvls_thresh), UCC_CONFIG_TYPE_MEMUNITS},
+    {"ALLREDUCE_ONESHOT_THRESH", "256K", "Allreduce messages up to this size use the one-shot push kernel", ucc_offsetof(ucc_tl_nvl_context_config_t, oneshot_thresh), UCC_CONFIG_TYPE_MEMUNITS},
+    {"ALLREDUCE_NVLS_THRESH", "512K", "Allreduce messages of at least this size use NVLS when available", ucc_offsetof(ucc_tl_nvl_context_config_t, nvls_thresh), UCC_CONFIG_TYPE_MEMUNITS},
     {"FD_VIA_PIDFD", "try", "Fetch peers' memory handles with pidfd_getfd before falling back to a unix socket", ucc_offsetof(ucc_tl_nvl_context_config_t, fd_via_pidfd), UCC_CONFIG_TYPE_TERNARY},
     {NULL}};
 

@@ -187,8 +187,8 @@ static ucc_status_t red_init(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, u
           if (inplace) r->dst = (char *)dst + r->rs_offset[me] * ucc_dt_size(dt); }
         break;
     }
-    if (alg == RED_ALG_ONESHOT) { t->kind = NVL_TASK_REDUCE_ONESHOT; t->nblocks = pick_blocks(ctx, bytes, 8192); if (t->nblocks > 8) t->nblocks = ucc_min(8u, ctx->cfg.max_blocks); }
-    else { t->kind = NVL_TASK_REDUCE_STAGED; t->nblocks = pick_blocks(ctx, bytes, 128 * 1024); }
+    if (alg == RED_ALG_ONESHOT) { t->kind = NVL_TASK_REDUCE_ONESHOT; t->nblocks = pick_blocks(ctx, bytes, 16384); if (t->nblocks > 32) t->nblocks = 32; }
+    else { t->kind = NVL_TASK_REDUCE_STAGED; t->nblocks = pick_blocks(ctx, bytes, 32 * 1024); }
     *task_p = &t->super;
     return UCC_OK;
 }
@@ -294,7 +294,7 @@ static ucc_status_t xchg_init(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, 
     st = task_alloc(b, b_team, &t);
     if (st != UCC_OK) return st;
     t->kind = NVL_TASK_XCHG; t->u.xchg = x;
-    t->nblocks = pick_blocks(ctx, moved, 256 * 1024);
+    t->nblocks = pick_blocks(ctx, moved, 64 * 1024);
     *task_p = &t->super;
     return UCC_OK;
 }

@@ -12,6 +12,12 @@ LIB_PATH = os.path.join(_HERE, "lib", "libucc.so")
 
 
 def _load():
+    # PyTorch ships its own libnccl.so.2; let it map that copy first so the tl/nccl plugin re-uses it instead
+    # of mapping the (older) system NCCL under the same soname
+    try:
+        import torch  # noqa: F401
+    except Exception:
+        pass
     if not os.path.exists(LIB_PATH):
         raise ImportError(
             f"{LIB_PATH} is missing: build it with `make -C {os.path.dirname(_HERE)}` "
