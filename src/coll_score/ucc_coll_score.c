@@ -503,10 +503,9 @@ ucc_status_t ucc_coll_score_build_map(ucc_coll_score_t *score, ucc_score_map_t *
 }
 void ucc_coll_score_free_map(ucc_score_map_t *map) { if (!map) return; ucc_coll_score_free(map->score); free(map); }
 
-ucc_status_t ucc_coll_score_map_lookup(ucc_score_map_t *map, ucc_base_coll_args_t *bargs, ucc_msg_range_t **range)
+static ucc_status_t map_lookup_as(ucc_score_map_t *map, ucc_base_coll_args_t *bargs, ucc_rank_t rank, ucc_rank_t size, ucc_msg_range_t **range)
 {
     ucc_coll_args_t *a = &bargs->args;
-    ucc_rank_t rank = bargs->team ? ucc_team_rank_(bargs->team) : 0, size = bargs->team ? ucc_team_size_(bargs->team) : 1;
     ucc_memory_type_t mt = ucc_coll_args_mem_type(a, rank);
     size_t msgsize = ucc_coll_args_msgsize(a, rank, size);
     const ucc_msg_range_t *r;
@@ -518,11 +517,22 @@ ucc_status_t ucc_coll_score_map_lookup(ucc_score_map_t *map, ucc_base_coll_args_
     return UCC_OK;
 }
 
+ucc_status_t ucc_coll_score_map_lookup(ucc_score_map_t *map, ucc_base_coll_args_t *bargs, ucc_msg_range_t **range)
+{
+    return map_lookup_as(map, bargs, bargs->team ? ucc_team_rank_(bargs->team) : 0, bargs->team ? ucc_team_size_(bargs->team) : 1, range);
+}
+
 ucc_status_t ucc_coll_init(ucc_score_map_t *map, ucc_base_coll_args_t *bargs, ucc_coll_task_t **task)
+{
+    return ucc_coll_init_as(map, bargs, bargs->team ? ucc_team_rank_(bargs->team) : 0, bargs->team ? ucc_team_size_(bargs->team) : 1, task);
+}
+
+/* selection for a collective that runs on a sub-group (cl/hier): root / sizes are relative to that group */
+ucc_status_t ucc_coll_init_as(ucc_score_map_t *map, ucc_base_coll_args_t *bargs, ucc_rank_t rank, ucc_rank_t size, ucc_coll_task_t **task)
 {
     ucc_msg_range_t *r;
     ucc_coll_entry_t *fb;
-    ucc_status_t st = ucc_coll_score_map_lookup(map, bargs, &r);
+    ucc_status_t st = map_lookup_as(map, bargs, rank, size, &r);
     if (st != UCC_OK) return st;
     st = r->super.init(bargs, r->super.team, task);
     if (st != UCC_ERR_NOT_SUPPORTED && st != UCC_ERR_NOT_IMPLEMENTED) return st;

@@ -80,6 +80,7 @@ ucc_status_t ucc_coll_score_build_map(ucc_coll_score_t *score, ucc_score_map_t *
 void         ucc_coll_score_free_map(ucc_score_map_t *map);
 /* select by (coll, mem type, msg size) and run init; walks fallbacks on NOT_SUPPORTED / NOT_IMPLEMENTED */
 ucc_status_t ucc_coll_init(ucc_score_map_t *map, ucc_base_coll_args_t *bargs, ucc_coll_task_t **task);
+ucc_status_t ucc_coll_init_as(ucc_score_map_t *map, ucc_base_coll_args_t *bargs, ucc_rank_t rank, ucc_rank_t size, ucc_coll_task_t **task);
 ucc_status_t ucc_coll_score_map_lookup(ucc_score_map_t *map, ucc_base_coll_args_t *bargs, ucc_msg_range_t **range);
 void         ucc_coll_score_map_print_info(const ucc_score_map_t *map, int verbosity);
 void         ucc_coll_score_map_str(const ucc_score_map_t *map, char *buf, size_t len);

@@ -1,0 +1,431 @@
+/* cl/hier: hierarchical collective layer for multi-node teams (reference cl/hier, 3.8 K LoC).
+ * Sub-groups NODE / NODE_LEADERS / NET / FULL each get their own TL teams and score map; a
+ * hierarchical algorithm is a schedule of collectives on those sub-groups:
+ *   allreduce  rab         node reduce -> leaders allreduce -> node bcast
+ *   allreduce  split_rail  node reduce_scatter -> per-rail (NET) allreduce -> node allgather
+ *   bcast      2step       leaders bcast + node bcast
+ *   reduce     2step       node reduce + leaders reduce
+ *   barrier    node fanin -> leaders barrier -> node fanout
+ * Like the reference (cl_hier_team.c:56-59) the CL refuses single-node teams; whatever it cannot do
+ * returns NOT_SUPPORTED at init so the score-map fallback hands the collective to cl/basic. */
+#include "components/cl/ucc_cl.h"
+#include "components/tl/ucc_tl.h"
+#include "components/topo/ucc_topo.h"
+#include "core/ucc_context.h"
+#include "core/ucc_team.h"
+#include "core/ucc_global_opts.h"
+#include "components/mc/ucc_mc.h"
+#include "utils/ucc_string.h"
+#include <strings.h>
+
+#define UCC_CL_HIER_DEFAULT_SCORE 50
+typedef enum { HIER_SBGP_NODE, HIER_SBGP_NODE_LEADERS, HIER_SBGP_NET, HIER_SBGP_FULL, HIER_SBGP_LAST } hier_sbgp_t;
+static const ucc_sbgp_type_t hier_to_topo[HIER_SBGP_LAST] = {UCC_SBGP_NODE, UCC_SBGP_NODE_LEADERS, UCC_SBGP_NET, UCC_SBGP_FULL};
+static const char *hier_sbgp_names[HIER_SBGP_LAST] = {"node", "node_leaders", "net", "full"};
+
+typedef struct ucc_cl_hier_lib_config { ucc_cl_lib_config_t super; ucc_config_allow_list_t sbgp_tls[HIER_SBGP_LAST]; } ucc_cl_hier_lib_config_t;
+typedef struct ucc_cl_hier_context_config { ucc_cl_context_config_t super; } ucc_cl_hier_context_config_t;
+typedef struct ucc_cl_hier_lib { ucc_cl_lib_t super; ucc_config_names_list_t sbgp_tls[HIER_SBGP_LAST]; } ucc_cl_hier_lib_t;
+typedef struct ucc_cl_hier_context { ucc_cl_context_t super; ucc_tl_context_t **tl_ctxs; unsigned n_tl_ctxs; char *tune; } ucc_cl_hier_context_t;
+typedef struct hier_sbgp {
+    int enabled; ucc_sbgp_t *sbgp; ucc_tl_team_t **tl_teams; unsigned n_tl_teams; ucc_coll_score_t *score; ucc_score_map_t *map;
+    ucc_team_multiple_req_t *req;
+} hier_sbgp_state_t;
+typedef struct ucc_cl_hier_team { ucc_cl_team_t super; hier_sbgp_state_t sb[HIER_SBGP_LAST]; int cur; ucc_coll_score_t *score; } ucc_cl_hier_team_t;
+extern ucc_cl_iface_t ucc_cl_hier;
+#define HLIB(_t) ((_t)->super.super.context->lib)
+
+static ucc_config_field_t cl_hier_lib_config_table[] = {
+    {"", "", NULL, ucc_offsetof(ucc_cl_hier_lib_config_t, super), UCC_CONFIG_TYPE_TABLE(ucc_cl_lib_config_table)},
+    {"NODE_SBGP_TLS", "all", "TLs used inside a node", ucc_offsetof(ucc_cl_hier_lib_config_t, sbgp_tls[HIER_SBGP_NODE]), UCC_CONFIG_TYPE_ALLOW_LIST},
+    {"NODE_LEADERS_SBGP_TLS", "all", "TLs used between node leaders", ucc_offsetof(ucc_cl_hier_lib_config_t, sbgp_tls[HIER_SBGP_NODE_LEADERS]), UCC_CONFIG_TYPE_ALLOW_LIST},
+    {"NET_SBGP_TLS", "all", "TLs used on a rail (ranks with the same local index on every node)", ucc_offsetof(ucc_cl_hier_lib_config_t, sbgp_tls[HIER_SBGP_NET]), UCC_CONFIG_TYPE_ALLOW_LIST},
+    {"FULL_SBGP_TLS", "all", "TLs used on the full team", ucc_offsetof(ucc_cl_hier_lib_config_t, sbgp_tls[HIER_SBGP_FULL]), UCC_CONFIG_TYPE_ALLOW_LIST},
+    {NULL}};
+static ucc_config_field_t cl_hier_context_config_table[] = {{"", "", NULL, 0, UCC_CONFIG_TYPE_TABLE(ucc_cl_context_config_table)}, {NULL}};
+
+/* ---- lib / ctx ---- */
+static ucc_status_t hier_lib_init(const ucc_base_lib_params_t *p, const ucc_base_lib_config_t *config, ucc_base_lib_t **lib_p)
+{
+    const ucc_cl_hier_lib_config_t *cfg = ucc_derived_of(config, ucc_cl_hier_lib_config_t);
+    ucc_cl_hier_lib_t *lib = (ucc_cl_hier_lib_t *)calloc(1, sizeof(*lib));
+    (void)p;
+    if (!lib) return UCC_ERR_NO_MEMORY;
+    if (ucc_cl_lib_init_base(&lib->super, &ucc_cl_hier, &cfg->super) != UCC_OK) { free(lib); return UCC_ERR_NO_MEMORY; }
+    for (int i = 0; i < HIER_SBGP_LAST; i++) ucc_config_allow_list_process(&cfg->sbgp_tls[i], &lib->super.tls.array, &lib->sbgp_tls[i]);
+    *lib_p = &lib->super.super;
+    return UCC_OK;
+}
+static void hier_lib_finalize(ucc_base_lib_t *b)
+{ ucc_cl_hier_lib_t *lib = ucc_derived_of(b, ucc_cl_hier_lib_t); for (int i = 0; i < HIER_SBGP_LAST; i++) ucc_config_names_array_free(&lib->sbgp_tls[i].array); ucc_cl_lib_cleanup_base(&lib->super); free(lib); }
+static ucc_status_t hier_lib_get_attr(const ucc_base_lib_t *b, ucc_base_lib_attr_t *battr)
+{
+    const ucc_cl_hier_lib_t *lib = ucc_derived_of(b, ucc_cl_hier_lib_t);
+    ucc_cl_lib_attr_t *attr = ucc_derived_of(battr, ucc_cl_lib_attr_t);
+    attr->super.attr.thread_mode = UCC_THREAD_MULTIPLE;
+    attr->super.attr.coll_types = UCC_COLL_TYPE_ALLREDUCE | UCC_COLL_TYPE_BCAST | UCC_COLL_TYPE_REDUCE | UCC_COLL_TYPE_BARRIER;
+    attr->super.flags = UCC_BASE_LIB_FLAG_SERVICE_TEAM_REQUIRED | UCC_BASE_LIB_FLAG_TEAM_ID_REQUIRED;
+    attr->tls = (ucc_config_names_array_t *)&lib->super.tls.array; attr->tls_forced = lib->super.tls_forced;
+    return UCC_OK;
+}
+static ucc_status_t hier_ctx_create(const ucc_base_context_params_t *p, const ucc_base_ctx_config_t *config, ucc_base_context_t **ctx_p)
+{
+    ucc_cl_lib_t *lib = ucc_derived_of(config->lib, ucc_cl_lib_t);
+    ucc_cl_hier_context_t *ctx = (ucc_cl_hier_context_t *)calloc(1, sizeof(*ctx));
+    if (!ctx) return UCC_ERR_NO_MEMORY;
+    ctx->super.super.ucc_context = p->context; ctx->super.super.lib = config->lib; ctx->tune = config->score_str ? strdup(config->score_str) : NULL;
+    ctx->tl_ctxs = (ucc_tl_context_t **)calloc(lib->tls.array.count + 1, sizeof(void *));
+    for (unsigned i = 0; i < lib->tls.array.count; i++) if (ucc_tl_context_get(p->context, lib->tls.array.names[i], &ctx->tl_ctxs[ctx->n_tl_ctxs]) == UCC_OK) ctx->n_tl_ctxs++;
+    if (!ctx->n_tl_ctxs) { free(ctx->tl_ctxs); free(ctx->tune); free(ctx); return UCC_ERR_NOT_FOUND; }
+    *ctx_p = &ctx->super.super;
+    return UCC_OK;
+}
+static void hier_ctx_destroy(ucc_base_context_t *b)
+{ ucc_cl_hier_context_t *ctx = ucc_derived_of(b, ucc_cl_hier_context_t); for (unsigned i = 0; i < ctx->n_tl_ctxs; i++) ucc_tl_context_put(ctx->tl_ctxs[i]); free(ctx->tl_ctxs); free(ctx->tune); free(ctx); }
+static ucc_status_t hier_ctx_get_attr(const ucc_base_context_t *b, ucc_base_ctx_attr_t *attr)
+{ (void)b; if (attr->attr.mask & UCC_CONTEXT_ATTR_FIELD_CTX_ADDR_LEN) attr->attr.ctx_addr_len = 0; attr->topo_required = 1; return UCC_OK; }
+
+/* ---- team ---- */
+static ucc_status_t sbgp_post(ucc_cl_hier_team_t *team, int i)
+{
+    ucc_cl_hier_context_t *ctx = ucc_derived_of(team->super.super.context, ucc_cl_hier_context_t);
+    ucc_cl_hier_lib_t *lib = ucc_derived_of(HLIB(team), ucc_cl_hier_lib_t);
+    hier_sbgp_state_t *s = &team->sb[i];
+    unsigned n = 0;
+    ucc_status_t st = ucc_team_multiple_req_alloc(&s->req, (int)ctx->n_tl_ctxs);
+    if (st != UCC_OK) return st;
+    for (unsigned k = 0; k < ctx->n_tl_ctxs; k++) {
+        ucc_team_multiple_req_descr_t *d;
+        if (ucc_config_names_search(&lib->sbgp_tls[i].array, UCC_TL_CTX_IFACE(ctx->tl_ctxs[k])->super.name) < 0) continue;
+        d = &s->req->descs[n++];
+        d->ctx = ctx->tl_ctxs[k]; d->param = team->super.super.params;
+        d->param.params.mask &= ~(uint64_t)UCC_TEAM_PARAM_FIELD_OOB; /* sub-teams wire up over the internal (service) OOB */
+        d->param.scope = UCC_CL_HIER; d->param.scope_id = i; d->param.rank = s->sbgp->group_rank; d->param.size = s->sbgp->group_size; d->param.map = s->sbgp->map;
+    }
+    s->req->n_teams = (int)n;
+    st = ucc_tl_team_create_multiple(s->req);
+    return st < 0 ? st : UCC_OK;
+}
+static ucc_status_t sbgp_finish(ucc_cl_hier_team_t *team, int i)
+{
+    hier_sbgp_state_t *s = &team->sb[i];
+    ucc_coll_score_t *tl_score;
+    s->tl_teams = (ucc_tl_team_t **)calloc((size_t)s->req->n_teams + 1, sizeof(void *));
+    for (int k = 0; k < s->req->n_teams; k++) if (s->req->descs[k].status == UCC_OK && s->req->descs[k].team) s->tl_teams[s->n_tl_teams++] = s->req->descs[k].team;
+    ucc_team_multiple_req_free(s->req); s->req = NULL;
+    if (!s->n_tl_teams) { s->enabled = 0; return UCC_OK; }
+    for (unsigned k = 0; k < s->n_tl_teams; k++) {
+        if (UCC_TL_TEAM_IFACE(s->tl_teams[k])->team.get_scores(&s->tl_teams[k]->super, &tl_score) != UCC_OK) continue;
+        if (!s->score) s->score = tl_score; else UCC_CHECK_RET(ucc_coll_score_merge_in(&s->score, tl_score));
+    }
+    if (!s->score) { s->enabled = 0; return UCC_OK; }
+    return ucc_coll_score_build_map(s->score, &s->map);
+}
+
+static ucc_status_t hier_team_create_post(ucc_base_context_t *b_ctx, const ucc_base_team_params_t *params, ucc_base_team_t **team_p)
+{
+    ucc_cl_hier_team_t *team;
+    ucc_topo_t *topo = params->team->topo;
+    if (!topo) { cl_debug(b_ctx->lib, "no topology information: cl/hier is not usable"); return UCC_ERR_NOT_SUPPORTED; }
+    if (ucc_topo_is_single_node(topo)) { cl_debug(b_ctx->lib, "single node team: cl/hier is not needed"); return UCC_ERR_NOT_SUPPORTED; }
+    team = (ucc_cl_hier_team_t *)calloc(1, sizeof(*team));
+    if (!team) return UCC_ERR_NO_MEMORY;
+    team->super.super.context = b_ctx; team->super.super.params = *params;
+    for (int i = 0; i < HIER_SBGP_LAST; i++) {
+        ucc_sbgp_t *sb = ucc_topo_get_sbgp(topo, hier_to_topo[i]);
+        team->sb[i].sbgp = sb;
+        /* a rank that is not a member (e.g. not a leader) simply does not have that sub-team */
+        team->sb[i].enabled = (sb->status == UCC_SBGP_ENABLED && sb->group_size > 1 && sb->group_rank != UCC_RANK_INVALID);
+    }
+    team->cur = -1;
+    *team_p = &team->super.super;
+    return UCC_OK;
+}
+static ucc_status_t hier_team_create_test(ucc_base_team_t *b)
+{
+    ucc_cl_hier_team_t *team = ucc_derived_of(b, ucc_cl_hier_team_t);
+    ucc_status_t st;
+    for (;;) {
+        if (team->cur >= 0 && team->sb[team->cur].req) {
+            st = ucc_tl_team_create_multiple(team->sb[team->cur].req);
+            if (st == UCC_INPROGRESS) return st;
+            if (st < 0) return st;
+            UCC_CHECK_RET(sbgp_finish(team, team->cur));
+        }
+        do { team->cur++; } while (team->cur < HIER_SBGP_LAST && !team->sb[team->cur].enabled);
+        if (team->cur >= HIER_SBGP_LAST) break;
+        st = sbgp_post(team, team->cur);
+        if (st < 0) return st;
+    }
+    if (!team->sb[HIER_SBGP_NODE].sbgp || team->sb[HIER_SBGP_NODE].sbgp->status != UCC_SBGP_ENABLED) return UCC_ERR_NOT_SUPPORTED;
+    return UCC_OK;
+}
+static ucc_status_t hier_team_destroy(ucc_base_team_t *b)
+{
+    ucc_cl_hier_team_t *team = ucc_derived_of(b, ucc_cl_hier_team_t);
+    for (int i = 0; i < HIER_SBGP_LAST; i++) {
+        hier_sbgp_state_t *s = &team->sb[i];
+        for (unsigned k = 0; k < s->n_tl_teams; k++) { ucc_status_t st; do { st = UCC_TL_TEAM_IFACE(s->tl_teams[k])->team.destroy(&s->tl_teams[k]->super); } while (st == UCC_INPROGRESS); }
+        if (s->map) ucc_coll_score_free_map(s->map); else if (s->score) ucc_coll_score_free(s->score);
+        free(s->tl_teams);
+    }
+    free(team);
+    return UCC_OK;
+}
+
+/* ------------------------------------------------------------------ */
+/* hierarchical algorithms = schedules of sub-collectives              */
+/* ------------------------------------------------------------------ */
+typedef struct hier_schedule { ucc_schedule_t super; ucc_mc_buffer_header_t *scratch; } hier_schedule_t;
+static ucc_status_t hier_schedule_finalize(ucc_coll_task_t *t)
+{ hier_schedule_t *hs = (hier_schedule_t *)t; ucc_status_t st = ucc_schedule_finalize(t); if (hs->scratch) ucc_mc_free(hs->scratch); free(t); return st; }
+static ucc_status_t hier_schedule_post(ucc_coll_task_t *t) { return ucc_schedule_start(t); }
+
+static ucc_status_t sub_coll(ucc_cl_hier_team_t *team, int sb, ucc_base_coll_args_t *proto, ucc_coll_args_t *args, ucc_coll_task_t **task)
+{
+    ucc_base_coll_args_t b = *proto;
+    b.args = *args; b.asymm.scratch = NULL;
+    if (!team->sb[sb].enabled || !team->sb[sb].map) return UCC_ERR_NOT_SUPPORTED;
+    /* sub-collectives select by their own (sub-team) size: give the score map a team view of that size */
+    return ucc_coll_init_as(team->sb[sb].map, &b, team->sb[sb].sbgp->group_rank, team->sb[sb].sbgp->group_size, task);
+}
+/* chain: tasks run one after another */
+static ucc_status_t chain(hier_schedule_t *hs, ucc_coll_task_t **tasks, int n)
+{
+    for (int i = 0; i < n; i++) {
+        UCC_CHECK_RET(ucc_schedule_add_task(&hs->super, tasks[i]));
+        if (i == 0) UCC_CHECK_RET(ucc_task_subscribe_dep(&hs->super.super, tasks[0], UCC_EVENT_SCHEDULE_STARTED));
+        else UCC_CHECK_RET(ucc_task_subscribe_dep(tasks[i - 1], tasks[i], UCC_EVENT_COMPLETED));
+    }
+    return UCC_OK;
+}
+static ucc_status_t hier_sched_alloc(ucc_base_coll_args_t *b, ucc_base_team_t *team, hier_schedule_t **hp)
+{
+    hier_schedule_t *hs = (hier_schedule_t *)calloc(1, sizeof(*hs));
+    if (!hs) return UCC_ERR_NO_MEMORY;
+    ucc_schedule_init(&hs->super, b, team);
+    hs->super.super.post = hier_schedule_post; hs->super.super.finalize = hier_schedule_finalize;
+    *hp = hs;
+    return UCC_OK;
+}
+static void free_tasks(ucc_coll_task_t **t, int n) { for (int i = 0; i < n; i++) if (t[i]) t[i]->finalize(t[i]); }
+static int is_leader(ucc_cl_hier_team_t *team) { ucc_sbgp_t *l = team->sb[HIER_SBGP_NODE_LEADERS].sbgp; return l && l->status == UCC_SBGP_ENABLED && l->group_rank != UCC_RANK_INVALID; }
+static int node_multi(ucc_cl_hier_team_t *team) { return team->sb[HIER_SBGP_NODE].enabled; }
+
+static ucc_status_t hier_allreduce_rab(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, ucc_coll_task_t **task_p)
+{
+    ucc_cl_hier_team_t *team = ucc_derived_of(b_team, ucc_cl_hier_team_t);
+    ucc_coll_args_t *a = &b->args, sub;
+    ucc_coll_task_t *tasks[3] = {NULL, NULL, NULL}; int n = 0; hier_schedule_t *hs; ucc_status_t st;
+    int leader = is_leader(team), inplace = UCC_IS_INPLACE(*a);
+    if (a->op == UCC_OP_AVG) return UCC_ERR_NOT_SUPPORTED; /* averaging over sub-groups needs the global size: left to cl/basic */
+    if (node_multi(team)) { /* node reduce to the leader (local rank 0) */
+        sub = *a; sub.coll_type = UCC_COLL_TYPE_REDUCE; sub.root = 0; sub.mask |= UCC_COLL_ARGS_FIELD_FLAGS;
+        if (inplace) { if (!leader) { sub.flags &= ~(uint64_t)UCC_COLL_ARGS_FLAG_IN_PLACE; sub.src.info = a->dst.info; } }
+        st = sub_coll(team, HIER_SBGP_NODE, b, &sub, &tasks[n]); if (st != UCC_OK) goto err; n++;
+    }
+    if (leader && team->sb[HIER_SBGP_NODE_LEADERS].enabled) {
+        sub = *a; sub.mask |= UCC_COLL_ARGS_FIELD_FLAGS;
+        if (node_multi(team)) sub.flags |= UCC_COLL_ARGS_FLAG_IN_PLACE; /* result of the node reduce is already in dst */
+        st = sub_coll(team, HIER_SBGP_NODE_LEADERS, b, &sub, &tasks[n]); if (st != UCC_OK) goto err; n++;
+    }
+    if (node_multi(team)) {
+        sub = *a; sub.coll_type = UCC_COLL_TYPE_BCAST; sub.root = 0; sub.src.info = a->dst.info; sub.mask |= UCC_COLL_ARGS_FIELD_FLAGS; sub.flags &= ~(uint64_t)UCC_COLL_ARGS_FLAG_IN_PLACE;
+        st = sub_coll(team, HIER_SBGP_NODE, b, &sub, &tasks[n]); if (st != UCC_OK) goto err; n++;
+    }
+    if (n == 0) return UCC_ERR_NOT_SUPPORTED;
+    st = hier_sched_alloc(b, b_team, &hs); if (st != UCC_OK) goto err;
+    st = chain(hs, tasks, n); if (st != UCC_OK) { free(hs); goto err; }
+    *task_p = &hs->super.super;
+    return UCC_OK;
+err:
+    free_tasks(tasks, 3);
+    return st == UCC_ERR_NOT_IMPLEMENTED ? UCC_ERR_NOT_SUPPORTED : st;
+}
+
+static ucc_status_t hier_allreduce_split_rail(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, ucc_coll_task_t **task_p)
+{
+    ucc_cl_hier_team_t *team = ucc_derived_of(b_team, ucc_cl_hier_team_t);
+    ucc_coll_args_t *a = &b->args, sub;
+    ucc_coll_task_t *tasks[3] = {NULL, NULL, NULL}; int n = 0; hier_schedule_t *hs; ucc_status_t st;
+    ucc_sbgp_t *node = team->sb[HIER_SBGP_NODE].sbgp;
+    size_t count = a->dst.info.count, dts = ucc_dt_size(a->dst.info.datatype), ppn, off, cnt;
+    if (a->op == UCC_OP_AVG || !node_multi(team) || !team->sb[HIER_SBGP_NET].enabled) return UCC_ERR_NOT_SUPPORTED;
+    ppn = node->group_size;
+    if (count < ppn) return UCC_ERR_NOT_SUPPORTED;
+    off = ucc_buffer_block_offset(count, (unsigned)ppn, node->group_rank); cnt = ucc_buffer_block_count(count, (unsigned)ppn, node->group_rank);
+    if (count % ppn) return UCC_ERR_NOT_SUPPORTED; /* equal blocks keep reduce_scatter / allgather plain */
+    /* 1) node reduce_scatter in place on dst (copy src first through the sub collective's non-inplace form) */
+    sub = *a; sub.coll_type = UCC_COLL_TYPE_REDUCE_SCATTER; sub.mask |= UCC_COLL_ARGS_FIELD_FLAGS;
+    if (UCC_IS_INPLACE(*a)) { sub.dst.info = a->dst.info; }
+    else { sub.flags &= ~(uint64_t)UCC_COLL_ARGS_FLAG_IN_PLACE; sub.src.info = a->src.info; sub.dst.info = a->dst.info; sub.dst.info.buffer = PTR_OFFSET(a->dst.info.buffer, off * dts); sub.dst.info.count = cnt; }
+    st = sub_coll(team, HIER_SBGP_NODE, b, &sub, &tasks[n]); if (st != UCC_OK) goto err; n++;
+    /* 2) rail allreduce of my block */
+    sub = *a; sub.mask |= UCC_COLL_ARGS_FIELD_FLAGS; sub.flags |= UCC_COLL_ARGS_FLAG_IN_PLACE;
+    sub.dst.info.buffer = PTR_OFFSET(a->dst.info.buffer, off * dts); sub.dst.info.count = cnt; sub.src.info = sub.dst.info;
+    st = sub_coll(team, HIER_SBGP_NET, b, &sub, &tasks[n]); if (st != UCC_OK) goto err; n++;
+    /* 3) node allgather in place */
+    sub = *a; sub.coll_type = UCC_COLL_TYPE_ALLGATHER; sub.mask |= UCC_COLL_ARGS_FIELD_FLAGS; sub.flags |= UCC_COLL_ARGS_FLAG_IN_PLACE; sub.dst.info = a->dst.info; sub.src.info = a->dst.info; sub.src.info.count = cnt;
+    st = sub_coll(team, HIER_SBGP_NODE, b, &sub, &tasks[n]); if (st != UCC_OK) goto err; n++;
+    st = hier_sched_alloc(b, b_team, &hs); if (st != UCC_OK) goto err;
+    st = chain(hs, tasks, n); if (st != UCC_OK) { free(hs); goto err; }
+    *task_p = &hs->super.super;
+    return UCC_OK;
+err:
+    free_tasks(tasks, 3);
+    return st == UCC_ERR_NOT_IMPLEMENTED ? UCC_ERR_NOT_SUPPORTED : st;
+}
+
+/* is the (team-rank) root its node's leader?  rooted 2-step algorithms need that */
+static int root_is_leader(ucc_cl_hier_team_t *team, ucc_rank_t root, ucc_rank_t *root_leader_rank)
+{
+    ucc_sbgp_t *l = ucc_topo_get_sbgp(team->super.super.params.team->topo, UCC_SBGP_NODE_LEADERS);
+    /* all ranks must be able to evaluate this: the leaders list is global knowledge (topology) */
+    ucc_rank_t *nl = NULL;
+    if (ucc_topo_get_node_leaders(team->super.super.params.team->topo, &nl) != UCC_OK) return 0;
+    if (nl[root] != root) return 0;
+    (void)l;
+    if (root_leader_rank) {
+        /* rank of root inside the leaders group = number of leaders with a smaller team rank */
+        ucc_rank_t r = 0, size = team->super.super.params.size;
+        for (ucc_rank_t i = 0; i < root; i++) if (nl[i] == i) r++;
+        (void)size; *root_leader_rank = r;
+    }
+    return 1;
+}
+
+static ucc_status_t hier_bcast_2step(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, ucc_coll_task_t **task_p)
+{
+    ucc_cl_hier_team_t *team = ucc_derived_of(b_team, ucc_cl_hier_team_t);
+    ucc_coll_args_t *a = &b->args, sub;
+    ucc_coll_task_t *tasks[2] = {NULL, NULL}; int n = 0; hier_schedule_t *hs; ucc_status_t st; ucc_rank_t lroot = 0;
+    if (UCC_COLL_ARGS_ACTIVE_SET(a) || !root_is_leader(team, (ucc_rank_t)a->root, &lroot)) return UCC_ERR_NOT_SUPPORTED;
+    if (is_leader(team) && team->sb[HIER_SBGP_NODE_LEADERS].enabled) { sub = *a; sub.root = lroot; st = sub_coll(team, HIER_SBGP_NODE_LEADERS, b, &sub, &tasks[n]); if (st != UCC_OK) goto err; n++; }
+    if (node_multi(team)) { sub = *a; sub.root = 0; st = sub_coll(team, HIER_SBGP_NODE, b, &sub, &tasks[n]); if (st != UCC_OK) goto err; n++; }
+    if (!n) return UCC_ERR_NOT_SUPPORTED;
+    st = hier_sched_alloc(b, b_team, &hs); if (st != UCC_OK) goto err;
+    st = chain(hs, tasks, n); if (st != UCC_OK) { free(hs); goto err; }
+    *task_p = &hs->super.super;
+    return UCC_OK;
+err:
+    free_tasks(tasks, 2);
+    return st == UCC_ERR_NOT_IMPLEMENTED ? UCC_ERR_NOT_SUPPORTED : st;
+}
+
+static ucc_status_t hier_reduce_2step(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, ucc_coll_task_t **task_p)
+{
+    ucc_cl_hier_team_t *team = ucc_derived_of(b_team, ucc_cl_hier_team_t);
+    ucc_coll_args_t *a = &b->args, sub;
+    ucc_coll_task_t *tasks[2] = {NULL, NULL}; int n = 0; hier_schedule_t *hs; ucc_status_t st; ucc_rank_t lroot = 0;
+    ucc_rank_t me = team->super.super.params.rank; int root = (ucc_rank_t)a->root == me, leader = is_leader(team);
+    ucc_mc_buffer_header_t *scratch = NULL;
+    if (a->op == UCC_OP_AVG || !root_is_leader(team, (ucc_rank_t)a->root, &lroot)) return UCC_ERR_NOT_SUPPORTED;
+    /* leaders that are not the root need a place for their node's partial result */
+    if (leader && !root && node_multi(team)) {
+        size_t len = a->src.info.count * ucc_dt_size(a->src.info.datatype);
+        if (ucc_mc_alloc(&scratch, len ? len : 1, a->src.info.mem_type) != UCC_OK) return UCC_ERR_NO_MEMORY;
+    }
+    if (node_multi(team)) {
+        sub = *a; sub.root = 0; sub.mask |= UCC_COLL_ARGS_FIELD_FLAGS;
+        if (leader && !root) { sub.dst.info = a->src.info; sub.dst.info.buffer = scratch->addr; sub.flags &= ~(uint64_t)UCC_COLL_ARGS_FLAG_IN_PLACE; }
+        st = sub_coll(team, HIER_SBGP_NODE, b, &sub, &tasks[n]); if (st != UCC_OK) goto err; n++;
+    }
+    if (leader && team->sb[HIER_SBGP_NODE_LEADERS].enabled) {
+        sub = *a; sub.root = lroot; sub.mask |= UCC_COLL_ARGS_FIELD_FLAGS;
+        if (node_multi(team)) { if (root) sub.flags |= UCC_COLL_ARGS_FLAG_IN_PLACE; else sub.src.info.buffer = scratch->addr; }
+        st = sub_coll(team, HIER_SBGP_NODE_LEADERS, b, &sub, &tasks[n]); if (st != UCC_OK) goto err; n++;
+    }
+    if (!n) { st = UCC_ERR_NOT_SUPPORTED; goto err; }
+    st = hier_sched_alloc(b, b_team, &hs); if (st != UCC_OK) goto err;
+    st = chain(hs, tasks, n); if (st != UCC_OK) { free(hs); goto err; }
+    hs->scratch = scratch; /* released with the schedule */
+    *task_p = &hs->super.super;
+    return UCC_OK;
+err:
+    if (scratch) ucc_mc_free(scratch);
+    free_tasks(tasks, 2);
+    return st == UCC_ERR_NOT_IMPLEMENTED ? UCC_ERR_NOT_SUPPORTED : st;
+}
+
+static ucc_status_t hier_barrier(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, ucc_coll_task_t **task_p)
+{
+    ucc_cl_hier_team_t *team = ucc_derived_of(b_team, ucc_cl_hier_team_t);
+    ucc_coll_args_t *a = &b->args, sub;
+    ucc_coll_task_t *tasks[3] = {NULL, NULL, NULL}; int n = 0; hier_schedule_t *hs; ucc_status_t st;
+    if (node_multi(team)) { sub = *a; sub.coll_type = UCC_COLL_TYPE_FANIN; sub.root = 0; st = sub_coll(team, HIER_SBGP_NODE, b, &sub, &tasks[n]); if (st != UCC_OK) goto err; n++; }
+    if (is_leader(team) && team->sb[HIER_SBGP_NODE_LEADERS].enabled) { sub = *a; st = sub_coll(team, HIER_SBGP_NODE_LEADERS, b, &sub, &tasks[n]); if (st != UCC_OK) goto err; n++; }
+    if (node_multi(team)) { sub = *a; sub.coll_type = UCC_COLL_TYPE_FANOUT; sub.root = 0; st = sub_coll(team, HIER_SBGP_NODE, b, &sub, &tasks[n]); if (st != UCC_OK) goto err; n++; }
+    if (!n) return UCC_ERR_NOT_SUPPORTED;
+    st = hier_sched_alloc(b, b_team, &hs); if (st != UCC_OK) goto err;
+    st = chain(hs, tasks, n); if (st != UCC_OK) { free(hs); goto err; }
+    *task_p = &hs->super.super;
+    return UCC_OK;
+err:
+    free_tasks(tasks, 3);
+    return st == UCC_ERR_NOT_IMPLEMENTED ? UCC_ERR_NOT_SUPPORTED : st;
+}
+
+/* ---- algorithm table / scores ---- */
+typedef struct hier_alg { const char *name, *desc; ucc_base_coll_init_fn_t init; } hier_alg_t;
+static const hier_alg_t hier_allreduce_algs[] = {{"rab", "intra-node reduce, followed by inter-node allreduce, followed by innode broadcast", hier_allreduce_rab},
+    {"split_rail", "intra-node reduce_scatter, followed by PPN concurrent inter-node allreduces, followed by intra-node allgather", hier_allreduce_split_rail}, {NULL, NULL, NULL}};
+static const hier_alg_t hier_bcast_algs[] = {{"2step", "leaders bcast followed by intra-node bcast", hier_bcast_2step}, {NULL, NULL, NULL}};
+static const hier_alg_t hier_reduce_algs[] = {{"2step", "intra-node reduce followed by leaders reduce", hier_reduce_2step}, {NULL, NULL, NULL}};
+static const hier_alg_t hier_barrier_algs[] = {{"knomial", "node fanin, leaders barrier, node fanout", hier_barrier}, {NULL, NULL, NULL}};
+static const hier_alg_t *hier_algs(ucc_coll_type_t ct)
+{ switch (ct) { case UCC_COLL_TYPE_ALLREDUCE: return hier_allreduce_algs; case UCC_COLL_TYPE_BCAST: return hier_bcast_algs; case UCC_COLL_TYPE_REDUCE: return hier_reduce_algs; case UCC_COLL_TYPE_BARRIER: return hier_barrier_algs; default: return NULL; } }
+static ucc_base_coll_alg_info_t hier_alg_info[UCC_COLL_TYPE_NUM][3];
+
+static ucc_status_t hier_alg_id_to_init(int alg_id, const char *s, ucc_coll_type_t ct, ucc_memory_type_t mt, ucc_base_coll_init_fn_t *init)
+{
+    const hier_alg_t *algs = hier_algs(ct); int n = 0; (void)mt;
+    if (!algs) return UCC_ERR_NOT_SUPPORTED;
+    while (algs[n].name) n++;
+    if (s) { alg_id = -1; for (int i = 0; i < n; i++) if (!strcasecmp(s, algs[i].name)) alg_id = i; }
+    if (alg_id < 0 || alg_id >= n) return s ? UCC_ERR_NOT_SUPPORTED : UCC_ERR_INVALID_PARAM;
+    *init = algs[alg_id].init;
+    return UCC_OK;
+}
+static ucc_status_t hier_coll_init(ucc_base_coll_args_t *b, ucc_base_team_t *team, ucc_coll_task_t **task)
+{ const hier_alg_t *algs = hier_algs(b->args.coll_type); return algs ? algs[0].init(b, team, task) : UCC_ERR_NOT_SUPPORTED; }
+
+static ucc_status_t hier_team_get_scores(ucc_base_team_t *b_team, ucc_coll_score_t **score_p)
+{
+    ucc_cl_hier_context_t *ctx = ucc_derived_of(b_team->context, ucc_cl_hier_context_t);
+    ucc_memory_type_t mt[3] = {UCC_MEMORY_TYPE_HOST, UCC_MEMORY_TYPE_CUDA, UCC_MEMORY_TYPE_CUDA_MANAGED};
+    uint64_t colls = UCC_COLL_TYPE_ALLREDUCE | UCC_COLL_TYPE_BCAST | UCC_COLL_TYPE_REDUCE | UCC_COLL_TYPE_BARRIER;
+    ucc_coll_score_team_info_t info = {UCC_CL_HIER_DEFAULT_SCORE, b_team->params.size, colls, mt, 3, hier_coll_init, hier_alg_id_to_init};
+    ucc_coll_score_t *score;
+    ucc_status_t st = ucc_coll_score_build_default(b_team, UCC_CL_HIER_DEFAULT_SCORE, hier_coll_init, colls, mt, 3, &score);
+    if (st != UCC_OK) return st;
+    /* reference defaults: rab for small/medium, split_rail for large vectors */
+    st = ucc_coll_score_update_from_str("allreduce:0-4k:@rab#allreduce:4k-inf:@split_rail", &info, b_team, score);
+    if (st == UCC_OK && ctx->tune && ctx->tune[0] && ucc_coll_score_update_from_str(ctx->tune, &info, b_team, score) != UCC_OK)
+        cl_warn(b_team->context->lib, "ignoring invalid CL_HIER_TUNE \"%s\"", ctx->tune);
+    if (st != UCC_OK) { ucc_coll_score_free(score); return st; }
+    *score_p = score;
+    return UCC_OK;
+}
+
+ucc_cl_iface_t ucc_cl_hier = {
+    .super = {.name = "hier", .score = UCC_CL_HIER_DEFAULT_SCORE},
+    .type = UCC_CL_HIER,
+    .cl_lib_config = {"CL_HIER lib", "CL_HIER_", cl_hier_lib_config_table, sizeof(ucc_cl_hier_lib_config_t), {NULL, NULL}},
+    .cl_context_config = {"CL_HIER context", "CL_HIER_", cl_hier_context_config_table, sizeof(ucc_cl_hier_context_config_t), {NULL, NULL}},
+    .lib = {hier_lib_init, hier_lib_finalize, hier_lib_get_attr, NULL},
+    .context = {hier_ctx_create, NULL, hier_ctx_destroy, hier_ctx_get_attr, NULL, NULL, NULL},
+    .team = {hier_team_create_post, hier_team_create_test, hier_team_destroy, hier_team_get_scores},
+    .coll = {hier_coll_init},
+};
+UCC_COMPONENT_REGISTER_STATIC(cl, ucc_cl_hier)
+static void UCC_CTOR cl_hier_register(void)
+{
+    ucc_config_table_register(&ucc_cl_hier.cl_lib_config); ucc_config_table_register(&ucc_cl_hier.cl_context_config);
+    for (int c = 0; c < UCC_COLL_TYPE_NUM; c++) {
+        const hier_alg_t *algs = hier_algs((ucc_coll_type_t)UCC_BIT(c)); int i = 0;
+        if (!algs) continue;
+        for (; algs[i].name && i < 2; i++) { hier_alg_info[c][i].id = (unsigned)i; hier_alg_info[c][i].name = algs[i].name; hier_alg_info[c][i].desc = algs[i].desc; }
+        hier_alg_info[c][i].name = NULL; ucc_cl_hier.alg_info[c] = hier_alg_info[c];
+    }
+    (void)hier_sbgp_names;
+}

@@ -26,7 +26,7 @@ ucc_status_t ucc_tl_shm_ctx_p2p_init(ucc_tl_shm_context_t *ctx)
     cell_size = ucc_align_up(sizeof(shm_cell_hdr_t) + ctx->cfg.cell_payload, 64);
     ctx->ring_len = sizeof(shm_ring_hdr_t) + (size_t)n_cells * cell_size;
     memset(&ctx->addr, 0, sizeof(ctx->addr));
-    ctx->addr.pid = (int32_t)getpid(); ctx->addr.host_hash = core->proc_info.host_hash;
+    ctx->addr.pid = (int32_t)getpid(); ctx->addr.host_hash = ucc_sys_host_hash(); /* physical host: an injected (synthetic) placement only shapes the topology */
     ctx->addr.n_cells = n_cells; ctx->addr.cell_size = (uint32_t)cell_size;
     ctx->addr.ep_id = ucc_hash_mix(((uint64_t)(uint32_t)ctx->addr.pid << 32 | my_seq) ^ ucc_sys_host_hash());
     snprintf(ctx->addr.name, sizeof(ctx->addr.name), "/ucc_b200.%d.%u.%llx", (int)getpid(), my_seq, (unsigned long long)(ctx->addr.ep_id & 0xffffff));

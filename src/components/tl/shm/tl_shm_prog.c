@@ -121,6 +121,7 @@ void ucc_tl_shm_task_progress(ucc_coll_task_t *ct)
             shm_req_t *r;
             ucc_rank_t peer = ucc_ep_map_eval(t->vmap, op->peer);
             uint64_t tag = shm_make_tag(team, t->coll_seq, op->step);
+            if (getenv("SHM_DBG")) fprintf(stderr, "[r%u/%u scope %d.%d] %s %s peer %u tag %lx buf %p len %zu\n", UCC_TL_TEAM_RANK(team), UCC_TL_TEAM_SIZE(team), team->super.super.params.scope, team->super.super.params.scope_id, ucc_coll_type_str(ct->bargs.args.coll_type), op->type == SHM_OP_SEND ? "send" : "recv", peer, (unsigned long)tag, op->dst, op->len);
             st = op->type == SHM_OP_SEND ? ucc_tl_shm_send_nb(team, peer, tag, op->dst, op->len, op->mt, &r)
                                          : ucc_tl_shm_recv_nb(team, peer, tag, op->dst, op->len, op->mt, &r);
             if (st == UCC_OK) st = req_track(t, r);

@@ -1,0 +1,78 @@
+"""cl/hier on synthetic multi-node placements (reference: test/gtest/core/test_topo.cc style fake proc info +
+cl/hier algorithm schedules, cl_hier/allreduce/allreduce_rab.c, allreduce_split_rail.c, bcast_2step.c, reduce_2step.c)."""
+import numpy as np
+import pytest
+
+from ucc_b200 import capi as U
+from ucc_b200.harness import UccJob, coll_args
+
+
+def run(team, args):
+    req = team.coll(args)
+    st = req.run()
+    req.finalize()
+    assert st == U.UCC_OK
+
+
+def job(n, ppn, tune=None):
+    env = {"UCC_CLS": "hier,basic", "UCC_CL_HIER_TLS": "shm,self", "UCC_CL_BASIC_TLS": "shm,self"}
+    if tune:
+        env["UCC_CL_HIER_TUNE"] = tune
+    return UccJob(n, ppn=ppn, env=env, cls="hier,basic")
+
+
+@pytest.mark.parametrize("n,ppn", [(4, 2), (8, 4), (6, 2), (6, 3), (5, 2), (8, 1)])
+@pytest.mark.parametrize("alg", ["rab", "split_rail"])
+def test_hier_allreduce(n, ppn, alg):
+    with job(n, ppn, tune=f"allreduce:0-inf:@{alg}") as j:
+        team = j.create_team()
+        rng = np.random.default_rng(n * 10 + ppn)
+        for count in (1, 7, 12 * ppn, 4096):
+            for inplace in (False, True):
+                src = [rng.integers(-50, 50, count).astype(np.int64) for _ in range(n)]
+                exp = np.sum(src, 0)
+                if inplace:
+                    dst = [s.copy() for s in src]
+                    run(team, [coll_args("allreduce", None, dst[r], dt="int64", op="sum", inplace=True) for r in range(n)])
+                else:
+                    dst = [np.zeros(count, np.int64) for _ in range(n)]
+                    run(team, [coll_args("allreduce", src[r], dst[r], dt="int64", op="sum") for r in range(n)])
+                for r in range(n):
+                    assert np.array_equal(dst[r], exp), (alg, count, inplace, r)
+        # avg is not hierarchical: must fall back to cl/basic and still be right
+        src = [rng.random(33) for _ in range(n)]
+        dst = [np.zeros(33) for _ in range(n)]
+        run(team, [coll_args("allreduce", src[r], dst[r], dt="float64", op="avg") for r in range(n)])
+        for r in range(n):
+            assert np.allclose(dst[r], np.mean(src, 0))
+
+
+@pytest.mark.parametrize("n,ppn", [(4, 2), (8, 4), (6, 3), (7, 3)])
+def test_hier_bcast_reduce_barrier(n, ppn):
+    with job(n, ppn) as j:
+        team = j.create_team()
+        rng = np.random.default_rng(n)
+        for root in range(n):   # leader roots go 2step, others fall back to cl/basic
+            bufs = [rng.random(100).astype(np.float32) if r == root else np.zeros(100, np.float32) for r in range(n)]
+            exp = bufs[root].copy()
+            run(team, [coll_args("bcast", bufs[r], None, root=root) for r in range(n)])
+            for r in range(n):
+                assert np.array_equal(bufs[r], exp), (root, r)
+            src = [rng.integers(0, 100, 64).astype(np.int32) for _ in range(n)]
+            keep = [s.copy() for s in src]
+            dst = [np.zeros(64, np.int32) for _ in range(n)]
+            run(team, [coll_args("reduce", src[r], dst[r] if r == root else None, dt="int32", op="sum", root=root) for r in range(n)])
+            assert np.array_equal(dst[root], np.sum(keep, 0)), root
+            for r in range(n):
+                assert np.array_equal(src[r], keep[r])
+        for _ in range(3):
+            run(team, [coll_args("barrier") for _ in range(n)])
+
+
+def test_hier_single_node_falls_back():
+    with job(4, 4) as j:   # one node: cl/hier refuses the team, cl/basic serves it
+        team = j.create_team()
+        src = [np.full(10, r + 1, np.int32) for r in range(4)]
+        dst = [np.zeros(10, np.int32) for _ in range(4)]
+        run(team, [coll_args("allreduce", src[r], dst[r], dt="int32", op="sum") for r in range(4)])
+        assert all(np.array_equal(d, np.full(10, 10)) for d in dst)
