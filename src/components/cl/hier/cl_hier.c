@@ -14,6 +14,7 @@
 #include "core/ucc_context.h"
 #include "core/ucc_team.h"
 #include "core/ucc_global_opts.h"
+#include "schedule/ucc_schedule_pipelined.h"
 #include "components/mc/ucc_mc.h"
 #include "utils/ucc_string.h"
 #include <strings.h>
@@ -23,9 +24,9 @@ typedef enum { HIER_SBGP_NODE, HIER_SBGP_NODE_LEADERS, HIER_SBGP_NET, HIER_SBGP_
 static const ucc_sbgp_type_t hier_to_topo[HIER_SBGP_LAST] = {UCC_SBGP_NODE, UCC_SBGP_NODE_LEADERS, UCC_SBGP_NET, UCC_SBGP_FULL};
 static const char *hier_sbgp_names[HIER_SBGP_LAST] = {"node", "node_leaders", "net", "full"};
 
-typedef struct ucc_cl_hier_lib_config { ucc_cl_lib_config_t super; ucc_config_allow_list_t sbgp_tls[HIER_SBGP_LAST]; } ucc_cl_hier_lib_config_t;
+typedef struct ucc_cl_hier_lib_config { ucc_cl_lib_config_t super; ucc_config_allow_list_t sbgp_tls[HIER_SBGP_LAST]; ucc_pipeline_params_t allreduce_rab_pipeline; } ucc_cl_hier_lib_config_t;
 typedef struct ucc_cl_hier_context_config { ucc_cl_context_config_t super; } ucc_cl_hier_context_config_t;
-typedef struct ucc_cl_hier_lib { ucc_cl_lib_t super; ucc_config_names_list_t sbgp_tls[HIER_SBGP_LAST]; } ucc_cl_hier_lib_t;
+typedef struct ucc_cl_hier_lib { ucc_cl_lib_t super; ucc_config_names_list_t sbgp_tls[HIER_SBGP_LAST]; ucc_pipeline_params_t allreduce_rab_pipeline; } ucc_cl_hier_lib_t;
 typedef struct ucc_cl_hier_context { ucc_cl_context_t super; ucc_tl_context_t **tl_ctxs; unsigned n_tl_ctxs; char *tune; } ucc_cl_hier_context_t;
 typedef struct hier_sbgp {
     int enabled; ucc_sbgp_t *sbgp; ucc_tl_team_t **tl_teams; unsigned n_tl_teams; ucc_coll_score_t *score; ucc_score_map_t *map;
@@ -41,6 +42,8 @@ static ucc_config_field_t cl_hier_lib_config_table[] = {
     {"NODE_LEADERS_SBGP_TLS", "all", "TLs used between node leaders", ucc_offsetof(ucc_cl_hier_lib_config_t, sbgp_tls[HIER_SBGP_NODE_LEADERS]), UCC_CONFIG_TYPE_ALLOW_LIST},
     {"NET_SBGP_TLS", "all", "TLs used on a rail (ranks with the same local index on every node)", ucc_offsetof(ucc_cl_hier_lib_config_t, sbgp_tls[HIER_SBGP_NET]), UCC_CONFIG_TYPE_ALLOW_LIST},
     {"FULL_SBGP_TLS", "all", "TLs used on the full team", ucc_offsetof(ucc_cl_hier_lib_config_t, sbgp_tls[HIER_SBGP_FULL]), UCC_CONFIG_TYPE_ALLOW_LIST},
+    {"ALLREDUCE_RAB_PIPELINE", "n", "Pipelining of the RAB allreduce: thresh=<size>:fragsize=<size>:nfrags=<n>:pdepth=<n>:<parallel|ordered|sequential>",
+     ucc_offsetof(ucc_cl_hier_lib_config_t, allreduce_rab_pipeline), UCC_CONFIG_TYPE_PIPELINE_PARAMS},
     {NULL}};
 static ucc_config_field_t cl_hier_context_config_table[] = {{"", "", NULL, 0, UCC_CONFIG_TYPE_TABLE(ucc_cl_context_config_table)}, {NULL}};
 
@@ -53,6 +56,7 @@ static ucc_status_t hier_lib_init(const ucc_base_lib_params_t *p, const ucc_base
     if (!lib) return UCC_ERR_NO_MEMORY;
     if (ucc_cl_lib_init_base(&lib->super, &ucc_cl_hier, &cfg->super) != UCC_OK) { free(lib); return UCC_ERR_NO_MEMORY; }
     for (int i = 0; i < HIER_SBGP_LAST; i++) ucc_config_allow_list_process(&cfg->sbgp_tls[i], &lib->super.tls.array, &lib->sbgp_tls[i]);
+    lib->allreduce_rab_pipeline = cfg->allreduce_rab_pipeline;
     *lib_p = &lib->super.super;
     return UCC_OK;
 }
@@ -63,7 +67,7 @@ static ucc_status_t hier_lib_get_attr(const ucc_base_lib_t *b, ucc_base_lib_attr
     const ucc_cl_hier_lib_t *lib = ucc_derived_of(b, ucc_cl_hier_lib_t);
     ucc_cl_lib_attr_t *attr = ucc_derived_of(battr, ucc_cl_lib_attr_t);
     attr->super.attr.thread_mode = UCC_THREAD_MULTIPLE;
-    attr->super.attr.coll_types = UCC_COLL_TYPE_ALLREDUCE | UCC_COLL_TYPE_BCAST | UCC_COLL_TYPE_REDUCE | UCC_COLL_TYPE_BARRIER;
+    attr->super.attr.coll_types = UCC_COLL_TYPE_ALLREDUCE | UCC_COLL_TYPE_BCAST | UCC_COLL_TYPE_REDUCE | UCC_COLL_TYPE_BARRIER | UCC_COLL_TYPE_ALLTOALL | UCC_COLL_TYPE_ALLTOALLV | UCC_COLL_TYPE_ALLGATHERV;
     attr->super.flags = UCC_BASE_LIB_FLAG_SERVICE_TEAM_REQUIRED | UCC_BASE_LIB_FLAG_TEAM_ID_REQUIRED;
     attr->tls = (ucc_config_names_array_t *)&lib->super.tls.array; attr->tls_forced = lib->super.tls_forced;
     return UCC_OK;
@@ -176,9 +180,9 @@ static ucc_status_t hier_team_destroy(ucc_base_team_t *b)
 /* ------------------------------------------------------------------ */
 /* hierarchical algorithms = schedules of sub-collectives              */
 /* ------------------------------------------------------------------ */
-typedef struct hier_schedule { ucc_schedule_t super; ucc_mc_buffer_header_t *scratch; } hier_schedule_t;
+typedef struct hier_schedule { ucc_schedule_t super; ucc_mc_buffer_header_t *scratch; void *arrays; } hier_schedule_t;
 static ucc_status_t hier_schedule_finalize(ucc_coll_task_t *t)
-{ hier_schedule_t *hs = (hier_schedule_t *)t; ucc_status_t st = ucc_schedule_finalize(t); if (hs->scratch) ucc_mc_free(hs->scratch); free(t); return st; }
+{ hier_schedule_t *hs = (hier_schedule_t *)t; ucc_status_t st = ucc_schedule_finalize(t); if (hs->scratch) ucc_mc_free(hs->scratch); free(hs->arrays); free(t); return st; }
 static ucc_status_t hier_schedule_post(ucc_coll_task_t *t) { return ucc_schedule_start(t); }
 
 static ucc_status_t sub_coll(ucc_cl_hier_team_t *team, int sb, ucc_base_coll_args_t *proto, ucc_coll_args_t *args, ucc_coll_task_t **task)
@@ -212,7 +216,7 @@ static void free_tasks(ucc_coll_task_t **t, int n) { for (int i = 0; i < n; i++)
 static int is_leader(ucc_cl_hier_team_t *team) { ucc_sbgp_t *l = team->sb[HIER_SBGP_NODE_LEADERS].sbgp; return l && l->status == UCC_SBGP_ENABLED && l->group_rank != UCC_RANK_INVALID; }
 static int node_multi(ucc_cl_hier_team_t *team) { return team->sb[HIER_SBGP_NODE].enabled; }
 
-static ucc_status_t hier_allreduce_rab(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, ucc_coll_task_t **task_p)
+static ucc_status_t hier_allreduce_rab_frag(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, ucc_coll_task_t **task_p)
 {
     ucc_cl_hier_team_t *team = ucc_derived_of(b_team, ucc_cl_hier_team_t);
     ucc_coll_args_t *a = &b->args, sub;
@@ -243,6 +247,71 @@ err:
     return st == UCC_ERR_NOT_IMPLEMENTED ? UCC_ERR_NOT_SUPPORTED : st;
 }
 
+
+/* pipelined rab: the vector is cut into fragments, up to pdepth rab chains are in flight and re-armed round robin
+ * (reference allreduce_rab.c:79-270 does the same on top of its pipelined schedule) */
+typedef struct hier_rab_pipe {
+    ucc_schedule_pipelined_t super;
+    void  *src0[UCC_SCHEDULE_PIPELINED_MAX_FRAGS][3], *dst0[UCC_SCHEDULE_PIPELINED_MAX_FRAGS][3]; /* buffers of each sub task for fragment offset 0 */
+    size_t total, dts;
+} hier_rab_pipe_t;
+static ucc_status_t rab_frag_init(ucc_base_coll_args_t *b, ucc_schedule_pipelined_t *sp, ucc_base_team_t *team, ucc_schedule_t **frag)
+{
+    hier_rab_pipe_t *rp = (hier_rab_pipe_t *)sp;
+    ucc_base_coll_args_t fb = *b; ucc_coll_task_t *t; ucc_schedule_t *f; ucc_status_t st; int slot = 0;
+    size_t fc = ucc_buffer_block_count(rp->total, (unsigned)sp->n_frags_total, 0); /* largest fragment */
+    fb.args.dst.info.count = fc; if (!UCC_IS_INPLACE(fb.args)) fb.args.src.info.count = fc;
+    st = hier_allreduce_rab_frag(&fb, team, &t); if (st != UCC_OK) return st;
+    f = (ucc_schedule_t *)t;
+    while (slot < UCC_SCHEDULE_PIPELINED_MAX_FRAGS && rp->src0[slot][0] != (void *)(uintptr_t)1) slot++; /* first unused slot */
+    if (slot == UCC_SCHEDULE_PIPELINED_MAX_FRAGS) { t->finalize(t); return UCC_ERR_NO_RESOURCE; }
+    for (unsigned j = 0; j < f->n_tasks && j < 3; j++) { rp->src0[slot][j] = f->tasks[j]->bargs.args.src.info.buffer; rp->dst0[slot][j] = f->tasks[j]->bargs.args.dst.info.buffer; }
+    *frag = f;
+    return UCC_OK;
+}
+static ucc_status_t rab_frag_setup(ucc_schedule_pipelined_t *sp, ucc_schedule_t *frag, int frag_num)
+{
+    hier_rab_pipe_t *rp = (hier_rab_pipe_t *)sp;
+    size_t off = ucc_buffer_block_offset(rp->total, (unsigned)sp->n_frags_total, (unsigned)frag_num) * rp->dts, cnt = ucc_buffer_block_count(rp->total, (unsigned)sp->n_frags_total, (unsigned)frag_num);
+    int slot = 0;
+    while (slot < sp->n_frags && sp->frags[slot] != frag) slot++;
+    for (unsigned j = 0; j < frag->n_tasks && j < 3; j++) {
+        ucc_coll_args_t *a = &frag->tasks[j]->bargs.args;
+        if (rp->src0[slot][j]) a->src.info.buffer = PTR_OFFSET(rp->src0[slot][j], off);
+        if (rp->dst0[slot][j]) a->dst.info.buffer = PTR_OFFSET(rp->dst0[slot][j], off);
+        a->src.info.count = cnt; a->dst.info.count = cnt;
+        frag->tasks[j]->flags |= UCC_COLL_TASK_FLAG_ARGS_UPDATED;
+    }
+    return UCC_OK;
+}
+static ucc_status_t rab_pipe_finalize(ucc_coll_task_t *t) { ucc_status_t st = ucc_schedule_pipelined_finalize(t); free(t); return st; }
+
+static ucc_status_t hier_allreduce_rab(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, ucc_coll_task_t **task_p)
+{
+    ucc_cl_hier_team_t *team = ucc_derived_of(b_team, ucc_cl_hier_team_t);
+    ucc_cl_hier_lib_t *lib = ucc_derived_of(HLIB(team), ucc_cl_hier_lib_t);
+    const ucc_pipeline_params_t *pp = &lib->allreduce_rab_pipeline;
+    size_t count = b->args.dst.info.count, dts = ucc_dt_size(b->args.dst.info.datatype), fcount;
+    hier_rab_pipe_t *rp; int n_total, depth; ucc_status_t st;
+    if (!pp->n_frags || !pp->pdepth || pp->threshold == UCC_MEMUNITS_INF || pp->threshold == UCC_MEMUNITS_AUTO || count * dts < pp->threshold || b->args.op == UCC_OP_AVG ||
+        UCC_DT_IS_GENERIC(b->args.dst.info.datatype))
+        return hier_allreduce_rab_frag(b, b_team, task_p);
+    fcount = (pp->frag_size == UCC_MEMUNITS_INF || pp->frag_size == UCC_MEMUNITS_AUTO) ? ucc_div_round_up(count, pp->n_frags) : ucc_max(1, pp->frag_size / dts);
+    n_total = (int)ucc_div_round_up(count, fcount);
+    if (n_total < 2) return hier_allreduce_rab_frag(b, b_team, task_p);
+    depth = (int)ucc_min(ucc_min(pp->pdepth, (unsigned)n_total), UCC_SCHEDULE_PIPELINED_MAX_FRAGS);
+    rp = (hier_rab_pipe_t *)calloc(1, sizeof(*rp));
+    if (!rp) return UCC_ERR_NO_MEMORY;
+    rp->total = count; rp->dts = dts;
+    for (int s2 = 0; s2 < UCC_SCHEDULE_PIPELINED_MAX_FRAGS; s2++) rp->src0[s2][0] = (void *)(uintptr_t)1; /* "slot unused" marker consumed by rab_frag_init */
+    rp->super.n_frags_total = n_total; /* frag_init needs it before pipelined_init stores it */
+    st = ucc_schedule_pipelined_init(b, b_team, rab_frag_init, rab_frag_setup, depth, n_total, pp->order, &rp->super);
+    if (st != UCC_OK) { free(rp); return st == UCC_ERR_NOT_IMPLEMENTED ? UCC_ERR_NOT_SUPPORTED : st; }
+    rp->super.super.super.finalize = rab_pipe_finalize;
+    *task_p = &rp->super.super.super;
+    return UCC_OK;
+}
+
 static ucc_status_t hier_allreduce_split_rail(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, ucc_coll_task_t **task_p)
 {
     ucc_cl_hier_team_t *team = ucc_derived_of(b_team, ucc_cl_hier_team_t);
@@ -250,7 +319,8 @@ static ucc_status_t hier_allreduce_split_rail(ucc_base_coll_args_t *b, ucc_base_
     ucc_coll_task_t *tasks[3] = {NULL, NULL, NULL}; int n = 0; hier_schedule_t *hs; ucc_status_t st;
     ucc_sbgp_t *node = team->sb[HIER_SBGP_NODE].sbgp;
     size_t count = a->dst.info.count, dts = ucc_dt_size(a->dst.info.datatype), ppn, off, cnt;
-    if (a->op == UCC_OP_AVG || !node_multi(team) || !team->sb[HIER_SBGP_NET].enabled) return UCC_ERR_NOT_SUPPORTED;
+    if (a->op == UCC_OP_AVG || !ucc_topo_isoppn(team->super.super.params.team->topo) || ucc_topo_min_ppn(team->super.super.params.team->topo) < 2 ||
+        !node_multi(team) || !team->sb[HIER_SBGP_NET].enabled) return UCC_ERR_NOT_SUPPORTED;
     ppn = node->group_size;
     if (count < ppn) return UCC_ERR_NOT_SUPPORTED;
     off = ucc_buffer_block_offset(count, (unsigned)ppn, node->group_rank); cnt = ucc_buffer_block_count(count, (unsigned)ppn, node->group_rank);
@@ -365,6 +435,107 @@ err:
     return st == UCC_ERR_NOT_IMPLEMENTED ? UCC_ERR_NOT_SUPPORTED : st;
 }
 
+
+/* ---- alltoall / alltoallv node_split: the exchange is cut into the intra-node part (NODE sub-team) and the rest
+ * (FULL sub-team with empty blocks for node peers); both halves run concurrently and write disjoint ranges ---- */
+static ucc_status_t hier_a2av_node_split(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, ucc_coll_task_t **task_p)
+{
+    ucc_cl_hier_team_t *team = ucc_derived_of(b_team, ucc_cl_hier_team_t);
+    ucc_coll_args_t *a = &b->args, sub;
+    ucc_coll_task_t *tasks[2] = {NULL, NULL}; hier_schedule_t *hs = NULL; ucc_status_t st;
+    ucc_sbgp_t *node = team->sb[HIER_SBGP_NODE].sbgp, *full = team->sb[HIER_SBGP_FULL].sbgp;
+    ucc_rank_t N = team->super.super.params.size, nn, i; int is_v = a->coll_type == UCC_COLL_TYPE_ALLTOALLV;
+    uint64_t *arr, *nsc, *nsd, *nrc, *nrd, *fsc, *fsd, *frc, *frd;
+    if (UCC_IS_INPLACE(*a) || !team->sb[HIER_SBGP_FULL].enabled) return UCC_ERR_NOT_SUPPORTED; /* both conditions are the same on every rank */
+    nn = node_multi(team) ? node->group_size : 0; /* alone on my node: everything goes through the FULL exchange */
+    arr = (uint64_t *)calloc(4 * (size_t)nn + 4 * (size_t)N, sizeof(uint64_t));
+    if (!arr) return UCC_ERR_NO_MEMORY;
+    nsc = arr; nsd = nsc + nn; nrc = nsd + nn; nrd = nrc + nn; fsc = nrd + nn; fsd = fsc + N; frc = fsd + N; frd = frc + N;
+    for (i = 0; i < N; i++) { /* FULL sub-team rank i == team rank rank_map[i] (identity for the full group) */
+        ucc_rank_t r = full->rank_map ? full->rank_map[i] : i;
+        if (is_v) { fsc[i] = ucc_coll_args_get_count(a, a->src.info_v.counts, r); fsd[i] = ucc_coll_args_get_displacement(a, a->src.info_v.displacements, r);
+                    frc[i] = ucc_coll_args_get_count(a, a->dst.info_v.counts, r); frd[i] = ucc_coll_args_get_displacement(a, a->dst.info_v.displacements, r); }
+        else { fsc[i] = a->src.info.count / N; fsd[i] = (uint64_t)r * fsc[i]; frc[i] = a->dst.info.count / N; frd[i] = (uint64_t)r * frc[i]; }
+    }
+    for (i = 0; i < nn; i++) {
+        ucc_rank_t r = node->rank_map[i], fi = r; /* node member's index inside FULL */
+        if (full->rank_map) for (fi = 0; fi < N && full->rank_map[fi] != r; fi++) ;
+        nsc[i] = fsc[fi]; nsd[i] = fsd[fi]; nrc[i] = frc[fi]; nrd[i] = frd[fi];
+        fsc[fi] = 0; frc[fi] = 0;
+    }
+    sub = *a; sub.coll_type = UCC_COLL_TYPE_ALLTOALLV; sub.mask |= UCC_COLL_ARGS_FIELD_FLAGS; sub.flags |= UCC_COLL_ARGS_FLAG_COUNT_64BIT | UCC_COLL_ARGS_FLAG_DISPLACEMENTS_64BIT;
+    if (!is_v) { sub.src.info_v.buffer = a->src.info.buffer; sub.src.info_v.datatype = a->src.info.datatype; sub.src.info_v.mem_type = a->src.info.mem_type;
+                 sub.dst.info_v.buffer = a->dst.info.buffer; sub.dst.info_v.datatype = a->dst.info.datatype; sub.dst.info_v.mem_type = a->dst.info.mem_type; }
+    sub.src.info_v.counts = (ucc_count_t *)nsc; sub.src.info_v.displacements = (ucc_aint_t *)nsd; sub.dst.info_v.counts = (ucc_count_t *)nrc; sub.dst.info_v.displacements = (ucc_aint_t *)nrd;
+    if (nn) { st = sub_coll(team, HIER_SBGP_NODE, b, &sub, &tasks[0]); if (st != UCC_OK) goto err; }
+    sub.src.info_v.counts = (ucc_count_t *)fsc; sub.src.info_v.displacements = (ucc_aint_t *)fsd; sub.dst.info_v.counts = (ucc_count_t *)frc; sub.dst.info_v.displacements = (ucc_aint_t *)frd;
+    st = sub_coll(team, HIER_SBGP_FULL, b, &sub, &tasks[1]); if (st != UCC_OK) goto err;
+    st = hier_sched_alloc(b, b_team, &hs); if (st != UCC_OK) goto err;
+    for (i = 0; i < 2; i++) { /* both start with the schedule */
+        if (!tasks[i]) continue;
+        st = ucc_schedule_add_task(&hs->super, tasks[i]); if (st != UCC_OK) goto err;
+        st = ucc_task_subscribe_dep(&hs->super.super, tasks[i], UCC_EVENT_SCHEDULE_STARTED); if (st != UCC_OK) goto err;
+    }
+    hs->arrays = arr;
+    *task_p = &hs->super.super;
+    return UCC_OK;
+err:
+    free(hs); free(arr); free_tasks(tasks, 2);
+    return st == UCC_ERR_NOT_IMPLEMENTED ? UCC_ERR_NOT_SUPPORTED : st;
+}
+
+/* ---- allgatherv gab: node gatherv -> leaders allgatherv -> node bcast.  Needs the packed layout
+ * (displs are the running sum of counts) and nodes made of consecutive ranks; other layouts go to cl/basic ---- */
+static ucc_status_t hier_allgatherv_gab(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, ucc_coll_task_t **task_p)
+{
+    ucc_cl_hier_team_t *team = ucc_derived_of(b_team, ucc_cl_hier_team_t);
+    ucc_coll_args_t *a = &b->args, sub;
+    ucc_coll_task_t *tasks[3] = {NULL, NULL, NULL}; int n = 0; hier_schedule_t *hs = NULL; ucc_status_t st;
+    ucc_sbgp_t *node = team->sb[HIER_SBGP_NODE].sbgp, *lead = ucc_topo_get_sbgp(team->super.super.params.team->topo, UCC_SBGP_NODE_LEADERS);
+    ucc_rank_t N = team->super.super.params.size, me = team->super.super.params.rank, i, nl = 0, *leaders = NULL;
+    size_t dts = ucc_dt_size(a->dst.info_v.datatype), total = 0; uint64_t *arr, *gc, *gd, *lc, *ld; int leader = is_leader(team), inplace = UCC_IS_INPLACE(*a);
+    if (ucc_topo_get_node_leaders(team->super.super.params.team->topo, &leaders) != UCC_OK) return UCC_ERR_NOT_SUPPORTED;
+    for (i = 0; i < N; i++) {
+        if (ucc_coll_args_get_displacement(a, a->dst.info_v.displacements, i) != total) return UCC_ERR_NOT_SUPPORTED;
+        total += ucc_coll_args_get_count(a, a->dst.info_v.counts, i);
+        if (leaders[i] == i) nl++; else if (i == 0 || leaders[i] != leaders[i - 1]) return UCC_ERR_NOT_SUPPORTED; /* node = consecutive ranks led by the first */
+    }
+    (void)lead;
+    arr = (uint64_t *)calloc(2 * (size_t)N + 2 * (size_t)nl + 2, sizeof(uint64_t));
+    if (!arr) return UCC_ERR_NO_MEMORY;
+    gc = arr; gd = gc + N; lc = gd + N; ld = lc + nl;
+    if (node_multi(team)) {
+        for (i = 0; i < node->group_size; i++) { gc[i] = ucc_coll_args_get_count(a, a->dst.info_v.counts, node->rank_map[i]); gd[i] = ucc_coll_args_get_displacement(a, a->dst.info_v.displacements, node->rank_map[i]); }
+        sub = *a; sub.coll_type = UCC_COLL_TYPE_GATHERV; sub.root = 0; sub.mask |= UCC_COLL_ARGS_FIELD_FLAGS; sub.flags |= UCC_COLL_ARGS_FLAG_COUNT_64BIT | UCC_COLL_ARGS_FLAG_DISPLACEMENTS_64BIT;
+        sub.dst.info_v.counts = (ucc_count_t *)gc; sub.dst.info_v.displacements = (ucc_aint_t *)gd;
+        if (inplace && !leader) { sub.flags &= ~(uint64_t)UCC_COLL_ARGS_FLAG_IN_PLACE; sub.src.info.buffer = PTR_OFFSET(a->dst.info_v.buffer, ucc_coll_args_get_displacement(a, a->dst.info_v.displacements, me) * dts);
+            sub.src.info.count = ucc_coll_args_get_count(a, a->dst.info_v.counts, me); sub.src.info.datatype = a->dst.info_v.datatype; sub.src.info.mem_type = a->dst.info_v.mem_type; }
+        st = sub_coll(team, HIER_SBGP_NODE, b, &sub, &tasks[n]); if (st != UCC_OK) goto err; n++;
+    }
+    if (leader && team->sb[HIER_SBGP_NODE_LEADERS].enabled) {
+        ucc_rank_t j = 0;
+        for (i = 0; i < N; i++) { if (leaders[i] == i) { ld[j] = ucc_coll_args_get_displacement(a, a->dst.info_v.displacements, i); j++; } lc[j - 1] += ucc_coll_args_get_count(a, a->dst.info_v.counts, i); }
+        sub = *a; sub.mask |= UCC_COLL_ARGS_FIELD_FLAGS; sub.flags |= UCC_COLL_ARGS_FLAG_COUNT_64BIT | UCC_COLL_ARGS_FLAG_DISPLACEMENTS_64BIT;
+        sub.dst.info_v.counts = (ucc_count_t *)lc; sub.dst.info_v.displacements = (ucc_aint_t *)ld;
+        if (node_multi(team) || inplace) sub.flags |= UCC_COLL_ARGS_FLAG_IN_PLACE; /* the node's data already sits in dst */
+        st = sub_coll(team, HIER_SBGP_NODE_LEADERS, b, &sub, &tasks[n]); if (st != UCC_OK) goto err; n++;
+    }
+    if (node_multi(team)) {
+        sub = *a; sub.coll_type = UCC_COLL_TYPE_BCAST; sub.root = 0; sub.mask |= UCC_COLL_ARGS_FIELD_FLAGS; sub.flags &= ~(uint64_t)UCC_COLL_ARGS_FLAG_IN_PLACE;
+        sub.src.info.buffer = a->dst.info_v.buffer; sub.src.info.count = total; sub.src.info.datatype = a->dst.info_v.datatype; sub.src.info.mem_type = a->dst.info_v.mem_type;
+        st = sub_coll(team, HIER_SBGP_NODE, b, &sub, &tasks[n]); if (st != UCC_OK) goto err; n++;
+    }
+    if (!n) { st = UCC_ERR_NOT_SUPPORTED; goto err; }
+    st = hier_sched_alloc(b, b_team, &hs); if (st != UCC_OK) goto err;
+    st = chain(hs, tasks, n); if (st != UCC_OK) goto err;
+    hs->arrays = arr;
+    *task_p = &hs->super.super;
+    return UCC_OK;
+err:
+    free(hs); free(arr); free_tasks(tasks, 3);
+    return st == UCC_ERR_NOT_IMPLEMENTED ? UCC_ERR_NOT_SUPPORTED : st;
+}
+
 /* ---- algorithm table / scores ---- */
 typedef struct hier_alg { const char *name, *desc; ucc_base_coll_init_fn_t init; } hier_alg_t;
 static const hier_alg_t hier_allreduce_algs[] = {{"rab", "intra-node reduce, followed by inter-node allreduce, followed by innode broadcast", hier_allreduce_rab},
@@ -372,8 +543,11 @@ static const hier_alg_t hier_allreduce_algs[] = {{"rab", "intra-node reduce, fol
 static const hier_alg_t hier_bcast_algs[] = {{"2step", "leaders bcast followed by intra-node bcast", hier_bcast_2step}, {NULL, NULL, NULL}};
 static const hier_alg_t hier_reduce_algs[] = {{"2step", "intra-node reduce followed by leaders reduce", hier_reduce_2step}, {NULL, NULL, NULL}};
 static const hier_alg_t hier_barrier_algs[] = {{"knomial", "node fanin, leaders barrier, node fanout", hier_barrier}, {NULL, NULL, NULL}};
+static const hier_alg_t hier_a2a_algs[] = {{"node_split", "splitting alltoall into two concurrent a2av calls withing the node and outside of it", hier_a2av_node_split}, {NULL, NULL, NULL}};
+static const hier_alg_t hier_a2av_algs[] = {{"node_split", "splitting alltoallv into two concurrent a2av calls withing the node and outside of it", hier_a2av_node_split}, {NULL, NULL, NULL}};
+static const hier_alg_t hier_agv_algs[] = {{"gab", "gatherv + allgatherv + bcast", hier_allgatherv_gab}, {NULL, NULL, NULL}};
 static const hier_alg_t *hier_algs(ucc_coll_type_t ct)
-{ switch (ct) { case UCC_COLL_TYPE_ALLREDUCE: return hier_allreduce_algs; case UCC_COLL_TYPE_BCAST: return hier_bcast_algs; case UCC_COLL_TYPE_REDUCE: return hier_reduce_algs; case UCC_COLL_TYPE_BARRIER: return hier_barrier_algs; default: return NULL; } }
+{ switch (ct) { case UCC_COLL_TYPE_ALLTOALL: return hier_a2a_algs; case UCC_COLL_TYPE_ALLTOALLV: return hier_a2av_algs; case UCC_COLL_TYPE_ALLGATHERV: return hier_agv_algs; case UCC_COLL_TYPE_ALLREDUCE: return hier_allreduce_algs; case UCC_COLL_TYPE_BCAST: return hier_bcast_algs; case UCC_COLL_TYPE_REDUCE: return hier_reduce_algs; case UCC_COLL_TYPE_BARRIER: return hier_barrier_algs; default: return NULL; } }
 static ucc_base_coll_alg_info_t hier_alg_info[UCC_COLL_TYPE_NUM][3];
 
 static ucc_status_t hier_alg_id_to_init(int alg_id, const char *s, ucc_coll_type_t ct, ucc_memory_type_t mt, ucc_base_coll_init_fn_t *init)
@@ -393,7 +567,7 @@ static ucc_status_t hier_team_get_scores(ucc_base_team_t *b_team, ucc_coll_score
 {
     ucc_cl_hier_context_t *ctx = ucc_derived_of(b_team->context, ucc_cl_hier_context_t);
     ucc_memory_type_t mt[3] = {UCC_MEMORY_TYPE_HOST, UCC_MEMORY_TYPE_CUDA, UCC_MEMORY_TYPE_CUDA_MANAGED};
-    uint64_t colls = UCC_COLL_TYPE_ALLREDUCE | UCC_COLL_TYPE_BCAST | UCC_COLL_TYPE_REDUCE | UCC_COLL_TYPE_BARRIER;
+    uint64_t colls = UCC_COLL_TYPE_ALLREDUCE | UCC_COLL_TYPE_BCAST | UCC_COLL_TYPE_REDUCE | UCC_COLL_TYPE_BARRIER | UCC_COLL_TYPE_ALLTOALL | UCC_COLL_TYPE_ALLTOALLV | UCC_COLL_TYPE_ALLGATHERV;
     ucc_coll_score_team_info_t info = {UCC_CL_HIER_DEFAULT_SCORE, b_team->params.size, colls, mt, 3, hier_coll_init, hier_alg_id_to_init};
     ucc_coll_score_t *score;
     ucc_status_t st = ucc_coll_score_build_default(b_team, UCC_CL_HIER_DEFAULT_SCORE, hier_coll_init, colls, mt, 3, &score);

@@ -11,7 +11,7 @@ ucc_config_field_t ucc_tl_nvl_context_config_table[] = {
     {"SYMMETRIC_SIZE", "128Mb", "Size of the data region of the per-team symmetric heap; larger messages are processed in rounds inside one kernel",
      ucc_offsetof(ucc_tl_nvl_context_config_t, symmetric_size), UCC_CONFIG_TYPE_MEMUNITS},
     {"NBLOCKS", "auto", "Thread blocks per collective kernel (auto: chosen from the message size)", ucc_offsetof(ucc_tl_nvl_context_config_t, nblocks), UCC_CONFIG_TYPE_UINT},
-    {"MAX_BLOCKS", "128", "Upper bound of thread blocks per collective kernel (all blocks of all ranks sharing a GPU must be co-resident)",
+    {"MAX_BLOCKS", "256", "Upper bound of thread blocks per collective kernel (all blocks of all ranks sharing a GPU must be co-resident)",
      ucc_offsetof(ucc_tl_nvl_context_config_t, max_blocks), UCC_CONFIG_TYPE_UINT},
     {"NTHREADS", "512", "Threads per block", ucc_offsetof(ucc_tl_nvl_context_config_t, nthreads), UCC_CONFIG_TYPE_UINT},
     {"TIMEOUT", "10s", "Spin budget of a device-side wait before the kernel gives up and the collective fails with UCC_ERR_TIMED_OUT",

@@ -365,7 +365,8 @@ ucc_status_t ucc_tl_nvl_team_get_scores(ucc_base_team_t *b_team, ucc_coll_score_
     /* message-size driven defaults: latency kernel below the threshold, in-switch reduction for big
      * messages when the multicast mapping is live (dt/op it cannot do fall back to twoshot through the
      * score fallback chain because nvls init returns NOT_SUPPORTED) */
-    if (team->nvls) snprintf(sel, sizeof(sel), "allreduce:0-%s:@oneshot#allreduce:%s-inf:@nvls#reduce_scatter:%s-inf:@nvls#reduce_scatterv:%s-inf:@nvls#reduce:%s-inf:@nvls", a, n, n, n, n);
+    /* with two members the switch has nothing to combine: pulling over P2P moves the same bytes with less overhead */
+    if (team->nvls && UCC_TL_TEAM_SIZE(team) > 2) snprintf(sel, sizeof(sel), "allreduce:0-%s:@oneshot#allreduce:%s-inf:@nvls#reduce_scatter:%s-inf:@nvls#reduce_scatterv:%s-inf:@nvls#reduce:%s-inf:@nvls", a, n, n, n, n);
     else snprintf(sel, sizeof(sel), "allreduce:0-%s:@oneshot", a);
     st = ucc_tl_apply_tune(&team->super, score, &info, sel, ctx->cfg.super.super.score_str);
     if (st != UCC_OK) { ucc_coll_score_free(score); return st; }

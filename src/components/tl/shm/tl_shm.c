@@ -101,6 +101,7 @@ static ucc_status_t shm_coll_init_alg(ucc_base_coll_args_t *bargs, ucc_base_team
     ucc_status_t st = ucc_tl_shm_task_alloc(bargs, team, &t);
     if (st != UCC_OK) return st;
     st = shm_task_setup(t);
+    t->build = fn;
     if (st == UCC_OK) st = fn(t);
     if (st != UCC_OK) { t->team->seq_num--; ucc_tl_shm_task_finalize(&t->super); return st; }
     *task_p = &t->super;

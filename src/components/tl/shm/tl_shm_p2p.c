@@ -18,7 +18,6 @@ ucc_status_t ucc_tl_shm_ctx_p2p_init(ucc_tl_shm_context_t *ctx)
 {
     static uint32_t seq = 0;
     uint32_t my_seq = ucc_atomic_fadd32(&seq, 1);
-    ucc_context_t *core = ctx->super.super.ucc_context;
     unsigned n_cells = ctx->cfg.n_cells;
     size_t cell_size;
     ucc_status_t st;

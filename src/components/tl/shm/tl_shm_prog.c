@@ -52,7 +52,7 @@ ucc_status_t ucc_tl_shm_task_alloc(ucc_base_coll_args_t *bargs, ucc_base_team_t 
     t->coll_seq = (team->seq_num++) & 0x7fff;
     t->ops = NULL; t->n_ops = t->cap_ops = t->pc = 0;
     t->reqs = NULL; t->n_reqs = t->cap_reqs = 0; t->etask = NULL; t->own_exec = NULL;
-    t->dt = UCC_DT_INT8; t->op = UCC_OP_SUM; t->alpha = 1.0; t->n_scratch = 0; t->host_copy = NULL;
+    t->dt = UCC_DT_INT8; t->op = UCC_OP_SUM; t->alpha = 1.0; t->n_scratch = 0; t->host_copy = NULL; t->build = NULL; t->setup = NULL;
     t->super.post = ucc_tl_shm_task_post; t->super.progress = ucc_tl_shm_task_progress; t->super.finalize = ucc_tl_shm_task_finalize;
     *task_p = t;
     return UCC_OK;
@@ -121,7 +121,7 @@ void ucc_tl_shm_task_progress(ucc_coll_task_t *ct)
             shm_req_t *r;
             ucc_rank_t peer = ucc_ep_map_eval(t->vmap, op->peer);
             uint64_t tag = shm_make_tag(team, t->coll_seq, op->step);
-            if (getenv("SHM_DBG")) fprintf(stderr, "[r%u/%u scope %d.%d] %s %s peer %u tag %lx buf %p len %zu\n", UCC_TL_TEAM_RANK(team), UCC_TL_TEAM_SIZE(team), team->super.super.params.scope, team->super.super.params.scope_id, ucc_coll_type_str(ct->bargs.args.coll_type), op->type == SHM_OP_SEND ? "send" : "recv", peer, (unsigned long)tag, op->dst, op->len);
+            tl_trace(UCC_TL_TEAM_LIB(team), "[r%u/%u scope %d.%d] %s %s peer %u tag %lx buf %p len %zu", UCC_TL_TEAM_RANK(team), UCC_TL_TEAM_SIZE(team), team->super.super.params.scope, team->super.super.params.scope_id, ucc_coll_type_str(ct->bargs.args.coll_type), op->type == SHM_OP_SEND ? "send" : "recv", peer, (unsigned long)tag, op->dst, op->len);
             st = op->type == SHM_OP_SEND ? ucc_tl_shm_send_nb(team, peer, tag, op->dst, op->len, op->mt, &r)
                                          : ucc_tl_shm_recv_nb(team, peer, tag, op->dst, op->len, op->mt, &r);
             if (st == UCC_OK) st = req_track(t, r);
@@ -168,5 +168,15 @@ ucc_status_t ucc_tl_shm_task_post(ucc_coll_task_t *ct)
 {
     ucc_tl_shm_task_t *t = ucc_derived_of(ct, ucc_tl_shm_task_t);
     t->pc = 0; t->n_reqs = 0; t->etask = NULL;
+    if (ucc_unlikely(ct->flags & UCC_COLL_TASK_FLAG_ARGS_UPDATED) && t->build) {
+        /* a pipelined parent re-targeted the buffers / counts: rebuild the step program in place */
+        ucc_status_t st;
+        ct->flags &= ~UCC_COLL_TASK_FLAG_ARGS_UPDATED;
+        for (unsigned i = 0; i < t->n_scratch; i++) ucc_mc_free(t->scratch[i]);
+        t->n_scratch = 0; t->n_ops = 0; free(t->host_copy); t->host_copy = NULL;
+        st = t->setup ? t->setup(t) : UCC_OK;
+        if (st == UCC_OK) st = t->build(t);
+        if (st != UCC_OK) { ct->status = st; return ucc_task_complete(ct); }
+    }
     return ucc_progress_queue_enqueue(UCC_TL_CORE_CTX(t->team)->pq, ct);
 }

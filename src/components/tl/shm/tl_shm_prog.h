@@ -42,6 +42,9 @@ typedef struct ucc_tl_shm_task {
     ucc_mc_buffer_header_t *scratch[4];
     unsigned           n_scratch;
     void              *host_copy;     /* malloc'ed aux (counts tables etc.) */
+    /* program builder: kept so that a pipelined parent can change bargs.args between posts (UCC_COLL_TASK_FLAG_ARGS_UPDATED) */
+    ucc_status_t     (*build)(struct ucc_tl_shm_task *t);
+    ucc_status_t     (*setup)(struct ucc_tl_shm_task *t);
 } ucc_tl_shm_task_t;
 
 /* builder */

@@ -75,6 +75,7 @@ enum {
     UCC_COLL_TASK_FLAG_IS_PIPELINED_SCHEDULE = UCC_BIT(6),
     UCC_COLL_TASK_FLAG_INTERNAL              = UCC_BIT(7), /* service task: no coll-trace */
     UCC_COLL_TASK_FLAG_AUTO_FINALIZE         = UCC_BIT(8), /* finalize() is called at the end of completion */
+    UCC_COLL_TASK_FLAG_ARGS_UPDATED          = UCC_BIT(9), /* a pipelined parent changed bargs.args since the last post */
 };
 
 struct ucc_coll_task {

@@ -5,7 +5,6 @@ static ucc_status_t launch_frag(ucc_schedule_pipelined_t *sp, int slot, int glob
 {
     ucc_schedule_t *f = sp->frags[slot];
     ucc_status_t    st;
-    int             pslot = (slot - 1 + sp->n_frags) % sp->n_frags;
     if (sp->frag_setup) { st = sp->frag_setup(sp, f, global); if (st != UCC_OK) return st; }
     sp->slot_global[slot] = global;
     f->n_completed_tasks  = 0;
@@ -20,9 +19,11 @@ static ucc_status_t launch_frag(ucc_schedule_pipelined_t *sp, int slot, int glob
         t->n_deps_satisfied = 0;
         t->generation++;
         if (xdep) {
-            /* predecessor = task j of global-1: already fired if its slot moved on, or fired in its current run */
-            int pg = sp->slot_global[pslot];
-            if (pg > global - 1 || pg < 0 || (pg == global - 1 && sp->fired[pslot][j])) t->n_deps_satisfied = 1;
+            /* predecessor = task j of fragment global-1.  Fragments are launched in order but may finish out of
+             * order, so look the predecessor up: not resident any more == completed, resident == check its fire mark */
+            int pslot = -1;
+            for (int s = 0; s < sp->n_frags; s++) if (s != slot && sp->slot_global[s] == global - 1) pslot = s;
+            if (pslot < 0 || j >= sp->frags[pslot]->n_tasks || sp->fired[pslot][j]) t->n_deps_satisfied = 1;
         } else if (global > 0 && sp->order != UCC_PIPELINE_PARALLEL && sp->n_frags == 1) {
             /* single slot: strictly sequential by construction */
         }
@@ -44,10 +45,11 @@ static void find_task(ucc_schedule_pipelined_t *sp, ucc_coll_task_t *t, int *slo
  * next fragment if that fragment is armed and waiting for exactly this predecessor */
 static ucc_status_t fire(ucc_schedule_pipelined_t *sp, int ps, int pj)
 {
-    int ss = (ps + 1) % sp->n_frags;
+    int ss = -1;
     if (sp->fired[ps][pj]) return UCC_OK;
     sp->fired[ps][pj] = 1;
-    if (sp->slot_global[ss] >= 0 && sp->slot_global[ss] == sp->slot_global[ps] + 1 && (unsigned)pj < sp->frags[ss]->n_tasks) {
+    for (int s = 0; s < sp->n_frags; s++) if (s != ps && sp->slot_global[s] == sp->slot_global[ps] + 1) ss = s;
+    if (ss >= 0 && (unsigned)pj < sp->frags[ss]->n_tasks) {
         ucc_coll_task_t *succ = sp->frags[ss]->tasks[pj];
         if (succ->super.status == UCC_OPERATION_INITIALIZED) return ucc_dependency_handler(sp->frags[ps]->tasks[pj], succ);
     }
@@ -62,7 +64,11 @@ static ucc_status_t cross_frag_handler(ucc_coll_task_t *parent, ucc_coll_task_t 
     (void)task;
     ucc_recursive_spin_lock(&sp->lock);
     find_task(sp, parent, &ps, &pj);
-    if (ps >= 0 && sp->slot_global[ps] >= 0) st = fire(sp, ps, pj);
+    /* an event of an incarnation that has been re-armed since is stale (everything it had to deliver was delivered by
+     * frag_completed_handler): the current incarnation has emitted COMPLETED only if it is OK, TASK_STARTED only if posted */
+    if (ps >= 0 && sp->slot_global[ps] >= 0 && sp->slot_global[ps] < sp->n_frags_total &&
+        (sp->order == UCC_PIPELINE_SEQUENTIAL ? parent->super.status == UCC_OK : parent->super.status != UCC_OPERATION_INITIALIZED))
+        st = fire(sp, ps, pj);
     ucc_recursive_spin_unlock(&sp->lock);
     return st;
 }
@@ -93,7 +99,7 @@ static ucc_status_t frag_completed_handler(ucc_coll_task_t *parent, ucc_coll_tas
             st = launch_frag(sp, slot, g); /* round-robin: slot == g % n_frags */
         } else {
             for (unsigned j = 0; j < frag->n_tasks; j++) sp->fired[slot][j] = 1;
-            sp->slot_global[slot] = sp->n_frags_total + slot; /* idle: "moved on" for successor checks */
+            sp->slot_global[slot] = sp->n_frags_total + slot; /* idle: not a predecessor of anything */
         }
     }
     ucc_recursive_spin_unlock(&sp->lock);

@@ -76,3 +76,72 @@ def test_hier_single_node_falls_back():
         dst = [np.zeros(10, np.int32) for _ in range(4)]
         run(team, [coll_args("allreduce", src[r], dst[r], dt="int32", op="sum") for r in range(4)])
         assert all(np.array_equal(d, np.full(10, 10)) for d in dst)
+
+
+@pytest.mark.parametrize("n,ppn", [(4, 2), (6, 3), (8, 4), (5, 2)])
+def test_hier_alltoall_node_split(n, ppn):
+    with job(n, ppn) as j:
+        team = j.create_team()
+        rng = np.random.default_rng(n)
+        count = 5
+        src = [rng.integers(0, 1 << 30, count * n).astype(np.int32) for _ in range(n)]
+        dst = [np.zeros(count * n, np.int32) for _ in range(n)]
+        run(team, [coll_args("alltoall", src[r], dst[r], dt="int32") for r in range(n)])
+        for r in range(n):
+            assert np.array_equal(dst[r], np.concatenate([src[p][r * count:(r + 1) * count] for p in range(n)])), r
+        sc = [[(r + 2 * p) % 4 for p in range(n)] for r in range(n)]
+        rc = [[sc[p][r] for p in range(n)] for r in range(n)]
+        sd = [np.concatenate([[0], np.cumsum(c)[:-1]]) for c in sc]
+        rd = [np.concatenate([[0], np.cumsum(c)[:-1]]) for c in rc]
+        src = [rng.random(max(1, sum(sc[r]))).astype(np.float32) for r in range(n)]
+        dst = [np.zeros(max(1, sum(rc[r])), np.float32) for r in range(n)]
+        run(team, [coll_args("alltoallv", src[r], dst[r], src_counts=sc[r], src_displs=sd[r], dst_counts=rc[r], dst_displs=rd[r]) for r in range(n)])
+        for r in range(n):
+            exp = np.concatenate([src[p][sd[p][r]:sd[p][r] + sc[p][r]] for p in range(n)])
+            assert np.array_equal(dst[r][:len(exp)], exp), r
+
+
+@pytest.mark.parametrize("n,ppn", [(4, 2), (6, 3), (8, 4), (7, 3)])
+@pytest.mark.parametrize("inplace", [False, True])
+def test_hier_allgatherv_gab(n, ppn, inplace):
+    with job(n, ppn) as j:
+        team = j.create_team()
+        rng = np.random.default_rng(n)
+        counts = [3 + (r % 4) for r in range(n)]
+        displs = np.concatenate([[0], np.cumsum(counts)[:-1]])
+        src = [rng.integers(0, 100, counts[r]).astype(np.int32) for r in range(n)]
+        dst = [np.zeros(sum(counts), np.int32) for _ in range(n)]
+        if inplace:
+            for r in range(n):
+                dst[r][displs[r]:displs[r] + counts[r]] = src[r]
+            run(team, [coll_args("allgatherv", None, dst[r], dt="int32", dst_counts=counts, dst_displs=displs, inplace=True) for r in range(n)])
+        else:
+            run(team, [coll_args("allgatherv", src[r], dst[r], dt="int32", dst_counts=counts, dst_displs=displs) for r in range(n)])
+        for r in range(n):
+            assert np.array_equal(dst[r], np.concatenate(src)), r
+
+
+@pytest.mark.parametrize("order", ["parallel", "ordered", "sequential"])
+@pytest.mark.parametrize("n,ppn", [(4, 2), (6, 3)])
+def test_hier_allreduce_rab_pipelined(n, ppn, order):
+    env_extra = {"UCC_CL_HIER_ALLREDUCE_RAB_PIPELINE": f"thresh=1k:fragsize=4k:nfrags=3:pdepth=2:{order}"}
+    env = {"UCC_CLS": "hier,basic", "UCC_CL_HIER_TLS": "shm,self", "UCC_CL_BASIC_TLS": "shm,self", "UCC_CL_HIER_TUNE": "allreduce:0-inf:@rab"}
+    env.update(env_extra)
+    with UccJob(n, ppn=ppn, env=env, cls="hier,basic") as j:
+        team = j.create_team()
+        rng = np.random.default_rng(5)
+        for count in (100, 3000, 10001):   # below threshold, 6 fragments, ragged 20 fragments
+            for inplace in (False, True):
+                src = [rng.integers(-50, 50, count).astype(np.int64) for _ in range(n)]
+                exp = np.sum(src, 0)
+                dst = [s.copy() for s in src] if inplace else [np.zeros(count, np.int64) for _ in range(n)]
+                args = [coll_args("allreduce", None if inplace else src[r], dst[r], dt="int64", op="sum", inplace=inplace, persistent=True) for r in range(n)]
+                req = team.coll(args)
+                for rep in range(2):    # persistent: the pipeline must re-arm cleanly
+                    if inplace and rep:
+                        for r in range(n):
+                            dst[r][:] = src[r]
+                    assert req.run() == U.UCC_OK
+                    for r in range(n):
+                        assert np.array_equal(dst[r], exp), (count, inplace, rep, r)
+                req.finalize()
