@@ -64,7 +64,8 @@ __global__ void __launch_bounds__(NVL_THREADS_MAX) nvl_exchange_kernel(nvl_xchg_
     char *mydata = data_of(t, me);
     /* phase A: publish my bytes (and the offset table peers use to find their block) */
     if (a.publish_table && blockIdx.x == 0 && (int)threadIdx.x < N) reinterpret_cast<uint64_t *>(mydata)[threadIdx.x] = (uint64_t)a.stage_off[threadIdx.x];
-    if (a.src_bytes) copy_bytes_grid<false>(mydata + NVL_XCHG_TABLE_BYTES, static_cast<const char *>(a.src), a.src_bytes);
+    /* zero-copy mode: the peers read my user buffer in place, nothing to stage */
+    if (a.src_bytes && !a.direct) copy_bytes_grid<false>(mydata + NVL_XCHG_TABLE_BYTES, static_cast<const char *>(a.src), a.src_bytes);
     bs.signal(t, 1);
     bs.wait_all_blocks(t, 1);
     /* phase B: pull */
@@ -76,7 +77,7 @@ __global__ void __launch_bounds__(NVL_THREADS_MAX) nvl_exchange_kernel(nvl_xchg_
         if (p == me) { if (d != static_cast<const char *>(a.src) + a.self_off) copy_bytes_grid<false>(d, static_cast<const char *>(a.src) + a.self_off, n); continue; }
         size_t off = a.pull_off[p];
         if (off == NVL_XCHG_LOOKUP) off = (size_t) * reinterpret_cast<volatile const uint64_t *>(data_of(t, p) + (size_t)me * 8);
-        copy_bytes_grid<true>(d, data_of(t, p) + NVL_XCHG_TABLE_BYTES + off, n);
+        copy_bytes_grid<true>(d, (a.direct ? a.d.src[p] : data_of(t, p) + NVL_XCHG_TABLE_BYTES) + off, n);
     }
     bs.signal(t, 2);
     bs.wait_all_blocks(t, 2);
@@ -121,6 +122,16 @@ extern "C" cudaError_t nvl_launch_reduce_staged(const nvl_red_args_t *a, int nbl
     if (nthreads > NVL_THREADS_MAX) nthreads = NVL_THREADS_MAX;
     if (a->dt < 0 || a->dt >= NVL_DT_LAST) return cudaErrorInvalidValue;
     return staged_fns[a->dt](a, nblocks, nthreads, s);
+}
+#define DECLD(_s) extern "C" cudaError_t nvl_launch_direct_##_s(const nvl_red_args_t *, int, int, cudaStream_t);
+DECLD(i8) DECLD(i16) DECLD(i32) DECLD(i64) DECLD(u8) DECLD(u16) DECLD(u32) DECLD(u64) DECLD(f16) DECLD(f32) DECLD(f64) DECLD(bf16)
+static const nvl_red_launch_fn direct_fns[NVL_DT_LAST] = {nvl_launch_direct_i8, nvl_launch_direct_i16, nvl_launch_direct_i32, nvl_launch_direct_i64, nvl_launch_direct_u8, nvl_launch_direct_u16,
+    nvl_launch_direct_u32, nvl_launch_direct_u64, nvl_launch_direct_f16, nvl_launch_direct_f32, nvl_launch_direct_f64, nvl_launch_direct_bf16};
+extern "C" cudaError_t nvl_launch_reduce_direct(const nvl_red_args_t *a, int nblocks, int nthreads, cudaStream_t s)
+{
+    if (nthreads > NVL_THREADS_MAX) nthreads = NVL_THREADS_MAX;
+    if (a->dt < 0 || a->dt >= NVL_DT_LAST) return cudaErrorInvalidValue;
+    return direct_fns[a->dt](a, nblocks, nthreads, s);
 }
 extern "C" cudaError_t nvl_launch_exchange(const nvl_xchg_args_t *a, int nblocks, int nthreads, cudaStream_t s)
 {

@@ -56,6 +56,14 @@ typedef enum {
     NVL_RED_REDUCE           /* only `root` gets the reduced vector */
 } nvl_red_kind_t;
 
+/* zero-copy view of the members' USER buffers (CUDA IPC mappings, or plain pointers inside one process), resolved
+ * by the host-side buffer exchange (tl_nvl_direct.c) right before the launch */
+typedef struct nvl_direct {
+    const char *src[NVL_MAX_PEERS];
+    char       *dst[NVL_MAX_PEERS];
+} nvl_direct_t;
+typedef enum { NVL_DIRECT_NONE = 0, NVL_DIRECT_FULL = 1, NVL_DIRECT_DST = 2 } nvl_direct_mode_t;
+
 typedef struct nvl_red_args {
     nvl_team_dev_t team;
     const void    *src;
@@ -65,6 +73,9 @@ typedef struct nvl_red_args {
     int            use_nvls;    /* reduce in the switch (multimem.ld_reduce) instead of pulling */
     size_t         rs_offset[NVL_MAX_PEERS]; /* REDUCE_SCATTER(V): element offset / count of each rank's block */
     size_t         rs_count[NVL_MAX_PEERS];
+    int            direct;      /* nvl_direct_mode_t: FULL = read peers' src and write peers' dst in place (no staging at all);
+                                   DST = staged/NVLS reduction whose result goes straight into every member's dst (no copy-out) */
+    nvl_direct_t   d;
 } nvl_red_args_t;
 
 /* generic staged exchange: allgather(v), alltoall(v), bcast, gather, scatter */
@@ -82,6 +93,8 @@ typedef struct nvl_xchg_args {
     size_t         pull_off[NVL_MAX_PEERS], pull_bytes[NVL_MAX_PEERS], dst_off[NVL_MAX_PEERS];
     size_t         self_off;
     int            publish_table;
+    int            direct;       /* pull from the peers' user buffers (d.src[p]) instead of their staged copies */
+    nvl_direct_t   d;
 } nvl_xchg_args_t;
 
 #ifdef __cplusplus
@@ -94,6 +107,8 @@ int          nvl_nvls_supports(int dt, int op);
 cudaError_t  nvl_launch_allreduce_oneshot(const nvl_red_args_t *a, int nblocks, int nthreads, cudaStream_t s);
 /* bandwidth path: staged two-shot (P2P pull or NVLS) for allreduce / reduce_scatter(v) / reduce */
 cudaError_t  nvl_launch_reduce_staged(const nvl_red_args_t *a, int nblocks, int nthreads, cudaStream_t s);
+/* zero-copy two-shot: every rank reduces its slice straight out of the members' src buffers into their dst buffers */
+cudaError_t  nvl_launch_reduce_direct(const nvl_red_args_t *a, int nblocks, int nthreads, cudaStream_t s);
 cudaError_t  nvl_launch_exchange(const nvl_xchg_args_t *a, int nblocks, int nthreads, cudaStream_t s);
 cudaError_t  nvl_launch_barrier(const nvl_team_dev_t *t, cudaStream_t s);
 cudaError_t  nvl_launch_ctrl_init(void *heap_base, cudaStream_t s);

@@ -115,9 +115,13 @@ template <typename T> static __device__ __forceinline__ void make_plan(const nvl
     pl.rounds = (int)((pl.slice_max + pl.cap_e - 1) / pl.cap_e);
 }
 
+/* where phase B puts a reduced vector when the members' dst buffers are mapped (NVL_DIRECT_DST): pointers are
+ * pre-offset to the first element of my slice in this round; n == 0 means "publish through the heap" */
+struct DOut { char *p[NVL_MAX_PEERS]; int n; };
+
 /* phase B worker: reduce vectors [j0,jend) of my slice. U vectors x NP sources in flight per thread. */
 template <typename T, int OP, int NP, int U>
-static __device__ __forceinline__ void reduce_p2p(const nvl_red_args_t &a, char *const *pd, size_t base, size_t j0, size_t jend, T *db, size_t rc, bool dal, float inv_n)
+static __device__ __forceinline__ void reduce_p2p(const nvl_red_args_t &a, char *const *pd, size_t base, size_t j0, size_t jend, T *db, size_t rc, bool dal, float inv_n, const DOut &dout)
 {
     constexpr int E = 16 / sizeof(T);
     const size_t nt = blockDim.x;
@@ -141,7 +145,9 @@ static __device__ __forceinline__ void reduce_p2p(const nvl_red_args_t &a, char 
                 for (int i = 1; i < NP; i++) if (i < N) acc.add(x[u][i]);
                 const uint4 r = acc.get(inv_n);
                 const size_t o = base + jj * 16;
-                if (a.kind == NVL_RED_ALLREDUCE) {
+                if (dout.n) {
+                    for (int i = 0; i < dout.n; i++) store_dst_vec<T>(reinterpret_cast<T *>(dout.p[i]), jj * E, rc, true, r);
+                } else if (a.kind == NVL_RED_ALLREDUCE) {
 #pragma unroll
                     for (int i = 0; i < NP; i++) if (i < N) st_v4(pd[i] + o, r);
                 } else if (a.kind == NVL_RED_REDUCE) st_v4(data_of(a.team, a.root) + o, r);
@@ -152,7 +158,7 @@ static __device__ __forceinline__ void reduce_p2p(const nvl_red_args_t &a, char 
 }
 
 template <typename T, int OP, int U>
-static __device__ __forceinline__ void reduce_nvls(const nvl_red_args_t &a, size_t base, size_t j0, size_t jend, T *db, size_t rc, bool dal, float inv_n)
+static __device__ __forceinline__ void reduce_nvls(const nvl_red_args_t &a, size_t base, size_t j0, size_t jend, T *db, size_t rc, bool dal, float inv_n, const DOut &dout)
 {
     constexpr int E = 16 / sizeof(T);
     const size_t nt = blockDim.x;
@@ -167,7 +173,8 @@ static __device__ __forceinline__ void reduce_nvls(const nvl_red_args_t &a, size
             if (jj < jend) {
                 uint4 v = r[u];
                 if (OP == NVL_OP_AVG) { VecAcc<T, OP> acc; acc.set(v); v = acc.get(inv_n); }
-                if (a.kind == NVL_RED_ALLREDUCE) mc_st_v4(mc + jj * 16, v);
+                if (dout.n) { for (int i = 0; i < dout.n; i++) store_dst_vec<T>(reinterpret_cast<T *>(dout.p[i]), jj * E, rc, true, v); }
+                else if (a.kind == NVL_RED_ALLREDUCE) mc_st_v4(mc + jj * 16, v);
                 else if (a.kind == NVL_RED_REDUCE) st_v4(data_of(a.team, a.root) + base + jj * 16, v);
                 else store_dst_vec<T>(db, jj * E, rc, dal, v);
             }
@@ -186,6 +193,7 @@ static __device__ __forceinline__ void staged_body(const nvl_red_args_t &a, Bloc
     const size_t cap_bytes = pl.cap_e * sizeof(T);
     const float inv_n = 1.0f / (float)N;
     const bool nvls = a.use_nvls && t.mc_heap != nullptr;
+    const bool direct_dst = a.direct == NVL_DIRECT_DST && a.kind != NVL_RED_REDUCE_SCATTER;
     char *mydata = data_of(t, me);
     char *pd[NVL_MAX_PEERS]; /* pd[i] = data region of my i-th right neighbour (i = 0: myself) */
 #pragma unroll
@@ -218,13 +226,20 @@ static __device__ __forceinline__ void staged_body(const nvl_red_args_t &a, Bloc
             const size_t jend = dmin(j1, (rc + E - 1) / E), base = (size_t)me * cap_bytes;
             T *db = dst + (a.kind == NVL_RED_REDUCE_SCATTER ? 0 : pl.off[me]) + e0;
             const bool dal = ((uintptr_t)db & 15) == 0;
-            if (nvls) reduce_nvls<T, OP, 8>(a, base, j0, jend, db, rc, dal, inv_n);
-            else if (N <= 2) reduce_p2p<T, OP, 2, 8>(a, pd, base, j0, jend, db, rc, dal, inv_n);
-            else if (N <= 4) reduce_p2p<T, OP, 4, 4>(a, pd, base, j0, jend, db, rc, dal, inv_n);
-            else if (N <= 8) reduce_p2p<T, OP, 8, 2>(a, pd, base, j0, jend, db, rc, dal, inv_n);
-            else reduce_p2p<T, OP, NVL_MAX_PEERS, 1>(a, pd, base, j0, jend, db, rc, dal, inv_n);
+            DOut dout; dout.n = 0;
+            if (direct_dst) { /* results go straight into the members' dst buffers: no heap publish, no phase C */
+                const size_t eo = (pl.off[me] + e0) * sizeof(T);
+                if (a.kind == NVL_RED_ALLREDUCE) { for (int i = 0; i < N; i++) { int p = me + i; if (p >= N) p -= N; dout.p[i] = a.d.dst[p] + eo; } dout.n = N; }
+                else { dout.p[0] = a.d.dst[a.root] + eo; dout.n = 1; }
+            }
+            if (nvls) reduce_nvls<T, OP, 8>(a, base, j0, jend, db, rc, dal, inv_n, dout);
+            else if (N <= 2) reduce_p2p<T, OP, 2, 8>(a, pd, base, j0, jend, db, rc, dal, inv_n, dout);
+            else if (N <= 4) reduce_p2p<T, OP, 4, 4>(a, pd, base, j0, jend, db, rc, dal, inv_n, dout);
+            else if (N <= 8) reduce_p2p<T, OP, 8, 2>(a, pd, base, j0, jend, db, rc, dal, inv_n, dout);
+            else reduce_p2p<T, OP, NVL_MAX_PEERS, 1>(a, pd, base, j0, jend, db, rc, dal, inv_n, dout);
         }
         bs.barrier(t, 2 * k + 2);
+        if (direct_dst) continue;
 
         /* phase C: my heap now holds vector range [j0,j1) of every reduced slice */
         if (a.kind == NVL_RED_ALLREDUCE || (a.kind == NVL_RED_REDUCE && me == a.root)) {
@@ -254,10 +269,91 @@ template <typename T> __global__ void __launch_bounds__(NVL_THREADS_MAX, 2) nvl_
 }
 
 
-/* one translation unit per datatype defines these two launchers */
+/* ------------------------------------------------------------------ */
+/* zero-copy two-shot: no staging, no copy-out                         */
+/*   barrier (every member's kernel is running => its src is final and */
+/*   its dst may be written) -> reduce my slice straight from the N    */
+/*   src buffers -> store into every member's dst -> barrier.          */
+/*   Each byte crosses NVLink exactly once per direction and HBM is    */
+/*   touched only for the payload itself.                              */
+/* ------------------------------------------------------------------ */
+template <typename T, int OP, int NP, int U>
+static __device__ __forceinline__ void direct_p2p(int N, const char *const *sp, const DOut &dout, size_t j0, size_t jend, float inv_n)
+{
+    const size_t nt = blockDim.x;
+    for (size_t j = j0 + threadIdx.x; j < jend; j += U * nt) {
+        uint4 x[U][NP];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const size_t jj = j + u * nt;
+            if (jj < jend) {
+#pragma unroll
+                for (int i = 0; i < NP; i++) if (i < N) x[u][i] = ld_peer_v4(sp[i] + jj * 16);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const size_t jj = j + u * nt;
+            if (jj < jend) {
+                VecAcc<T, OP> acc; acc.set(x[u][0]);
+#pragma unroll
+                for (int i = 1; i < NP; i++) if (i < N) acc.add(x[u][i]);
+                const uint4 r = acc.get(inv_n);
+#pragma unroll
+                for (int i = 0; i < NP; i++) if (i < dout.n) st_v4(dout.p[i] + jj * 16, r);
+            }
+        }
+    }
+}
+
+template <typename T, int OP>
+static __device__ __forceinline__ void direct_body(const nvl_red_args_t &a, const SlicePlan &pl)
+{
+    constexpr int E = 16 / sizeof(T);
+    const nvl_team_dev_t &t = a.team;
+    const int N = t.size, me = t.rank, nb = gridDim.x, b = blockIdx.x;
+    const size_t cnt = pl.cnt[me], nfull = cnt / E, per = (nfull + nb - 1) / nb;
+    const size_t j0 = dmin((size_t)b * per, nfull), j1 = dmin(j0 + per, nfull);
+    const size_t so = pl.off[me] * sizeof(T);
+    const float inv_n = 1.0f / (float)N;
+    const char *sp[NVL_MAX_PEERS]; DOut dout;
+#pragma unroll
+    for (int i = 0; i < NVL_MAX_PEERS; i++) { int p = me + i; if (p >= N) p -= N; sp[i] = i < N ? a.d.src[p] + so : nullptr; }
+    if (a.kind == NVL_RED_ALLREDUCE) { for (int i = 0; i < N; i++) { int p = me + i; if (p >= N) p -= N; dout.p[i] = a.d.dst[p] + so; } dout.n = N; }
+    else if (a.kind == NVL_RED_REDUCE) { dout.p[0] = a.d.dst[a.root] + so; dout.n = 1; }
+    else { dout.p[0] = static_cast<char *>(a.dst); dout.n = 1; } /* reduce_scatter(v): my block, already a local pointer */
+    if (N <= 2) direct_p2p<T, OP, 2, 8>(N, sp, dout, j0, j1, inv_n);
+    else if (N <= 4) direct_p2p<T, OP, 4, 4>(N, sp, dout, j0, j1, inv_n);
+    else if (N <= 8) direct_p2p<T, OP, 8, 2>(N, sp, dout, j0, j1, inv_n);
+    else direct_p2p<T, OP, NVL_MAX_PEERS, 1>(N, sp, dout, j0, j1, inv_n);
+    /* ragged tail of the slice (fewer than E elements): one thread, element by element */
+    if (b == nb - 1 && threadIdx.x == 0 && nfull * E < cnt) {
+        for (size_t e = nfull * E; e < cnt; e++) {
+            typename AccOf<T>::type acc = to_acc<T>(reinterpret_cast<const T *>(sp[0])[e]);
+            for (int i = 1; i < N; i++) acc = OpFn<OP, typename AccOf<T>::type>::f(acc, to_acc<T>(reinterpret_cast<const T *>(sp[i])[e]));
+            if (OP == NVL_OP_AVG) acc = (typename AccOf<T>::type)(acc * (typename AccOf<T>::type)inv_n);
+            for (int i = 0; i < dout.n; i++) reinterpret_cast<T *>(dout.p[i])[e] = from_acc<T>(acc);
+        }
+    }
+}
+
+template <typename T> __global__ void __launch_bounds__(NVL_THREADS_MAX, 2) nvl_reduce_direct_kernel(nvl_red_args_t a)
+{
+    BlockSync bs; bs.init(a.team);
+    SlicePlan pl; make_plan<T>(a, pl);
+    bs.barrier(a.team, 1);
+#define CALL_DIRECT(_T, _OP) direct_body<_T, _OP>(a, pl)
+    NVL_DISPATCH_OP(T, a.op, CALL_DIRECT);
+    bs.barrier(a.team, 2);
+    bs.finish(2);
+}
+
+/* one translation unit per datatype defines these launchers */
 #define NVL_INSTANTIATE_REDUCE(_T, _suffix)                                                                              \
     extern "C" cudaError_t nvl_launch_oneshot_##_suffix(const nvl_red_args_t *a, int nblocks, int nthreads, cudaStream_t s) \
     { nvl_allreduce_oneshot_kernel<_T><<<nblocks, nthreads, 0, s>>>(*a); return cudaGetLastError(); }                     \
     extern "C" cudaError_t nvl_launch_staged_##_suffix(const nvl_red_args_t *a, int nblocks, int nthreads, cudaStream_t s)  \
-    { nvl_reduce_staged_kernel<_T><<<nblocks, nthreads, 0, s>>>(*a); return cudaGetLastError(); }
+    { nvl_reduce_staged_kernel<_T><<<nblocks, nthreads, 0, s>>>(*a); return cudaGetLastError(); }                      \
+    extern "C" cudaError_t nvl_launch_direct_##_suffix(const nvl_red_args_t *a, int nblocks, int nthreads, cudaStream_t s)  \
+    { nvl_reduce_direct_kernel<_T><<<nblocks, nthreads, 0, s>>>(*a); return cudaGetLastError(); }
 #endif

@@ -20,6 +20,8 @@
 #include "core/ucc_team.h"
 #include "core/ucc_ee.h"
 #include "utils/ucc_mpool.h"
+#include "utils/ucc_list.h"
+#include "utils/ucc_atomic.h"
 #include "utils/cuda/ucc_cuda_util.h"
 #include "kernels/nvl_kernels.h"
 
@@ -39,7 +41,19 @@ typedef struct ucc_tl_nvl_context_config {
     size_t   oneshot_thresh;   /* allreduce: one-shot push below, two-shot above */
     size_t   nvls_thresh;      /* allreduce: use NVLS at or above this size */
     int      fd_via_pidfd;     /* ternary: try pidfd_getfd before the unix socket */
+    int      zcopy;            /* ternary: read / write the members' user buffers in place (CUDA IPC) */
+    size_t   zcopy_thresh;     /* ... for messages of at least this size */
 } ucc_tl_nvl_context_config_t;
+
+/* ---- zero-copy buffer exchange board (tl_nvl_direct.c): one single-writer POSIX shm segment per rank ---- */
+#define NVL_XB_SLOTS 64
+#define NVL_GATE_SLOTS 1024
+#define NVL_IPC_CACHE_MAX 64
+typedef enum { NVL_XB_NONE = 0, NVL_XB_EMPTY, NVL_XB_RAW, NVL_XB_IPC } nvl_xb_kind_t;
+typedef struct nvl_xb_buf { int32_t kind; int32_t pad; uint64_t base, off, len, alloc_len; cudaIpcMemHandle_t handle; } nvl_xb_buf_t;
+typedef struct nvl_xb_entry { uint64_t seq; nvl_xb_buf_t src, dst; } nvl_xb_entry_t;
+typedef struct nvl_xb_seg { uint64_t consumed; uint64_t pad[7]; nvl_xb_entry_t e[NVL_XB_SLOTS]; } nvl_xb_seg_t;
+typedef struct nvl_ipc_cache { unsigned n; struct { uint64_t base; cudaIpcMemHandle_t handle; void *mapped; } e[NVL_IPC_CACHE_MAX]; } nvl_ipc_cache_t;
 
 typedef struct ucc_tl_nvl_lib { ucc_tl_lib_t super; } ucc_tl_nvl_lib_t;
 
@@ -66,6 +80,7 @@ typedef struct nvl_rank_info {
     uint64_t size;
     cudaIpcMemHandle_t ipc;
     char     sock[48];   /* abstract unix socket serving the fds */
+    char     xb_name[48];/* POSIX shm name of this rank's buffer exchange board ("" = none) */
 } nvl_rank_info_t;
 
 typedef enum { NVL_TEAM_INIT, NVL_TEAM_XCHG_INFO, NVL_TEAM_MAP, NVL_TEAM_SYNC1, NVL_TEAM_MC_CREATE, NVL_TEAM_MC_IMPORT,
@@ -100,9 +115,24 @@ typedef struct ucc_tl_nvl_team {
     cudaStream_t      stream;
     uint32_t         *host_err;             /* pinned, device mapped */
     uint32_t          seq_num;
+    /* zero-copy exchange */
+    int               zcopy;                /* boards of all members are mapped */
+    char              xb_name[48]; int xb_named;
+    nvl_xb_seg_t     *xb_mine, *xb[NVL_MAX_PEERS];
+    nvl_ipc_cache_t   ipc_cache[NVL_MAX_PEERS];
+    uint64_t          xb_seq;               /* next exchange sequence (advances at post, same order on every rank) */
+    /* launch ordering: kernels of one team must start in post order on every rank (the device-side epochs assume it) */
+    ucc_list_link_t   launch_q;             /* posted tasks whose kernel is not launched yet */
+    ucc_spinlock_t    launch_lock;
+    cudaStream_t      last_stream;          /* stream of the most recent launch */
+    cudaEvent_t       order_event;          /* spare event: swapped with a finalized task's event that last_event points to */
+    cudaEvent_t       last_event;           /* completion event of the most recent launch */
+    uint32_t         *gates;                /* device words user streams wait on while their collective is deferred */
+    uint32_t          gate_seq;
 } ucc_tl_nvl_team_t;
 
 typedef enum { NVL_TASK_REDUCE_ONESHOT, NVL_TASK_REDUCE_STAGED, NVL_TASK_XCHG, NVL_TASK_BARRIER } nvl_task_kind_t;
+typedef enum { NVL_TASK_LAUNCHED, NVL_TASK_QUEUED } nvl_task_state_t;
 typedef struct ucc_tl_nvl_task {
     ucc_coll_task_t     super;
     ucc_tl_nvl_team_t  *team;
@@ -112,7 +142,27 @@ typedef struct ucc_tl_nvl_task {
     cudaEvent_t         event;
     cudaStream_t        stream;     /* stream of the current post */
     int                 captured;   /* posted into a capturing stream: completes immediately */
+    /* zero-copy / deferred launch */
+    nvl_task_state_t    state;
+    ucc_list_link_t     q_elem;
+    int                 want_direct;   /* try the in-place kernels for this collective (nvl_direct_mode_t, 0 = no) */
+    int                 need_src, need_dst;
+    const void         *exp_src; void *exp_dst; size_t exp_src_len, exp_dst_len; /* what is published to the peers */
+    uint64_t            cseq;
+    int                 published;
+    int                 gated;         /* the user's stream is parked on gates[gate_idx] until the deferred kernel ran */
+    uint32_t            gate_val;
+    cudaEvent_t         in_event;
+    int                 nblocks_direct;
 } ucc_tl_nvl_task_t;
+
+ucc_status_t ucc_tl_nvl_xb_create(ucc_tl_nvl_team_t *team);
+ucc_status_t ucc_tl_nvl_xb_attach(ucc_tl_nvl_team_t *team);
+void         ucc_tl_nvl_xb_unlink(ucc_tl_nvl_team_t *team);
+void         ucc_tl_nvl_xb_release(ucc_tl_nvl_team_t *team);
+int          ucc_tl_nvl_xb_publish(ucc_tl_nvl_team_t *team, uint64_t cseq, const void *src, size_t src_len, void *dst, size_t dst_len, int usable);
+int          ucc_tl_nvl_xb_ready(ucc_tl_nvl_team_t *team, uint64_t cseq);
+int          ucc_tl_nvl_xb_resolve(ucc_tl_nvl_team_t *team, uint64_t cseq, int need_src, int need_dst, int need_align, const void *my_src, void *my_dst, nvl_direct_t *d);
 
 #define NVL_CTX(_team) ucc_derived_of((_team)->super.super.context, ucc_tl_nvl_context_t)
 extern ucc_tl_iface_t ucc_tl_nvl;

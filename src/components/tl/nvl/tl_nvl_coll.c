@@ -39,7 +39,10 @@ static ucc_status_t nvl_launch(ucc_tl_nvl_task_t *t, cudaStream_t s)
     cudaError_t e;
     switch (t->kind) {
     case NVL_TASK_REDUCE_ONESHOT: e = nvl_launch_allreduce_oneshot(&t->u.red, t->nblocks, t->nthreads, s); break;
-    case NVL_TASK_REDUCE_STAGED: e = nvl_launch_reduce_staged(&t->u.red, t->nblocks, t->nthreads, s); break;
+    case NVL_TASK_REDUCE_STAGED:
+        if (t->u.red.direct == NVL_DIRECT_FULL) e = nvl_launch_reduce_direct(&t->u.red, t->nblocks_direct, t->nthreads, s);
+        else e = nvl_launch_reduce_staged(&t->u.red, t->nblocks, t->nthreads, s);
+        break;
     case NVL_TASK_XCHG: e = nvl_launch_exchange(&t->u.xchg, t->nblocks, t->nthreads, s); break;
     default: e = nvl_launch_barrier(&t->team->dev, s); break;
     }
@@ -47,10 +50,66 @@ static ucc_status_t nvl_launch(ucc_tl_nvl_task_t *t, cudaStream_t s)
     return UCC_OK;
 }
 
+/* Kernels of one team must start in post order on every rank (the device-side epochs count launches), even when
+ * consecutive posts use different streams: chain them with the completion event of the previous launch. */
+static ucc_status_t launch_ordered(ucc_tl_nvl_task_t *t, cudaStream_t s)
+{
+    ucc_tl_nvl_team_t *team = t->team;
+    ucc_status_t st;
+    if (t->captured) return nvl_launch(t, s);
+    if (team->last_event && team->last_stream != s) CUDA_CHECK(cudaStreamWaitEvent(s, team->last_event, 0));
+    st = nvl_launch(t, s);
+    if (st != UCC_OK) return st;
+    CUDA_CHECK(cudaEventRecord(t->event, s));
+    team->last_event = t->event; team->last_stream = s;
+    return UCC_OK;
+}
+
+/* every member published its buffers for this collective: pick (identically everywhere) the in-place kernel or
+ * the staged one and fill the pointer tables */
+static ucc_status_t resolve_direct(ucc_tl_nvl_task_t *t)
+{
+    nvl_direct_t d;
+    int ok = ucc_tl_nvl_xb_resolve(t->team, t->cseq, t->need_src, t->need_dst, t->kind != NVL_TASK_XCHG, t->exp_src, t->exp_dst, &d);
+    if (t->kind == NVL_TASK_XCHG) { t->u.xchg.direct = ok; if (ok) t->u.xchg.d = d; }
+    else { t->u.red.direct = ok ? t->want_direct : NVL_DIRECT_NONE; if (ok) t->u.red.d = d; }
+    return UCC_OK;
+}
+static inline int task_is_direct(const ucc_tl_nvl_task_t *t) { return t->want_direct && t->team->zcopy; }
+
+/* head of the launch queue: start it once its buffer exchange (if any) is complete */
+static ucc_status_t try_launch_queued(ucc_tl_nvl_task_t *t)
+{
+    ucc_tl_nvl_team_t *team = t->team;
+    cudaStream_t s;
+    ucc_status_t st;
+    if (ucc_list_head(&team->launch_q, ucc_tl_nvl_task_t, q_elem) != t) return UCC_INPROGRESS;
+    if (task_is_direct(t)) {
+        if (!t->published) t->published = ucc_tl_nvl_xb_publish(team, t->cseq, t->exp_src, t->exp_src_len, t->exp_dst, t->exp_dst_len, 1);
+        if (!t->published || !ucc_tl_nvl_xb_ready(team, t->cseq)) return UCC_INPROGRESS;
+        resolve_direct(t);
+    }
+    s = t->gated ? team->stream : t->stream;
+    if (t->gated) CUDA_CHECK(cudaStreamWaitEvent(team->stream, t->in_event, 0));
+    st = launch_ordered(t, s);
+    if (st != UCC_OK) return st;
+    if (t->gated && ucc_cu.cuStreamWriteValue32((CUstream)team->stream, (CUdeviceptr)(uintptr_t)&team->gates[t->gate_val % NVL_GATE_SLOTS], t->gate_val, 0) != CUDA_SUCCESS) return UCC_ERR_NO_MESSAGE;
+    ucc_list_del(&t->q_elem); t->state = NVL_TASK_LAUNCHED;
+    return UCC_OK;
+}
+
 static void nvl_progress(ucc_coll_task_t *ct)
 {
     ucc_tl_nvl_task_t *t = ucc_derived_of(ct, ucc_tl_nvl_task_t);
     cudaError_t e;
+    if (t->state == NVL_TASK_QUEUED) {
+        ucc_status_t st;
+        ucc_spin_lock(&t->team->launch_lock);
+        st = try_launch_queued(t);
+        ucc_spin_unlock(&t->team->launch_lock);
+        if (st == UCC_INPROGRESS) return;
+        if (st != UCC_OK) { ct->status = st; return; }
+    }
     if (t->captured) { ct->status = UCC_OK; return; }
     e = cudaEventQuery(t->event);
     if (e == cudaErrorNotReady) { (void)cudaGetLastError(); return; }
@@ -67,11 +126,40 @@ static ucc_status_t nvl_post_on(ucc_tl_nvl_task_t *t, cudaStream_t s)
     enum cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     ucc_status_t st;
     UCC_PROFILE_REQUEST_EVENT(t, "nvl_coll_start", 0);
-    t->stream = s; t->captured = 0;
+    ucc_tl_nvl_team_t *team = t->team;
+    int direct;
+    t->stream = s; t->captured = 0; t->state = NVL_TASK_LAUNCHED; t->gated = 0; t->published = 0;
     if (cudaStreamIsCapturing(s, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusActive) t->captured = 1;
-    st = nvl_launch(t, s);
+    ucc_spin_lock(&team->launch_lock);
+    direct = task_is_direct(t);
+    if (t->kind == NVL_TASK_XCHG) t->u.xchg.direct = 0; else t->u.red.direct = NVL_DIRECT_NONE;
+    if (direct) {
+        /* the exchange sequence advances on every rank in post order; a capturing stream cannot wait for the
+         * peers, so it tells them "not usable" and everybody takes the staged kernel for this one */
+        t->cseq = team->xb_seq++;
+        t->published = ucc_tl_nvl_xb_publish(team, t->cseq, t->exp_src, t->exp_src_len, t->exp_dst, t->exp_dst_len, !t->captured);
+        if (t->captured) { direct = 0; if (team->xb_mine->consumed < t->cseq + 1) ucc_store_release(&team->xb_mine->consumed, t->cseq + 1); }
+    }
+    if (t->captured || (ucc_list_is_empty(&team->launch_q) && (!direct || (t->published && ucc_tl_nvl_xb_ready(team, t->cseq))))) {
+        if (direct) resolve_direct(t);
+        st = launch_ordered(t, s);
+    } else {
+        /* deferred: the kernel is launched from progress once the peers' buffers are known / the tasks ahead of it
+         * are launched.  A user stream is parked on a gate word so that work enqueued after this post still runs
+         * after the collective; the kernel itself then goes to the team stream behind an event of the user stream. */
+        st = UCC_OK;
+        if (s != team->stream) {
+            t->gate_val = ++team->gate_seq;
+            if ((!t->in_event && cudaEventCreateWithFlags(&t->in_event, cudaEventDisableTiming) != cudaSuccess) || cudaEventRecord(t->in_event, s) != cudaSuccess ||
+                ucc_cu.cuStreamWaitValue32((CUstream)s, (CUdeviceptr)(uintptr_t)&team->gates[t->gate_val % NVL_GATE_SLOTS], t->gate_val, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS) {
+                (void)cudaGetLastError(); st = UCC_ERR_NO_MESSAGE;
+            }
+            t->gated = 1;
+        }
+        if (st == UCC_OK) { ucc_list_add_tail(&team->launch_q, &t->q_elem); t->state = NVL_TASK_QUEUED; }
+    }
+    ucc_spin_unlock(&team->launch_lock);
     if (st != UCC_OK) return st;
-    if (!t->captured) CUDA_CHECK(cudaEventRecord(t->event, s));
     return ucc_progress_queue_enqueue(UCC_TL_CORE_CTX(t->team)->pq, &t->super);
 }
 static ucc_status_t nvl_post(ucc_coll_task_t *ct)
@@ -96,6 +184,17 @@ static ucc_status_t nvl_triggered_post(ucc_ee_h ee, ucc_ev_t *ev, ucc_coll_task_
 static ucc_status_t nvl_finalize(ucc_coll_task_t *ct)
 {
     ucc_tl_nvl_task_t *t = ucc_derived_of(ct, ucc_tl_nvl_task_t);
+    ucc_tl_nvl_team_t *team = t->team;
+    ucc_spin_lock(&team->launch_lock);
+    if (t->state == NVL_TASK_QUEUED) { /* abandoned before its kernel was launched (timeout / error): release the user's stream */
+        ucc_list_del(&t->q_elem); t->state = NVL_TASK_LAUNCHED;
+        if (t->gated) ucc_cu.cuStreamWriteValue32((CUstream)team->stream, (CUdeviceptr)(uintptr_t)&team->gates[t->gate_val % NVL_GATE_SLOTS], t->gate_val, 0);
+    }
+    if (t->event && team->last_event == t->event) { /* the team still orders the next launch after this event: keep it alive */
+        cudaEvent_t spare = team->order_event; team->order_event = t->event; t->event = spare;
+    }
+    ucc_spin_unlock(&team->launch_lock);
+    if (t->in_event) cudaEventDestroy(t->in_event);
     if (t->event) cudaEventDestroy(t->event);
     ucc_coll_task_destruct(ct);
     ucc_mpool_put(t);
@@ -109,7 +208,8 @@ static ucc_status_t task_alloc(ucc_base_coll_args_t *b, ucc_base_team_t *b_team,
     ucc_tl_nvl_task_t *t = (ucc_tl_nvl_task_t *)ucc_mpool_get(&ctx->task_mp);
     if (!t) return UCC_ERR_NO_MEMORY;
     ucc_coll_task_init(&t->super, b, b_team);
-    t->team = team; t->event = NULL; t->captured = 0;
+    t->team = team; t->event = NULL; t->captured = 0; t->in_event = NULL; t->state = NVL_TASK_LAUNCHED; t->want_direct = 0; t->gated = 0;
+    t->need_src = t->need_dst = 0; t->exp_src = NULL; t->exp_dst = NULL; t->exp_src_len = t->exp_dst_len = 0; t->nblocks_direct = 0;
     t->nthreads = (int)ctx->cfg.nthreads;
     t->super.post = nvl_post; t->super.progress = nvl_progress; t->super.finalize = nvl_finalize; t->super.triggered_post = nvl_triggered_post;
     if (cudaEventCreateWithFlags(&t->event, cudaEventDisableTiming) != cudaSuccess) { (void)cudaGetLastError(); ucc_mpool_put(t); return UCC_ERR_NO_RESOURCE; }
@@ -189,6 +289,19 @@ static ucc_status_t red_init(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, u
     }
     if (alg == RED_ALG_ONESHOT) { t->kind = NVL_TASK_REDUCE_ONESHOT; t->nblocks = pick_blocks(ctx, bytes, 16384); if (t->nblocks > 32) t->nblocks = 32; }
     else { t->kind = NVL_TASK_REDUCE_STAGED; t->nblocks = pick_blocks(ctx, bytes, 32 * 1024); }
+    /* zero-copy: every criterion below is evaluated identically on all ranks (sizes / counts are collective
+     * arguments); what only the owner knows (can the buffer be exported? is it aligned?) travels with the exchange */
+    if (alg != RED_ALG_ONESHOT && team->zcopy && ctx->cfg.zcopy != UCC_NO && bytes >= ctx->cfg.zcopy_thresh) {
+        int mode = alg == RED_ALG_NVLS ? (r->kind == NVL_RED_REDUCE_SCATTER ? NVL_DIRECT_NONE : NVL_DIRECT_DST) : NVL_DIRECT_FULL;
+        if (mode == NVL_DIRECT_FULL && r->kind == NVL_RED_REDUCE_SCATTER)
+            for (ucc_rank_t i = 0; i < N; i++) if ((r->rs_offset[i] * ucc_dt_size(dt)) & 15) mode = NVL_DIRECT_NONE;
+        if (mode != NVL_DIRECT_NONE) {
+            t->want_direct = mode; t->nblocks_direct = t->nblocks;
+            t->need_src = mode == NVL_DIRECT_FULL; t->need_dst = r->kind != NVL_RED_REDUCE_SCATTER;
+            t->exp_src = src; t->exp_src_len = bytes;
+            t->exp_dst = r->kind == NVL_RED_REDUCE_SCATTER ? NULL : dst; t->exp_dst_len = t->exp_dst ? bytes : 0;
+        }
+    }
     *task_p = &t->super;
     return UCC_OK;
 }
@@ -295,6 +408,15 @@ static ucc_status_t xchg_init(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, 
     if (st != UCC_OK) return st;
     t->kind = NVL_TASK_XCHG; t->u.xchg = x;
     t->nblocks = pick_blocks(ctx, moved, 64 * 1024);
+    if (team->zcopy && ctx->cfg.zcopy != UCC_NO) {
+        /* `moved` is the same number on every rank except for the v-collectives whose counts are private to a
+         * rank (alltoallv, gatherv, scatterv): those only go zero-copy when it is forced, size-independently */
+        int symmetric = a->coll_type != UCC_COLL_TYPE_ALLTOALLV && a->coll_type != UCC_COLL_TYPE_GATHERV && a->coll_type != UCC_COLL_TYPE_SCATTERV;
+        if (symmetric ? moved >= ctx->cfg.zcopy_thresh : ctx->cfg.zcopy == UCC_YES) {
+            t->want_direct = NVL_DIRECT_FULL; t->need_src = 1; t->need_dst = 0;
+            t->exp_src = x.src_bytes ? x.src : NULL; t->exp_src_len = x.src_bytes;
+        }
+    }
     *task_p = &t->super;
     return UCC_OK;
 }

@@ -145,6 +145,9 @@ static void team_release(ucc_tl_nvl_team_t *team)
     }
     if (team->mc_fd >= 0) { close(team->mc_fd); team->mc_fd = -1; }
     if (team->host_err) { cudaFreeHost(team->host_err); team->host_err = NULL; }
+    if (team->gates) { cudaFree(team->gates); team->gates = NULL; }
+    if (team->order_event) { cudaEventDestroy(team->order_event); team->order_event = NULL; }
+    ucc_tl_nvl_xb_release(team);
     if (team->oob_internal) { ucc_internal_oob_finalize(&team->oob); team->oob_internal = 0; }
     free(team->infos); team->infos = NULL; free(team->sync_vals); team->sync_vals = NULL;
     (void)cudaGetLastError();
@@ -202,6 +205,7 @@ ucc_status_t ucc_tl_nvl_team_create_post(ucc_base_context_t *b_ctx, const ucc_ba
     if (st == UCC_OK && team->heap_kind == NVL_HEAP_IPC && cudaIpcGetMemHandle(&team->my_info.ipc, team->heap) != cudaSuccess) { (void)cudaGetLastError(); st = UCC_ERR_NO_RESOURCE; }
     team->my_info.status = (int32_t)st; team->my_info.ptr = (uint64_t)(uintptr_t)team->heap; team->my_info.size = team->heap_size;
     team->sync_send[3] = want_mc;
+    if (ctx->cfg.zcopy != UCC_NO && ucc_tl_nvl_xb_create(team) == UCC_OK) snprintf(team->my_info.xb_name, sizeof(team->my_info.xb_name), "%s", team->xb_name);
     st = team->oob.allgather(&team->my_info, team->infos, sizeof(nvl_rank_info_t), team->oob.coll_info, &team->oob_req);
     if (st != UCC_OK) { team_release(team); free(team); return st; }
     team->state = NVL_TEAM_XCHG_INFO;
@@ -263,6 +267,11 @@ static ucc_status_t team_finish(ucc_tl_nvl_team_t *team)
     CUDA_CHECK(cudaStreamCreateWithFlags(&team->stream, cudaStreamNonBlocking));
     CUDA_CHECK(cudaHostAlloc((void **)&team->host_err, sizeof(uint32_t), cudaHostAllocMapped));
     *team->host_err = 0;
+    CUDA_CHECK(cudaMalloc((void **)&team->gates, NVL_GATE_SLOTS * sizeof(uint32_t)));
+    CUDA_CHECK(cudaMemset(team->gates, 0, NVL_GATE_SLOTS * sizeof(uint32_t)));
+    CUDA_CHECK(cudaEventCreateWithFlags(&team->order_event, cudaEventDisableTiming));
+    ucc_list_head_init(&team->launch_q); ucc_spinlock_init(&team->launch_lock);
+    team->last_stream = NULL; team->gate_seq = 0; team->xb_seq = 0;
     memset(&team->dev, 0, sizeof(team->dev));
     team->dev.rank = (int)UCC_TL_TEAM_RANK(team); team->dev.size = (int)N;
     for (ucc_rank_t p = 0; p < N; p++) team->dev.heap[p] = team->peer_va[p];
@@ -292,6 +301,7 @@ ucc_status_t ucc_tl_nvl_team_create_test(ucc_base_team_t *b)
         st = UCC_OK;
         for (ucc_rank_t r = 0; r < N; r++) if (team->infos[r].status != UCC_OK) st = UCC_ERR_NOT_SUPPORTED;
         if (st == UCC_OK) st = map_peers(team);
+        team->sync_send[2] = (st == UCC_OK && team->xb_mine && ucc_tl_nvl_xb_attach(team) == UCC_OK); /* zero-copy needs every board */
         if ((st = post_sync(team, (int32_t)st, 0)) != UCC_OK) goto fail;
         team->state = NVL_TEAM_SYNC1;
         /* fall through */
@@ -299,6 +309,9 @@ ucc_status_t ucc_tl_nvl_team_create_test(ucc_base_team_t *b)
         st = test_sync(team, &ok);
         if (st == UCC_INPROGRESS) return st;
         if (st < 0 || !ok) { st = UCC_ERR_NOT_SUPPORTED; goto fail; }
+        team->zcopy = ucc_cu.cuStreamWaitValue32 && ucc_cu.cuStreamWriteValue32; /* deferred launches park user streams on a gate word */
+        for (ucc_rank_t r = 0; r < N; r++) if (!team->sync_vals[4 * r + 2]) team->zcopy = 0;
+        ucc_tl_nvl_xb_unlink(team); /* everybody who could attach has done so */
         if (!want_mc) return team_finish(team);
         /* rank 0 creates the multicast object and offers it to the others */
         st = UCC_OK;

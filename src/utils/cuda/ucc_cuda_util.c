@@ -18,7 +18,7 @@ ucc_status_t ucc_cu_api_load(void)
         LOAD(cuMemMap); LOAD(cuMemUnmap); LOAD(cuMemSetAccess); LOAD(cuMemGetAllocationGranularity);
         LOAD(cuMemExportToShareableHandle); LOAD(cuMemImportFromShareableHandle); LOAD(cuMulticastCreate); LOAD(cuMulticastAddDevice);
         LOAD(cuMulticastBindMem); LOAD(cuMulticastUnbind); LOAD(cuMulticastGetGranularity); LOAD(cuDeviceGet); LOAD(cuDeviceGetAttribute);
-        LOAD(cuGetErrorString); LOAD(cuStreamWriteValue32); LOAD(cuCtxGetDevice);
+        LOAD(cuGetErrorString); LOAD(cuStreamWriteValue32); LOAD(cuCtxGetDevice); LOAD(cuStreamWaitValue32);
         ucc_cu.loaded = 1;
     }
     pthread_mutex_unlock(&cu_lock);

@@ -51,6 +51,7 @@ typedef struct ucc_cu_api {
     CUresult (*cuGetErrorString)(CUresult, const char **);
     CUresult (*cuStreamWriteValue32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
     CUresult (*cuCtxGetDevice)(CUdevice *);
+    CUresult (*cuStreamWaitValue32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
     int loaded;
 } ucc_cu_api_t;
 extern ucc_cu_api_t ucc_cu;

@@ -36,8 +36,21 @@ def main():
             if not torch.allclose(dst.cpu().double(), exp, rtol=tol, atol=tol):
                 print(f"rank {rank}: allreduce mismatch count {count} dt {dt}", flush=True)
                 ok = False
-    # allgather + alltoall + bcast + reduce_scatter
-    blk = 1000
+    # allgather + alltoall + bcast + reduce_scatter: small (staged kernels) and large (zero-copy kernels on CUDA)
+    for blk in (1000, 300000):
+        ok &= other_colls(comm, rank, world, dev, use_cuda, blk)
+    comm.barrier()
+    flag = torch.tensor([1 if ok else 0])
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    comm.destroy()
+    if rank == 0:
+        print("DIST_WORKER_OK" if flag.item() == 1 else "DIST_WORKER_FAIL", flush=True)
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() == 1 else 1)
+
+
+def other_colls(comm, rank, world, dev, use_cuda, blk):
+    ok = True
     src = torch.full((blk,), float(rank), device=dev)
     dst = torch.zeros(blk * world, device=dev)
     comm.run(comm.coll_init("allgather", src, dst))
@@ -49,21 +62,20 @@ def main():
     comm.run(comm.coll_init("alltoall", src, dst))
     exp = torch.cat([torch.arange(rank * blk, (rank + 1) * blk, dtype=torch.float32) + 1000 * p for p in range(world)])
     ok &= bool(torch.equal(dst.cpu(), exp))
-    b = torch.full((5000,), 7.0 if rank == 0 else 0.0, device=dev)
+    b = torch.full((5 * blk,), 7.0 if rank == 0 else 0.0, device=dev)
     comm.run(comm.coll_init("bcast", b, None, root=0))
     ok &= bool((b.cpu() == 7.0).all())
     src = torch.ones(blk * world, device=dev) * (rank + 1)
     dst = torch.zeros(blk, device=dev)
     comm.run(comm.coll_init("reduce_scatter", src, dst))
     ok &= bool((dst.cpu() == world * (world + 1) / 2).all())
-    comm.barrier()
-    flag = torch.tensor([1 if ok else 0])
-    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-    comm.destroy()
-    if rank == 0:
-        print("DIST_WORKER_OK" if flag.item() == 1 else "DIST_WORKER_FAIL", flush=True)
-    dist.destroy_process_group()
-    sys.exit(0 if flag.item() == 1 else 1)
+    # in-place allreduce + reduce to a non-zero root
+    x = torch.full((blk * 3 + 5,), float(rank + 1), device=dev)
+    comm.run(comm.allreduce_init(x, x))
+    ok &= bool((x.cpu() == world * (world + 1) / 2).all())
+    if not ok:
+        print(f"rank {rank}: collective mismatch at blk {blk}", flush=True)
+    return ok
 
 
 if __name__ == "__main__":

@@ -39,3 +39,17 @@ def test_multiproc_ipc_heap():
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
     _run(n, {"UCC_TL_NVL_USE_VMM": "n"})
+
+
+def test_multiproc_zcopy_forced():
+    n = torch.cuda.device_count() if torch.cuda.is_available() else 0
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    _run(n, {"UCC_TL_NVL_ZCOPY": "y", "UCC_TL_NVL_ZCOPY_THRESH": "0"})
+
+
+def test_multiproc_no_zcopy():
+    n = torch.cuda.device_count() if torch.cuda.is_available() else 0
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    _run(n, {"UCC_TL_NVL_ZCOPY": "n"})

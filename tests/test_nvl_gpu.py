@@ -18,6 +18,9 @@ from ucc_b200.harness import UccJob, coll_args  # noqa: E402
 CUDA = U.UCC_MEMORY_TYPE_CUDA
 TDT = {"float32": torch.float32, "float64": torch.float64, "float16": torch.float16, "bfloat16": torch.bfloat16,
        "int32": torch.int32, "int64": torch.int64, "int8": torch.int8, "uint8": torch.uint8, "int16": torch.int16}
+# zero-copy kernels (members' user buffers used in place) forced for every size / never used
+ZC = {"UCC_TL_NVL_ZCOPY": "y", "UCC_TL_NVL_ZCOPY_THRESH": "0"}
+NOZC = {"UCC_TL_NVL_ZCOPY": "n"}
 ENV = {"UCC_TL_NVL_MAX_BLOCKS": "4", "UCC_TL_NVL_TIMEOUT": "5s", "UCC_TL_NVL_SYMMETRIC_SIZE": "8Mb"}
 
 
@@ -73,11 +76,12 @@ def assert_close(got, exp, dt):
         assert torch.equal(got.long(), exp.long())
 
 
-@pytest.fixture(scope="module", params=["oneshot", "twoshot"])
+@pytest.fixture(scope="module", params=["oneshot", "twoshot", "twoshot-zcopy"])
 def alg_job(request):
     need_cuda()
     env = dict(ENV)
-    env["UCC_TL_NVL_TUNE"] = f"allreduce:cuda:inf:@{request.param}"
+    env["UCC_TL_NVL_TUNE"] = f"allreduce:cuda:inf:@{request.param.split('-')[0]}"
+    env.update(ZC if request.param.endswith("zcopy") else NOZC)
     job = UccJob(8, env=env)
     teams = {n: job.create_team(range(n)) for n in (2, 3, 4, 8)}
     yield request.param, teams
@@ -131,10 +135,10 @@ def test_allreduce_inplace_persistent_unaligned(alg_job):
     req.finalize()
 
 
-@pytest.fixture(scope="module")
-def job():
+@pytest.fixture(scope="module", params=["staged", "zcopy"])
+def job(request):
     need_cuda()
-    j = UccJob(8, env=ENV)
+    j = UccJob(8, env=dict(ENV, **(ZC if request.param == "zcopy" else NOZC)))
     teams = {n: j.create_team(range(n)) for n in (2, 3, 4, 8)}
     yield teams
     j.cleanup()
