@@ -127,7 +127,9 @@ def main():
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
             for r in reqs[warm:]:
-                r.post_on_stream(stream)
+                r.post_on_stream(stream, wait_posted=False)
+            for r in reqs[warm:]:
+                r.wait_posted()      # zero-copy kernels enter the stream once the peers' buffers are mapped
             e1.record(stream)
             for r in reqs[warm:]:
                 r.wait()

@@ -14,7 +14,7 @@
 
 #define NVL_MAX_PEERS  16
 #define NVL_MAX_BLOCKS 320
-#define NVL_LL_MAX     (512 * 1024)          /* bytes per rank in the one-shot (latency) region */
+#define NVL_LL_MAX     (1024 * 1024)         /* bytes per rank in the one-shot (latency) region */
 
 /* control block at offset 0 of every rank's heap */
 typedef struct nvl_ctrl {

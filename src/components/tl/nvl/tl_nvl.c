@@ -19,7 +19,7 @@ ucc_config_field_t ucc_tl_nvl_context_config_table[] = {
     {"USE_NVLS", "try", "Use NVSwitch multicast / in-switch reduction (multimem.*) when the fabric supports it", ucc_offsetof(ucc_tl_nvl_context_config_t, use_nvls), UCC_CONFIG_TYPE_TERNARY},
     {"USE_VMM", "try", "Allocate the heap with the CUDA virtual memory management API and share it as a POSIX fd (required for NVLS); otherwise cudaMalloc + cudaIpc",
      ucc_offsetof(ucc_tl_nvl_context_config_t, use_vmm), UCC_CONFIG_TYPE_TERNARY},
-    {"ALLREDUCE_ONESHOT_THRESH", "256K", "Allreduce messages up to this size use the one-shot push kernel", ucc_offsetof(ucc_tl_nvl_context_config_t, oneshot_thresh), UCC_CONFIG_TYPE_MEMUNITS},
+    {"ALLREDUCE_ONESHOT_THRESH", "1M", "Allreduce messages up to (and including) this size use the one-shot push kernel", ucc_offsetof(ucc_tl_nvl_context_config_t, oneshot_thresh), UCC_CONFIG_TYPE_MEMUNITS},
     {"ZCOPY", "try", "Read and write the members' user buffers in place (CUDA IPC handles exchanged per collective, mappings cached) instead of staging through the heap",
      ucc_offsetof(ucc_tl_nvl_context_config_t, zcopy), UCC_CONFIG_TYPE_TERNARY},
     {"ZCOPY_THRESH", "1M", "Messages of at least this size use the zero-copy kernels", ucc_offsetof(ucc_tl_nvl_context_config_t, zcopy_thresh), UCC_CONFIG_TYPE_MEMUNITS},

@@ -71,6 +71,7 @@ static ucc_status_t resolve_direct(ucc_tl_nvl_task_t *t)
 {
     nvl_direct_t d;
     int ok = ucc_tl_nvl_xb_resolve(t->team, t->cseq, t->need_src, t->need_dst, t->kind != NVL_TASK_XCHG, t->exp_src, t->exp_dst, &d);
+    tl_debug(NVL_LIB(t->team), "exchange %lu: %s (src %d dst %d)", (unsigned long)t->cseq, ok ? "zero-copy" : "staged", t->need_src, t->need_dst);
     if (t->kind == NVL_TASK_XCHG) { t->u.xchg.direct = ok; if (ok) t->u.xchg.d = d; }
     else { t->u.red.direct = ok ? t->want_direct : NVL_DIRECT_NONE; if (ok) t->u.red.d = d; }
     return UCC_OK;
@@ -89,12 +90,15 @@ static ucc_status_t try_launch_queued(ucc_tl_nvl_task_t *t)
         if (!t->published || !ucc_tl_nvl_xb_ready(team, t->cseq)) return UCC_INPROGRESS;
         resolve_direct(t);
     }
-    s = t->gated ? team->stream : t->stream;
-    if (t->gated) CUDA_CHECK(cudaStreamWaitEvent(team->stream, t->in_event, 0));
+    s = t->stream;
     st = launch_ordered(t, s);
     if (st != UCC_OK) return st;
-    if (t->gated && ucc_cu.cuStreamWriteValue32((CUstream)team->stream, (CUdeviceptr)(uintptr_t)&team->gates[t->gate_val % NVL_GATE_SLOTS], t->gate_val, 0) != CUDA_SUCCESS) return UCC_ERR_NO_MESSAGE;
     ucc_list_del(&t->q_elem); t->state = NVL_TASK_LAUNCHED;
+    if (t->super.ee) { /* stream-ordered post: only now is the collective really in the user's stream */
+        ucc_ev_t post_event;
+        post_event.ev_type = UCC_EVENT_COLLECTIVE_POST; post_event.ev_context = NULL; post_event.ev_context_size = 0; post_event.req = &t->super.super;
+        ucc_ee_set_event_internal(t->super.ee, &post_event, &t->super.ee->event_out_queue);
+    }
     return UCC_OK;
 }
 
@@ -144,26 +148,20 @@ static ucc_status_t nvl_post_on(ucc_tl_nvl_task_t *t, cudaStream_t s)
         if (direct) resolve_direct(t);
         st = launch_ordered(t, s);
     } else {
-        /* deferred: the kernel is launched from progress once the peers' buffers are known / the tasks ahead of it
-         * are launched.  A user stream is parked on a gate word so that work enqueued after this post still runs
-         * after the collective; the kernel itself then goes to the team stream behind an event of the user stream. */
+        /* deferred: the kernel is launched (into the same stream) from progress once the peers' buffers are known and
+         * the tasks ahead of it are launched.  As with the reference's triggered post, a stream-ordered consumer
+         * learns from UCC_EVENT_COLLECTIVE_POST when the collective is really in its stream.  (Parking the user's
+         * stream on a cuStreamWaitValue32 gate was tried and dropped: streams share hardware channels, so the
+         * parked wait can block the very kernel that is supposed to release it.) */
         st = UCC_OK;
-        if (s != team->stream) {
-            t->gate_val = ++team->gate_seq;
-            if ((!t->in_event && cudaEventCreateWithFlags(&t->in_event, cudaEventDisableTiming) != cudaSuccess) || cudaEventRecord(t->in_event, s) != cudaSuccess ||
-                ucc_cu.cuStreamWaitValue32((CUstream)s, (CUdeviceptr)(uintptr_t)&team->gates[t->gate_val % NVL_GATE_SLOTS], t->gate_val, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS) {
-                (void)cudaGetLastError(); st = UCC_ERR_NO_MESSAGE;
-            }
-            t->gated = 1;
-        }
-        if (st == UCC_OK) { ucc_list_add_tail(&team->launch_q, &t->q_elem); t->state = NVL_TASK_QUEUED; }
+        ucc_list_add_tail(&team->launch_q, &t->q_elem); t->state = NVL_TASK_QUEUED;
     }
     ucc_spin_unlock(&team->launch_lock);
     if (st != UCC_OK) return st;
     return ucc_progress_queue_enqueue(UCC_TL_CORE_CTX(t->team)->pq, &t->super);
 }
 static ucc_status_t nvl_post(ucc_coll_task_t *ct)
-{ ucc_tl_nvl_task_t *t = ucc_derived_of(ct, ucc_tl_nvl_task_t); return nvl_post_on(t, t->team->stream); }
+{ ucc_tl_nvl_task_t *t = ucc_derived_of(ct, ucc_tl_nvl_task_t); ct->ee = NULL; return nvl_post_on(t, t->team->stream); }
 
 /* stream-ordered post: the kernel goes straight onto the user's stream (what PyTorch-style
  * consumers use); no host-side dependency resolution is needed */
@@ -177,6 +175,7 @@ static ucc_status_t nvl_triggered_post(ucc_ee_h ee, ucc_ev_t *ev, ucc_coll_task_
     ct->ee = ee;
     st = nvl_post_on(t, (cudaStream_t)ee->ee_context);
     if (st != UCC_OK) return st;
+    if (t->state == NVL_TASK_QUEUED) return UCC_OK; /* the post event follows the deferred launch */
     post_event.ev_type = UCC_EVENT_COLLECTIVE_POST; post_event.ev_context = NULL; post_event.ev_context_size = 0; post_event.req = &ct->super;
     ucc_ee_set_event_internal(ee, &post_event, &ee->event_out_queue);
     return UCC_OK;
@@ -188,7 +187,6 @@ static ucc_status_t nvl_finalize(ucc_coll_task_t *ct)
     ucc_spin_lock(&team->launch_lock);
     if (t->state == NVL_TASK_QUEUED) { /* abandoned before its kernel was launched (timeout / error): release the user's stream */
         ucc_list_del(&t->q_elem); t->state = NVL_TASK_LAUNCHED;
-        if (t->gated) ucc_cu.cuStreamWriteValue32((CUstream)team->stream, (CUdeviceptr)(uintptr_t)&team->gates[t->gate_val % NVL_GATE_SLOTS], t->gate_val, 0);
     }
     if (t->event && team->last_event == t->event) { /* the team still orders the next launch after this event: keep it alive */
         cudaEvent_t spare = team->order_event; team->order_event = t->event; t->event = spare;
@@ -287,7 +285,7 @@ static ucc_status_t red_init(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, u
           if (inplace) r->dst = (char *)dst + r->rs_offset[me] * ucc_dt_size(dt); }
         break;
     }
-    if (alg == RED_ALG_ONESHOT) { t->kind = NVL_TASK_REDUCE_ONESHOT; t->nblocks = pick_blocks(ctx, bytes, 16384); if (t->nblocks > 32) t->nblocks = 32; }
+    if (alg == RED_ALG_ONESHOT) { t->kind = NVL_TASK_REDUCE_ONESHOT; t->nblocks = pick_blocks(ctx, bytes, 16384); if (t->nblocks > 64) t->nblocks = 64; }
     else { t->kind = NVL_TASK_REDUCE_STAGED; t->nblocks = pick_blocks(ctx, bytes, 32 * 1024); }
     /* zero-copy: every criterion below is evaluated identically on all ranks (sizes / counts are collective
      * arguments); what only the owner knows (can the buffer be exported? is it aligned?) travels with the exchange */
@@ -483,7 +481,8 @@ ucc_status_t ucc_tl_nvl_team_get_scores(ucc_base_team_t *b_team, ucc_coll_score_
     char sel[512], a[32], n[32];
     ucc_status_t st = ucc_coll_score_build_default(b_team, UCC_TL_NVL_DEFAULT_SCORE, ucc_tl_nvl_coll_init, UCC_TL_NVL_SUPPORTED_COLLS, mt, 1, &score);
     if (st != UCC_OK) return st;
-    ucc_memunits_to_str(ctx->cfg.oneshot_thresh, a, sizeof(a)); ucc_memunits_to_str(ctx->cfg.nvls_thresh, n, sizeof(n));
+    snprintf(a, sizeof(a), "%zu", ctx->cfg.oneshot_thresh + 1); /* ranges are end-exclusive, the threshold itself is still one-shot */
+    ucc_memunits_to_str(ucc_max(ctx->cfg.nvls_thresh, ctx->cfg.oneshot_thresh + 1), n, sizeof(n));
     /* message-size driven defaults: latency kernel below the threshold, in-switch reduction for big
      * messages when the multicast mapping is live (dt/op it cannot do fall back to twoshot through the
      * score fallback chain because nvls init returns NOT_SUPPORTED) */

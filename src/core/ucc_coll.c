@@ -297,7 +297,14 @@ UCC_EXPORT ucc_status_t ucc_collective_post(ucc_coll_req_h request)
 }
 
 UCC_EXPORT ucc_status_t ucc_collective_init_and_post(ucc_coll_args_t *coll_args, ucc_coll_req_h *request, ucc_team_h team)
-{ (void)coll_args; (void)request; (void)team; ucc_error("ucc_collective_init_and_post() is not implemented"); return UCC_ERR_NOT_IMPLEMENTED; }
+{
+    /* the reference leaves this entry point unimplemented (core/ucc_coll.c:439-445); here it is the obvious composition */
+    ucc_status_t st = ucc_collective_init(coll_args, request, team);
+    if (st != UCC_OK) return st;
+    st = ucc_collective_post(*request);
+    if (st != UCC_OK) { ucc_collective_finalize(*request); *request = NULL; }
+    return st;
+}
 
 UCC_EXPORT ucc_status_t ucc_collective_finalize(ucc_coll_req_h request)
 {

@@ -11,6 +11,9 @@ from ucc_b200.dist import Communicator, init_distributed  # noqa: E402
 
 
 def main():
+    if os.environ.get("DW_FAULT"):
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["DW_FAULT"]), exit=False)
     use_cuda = len(sys.argv) > 1 and sys.argv[1] == "cuda"
     rank, world, lrank = init_distributed("cpu:gloo,cuda:nccl" if use_cuda else "gloo")
     dev = torch.device("cuda", torch.cuda.current_device()) if use_cuda else torch.device("cpu")

@@ -1,0 +1,88 @@
+"""Worker under torchrun: DDP / tensor-parallel / MoE helpers of ucc_b200.parallel against single-process references."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from ucc_b200 import ops  # noqa: E402
+from ucc_b200.dist import init_distributed  # noqa: E402
+from ucc_b200.models import MLP, TPTransformerBlock  # noqa: E402
+from ucc_b200.parallel import DistributedDataParallel, moe_combine, moe_dispatch  # noqa: E402
+
+
+def main():
+    use_cuda = len(sys.argv) > 1 and sys.argv[1] == "cuda"
+    rank, world, _ = init_distributed("cpu:gloo,cuda:nccl" if use_cuda else "gloo")
+    dev = torch.device("cuda", torch.cuda.current_device()) if use_cuda else torch.device("cpu")
+    comm = ops.init()
+    ok = True
+
+    # ---- DDP: averaged gradients == gradients of the mean loss over the global batch
+    torch.manual_seed(0)
+    model = MLP(32, 64, 2, 5).to(dev)
+    ref = MLP(32, 64, 2, 5).to(dev)
+    ref.load_state_dict(model.state_dict())
+    ddp = DistributedDataParallel(model, comm=comm, bucket_mb=0.01)   # tiny buckets: several collectives in flight
+    g = torch.Generator().manual_seed(1)
+    xs = torch.randn(world, 8, 32, generator=g).to(dev)
+    ys = torch.randn(world, 8, 5, generator=g).to(dev)
+    for step in range(2):
+        ddp.zero_grad()
+        loss = torch.nn.functional.mse_loss(ddp(xs[rank]), ys[rank])
+        loss.backward()
+        ddp.finish_gradient_sync()
+        ref.zero_grad()
+        sum(torch.nn.functional.mse_loss(ref(xs[r]), ys[r]) for r in range(world)).div(world).backward()
+        for (n1, p), (_, q) in zip(model.named_parameters(), ref.named_parameters()):
+            if not torch.allclose(p.grad, q.grad, rtol=1e-4, atol=1e-5):
+                print(f"rank {rank}: DDP grad mismatch {n1} step {step}", flush=True)
+                ok = False
+
+    # ---- tensor parallel block == dense block assembled from the shards
+    torch.manual_seed(100 + rank)
+    d, h = 16, 8 * world
+    blk = TPTransformerBlock(d, h, comm=comm, device=dev)
+    with torch.no_grad():   # same LayerNorm / bias on every rank
+        for p in (blk.norm.weight, blk.norm.bias, blk.down.bias):
+            ops.broadcast(p.data, 0, comm=comm)
+    x = torch.randn(4, d, generator=torch.Generator().manual_seed(7)).to(dev).requires_grad_()
+    y = blk(x)
+    y.sum().backward()
+    w1 = torch.empty(world, h // world, d, device=dev); ops.all_gather_into_tensor(w1, blk.up.weight.data.contiguous(), comm=comm)
+    b1 = torch.empty(world, h // world, device=dev); ops.all_gather_into_tensor(b1, blk.up.bias.data.contiguous(), comm=comm)
+    w2 = torch.empty(world, d, h // world, device=dev); ops.all_gather_into_tensor(w2, blk.down.weight.data.contiguous(), comm=comm)
+    xd = x.detach().clone().requires_grad_()
+    hid = torch.nn.functional.gelu(torch.nn.functional.linear(blk.norm(xd), w1.reshape(h, d), b1.reshape(h)))
+    yd = xd + torch.nn.functional.linear(hid, torch.cat(list(w2), dim=1), blk.down.bias)
+    yd.sum().backward()
+    if not torch.allclose(y, yd, rtol=1e-4, atol=1e-5) or not torch.allclose(x.grad, xd.grad, rtol=1e-4, atol=1e-5):
+        print(f"rank {rank}: tensor-parallel mismatch", flush=True)
+        ok = False
+
+    # ---- MoE dispatch / combine round trip with skewed routing
+    T, H = 50 + 7 * rank, 12
+    tok = torch.arange(T * H, dtype=torch.float32, device=dev).view(T, H) + 10000 * rank
+    dest = (torch.arange(T, device=dev) * (rank + 2)) % world
+    if world > 1:
+        dest[: T // 2] = 0          # skew: rank 0's expert is hot
+    recv, sc, rc, order = moe_dispatch(tok, dest, comm=comm)
+    if recv.shape[0] != sum(rc):
+        ok = False
+    out = moe_combine(recv * 2.0, sc, rc, order, comm=comm)
+    if not torch.equal(out, tok * 2.0):
+        print(f"rank {rank}: MoE round trip mismatch", flush=True)
+        ok = False
+
+    flag = torch.tensor([1 if ok else 0])
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    ops.shutdown()
+    if rank == 0:
+        print("PARALLEL_WORKER_OK" if flag.item() == 1 else "PARALLEL_WORKER_FAIL", flush=True)
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()

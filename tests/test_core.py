@@ -1,0 +1,333 @@
+"""Core object model (model: reference test/gtest/core/test_lib.cc, test_lib_config.cc, test_context.cc, test_team.cc,
+test_timeout.cc, active_set/test_active_set.cc, asym_mem/test_asymmetric_memory.cc, core/test_mem_map.cc)."""
+import ctypes as C
+import os
+import time
+
+import numpy as np
+import pytest
+
+from ucc_b200 import capi as U
+from ucc_b200.harness import UccJob, coll_args
+
+libc = C.CDLL(None)
+libc.open_memstream.restype = C.c_void_p
+libc.open_memstream.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_size_t)]
+libc.fclose.argtypes = [C.c_void_p]
+U.lib.ucc_lib_config_print.argtypes = [U.handle, C.c_void_p, C.c_char_p, C.c_int]
+U.lib.ucc_lib_config_print.restype = None
+U.lib.ucc_context_config_print.argtypes = [U.handle, C.c_void_p, C.c_char_p, C.c_int]
+U.lib.ucc_context_config_print.restype = None
+
+
+def run(team, args):
+    req = team.coll(args)
+    st = req.run()
+    req.finalize()
+    return st
+
+
+def _print_cfg(fn, cfg, flags=1 | 2 | 4):
+    buf, size = C.c_char_p(), C.c_size_t()
+    f = libc.open_memstream(C.byref(buf), C.byref(size))
+    fn(cfg, f, b"title", flags)
+    libc.fclose(f)
+    return C.string_at(buf, size.value).decode()
+
+
+def test_version_and_status_strings():
+    assert U.ucc_get_version_string().decode().startswith("1.")
+    assert U.ucc_status_string(U.UCC_OK) == b"Success"
+    assert b"progress" in U.ucc_status_string(U.UCC_INPROGRESS).lower()
+    assert U.ucc_status_string(-12345) is not None
+
+
+def test_lib_config_read_modify_print(monkeypatch):
+    monkeypatch.setenv("UCC_CLS", "basic")
+    cfg = U.handle()
+    assert U.ucc_lib_config_read(None, None, C.byref(cfg)) == U.UCC_OK
+    out = _print_cfg(U.lib.ucc_lib_config_print, cfg)
+    assert "UCC_CLS=basic" in out and "title" in out
+    assert U.ucc_lib_config_modify(cfg, b"CLS", b"all") == U.UCC_OK
+    assert "UCC_CLS=all" in _print_cfg(U.lib.ucc_lib_config_print, cfg)
+    assert U.ucc_lib_config_modify(cfg, b"NO_SUCH_FIELD", b"1") != U.UCC_OK
+    U.ucc_lib_config_release(cfg)
+
+
+def test_lib_config_env_prefix(monkeypatch):
+    # "<PREFIX>_UCC_<NAME>" wins over the plain "UCC_<NAME>" (reference ucc_lib_config_read semantics)
+    monkeypatch.setenv("UCC_CLS", "basic")
+    monkeypatch.setenv("MYAPP_UCC_CLS", "basic,hier")
+    cfg = U.handle()
+    assert U.ucc_lib_config_read(b"MYAPP", None, C.byref(cfg)) == U.UCC_OK
+    assert "CLS=basic,hier" in _print_cfg(U.lib.ucc_lib_config_print, cfg)
+    U.ucc_lib_config_release(cfg)
+
+
+def test_config_file(tmp_path):
+    # the file is read once, when the library is loaded -> needs a fresh process
+    import subprocess
+    import sys
+    f = tmp_path / "ucc.conf"
+    f.write_text("# comment\nUCC_TL_SHM_TUNE = allreduce:@ring\n\n[section]\nUCC_CLS=basic\n")
+    code = (
+        "import ctypes as C, numpy as np\n"
+        "from ucc_b200 import capi as U\n"
+        "from ucc_b200.harness import UccJob, coll_args\n"
+        "j = UccJob(2); team = j.create_team()\n"
+        "src = [np.full(64, r + 1.0, np.float32) for r in range(2)]; dst = [np.zeros(64, np.float32) for _ in range(2)]\n"
+        "req = team.coll([coll_args('allreduce', src[r], dst[r]) for r in range(2)]); assert req.run() == 0; req.finalize()\n"
+        "assert np.all(dst[0] == 3)\n"
+        "U.lib.ucc_context_config_print.argtypes = [U.handle, C.c_void_p, C.c_char_p, C.c_int]\n"
+        "libc = C.CDLL(None); libc.fdopen.restype = C.c_void_p\n"
+        "cfg = U.handle(); assert U.ucc_context_config_read(j.procs[0].lib, None, C.byref(cfg)) == 0\n"
+        "fp = libc.fdopen(1, b'w'); U.lib.ucc_context_config_print(cfg, fp, b't', 1); libc.fflush(C.c_void_p(fp))\n"
+        "j.cleanup()\n")
+    env = dict(os.environ, UCC_CONFIG_FILE=str(f), PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    env.pop("UCC_TL_SHM_TUNE", None)
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "UCC_TL_SHM_TUNE=allreduce:@ring" in out.stdout
+
+
+def test_lib_attr_thread_mode():
+    for tm in (U.UCC_THREAD_SINGLE, U.UCC_THREAD_MULTIPLE):
+        with UccJob(1, thread_mode=tm, with_ctx_oob=False) as j:
+            attr = U.ucc_lib_attr_t()
+            attr.mask = U.UCC_LIB_PARAM_FIELD_THREAD_MODE | (1 << 1)
+            assert U.ucc_lib_get_attr(j.procs[0].lib, C.byref(attr)) == U.UCC_OK
+            assert attr.thread_mode == tm
+            assert attr.coll_types != 0
+
+
+def test_context_attr_addr():
+    with UccJob(2) as j:
+        a = U.ucc_context_attr_t()
+        a.mask = U.UCC_CONTEXT_ATTR_FIELD_CTX_ADDR | U.UCC_CONTEXT_ATTR_FIELD_CTX_ADDR_LEN | U.UCC_CONTEXT_ATTR_FIELD_WORK_BUFFER_SIZE
+        assert U.ucc_context_get_attr(j.procs[0].ctx, C.byref(a)) == U.UCC_OK
+        assert a.ctx_addr_len > 0 and a.ctx_addr
+
+
+def test_local_context_team_with_oob_only():
+    # contexts created without a context OOB: the team's OOB carries the address exchange
+    with UccJob(3, with_ctx_oob=False) as j:
+        team = j.create_team()
+        src = [np.full(10, r, np.int32) for r in range(3)]
+        dst = [np.zeros(10, np.int32) for _ in range(3)]
+        assert run(team, [coll_args("allreduce", src[r], dst[r], dt="int32") for r in range(3)]) == U.UCC_OK
+        assert np.all(dst[2] == 3)
+
+
+def test_many_teams_subsets_and_ids():
+    with UccJob(6) as j:
+        teams = [j.create_team(), j.create_team([0, 2, 4]), j.create_team([1, 3, 5]), j.create_team([5, 0]), j.create_team(range(6), use_ep_map=True)]
+        for t in teams:
+            n = len(t.ranks)
+            attr = U.ucc_team_attr_t()
+            attr.mask = U.UCC_TEAM_ATTR_FIELD_SIZE | U.UCC_TEAM_ATTR_FIELD_EP
+            assert U.ucc_team_get_attr(t.members[n - 1].team, C.byref(attr)) == U.UCC_OK
+            assert attr.size == n and attr.ep == n - 1
+            src = [np.full(33, i + 1, np.int64) for i in range(n)]
+            dst = [np.zeros(33, np.int64) for _ in range(n)]
+            assert run(t, [coll_args("allreduce", src[i], dst[i], dt="int64") for i in range(n)]) == U.UCC_OK
+            assert all(np.all(d == n * (n + 1) // 2) for d in dst)
+        # destroy / re-create: team ids are recycled without clashes
+        for _ in range(5):
+            t = j.create_team([1, 2, 3])
+            src = [np.full(5, 1, np.int32) for _ in range(3)]
+            dst = [np.zeros(5, np.int32) for _ in range(3)]
+            assert run(t, [coll_args("allreduce", src[i], dst[i], dt="int32") for i in range(3)]) == U.UCC_OK
+            t.destroy()
+            j.teams.remove(t)
+
+
+def test_interleaved_collectives_two_teams():
+    with UccJob(4) as j:
+        ta, tb = j.create_team(), j.create_team([0, 1, 2, 3])
+        n = 4
+        bufs = []
+        reqs = []
+        for k in range(6):
+            t = ta if k % 2 == 0 else tb
+            src = [np.full(1000, (k + 1) * (r + 1), np.int64) for r in range(n)]
+            dst = [np.zeros(1000, np.int64) for _ in range(n)]
+            bufs.append((src, dst, (k + 1) * 10))
+            reqs.append(t.coll([coll_args("allreduce", src[r], dst[r], dt="int64") for r in range(n)]))
+        for r in reqs:
+            r.post()
+        for r in reversed(reqs):
+            assert r.wait() == U.UCC_OK
+        for r in reqs:
+            r.finalize()
+        for src, dst, exp in bufs:
+            assert all(np.all(d == exp) for d in dst)
+
+
+def test_timeout_fires_when_a_rank_is_missing():
+    with UccJob(2) as j:
+        team = j.create_team()
+        src = np.ones(16, np.float32)
+        dst = np.zeros(16, np.float32)
+        args = coll_args("allreduce", src, dst, timeout=0.2)
+        req = C.POINTER(U.ucc_coll_req_t)()
+        assert U.ucc_collective_init(C.byref(args), C.byref(req), team.members[0].team) == U.UCC_OK
+        assert U.ucc_collective_post(req) == U.UCC_OK
+        t0 = time.time()
+        while req.contents.status == U.UCC_INPROGRESS and time.time() - t0 < 5:
+            j.progress()
+        assert req.contents.status == U.UCC_ERR_TIMED_OUT
+        assert time.time() - t0 >= 0.19
+        U.ucc_collective_finalize(req)
+        # the late rank still has to run its side so that sequence numbers stay aligned
+        args1 = coll_args("allreduce", src, np.zeros(16, np.float32), timeout=0.2)
+        req1 = C.POINTER(U.ucc_coll_req_t)()
+        assert U.ucc_collective_init(C.byref(args1), C.byref(req1), team.members[1].team) == U.UCC_OK
+        assert U.ucc_collective_post(req1) == U.UCC_OK
+        t0 = time.time()
+        while req1.contents.status == U.UCC_INPROGRESS and time.time() - t0 < 5:
+            j.progress()
+        assert req1.contents.status in (U.UCC_OK, U.UCC_ERR_TIMED_OUT)
+        U.ucc_collective_finalize(req1)
+
+
+def test_active_set_bcast():
+    # reference test_active_set.cc: point-to-point style bcast between a strided pair inside a bigger team
+    n = 8
+    with UccJob(n) as j:
+        team = j.create_team()
+        for start, stride, size in ((0, 1, 2), (1, 3, 2), (2, 2, 3), (7, -3, 3)):
+            members = [start + i * stride for i in range(size)]
+            root = members[0]
+            bufs = {r: (np.arange(100, dtype=np.int32) + 7 * root if r == root else np.zeros(100, np.int32)) for r in members}
+            reqs = []
+            for r in members:
+                a = coll_args("bcast", bufs[r], None, dt="int32", root=root, active_set=(start, stride, size), tag=5)
+                q = C.POINTER(U.ucc_coll_req_t)()
+                assert U.ucc_collective_init(C.byref(a), C.byref(q), team.members[r].team) == U.UCC_OK
+                reqs.append((q, a))
+            for q, _ in reqs:
+                assert U.ucc_collective_post(q) == U.UCC_OK
+            t0 = time.time()
+            while any(q.contents.status == U.UCC_INPROGRESS for q, _ in reqs) and time.time() - t0 < 10:
+                j.progress()
+            for q, _ in reqs:
+                assert q.contents.status == U.UCC_OK
+                U.ucc_collective_finalize(q)
+            for r in members:
+                assert np.array_equal(bufs[r], np.arange(100, dtype=np.int32) + 7 * root), (start, stride, r)
+        # the full team still works afterwards (sequence numbers untouched)
+        src = [np.full(4, 1, np.int32) for _ in range(n)]
+        dst = [np.zeros(4, np.int32) for _ in range(n)]
+        assert run(team, [coll_args("allreduce", src[r], dst[r], dt="int32") for r in range(n)]) == U.UCC_OK
+        assert np.all(dst[3] == n)
+
+
+def test_callback_on_completion():
+    with UccJob(2) as j:
+        team = j.create_team()
+        fired = []
+        CB = U.COLL_CB_FN
+
+        def mk(i):
+            return CB(lambda data, st: fired.append((i, st)))
+        cbs = [mk(i) for i in range(2)]
+        src = [np.full(8, r + 1.0, np.float32) for r in range(2)]
+        dst = [np.zeros(8, np.float32) for _ in range(2)]
+        args = []
+        for r in range(2):
+            a = coll_args("allreduce", src[r], dst[r])
+            a.mask |= U.UCC_COLL_ARGS_FIELD_CB
+            a.cb.cb = cbs[r]
+            a.cb.data = None
+            args.append(a)
+        req = team.coll(args)
+        assert req.run() == U.UCC_OK
+        req.finalize()
+        assert sorted(fired) == [(0, U.UCC_OK), (1, U.UCC_OK)]
+
+
+def test_init_and_post_and_errors():
+    with UccJob(2) as j:
+        team = j.create_team()
+        # invalid: unknown collective type
+        a = coll_args("allreduce", np.zeros(4, np.float32), np.zeros(4, np.float32))
+        a.coll_type = 1 << 20
+        q = C.POINTER(U.ucc_coll_req_t)()
+        assert U.ucc_collective_init(C.byref(a), C.byref(q), team.members[0].team) < 0
+        # init_and_post
+        src = [np.full(8, r + 1, np.int32) for r in range(2)]
+        dst = [np.zeros(8, np.int32) for _ in range(2)]
+        qs = []
+        for r in range(2):
+            a = coll_args("allreduce", src[r], dst[r], dt="int32")
+            q = C.POINTER(U.ucc_coll_req_t)()
+            assert U.ucc_collective_init_and_post(C.byref(a), C.byref(q), team.members[r].team) == U.UCC_OK
+            qs.append((q, a))
+        while any(q.contents.status == U.UCC_INPROGRESS for q, _ in qs):
+            j.progress()
+        for q, _ in qs:
+            assert q.contents.status == U.UCC_OK
+            U.ucc_collective_finalize(q)
+        assert np.all(dst[0] == 3)
+
+
+def test_thread_multiple_concurrent_progress():
+    import threading
+    n = 4
+    with UccJob(n, thread_mode=U.UCC_THREAD_MULTIPLE) as j:
+        team = j.create_team()
+        errs = []
+
+        def worker(r):
+            try:
+                for k in range(30):
+                    src = np.full(2048, r + k, np.int64)
+                    dst = np.zeros(2048, np.int64)
+                    a = coll_args("allreduce", src, dst, dt="int64")
+                    q = C.POINTER(U.ucc_coll_req_t)()
+                    U.check(U.ucc_collective_init(C.byref(a), C.byref(q), team.members[r].team), "init")
+                    U.check(U.ucc_collective_post(q), "post")
+                    t0 = time.time()
+                    while q.contents.status == U.UCC_INPROGRESS:
+                        U.ucc_context_progress(j.procs[r].ctx)
+                        if time.time() - t0 > 60:
+                            raise TimeoutError()
+                    assert q.contents.status == U.UCC_OK
+                    U.ucc_collective_finalize(q)
+                    assert np.all(dst == sum(range(n)) + n * k), (r, k)
+            except Exception as e:  # noqa: BLE001
+                errs.append(repr(e))
+        ths = [threading.Thread(target=worker, args=(r,)) for r in range(n)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        assert not errs, errs
+
+
+def test_mem_map_export_import():
+    U.lib.ucc_mem_map.argtypes = [U.handle, C.c_int, C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_void_p)]
+    U.lib.ucc_mem_map.restype = C.c_int
+    U.lib.ucc_mem_unmap.argtypes = [C.POINTER(C.c_void_p)]
+    U.lib.ucc_mem_unmap.restype = C.c_int
+    with UccJob(2) as j:
+        buf = np.arange(1024, dtype=np.int32)
+        seg = U.ucc_mem_map_t(buf.ctypes.data, buf.nbytes)
+        params = U.ucc_mem_map_params_t()
+        params.segments = C.pointer(seg)
+        params.n_segments = 1
+        memh, size = C.c_void_p(), C.c_size_t()
+        assert U.lib.ucc_mem_map(j.procs[0].ctx, 0, C.byref(params), C.byref(size), C.byref(memh)) == U.UCC_OK
+        assert size.value > 0 and memh.value
+        # "send" the relocatable handle to the peer and import it there
+        blob = C.create_string_buffer(C.string_at(memh.value, size.value), size.value)
+        imp, isz = C.c_void_p(C.addressof(blob)), C.c_size_t()
+        assert U.lib.ucc_mem_map(j.procs[1].ctx, 1, None, C.byref(isz), C.byref(imp)) == U.UCC_OK
+        assert isz.value == size.value
+        # garbage is rejected
+        junk = C.create_string_buffer(64)
+        jp = C.c_void_p(C.addressof(junk))
+        assert U.lib.ucc_mem_map(j.procs[1].ctx, 1, None, None, C.byref(jp)) != U.UCC_OK
+        # unsupported modes
+        assert U.lib.ucc_mem_map(j.procs[0].ctx, 2, C.byref(params), C.byref(size), C.byref(C.c_void_p())) == U.UCC_ERR_NOT_SUPPORTED
+        assert U.lib.ucc_mem_unmap(C.byref(memh)) == U.UCC_OK

@@ -53,3 +53,14 @@ def test_multiproc_no_zcopy():
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
     _run(n, {"UCC_TL_NVL_ZCOPY": "n"})
+
+
+def test_parallel_helpers_cuda():
+    """DDP buckets / tensor parallel / MoE alltoallv on CUDA tensors through the tl/nvl kernels."""
+    n = torch.cuda.device_count() if torch.cuda.is_available() else 0
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+           "--master-port", "29790", os.path.join(ROOT, "tests", "parallel_worker.py"), "cuda"]
+    out = subprocess.run(cmd, env=dict(os.environ, PYTHONPATH=ROOT), capture_output=True, text=True, timeout=900)
+    assert "PARALLEL_WORKER_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]

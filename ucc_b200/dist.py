@@ -65,13 +65,30 @@ class Request:
         U.check(U.ucc_collective_post(self.req), "collective_post")
         return self
 
-    def post_on_stream(self, stream=None):
-        """Stream-ordered post: the collective kernel is enqueued on `stream` (default: current)."""
+    def post_on_stream(self, stream=None, wait_posted=True):
+        """Stream-ordered post: the collective kernel is enqueued on `stream` (default: current).
+
+        With `wait_posted` the call returns once UCC_EVENT_COLLECTIVE_POST was delivered, i.e. the kernel really is
+        in the stream (a zero-copy collective first learns the peers' buffer mappings, which takes a few host
+        microseconds); work enqueued on the stream afterwards is ordered behind the collective."""
         ev = U.ucc_ev_t()
         ev.ev_type = U.UCC_EVENT_COMPUTE_COMPLETE
         ev.req = C.cast(self.req, C.c_void_p)
-        U.check(U.ucc_collective_triggered_post(self.comm.ee_for(stream), C.byref(ev)), "triggered_post")
+        self._ee = self.comm.ee_for(stream)
+        U.check(U.ucc_collective_triggered_post(self._ee, C.byref(ev)), "triggered_post")
+        if wait_posted:
+            self.wait_posted()
         return self
+
+    def wait_posted(self):
+        key = C.cast(self.req, C.c_void_p).value
+        while key not in self.comm._posted:
+            st = self.req.contents.status
+            if st < 0:
+                raise U.UccError(st, "collective")
+            if not self.comm.collect_events(self._ee):
+                U.ucc_context_progress(self.comm.ctx)
+        self.comm._posted.discard(key)
 
     def test(self):
         return self.req.contents.status
@@ -136,6 +153,7 @@ class Communicator:
             U.check(st, "team_create_test")
             U.ucc_context_progress(self.ctx)
         self._ees = {}
+        self._posted = set()
 
     # ------------------------------------------------------------------ streams
     def ee_for(self, stream=None):
@@ -149,11 +167,22 @@ class Communicator:
             self._ees[key] = ee
         return self._ees[key]
 
+    def collect_events(self, ee):
+        """Move pending EE events into the bookkeeping sets; returns how many were seen."""
+        n = 0
+        ev = C.POINTER(U.ucc_ev_t)()
+        while U.ucc_ee_get_event(ee, C.byref(ev)) == U.UCC_OK:
+            if ev.contents.ev_type == U.UCC_EVENT_COLLECTIVE_POST and ev.contents.req:
+                self._posted.add(ev.contents.req)
+            U.ucc_ee_ack_event(ee, ev)
+            n += 1
+        return n
+
     def drain_events(self):
         for ee in self._ees.values():
-            ev = C.POINTER(U.ucc_ev_t)()
-            while U.ucc_ee_get_event(ee, C.byref(ev)) == U.UCC_OK:
-                U.ucc_ee_ack_event(ee, ev)
+            self.collect_events(ee)
+        if len(self._posted) > 4096:
+            self._posted.clear()
 
     def progress(self):
         U.ucc_context_progress(self.ctx)
@@ -193,6 +222,7 @@ class Communicator:
         for ee in self._ees.values():
             U.ucc_ee_destroy(ee)
         self._ees = {}
+        self._posted = set()
         while True:
             st = U.ucc_team_destroy(self.team)
             if st != U.UCC_INPROGRESS:

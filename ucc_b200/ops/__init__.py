@@ -1,0 +1,120 @@
+"""Functional collectives on torch tensors, executed by libucc (tl/nvl kernels for CUDA tensors, tl/shm for host).
+
+The call shapes follow torch.distributed so a user of `torch.distributed` + ProcessGroupUCC (reference consumer:
+pytorch/torch-ucc) can switch by changing the import.  Every function returns a `Work` whose `.wait()` blocks the
+host; with `async_op=False` (default) the wait is done before returning.  CUDA tensors are posted stream-ordered
+(ucc_collective_triggered_post) on the current stream."""
+from __future__ import annotations
+
+import torch
+
+from ..dist import Communicator
+
+_default = None
+
+
+def init(group=None, **kw) -> Communicator:
+    """Create (once) the default communicator over `group` (default: WORLD)."""
+    global _default
+    if _default is None:
+        _default = Communicator(group, **kw)
+    return _default
+
+
+def default_comm() -> Communicator:
+    return init()
+
+
+def shutdown():
+    global _default
+    if _default is not None:
+        _default.destroy()
+        _default = None
+
+
+class Work:
+    def __init__(self, req, keep=()):
+        self.req, self._keep = req, keep
+
+    def is_completed(self):
+        return self.req is None or self.req.test() == 0
+
+    def wait(self):
+        if self.req is not None:
+            self.req.wait()
+            self.req.finalize()
+            self.req = None
+        return True
+
+
+def _launch(comm, req, tensor, async_op, keep=()):
+    if tensor is not None and tensor.is_cuda:
+        req.post_on_stream()
+    else:
+        req.post()
+    w = Work(req, keep)
+    if not async_op:
+        w.wait()
+    return w
+
+
+def all_reduce(tensor, op="sum", comm=None, async_op=False):
+    comm = comm or default_comm()
+    return _launch(comm, comm.allreduce_init(tensor, tensor, op=op), tensor, async_op)
+
+
+def reduce(tensor, dst=0, op="sum", comm=None, async_op=False):
+    comm = comm or default_comm()
+    req = comm.coll_init("reduce", None if comm.rank == dst else tensor, tensor if comm.rank == dst else None, op=op, root=dst, inplace=comm.rank == dst)
+    return _launch(comm, req, tensor, async_op)
+
+
+def broadcast(tensor, src=0, comm=None, async_op=False):
+    comm = comm or default_comm()
+    return _launch(comm, comm.coll_init("bcast", tensor, None, root=src), tensor, async_op)
+
+
+def all_gather_into_tensor(output, input, comm=None, async_op=False):
+    comm = comm or default_comm()
+    assert output.numel() == input.numel() * comm.size
+    return _launch(comm, comm.coll_init("allgather", input, output), input, async_op)
+
+
+def reduce_scatter_tensor(output, input, op="sum", comm=None, async_op=False):
+    comm = comm or default_comm()
+    assert input.numel() == output.numel() * comm.size
+    return _launch(comm, comm.coll_init("reduce_scatter", input, output, op=op), input, async_op)
+
+
+def all_to_all_single(output, input, output_split_sizes=None, input_split_sizes=None, comm=None, async_op=False):
+    """Equal splits -> alltoall; explicit split sizes (in elements of dim 0 rows) -> alltoallv (MoE dispatch / combine)."""
+    comm = comm or default_comm()
+    if output_split_sizes is None and input_split_sizes is None:
+        return _launch(comm, comm.coll_init("alltoall", input, output), input, async_op)
+    row = input[0].numel() if input.dim() > 1 else 1
+    sc = [int(s) * row for s in input_split_sizes]
+    rc = [int(s) * row for s in output_split_sizes]
+    sd = [sum(sc[:i]) for i in range(len(sc))]
+    rd = [sum(rc[:i]) for i in range(len(rc))]
+    req = comm.coll_init("alltoallv", input, output, src_counts=sc, src_displs=sd, dst_counts=rc, dst_displs=rd)
+    return _launch(comm, req, input, async_op)
+
+
+def all_gather_v(output, input, counts, comm=None, async_op=False):
+    comm = comm or default_comm()
+    displs = [sum(counts[:i]) for i in range(len(counts))]
+    return _launch(comm, comm.coll_init("allgatherv", input, output, dst_counts=list(counts), dst_displs=displs), input, async_op)
+
+
+def gather(output, input, dst=0, comm=None, async_op=False):
+    comm = comm or default_comm()
+    return _launch(comm, comm.coll_init("gather", input, output if comm.rank == dst else None, root=dst), input, async_op)
+
+
+def scatter(output, input, src=0, comm=None, async_op=False):
+    comm = comm or default_comm()
+    return _launch(comm, comm.coll_init("scatter", input if comm.rank == src else None, output, root=src), output, async_op)
+
+
+def barrier(comm=None):
+    (comm or default_comm()).barrier()
