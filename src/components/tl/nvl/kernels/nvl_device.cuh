@@ -37,6 +37,25 @@ NVL_DEV void st_v4(void *p, uint4 v)
 NVL_DEV uint4 mc_ld_reduce_f32(const void *mc) { uint4 v; asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(mc) : "memory"); return v; }
 NVL_DEV uint4 mc_ld_reduce_bf16(const void *mc) { uint4 v; asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(mc) : "memory"); return v; }
 NVL_DEV uint4 mc_ld_reduce_f16(const void *mc) { uint4 v; asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.f16x2 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(mc) : "memory"); return v; }
+/* integer / bitwise in-switch reductions are scalar (32 or 64 bit per instruction): 4 resp. 2 of them make one 16-byte vector
+ * (reference kernels K2: tl/cuda/kernels/allreduce_kernel.cu:59-141 do the same for add) */
+#define NVL_MC_RED32(_name, _op)                                                                                         \
+    NVL_DEV uint4 _name(const void *mc) { uint4 v; const char *p = static_cast<const char *>(mc);                          \
+        asm volatile("multimem.ld_reduce.relaxed.sys.global." _op " %0, [%1];" : "=r"(v.x) : "l"(p) : "memory");        \
+        asm volatile("multimem.ld_reduce.relaxed.sys.global." _op " %0, [%1];" : "=r"(v.y) : "l"(p + 4) : "memory");    \
+        asm volatile("multimem.ld_reduce.relaxed.sys.global." _op " %0, [%1];" : "=r"(v.z) : "l"(p + 8) : "memory");    \
+        asm volatile("multimem.ld_reduce.relaxed.sys.global." _op " %0, [%1];" : "=r"(v.w) : "l"(p + 12) : "memory");   \
+        return v; }
+#define NVL_MC_RED64(_name, _op)                                                                                         \
+    NVL_DEV uint4 _name(const void *mc) { unsigned long long a, b; const char *p = static_cast<const char *>(mc);         \
+        asm volatile("multimem.ld_reduce.relaxed.sys.global." _op " %0, [%1];" : "=l"(a) : "l"(p) : "memory");          \
+        asm volatile("multimem.ld_reduce.relaxed.sys.global." _op " %0, [%1];" : "=l"(b) : "l"(p + 8) : "memory");      \
+        return make_uint4((unsigned)a, (unsigned)(a >> 32), (unsigned)b, (unsigned)(b >> 32)); }
+NVL_MC_RED32(mc_red_add_s32, "add.s32") NVL_MC_RED32(mc_red_add_u32, "add.u32") NVL_MC_RED32(mc_red_min_s32, "min.s32") NVL_MC_RED32(mc_red_max_s32, "max.s32")
+NVL_MC_RED32(mc_red_min_u32, "min.u32") NVL_MC_RED32(mc_red_max_u32, "max.u32") NVL_MC_RED32(mc_red_and_b32, "and.b32") NVL_MC_RED32(mc_red_or_b32, "or.b32")
+NVL_MC_RED32(mc_red_xor_b32, "xor.b32")
+NVL_MC_RED64(mc_red_add_u64, "add.u64") NVL_MC_RED64(mc_red_min_s64, "min.s64") NVL_MC_RED64(mc_red_max_s64, "max.s64") NVL_MC_RED64(mc_red_min_u64, "min.u64")
+NVL_MC_RED64(mc_red_max_u64, "max.u64") NVL_MC_RED64(mc_red_and_b64, "and.b64") NVL_MC_RED64(mc_red_or_b64, "or.b64") NVL_MC_RED64(mc_red_xor_b64, "xor.b64")
 NVL_DEV void mc_st_v4(void *mc, uint4 v) { asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); }
 
 /* ------------------------------------------------------------------ */

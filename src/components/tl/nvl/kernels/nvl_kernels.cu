@@ -56,16 +56,96 @@ template <bool PEER> static __device__ __forceinline__ void copy_bytes_grid(char
     }
 }
 
+/* store up to 16 bytes of x at an arbitrarily aligned address */
+static __device__ __forceinline__ void store_any16(char *d, uint4 x, size_t nbytes)
+{
+    if (nbytes >= 16 && ((uintptr_t)d & 15) == 0) { st_v4(d, x); return; }
+    const unsigned w[4] = {x.x, x.y, x.z, x.w};
+    if (((uintptr_t)d & 3) == 0 && (nbytes & 3) == 0) { for (size_t i = 0; i < nbytes / 4 && i < 4; i++) reinterpret_cast<unsigned *>(d)[i] = w[i]; return; }
+    for (size_t i = 0; i < nbytes && i < 16; i++) d[i] = (char)(w[i >> 2] >> (8 * (i & 3)));
+}
+
+/* ring allgather(v) (reference tl/cuda allgatherv_ring.c: host-driven multi-ring pipeline through scratch): N-1 steps, at
+ * step s every rank pulls block (me-1-s) from its LEFT neighbour's heap into its own heap and into dst.  Only
+ * neighbour links are used, so it also serves topologies without an all-to-all NVLink fabric.  All heaps use the
+ * same 16-byte aligned block layout (pull_off[]), which makes block b of a rank depend only on block b of its
+ * neighbour: one per-block flag wait per step. */
+static __device__ void exchange_ring(const nvl_xchg_args_t &a, BlockSync &bs)
+{
+    const nvl_team_dev_t &t = a.team;
+    const int N = t.size, me = t.rank, L = (me + N - 1) % N;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (size_t)gridDim.x * blockDim.x;
+    char *mine = data_of(t, me) + NVL_XCHG_TABLE_BYTES;
+    const char *left = data_of(t, L) + NVL_XCHG_TABLE_BYTES;
+    /* step -1: my own block into my heap (vector granularity, identical thread->vector mapping as the steps below) and into dst */
+    {
+        const size_t n = a.pull_bytes[me], nv = (n + 15) / 16;
+        const char *s = static_cast<const char *>(a.src);
+        char *d = static_cast<char *>(a.dst) + a.dst_off[me];
+        for (size_t v = tid; v < nv; v += nt) {
+            const size_t nb = n - v * 16 < 16 ? n - v * 16 : 16;
+            uint4 x = make_uint4(0, 0, 0, 0);
+            if (nb == 16 && ((uintptr_t)s & 15) == 0) x = ld_src_v4(s + v * 16);
+            else { unsigned w[4] = {0, 0, 0, 0}; for (size_t i = 0; i < nb; i++) w[i >> 2] |= (unsigned)(unsigned char)s[v * 16 + i] << (8 * (i & 3)); x = make_uint4(w[0], w[1], w[2], w[3]); }
+            st_v4(mine + a.pull_off[me] + v * 16, x);
+            if (d != s) store_any16(d + v * 16, x, nb);
+        }
+    }
+    for (int s = 0; s + 1 < N; s++) {
+        const int c = (me - 1 - s + 2 * N) % N;
+        const size_t n = a.pull_bytes[c], nv = (n + 15) / 16;
+        char *d = static_cast<char *>(a.dst) + a.dst_off[c];
+        bs.barrier(t, (uint32_t)s + 1);
+        for (size_t v = tid; v < nv; v += 4 * nt) {
+            uint4 x[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) if (v + u * nt < nv) x[u] = ld_peer_v4(left + a.pull_off[c] + (v + u * nt) * 16);
+#pragma unroll
+            for (int u = 0; u < 4; u++) if (v + u * nt < nv) {
+                const size_t vv = v + u * nt, nb = n - vv * 16 < 16 ? n - vv * 16 : 16;
+                if (s + 2 < N) st_v4(mine + a.pull_off[c] + vv * 16, x[u]); /* the last step's block is not forwarded */
+                store_any16(d + vv * 16, x[u], nb);
+            }
+        }
+    }
+    bs.barrier(t, (uint32_t)N); /* nobody leaves while its right neighbour may still be reading its heap */
+    bs.finish((uint32_t)N);
+}
+
 __global__ void __launch_bounds__(NVL_THREADS_MAX) nvl_exchange_kernel(nvl_xchg_args_t a)
 {
     const nvl_team_dev_t &t = a.team;
     const int N = t.size, me = t.rank;
     BlockSync bs; bs.init(t);
     char *mydata = data_of(t, me);
+    if (a.ring) { exchange_ring(a, bs); return; }
     /* phase A: publish my bytes (and the offset table peers use to find their block) */
     if (a.publish_table && blockIdx.x == 0 && (int)threadIdx.x < N) reinterpret_cast<uint64_t *>(mydata)[threadIdx.x] = (uint64_t)a.stage_off[threadIdx.x];
-    /* zero-copy mode: the peers read my user buffer in place, nothing to stage */
-    if (a.src_bytes && !a.direct) copy_bytes_grid<false>(mydata + NVL_XCHG_TABLE_BYTES, static_cast<const char *>(a.src), a.src_bytes);
+    if (a.use_mc) {
+        /* NVLS push (reference kernel K5, tl/cuda/kernels/allgatherv_kernel.cu:19-51, there followed by a cudaMemcpyAsync):
+         * one multimem.st per vector lands my block in EVERY member's heap; phase B then is a local copy */
+        if (a.src_bytes) {
+            char *mc = t.mc_heap + NVL_DATA_OFFSET + NVL_XCHG_TABLE_BYTES + a.push_off;
+            const char *s = static_cast<const char *>(a.src);
+            /* a misaligned source (only its owner knows) cannot feed 16-byte multicast stores: it goes the slow per-byte way */
+            const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (size_t)gridDim.x * blockDim.x, nv = ((uintptr_t)s & 15) ? 0 : a.src_bytes / 16;
+            size_t v = tid;
+            for (; v + 3 * nt < nv; v += 4 * nt) {
+                uint4 x[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) x[u] = ld_src_v4(s + (v + u * nt) * 16);
+#pragma unroll
+                for (int u = 0; u < 4; u++) mc_st_v4(mc + (v + u * nt) * 16, x[u]);
+            }
+            for (; v < nv; v += nt) mc_st_v4(mc + v * 16, ld_src_v4(s + v * 16));
+            /* ragged tail (< 16 bytes): plain stores into each member's heap */
+            for (size_t i = nv * 16 + tid; i < a.src_bytes; i += nt)
+                for (int p = 0; p < N; p++) data_of(t, p)[NVL_XCHG_TABLE_BYTES + a.push_off + i] = s[i];
+        }
+    } else if (a.src_bytes && !a.direct) {
+        /* (zero-copy mode: the peers read my user buffer in place, nothing to stage) */
+        copy_bytes_grid<false>(mydata + NVL_XCHG_TABLE_BYTES, static_cast<const char *>(a.src), a.src_bytes);
+    }
     bs.signal(t, 1);
     bs.wait_all_blocks(t, 1);
     /* phase B: pull */
@@ -77,7 +157,7 @@ __global__ void __launch_bounds__(NVL_THREADS_MAX) nvl_exchange_kernel(nvl_xchg_
         if (p == me) { if (d != static_cast<const char *>(a.src) + a.self_off) copy_bytes_grid<false>(d, static_cast<const char *>(a.src) + a.self_off, n); continue; }
         size_t off = a.pull_off[p];
         if (off == NVL_XCHG_LOOKUP) off = (size_t) * reinterpret_cast<volatile const uint64_t *>(data_of(t, p) + (size_t)me * 8);
-        copy_bytes_grid<true>(d, (a.direct ? a.d.src[p] : data_of(t, p) + NVL_XCHG_TABLE_BYTES) + off, n);
+        copy_bytes_grid<true>(d, (a.direct ? a.d.src[p] : (a.use_mc ? mydata : data_of(t, p)) + NVL_XCHG_TABLE_BYTES) + off, n);
     }
     bs.signal(t, 2);
     bs.wait_all_blocks(t, 2);
@@ -100,7 +180,13 @@ extern "C" int nvl_dt_supports_op(int dt, int op)
     return 1;
 }
 extern "C" int nvl_nvls_supports(int dt, int op)
-{ return (op == NVL_OP_SUM || op == NVL_OP_AVG) && (dt == NVL_DT_F32 || dt == NVL_DT_BF16 || dt == NVL_DT_F16); }
+{
+    /* mirrors the McRed<T,OP> specialisations: what multimem.ld_reduce can do for 16-byte vectors of that type */
+    if (dt == NVL_DT_F32 || dt == NVL_DT_BF16 || dt == NVL_DT_F16) return op == NVL_OP_SUM || op == NVL_OP_AVG;
+    if (dt == NVL_DT_I32 || dt == NVL_DT_U32 || dt == NVL_DT_I64 || dt == NVL_DT_U64)
+        return op == NVL_OP_SUM || op == NVL_OP_MIN || op == NVL_OP_MAX || op == NVL_OP_BAND || op == NVL_OP_BOR || op == NVL_OP_BXOR;
+    return 0;
+}
 
 typedef cudaError_t (*nvl_red_launch_fn)(const nvl_red_args_t *, int, int, cudaStream_t);
 #define DECL(_s) extern "C" cudaError_t nvl_launch_oneshot_##_s(const nvl_red_args_t *, int, int, cudaStream_t); \
@@ -132,6 +218,16 @@ extern "C" cudaError_t nvl_launch_reduce_direct(const nvl_red_args_t *a, int nbl
     if (nthreads > NVL_THREADS_MAX) nthreads = NVL_THREADS_MAX;
     if (a->dt < 0 || a->dt >= NVL_DT_LAST) return cudaErrorInvalidValue;
     return direct_fns[a->dt](a, nblocks, nthreads, s);
+}
+#define DECLS(_s) extern "C" cudaError_t nvl_launch_steps_##_s(const nvl_red_args_t *, int, int, cudaStream_t);
+DECLS(i8) DECLS(i16) DECLS(i32) DECLS(i64) DECLS(u8) DECLS(u16) DECLS(u32) DECLS(u64) DECLS(f16) DECLS(f32) DECLS(f64) DECLS(bf16)
+static const nvl_red_launch_fn steps_fns[NVL_DT_LAST] = {nvl_launch_steps_i8, nvl_launch_steps_i16, nvl_launch_steps_i32, nvl_launch_steps_i64, nvl_launch_steps_u8, nvl_launch_steps_u16,
+    nvl_launch_steps_u32, nvl_launch_steps_u64, nvl_launch_steps_f16, nvl_launch_steps_f32, nvl_launch_steps_f64, nvl_launch_steps_bf16};
+extern "C" cudaError_t nvl_launch_reduce_steps(const nvl_red_args_t *a, int nblocks, int nthreads, cudaStream_t s)
+{
+    if (nthreads > NVL_THREADS_MAX) nthreads = NVL_THREADS_MAX;
+    if (a->dt < 0 || a->dt >= NVL_DT_LAST) return cudaErrorInvalidValue;
+    return steps_fns[a->dt](a, nblocks, nthreads, s);
 }
 extern "C" cudaError_t nvl_launch_exchange(const nvl_xchg_args_t *a, int nblocks, int nthreads, cudaStream_t s)
 {

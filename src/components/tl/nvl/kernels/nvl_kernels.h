@@ -73,6 +73,7 @@ typedef struct nvl_red_args {
     int            use_nvls;    /* reduce in the switch (multimem.ld_reduce) instead of pulling */
     size_t         rs_offset[NVL_MAX_PEERS]; /* REDUCE_SCATTER(V): element offset / count of each rank's block */
     size_t         rs_count[NVL_MAX_PEERS];
+    int            sched;       /* step-structured kernel: 1 = ring, 2 = recursive halving / doubling */
     int            direct;      /* nvl_direct_mode_t: FULL = read peers' src and write peers' dst in place (no staging at all);
                                    DST = staged/NVLS reduction whose result goes straight into every member's dst (no copy-out) */
     nvl_direct_t   d;
@@ -93,6 +94,9 @@ typedef struct nvl_xchg_args {
     size_t         pull_off[NVL_MAX_PEERS], pull_bytes[NVL_MAX_PEERS], dst_off[NVL_MAX_PEERS];
     size_t         self_off;
     int            publish_table;
+    int            use_mc;       /* NVLS push: phase A multimem.st's my bytes to offset push_off of EVERY heap, phase B reads my own heap */
+    size_t         push_off;
+    int            ring;         /* allgather(v) over neighbour links only: pull_off[] is the common heap layout, N-1 pull steps */
     int            direct;       /* pull from the peers' user buffers (d.src[p]) instead of their staged copies */
     nvl_direct_t   d;
 } nvl_xchg_args_t;
@@ -109,6 +113,8 @@ cudaError_t  nvl_launch_allreduce_oneshot(const nvl_red_args_t *a, int nblocks, 
 cudaError_t  nvl_launch_reduce_staged(const nvl_red_args_t *a, int nblocks, int nthreads, cudaStream_t s);
 /* zero-copy two-shot: every rank reduces its slice straight out of the members' src buffers into their dst buffers */
 cudaError_t  nvl_launch_reduce_direct(const nvl_red_args_t *a, int nblocks, int nthreads, cudaStream_t s);
+/* ring / recursive halving-doubling allreduce and reduce_scatter(v) through the heaps (a->sched), single round */
+cudaError_t  nvl_launch_reduce_steps(const nvl_red_args_t *a, int nblocks, int nthreads, cudaStream_t s);
 cudaError_t  nvl_launch_exchange(const nvl_xchg_args_t *a, int nblocks, int nthreads, cudaStream_t s);
 cudaError_t  nvl_launch_barrier(const nvl_team_dev_t *t, cudaStream_t s);
 cudaError_t  nvl_launch_ctrl_init(void *heap_base, cudaStream_t s);

@@ -88,10 +88,20 @@ template <typename T> __global__ void __launch_bounds__(NVL_THREADS_MAX) nvl_all
 /* ------------------------------------------------------------------ */
 /* staged two-shot reduction: allreduce / reduce_scatter(v) / reduce   */
 /* ------------------------------------------------------------------ */
-template <typename T> static __device__ __forceinline__ uint4 mc_ld_reduce(const void *mc) { return make_uint4(0, 0, 0, 0); }
-template <> __device__ __forceinline__ uint4 mc_ld_reduce<float>(const void *mc) { return mc_ld_reduce_f32(mc); }
-template <> __device__ __forceinline__ uint4 mc_ld_reduce<__half>(const void *mc) { return mc_ld_reduce_f16(mc); }
-template <> __device__ __forceinline__ uint4 mc_ld_reduce<__nv_bfloat16>(const void *mc) { return mc_ld_reduce_bf16(mc); }
+/* (datatype, operator) pairs the NVSwitch can reduce; must mirror nvl_nvls_supports() in nvl_kernels.cu */
+template <typename T, int OP> struct McRed { static __device__ __forceinline__ uint4 ld(const void *) { return make_uint4(0, 0, 0, 0); } };
+#define NVL_MCRED(_T, _OP, _fn) template <> struct McRed<_T, _OP> { static __device__ __forceinline__ uint4 ld(const void *p) { return _fn(p); } };
+NVL_MCRED(float, NVL_OP_SUM, mc_ld_reduce_f32) NVL_MCRED(float, NVL_OP_AVG, mc_ld_reduce_f32)
+NVL_MCRED(__half, NVL_OP_SUM, mc_ld_reduce_f16) NVL_MCRED(__half, NVL_OP_AVG, mc_ld_reduce_f16)
+NVL_MCRED(__nv_bfloat16, NVL_OP_SUM, mc_ld_reduce_bf16) NVL_MCRED(__nv_bfloat16, NVL_OP_AVG, mc_ld_reduce_bf16)
+NVL_MCRED(int32_t, NVL_OP_SUM, mc_red_add_s32) NVL_MCRED(int32_t, NVL_OP_MIN, mc_red_min_s32) NVL_MCRED(int32_t, NVL_OP_MAX, mc_red_max_s32)
+NVL_MCRED(int32_t, NVL_OP_BAND, mc_red_and_b32) NVL_MCRED(int32_t, NVL_OP_BOR, mc_red_or_b32) NVL_MCRED(int32_t, NVL_OP_BXOR, mc_red_xor_b32)
+NVL_MCRED(uint32_t, NVL_OP_SUM, mc_red_add_u32) NVL_MCRED(uint32_t, NVL_OP_MIN, mc_red_min_u32) NVL_MCRED(uint32_t, NVL_OP_MAX, mc_red_max_u32)
+NVL_MCRED(uint32_t, NVL_OP_BAND, mc_red_and_b32) NVL_MCRED(uint32_t, NVL_OP_BOR, mc_red_or_b32) NVL_MCRED(uint32_t, NVL_OP_BXOR, mc_red_xor_b32)
+NVL_MCRED(int64_t, NVL_OP_SUM, mc_red_add_u64) NVL_MCRED(int64_t, NVL_OP_MIN, mc_red_min_s64) NVL_MCRED(int64_t, NVL_OP_MAX, mc_red_max_s64)
+NVL_MCRED(int64_t, NVL_OP_BAND, mc_red_and_b64) NVL_MCRED(int64_t, NVL_OP_BOR, mc_red_or_b64) NVL_MCRED(int64_t, NVL_OP_BXOR, mc_red_xor_b64)
+NVL_MCRED(uint64_t, NVL_OP_SUM, mc_red_add_u64) NVL_MCRED(uint64_t, NVL_OP_MIN, mc_red_min_u64) NVL_MCRED(uint64_t, NVL_OP_MAX, mc_red_max_u64)
+NVL_MCRED(uint64_t, NVL_OP_BAND, mc_red_and_b64) NVL_MCRED(uint64_t, NVL_OP_BOR, mc_red_or_b64) NVL_MCRED(uint64_t, NVL_OP_BXOR, mc_red_xor_b64)
 
 struct SlicePlan {
     size_t off[NVL_MAX_PEERS], cnt[NVL_MAX_PEERS]; /* elements of the user vector owned by slice s */
@@ -166,7 +176,7 @@ static __device__ __forceinline__ void reduce_nvls(const nvl_red_args_t &a, size
     for (size_t j = j0 + threadIdx.x; j < jend; j += U * nt) {
         uint4 r[U];
 #pragma unroll
-        for (int u = 0; u < U; u++) if (j + u * nt < jend) r[u] = mc_ld_reduce<T>(mc + (j + u * nt) * 16);
+        for (int u = 0; u < U; u++) if (j + u * nt < jend) r[u] = McRed<T, OP>::ld(mc + (j + u * nt) * 16);
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const size_t jj = j + u * nt;
@@ -348,6 +358,142 @@ template <typename T> __global__ void __launch_bounds__(NVL_THREADS_MAX, 2) nvl_
     bs.finish(2);
 }
 
+/* ------------------------------------------------------------------ */
+/* step-structured allreduce / reduce_scatter through the heaps:       */
+/*   sched 1: ring (N-1 reduce-scatter steps + N-1 allgather steps,    */
+/*            neighbour links only)                                    */
+/*   sched 2: recursive halving + recursive doubling (log2 N + log2 N  */
+/*            pairwise steps; "SRA" with radix 2, power-of-two teams)  */
+/* Both keep every slice at the same heap slot on every rank and give  */
+/* block b the same vector range of every slice, so one per-block flag */
+/* wait per step is all the synchronisation needed.  Single round: the */
+/* vector has to fit the heap (larger ones use the two-shot kernels).  */
+/* ------------------------------------------------------------------ */
+/* acc[j] = op(peer[j], mine[j]) for my block's vectors of one slice; optionally scaled (AVG) and mirrored into dst */
+template <typename T, int OP>
+static __device__ __forceinline__ void step_reduce(const char *peer, char *mine, size_t j0, size_t jend, bool last, float inv_n, T *db, size_t rc, bool dal)
+{
+    constexpr int E = 16 / sizeof(T);
+    const size_t nt = blockDim.x;
+    for (size_t j = j0 + threadIdx.x; j < jend; j += 4 * nt) {
+        uint4 x[4], y[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (j + u * nt < jend) { x[u] = ld_peer_v4(peer + (j + u * nt) * 16); y[u] = ld_peer_v4(mine + (j + u * nt) * 16); }
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (j + u * nt < jend) {
+            VecAcc<T, OP> acc; acc.set(y[u]); acc.add(x[u]);
+            const uint4 r = acc.get(last ? inv_n : 1.0f); /* get() scales for AVG only; partial sums must stay unscaled */
+            st_v4(mine + (j + u * nt) * 16, r);
+            if (db) store_dst_vec<T>(db, (j + u * nt) * E, rc, dal, r);
+        }
+    }
+}
+/* mine[j] = peer[j] (+ dst) for my block's vectors of one slice */
+template <typename T>
+static __device__ __forceinline__ void step_copy(const char *peer, char *mine, size_t j0, size_t jend, bool keep, T *db, size_t rc, bool dal)
+{
+    constexpr int E = 16 / sizeof(T);
+    const size_t nt = blockDim.x;
+    for (size_t j = j0 + threadIdx.x; j < jend; j += 4 * nt) {
+        uint4 x[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (j + u * nt < jend) x[u] = ld_peer_v4(peer + (j + u * nt) * 16);
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (j + u * nt < jend) {
+            if (keep) st_v4(mine + (j + u * nt) * 16, x[u]);
+            store_dst_vec<T>(db, (j + u * nt) * E, rc, dal, x[u]);
+        }
+    }
+}
+
+template <typename T, int OP>
+static __device__ __forceinline__ void steps_body(const nvl_red_args_t &a, BlockSync &bs, const SlicePlan &pl, uint32_t &phase)
+{
+    constexpr int E = 16 / sizeof(T);
+    const nvl_team_dev_t &t = a.team;
+    const int N = t.size, me = t.rank, nb = gridDim.x, b = blockIdx.x;
+    const T *src = static_cast<const T *>(a.src);
+    T *dst = static_cast<T *>(a.dst);
+    const size_t cap_bytes = pl.cap_e * sizeof(T);
+    const float inv_n = 1.0f / (float)N;
+    const size_t nvmax = (pl.slice_max + E - 1) / E, per = (nvmax + nb - 1) / nb;
+    const size_t j0 = dmin((size_t)b * per, nvmax), j1 = dmin(j0 + per, nvmax);
+    char *mydata = data_of(t, me);
+    const bool allred = a.kind == NVL_RED_ALLREDUCE;
+#define SLICE_JEND(_s) dmin(j1, (pl.cnt[_s] + E - 1) / E)
+#define SLICE_DST(_s) (dst + (allred ? pl.off[_s] : 0))
+    /* stage every slice of my vector (same loop as phase A of the two-shot kernel) */
+    for (int s = 0; s < N; s++) {
+        const size_t rc = pl.cnt[s], nfull = rc / E, jend = SLICE_JEND(s);
+        const T *sb = src + pl.off[s];
+        char *hb = mydata + (size_t)s * cap_bytes;
+        if (((uintptr_t)sb & 15) == 0) {
+            copy_vecs<8, false>(hb, reinterpret_cast<const char *>(sb), j0, dmin(jend, nfull));
+            if (nfull >= j0 && nfull < jend && threadIdx.x == 0) st_v4(hb + nfull * 16, load_src_vec<T>(sb, nfull * E, rc, false));
+        } else {
+            for (size_t j = j0 + threadIdx.x; j < jend; j += blockDim.x) st_v4(hb + j * 16, load_src_vec<T>(sb, j * E, rc, false));
+        }
+    }
+    bs.barrier(t, ++phase);
+    if (a.sched == 1) {
+        /* ---- ring ---- slice j starts at rank j+1 and ends, complete, at rank j */
+        const int L = (me + N - 1) % N;
+        char *left = data_of(t, L);
+        for (int s = 0; s + 1 < N; s++) {
+            const int c = (me - 2 - s + 3 * N) % N;
+            const bool last = s + 2 == N;
+            T *db = last ? SLICE_DST(c) : nullptr; /* c == me in the last step */
+            step_reduce<T, OP>(left + (size_t)c * cap_bytes, mydata + (size_t)c * cap_bytes, j0, SLICE_JEND(c), last, inv_n, db, pl.cnt[c], db && ((uintptr_t)db & 15) == 0);
+            bs.barrier(t, ++phase);
+        }
+        if (allred) for (int s = 0; s + 1 < N; s++) {
+            const int c = (me - 1 - s + 2 * N) % N;
+            T *db = SLICE_DST(c);
+            step_copy<T>(left + (size_t)c * cap_bytes, mydata + (size_t)c * cap_bytes, j0, SLICE_JEND(c), s + 2 < N, db, pl.cnt[c], ((uintptr_t)db & 15) == 0);
+            bs.barrier(t, ++phase);
+        }
+    } else {
+        /* ---- recursive halving (reduce-scatter) ... ---- */
+        int lo = 0, hi = N; /* slices [lo,hi) are still mine to reduce */
+        for (int d = N >> 1; d >= 1; d >>= 1) {
+            const int partner = me ^ d, mid = lo + (hi - lo) / 2;
+            const int klo = (me & d) ? mid : lo, khi = (me & d) ? hi : mid; /* the half I keep */
+            const bool last = d == 1;
+            char *pd = data_of(t, partner);
+            for (int c = klo; c < khi; c++) {
+                T *db = last ? SLICE_DST(c) : nullptr;
+                step_reduce<T, OP>(pd + (size_t)c * cap_bytes, mydata + (size_t)c * cap_bytes, j0, SLICE_JEND(c), last, inv_n, db, pl.cnt[c], db && ((uintptr_t)db & 15) == 0);
+            }
+            lo = klo; hi = khi;
+            bs.barrier(t, ++phase);
+        }
+        /* ---- ... recursive doubling (allgather) ---- */
+        if (allred) for (int d = 1; d < N; d <<= 1) {
+            const int partner = me ^ d, span = hi - lo;
+            const int plo = (me & d) ? lo - span : hi; /* the partner's complete range sits next to mine */
+            char *pd = data_of(t, partner);
+            for (int c = plo; c < plo + span; c++) {
+                T *db = SLICE_DST(c);
+                step_copy<T>(pd + (size_t)c * cap_bytes, mydata + (size_t)c * cap_bytes, j0, SLICE_JEND(c), (d << 1) < N, db, pl.cnt[c], ((uintptr_t)db & 15) == 0);
+            }
+            if (me & d) lo -= span; else hi += span;
+            bs.barrier(t, ++phase);
+        }
+    }
+#undef SLICE_JEND
+#undef SLICE_DST
+}
+
+template <typename T> __global__ void __launch_bounds__(NVL_THREADS_MAX, 2) nvl_reduce_steps_kernel(nvl_red_args_t a)
+{
+    BlockSync bs; bs.init(a.team);
+    SlicePlan pl; make_plan<T>(a, pl);
+    uint32_t phase = 0;
+#define CALL_STEPS(_T, _OP) steps_body<_T, _OP>(a, bs, pl, phase)
+    NVL_DISPATCH_OP(T, a.op, CALL_STEPS);
+    bs.finish(phase);
+}
+
 /* one translation unit per datatype defines these launchers */
 #define NVL_INSTANTIATE_REDUCE(_T, _suffix)                                                                              \
     extern "C" cudaError_t nvl_launch_oneshot_##_suffix(const nvl_red_args_t *a, int nblocks, int nthreads, cudaStream_t s) \
@@ -355,5 +501,7 @@ template <typename T> __global__ void __launch_bounds__(NVL_THREADS_MAX, 2) nvl_
     extern "C" cudaError_t nvl_launch_staged_##_suffix(const nvl_red_args_t *a, int nblocks, int nthreads, cudaStream_t s)  \
     { nvl_reduce_staged_kernel<_T><<<nblocks, nthreads, 0, s>>>(*a); return cudaGetLastError(); }                      \
     extern "C" cudaError_t nvl_launch_direct_##_suffix(const nvl_red_args_t *a, int nblocks, int nthreads, cudaStream_t s)  \
-    { nvl_reduce_direct_kernel<_T><<<nblocks, nthreads, 0, s>>>(*a); return cudaGetLastError(); }
+    { nvl_reduce_direct_kernel<_T><<<nblocks, nthreads, 0, s>>>(*a); return cudaGetLastError(); }                      \
+    extern "C" cudaError_t nvl_launch_steps_##_suffix(const nvl_red_args_t *a, int nblocks, int nthreads, cudaStream_t s)   \
+    { nvl_reduce_steps_kernel<_T><<<nblocks, nthreads, 0, s>>>(*a); return cudaGetLastError(); }
 #endif

@@ -43,6 +43,7 @@ static ucc_status_t nvl_launch(ucc_tl_nvl_task_t *t, cudaStream_t s)
         if (t->u.red.direct == NVL_DIRECT_FULL) e = nvl_launch_reduce_direct(&t->u.red, t->nblocks_direct, t->nthreads, s);
         else e = nvl_launch_reduce_staged(&t->u.red, t->nblocks, t->nthreads, s);
         break;
+    case NVL_TASK_REDUCE_STEPS: e = nvl_launch_reduce_steps(&t->u.red, t->nblocks, t->nthreads, s); break;
     case NVL_TASK_XCHG: e = nvl_launch_exchange(&t->u.xchg, t->nblocks, t->nthreads, s); break;
     default: e = nvl_launch_barrier(&t->team->dev, s); break;
     }
@@ -227,7 +228,7 @@ static int pick_blocks(ucc_tl_nvl_context_t *ctx, size_t bytes, size_t bytes_per
 /* ------------------------------------------------------------------ */
 /* reduce family                                                       */
 /* ------------------------------------------------------------------ */
-typedef enum { RED_ALG_ONESHOT, RED_ALG_TWOSHOT, RED_ALG_NVLS } red_alg_t;
+typedef enum { RED_ALG_ONESHOT, RED_ALG_TWOSHOT, RED_ALG_NVLS, RED_ALG_RING, RED_ALG_RHD } red_alg_t;
 
 static ucc_status_t red_init(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, ucc_coll_task_t **task_p, red_alg_t alg)
 {
@@ -266,6 +267,14 @@ static ucc_status_t red_init(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, u
     bytes = count * ucc_dt_size(dt);
     if (alg == RED_ALG_ONESHOT && (a->coll_type != UCC_COLL_TYPE_ALLREDUCE || bytes > NVL_LL_MAX)) return UCC_ERR_NOT_SUPPORTED;
     if (alg == RED_ALG_NVLS && (!team->nvls || !nvl_nvls_supports(ndt, nop))) return UCC_ERR_NOT_SUPPORTED;
+    if (alg == RED_ALG_RING || alg == RED_ALG_RHD) {
+        /* step-structured kernels: allreduce / reduce_scatter(v) whose slices fit one heap round; rhd pairs ranks by xor */
+        size_t slice_cap = (ctx->cfg.symmetric_size / N / 16) * 16, need;
+        if (a->coll_type == UCC_COLL_TYPE_REDUCE || (alg == RED_ALG_RHD && !ucc_is_pow2(N))) return UCC_ERR_NOT_SUPPORTED;
+        if (a->coll_type == UCC_COLL_TYPE_REDUCE_SCATTERV) { need = 0; for (ucc_rank_t i = 0; i < N; i++) need = ucc_max(need, ucc_coll_args_get_count(a, a->dst.info_v.counts, i) * ucc_dt_size(dt)); }
+        else need = ucc_div_round_up(count, N) * ucc_dt_size(dt);
+        if (ucc_align_up(need, 16) > slice_cap) return UCC_ERR_NOT_SUPPORTED;
+    }
     st = task_alloc(b, b_team, &t);
     if (st != UCC_OK) return st;
     r = &t->u.red;
@@ -286,10 +295,11 @@ static ucc_status_t red_init(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, u
         break;
     }
     if (alg == RED_ALG_ONESHOT) { t->kind = NVL_TASK_REDUCE_ONESHOT; t->nblocks = pick_blocks(ctx, bytes, 16384); if (t->nblocks > 64) t->nblocks = 64; }
+    else if (alg == RED_ALG_RING || alg == RED_ALG_RHD) { t->kind = NVL_TASK_REDUCE_STEPS; r->sched = alg == RED_ALG_RING ? 1 : 2; t->nblocks = pick_blocks(ctx, bytes, 64 * 1024); }
     else { t->kind = NVL_TASK_REDUCE_STAGED; t->nblocks = pick_blocks(ctx, bytes, 32 * 1024); }
     /* zero-copy: every criterion below is evaluated identically on all ranks (sizes / counts are collective
      * arguments); what only the owner knows (can the buffer be exported? is it aligned?) travels with the exchange */
-    if (alg != RED_ALG_ONESHOT && team->zcopy && ctx->cfg.zcopy != UCC_NO && bytes >= ctx->cfg.zcopy_thresh) {
+    if ((alg == RED_ALG_TWOSHOT || alg == RED_ALG_NVLS) && team->zcopy && ctx->cfg.zcopy != UCC_NO && bytes >= ctx->cfg.zcopy_thresh) {
         int mode = alg == RED_ALG_NVLS ? (r->kind == NVL_RED_REDUCE_SCATTER ? NVL_DIRECT_NONE : NVL_DIRECT_DST) : NVL_DIRECT_FULL;
         if (mode == NVL_DIRECT_FULL && r->kind == NVL_RED_REDUCE_SCATTER)
             for (ucc_rank_t i = 0; i < N; i++) if ((r->rs_offset[i] * ucc_dt_size(dt)) & 15) mode = NVL_DIRECT_NONE;
@@ -306,6 +316,8 @@ static ucc_status_t red_init(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, u
 static ucc_status_t red_init_oneshot(ucc_base_coll_args_t *b, ucc_base_team_t *t, ucc_coll_task_t **p) { return red_init(b, t, p, RED_ALG_ONESHOT); }
 static ucc_status_t red_init_twoshot(ucc_base_coll_args_t *b, ucc_base_team_t *t, ucc_coll_task_t **p) { return red_init(b, t, p, RED_ALG_TWOSHOT); }
 static ucc_status_t red_init_nvls(ucc_base_coll_args_t *b, ucc_base_team_t *t, ucc_coll_task_t **p) { return red_init(b, t, p, RED_ALG_NVLS); }
+static ucc_status_t red_init_ring(ucc_base_coll_args_t *b, ucc_base_team_t *t, ucc_coll_task_t **p) { return red_init(b, t, p, RED_ALG_RING); }
+static ucc_status_t red_init_rhd(ucc_base_coll_args_t *b, ucc_base_team_t *t, ucc_coll_task_t **p) { return red_init(b, t, p, RED_ALG_RHD); }
 
 /* ------------------------------------------------------------------ */
 /* data movement family                                                */
@@ -419,6 +431,49 @@ static ucc_status_t xchg_init(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, 
     return UCC_OK;
 }
 
+/* allgather(v) / bcast through the switch: every rank multicasts its block once (multimem.st), everybody then
+ * copies out of its OWN heap.  Same bytes into every GPU as the pull variant, 1/(N-1) of the bytes out. */
+static ucc_status_t xchg_init_nvls(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, ucc_coll_task_t **task_p)
+{
+    ucc_tl_nvl_team_t *team = ucc_derived_of(b_team, ucc_tl_nvl_team_t);
+    ucc_tl_nvl_context_t *ctx = NVL_CTX(team);
+    ucc_rank_t N = UCC_TL_TEAM_SIZE(team), me = UCC_TL_TEAM_RANK(team);
+    ucc_coll_type_t ct = b->args.coll_type;
+    size_t cap = ctx->cfg.symmetric_size > NVL_XCHG_TABLE_BYTES ? ctx->cfg.symmetric_size - NVL_XCHG_TABLE_BYTES : 0, off = 0;
+    ucc_tl_nvl_task_t *t;
+    nvl_xchg_args_t *x;
+    ucc_status_t st;
+    if (!team->nvls || (ct != UCC_COLL_TYPE_ALLGATHER && ct != UCC_COLL_TYPE_ALLGATHERV && ct != UCC_COLL_TYPE_BCAST)) return UCC_ERR_NOT_SUPPORTED;
+    st = xchg_init(b, b_team, task_p);
+    if (st != UCC_OK) return st;
+    t = ucc_derived_of(*task_p, ucc_tl_nvl_task_t); x = &t->u.xchg;
+    t->want_direct = 0;
+    if (ct == UCC_COLL_TYPE_BCAST) { x->push_off = 0; off = x->src_bytes; }
+    else for (ucc_rank_t p = 0; p < N; p++) { if (p == me) x->push_off = off; x->pull_off[p] = off; off += ucc_align_up(x->pull_bytes[p] ? x->pull_bytes[p] : (p == me ? x->src_bytes : 0), 16); }
+    /* NOTE for allgatherv every rank knows all counts, so `off` (and the decisions below) agree everywhere */
+    if (off > cap) { (*task_p)->finalize(*task_p); *task_p = NULL; return UCC_ERR_NOT_SUPPORTED; }
+    x->use_mc = 1;
+    return UCC_OK;
+}
+/* ring allgather(v): same heap layout as the nvls variant, N-1 neighbour-to-neighbour steps inside one kernel */
+static ucc_status_t xchg_init_ring(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, ucc_coll_task_t **task_p)
+{
+    ucc_tl_nvl_team_t *team = ucc_derived_of(b_team, ucc_tl_nvl_team_t);
+    ucc_tl_nvl_context_t *ctx = NVL_CTX(team);
+    ucc_rank_t N = UCC_TL_TEAM_SIZE(team);
+    size_t cap = ctx->cfg.symmetric_size > NVL_XCHG_TABLE_BYTES ? ctx->cfg.symmetric_size - NVL_XCHG_TABLE_BYTES : 0, off = 0;
+    ucc_tl_nvl_task_t *t; nvl_xchg_args_t *x; ucc_status_t st;
+    if (b->args.coll_type != UCC_COLL_TYPE_ALLGATHER && b->args.coll_type != UCC_COLL_TYPE_ALLGATHERV) return UCC_ERR_NOT_SUPPORTED;
+    st = xchg_init(b, b_team, task_p);
+    if (st != UCC_OK) return st;
+    t = ucc_derived_of(*task_p, ucc_tl_nvl_task_t); x = &t->u.xchg;
+    t->want_direct = 0;
+    for (ucc_rank_t p = 0; p < N; p++) { x->pull_off[p] = off; off += ucc_align_up(x->pull_bytes[p], 16); }
+    if (off > cap) { (*task_p)->finalize(*task_p); *task_p = NULL; return UCC_ERR_NOT_SUPPORTED; }
+    x->ring = 1;
+    return UCC_OK;
+}
+
 static ucc_status_t barrier_init(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, ucc_coll_task_t **task_p)
 {
     ucc_tl_nvl_task_t *t;
@@ -436,22 +491,34 @@ typedef struct nvl_alg { const char *name; const char *desc; ucc_base_coll_init_
 static const nvl_alg_t algs_allreduce[] = {
     {"twoshot", "stage + pull-reduce own slice over NVLink + push result to every peer, one kernel", red_init_twoshot},
     {"oneshot", "push the whole vector to every peer and reduce locally (latency path, <= 64K)", red_init_oneshot},
-    {"nvls", "stage + multimem.ld_reduce / multimem.st through the NVSwitch (in-switch reduction)", red_init_nvls}, {NULL}};
+    {"nvls", "stage + multimem.ld_reduce / multimem.st through the NVSwitch (in-switch reduction)", red_init_nvls},
+    {"ring", "ring reduce-scatter + ring allgather through the heaps, neighbour links only, one kernel", red_init_ring},
+    {"rhd", "recursive halving + recursive doubling (radix-2 scatter-reduce-allgather), power-of-two teams, one kernel", red_init_rhd}, {NULL}};
+static const nvl_alg_t algs_rs[] = {
+    {"twoshot", "stage + pull-reduce own slice over NVLink", red_init_twoshot},
+    {"nvls", "stage + multimem.ld_reduce own slice in the NVSwitch", red_init_nvls},
+    {"ring", "ring reduce-scatter through the heaps, neighbour links only", red_init_ring},
+    {"rhd", "recursive halving, power-of-two teams", red_init_rhd}, {NULL}};
 static const nvl_alg_t algs_red[] = {
     {"twoshot", "stage + pull-reduce own slice over NVLink", red_init_twoshot},
     {"nvls", "stage + multimem.ld_reduce own slice in the NVSwitch", red_init_nvls}, {NULL}};
 static const nvl_alg_t algs_xchg[] = {{"pull", "stage once, every peer pulls its part over NVLink", xchg_init}, {NULL}};
+static const nvl_alg_t algs_xchg_mc[] = {{"pull", "stage once, every peer pulls its part over NVLink", xchg_init},
+    {"nvls", "multicast the own block into every member's heap with multimem.st, copy out locally", xchg_init_nvls}, {NULL}};
+static const nvl_alg_t algs_ag[] = {{"pull", "stage once, every peer pulls its part over NVLink", xchg_init},
+    {"nvls", "multicast the own block into every member's heap with multimem.st, copy out locally", xchg_init_nvls},
+    {"ring", "N-1 neighbour-to-neighbour pull steps through the heaps, one kernel", xchg_init_ring}, {NULL}};
 static const nvl_alg_t algs_barrier[] = {{"flags", "flag exchange in peer memory", barrier_init}, {NULL}};
 static const nvl_alg_t *const nvl_algs[UCC_COLL_TYPE_NUM] = {
-    algs_xchg, algs_xchg, algs_allreduce, algs_xchg, algs_xchg, algs_barrier, algs_xchg, algs_barrier, algs_barrier,
-    algs_xchg, algs_xchg, algs_red, algs_red, algs_red, algs_xchg, algs_xchg};
-static ucc_base_coll_alg_info_t nvl_alg_info[UCC_COLL_TYPE_NUM][4];
+    algs_ag, algs_ag, algs_allreduce, algs_xchg, algs_xchg, algs_barrier, algs_xchg_mc, algs_barrier, algs_barrier,
+    algs_xchg, algs_xchg, algs_red, algs_rs, algs_rs, algs_xchg, algs_xchg};
+static ucc_base_coll_alg_info_t nvl_alg_info[UCC_COLL_TYPE_NUM][8];
 
 void ucc_tl_nvl_register_alg_info(void)
 {
     for (int c = 0; c < UCC_COLL_TYPE_NUM; c++) {
         int i;
-        for (i = 0; nvl_algs[c][i].name && i < 3; i++) { nvl_alg_info[c][i].id = (unsigned)i; nvl_alg_info[c][i].name = nvl_algs[c][i].name; nvl_alg_info[c][i].desc = nvl_algs[c][i].desc; }
+        for (i = 0; nvl_algs[c][i].name && i < 7; i++) { nvl_alg_info[c][i].id = (unsigned)i; nvl_alg_info[c][i].name = nvl_algs[c][i].name; nvl_alg_info[c][i].desc = nvl_algs[c][i].desc; }
         nvl_alg_info[c][i].name = NULL;
         ucc_tl_nvl.alg_info[c] = nvl_alg_info[c];
     }

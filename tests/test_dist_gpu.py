@@ -64,3 +64,18 @@ def test_parallel_helpers_cuda():
            "--master-port", "29790", os.path.join(ROOT, "tests", "parallel_worker.py"), "cuda"]
     out = subprocess.run(cmd, env=dict(os.environ, PYTHONPATH=ROOT), capture_output=True, text=True, timeout=900)
     assert "PARALLEL_WORKER_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+
+
+def test_multiproc_nvls_everything():
+    """NVLS variants forced: in-switch allreduce / reduce_scatter (float and integer), multicast allgather / bcast."""
+    n = torch.cuda.device_count() if torch.cuda.is_available() else 0
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    _run(n, {"UCC_TL_NVL_TUNE": "allreduce:cuda:inf:@nvls#reduce_scatter:cuda:inf:@nvls#allgather:cuda:inf:@nvls#bcast:cuda:inf:@nvls", "UCC_TL_NVL_ALLREDUCE_ONESHOT_THRESH": "0"})
+
+
+def test_multiproc_ring_rhd():
+    n = torch.cuda.device_count() if torch.cuda.is_available() else 0
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    _run(n, {"UCC_TL_NVL_TUNE": "allreduce:cuda:inf:@ring#reduce_scatter:cuda:inf:@rhd#allgather:cuda:inf:@ring", "UCC_TL_NVL_ZCOPY": "n"})

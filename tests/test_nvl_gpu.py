@@ -275,3 +275,80 @@ def test_bcast_gather_scatter_barrier(job, n):
         for r in range(n):
             assert torch.equal(out[r], big[r * 100:(r + 1) * 100])
     run(team, [coll_args("barrier") for _ in range(n)])
+
+
+# ---------------------------------------------------------------- step-structured algorithms (ring, recursive halving/doubling)
+@pytest.fixture(scope="module", params=["ring", "rhd"])
+def steps_job(request):
+    need_cuda()
+    alg = request.param
+    tune = f"allreduce:cuda:inf:@{alg}#reduce_scatter:cuda:inf:@{alg}#reduce_scatterv:cuda:inf:@{alg}#allgather:cuda:inf:@ring#allgatherv:cuda:inf:@ring"
+    j = UccJob(8, env=dict(ENV, UCC_TL_NVL_TUNE=tune, **NOZC))
+    teams = {n: j.create_team(range(n)) for n in (2, 3, 4, 8)}
+    yield alg, teams
+    j.cleanup()
+
+
+@pytest.mark.parametrize("n", [2, 3, 4, 8])
+@pytest.mark.parametrize("count", [1, 7, 4097, 100003])
+def test_steps_allreduce(steps_job, n, count):
+    alg, teams = steps_job
+    team = teams[n]
+    for dt, op in (("float32", "sum"), ("bfloat16", "avg"), ("int32", "max")):
+        src = [gen(dt, count, 31 * r + 1) for r in range(n)]
+        dst = [torch.zeros(count, dtype=TDT[dt], device="cuda") for _ in range(n)]
+        run(team, [cargs("allreduce", src[r], dst[r], dt, op=op) for r in range(n)])
+        exp = ref_reduce(op, src)
+        for r in range(n):
+            assert_close(dst[r], exp, dt)
+    # in place
+    bufs = [gen("float32", count, r) for r in range(n)]
+    exp = ref_reduce("sum", bufs)
+    run(team, [cargs("allreduce", None, bufs[r], "float32", inplace=True) for r in range(n)])
+    for r in range(n):
+        assert_close(bufs[r], exp, "float32")
+
+
+@pytest.mark.parametrize("n", [2, 4, 8, 3])
+def test_steps_reduce_scatter(steps_job, n):
+    alg, teams = steps_job
+    team = teams[n]
+    blk = 1001
+    src = [gen("float32", blk * n, r) for r in range(n)]
+    dst = [torch.zeros(blk, device="cuda") for _ in range(n)]
+    run(team, [cargs("reduce_scatter", src[r], dst[r], "float32") for r in range(n)])
+    exp = ref_reduce("sum", src)
+    for r in range(n):
+        assert_close(dst[r], exp[r * blk:(r + 1) * blk], "float32")
+    counts = [100 + 33 * r for r in range(n)]
+    tot = sum(counts)
+    src = [gen("float32", tot, 5 + r) for r in range(n)]
+    dst = [torch.zeros(counts[r], device="cuda") for r in range(n)]
+    offs = np.concatenate([[0], np.cumsum(counts)[:-1]])
+    run(team, [cargs("reduce_scatterv", src[r], dst[r], "float32", dst_counts=counts, dst_displs=offs) for r in range(n)])
+    exp = ref_reduce("sum", src)
+    off = 0
+    for r in range(n):
+        assert_close(dst[r], exp[off:off + counts[r]], "float32")
+        off += counts[r]
+
+
+@pytest.mark.parametrize("n", [2, 3, 8])
+@pytest.mark.parametrize("count", [1, 1000, 100001])
+def test_ring_allgather(steps_job, n, count):
+    alg, teams = steps_job
+    team = teams[n]
+    for dt in ("float32", "int8"):
+        src = [gen(dt, count, 11 * r) for r in range(n)]
+        dst = [torch.zeros(count * n, dtype=TDT[dt], device="cuda") for _ in range(n)]
+        run(team, [cargs("allgather", src[r], dst[r], dt) for r in range(n)])
+        exp = torch.cat(src)
+        for r in range(n):
+            assert torch.equal(dst[r], exp), (dt, r)
+    counts = [count + 3 * r for r in range(n)]
+    displs = np.concatenate([[0], np.cumsum(counts)[:-1]])
+    src = [gen("int32", counts[r], r) for r in range(n)]
+    dst = [torch.zeros(sum(counts), dtype=torch.int32, device="cuda") for _ in range(n)]
+    run(team, [cargs("allgatherv", src[r], dst[r], "int32", dst_counts=counts, dst_displs=displs) for r in range(n)])
+    for r in range(n):
+        assert torch.equal(dst[r], torch.cat(src)), r
