@@ -112,7 +112,9 @@ static __device__ void exchange_ring(const nvl_xchg_args_t &a, BlockSync &bs)
     bs.finish((uint32_t)N);
 }
 
-__global__ void __launch_bounds__(NVL_THREADS_MAX) nvl_exchange_kernel(nvl_xchg_args_t a)
+/* 2 CTAs per SM like the reduce kernels: wait_all_blocks() needs every block of every rank resident, and the host caps
+ * the grid at 2 x SM count */
+__global__ void __launch_bounds__(NVL_THREADS_MAX, 2) nvl_exchange_kernel(nvl_xchg_args_t a)
 {
     const nvl_team_dev_t &t = a.team;
     const int N = t.size, me = t.rank;

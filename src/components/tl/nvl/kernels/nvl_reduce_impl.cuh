@@ -243,9 +243,9 @@ static __device__ __forceinline__ void staged_body(const nvl_red_args_t &a, Bloc
                 else { dout.p[0] = a.d.dst[a.root] + eo; dout.n = 1; }
             }
             if (nvls) reduce_nvls<T, OP, 8>(a, base, j0, jend, db, rc, dal, inv_n, dout);
-            else if (N <= 2) reduce_p2p<T, OP, 2, 8>(a, pd, base, j0, jend, db, rc, dal, inv_n, dout);
-            else if (N <= 4) reduce_p2p<T, OP, 4, 4>(a, pd, base, j0, jend, db, rc, dal, inv_n, dout);
-            else if (N <= 8) reduce_p2p<T, OP, 8, 2>(a, pd, base, j0, jend, db, rc, dal, inv_n, dout);
+            else if (N <= 2) reduce_p2p<T, OP, 2, 4>(a, pd, base, j0, jend, db, rc, dal, inv_n, dout);
+            else if (N <= 4) reduce_p2p<T, OP, 4, 2>(a, pd, base, j0, jend, db, rc, dal, inv_n, dout);
+            else if (N <= 8) reduce_p2p<T, OP, 8, 1>(a, pd, base, j0, jend, db, rc, dal, inv_n, dout);
             else reduce_p2p<T, OP, NVL_MAX_PEERS, 1>(a, pd, base, j0, jend, db, rc, dal, inv_n, dout);
         }
         bs.barrier(t, 2 * k + 2);
@@ -288,9 +288,20 @@ template <typename T> __global__ void __launch_bounds__(NVL_THREADS_MAX, 2) nvl_
 /*   touched only for the payload itself.                              */
 /* ------------------------------------------------------------------ */
 template <typename T, int OP, int NP, int U>
-static __device__ __forceinline__ void direct_p2p(int N, const char *const *sp, const DOut &dout, size_t j0, size_t jend, float inv_n)
+static __device__ __forceinline__ void direct_p2p(const nvl_red_args_t &a, size_t so, size_t j0, size_t jend, float inv_n)
 {
     const size_t nt = blockDim.x;
+    const int N = a.team.size, me = a.team.rank;
+    /* pointer tables with compile-time indices only, so they live in registers (a runtime-indexed copy would sit in local memory) */
+    const char *sp[NP]; char *dp[NP]; int nd = 0;
+#pragma unroll
+    for (int i = 0; i < NP; i++) {
+        int p = me + i; if (p >= N) p -= N;
+        sp[i] = i < N ? a.d.src[p] + so : nullptr;
+        dp[i] = (i < N && a.kind == NVL_RED_ALLREDUCE) ? a.d.dst[p] + so : nullptr;
+    }
+    if (a.kind == NVL_RED_ALLREDUCE) nd = N;
+    else { dp[0] = a.kind == NVL_RED_REDUCE ? a.d.dst[a.root] + so : static_cast<char *>(a.dst); nd = 1; }
     for (size_t j = j0 + threadIdx.x; j < jend; j += U * nt) {
         uint4 x[U][NP];
 #pragma unroll
@@ -310,13 +321,13 @@ static __device__ __forceinline__ void direct_p2p(int N, const char *const *sp, 
                 for (int i = 1; i < NP; i++) if (i < N) acc.add(x[u][i]);
                 const uint4 r = acc.get(inv_n);
 #pragma unroll
-                for (int i = 0; i < NP; i++) if (i < dout.n) st_v4(dout.p[i] + jj * 16, r);
+                for (int i = 0; i < NP; i++) if (i < nd) st_v4(dp[i] + jj * 16, r);
             }
         }
     }
 }
 
-template <typename T, int OP>
+template <typename T, int OP, int NP, int U>
 static __device__ __forceinline__ void direct_body(const nvl_red_args_t &a, const SlicePlan &pl)
 {
     constexpr int E = 16 / sizeof(T);
@@ -326,18 +337,16 @@ static __device__ __forceinline__ void direct_body(const nvl_red_args_t &a, cons
     const size_t j0 = dmin((size_t)b * per, nfull), j1 = dmin(j0 + per, nfull);
     const size_t so = pl.off[me] * sizeof(T);
     const float inv_n = 1.0f / (float)N;
-    const char *sp[NVL_MAX_PEERS]; DOut dout;
-#pragma unroll
-    for (int i = 0; i < NVL_MAX_PEERS; i++) { int p = me + i; if (p >= N) p -= N; sp[i] = i < N ? a.d.src[p] + so : nullptr; }
-    if (a.kind == NVL_RED_ALLREDUCE) { for (int i = 0; i < N; i++) { int p = me + i; if (p >= N) p -= N; dout.p[i] = a.d.dst[p] + so; } dout.n = N; }
-    else if (a.kind == NVL_RED_REDUCE) { dout.p[0] = a.d.dst[a.root] + so; dout.n = 1; }
-    else { dout.p[0] = static_cast<char *>(a.dst); dout.n = 1; } /* reduce_scatter(v): my block, already a local pointer */
-    if (N <= 2) direct_p2p<T, OP, 2, 8>(N, sp, dout, j0, j1, inv_n);
-    else if (N <= 4) direct_p2p<T, OP, 4, 4>(N, sp, dout, j0, j1, inv_n);
-    else if (N <= 8) direct_p2p<T, OP, 8, 2>(N, sp, dout, j0, j1, inv_n);
-    else direct_p2p<T, OP, NVL_MAX_PEERS, 1>(N, sp, dout, j0, j1, inv_n);
+    /* in flight per thread: U x NP 16-byte loads; 2 CTAs x 512 threads per SM keep > 64 KB outstanding per SM, far above
+     * the NVLink bandwidth-delay product, and U x NP x 4 registers stay within the 64-register budget */
+    direct_p2p<T, OP, NP, U>(a, so, j0, j1, inv_n); /* NP (team size class) is a kernel template parameter: each class gets its own register allocation */
     /* ragged tail of the slice (fewer than E elements): one thread, element by element */
     if (b == nb - 1 && threadIdx.x == 0 && nfull * E < cnt) {
+        const char *sp[NVL_MAX_PEERS]; DOut dout;
+        for (int i = 0; i < N; i++) { int p = me + i; if (p >= N) p -= N; sp[i] = a.d.src[p] + so; }
+        if (a.kind == NVL_RED_ALLREDUCE) { for (int i = 0; i < N; i++) { int p = me + i; if (p >= N) p -= N; dout.p[i] = a.d.dst[p] + so; } dout.n = N; }
+        else if (a.kind == NVL_RED_REDUCE) { dout.p[0] = a.d.dst[a.root] + so; dout.n = 1; }
+        else { dout.p[0] = static_cast<char *>(a.dst); dout.n = 1; } /* reduce_scatter(v): my block, already a local pointer */
         for (size_t e = nfull * E; e < cnt; e++) {
             typename AccOf<T>::type acc = to_acc<T>(reinterpret_cast<const T *>(sp[0])[e]);
             for (int i = 1; i < N; i++) acc = OpFn<OP, typename AccOf<T>::type>::f(acc, to_acc<T>(reinterpret_cast<const T *>(sp[i])[e]));
@@ -347,12 +356,12 @@ static __device__ __forceinline__ void direct_body(const nvl_red_args_t &a, cons
     }
 }
 
-template <typename T> __global__ void __launch_bounds__(NVL_THREADS_MAX, 2) nvl_reduce_direct_kernel(nvl_red_args_t a)
+template <typename T, int NP, int U> __global__ void __launch_bounds__(NVL_THREADS_MAX, 2) nvl_reduce_direct_kernel(nvl_red_args_t a)
 {
     BlockSync bs; bs.init(a.team);
     SlicePlan pl; make_plan<T>(a, pl);
     bs.barrier(a.team, 1);
-#define CALL_DIRECT(_T, _OP) direct_body<_T, _OP>(a, pl)
+#define CALL_DIRECT(_T, _OP) direct_body<_T, _OP, NP, U>(a, pl)
     NVL_DISPATCH_OP(T, a.op, CALL_DIRECT);
     bs.barrier(a.team, 2);
     bs.finish(2);
@@ -501,7 +510,11 @@ template <typename T> __global__ void __launch_bounds__(NVL_THREADS_MAX, 2) nvl_
     extern "C" cudaError_t nvl_launch_staged_##_suffix(const nvl_red_args_t *a, int nblocks, int nthreads, cudaStream_t s)  \
     { nvl_reduce_staged_kernel<_T><<<nblocks, nthreads, 0, s>>>(*a); return cudaGetLastError(); }                      \
     extern "C" cudaError_t nvl_launch_direct_##_suffix(const nvl_red_args_t *a, int nblocks, int nthreads, cudaStream_t s)  \
-    { nvl_reduce_direct_kernel<_T><<<nblocks, nthreads, 0, s>>>(*a); return cudaGetLastError(); }                      \
+    { if (a->team.size <= 2) nvl_reduce_direct_kernel<_T, 2, 4><<<nblocks, nthreads, 0, s>>>(*a);                       \
+      else if (a->team.size <= 4) nvl_reduce_direct_kernel<_T, 4, 2><<<nblocks, nthreads, 0, s>>>(*a);                  \
+      else if (a->team.size <= 8) nvl_reduce_direct_kernel<_T, 8, 1><<<nblocks, nthreads, 0, s>>>(*a);                  \
+      else nvl_reduce_direct_kernel<_T, NVL_MAX_PEERS, 1><<<nblocks, nthreads, 0, s>>>(*a);                             \
+      return cudaGetLastError(); }                                                                                     \
     extern "C" cudaError_t nvl_launch_steps_##_suffix(const nvl_red_args_t *a, int nblocks, int nthreads, cudaStream_t s)   \
     { nvl_reduce_steps_kernel<_T><<<nblocks, nthreads, 0, s>>>(*a); return cudaGetLastError(); }
 #endif

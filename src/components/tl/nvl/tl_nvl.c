@@ -73,6 +73,8 @@ static ucc_status_t nvl_ctx_create(const ucc_base_context_params_t *p, const ucc
     if (ctx->cfg.use_nvls == UCC_NO || !ctx->addr.vmm_ok) ctx->addr.mc_ok = 0;
     if (ctx->cfg.oneshot_thresh > NVL_LL_MAX) ctx->cfg.oneshot_thresh = NVL_LL_MAX;
     if (ctx->cfg.max_blocks > NVL_MAX_BLOCKS) ctx->cfg.max_blocks = NVL_MAX_BLOCKS;
+    /* every block of a collective kernel must be resident at once (they wait for each other): 2 CTAs of 512 threads per SM */
+    if (ctx->sm_count > 0 && ctx->cfg.max_blocks > 2u * (unsigned)ctx->sm_count) ctx->cfg.max_blocks = 2u * (unsigned)ctx->sm_count;
     if (ctx->cfg.max_blocks < 1) ctx->cfg.max_blocks = 1;
     if (ctx->cfg.nthreads < 64) ctx->cfg.nthreads = 64;
     if (ctx->cfg.nthreads > 1024) ctx->cfg.nthreads = 1024;
