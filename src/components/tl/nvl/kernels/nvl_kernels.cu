@@ -237,6 +237,15 @@ extern "C" cudaError_t nvl_launch_exchange(const nvl_xchg_args_t *a, int nblocks
     nvl_exchange_kernel<<<nblocks, nthreads, 0, s>>>(*a);
     return cudaGetLastError();
 }
+/* single-member team: every collective degenerates to (at most) one device copy; this is that copy, at HBM speed */
+__global__ void __launch_bounds__(NVL_THREADS_MAX, 2) nvl_self_copy_kernel(char *dst, const char *src, size_t n)
+{ copy_bytes_grid<false>(dst, src, n); }
+extern "C" cudaError_t nvl_launch_self_copy(void *dst, const void *src, size_t bytes, int nblocks, int nthreads, cudaStream_t s)
+{
+    if (nthreads > NVL_THREADS_MAX) nthreads = NVL_THREADS_MAX;
+    nvl_self_copy_kernel<<<nblocks, nthreads, 0, s>>>(static_cast<char *>(dst), static_cast<const char *>(src), bytes);
+    return cudaGetLastError();
+}
 extern "C" cudaError_t nvl_launch_barrier(const nvl_team_dev_t *t, cudaStream_t s)
 {
     nvl_barrier_kernel<<<1, 32, 0, s>>>(*t);

@@ -117,6 +117,7 @@ cudaError_t  nvl_launch_reduce_direct(const nvl_red_args_t *a, int nblocks, int 
 cudaError_t  nvl_launch_reduce_steps(const nvl_red_args_t *a, int nblocks, int nthreads, cudaStream_t s);
 cudaError_t  nvl_launch_exchange(const nvl_xchg_args_t *a, int nblocks, int nthreads, cudaStream_t s);
 cudaError_t  nvl_launch_barrier(const nvl_team_dev_t *t, cudaStream_t s);
+cudaError_t  nvl_launch_self_copy(void *dst, const void *src, size_t bytes, int nblocks, int nthreads, cudaStream_t s); /* team of one */
 cudaError_t  nvl_launch_ctrl_init(void *heap_base, cudaStream_t s);
 #ifdef __cplusplus
 }

@@ -40,8 +40,8 @@ static ucc_status_t nvl_lib_init(const ucc_base_lib_params_t *p, const ucc_base_
 }
 static void nvl_lib_finalize(ucc_base_lib_t *lib) { free(lib); }
 static ucc_status_t nvl_lib_get_attr(const ucc_base_lib_t *lib, ucc_base_lib_attr_t *attr)
-{ (void)lib; attr->attr.thread_mode = UCC_THREAD_MULTIPLE; attr->attr.coll_types = UCC_TL_NVL_SUPPORTED_COLLS; attr->flags = 0; attr->min_team_size = 2; attr->max_team_size = NVL_MAX_PEERS; return UCC_OK; }
-static ucc_status_t nvl_lib_get_properties(ucc_base_lib_properties_t *p) { p->default_team_size = 2; p->min_team_size = 2; p->max_team_size = NVL_MAX_PEERS; return UCC_OK; }
+{ (void)lib; attr->attr.thread_mode = UCC_THREAD_MULTIPLE; attr->attr.coll_types = UCC_TL_NVL_SUPPORTED_COLLS; attr->flags = 0; attr->min_team_size = 1; attr->max_team_size = NVL_MAX_PEERS; return UCC_OK; }
+static ucc_status_t nvl_lib_get_properties(ucc_base_lib_properties_t *p) { p->default_team_size = 2; p->min_team_size = 1; p->max_team_size = NVL_MAX_PEERS; return UCC_OK; }
 
 static ucc_status_t nvl_ctx_create(const ucc_base_context_params_t *p, const ucc_base_ctx_config_t *config, ucc_base_context_t **ctx_p)
 {

@@ -89,6 +89,7 @@ typedef enum { NVL_TEAM_INIT, NVL_TEAM_XCHG_INFO, NVL_TEAM_MAP, NVL_TEAM_SYNC1, 
 typedef struct ucc_tl_nvl_team {
     ucc_tl_team_t     super;
     nvl_team_state_t  state;
+    int               self;                 /* single-member team: no heap, collectives are local copies */
     ucc_team_oob_coll_t oob;
     int               oob_internal;
     void             *oob_req;
@@ -131,7 +132,8 @@ typedef struct ucc_tl_nvl_team {
     uint32_t          gate_seq;
 } ucc_tl_nvl_team_t;
 
-typedef enum { NVL_TASK_REDUCE_ONESHOT, NVL_TASK_REDUCE_STAGED, NVL_TASK_REDUCE_STEPS, NVL_TASK_XCHG, NVL_TASK_BARRIER } nvl_task_kind_t;
+typedef enum { NVL_TASK_REDUCE_ONESHOT, NVL_TASK_REDUCE_STAGED, NVL_TASK_REDUCE_STEPS, NVL_TASK_XCHG, NVL_TASK_BARRIER,
+               NVL_TASK_SELF_COPY /* team of one: u.xchg.{dst,src,src_bytes} describe the only data movement */ } nvl_task_kind_t;
 typedef enum { NVL_TASK_LAUNCHED, NVL_TASK_QUEUED } nvl_task_state_t;
 typedef struct ucc_tl_nvl_task {
     ucc_coll_task_t     super;

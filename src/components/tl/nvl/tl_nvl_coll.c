@@ -45,6 +45,9 @@ static ucc_status_t nvl_launch(ucc_tl_nvl_task_t *t, cudaStream_t s)
         break;
     case NVL_TASK_REDUCE_STEPS: e = nvl_launch_reduce_steps(&t->u.red, t->nblocks, t->nthreads, s); break;
     case NVL_TASK_XCHG: e = nvl_launch_exchange(&t->u.xchg, t->nblocks, t->nthreads, s); break;
+    case NVL_TASK_SELF_COPY:
+        e = t->u.xchg.src_bytes ? nvl_launch_self_copy(t->u.xchg.dst, t->u.xchg.src, t->u.xchg.src_bytes, t->nblocks, t->nthreads, s) : cudaSuccess;
+        break;
     default: e = nvl_launch_barrier(&t->team->dev, s); break;
     }
     if (e != cudaSuccess) { tl_error(NVL_LIB(t->team), "kernel launch failed: %s", cudaGetErrorString(e)); return UCC_ERR_NO_MESSAGE; }
@@ -226,6 +229,52 @@ static int pick_blocks(ucc_tl_nvl_context_t *ctx, size_t bytes, size_t bytes_per
 }
 
 /* ------------------------------------------------------------------ */
+/* team of one: each collective is at most one local copy (cf. reference tl/self/tl_self_coll.c:49-278, which    */
+/* hands the copy to the EC executor); here it is a copy kernel on the caller's stream                          */
+/* ------------------------------------------------------------------ */
+static ucc_status_t self_init(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, ucc_coll_task_t **task_p)
+{
+    ucc_tl_nvl_team_t *team = ucc_derived_of(b_team, ucc_tl_nvl_team_t);
+    ucc_tl_nvl_context_t *ctx = NVL_CTX(team);
+    ucc_coll_args_t *a = &b->args;
+    const void *src = NULL; void *dst = NULL; size_t bytes = 0;
+    ucc_memory_type_t smt = UCC_MEMORY_TYPE_CUDA, dmt = UCC_MEMORY_TYPE_CUDA;
+    ucc_tl_nvl_task_t *t;
+    ucc_status_t st;
+    if (!UCC_IS_INPLACE(*a)) {
+        switch (a->coll_type) {
+        case UCC_COLL_TYPE_ALLGATHER: case UCC_COLL_TYPE_ALLREDUCE: case UCC_COLL_TYPE_ALLTOALL: case UCC_COLL_TYPE_GATHER: case UCC_COLL_TYPE_REDUCE:
+        case UCC_COLL_TYPE_REDUCE_SCATTER: case UCC_COLL_TYPE_SCATTER:
+            src = a->src.info.buffer; dst = a->dst.info.buffer; bytes = a->dst.info.count * ucc_dt_size(a->dst.info.datatype);
+            smt = a->src.info.mem_type; dmt = a->dst.info.mem_type; break;
+        case UCC_COLL_TYPE_ALLGATHERV: case UCC_COLL_TYPE_GATHERV: case UCC_COLL_TYPE_REDUCE_SCATTERV:
+            src = a->src.info.buffer; bytes = ucc_coll_args_get_count(a, a->dst.info_v.counts, 0) * ucc_dt_size(a->dst.info_v.datatype);
+            dst = PTR_OFFSET(a->dst.info_v.buffer, (a->dst.info_v.displacements ? ucc_coll_args_get_displacement(a, a->dst.info_v.displacements, 0) : 0) * ucc_dt_size(a->dst.info_v.datatype));
+            smt = a->src.info.mem_type; dmt = a->dst.info_v.mem_type; break;
+        case UCC_COLL_TYPE_ALLTOALLV:
+            bytes = ucc_coll_args_get_count(a, a->src.info_v.counts, 0) * ucc_dt_size(a->src.info_v.datatype);
+            src = PTR_OFFSET(a->src.info_v.buffer, ucc_coll_args_get_displacement(a, a->src.info_v.displacements, 0) * ucc_dt_size(a->src.info_v.datatype));
+            dst = PTR_OFFSET(a->dst.info_v.buffer, ucc_coll_args_get_displacement(a, a->dst.info_v.displacements, 0) * ucc_dt_size(a->dst.info_v.datatype));
+            smt = a->src.info_v.mem_type; dmt = a->dst.info_v.mem_type; break;
+        case UCC_COLL_TYPE_SCATTERV:
+            bytes = a->dst.info.count * ucc_dt_size(a->dst.info.datatype); dst = a->dst.info.buffer;
+            src = PTR_OFFSET(a->src.info_v.buffer, (a->src.info_v.displacements ? ucc_coll_args_get_displacement(a, a->src.info_v.displacements, 0) : 0) * ucc_dt_size(a->src.info_v.datatype));
+            smt = a->src.info_v.mem_type; dmt = a->dst.info.mem_type; break;
+        default: break; /* bcast, barrier, fanin, fanout: nothing moves */
+        }
+    }
+    if (bytes && (!is_cuda(smt) || !is_cuda(dmt))) return UCC_ERR_NOT_SUPPORTED;
+    st = task_alloc(b, b_team, &t);
+    if (st != UCC_OK) return st;
+    memset(&t->u.xchg, 0, sizeof(t->u.xchg));
+    t->kind = NVL_TASK_SELF_COPY;
+    t->u.xchg.src = src; t->u.xchg.dst = dst; t->u.xchg.src_bytes = (src && dst && src != dst) ? bytes : 0;
+    t->nblocks = pick_blocks(ctx, bytes, 64 * 1024);
+    *task_p = &t->super;
+    return UCC_OK;
+}
+
+/* ------------------------------------------------------------------ */
 /* reduce family                                                       */
 /* ------------------------------------------------------------------ */
 typedef enum { RED_ALG_ONESHOT, RED_ALG_TWOSHOT, RED_ALG_NVLS, RED_ALG_RING, RED_ALG_RHD } red_alg_t;
@@ -243,6 +292,7 @@ static ucc_status_t red_init(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, u
     const void *src; void *dst; size_t count, bytes;
     int ndt, nop;
     ucc_status_t st;
+    if (team->self) return self_init(b, b_team, task_p);
     switch (a->coll_type) {
     case UCC_COLL_TYPE_ALLREDUCE:
         dt = a->dst.info.datatype; count = a->dst.info.count; dst = a->dst.info.buffer; dmt = a->dst.info.mem_type;
@@ -334,6 +384,7 @@ static ucc_status_t xchg_init(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, 
     ucc_tl_nvl_task_t *t;
     size_t moved = 0, dts;
     ucc_status_t st;
+    if (team->self) return self_init(b, b_team, task_p);
     memset(&x, 0, sizeof(x));
     x.team = team->dev;
     if (UCC_COLL_ARGS_ACTIVE_SET(a)) return UCC_ERR_NOT_SUPPORTED;
@@ -477,7 +528,9 @@ static ucc_status_t xchg_init_ring(ucc_base_coll_args_t *b, ucc_base_team_t *b_t
 static ucc_status_t barrier_init(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, ucc_coll_task_t **task_p)
 {
     ucc_tl_nvl_task_t *t;
-    ucc_status_t st = task_alloc(b, b_team, &t);
+    ucc_status_t st;
+    if (ucc_derived_of(b_team, ucc_tl_nvl_team_t)->self) return self_init(b, b_team, task_p);
+    st = task_alloc(b, b_team, &t);
     if (st != UCC_OK) return st;
     t->kind = NVL_TASK_BARRIER; t->nblocks = 1;
     *task_p = &t->super;
@@ -546,8 +599,10 @@ ucc_status_t ucc_tl_nvl_team_get_scores(ucc_base_team_t *b_team, ucc_coll_score_
     ucc_coll_score_team_info_t info = {UCC_TL_NVL_DEFAULT_SCORE, UCC_TL_TEAM_SIZE(team), UCC_TL_NVL_SUPPORTED_COLLS, mt, 1, ucc_tl_nvl_coll_init, ucc_tl_nvl_alg_id_to_init};
     ucc_coll_score_t *score;
     char sel[512], a[32], n[32];
-    ucc_status_t st = ucc_coll_score_build_default(b_team, UCC_TL_NVL_DEFAULT_SCORE, ucc_tl_nvl_coll_init, UCC_TL_NVL_SUPPORTED_COLLS, mt, 1, &score);
+    /* a team of one outranks tl/self (50) for CUDA buffers: its copy is a stream-ordered kernel instead of a blocking memcpy */
+    ucc_status_t st = ucc_coll_score_build_default(b_team, team->self ? 60 : UCC_TL_NVL_DEFAULT_SCORE, ucc_tl_nvl_coll_init, UCC_TL_NVL_SUPPORTED_COLLS, mt, 1, &score);
     if (st != UCC_OK) return st;
+    if (team->self) { info.default_score = 60; st = ucc_tl_apply_tune(&team->super, score, &info, NULL, ctx->cfg.super.super.score_str); if (st != UCC_OK) { ucc_coll_score_free(score); return st; } *score_p = score; return UCC_OK; }
     snprintf(a, sizeof(a), "%zu", ctx->cfg.oneshot_thresh + 1); /* ranges are end-exclusive, the threshold itself is still one-shot */
     ucc_memunits_to_str(ucc_max(ctx->cfg.nvls_thresh, ctx->cfg.oneshot_thresh + 1), n, sizeof(n));
     /* message-size driven defaults: latency kernel below the threshold, in-switch reduction for big

@@ -156,6 +156,7 @@ static void team_release(ucc_tl_nvl_team_t *team)
 /* ------------------------------------------------------------------ */
 /* create                                                              */
 /* ------------------------------------------------------------------ */
+static ucc_status_t team_finish(ucc_tl_nvl_team_t *team);
 ucc_status_t ucc_tl_nvl_team_create_post(ucc_base_context_t *b_ctx, const ucc_base_team_params_t *params, ucc_base_team_t **team_p)
 {
     ucc_tl_nvl_context_t *ctx = ucc_derived_of(b_ctx, ucc_tl_nvl_context_t);
@@ -164,12 +165,19 @@ ucc_status_t ucc_tl_nvl_team_create_post(ucc_base_context_t *b_ctx, const ucc_ba
     int same_pid = 1, all_vmm = 1, all_mc = 1, distinct_dev = 1, want_mc, dev;
     int devs[NVL_MAX_PEERS];
     ucc_status_t st;
-    if (N < 2 || N > NVL_MAX_PEERS) return UCC_ERR_NOT_SUPPORTED;
+    if (N < 1 || N > NVL_MAX_PEERS) return UCC_ERR_NOT_SUPPORTED;
     if (cudaGetDevice(&dev) != cudaSuccess || dev != ctx->dev) { (void)cudaGetLastError(); tl_debug(b_ctx->lib, "current device differs from the context's device"); return UCC_ERR_NOT_SUPPORTED; }
     team = (ucc_tl_nvl_team_t *)calloc(1, sizeof(*team));
     if (!team) return UCC_ERR_NO_MEMORY;
     team->super.super.context = b_ctx; team->super.super.params = *params;
     team->heap_fd = -1; team->mc_fd = -1; team->srv_sock = -1;
+    if (N == 1) { /* nothing to share: collectives on CUDA buffers become one copy kernel on the caller's stream */
+        team->self = 1; team->heap_kind = NVL_HEAP_LOCAL;
+        st = team_finish(team);
+        if (st != UCC_OK) { team_release(team); free(team); return st; }
+        *team_p = &team->super.super;
+        return UCC_OK;
+    }
     for (ucc_rank_t r = 0; r < N; r++) {
         uint32_t len = 0;
         ucc_tl_nvl_addr_t *a = (ucc_tl_nvl_addr_t *)ucc_get_team_ep_addr(b_ctx->ucc_context, params->team, ucc_ep_map_eval(params->map, r), ucc_tl_nvl.super.id, &len);

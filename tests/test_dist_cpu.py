@@ -27,3 +27,14 @@ def test_parallel_helpers_host(n):
     env = dict(os.environ, PYTHONPATH=ROOT, CUDA_VISIBLE_DEVICES="")
     out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert "PARALLEL_WORKER_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
+
+
+@pytest.mark.parametrize("n", [2, 3])
+def test_torch_backend_host(n):
+    """torch.distributed backend "ucc_b200" (the ProcessGroupUCC role): c10d collectives + torch DDP on host tensors."""
+    port = 29670 + n
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tests", "pg_worker.py"), "cpu"]
+    env = dict(os.environ, PYTHONPATH=ROOT, CUDA_VISIBLE_DEVICES="")
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert "PG_WORKER_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]

@@ -79,3 +79,14 @@ def test_multiproc_ring_rhd():
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
     _run(n, {"UCC_TL_NVL_TUNE": "allreduce:cuda:inf:@ring#reduce_scatter:cuda:inf:@rhd#allgather:cuda:inf:@ring", "UCC_TL_NVL_ZCOPY": "n"})
+
+
+def test_torch_backend_cuda():
+    """init_process_group("ucc_b200"): c10d collectives and torch DDP on CUDA tensors run on the tl/nvl kernels."""
+    n = torch.cuda.device_count() if torch.cuda.is_available() else 0
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+           "--master-port", "29795", os.path.join(ROOT, "tests", "pg_worker.py"), "cuda"]
+    out = subprocess.run(cmd, env=dict(os.environ, PYTHONPATH=ROOT), capture_output=True, text=True, timeout=900)
+    assert "PG_WORKER_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]

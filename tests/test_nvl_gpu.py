@@ -352,3 +352,22 @@ def test_ring_allgather(steps_job, n, count):
     run(team, [cargs("allgatherv", src[r], dst[r], "int32", dst_counts=counts, dst_displs=displs) for r in range(n)])
     for r in range(n):
         assert torch.equal(dst[r], torch.cat(src)), r
+
+
+def test_single_rank_team_copy_kernel():
+    """team of one on CUDA buffers: served by tl/nvl's stream-ordered copy kernel (score above tl/self)."""
+    need_cuda()
+    with UccJob(1, env=dict(ENV), with_ctx_oob=False) as j:
+        team = j.create_team()
+        for count in (1, 1000, 1 << 20):
+            src = [gen("float32", count, 3)]
+            dst = [torch.zeros(count, device="cuda")]
+            run(team, [cargs("allreduce", src[0], dst[0], "float32", op="avg")])
+            assert torch.equal(dst[0], src[0])
+            run(team, [cargs("allgather", src[0], dst[0].zero_(), "float32")])
+            assert torch.equal(dst[0], src[0])
+            buf = [gen("float32", count, 4)]
+            keep = buf[0].clone()
+            run(team, [cargs("allreduce", None, buf[0], "float32", inplace=True)])
+            assert torch.equal(buf[0], keep)
+        run(team, [coll_args("barrier")])

@@ -57,6 +57,28 @@ class _TorchOob:
         return o
 
 
+class _StoreOob(_TorchOob):
+    """ucc_oob_coll_t over a c10d Store (TCPStore / FileStore): used when ucc_b200 itself is the torch.distributed
+    backend and no other process group exists yet."""
+
+    def __init__(self, store, rank, size, prefix="ucc_b200_oob"):
+        self.group, self.rank, self.size = None, rank, size
+        self._seq = 0
+
+        def allgather(src, recv, nbytes, info, req_pp):
+            seq = self._seq
+            self._seq += 1
+            store.set(f"{prefix}/{seq}/{rank}", bytes(C.string_at(src, nbytes)))
+            for r in range(size):
+                C.memmove(recv + r * nbytes, store.get(f"{prefix}/{seq}/{r}"), nbytes)
+            req_pp[0] = next(_TorchOob._ids)
+            return U.UCC_OK
+
+        self._ag = U.OOB_ALLGATHER_FN(allgather)
+        self._test = U.OOB_REQ_FN(lambda req: U.UCC_OK)
+        self._free = U.OOB_REQ_FN(lambda req: U.UCC_OK)
+
+
 class Request:
     def __init__(self, comm, req, keep):
         self.comm, self.req, self._keep = comm, req, keep
@@ -111,12 +133,16 @@ class Request:
 class Communicator:
     """lib + context + one team spanning `group` (default: all ranks)."""
 
-    def __init__(self, group=None, thread_mode=U.UCC_THREAD_SINGLE, lib_modify=(), ctx_modify=()):
-        if not dist.is_initialized():
-            raise RuntimeError("torch.distributed must be initialised (gloo is enough)")
-        self.rank = dist.get_rank(group)
-        self.size = dist.get_world_size(group)
-        self.oob = _TorchOob(group, self.rank, self.size)
+    def __init__(self, group=None, thread_mode=U.UCC_THREAD_SINGLE, lib_modify=(), ctx_modify=(), store=None, rank=None, size=None):
+        if store is not None:
+            self.rank, self.size = rank, size
+            self.oob = _StoreOob(store, rank, size)
+        else:
+            if not dist.is_initialized():
+                raise RuntimeError("torch.distributed must be initialised (gloo is enough)")
+            self.rank = dist.get_rank(group)
+            self.size = dist.get_world_size(group)
+            self.oob = _TorchOob(group, self.rank, self.size)
         cfg = U.handle()
         U.check(U.ucc_lib_config_read(None, None, C.byref(cfg)), "lib_config_read")
         for k, v in lib_modify:
