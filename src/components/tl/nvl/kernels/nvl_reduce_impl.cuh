@@ -125,13 +125,12 @@ template <typename T> static __device__ __forceinline__ void make_plan(const nvl
     pl.rounds = (int)((pl.slice_max + pl.cap_e - 1) / pl.cap_e);
 }
 
-/* where phase B puts a reduced vector when the members' dst buffers are mapped (NVL_DIRECT_DST): pointers are
- * pre-offset to the first element of my slice in this round; n == 0 means "publish through the heap" */
+/* destination pointer table of the zero-copy kernel's cold tail path */
 struct DOut { char *p[NVL_MAX_PEERS]; int n; };
 
 /* phase B worker: reduce vectors [j0,jend) of my slice. U vectors x NP sources in flight per thread. */
 template <typename T, int OP, int NP, int U>
-static __device__ __forceinline__ void reduce_p2p(const nvl_red_args_t &a, char *const *pd, size_t base, size_t j0, size_t jend, T *db, size_t rc, bool dal, float inv_n, const DOut &dout)
+static __device__ __forceinline__ void reduce_p2p(const nvl_red_args_t &a, char *const *pd, size_t base, size_t j0, size_t jend, T *db, size_t rc, bool dal, float inv_n)
 {
     constexpr int E = 16 / sizeof(T);
     const size_t nt = blockDim.x;
@@ -155,9 +154,7 @@ static __device__ __forceinline__ void reduce_p2p(const nvl_red_args_t &a, char 
                 for (int i = 1; i < NP; i++) if (i < N) acc.add(x[u][i]);
                 const uint4 r = acc.get(inv_n);
                 const size_t o = base + jj * 16;
-                if (dout.n) {
-                    for (int i = 0; i < dout.n; i++) store_dst_vec<T>(reinterpret_cast<T *>(dout.p[i]), jj * E, rc, true, r);
-                } else if (a.kind == NVL_RED_ALLREDUCE) {
+                if (a.kind == NVL_RED_ALLREDUCE) {
 #pragma unroll
                     for (int i = 0; i < NP; i++) if (i < N) st_v4(pd[i] + o, r);
                 } else if (a.kind == NVL_RED_REDUCE) st_v4(data_of(a.team, a.root) + o, r);
@@ -168,7 +165,7 @@ static __device__ __forceinline__ void reduce_p2p(const nvl_red_args_t &a, char 
 }
 
 template <typename T, int OP, int U>
-static __device__ __forceinline__ void reduce_nvls(const nvl_red_args_t &a, size_t base, size_t j0, size_t jend, T *db, size_t rc, bool dal, float inv_n, const DOut &dout)
+static __device__ __forceinline__ void reduce_nvls(const nvl_red_args_t &a, size_t base, size_t j0, size_t jend, T *db, size_t rc, bool dal, float inv_n)
 {
     constexpr int E = 16 / sizeof(T);
     const size_t nt = blockDim.x;
@@ -183,8 +180,7 @@ static __device__ __forceinline__ void reduce_nvls(const nvl_red_args_t &a, size
             if (jj < jend) {
                 uint4 v = r[u];
                 if (OP == NVL_OP_AVG) { VecAcc<T, OP> acc; acc.set(v); v = acc.get(inv_n); }
-                if (dout.n) { for (int i = 0; i < dout.n; i++) store_dst_vec<T>(reinterpret_cast<T *>(dout.p[i]), jj * E, rc, true, v); }
-                else if (a.kind == NVL_RED_ALLREDUCE) mc_st_v4(mc + jj * 16, v);
+                if (a.kind == NVL_RED_ALLREDUCE) mc_st_v4(mc + jj * 16, v);
                 else if (a.kind == NVL_RED_REDUCE) st_v4(data_of(a.team, a.root) + base + jj * 16, v);
                 else store_dst_vec<T>(db, jj * E, rc, dal, v);
             }
@@ -203,7 +199,6 @@ static __device__ __forceinline__ void staged_body(const nvl_red_args_t &a, Bloc
     const size_t cap_bytes = pl.cap_e * sizeof(T);
     const float inv_n = 1.0f / (float)N;
     const bool nvls = a.use_nvls && t.mc_heap != nullptr;
-    const bool direct_dst = a.direct == NVL_DIRECT_DST && a.kind != NVL_RED_REDUCE_SCATTER;
     char *mydata = data_of(t, me);
     char *pd[NVL_MAX_PEERS]; /* pd[i] = data region of my i-th right neighbour (i = 0: myself) */
 #pragma unroll
@@ -236,20 +231,13 @@ static __device__ __forceinline__ void staged_body(const nvl_red_args_t &a, Bloc
             const size_t jend = dmin(j1, (rc + E - 1) / E), base = (size_t)me * cap_bytes;
             T *db = dst + (a.kind == NVL_RED_REDUCE_SCATTER ? 0 : pl.off[me]) + e0;
             const bool dal = ((uintptr_t)db & 15) == 0;
-            DOut dout; dout.n = 0;
-            if (direct_dst) { /* results go straight into the members' dst buffers: no heap publish, no phase C */
-                const size_t eo = (pl.off[me] + e0) * sizeof(T);
-                if (a.kind == NVL_RED_ALLREDUCE) { for (int i = 0; i < N; i++) { int p = me + i; if (p >= N) p -= N; dout.p[i] = a.d.dst[p] + eo; } dout.n = N; }
-                else { dout.p[0] = a.d.dst[a.root] + eo; dout.n = 1; }
-            }
-            if (nvls) reduce_nvls<T, OP, 8>(a, base, j0, jend, db, rc, dal, inv_n, dout);
-            else if (N <= 2) reduce_p2p<T, OP, 2, 4>(a, pd, base, j0, jend, db, rc, dal, inv_n, dout);
-            else if (N <= 4) reduce_p2p<T, OP, 4, 2>(a, pd, base, j0, jend, db, rc, dal, inv_n, dout);
-            else if (N <= 8) reduce_p2p<T, OP, 8, 1>(a, pd, base, j0, jend, db, rc, dal, inv_n, dout);
-            else reduce_p2p<T, OP, NVL_MAX_PEERS, 1>(a, pd, base, j0, jend, db, rc, dal, inv_n, dout);
+            if (nvls) reduce_nvls<T, OP, 8>(a, base, j0, jend, db, rc, dal, inv_n);
+            else if (N <= 2) reduce_p2p<T, OP, 2, 4>(a, pd, base, j0, jend, db, rc, dal, inv_n);
+            else if (N <= 4) reduce_p2p<T, OP, 4, 2>(a, pd, base, j0, jend, db, rc, dal, inv_n);
+            else if (N <= 8) reduce_p2p<T, OP, 8, 1>(a, pd, base, j0, jend, db, rc, dal, inv_n);
+            else reduce_p2p<T, OP, NVL_MAX_PEERS, 1>(a, pd, base, j0, jend, db, rc, dal, inv_n);
         }
         bs.barrier(t, 2 * k + 2);
-        if (direct_dst) continue;
 
         /* phase C: my heap now holds vector range [j0,j1) of every reduced slice */
         if (a.kind == NVL_RED_ALLREDUCE || (a.kind == NVL_RED_REDUCE && me == a.root)) {

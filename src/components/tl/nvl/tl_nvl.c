@@ -23,7 +23,7 @@ ucc_config_field_t ucc_tl_nvl_context_config_table[] = {
     {"ZCOPY", "try", "Read and write the members' user buffers in place (CUDA IPC handles exchanged per collective, mappings cached) instead of staging through the heap",
      ucc_offsetof(ucc_tl_nvl_context_config_t, zcopy), UCC_CONFIG_TYPE_TERNARY},
     {"ZCOPY_THRESH", "1M", "Messages of at least this size use the zero-copy kernels", ucc_offsetof(ucc_tl_nvl_context_config_t, zcopy_thresh), UCC_CONFIG_TYPE_MEMUNITS},
-    {"ALLREDUCE_NVLS_THRESH", "512K", "Allreduce messages of at least this size use NVLS when available", ucc_offsetof(ucc_tl_nvl_context_config_t, nvls_thresh), UCC_CONFIG_TYPE_MEMUNITS},
+    {"ALLREDUCE_NVLS_THRESH", "512M", "Allreduce messages of at least this size use NVLS when available", ucc_offsetof(ucc_tl_nvl_context_config_t, nvls_thresh), UCC_CONFIG_TYPE_MEMUNITS},
     {"FD_VIA_PIDFD", "try", "Fetch peers' memory handles with pidfd_getfd before falling back to a unix socket", ucc_offsetof(ucc_tl_nvl_context_config_t, fd_via_pidfd), UCC_CONFIG_TYPE_TERNARY},
     {NULL}};
 

@@ -350,7 +350,9 @@ static ucc_status_t red_init(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, u
     /* zero-copy: every criterion below is evaluated identically on all ranks (sizes / counts are collective
      * arguments); what only the owner knows (can the buffer be exported? is it aligned?) travels with the exchange */
     if ((alg == RED_ALG_TWOSHOT || alg == RED_ALG_NVLS) && team->zcopy && ctx->cfg.zcopy != UCC_NO && bytes >= ctx->cfg.zcopy_thresh) {
-        int mode = alg == RED_ALG_NVLS ? (r->kind == NVL_RED_REDUCE_SCATTER ? NVL_DIRECT_NONE : NVL_DIRECT_DST) : NVL_DIRECT_FULL;
+        /* the NVLS kernels stay staged: writing the result to N mapped destinations instead of one multicast store was
+         * tried (NVL_DIRECT_DST) and measured slower on 8 GPUs - it multiplies the bytes leaving each GPU by 1.75 */
+        int mode = alg == RED_ALG_NVLS ? NVL_DIRECT_NONE : NVL_DIRECT_FULL;
         if (mode == NVL_DIRECT_FULL && r->kind == NVL_RED_REDUCE_SCATTER)
             for (ucc_rank_t i = 0; i < N; i++) if ((r->rs_offset[i] * ucc_dt_size(dt)) & 15) mode = NVL_DIRECT_NONE;
         if (mode != NVL_DIRECT_NONE) {
@@ -469,6 +471,10 @@ static ucc_status_t xchg_init(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, 
     if (st != UCC_OK) return st;
     t->kind = NVL_TASK_XCHG; t->u.xchg = x;
     t->nblocks = pick_blocks(ctx, moved, 64 * 1024);
+    /* the grid must be the same on every rank (blocks pair up through per-block flags), but for alltoallv / gatherv /
+     * scatterv `moved` is private to a rank: use a fixed grid for those */
+    if (a->coll_type == UCC_COLL_TYPE_ALLTOALLV || a->coll_type == UCC_COLL_TYPE_GATHERV || a->coll_type == UCC_COLL_TYPE_SCATTERV)
+        t->nblocks = (int)ucc_min(ctx->cfg.max_blocks, (ctx->cfg.nblocks != UCC_UUNITS_AUTO && ctx->cfg.nblocks > 0) ? ctx->cfg.nblocks : 64u);
     if (team->zcopy && ctx->cfg.zcopy != UCC_NO) {
         /* `moved` is the same number on every rank except for the v-collectives whose counts are private to a
          * rank (alltoallv, gatherv, scatterv): those only go zero-copy when it is forced, size-independently */
@@ -609,7 +615,10 @@ ucc_status_t ucc_tl_nvl_team_get_scores(ucc_base_team_t *b_team, ucc_coll_score_
      * messages when the multicast mapping is live (dt/op it cannot do fall back to twoshot through the
      * score fallback chain because nvls init returns NOT_SUPPORTED) */
     /* with two members the switch has nothing to combine: pulling over P2P moves the same bytes with less overhead */
-    if (team->nvls && UCC_TL_TEAM_SIZE(team) > 2) snprintf(sel, sizeof(sel), "allreduce:0-%s:@oneshot#allreduce:%s-inf:@nvls#reduce_scatter:%s-inf:@nvls#reduce_scatterv:%s-inf:@nvls#reduce:%s-inf:@nvls", a, n, n, n, n);
+    /* measured on 8 x B200: zero-copy two-shot wins from 1 MB to a few hundred MB (every byte crosses NVLink once, no
+     * staging); beyond that the in-switch reduction with its multicast store moves 1.75x fewer bytes out of each GPU and
+     * overtakes it despite the two staging passes (ALLREDUCE_NVLS_THRESH, default 512M) */
+    if (team->nvls && UCC_TL_TEAM_SIZE(team) > 2) snprintf(sel, sizeof(sel), "allreduce:0-%s:@oneshot#allreduce:%s-inf:@nvls#reduce_scatter:512K-inf:@nvls#reduce_scatterv:512K-inf:@nvls#reduce:512K-inf:@nvls", a, n);
     else snprintf(sel, sizeof(sel), "allreduce:0-%s:@oneshot", a);
     st = ucc_tl_apply_tune(&team->super, score, &info, sel, ctx->cfg.super.super.score_str);
     if (st != UCC_OK) { ucc_coll_score_free(score); return st; }
