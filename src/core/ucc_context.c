@@ -388,6 +388,7 @@ ucc_status_t ucc_context_create_proc_info(ucc_lib_h lib, const ucc_context_param
         if (iface->context.create_epilog && (st = iface->context.create_epilog(&ctx->cl_ctx[i]->super)) != UCC_OK) goto err_ids;
     }
     ucc_debug("created ucc context %p for lib %s", (void *)ctx, lib->full_prefix);
+    if (ucc_global_config.warn_unused_env_vars) ucc_config_parser_warn_unused_env_vars_once(); /* every CL/TL table is registered by now */
     *context = ctx;
     return UCC_OK;
 err_ids:

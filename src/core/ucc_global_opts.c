@@ -20,6 +20,8 @@ ucc_config_field_t ucc_global_config_table[] = {
      "UCC collective logging level. Higher level will result in more verbose collective info.\n"
      "Possible values are: fatal, error, warn, info, debug, trace.",
      ucc_offsetof(ucc_global_config_t, coll_trace_level), UCC_CONFIG_TYPE_ENUM(ucc_log_level_cfg_names)},
+    {"WARN_UNUSED_ENV_VARS", "y", "Issue a warning about UCC_* environment variables that no configuration table uses.",
+     ucc_offsetof(ucc_global_config_t, warn_unused_env_vars), UCC_CONFIG_TYPE_BOOL},
     {"PROFILE_MODE", "",
      "Profile collection modes. If none is specified, profiling is disabled.\n"
      " - log   - Record all timestamps.\n - accum - Accumulate measurements per location.",

@@ -11,6 +11,7 @@ typedef struct ucc_global_config {
     ucc_log_component_config_t log_component;   /* LOG_LEVEL */
     ucc_log_level_t            coll_trace_level;/* COLL_TRACE */
     ucc_log_component_config_t coll_trace;
+    int                        warn_unused_env_vars;
     char                      *component_path;  /* resolved <libdir>/ucc */
     char                      *install_path;
     int                        initialized;

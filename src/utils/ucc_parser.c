@@ -16,6 +16,42 @@ void ucc_config_table_register(ucc_config_global_list_entry_t *e)
     ucc_list_add_tail(&ucc_config_global_list, &e->list);
 }
 
+/* Does UCC_<rest> name a field of `table` (directly as <table prefix><field> or through the short-name fall-back)? */
+static int env_names_field(const char *rest, const ucc_config_field_t *table, const char *tprefix)
+{
+    size_t pl = strlen(tprefix);
+    for (const ucc_config_field_t *f = table; f->name; f++) {
+        if (f->parser.read == ucc_config_sscanf_table) { if (env_names_field(rest, (const ucc_config_field_t *)f->parser.arg, tprefix)) return 1; continue; }
+        if (!f->name[0]) continue;
+        if (!strcmp(rest, f->name)) return 1;
+        if (pl && !strncmp(rest, tprefix, pl) && !strcmp(rest + pl, f->name)) return 1;
+    }
+    return 0;
+}
+
+/* One-time warning about UCC_* environment variables that no registered configuration table consumes (typos are the
+ * usual reason).  Same service as the UCS parser gives the reference (UCC_WARN_UNUSED_ENV_VARS). */
+void ucc_config_parser_warn_unused_env_vars_once(void)
+{
+    static int done = 0;
+    static const char *direct[] = {"UCC_DEBUGGER_WAIT", "UCC_TL_NCCL_LIB", "UCC_MODULE_DIR", NULL}; /* read with getenv() */
+    extern char **environ;
+    char unused[1024]; size_t len = 0; int n = 0;
+    if (done) return;
+    done = 1;
+    for (char **e = environ; e && *e; e++) {
+        const char *eq = strchr(*e, '='), *p = strstr(*e, "UCC_");
+        char name[256]; ucc_config_global_list_entry_t *it; int used = 0;
+        if (!eq || !p || p > eq || (size_t)(eq - *e) >= sizeof(name)) continue;
+        if (p != *e && p[-1] != '_') continue; /* "<APP>_UCC_..." is fine, "FOOUCC_" is not ours */
+        memcpy(name, *e, (size_t)(eq - *e)); name[eq - *e] = 0;
+        for (int i = 0; direct[i]; i++) if (!strcmp(name + (p - *e), direct[i])) used = 1;
+        ucc_list_for_each(it, &ucc_config_global_list, list) { if (used) break; used = env_names_field(name + (p - *e) + 4, it->table, it->prefix ? it->prefix : ""); }
+        if (!used && len + strlen(name) + 3 < sizeof(unused)) { len += (size_t)snprintf(unused + len, sizeof(unused) - len, "%s%s", n ? "; " : "", name); n++; }
+    }
+    if (n) ucc_warn("unused environment variable%s: %s (set UCC_WARN_UNUSED_ENV_VARS=n to suppress this warning)", n > 1 ? "s" : "", unused);
+}
+
 /* ------------------------------------------------------------------ */
 /* scalar types                                                        */
 /* ------------------------------------------------------------------ */

@@ -48,6 +48,7 @@ extern ucc_list_link_t ucc_config_global_list;
     static void UCC_CTOR _table##_config_register(void)                                            \
     { ucc_config_table_register(&_table##_config_entry); }
 void ucc_config_table_register(ucc_config_global_list_entry_t *e);
+void ucc_config_parser_warn_unused_env_vars_once(void); /* UCC_* variables that no registered table consumes */
 
 typedef struct ucc_config_names_array { char **names; unsigned count; unsigned pad; } ucc_config_names_array_t;
 typedef enum { UCC_CONFIG_ALLOW_LIST_ALLOW_ALL, UCC_CONFIG_ALLOW_LIST_ALLOW, UCC_CONFIG_ALLOW_LIST_NEGATE } ucc_config_allow_list_mode_t;
