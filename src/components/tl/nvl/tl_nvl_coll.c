@@ -474,12 +474,14 @@ static ucc_status_t xchg_init(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, 
     /* the grid must be the same on every rank (blocks pair up through per-block flags), but for alltoallv / gatherv /
      * scatterv `moved` is private to a rank: use a fixed grid for those */
     if (a->coll_type == UCC_COLL_TYPE_ALLTOALLV || a->coll_type == UCC_COLL_TYPE_GATHERV || a->coll_type == UCC_COLL_TYPE_SCATTERV)
-        t->nblocks = (int)ucc_min(ctx->cfg.max_blocks, (ctx->cfg.nblocks != UCC_UUNITS_AUTO && ctx->cfg.nblocks > 0) ? ctx->cfg.nblocks : 64u);
+        t->nblocks = (int)ucc_min(ctx->cfg.max_blocks, (ctx->cfg.nblocks != UCC_UUNITS_AUTO && ctx->cfg.nblocks > 0) ? ctx->cfg.nblocks : 128u);
     if (team->zcopy && ctx->cfg.zcopy != UCC_NO) {
         /* `moved` is the same number on every rank except for the v-collectives whose counts are private to a
          * rank (alltoallv, gatherv, scatterv): those only go zero-copy when it is forced, size-independently */
         int symmetric = a->coll_type != UCC_COLL_TYPE_ALLTOALLV && a->coll_type != UCC_COLL_TYPE_GATHERV && a->coll_type != UCC_COLL_TYPE_SCATTERV;
-        if (symmetric ? moved >= ctx->cfg.zcopy_thresh : ctx->cfg.zcopy == UCC_YES) {
+        /* (asymmetric ones: always - the choice may only depend on what every rank knows, and staging a skewed
+         * alltoallv through the heap was 2.4x slower than NCCL at 16 MB on 4 GPUs) */
+        if (symmetric ? moved >= (ctx->cfg.zcopy == UCC_YES ? ctx->cfg.zcopy_thresh : ucc_max(ctx->cfg.zcopy_thresh, (size_t)4 << 20)) : 1) { /* below ~4 MB the host-side exchange costs more than the staging copy */
             t->want_direct = NVL_DIRECT_FULL; t->need_src = 1; t->need_dst = 0;
             t->exp_src = x.src_bytes ? x.src : NULL; t->exp_src_len = x.src_bytes;
         }
@@ -618,7 +620,10 @@ ucc_status_t ucc_tl_nvl_team_get_scores(ucc_base_team_t *b_team, ucc_coll_score_
     /* measured on 8 x B200: zero-copy two-shot wins from 1 MB to a few hundred MB (every byte crosses NVLink once, no
      * staging); beyond that the in-switch reduction with its multicast store moves 1.75x fewer bytes out of each GPU and
      * overtakes it despite the two staging passes (ALLREDUCE_NVLS_THRESH, default 512M) */
-    if (team->nvls && UCC_TL_TEAM_SIZE(team) > 2) snprintf(sel, sizeof(sel), "allreduce:0-%s:@oneshot#allreduce:%s-inf:@nvls#reduce_scatter:512K-inf:@nvls#reduce_scatterv:512K-inf:@nvls#reduce:512K-inf:@nvls", a, n);
+    /* 4 x B200: zero-copy two-shot stays ahead at every size (634 GB/s at 256 MB vs 605 for NVLS at 1 GiB), and the
+     * NVLS reduce_scatter loses to it because of the staging pass (390 vs NCCL 525 GB/s at 256 MB) - so NVLS is the
+     * default only for very large allreduce on teams of more than four; `@nvls` remains selectable for everything */
+    if (team->nvls && UCC_TL_TEAM_SIZE(team) > 4) snprintf(sel, sizeof(sel), "allreduce:0-%s:@oneshot#allreduce:%s-inf:@nvls", a, n);
     else snprintf(sel, sizeof(sel), "allreduce:0-%s:@oneshot", a);
     st = ucc_tl_apply_tune(&team->super, score, &info, sel, ctx->cfg.super.super.score_str);
     if (st != UCC_OK) { ucc_coll_score_free(score); return st; }

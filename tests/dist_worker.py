@@ -42,6 +42,7 @@ def main():
     # allgather + alltoall + bcast + reduce_scatter: small (staged kernels) and large (zero-copy kernels on CUDA)
     for blk in (1000, 300000):
         ok &= other_colls(comm, rank, world, dev, use_cuda, blk)
+    ok &= team_kinds(rank, world, dev, use_cuda)
     comm.barrier()
     flag = torch.tensor([1 if ok else 0])
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
@@ -50,6 +51,47 @@ def main():
         print("DIST_WORKER_OK" if flag.item() == 1 else "DIST_WORKER_FAIL", flush=True)
     dist.destroy_process_group()
     sys.exit(0 if flag.item() == 1 else 1)
+
+
+def team_kinds(rank, world, dev, use_cuda):
+    """Teams other than WORLD (reference test/mpi team kinds: half, odd_even, reverse), each checked against an oracle."""
+    ok = True
+    if world < 3:
+        return ok
+    kinds = {"half": list(range((world + 1) // 2)), "odd_even": [r for r in range(world) if r % 2 == rank % 2]}
+    groups = {"half": dist.new_group(kinds["half"], backend="gloo")}
+    even, odd = dist.new_group([r for r in range(world) if r % 2 == 0], backend="gloo"), dist.new_group([r for r in range(world) if r % 2 == 1], backend="gloo")
+    groups["odd_even"] = even if rank % 2 == 0 else odd
+    for kind, members in kinds.items():
+        if rank not in members or len(members) < 2:
+            continue
+        c = Communicator(groups[kind])
+        x = torch.full((257,), float(rank + 1), device=dev)
+        c.run(c.allreduce_init(x, x))
+        if use_cuda:
+            torch.cuda.synchronize()
+        ok &= bool((x.cpu() == float(sum(m + 1 for m in members))).all())
+        g = torch.zeros(len(members) * 3, device=dev)
+        c.run(c.coll_init("allgather", torch.full((3,), float(rank), device=dev), g))
+        if use_cuda:
+            torch.cuda.synchronize()
+        ok &= bool(torch.equal(g.view(len(members), 3)[:, 0].cpu(), torch.tensor([float(m) for m in members])))
+        c.destroy()
+    # reverse: every process takes part, UCC rank = world - 1 - torch rank
+    perm = [world - 1 - g for g in range(world)]
+    c = Communicator(perm=perm)
+    g = torch.zeros(world * 2, device=dev)
+    c.run(c.coll_init("allgather", torch.full((2,), float(rank), device=dev), g))
+    b = torch.full((64,), 5.0 if c.rank == 0 else 0.0, device=dev)     # UCC root 0 is torch rank world-1
+    c.run(c.coll_init("bcast", b, None, root=0))
+    if use_cuda:
+        torch.cuda.synchronize()
+    ok &= bool(torch.equal(g.view(world, 2)[:, 0].cpu(), torch.tensor([float(world - 1 - u) for u in range(world)])))
+    ok &= bool((b.cpu() == 5.0).all())
+    c.destroy()
+    if not ok:
+        print(f"rank {rank}: team kinds mismatch", flush=True)
+    return ok
 
 
 def other_colls(comm, rank, world, dev, use_cuda, blk):

@@ -33,13 +33,18 @@ class _TorchOob:
     """ucc_oob_coll_t whose allgather is a (blocking) gloo all_gather."""
     _ids = itertools.count(1)
 
-    def __init__(self, group, rank, size):
+    def __init__(self, group, rank, size, perm=None):
         self.group, self.rank, self.size = group, rank, size
 
         def allgather(src, recv, nbytes, info, req_pp):
             mine = torch.frombuffer(bytearray(C.string_at(src, nbytes)), dtype=torch.uint8).clone()
             outs = [torch.empty(nbytes, dtype=torch.uint8) for _ in range(self.size)]
             dist.all_gather(outs, mine, group=self.group)
+            if perm is not None:          # UCC rank perm[g] is played by group rank g
+                by_ucc = [None] * self.size
+                for g, o in enumerate(outs):
+                    by_ucc[perm[g]] = o
+                outs = by_ucc
             flat = torch.cat(outs).contiguous()
             C.memmove(recv, flat.data_ptr(), nbytes * self.size)
             req_pp[0] = next(_TorchOob._ids)
@@ -133,16 +138,18 @@ class Request:
 class Communicator:
     """lib + context + one team spanning `group` (default: all ranks)."""
 
-    def __init__(self, group=None, thread_mode=U.UCC_THREAD_SINGLE, lib_modify=(), ctx_modify=(), store=None, rank=None, size=None):
+    def __init__(self, group=None, thread_mode=U.UCC_THREAD_SINGLE, lib_modify=(), ctx_modify=(), store=None, rank=None, size=None, perm=None):
+        """`perm[g]` = UCC rank of group rank g (default identity): lets a team use any rank order (e.g. reversed)."""
         if store is not None:
             self.rank, self.size = rank, size
             self.oob = _StoreOob(store, rank, size)
         else:
             if not dist.is_initialized():
                 raise RuntimeError("torch.distributed must be initialised (gloo is enough)")
-            self.rank = dist.get_rank(group)
+            grank = dist.get_rank(group)
             self.size = dist.get_world_size(group)
-            self.oob = _TorchOob(group, self.rank, self.size)
+            self.rank = perm[grank] if perm is not None else grank
+            self.oob = _TorchOob(group, self.rank, self.size, perm)
         cfg = U.handle()
         U.check(U.ucc_lib_config_read(None, None, C.byref(cfg)), "lib_config_read")
         for k, v in lib_modify:
@@ -214,10 +221,10 @@ class Communicator:
         U.ucc_context_progress(self.ctx)
 
     # ------------------------------------------------------------------ collectives
-    def init(self, args):
+    def init(self, args, hold=()):
         r = C.POINTER(U.ucc_coll_req_t)()
         U.check(U.ucc_collective_init(C.byref(args), C.byref(r), self.team), "collective_init")
-        return Request(self, r, args)
+        return Request(self, r, (args, hold))   # `hold` keeps the tensors alive until the request is finalized
 
     def _args(self, coll, src=None, dst=None, op="sum", root=0, inplace=False, persistent=False, **kw):
         from .harness import coll_args
@@ -231,10 +238,10 @@ class Communicator:
 
     def allreduce_init(self, src, dst, op="sum", persistent=False):
         inplace = src is None or src.data_ptr() == dst.data_ptr()
-        return self.init(self._args("allreduce", None if inplace else src, dst, op=op, inplace=inplace, persistent=persistent))
+        return self.init(self._args("allreduce", None if inplace else src, dst, op=op, inplace=inplace, persistent=persistent), (src, dst))
 
     def coll_init(self, coll, src=None, dst=None, **kw):
-        return self.init(self._args(coll, src, dst, **kw))
+        return self.init(self._args(coll, src, dst, **kw), (src, dst))
 
     def run(self, req, stream=None):
         """Convenience: post, wait (host), finalize."""
