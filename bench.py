@@ -46,7 +46,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -165,7 +165,6 @@ def main():
     sampler.start()
     us, ok = time_ours(S, a.steps, a.warmup)
     launches["n"] = a.steps
-    clocks = sampler.stop()
     value = busbw(S, us)
     nccl_us = time_nccl(S, a.steps, a.warmup)
 
@@ -200,6 +199,8 @@ def main():
         e2e = {"value": busbw(S, e2e_us), "unit": "GB/s", "h2d_bytes_per_step": S, "d2h_bytes_per_step": 16 * esz, "us_per_step": e2e_us}
         del host, src, dst
 
+    clocks = sampler.stop()   # sampled across the device-timed headline steps and the end-to-end steps
+
     # ------------------------------------------------------------------ sweep (latency + bus bandwidth vs size)
     sweep = []
     if not a.no_sweep:
@@ -220,7 +221,8 @@ def main():
                    "seq_len": S // esz, "parallelism": f"dp{N}", "timing": "cuda events on the posting stream, max over ranks",
                    "l2": "message (1 GiB) is larger than the 126 MB L2", "algorithm": "tl/nvl fused kernel chosen by coll_score"},
         "correct": bool(ok), "clocks": clocks, "gpu_launches": launches["n"],
-        "latency_us": round(us, 2), "roofline_frac_of_900": round(value / 900.0, 4), "roofline_frac_of_measured_770": round(value / 770.0, 4),
+        "latency_us": round(us, 2), "roofline_frac_of_900": round(value / 900.0, 4) if N > 1 else None, "roofline_frac_of_measured_770": round(value / 770.0, 4) if N > 1 else None,
+        "roofline_frac_of_hbm_copy_6478": round(2.0 * value / 6478.3, 4) if N == 1 else None,
         "nccl_same_box": {"us": round(nccl_us, 2), "busbw": round(busbw(S, nccl_us), 2)} if nccl_us else None,
     }
     if e2e:
