@@ -40,6 +40,17 @@ def main():
     exp = torch.cat([torch.arange(rank * 2, rank * 2 + 2, dtype=torch.float32) + 100 * p for p in range(world)])
     ok &= bool(torch.equal(a2a.cpu(), exp))
     dist.barrier()
+    # point to point (active-set bcast underneath): ring shift
+    nxt, prv = (rank + 1) % world, (rank - 1 + world) % world
+    got = torch.zeros(7, device=dev)
+    if rank % 2 == 0:
+        dist.send(torch.full((7,), float(rank), device=dev), nxt)
+        dist.recv(got, prv)
+    else:
+        dist.recv(got, prv)
+        dist.send(torch.full((7,), float(rank), device=dev), nxt)
+    if world % 2 == 0 or rank not in (0, world - 1):     # (odd rings would need non-blocking p2p to avoid the wrap-around wait)
+        ok &= bool((got == float(prv)).all())
     # torch's own DDP on top of the backend
     torch.manual_seed(0)
     model = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.ReLU(), torch.nn.Linear(32, 4)).to(dev)

@@ -166,6 +166,17 @@ class ProcessGroupUCCB200(dist.ProcessGroup):
         req = self._comm.coll_init("alltoallv", input.contiguous(), output, src_counts=sc, src_displs=sd, dst_counts=rc, dst_displs=rd)
         return self._run([req], [input], output)
 
+    # ---- point to point: a two-member active-set broadcast, exactly how ProcessGroupUCC maps send/recv onto UCC
+    def _p2p(self, tensors, src, dst, tag):
+        reqs = [self._comm.coll_init("bcast", t, None, root=src, active_set=(src, dst - src, 2), tag=int(tag) & 0x3fff) for t in tensors]
+        return self._run(reqs, tensors, tensors)
+
+    def send(self, tensors, dstRank, tag=0):
+        return self._p2p(tensors, self.rank(), dstRank, tag)
+
+    def recv(self, tensors, srcRank, tag=0):
+        return self._p2p(tensors, srcRank, self.rank(), tag)
+
     def barrier(self, opts=None):
         self._comm.barrier()
         w = _Work(self, [], None, False)
