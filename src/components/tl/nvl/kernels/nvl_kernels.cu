@@ -150,16 +150,41 @@ __global__ void __launch_bounds__(NVL_THREADS_MAX, 2) nvl_exchange_kernel(nvl_xc
     }
     bs.signal(t, 1);
     bs.wait_all_blocks(t, 1);
-    /* phase B: pull */
-    for (int i = 0; i < N; i++) {
+    /* phase B: pull.  Resolve every remote block first; when all of them are 16-byte aligned the vectors of up to eight
+     * peers are requested together (one NVLink round trip instead of one per peer - what matters for the 1..64 MB range
+     * where a thread owns only a few vectors of each block) */
+    const char *sp[NVL_MAX_PEERS]; char *dp[NVL_MAX_PEERS]; size_t nb[NVL_MAX_PEERS]; int np = 0; bool vec = true; size_t nvmax = 0;
+    for (int i = 1; i < N; i++) {
         int p = me + i; if (p >= N) p -= N;
         const size_t n = a.pull_bytes[p];
         if (!n) continue;
-        char *d = static_cast<char *>(a.dst) + a.dst_off[p];
-        if (p == me) { if (d != static_cast<const char *>(a.src) + a.self_off) copy_bytes_grid<false>(d, static_cast<const char *>(a.src) + a.self_off, n); continue; }
         size_t off = a.pull_off[p];
         if (off == NVL_XCHG_LOOKUP) off = (size_t) * reinterpret_cast<volatile const uint64_t *>(data_of(t, p) + (size_t)me * 8);
-        copy_bytes_grid<true>(d, (a.direct ? a.d.src[p] : (a.use_mc ? mydata : data_of(t, p)) + NVL_XCHG_TABLE_BYTES) + off, n);
+        sp[np] = (a.direct ? a.d.src[p] : (a.use_mc ? mydata : data_of(t, p)) + NVL_XCHG_TABLE_BYTES) + off;
+        dp[np] = static_cast<char *>(a.dst) + a.dst_off[p]; nb[np] = n;
+        if (((uintptr_t)sp[np] | (uintptr_t)dp[np]) & 15) vec = false;
+        if (n / 16 > nvmax) nvmax = n / 16;
+        np++;
+    }
+    if (a.pull_bytes[me]) { /* own block: a local copy */
+        char *d = static_cast<char *>(a.dst) + a.dst_off[me];
+        if (d != static_cast<const char *>(a.src) + a.self_off) copy_bytes_grid<false>(d, static_cast<const char *>(a.src) + a.self_off, a.pull_bytes[me]);
+    }
+    if (vec && np > 1) {
+        const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (size_t)gridDim.x * blockDim.x;
+        for (int g = 0; g < np; g += 8) {
+            for (size_t v = tid; v < nvmax; v += nt) {
+                uint4 x[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) if (g + k < np && v < nb[g + k] / 16) x[k] = ld_peer_v4(sp[g + k] + v * 16);
+#pragma unroll
+                for (int k = 0; k < 8; k++) if (g + k < np && v < nb[g + k] / 16) st_v4(dp[g + k] + v * 16, x[k]);
+            }
+        }
+        for (int q = 0; q < np; q++) /* ragged tails (< 16 bytes per block) */
+            for (size_t i = (nb[q] / 16) * 16 + tid; i < nb[q]; i += nt) dp[q][i] = *(volatile const char *)(sp[q] + i);
+    } else {
+        for (int q = 0; q < np; q++) copy_bytes_grid<true>(dp[q], sp[q], nb[q]);
     }
     bs.signal(t, 2);
     bs.wait_all_blocks(t, 2);

@@ -371,3 +371,24 @@ def test_single_rank_team_copy_kernel():
             run(team, [cargs("allreduce", None, buf[0], "float32", inplace=True)])
             assert torch.equal(buf[0], keep)
         run(team, [coll_args("barrier")])
+
+
+@pytest.mark.parametrize("alg", ["rab", "split_rail"])
+def test_cl_hier_on_cuda_buffers(alg):
+    """cl/hier with a synthetic 2-node x 4-GPU placement: node / leaders / rail sub-teams are tl/nvl teams over sub-group maps."""
+    need_cuda()
+    env = dict(ENV, UCC_CLS="hier,basic", UCC_CL_HIER_TUNE=f"allreduce:0-inf:@{alg}", **NOZC)
+    with UccJob(8, ppn=4, env=env, cls="hier,basic") as j:
+        team = j.create_team()
+        n = 8
+        for count in (16, 4096, 100000):
+            src = [gen("float32", count, 7 * r + 1) for r in range(n)]
+            dst = [torch.zeros(count, device="cuda") for _ in range(n)]
+            run(team, [cargs("allreduce", src[r], dst[r], "float32") for r in range(n)])
+            exp = ref_reduce("sum", src)
+            for r in range(n):
+                assert_close(dst[r], exp, "float32")
+        b = [gen("float32", 5000, 3) if r == 0 else torch.zeros(5000, device="cuda") for r in range(n)]
+        run(team, [cargs("bcast", b[r], None, "float32", root=0, count_dst=0) for r in range(n)])
+        for r in range(n):
+            assert torch.equal(b[r], b[0])
