@@ -392,3 +392,26 @@ def test_cl_hier_on_cuda_buffers(alg):
         run(team, [cargs("bcast", b[r], None, "float32", root=0, count_dst=0) for r in range(n)])
         for r in range(n):
             assert torch.equal(b[r], b[0])
+
+
+def test_asymmetric_memory_at_root(job):
+    """reference test/gtest/asym_mem: root's src and dst live in different memory types (staged by the core)."""
+    team = job[4]
+    n, count = 4, 3000
+    # reduce: everybody contributes CUDA data, the root wants the result in HOST memory
+    src = [gen("float32", count, r) for r in range(n)]
+    host_dst = np.zeros(count, np.float32)
+    args = [cargs("reduce", src[r], None, "float32", root=1, count_dst=0) for r in range(n)]
+    args[1] = coll_args("reduce", dt="float32", root=1, src_ptr=src[1].data_ptr(), dst_ptr=host_dst.ctypes.data, count_src=count, count_dst=count,
+                        src_mem_type=CUDA, dst_mem_type=U.UCC_MEMORY_TYPE_HOST)
+    run(team, args)
+    assert np.allclose(host_dst, ref_reduce("sum", src).cpu().numpy(), rtol=1e-5)
+    # scatter: the root's source is in HOST memory, every destination is CUDA
+    host_src = np.arange(n * 100, dtype=np.float32)
+    dst = [torch.zeros(100, device="cuda") for _ in range(n)]
+    args = [coll_args("scatter", dt="float32", root=0, dst_ptr=dst[r].data_ptr(), count_dst=100, count_src=0, mem_type=CUDA) for r in range(n)]
+    args[0] = coll_args("scatter", dt="float32", root=0, src_ptr=host_src.ctypes.data, dst_ptr=dst[0].data_ptr(), count_src=n * 100, count_dst=100,
+                        src_mem_type=U.UCC_MEMORY_TYPE_HOST, dst_mem_type=CUDA)
+    run(team, args)
+    for r in range(n):
+        assert np.array_equal(dst[r].cpu().numpy(), host_src[r * 100:(r + 1) * 100])
