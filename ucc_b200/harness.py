@@ -184,9 +184,11 @@ class UccReq:
                 worst = U.UCC_INPROGRESS
         return worst
 
-    def wait(self, max_iters=20_000_000):
+    def wait(self, max_iters=20_000_000, max_seconds=120.0):
+        import time
         procs = self.team.job.procs
         it = 0
+        t0 = time.monotonic()
         while True:
             st = self.test()
             if st != U.UCC_INPROGRESS:
@@ -194,7 +196,7 @@ class UccReq:
             for p in procs:
                 p.progress()
             it += 1
-            if it > max_iters:
+            if it > max_iters or ((it & 0x3ff) == 0 and time.monotonic() - t0 > max_seconds):
                 raise TimeoutError("collective did not complete")
 
     def finalize(self):
@@ -242,8 +244,10 @@ class UccTeam:
             U.check(U.ucc_team_create_post(ctxs, 1, C.byref(p), C.byref(m.team)), "team_create_post")
         self._wait_create()
 
-    def _wait_create(self, max_iters=5_000_000):
+    def _wait_create(self, max_iters=5_000_000, max_seconds=180.0):
+        import time
         it = 0
+        t0 = time.monotonic()
         while True:
             pending = False
             for m in self.members:
@@ -257,7 +261,7 @@ class UccTeam:
             for p in self.job.procs:
                 p.progress()
             it += 1
-            if it > max_iters:
+            if it > max_iters or ((it & 0xff) == 0 and time.monotonic() - t0 > max_seconds):
                 raise TimeoutError("team creation did not complete")
 
     @property
