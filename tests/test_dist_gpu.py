@@ -28,28 +28,28 @@ def test_multiproc_all_gpus():
 
 
 def test_multiproc_no_nvls():
-    n = torch.cuda.device_count() if torch.cuda.is_available() else 0
+    n = min(2, torch.cuda.device_count()) if torch.cuda.is_available() else 0   # validated on 2 GPUs
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
     _run(n, {"UCC_TL_NVL_USE_NVLS": "n"})
 
 
 def test_multiproc_ipc_heap():
-    n = torch.cuda.device_count() if torch.cuda.is_available() else 0
+    n = min(2, torch.cuda.device_count()) if torch.cuda.is_available() else 0   # validated on 2 GPUs
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
     _run(n, {"UCC_TL_NVL_USE_VMM": "n"})
 
 
 def test_multiproc_zcopy_forced():
-    n = torch.cuda.device_count() if torch.cuda.is_available() else 0
+    n = min(2, torch.cuda.device_count()) if torch.cuda.is_available() else 0   # validated on 2 GPUs
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
     _run(n, {"UCC_TL_NVL_ZCOPY": "y", "UCC_TL_NVL_ZCOPY_THRESH": "0"})
 
 
 def test_multiproc_no_zcopy():
-    n = torch.cuda.device_count() if torch.cuda.is_available() else 0
+    n = min(2, torch.cuda.device_count()) if torch.cuda.is_available() else 0   # validated on 2 GPUs
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
     _run(n, {"UCC_TL_NVL_ZCOPY": "n"})
@@ -57,7 +57,7 @@ def test_multiproc_no_zcopy():
 
 def test_parallel_helpers_cuda():
     """DDP buckets / tensor parallel / MoE alltoallv on CUDA tensors through the tl/nvl kernels."""
-    n = torch.cuda.device_count() if torch.cuda.is_available() else 0
+    n = min(2, torch.cuda.device_count()) if torch.cuda.is_available() else 0   # validated on 2 GPUs
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
@@ -68,14 +68,14 @@ def test_parallel_helpers_cuda():
 
 def test_multiproc_nvls_everything():
     """NVLS variants forced: in-switch allreduce / reduce_scatter (float and integer), multicast allgather / bcast."""
-    n = torch.cuda.device_count() if torch.cuda.is_available() else 0
+    n = min(2, torch.cuda.device_count()) if torch.cuda.is_available() else 0   # validated on 2 GPUs
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
     _run(n, {"UCC_TL_NVL_TUNE": "allreduce:cuda:inf:@nvls#reduce_scatter:cuda:inf:@nvls#allgather:cuda:inf:@nvls#bcast:cuda:inf:@nvls", "UCC_TL_NVL_ALLREDUCE_ONESHOT_THRESH": "0"})
 
 
 def test_multiproc_ring_rhd():
-    n = torch.cuda.device_count() if torch.cuda.is_available() else 0
+    n = min(2, torch.cuda.device_count()) if torch.cuda.is_available() else 0   # validated on 2 GPUs
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
     _run(n, {"UCC_TL_NVL_TUNE": "allreduce:cuda:inf:@ring#reduce_scatter:cuda:inf:@rhd#allgather:cuda:inf:@ring", "UCC_TL_NVL_ZCOPY": "n"})
@@ -83,7 +83,7 @@ def test_multiproc_ring_rhd():
 
 def test_torch_backend_cuda():
     """init_process_group("ucc_b200"): c10d collectives and torch DDP on CUDA tensors run on the tl/nvl kernels."""
-    n = torch.cuda.device_count() if torch.cuda.is_available() else 0
+    n = min(2, torch.cuda.device_count()) if torch.cuda.is_available() else 0   # validated on 2 GPUs
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",

@@ -373,12 +373,11 @@ def test_single_rank_team_copy_kernel():
         run(team, [coll_args("barrier")])
 
 
-# Not yet validated on hardware (the GPU budget of round 1 ran out while split_rail on CUDA buffers was hanging on the
-# host side): opt-in until they have been seen passing.
+# Opt-in: seen hanging on the host side in the last GPU session of round 1 (asymmetric memory at the root with tl/nvl),
+# not debugged yet because the GPU budget was exhausted.
 EXPERIMENTAL = pytest.mark.skipif(os.environ.get("UCC_B200_EXPERIMENTAL_TESTS") != "1", reason="set UCC_B200_EXPERIMENTAL_TESTS=1")
 
 
-@EXPERIMENTAL
 @pytest.mark.parametrize("alg", ["rab", "split_rail"])
 def test_cl_hier_on_cuda_buffers(alg):
     """cl/hier with a synthetic 2-node x 4-GPU placement: node / leaders / rail sub-teams are tl/nvl teams over sub-group maps."""
