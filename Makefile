@@ -51,9 +51,16 @@ ifneq ($(wildcard tools/perf/*.c*),)
 TOOLS += $(BINDIR)/ucc_perftest
 endif
 
+# host-side algorithm plugins of tl/shm (libucc_tlcp_shm_<name>.so, plain C)
+TLCP_SRCS := $(wildcard src/components/tl/shm/coll_plugins/*/*.c)
+TLCPS     := $(foreach s,$(TLCP_SRCS),$(MODDIR)/libucc_tlcp_shm_$(notdir $(patsubst %/,%,$(dir $(s)))).so)
+
 .PHONY: all core plugins tools clean sass
 all: core plugins tools
-core: $(OUT)/libucc.so
+core: $(OUT)/libucc.so $(TLCPS)
+$(MODDIR)/libucc_tlcp_shm_%.so: src/components/tl/shm/coll_plugins/%/*.c $(OUT)/libucc.so
+	@mkdir -p $(MODDIR)
+	$(CC) $(CFLAGS) -shared -o $@ $(wildcard src/components/tl/shm/coll_plugins/$*/*.c) -L$(OUT) -lucc -Wl,-rpath,'$$ORIGIN/..'
 plugins: $(PLUGINS)
 tools: $(TOOLS)
 

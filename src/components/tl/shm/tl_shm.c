@@ -153,6 +153,13 @@ static ucc_status_t shm_lib_init(const ucc_base_lib_params_t *p, const ucc_base_
     (void)p;
     if (!lib) return UCC_ERR_NO_MEMORY;
     ucc_tl_lib_init_base(&lib->super, &ucc_tl_shm, ucc_derived_of(config, ucc_tl_lib_config_t));
+    /* algorithm plugins (reference tl/ucc_tl.h:64-69, tl/ucp/coll_plugins/example): modules libucc_tlcp_shm_<name>.so
+     * exporting `ucc_tlcp_shm_<name>`; each contributes a score table that is merged into the TL's */
+    if (!ucc_tl_shm.coll_plugins.framework_name) {
+        if (ucc_components_load("tlcp_shm", &ucc_tl_shm.coll_plugins) != UCC_OK) ucc_tl_shm.coll_plugins.n_components = 0;
+        for (int i = 0; i < ucc_tl_shm.coll_plugins.n_components; i++) /* so that ucc_info -c and the unused-variable check know them */
+            ucc_config_table_register(&ucc_derived_of(ucc_tl_shm.coll_plugins.components[i], ucc_tl_coll_plugin_iface_t)->config);
+    }
     *lib_p = &lib->super.super;
     return UCC_OK;
 }
@@ -238,6 +245,13 @@ static ucc_status_t shm_team_get_scores(ucc_base_team_t *b_team, ucc_coll_score_
     if (st != UCC_OK) return st;
     st = ucc_tl_apply_tune(&team->super, score, &info, SHM_DEFAULT_SELECT_STR, ctx->cfg.super.super.score_str);
     if (st != UCC_OK) { ucc_coll_score_free(score); return st; }
+    for (int i = 0; i < ucc_tl_shm.coll_plugins.n_components; i++) {
+        ucc_tl_coll_plugin_iface_t *p = ucc_derived_of(ucc_tl_shm.coll_plugins.components[i], ucc_tl_coll_plugin_iface_t);
+        ucc_coll_score_t *ps = NULL;
+        if (!p->get_scores || p->get_scores(b_team, &ps) != UCC_OK || !ps) continue;
+        st = ucc_coll_score_merge_in(&score, ps); /* higher score wins per range, the TL's own entry stays as the fallback */
+        if (st != UCC_OK) return st;
+    }
     *score_p = score;
     return UCC_OK;
 }

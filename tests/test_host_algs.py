@@ -113,3 +113,34 @@ def test_forced_alg(coll, alg):
             for count in (1, 24, 5000):
                 check_coll(team, coll, n, count)
             team.destroy()
+
+
+def test_tl_coll_plugin_example(monkeypatch):
+    """tl/shm algorithm plugin (libucc_tlcp_shm_example.so): with a score above the TL's own it takes the allreduce ranges,
+    what it declines (AVG) falls back to the built-in algorithms."""
+    import ctypes as C
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    plugin = os.path.join(root, "ucc_b200", "lib", "ucc", "libucc_tlcp_shm_example.so")
+    if not os.path.exists(plugin):
+        pytest.skip("plugin not built")
+    code = (
+        "import ctypes as C, numpy as np\n"
+        "from ucc_b200 import capi as U\n"
+        "from ucc_b200.harness import UccJob, coll_args\n"
+        "j = UccJob(4); t = j.create_team()\n"
+        f"calls = C.c_int.in_dll(C.CDLL({plugin!r}), 'ucc_tlcp_shm_example_calls')\n"
+        "for op, exp in (('sum', 10), ('max', 4), ('avg', 2.5)):\n"
+        "    s = [np.full(100, r + 1, np.float64) for r in range(4)]; d = [np.zeros(100) for _ in range(4)]\n"
+        "    before = calls.value\n"
+        "    q = t.coll([coll_args('allreduce', s[r], d[r], dt='float64', op=op) for r in range(4)]); assert q.run() == 0; q.finalize()\n"
+        "    assert all(np.allclose(x, exp) for x in d), (op, d[0][:3])\n"
+        "    print(op, calls.value - before)\n")
+    for score, expect in (("100", {"sum": 4, "max": 4, "avg": 0}), ("0", {"sum": 0, "max": 0, "avg": 0})):
+        env = dict(os.environ, PYTHONPATH=root, UCC_TLCP_SHM_EXAMPLE_SCORE=score)
+        out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
+        assert out.returncode == 0, out.stderr[-2000:]
+        got = dict((ln.split()[0], int(ln.split()[1])) for ln in out.stdout.splitlines() if ln and ln.split()[0] in expect)
+        assert got == expect, (score, out.stdout)
