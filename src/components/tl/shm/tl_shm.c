@@ -14,7 +14,9 @@ static ucc_config_field_t tl_shm_context_config_table[] = {
     {"", "", NULL, ucc_offsetof(ucc_tl_shm_context_config_t, super), UCC_CONFIG_TYPE_TABLE(ucc_tl_context_config_table)},
     {"N_CELLS", "256", "Depth of the per-context receive ring (rounded up to a power of two)", ucc_offsetof(ucc_tl_shm_context_config_t, n_cells), UCC_CONFIG_TYPE_UINT},
     {"CELL_SIZE", "8K", "Eager payload carried by one ring cell", ucc_offsetof(ucc_tl_shm_context_config_t, cell_payload), UCC_CONFIG_TYPE_MEMUNITS},
-    {"RNDV_THRESH", "16K", "Messages of at least this size between contexts of one process are copied directly from the source buffer (zero copy)",
+    {"CMA", "try", "Cross-memory attach (process_vm_readv) rendezvous between processes of one host: large host messages are copied once, straight from the sender's buffer",
+     ucc_offsetof(ucc_tl_shm_context_config_t, cma), UCC_CONFIG_TYPE_TERNARY},
+    {"RNDV_THRESH", "16K", "Messages of at least this size are copied directly from the source buffer (same process: always; other processes: through CMA)",
      ucc_offsetof(ucc_tl_shm_context_config_t, rndv_thresh), UCC_CONFIG_TYPE_MEMUNITS},
     {"ALLREDUCE_KN_RADIX", "auto", "Radix of the recursive k-nomial allreduce (per msg range)", ucc_offsetof(ucc_tl_shm_context_config_t, allreduce_kn_radix), UCC_CONFIG_TYPE_UINT_RANGED},
     {"BCAST_KN_RADIX", "auto", "Radix of the k-nomial tree bcast", ucc_offsetof(ucc_tl_shm_context_config_t, bcast_kn_radix), UCC_CONFIG_TYPE_UINT_RANGED},

@@ -50,9 +50,11 @@ typedef struct shm_ring_hdr {
 #define SHM_CELL_PAYLOAD(_c) ((void *)((shm_cell_hdr_t *)(_c) + 1))
 
 /* address published through the core address exchange */
-typedef struct ucc_tl_shm_addr { uint64_t ep_id; uint64_t host_hash; int32_t pid; uint32_t n_cells, cell_size; char name[UCC_TL_SHM_NAME_MAX]; } ucc_tl_shm_addr_t;
+typedef struct ucc_tl_shm_addr { uint64_t ep_id; uint64_t host_hash; int32_t pid; uint32_t n_cells, cell_size; char name[UCC_TL_SHM_NAME_MAX];
+                                 uint64_t probe_addr, probe_val; /* a word in the owner's address space: peers verify cross-memory-attach with it */ } ucc_tl_shm_addr_t;
 
-typedef struct ucc_tl_shm_ep { ucc_tl_shm_addr_t addr; shm_ring_hdr_t *ring; size_t map_len; int same_process; } ucc_tl_shm_ep_t;
+typedef struct ucc_tl_shm_ep { ucc_tl_shm_addr_t addr; shm_ring_hdr_t *ring; size_t map_len; int same_process;
+                               int cma_ok; /* process_vm_readv() into the peer works: large host messages are read in one copy */ } ucc_tl_shm_ep_t;
 
 /* ---- config ---- */
 typedef struct ucc_tl_shm_lib_config { ucc_tl_lib_config_t super; } ucc_tl_shm_lib_config_t;
@@ -60,7 +62,8 @@ typedef struct ucc_tl_shm_context_config {
     ucc_tl_context_config_t super;
     unsigned  n_cells;           /* ring depth (power of two) */
     size_t    cell_payload;      /* eager payload per cell */
-    size_t    rndv_thresh;       /* same-process zero-copy threshold */
+    size_t    rndv_thresh;       /* rendezvous (single copy) threshold: same process, or other processes through CMA */
+    int       cma;               /* ternary: cross-memory-attach rendezvous between processes */
     ucc_mrange_uint_t allreduce_kn_radix, bcast_kn_radix, reduce_kn_radix, barrier_kn_radix, allgather_kn_radix, gather_kn_radix;
     unsigned  alltoall_pairwise_num_posts;
     int       reduce_avg_pre_op;

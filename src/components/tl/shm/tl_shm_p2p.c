@@ -3,6 +3,8 @@
 #include "tl_shm.h"
 #include "utils/ucc_sys.h"
 #include <unistd.h>
+#include <sys/uio.h>
+#include <sys/prctl.h>
 
 #define CTX_LOCK(_c)   do { if ((_c)->tm == UCC_THREAD_MULTIPLE) ucc_recursive_spin_lock(&(_c)->lock); } while (0)
 #define CTX_UNLOCK(_c) do { if ((_c)->tm == UCC_THREAD_MULTIPLE) ucc_recursive_spin_unlock(&(_c)->lock); } while (0)
@@ -12,6 +14,31 @@ static inline void shm_copy(void *dst, const void *src, size_t len, ucc_memory_t
     if (!len) return;
     if (dmt == UCC_MEMORY_TYPE_HOST && smt == UCC_MEMORY_TYPE_HOST) memcpy(dst, src, len);
     else ucc_mc_memcpy(dst, src, len, dmt, smt);
+}
+
+/* cross-memory attach: read `len` bytes at `remote` of process `pid` into local host memory */
+static uint64_t cma_probe_word = 0x75636362323030ull; /* the word peers read to verify that CMA works */
+static int cma_read(int pid, void *local, const void *remote, size_t len)
+{
+    size_t done = 0;
+    while (done < len) {
+        struct iovec l = {(char *)local + done, len - done}, r = {(char *)(uintptr_t)remote + done, len - done};
+        ssize_t n = process_vm_readv((pid_t)pid, &l, 1, &r, 1, 0);
+        if (n <= 0) return -1;
+        done += (size_t)n;
+    }
+    return 0;
+}
+/* payload of a rendezvous: the source lives in this process (plain copy) or in a peer process (CMA, host memory only) */
+static void rndv_fetch(ucc_tl_shm_context_t *ctx, ucc_tl_shm_ep_t *ep, void *dst, ucc_memory_type_t dmt, const void *src, ucc_memory_type_t smt, size_t len)
+{
+    if (!len) return;
+    if (ep->same_process) { shm_copy(dst, src, len, dmt, smt); return; }
+    if (dmt == UCC_MEMORY_TYPE_HOST) { if (cma_read(ep->addr.pid, dst, src, len)) tl_error(ctx->super.super.lib, "process_vm_readv from pid %d failed: %m", ep->addr.pid); return; }
+    { void *tmp = malloc(len); /* device destination: bounce through host memory */
+      if (!tmp || cma_read(ep->addr.pid, tmp, src, len)) tl_error(ctx->super.super.lib, "process_vm_readv from pid %d failed: %m", ep->addr.pid);
+      else shm_copy(dst, tmp, len, dmt, UCC_MEMORY_TYPE_HOST);
+      free(tmp); }
 }
 
 ucc_status_t ucc_tl_shm_ctx_p2p_init(ucc_tl_shm_context_t *ctx)
@@ -28,6 +55,10 @@ ucc_status_t ucc_tl_shm_ctx_p2p_init(ucc_tl_shm_context_t *ctx)
     ctx->addr.pid = (int32_t)getpid(); ctx->addr.host_hash = ucc_sys_host_hash(); /* physical host: an injected (synthetic) placement only shapes the topology */
     ctx->addr.n_cells = n_cells; ctx->addr.cell_size = (uint32_t)cell_size;
     ctx->addr.ep_id = ucc_hash_mix(((uint64_t)(uint32_t)ctx->addr.pid << 32 | my_seq) ^ ucc_sys_host_hash());
+    ctx->addr.probe_addr = (uint64_t)(uintptr_t)&cma_probe_word; ctx->addr.probe_val = cma_probe_word;
+#ifdef PR_SET_PTRACER
+    if (ctx->cfg.cma != UCC_NO) prctl(PR_SET_PTRACER, PR_SET_PTRACER_ANY, 0, 0, 0); /* yama ptrace_scope=1: let the peers read my buffers */
+#endif
     snprintf(ctx->addr.name, sizeof(ctx->addr.name), "/ucc_b200.%d.%u.%llx", (int)getpid(), my_seq, (unsigned long long)(ctx->addr.ep_id & 0xffffff));
     st = ucc_shm_create(ctx->addr.name, ctx->ring_len, (void **)&ctx->ring);
     if (st != UCC_OK) { ucc_shm_unlink(ctx->addr.name); st = ucc_shm_create(ctx->addr.name, ctx->ring_len, (void **)&ctx->ring); }
@@ -71,6 +102,11 @@ static ucc_status_t ep_from_addr(ucc_tl_shm_context_t *ctx, const ucc_tl_shm_add
             ucc_status_t st = ucc_shm_attach(addr->name, ep->map_len, (void **)&ep->ring);
             if (st != UCC_OK) { tl_error(ctx->super.super.lib, "failed to attach to peer segment %s", addr->name); free(ep); return UCC_ERR_NO_RESOURCE; }
             if (ep->ring->magic != SHM_RING_MAGIC) { ucc_shm_detach(ep->ring, ep->map_len); free(ep); return UCC_ERR_NO_RESOURCE; }
+            if (!ep->same_process && ctx->cfg.cma != UCC_NO && addr->probe_addr) { /* can I read the peer's memory? (assumed symmetric) */
+                uint64_t v = 0;
+                ep->cma_ok = cma_read(addr->pid, &v, (const void *)(uintptr_t)addr->probe_addr, sizeof(v)) == 0 && v == addr->probe_val;
+                if (!ep->cma_ok && ctx->cfg.cma == UCC_YES) tl_warn(ctx->super.super.lib, "cross-memory attach to pid %d is not permitted: large messages use the copy-in/copy-out ring", addr->pid);
+            }
         }
         ucc_hash_put(&ctx->eps, addr->ep_id, ep);
     }
@@ -159,7 +195,7 @@ ucc_status_t ucc_tl_shm_send_nb(ucc_tl_shm_team_t *team, ucc_rank_t dst, uint64_
     r = (shm_req_t *)ucc_mpool_get(&ctx->req_mp);
     if (!r) return UCC_ERR_NO_MEMORY;
     r->is_send = 1; r->done = 0; r->tag = tag; r->peer_ep = ep->addr.ep_id; r->buf = buf; r->len = len; r->progressed = 0; r->mt = mt; r->ep = ep;
-    r->rndv = (ep->same_process && len >= ctx->cfg.rndv_thresh);
+    r->rndv = len >= ctx->cfg.rndv_thresh && (ep->same_process || (ep->cma_ok && mt == UCC_MEMORY_TYPE_HOST));
     CTX_LOCK(ctx);
     if (ucc_list_is_empty(&ctx->pending_sends)) send_push(ctx, r); /* keep per-destination FIFO order simple: never overtake */
     if (r->rndv) ucc_list_add_tail(r->progressed ? &ctx->rndv_sends : &ctx->pending_sends, &r->list);
@@ -191,7 +227,7 @@ ucc_status_t ucc_tl_shm_recv_nb(ucc_tl_shm_team_t *team, ucc_rank_t src, uint64_
     if (u) {
         if (u->total_len > len) tl_error(UCC_TL_TEAM_LIB(team), "message truncated: incoming %llu bytes, receive buffer %zu", (unsigned long long)u->total_len, len);
         if (u->is_rts) {
-            shm_copy(buf, u->rts_ptr, ucc_min((size_t)u->total_len, len), mt, (ucc_memory_type_t)u->rts_mt);
+            rndv_fetch(ctx, ep, buf, mt, u->rts_ptr, (ucc_memory_type_t)u->rts_mt, ucc_min((size_t)u->total_len, len));
             send_ack(ctx, ep, u->rts_cookie);
             r->progressed = u->total_len; r->done = 1;
         } else {
@@ -222,7 +258,7 @@ static void handle_cell(ucc_tl_shm_context_t *ctx, shm_cell_hdr_t *c)
     ucc_list_for_each(r, &ctx->posted_recvs, list) {
         if (r->peer_ep != c->src_ep || r->tag != c->tag) continue;
         if (c->type == SHM_CELL_RTS) {
-            shm_copy(r->buf, (void *)(uintptr_t)c->offset, ucc_min((size_t)c->total_len, r->len), r->mt, (ucc_memory_type_t)c->src_mt);
+            rndv_fetch(ctx, r->ep, r->buf, r->mt, (void *)(uintptr_t)c->offset, (ucc_memory_type_t)c->src_mt, ucc_min((size_t)c->total_len, r->len));
             send_ack(ctx, r->ep, c->cookie);
             r->progressed = c->total_len;
         } else {
