@@ -41,8 +41,10 @@ static const shm_alg_t algs_allgather[] = {A("knomial", "recursive doubling", al
                                            A("bruck", "O(log N) Bruck allgather", allgather_bruck), A("sparbit", "O(log N) data-locality aware allgather", allgather_sparbit),
                                            A("linear", "everyone sends to everyone", allgather_linear), A("batched", "linear with bounded outstanding messages", allgather_batched), {NULL}};
 static const shm_alg_t algs_allgatherv[] = {A("ring", "ring", allgatherv_ring), A("knomial", "direct exchange for small messages", allgatherv_knomial), A("linear", "everyone sends to everyone", allgatherv_linear), {NULL}};
-static const shm_alg_t algs_alltoall[] = {A("pairwise", "pairwise exchange", alltoall_pairwise), A("bruck", "O(log N) Bruck alltoall", alltoall_bruck), {NULL}};
-static const shm_alg_t algs_alltoallv[] = {A("pairwise", "pairwise exchange", alltoallv_pairwise), A("hybrid", "pairwise exchange (alias kept for TUNE compatibility)", alltoallv_pairwise), {NULL}};
+static const shm_alg_t algs_alltoall[] = {A("pairwise", "pairwise exchange", alltoall_pairwise), A("bruck", "O(log N) Bruck alltoall", alltoall_bruck),
+                                          A("onesided", "every rank reads its blocks directly from the peers' source buffers (pointer / CMA)", alltoall_onesided), {NULL}};
+static const shm_alg_t algs_alltoallv[] = {A("pairwise", "pairwise exchange", alltoallv_pairwise), A("hybrid", "pairwise exchange (alias kept for TUNE compatibility)", alltoallv_pairwise),
+                                           A("onesided", "every rank reads its blocks directly from the peers' source buffers (pointer / CMA)", alltoallv_onesided), {NULL}};
 static const shm_alg_t algs_barrier[] = {A("knomial", "k-nomial fanin + fanout", barrier_knomial), {NULL}};
 static const shm_alg_t algs_bcast[] = {A("knomial", "k-nomial tree", bcast_knomial), A("sag_knomial", "scatter + ring allgather", bcast_sag), A("dbt", "double binary tree", bcast_dbt), {NULL}};
 static const shm_alg_t algs_fanin[] = {A("knomial", "k-nomial tree", fanin_knomial), {NULL}};

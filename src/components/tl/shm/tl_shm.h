@@ -122,6 +122,8 @@ ucc_status_t ucc_tl_shm_get_ep(ucc_tl_shm_team_t *team, ucc_rank_t team_rank, uc
 ucc_status_t ucc_tl_shm_send_nb(ucc_tl_shm_team_t *team, ucc_rank_t dst, uint64_t tag, void *buf, size_t len, ucc_memory_type_t mt, shm_req_t **req);
 ucc_status_t ucc_tl_shm_recv_nb(ucc_tl_shm_team_t *team, ucc_rank_t src, uint64_t tag, void *buf, size_t len, ucc_memory_type_t mt, shm_req_t **req);
 void         ucc_tl_shm_req_free(ucc_tl_shm_context_t *ctx, shm_req_t *req);
+int          ucc_tl_shm_can_get(ucc_tl_shm_team_t *team, ucc_rank_t rank); /* direct (one-sided) reads from that rank's memory possible? */
+ucc_status_t ucc_tl_shm_get(ucc_tl_shm_team_t *team, ucc_rank_t rank, void *dst, ucc_memory_type_t dmt, uint64_t remote_addr, size_t len);
 ucc_status_t ucc_tl_shm_progress(void *ctx); /* registered with the core context */
 
 extern ucc_tl_iface_t ucc_tl_shm;

@@ -648,6 +648,40 @@ err:
 }
 ucc_status_t ucc_tl_shm_alltoall_pairwise(ucc_tl_shm_task_t *t) { return a2a_common(t, 0); }
 ucc_status_t ucc_tl_shm_alltoallv_pairwise(ucc_tl_shm_task_t *t) { return a2a_common(t, 1); }
+
+/* one-sided alltoall(v) (role of reference tl/ucp alltoall_onesided.c / alltoallv_onesided.c, which put into registered
+ * memory): every rank tells each peer where that peer's block starts, then READS its blocks straight out of the peers'
+ * source buffers (pointer inside one process, process_vm_readv across processes) and finally confirms to each peer that
+ * its buffer is no longer needed.  One copy per block, no intermediate cells; host memory only. */
+static ucc_status_t a2a_onesided(ucc_tl_shm_task_t *t, int is_v)
+{
+    ucc_coll_args_t *a = ARGS(t); ucc_rank_t N = t->vsize, r = t->vrank; const int inplace = 0;
+    size_t sdt, ddt; ucc_memory_type_t smt, dmt; char *src, *dst; ucc_status_t st = UCC_OK; void *sv; uint64_t *out, *in; char *tok;
+    if (UCC_IS_INPLACE(*a)) return UCC_ERR_NOT_SUPPORTED;
+    if (is_v) { sdt = ucc_dt_size(a->src.info_v.datatype); ddt = ucc_dt_size(a->dst.info_v.datatype); smt = a->src.info_v.mem_type; dmt = a->dst.info_v.mem_type; src = (char *)a->src.info_v.buffer; dst = (char *)a->dst.info_v.buffer; }
+    else { sdt = ucc_dt_size(a->src.info.datatype); ddt = ucc_dt_size(a->dst.info.datatype); smt = a->src.info.mem_type; dmt = a->dst.info.mem_type; src = (char *)a->src.info.buffer; dst = (char *)a->dst.info.buffer; }
+    if (smt != UCC_MEMORY_TYPE_HOST || dmt != UCC_MEMORY_TYPE_HOST) return UCC_ERR_NOT_SUPPORTED;
+    for (ucc_rank_t p = 0; p < N; p++) if (p != r && !ucc_tl_shm_can_get(t->team, ucc_ep_map_eval(t->vmap, p))) return UCC_ERR_NOT_SUPPORTED;
+    CHK(shm_task_scratch(t, (size_t)N * 18, UCC_MEMORY_TYPE_HOST, &sv));
+    out = (uint64_t *)sv; in = out + N; tok = (char *)(in + N);
+    for (ucc_rank_t p = 0; p < N; p++) {
+        if (p == r) continue;
+        out[p] = (uint64_t)(uintptr_t)(src + SOFF(p)); tok[p] = 1;
+        CHK(shm_prog_send(t, p, &out[p], 8, UCC_MEMORY_TYPE_HOST, 1)); CHK(shm_prog_recv(t, p, &in[p], 8, UCC_MEMORY_TYPE_HOST, 1));
+    }
+    CHK(shm_prog_copy(t, dst + DOFF(r), src + SOFF(r), ucc_min(SCNT(r), DCNT(r)), dmt, smt));
+    CHK(shm_prog_wait(t));
+    for (ucc_rank_t s = 1; s < N; s++) { ucc_rank_t p = (r + s) % N; CHK(shm_prog_get(t, p, dst + DOFF(p), &in[p], DCNT(p), dmt)); }
+    for (ucc_rank_t p = 0; p < N; p++) { /* "I have read your buffer" in both directions */
+        if (p == r) continue;
+        CHK(shm_prog_send(t, p, &tok[p], 1, UCC_MEMORY_TYPE_HOST, 2)); CHK(shm_prog_recv(t, p, &tok[N + p], 1, UCC_MEMORY_TYPE_HOST, 2));
+    }
+    CHK(shm_prog_wait(t));
+err:
+    return st;
+}
+ucc_status_t ucc_tl_shm_alltoall_onesided(ucc_tl_shm_task_t *t) { return a2a_onesided(t, 0); }
+ucc_status_t ucc_tl_shm_alltoallv_onesided(ucc_tl_shm_task_t *t) { return a2a_onesided(t, 1); }
 /* Bruck alltoall: log2(N) rounds, each moving the blocks whose index has bit k set (latency optimal for small blocks) */
 ucc_status_t ucc_tl_shm_alltoall_bruck(ucc_tl_shm_task_t *t)
 {

@@ -132,6 +132,21 @@ ucc_status_t ucc_tl_shm_get_ep(ucc_tl_shm_team_t *team, ucc_rank_t rank, ucc_tl_
     return st;
 }
 
+/* one-sided access (the "onesided" algorithms): can this context read the memory of team rank `rank` directly? */
+int ucc_tl_shm_can_get(ucc_tl_shm_team_t *team, ucc_rank_t rank)
+{
+    ucc_tl_shm_ep_t *ep;
+    return ucc_tl_shm_get_ep(team, rank, &ep) == UCC_OK && (ep->same_process || ep->cma_ok);
+}
+ucc_status_t ucc_tl_shm_get(ucc_tl_shm_team_t *team, ucc_rank_t rank, void *dst, ucc_memory_type_t dmt, uint64_t remote_addr, size_t len)
+{
+    ucc_tl_shm_ep_t *ep;
+    UCC_CHECK_RET(ucc_tl_shm_get_ep(team, rank, &ep));
+    if (!ep->same_process && !ep->cma_ok) return UCC_ERR_NOT_SUPPORTED;
+    rndv_fetch(SHM_CTX(team), ep, dst, dmt, (const void *)(uintptr_t)remote_addr, UCC_MEMORY_TYPE_HOST, len);
+    return UCC_OK;
+}
+
 /* reserve one cell in `ring`; NULL when full */
 static inline shm_cell_hdr_t *ring_reserve(shm_ring_hdr_t *ring, uint64_t *pos_p)
 {

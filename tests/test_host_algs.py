@@ -10,8 +10,8 @@ ALGS = {
     "allreduce": ["knomial", "sra_knomial", "dbt", "ring"],
     "allgather": ["knomial", "ring", "neighbor", "bruck", "sparbit", "linear", "batched"],
     "allgatherv": ["ring", "knomial", "linear"],
-    "alltoall": ["pairwise", "bruck"],
-    "alltoallv": ["pairwise", "hybrid"],
+    "alltoall": ["pairwise", "bruck", "onesided"],
+    "alltoallv": ["pairwise", "hybrid", "onesided"],
     "bcast": ["knomial", "sag_knomial", "dbt"],
     "reduce": ["knomial", "dbt", "srg"],
     "reduce_scatter": ["ring", "knomial"],
