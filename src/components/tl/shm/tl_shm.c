@@ -36,7 +36,8 @@ static ucc_config_field_t tl_shm_context_config_table[] = {
 typedef struct shm_alg { const char *name; const char *desc; ucc_tl_shm_alg_fn_t fn; } shm_alg_t;
 #define A(_n, _d, _f) {_n, _d, ucc_tl_shm_##_f}
 static const shm_alg_t algs_allreduce[] = {A("knomial", "recursive k-nomial exchange (latency)", allreduce_knomial), A("sra_knomial", "scatter-reduce by vector halving + allgather by doubling (bandwidth)", allreduce_sra),
-                                           A("dbt", "double binary tree reduce + bcast", allreduce_dbt), A("ring", "ring reduce-scatter + ring allgather", allreduce_ring), {NULL}};
+                                           A("dbt", "double binary tree reduce + bcast", allreduce_dbt), A("ring", "ring reduce-scatter + ring allgather", allreduce_ring),
+                                           A("sliding_window", "one-sided: windows of the own slice are read from the peers' buffers (pointer / CMA) and reduced", allreduce_sliding_window), {NULL}};
 static const shm_alg_t algs_allgather[] = {A("knomial", "recursive doubling", allgather_knomial), A("ring", "ring", allgather_ring), A("neighbor", "neighbor exchange (even team size)", allgather_neighbor),
                                            A("bruck", "O(log N) Bruck allgather", allgather_bruck), A("sparbit", "O(log N) data-locality aware allgather", allgather_sparbit),
                                            A("linear", "everyone sends to everyone", allgather_linear), A("batched", "linear with bounded outstanding messages", allgather_batched), {NULL}};

@@ -243,6 +243,49 @@ ucc_status_t ucc_tl_shm_allreduce_ring(ucc_tl_shm_task_t *t)
 err:
     return st;
 }
+/* one-sided "sliding window" allreduce (role of reference tl/ucp allreduce_sliding_window.c, which gets/puts registered
+ * memory): rank r owns slice r; it READS window after window of that slice from every peer's source buffer (pointer / CMA),
+ * reduces into its dst, and after a token exchange reads the other finished slices out of the peers' dst buffers. */
+ucc_status_t ucc_tl_shm_allreduce_sliding_window(ucc_tl_shm_task_t *t)
+{
+    ucc_coll_args_t *a = ARGS(t);
+    size_t count = a->dst.info.count, dts = ucc_dt_size(a->dst.info.datatype), win = (512u << 10) / dts, mo, mc;
+    ucc_memory_type_t mt = a->dst.info.mem_type; ucc_rank_t N = t->vsize, r = t->vrank;
+    char *dst = (char *)a->dst.info.buffer, *src = UCC_IS_INPLACE(*a) ? dst : (char *)a->src.info.buffer, *tok;
+    void *sv, *scratch; uint64_t *out, *in; ucc_status_t st;
+    if (mt != UCC_MEMORY_TYPE_HOST || (!UCC_IS_INPLACE(*a) && a->src.info.mem_type != mt) || count < N) return UCC_ERR_NOT_SUPPORTED;
+    for (ucc_rank_t p = 0; p < N; p++) if (p != r && !ucc_tl_shm_can_get(t->team, ucc_ep_map_eval(t->vmap, p))) return UCC_ERR_NOT_SUPPORTED;
+    if (!win) win = 1;
+    CHK(shm_task_scratch(t, (size_t)N * 48, UCC_MEMORY_TYPE_HOST, &sv)); CHK(shm_task_scratch(t, win * dts, mt, &scratch));
+    out = (uint64_t *)sv; in = out + 2; tok = (char *)(in + 2 * N); /* out: my {src, dst}; in[2p], in[2p+1]: peer p's; tok: 4N bytes */
+    out[0] = (uint64_t)(uintptr_t)src; out[1] = (uint64_t)(uintptr_t)dst;
+    for (ucc_rank_t p = 0; p < N; p++) { if (p == r) continue; CHK(shm_prog_send(t, p, out, 16, UCC_MEMORY_TYPE_HOST, 1)); CHK(shm_prog_recv(t, p, &in[2 * p], 16, UCC_MEMORY_TYPE_HOST, 1)); }
+    CHK(shm_prog_wait(t));
+    mo = ucc_buffer_block_offset(count, N, r); mc = ucc_buffer_block_count(count, N, r);
+    /* scatter-reduce of my slice, one window at a time (the peers' base addresses arrive at run time: GET steps carry
+     * "slot holding the base" + byte offset) */
+    for (size_t wo = 0; wo < mc; wo += win) {
+        size_t wc = ucc_min(win, mc - wo);
+        if (src != dst) CHK(shm_prog_copy(t, dst + (mo + wo) * dts, src + (mo + wo) * dts, wc * dts, mt, mt));
+        for (ucc_rank_t s = 1; s < N; s++) {
+            ucc_rank_t p = (r + s) % N;
+            CHK(shm_prog_get_off(t, p, scratch, &in[2 * p], (mo + wo) * dts, wc * dts, mt));
+            CHK(shm_prog_reduce(t, dst + (mo + wo) * dts, dst + (mo + wo) * dts, scratch, wc, mt, 0));
+        }
+        if (t->op == UCC_OP_AVG) CHK(shm_prog_reduce(t, dst + (mo + wo) * dts, dst + (mo + wo) * dts, NULL, wc, mt, 1));
+    }
+    /* everybody's slice is final once all tokens of step 2 are here */
+    for (ucc_rank_t p = 0; p < N; p++) { if (p == r) continue; tok[p] = 1; CHK(shm_prog_send(t, p, &tok[p], 1, UCC_MEMORY_TYPE_HOST, 2)); CHK(shm_prog_recv(t, p, &tok[N + p], 1, UCC_MEMORY_TYPE_HOST, 2)); }
+    CHK(shm_prog_wait(t));
+    for (ucc_rank_t s = 1; s < N; s++) {
+        ucc_rank_t p = (r + s) % N; size_t po = ucc_buffer_block_offset(count, N, p), pc = ucc_buffer_block_count(count, N, p);
+        CHK(shm_prog_get_off(t, p, dst + po * dts, &in[2 * p + 1], po * dts, pc * dts, mt));
+    }
+    for (ucc_rank_t p = 0; p < N; p++) { if (p == r) continue; CHK(shm_prog_send(t, p, &tok[2 * N + p], 1, UCC_MEMORY_TYPE_HOST, 3)); CHK(shm_prog_recv(t, p, &tok[3 * N + p], 1, UCC_MEMORY_TYPE_HOST, 3)); }
+    CHK(shm_prog_wait(t));
+err:
+    return st;
+}
 /* scatter-reduce by recursive vector halving + allgather by recursive doubling (radix 2 SRA) */
 ucc_status_t ucc_tl_shm_allreduce_sra(ucc_tl_shm_task_t *t)
 {

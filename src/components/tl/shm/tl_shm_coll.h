@@ -6,7 +6,7 @@ typedef ucc_status_t (*ucc_tl_shm_alg_fn_t)(ucc_tl_shm_task_t *task);
 #define SHM_ALG(_n) ucc_status_t ucc_tl_shm_##_n(ucc_tl_shm_task_t *t)
 SHM_ALG(barrier_knomial); SHM_ALG(fanin_knomial); SHM_ALG(fanout_knomial);
 SHM_ALG(bcast_knomial); SHM_ALG(bcast_sag); SHM_ALG(bcast_dbt);
-SHM_ALG(allreduce_knomial); SHM_ALG(allreduce_sra); SHM_ALG(allreduce_ring); SHM_ALG(allreduce_dbt);
+SHM_ALG(allreduce_knomial); SHM_ALG(allreduce_sra); SHM_ALG(allreduce_ring); SHM_ALG(allreduce_dbt); SHM_ALG(allreduce_sliding_window);
 SHM_ALG(reduce_knomial); SHM_ALG(reduce_srg); SHM_ALG(reduce_dbt);
 SHM_ALG(reduce_scatter_ring); SHM_ALG(reduce_scatter_knomial); SHM_ALG(reduce_scatterv_ring);
 SHM_ALG(allgather_knomial); SHM_ALG(allgather_ring); SHM_ALG(allgather_neighbor); SHM_ALG(allgather_bruck);

@@ -31,13 +31,15 @@ ucc_status_t shm_prog_copy(ucc_tl_shm_task_t *t, void *dst, const void *src, siz
     op.type = SHM_OP_COPY; op.dst = dst; op.src1 = (void *)src; op.len = len; op.mt = dmt; op.mt_src = smt;
     return op_push(t, &op);
 }
-ucc_status_t shm_prog_get(ucc_tl_shm_task_t *t, ucc_rank_t peer, void *dst, const uint64_t *remote_addr_slot, size_t len, ucc_memory_type_t mt)
+ucc_status_t shm_prog_get_off(ucc_tl_shm_task_t *t, ucc_rank_t peer, void *dst, const uint64_t *remote_addr_slot, size_t off, size_t len, ucc_memory_type_t mt)
 {
     shm_op_t op; memset(&op, 0, sizeof(op));
     if (!len) return UCC_OK;
-    op.type = SHM_OP_GET; op.peer = peer; op.dst = dst; op.src1 = (void *)(uintptr_t)remote_addr_slot; op.len = len; op.mt = mt;
+    op.type = SHM_OP_GET; op.peer = peer; op.dst = dst; op.src1 = (void *)(uintptr_t)remote_addr_slot; op.src2 = (void *)(uintptr_t)off; op.len = len; op.mt = mt;
     return op_push(t, &op);
 }
+ucc_status_t shm_prog_get(ucc_tl_shm_task_t *t, ucc_rank_t peer, void *dst, const uint64_t *remote_addr_slot, size_t len, ucc_memory_type_t mt)
+{ return shm_prog_get_off(t, peer, dst, remote_addr_slot, 0, len, mt); }
 ucc_status_t shm_task_scratch(ucc_tl_shm_task_t *t, size_t len, ucc_memory_type_t mt, void **ptr)
 {
     ucc_status_t st;
@@ -137,7 +139,7 @@ void ucc_tl_shm_task_progress(ucc_coll_task_t *ct)
             break;
         }
         case SHM_OP_GET:
-            st = ucc_tl_shm_get(team, ucc_ep_map_eval(t->vmap, op->peer), op->dst, op->mt, *(const uint64_t *)op->src1, op->len);
+            st = ucc_tl_shm_get(team, ucc_ep_map_eval(t->vmap, op->peer), op->dst, op->mt, *(const uint64_t *)op->src1 + (uint64_t)(uintptr_t)op->src2, op->len);
             if (st != UCC_OK) { ct->status = st; return; }
             t->pc++;
             break;

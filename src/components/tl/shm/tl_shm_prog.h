@@ -54,6 +54,7 @@ ucc_status_t shm_prog_recv(ucc_tl_shm_task_t *t, ucc_rank_t peer, void *buf, siz
 ucc_status_t shm_prog_wait(ucc_tl_shm_task_t *t);
 /* dst <- len bytes at the remote address that will be stored in *remote_addr_slot by the time the step runs */
 ucc_status_t shm_prog_get(ucc_tl_shm_task_t *t, ucc_rank_t peer, void *dst, const uint64_t *remote_addr_slot, size_t len, ucc_memory_type_t mt);
+ucc_status_t shm_prog_get_off(ucc_tl_shm_task_t *t, ucc_rank_t peer, void *dst, const uint64_t *remote_addr_slot, size_t off, size_t len, ucc_memory_type_t mt);
 ucc_status_t shm_prog_reduce(ucc_tl_shm_task_t *t, void *dst, const void *src1, const void *src2, size_t count, ucc_memory_type_t mt, int with_alpha);
 ucc_status_t shm_prog_copy(ucc_tl_shm_task_t *t, void *dst, const void *src, size_t len, ucc_memory_type_t dmt, ucc_memory_type_t smt);
 ucc_status_t shm_task_scratch(ucc_tl_shm_task_t *t, size_t len, ucc_memory_type_t mt, void **ptr);

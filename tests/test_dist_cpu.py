@@ -44,6 +44,6 @@ def test_torchrun_host_onesided_cma():
     """one-sided alltoall between processes: blocks are read with process_vm_readv straight from the peers' buffers."""
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=3", "--master-addr", "127.0.0.1",
            "--master-port", "29611", os.path.join(ROOT, "tests", "dist_worker.py"), "cpu"]
-    env = dict(os.environ, PYTHONPATH=ROOT, CUDA_VISIBLE_DEVICES="", UCC_TL_SHM_TUNE="alltoall:@onesided#alltoallv:@onesided", UCC_TL_SHM_CMA="y")
+    env = dict(os.environ, PYTHONPATH=ROOT, CUDA_VISIBLE_DEVICES="", UCC_TL_SHM_TUNE="alltoall:@onesided#alltoallv:@onesided#allreduce:@sliding_window", UCC_TL_SHM_CMA="y")
     out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert "DIST_WORKER_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]

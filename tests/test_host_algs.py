@@ -7,7 +7,7 @@ from ucc_b200 import capi as U
 from ucc_b200.harness import UccJob, coll_args
 
 ALGS = {
-    "allreduce": ["knomial", "sra_knomial", "dbt", "ring"],
+    "allreduce": ["knomial", "sra_knomial", "dbt", "ring", "sliding_window"],
     "allgather": ["knomial", "ring", "neighbor", "bruck", "sparbit", "linear", "batched"],
     "allgatherv": ["ring", "knomial", "linear"],
     "alltoall": ["pairwise", "bruck", "onesided"],
@@ -144,3 +144,18 @@ def test_tl_coll_plugin_example(monkeypatch):
         assert out.returncode == 0, out.stderr[-2000:]
         got = dict((ln.split()[0], int(ln.split()[1])) for ln in out.stdout.splitlines() if ln and ln.split()[0] in expect)
         assert got == expect, (score, out.stdout)
+
+
+@pytest.mark.parametrize("n", [2, 3, 5])
+def test_sliding_window_multi_window_inplace(n):
+    with UccJob(n, env={"UCC_TL_SHM_TUNE": "allreduce:inf:@sliding_window"}) as job:
+        team = job.create_team()
+        rng = np.random.default_rng(n)
+        count = 400_003                                   # float64: slices of > 1 MB => several 512 KB windows each
+        for inplace in (False, True):
+            src = [rng.random(count) for _ in range(n)]
+            exp = np.sum(src, 0)
+            dst = [s.copy() for s in src] if inplace else [np.zeros(count) for _ in range(n)]
+            run(team, [coll_args("allreduce", None if inplace else src[r], dst[r], dt="float64", op="sum", inplace=inplace) for r in range(n)])
+            for r in range(n):
+                assert np.allclose(dst[r], exp), (inplace, r)
