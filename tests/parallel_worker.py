@@ -9,7 +9,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ucc_b200 import ops  # noqa: E402
 from ucc_b200.dist import init_distributed  # noqa: E402
 from ucc_b200.models import MLP, TPTransformerBlock  # noqa: E402
-from ucc_b200.parallel import DistributedDataParallel, moe_combine, moe_dispatch  # noqa: E402
+from ucc_b200.parallel import DistributedDataParallel, ZeroRedundancyTrainer, moe_combine, moe_dispatch, ring_pass, ulysses_all_to_all  # noqa: E402
 
 
 def main():
@@ -74,6 +74,37 @@ def main():
     if not torch.equal(out, tok * 2.0):
         print(f"rank {rank}: MoE round trip mismatch", flush=True)
         ok = False
+
+    # ---- ZeRO-1: sharded SGD step == plain SGD on the averaged gradient
+    torch.manual_seed(3)
+    zm, rm = MLP(16, 24, 2, 3).to(dev), MLP(16, 24, 2, 3).to(dev)
+    rm.load_state_dict(zm.state_dict())
+    zt = ZeroRedundancyTrainer(zm, torch.optim.SGD, comm=comm, lr=0.1, momentum=0.9)
+    ropt = torch.optim.SGD(rm.parameters(), lr=0.1, momentum=0.9)
+    for step in range(3):
+        zt.zero_grad()
+        torch.nn.functional.mse_loss(zm(xs[rank][:, :16]), ys[rank][:, :3]).backward()
+        zt.step()
+        ropt.zero_grad()
+        sum(torch.nn.functional.mse_loss(rm(xs[r][:, :16]), ys[r][:, :3]) for r in range(world)).div(world).backward()
+        ropt.step()
+    for (n1, p), (_, q) in zip(zm.named_parameters(), rm.named_parameters()):
+        if not torch.allclose(p, q, rtol=1e-4, atol=1e-5):
+            print(f"rank {rank}: ZeRO parameter mismatch {n1}", flush=True)
+            ok = False
+
+    # ---- Ulysses all-to-all: [S/N, H, D] -> [S, H/N, D], and one ring-attention hop
+    S, H, D = 4 * world, 2 * world, 3
+    full = torch.arange(S * H * D, dtype=torch.float32).view(S, H, D).to(dev)
+    mine = full[rank * (S // world):(rank + 1) * (S // world)].contiguous()
+    got = ulysses_all_to_all(mine, scatter_dim=1, gather_dim=0, comm=comm)
+    if not torch.equal(got, full[:, rank * (H // world):(rank + 1) * (H // world)]):
+        print(f"rank {rank}: ulysses mismatch", flush=True)
+        ok = False
+    kv = torch.full((5, 7), float(rank), device=dev)
+    if world % 2 == 0 or world == 1:
+        prev = ring_pass(kv, comm=comm)
+        ok &= bool((prev == float((rank - 1) % world)).all())
 
     flag = torch.tensor([1 if ok else 0])
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)

@@ -118,3 +118,34 @@ def scatter(output, input, src=0, comm=None, async_op=False):
 
 def barrier(comm=None):
     (comm or default_comm()).barrier()
+
+
+# ---- point to point (pipeline / ring-attention shapes): a two-member active-set broadcast, the way ProcessGroupUCC does it
+def _p2p(tensor, src, dst, tag, comm, async_op):
+    req = comm.coll_init("bcast", tensor, None, root=src, active_set=(src, dst - src, 2), tag=int(tag) & 0x3fff)
+    return _launch(comm, req, tensor, async_op)
+
+
+def send(tensor, dst, tag=0, comm=None, async_op=False):
+    comm = comm or default_comm()
+    return _p2p(tensor, comm.rank, dst, tag, comm, async_op)
+
+
+def recv(tensor, src, tag=0, comm=None, async_op=False):
+    comm = comm or default_comm()
+    return _p2p(tensor, src, comm.rank, tag, comm, async_op)
+
+
+def ring_exchange(send_tensor, recv_tensor, shift=1, tag=0, comm=None):
+    """Every rank sends to (rank + shift) and receives from (rank - shift): one hop of ring attention / a pipeline bubble step.
+    Even ranks send first, odd ranks receive first; with an odd ring the last rank pairs up with rank 0 afterwards."""
+    comm = comm or default_comm()
+    n, r = comm.size, comm.rank
+    to, frm = (r + shift) % n, (r - shift) % n
+    if n == 1:
+        recv_tensor.copy_(send_tensor)
+        return
+    w_s = send(send_tensor, to, tag, comm, async_op=True)
+    w_r = recv(recv_tensor, frm, tag, comm, async_op=True)
+    w_s.wait()
+    w_r.wait()
