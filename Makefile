@@ -55,7 +55,7 @@ endif
 TLCP_SRCS := $(wildcard src/components/tl/shm/coll_plugins/*/*.c)
 TLCPS     := $(foreach s,$(TLCP_SRCS),$(MODDIR)/libucc_tlcp_shm_$(notdir $(patsubst %/,%,$(dir $(s)))).so)
 
-.PHONY: all core plugins tools clean sass
+.PHONY: all core plugins tools clean sass asan
 all: core plugins tools
 core: $(OUT)/libucc.so $(TLCPS)
 $(MODDIR)/libucc_tlcp_shm_%.so: src/components/tl/shm/coll_plugins/%/*.c $(OUT)/libucc.so
@@ -107,8 +107,15 @@ sass: plugins
 	  cuobjdump -sass $(MODDIR)/libucc_$$m.so > profiles/sass/$$m.sass 2>/dev/null; \
 	  cuobjdump -ptx $(MODDIR)/libucc_$$m.so > profiles/sass/$$m.ptx 2>/dev/null; fi; done
 
+# AddressSanitizer + UBSan build of the host side (core, tl/shm plugins) into build-asan/; run the suite against it with
+#   LD_PRELOAD=$$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0 UCC_B200_LIB=build-asan/lib/libucc.so pytest ...
+asan:
+	$(MAKE) core CC=/usr/bin/gcc BUILD=build-asan/obj OUT=build-asan/lib BINDIR=build-asan/bin \
+	  EXTRA_CFLAGS="-fsanitize=address,undefined -fno-sanitize=alignment -fno-omit-frame-pointer -O1" \
+	  LDFLAGS="-shared -fsanitize=address,undefined -lpthread -ldl -lrt -lm"
+
 clean:
-	rm -rf $(BUILD) $(OUT) $(BINDIR)
+	rm -rf $(BUILD) $(OUT) $(BINDIR) build-asan
 
 -include $(CORE_OBJS:.o=.d)
 -include $(shell find $(BUILD) -name '*.d' 2>/dev/null)

@@ -325,7 +325,7 @@ ucc_status_t ucc_context_create_proc_info(ucc_lib_h lib, const ucc_context_param
     for (int i = 0; i < config->n_cl_cfg; i++) {
         ucc_cl_lib_t *cl_lib = config->cl_cfgs[i]->cl_lib;
         ucc_base_context_t *b_ctx = NULL;
-        ucc_base_lib_attr_t lattr;
+        ucc_cl_lib_attr_t lattr; /* CL get_attr fills the CL-sized structure */
         st = cl_lib->iface->context.create(&bp, &config->cl_cfgs[i]->super, &b_ctx);
         if (st != UCC_OK) {
             if (lib->specific_cls_requested) { ucc_error("failed to create cl context for %s", cl_lib->iface->super.name); goto err_cl; }
@@ -333,8 +333,8 @@ ucc_status_t ucc_context_create_proc_info(ucc_lib_h lib, const ucc_context_param
             continue;
         }
         memset(&lattr, 0, sizeof(lattr));
-        cl_lib->iface->lib.get_attr(&cl_lib->super, &lattr);
-        ctx->cl_flags |= lattr.flags;
+        cl_lib->iface->lib.get_attr(&cl_lib->super, &lattr.super);
+        ctx->cl_flags |= lattr.super.flags;
         ctx->cl_ctx[ctx->n_cl_ctx++] = ucc_derived_of(b_ctx, ucc_cl_context_t);
     }
     if (ctx->n_cl_ctx == 0) { ucc_error("no CL context created in ucc_context_create"); st = UCC_ERR_NO_MESSAGE; goto err_cl; }

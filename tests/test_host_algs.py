@@ -123,7 +123,8 @@ def test_tl_coll_plugin_example(monkeypatch):
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    plugin = os.path.join(root, "ucc_b200", "lib", "ucc", "libucc_tlcp_shm_example.so")
+    libdir = os.path.dirname(os.environ.get("UCC_B200_LIB") or os.path.join(root, "ucc_b200", "lib", "libucc.so"))
+    plugin = os.path.join(libdir, "ucc", "libucc_tlcp_shm_example.so")
     if not os.path.exists(plugin):
         pytest.skip("plugin not built")
     code = (

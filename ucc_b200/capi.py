@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libucc.so")
+# UCC_B200_LIB points the binding at another build of the library (e.g. the ASAN one from `make asan`)
+LIB_PATH = os.environ.get("UCC_B200_LIB") or os.path.join(_HERE, "lib", "libucc.so")
 
 
 def _load():
