@@ -55,7 +55,7 @@ endif
 TLCP_SRCS := $(wildcard src/components/tl/shm/coll_plugins/*/*.c)
 TLCPS     := $(foreach s,$(TLCP_SRCS),$(MODDIR)/libucc_tlcp_shm_$(notdir $(patsubst %/,%,$(dir $(s)))).so)
 
-.PHONY: all core plugins tools clean sass asan
+.PHONY: all core plugins tools clean sass asan tsan
 all: core plugins tools
 core: $(OUT)/libucc.so $(TLCPS)
 $(MODDIR)/libucc_tlcp_shm_%.so: src/components/tl/shm/coll_plugins/%/*.c $(OUT)/libucc.so
@@ -114,8 +114,13 @@ asan:
 	  EXTRA_CFLAGS="-fsanitize=address,undefined -fno-sanitize=alignment -fno-omit-frame-pointer -O1" \
 	  LDFLAGS="-shared -fsanitize=address,undefined -lpthread -ldl -lrt -lm"
 
+# ThreadSanitizer build (THREAD_MULTIPLE paths): LD_PRELOAD=$$(gcc -print-file-name=libtsan.so) UCC_B200_LIB=build-tsan/lib/libucc.so
+tsan:
+	$(MAKE) core CC=/usr/bin/gcc BUILD=build-tsan/obj OUT=build-tsan/lib BINDIR=build-tsan/bin \
+	  EXTRA_CFLAGS="-fsanitize=thread -fno-omit-frame-pointer -O1" LDFLAGS="-shared -fsanitize=thread -lpthread -ldl -lrt -lm"
+
 clean:
-	rm -rf $(BUILD) $(OUT) $(BINDIR) build-asan
+	rm -rf $(BUILD) $(OUT) $(BINDIR) build-asan build-tsan
 
 -include $(CORE_OBJS:.o=.d)
 -include $(shell find $(BUILD) -name '*.d' 2>/dev/null)

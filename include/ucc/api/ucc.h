@@ -515,7 +515,12 @@ ucc_status_t ucc_collective_init_and_post(ucc_coll_args_t *coll_args,
 
 static inline ucc_status_t ucc_collective_test(ucc_coll_req_h request)
 {
+#if defined(__GNUC__) || defined(__clang__)
+    /* acquire: the completing thread may differ from the testing one under UCC_THREAD_MULTIPLE */
+    return (ucc_status_t)__atomic_load_n((const volatile int *)&request->status, __ATOMIC_ACQUIRE);
+#else
     return request->status;
+#endif
 }
 
 ucc_status_t ucc_collective_finalize(ucc_coll_req_h request);

@@ -545,7 +545,7 @@ ucc_status_t ucc_coll_init_as(ucc_score_map_t *map, ucc_base_coll_args_t *bargs,
 }
 
 static ucc_coll_score_name_fn_t name_resolver = NULL;
-void ucc_coll_score_set_name_resolver(ucc_coll_score_name_fn_t fn) { name_resolver = fn; }
+void ucc_coll_score_set_name_resolver(ucc_coll_score_name_fn_t fn) { __atomic_store_n(&name_resolver, fn, __ATOMIC_RELAXED); /* every context sets the same function */ }
 
 static const char *init_name(ucc_base_coll_init_fn_t init, ucc_base_team_t *team, char *tmp, size_t max)
 {

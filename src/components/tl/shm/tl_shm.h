@@ -83,6 +83,9 @@ typedef struct shm_req {
     ucc_tl_shm_ep_t   *ep;             /* send: destination */
     int                rndv;           /* send: waiting for ACK */
 } shm_req_t;
+/* `done` is set under the context lock by whoever drains the ring and polled without it by the owning task (THREAD_MULTIPLE) */
+static inline void shm_req_complete(shm_req_t *r) { __atomic_store_n(&r->done, 1, __ATOMIC_RELEASE); }
+static inline int  shm_req_is_done(const shm_req_t *r) { return __atomic_load_n(&r->done, __ATOMIC_ACQUIRE); }
 
 typedef struct shm_unexp { ucc_list_link_t list; uint64_t tag, src_ep, total_len, received; int is_rts; void *rts_ptr; uint64_t rts_cookie; uint16_t rts_mt; void *data; } shm_unexp_t;
 

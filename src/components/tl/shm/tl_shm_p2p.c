@@ -189,7 +189,7 @@ static void send_push(ucc_tl_shm_context_t *ctx, shm_req_t *r)
         ring_publish(c, pos);
         r->progressed += chunk;
     } while (r->progressed < r->len);
-    r->done = 1;
+    shm_req_complete(r);
 }
 
 static void send_ack(ucc_tl_shm_context_t *ctx, ucc_tl_shm_ep_t *ep, uint64_t cookie)
@@ -244,12 +244,12 @@ ucc_status_t ucc_tl_shm_recv_nb(ucc_tl_shm_team_t *team, ucc_rank_t src, uint64_
         if (u->is_rts) {
             rndv_fetch(ctx, ep, buf, mt, u->rts_ptr, (ucc_memory_type_t)u->rts_mt, ucc_min((size_t)u->total_len, len));
             send_ack(ctx, ep, u->rts_cookie);
-            r->progressed = u->total_len; r->done = 1;
+            r->progressed = u->total_len; shm_req_complete(r);
         } else {
             shm_copy(buf, u->data, ucc_min((size_t)u->received, len), mt, UCC_MEMORY_TYPE_HOST);
             r->progressed = u->received;
             r->len = u->total_len < len ? (size_t)u->total_len : len;
-            if (u->received >= u->total_len) r->done = 1;
+            if (u->received >= u->total_len) shm_req_complete(r);
         }
         ucc_list_del(&u->list); free(u->data); free(u);
     }
@@ -267,7 +267,7 @@ static void handle_cell(ucc_tl_shm_context_t *ctx, shm_cell_hdr_t *c)
     shm_unexp_t *u;
     if (c->type == SHM_CELL_ACK) {
         shm_req_t *s = (shm_req_t *)(uintptr_t)c->offset;
-        ucc_list_for_each(r, &ctx->rndv_sends, list) if (r == s) { ucc_list_del(&r->list); r->done = 1; return; }
+        ucc_list_for_each(r, &ctx->rndv_sends, list) if (r == s) { ucc_list_del(&r->list); shm_req_complete(r); return; }
         return;
     }
     ucc_list_for_each(r, &ctx->posted_recvs, list) {
@@ -280,7 +280,7 @@ static void handle_cell(ucc_tl_shm_context_t *ctx, shm_cell_hdr_t *c)
             if (c->offset + c->len <= r->len) shm_copy((char *)r->buf + c->offset, SHM_CELL_PAYLOAD(c), c->len, r->mt, UCC_MEMORY_TYPE_HOST);
             r->progressed += c->len;
         }
-        if (r->progressed >= c->total_len) { ucc_list_del(&r->list); r->done = 1; }
+        if (r->progressed >= c->total_len) { ucc_list_del(&r->list); shm_req_complete(r); }
         return;
     }
     /* nobody waits for it yet: stash */

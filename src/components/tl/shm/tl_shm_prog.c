@@ -115,7 +115,7 @@ void ucc_tl_shm_task_progress(ucc_coll_task_t *ct)
             int all_done = 1;
             if (t->n_reqs) {
                 ucc_tl_shm_progress(ctx);
-                for (unsigned i = 0; i < t->n_reqs; i++) if (!t->reqs[i]->done) { all_done = 0; break; }
+                for (unsigned i = 0; i < t->n_reqs; i++) if (!shm_req_is_done(t->reqs[i])) { all_done = 0; break; }
                 if (!all_done) return;
                 for (unsigned i = 0; i < t->n_reqs; i++) ucc_tl_shm_req_free(ctx, t->reqs[i]);
                 t->n_reqs = 0;

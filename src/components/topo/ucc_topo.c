@@ -148,7 +148,9 @@ static void build_node_nvlink(ucc_topo_t *topo, ucc_sbgp_t *s)
 
 ucc_sbgp_t *ucc_topo_get_sbgp(ucc_topo_t *topo, ucc_sbgp_type_t type)
 {
-    ucc_sbgp_t *s = &topo->sbgps[type];
+    ucc_sbgp_t *s;
+    if ((unsigned)type >= UCC_SBGP_LAST) return NULL;
+    s = &topo->sbgps[type];
     if (s->status != UCC_SBGP_NOT_INIT) return s;
     s->type = type;
     switch (type) {

@@ -312,7 +312,8 @@ UCC_EXPORT ucc_status_t ucc_collective_finalize(ucc_coll_req_h request)
     ucc_status_t st;
     UCC_PROFILE_FUNC_BEGIN("ucc_collective_finalize");
     if (!request) return UCC_ERR_INVALID_PARAM;
-    if (task->super.status == UCC_INPROGRESS) { ucc_error("attempt to finalize an in-progress request"); return UCC_ERR_INVALID_PARAM; }
+    /* acquire: pairs with the release in ucc_task_complete, which may have run on another thread (THREAD_MULTIPLE) */
+    if (ucc_load_acquire((volatile int *)&task->super.status) == UCC_INPROGRESS) { ucc_error("attempt to finalize an in-progress request"); return UCC_ERR_INVALID_PARAM; }
     if (ucc_global_config.coll_trace.log_level >= UCC_LOG_LEVEL_DEBUG && !(task->flags & UCC_COLL_TASK_FLAG_INTERNAL))
         COLL_TRACE(UCC_LOG_LEVEL_DEBUG, "coll_finalize: req %p, seq_num %u", (void *)task, task->seq_num);
     if (task->executor) { ucc_ee_executor_finalize(task->executor); task->executor = NULL; }

@@ -70,12 +70,12 @@ static int mt_progress(ucc_progress_queue_t *pq)
     ucc_coll_task_t *task;
     pq->dequeue(pq, &task);
     if (!task) return 0;
-    if (ucc_pq_progress_one(task)) return ucc_task_complete(task) < 0 ? (int)task->status : 1;
+    if (ucc_pq_progress_one(task)) { ucc_status_t st = ucc_task_complete(task); return st < 0 ? (int)st : 1; } /* the task may already be finalized by its owner */
     pq->enqueue(pq, task);
     return 0;
 }
 static int mt_is_empty(ucc_progress_queue_t *pq)
-{ ucc_pq_mt_t *q = (ucc_pq_mt_t *)pq; return q->lock_free ? 0 /* cannot tell cheaply */ : ucc_list_is_empty(&q->list); }
+{ ucc_pq_mt_t *q = (ucc_pq_mt_t *)pq; int e; if (q->lock_free) return 0; /* cannot tell cheaply */ ucc_spin_lock(&q->lock); e = ucc_list_is_empty(&q->list); ucc_spin_unlock(&q->lock); return e; }
 static void mt_finalize(ucc_progress_queue_t *pq)
 { ucc_pq_mt_t *q = (ucc_pq_mt_t *)pq; if (q->lfq) { ucc_lf_queue_destroy(q->lfq); free(q->lfq); } free(q); }
 

@@ -28,7 +28,7 @@ static inline void ucc_spinlock_init(ucc_spinlock_t *l) { l->v = 0; }
 static inline void ucc_spinlock_destroy(ucc_spinlock_t *l) { (void)l; }
 static inline int  ucc_spin_trylock(ucc_spinlock_t *l) { return !__atomic_exchange_n(&l->v, 1, __ATOMIC_ACQUIRE); }
 static inline void ucc_spin_lock(ucc_spinlock_t *l)
-{ while (!ucc_spin_trylock(l)) { while (l->v) ucc_cpu_relax(); } }
+{ while (!ucc_spin_trylock(l)) { while (__atomic_load_n(&l->v, __ATOMIC_RELAXED)) ucc_cpu_relax(); } }
 static inline void ucc_spin_unlock(ucc_spinlock_t *l) { __atomic_store_n(&l->v, 0, __ATOMIC_RELEASE); }
 
 typedef struct ucc_recursive_spinlock { ucc_spinlock_t l; pthread_t owner; int count; } ucc_recursive_spinlock_t;
@@ -36,11 +36,12 @@ static inline void ucc_recursive_spinlock_init(ucc_recursive_spinlock_t *l) { uc
 static inline void ucc_recursive_spin_lock(ucc_recursive_spinlock_t *l)
 {
     pthread_t self = pthread_self();
-    if (l->count > 0 && pthread_equal(l->owner, self)) { l->count++; return; }
-    ucc_spin_lock(&l->l); l->owner = self; l->count = 1;
+    /* owner is only ever equal to `self` if this thread stored it, so a relaxed read is enough */
+    if (pthread_equal(__atomic_load_n(&l->owner, __ATOMIC_RELAXED), self)) { l->count++; return; }
+    ucc_spin_lock(&l->l); __atomic_store_n(&l->owner, self, __ATOMIC_RELAXED); l->count = 1;
 }
 static inline void ucc_recursive_spin_unlock(ucc_recursive_spinlock_t *l)
-{ if (--l->count == 0) { l->owner = 0; ucc_spin_unlock(&l->l); } }
+{ if (--l->count == 0) { __atomic_store_n(&l->owner, (pthread_t)0, __ATOMIC_RELAXED); ucc_spin_unlock(&l->l); } }
 
 /* lock that degenerates to a no-op for UCC_THREAD_SINGLE */
 typedef struct ucc_tm_lock { int enabled; ucc_spinlock_t l; } ucc_tm_lock_t;

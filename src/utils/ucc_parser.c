@@ -37,8 +37,7 @@ void ucc_config_parser_warn_unused_env_vars_once(void)
     static const char *direct[] = {"UCC_DEBUGGER_WAIT", "UCC_TL_NCCL_LIB", "UCC_MODULE_DIR", NULL}; /* read with getenv() */
     extern char **environ;
     char unused[1024]; size_t len = 0; int n = 0;
-    if (done) return;
-    done = 1;
+    if (__atomic_exchange_n(&done, 1, __ATOMIC_ACQ_REL)) return;
     for (char **e = environ; e && *e; e++) {
         const char *eq = strchr(*e, '='), *p = strstr(*e, "UCC_");
         char name[256]; ucc_config_global_list_entry_t *it; int used = 0;

@@ -305,6 +305,63 @@ def test_thread_multiple_concurrent_progress():
         assert not errs, errs
 
 
+def test_thread_multiple_shared_context_stress():
+    """THREAD_MULTIPLE proper: several threads share one context per rank, each drives its own team (allreduce, alltoall, bcast,
+    barrier mixes) and everybody calls ucc_context_progress on the shared context concurrently."""
+    import threading
+    n, nteams, iters = 3, 3, 25
+    with UccJob(n, thread_mode=U.UCC_THREAD_MULTIPLE) as j:
+        teams = [j.create_team() for _ in range(nteams)]
+        errs = []
+
+        def run_one(r, a):
+            q = C.POINTER(U.ucc_coll_req_t)()
+            U.check(U.ucc_collective_init(C.byref(a), C.byref(q), a._team), "init")
+            U.check(U.ucc_collective_post(q), "post")
+            t0 = time.time()
+            while q.contents.status == U.UCC_INPROGRESS:
+                U.ucc_context_progress(j.procs[r].ctx)
+                if time.time() - t0 > 90:
+                    raise TimeoutError()
+            assert q.contents.status == U.UCC_OK, q.contents.status
+            U.ucc_collective_finalize(q)
+
+        def worker(r, t):
+            try:
+                th = teams[t].members[r].team
+                for k in range(iters):
+                    count = 64 * (1 + (k + t) % 5) * (64 if k % 7 == 0 else 1)
+                    src = np.full(count, r + k + t, np.int32)
+                    dst = np.zeros(count, np.int32)
+                    a = coll_args("allreduce", src, dst, dt="int32")
+                    a._team = th
+                    run_one(r, a)
+                    assert np.all(dst == sum(range(n)) + n * (k + t)), ("allreduce", r, t, k)
+                    s2 = np.repeat(np.arange(n, dtype=np.int64) + 100 * r + k, 16)
+                    d2 = np.zeros(n * 16, np.int64)
+                    a = coll_args("alltoall", s2, d2, dt="int64")
+                    a._team = th
+                    run_one(r, a)
+                    exp = np.repeat(np.array([r + 100 * p + k for p in range(n)], np.int64), 16)
+                    assert np.array_equal(d2, exp), ("alltoall", r, t, k)
+                    b = np.full(33, k if r == k % n else -1, np.int64)
+                    a = coll_args("bcast", b, None, dt="int64", root=k % n)
+                    a._team = th
+                    run_one(r, a)
+                    assert np.all(b == k), ("bcast", r, t, k)
+                    a = coll_args("barrier")
+                    a._team = th
+                    run_one(r, a)
+            except Exception as e:  # noqa: BLE001
+                errs.append(repr(e))
+        ths = [threading.Thread(target=worker, args=(r, t)) for r in range(n) for t in range(nteams)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        assert not errs, errs
+
+
 def test_mem_map_export_import():
     U.lib.ucc_mem_map.argtypes = [U.handle, C.c_int, C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_void_p)]
     U.lib.ucc_mem_map.restype = C.c_int
