@@ -1,4 +1,5 @@
 #include "tl_shm_prog.h"
+#include "utils/profile/ucc_profile.h"
 
 static ucc_status_t op_push(ucc_tl_shm_task_t *t, const shm_op_t *op)
 {
@@ -120,7 +121,10 @@ void ucc_tl_shm_task_progress(ucc_coll_task_t *ct)
                 for (unsigned i = 0; i < t->n_reqs; i++) ucc_tl_shm_req_free(ctx, t->reqs[i]);
                 t->n_reqs = 0;
             }
-            if (at_end) { ct->status = UCC_OK; return; }
+            if (at_end) {
+                UCC_PROFILE_REQUEST_EVENT_NAMED(t, "shm", ucc_coll_type_str(ct->bargs.args.coll_type), "done");
+                ct->status = UCC_OK; return;
+            }
             t->pc++;
             continue;
         }
@@ -182,6 +186,7 @@ ucc_status_t ucc_tl_shm_task_post(ucc_coll_task_t *ct)
 {
     ucc_tl_shm_task_t *t = ucc_derived_of(ct, ucc_tl_shm_task_t);
     t->pc = 0; t->n_reqs = 0; t->etask = NULL;
+    UCC_PROFILE_REQUEST_EVENT_NAMED(t, "shm", ucc_coll_type_str(ct->bargs.args.coll_type), "start");
     if (ucc_unlikely(ct->flags & UCC_COLL_TASK_FLAG_ARGS_UPDATED) && t->build) {
         /* a pipelined parent re-targeted the buffers / counts: rebuild the step program in place */
         ucc_status_t st;

@@ -4,6 +4,7 @@
 #include "core/ucc_context.h"
 #include "utils/ucc_log.h"
 #include "utils/ucc_atomic.h"
+#include "utils/profile/ucc_profile.h"
 
 /* ---------------- events ---------------- */
 ucc_status_t ucc_event_manager_subscribe(ucc_coll_task_t *parent, ucc_event_t event, ucc_coll_task_t *task,
@@ -128,6 +129,7 @@ ucc_status_t ucc_task_complete(ucc_coll_task_t *task)
             task->executor = NULL;
         }
     }
+    if (task->flags & UCC_COLL_TASK_FLAG_TOP_LEVEL) UCC_PROFILE_REQUEST_EVENT(task, "ucc_coll_complete", 0);
     ucc_store_release((volatile int *)&task->super.status, (int)status);
     if (has_cb) cb.cb(cb.data, status);
     if (in_sched && status == UCC_OK) ucc_event_manager_notify(task, UCC_EVENT_COMPLETED_SCHEDULE);

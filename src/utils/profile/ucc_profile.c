@@ -44,6 +44,24 @@ void ucc_profile_record(ucc_profile_loc_t *loc, double t0, double t1, const void
     ucc_spin_unlock(&lock);
 }
 
+typedef struct dyn_loc { ucc_profile_loc_t loc; char name[64]; } dyn_loc_t;
+static dyn_loc_t *dyn_locs[128]; static int n_dyn;
+void ucc_profile_event_named(const char *prefix, const char *mid, const char *suffix, const void *req)
+{
+    char name[64]; dyn_loc_t *d = NULL; double t;
+    snprintf(name, sizeof(name), "%s_%s_%s", prefix, mid, suffix);
+    for (char *c = name; *c; c++) if (*c >= 'A' && *c <= 'Z') *c = (char)(*c - 'A' + 'a');
+    ucc_spin_lock(&lock);
+    for (int i = 0; i < n_dyn; i++) if (!strcmp(dyn_locs[i]->name, name)) { d = dyn_locs[i]; break; }
+    if (!d && n_dyn < 128 && (d = (dyn_loc_t *)calloc(1, sizeof(*d)))) {
+        memcpy(d->name, name, sizeof(name)); d->loc.name = d->name; d->loc.file = "-"; d->loc.line = 0; dyn_locs[n_dyn++] = d;
+    }
+    ucc_spin_unlock(&lock);
+    if (!d) return;
+    t = ucc_get_time();
+    ucc_profile_record(&d->loc, t, t, req);
+}
+
 void ucc_profile_cleanup(void)
 {
     FILE *f;
@@ -66,6 +84,8 @@ void ucc_profile_cleanup(void)
         fclose(f);
     }
     free(recs); recs = NULL; n_recs = cap_recs = rec_pos = 0; ucc_profile_mode_mask = 0;
+    for (int i = 0; i < n_dyn; i++) free(dyn_locs[i]);
+    n_dyn = 0; n_locs = 0;
 }
 void ucc_profile_range_push(const char *name) { if (nvtx_push) nvtx_push(name); }
 void ucc_profile_range_pop(void) { if (nvtx_pop) nvtx_pop(); }

@@ -27,6 +27,12 @@ extern unsigned ucc_profile_mode_mask;
 #define UCC_PROFILE_REQUEST_EVENT(_req, _name, _param) UCC_PROFILE_EVENT_(_name, _req)
 #define UCC_PROFILE_REQUEST_FREE(_req)                 UCC_PROFILE_EVENT_("request_free", _req)
 
+/* event whose name is composed at run time ("<prefix>_<coll>_<suffix>", reference e.g. "ucp_allreduce_kn_start"): the location is
+ * looked up by name, so this is slower than the static macros - only called when profiling is on */
+void ucc_profile_event_named(const char *prefix, const char *mid, const char *suffix, const void *req);
+#define UCC_PROFILE_REQUEST_EVENT_NAMED(_req, _prefix, _mid, _suffix) \
+    do { if (ucc_unlikely(ucc_profile_mode_mask)) ucc_profile_event_named(_prefix, _mid, _suffix, _req); } while (0)
+
 /* NVTX-style range hooks used around kernel launches; resolved at runtime if libnvToolsExt is loadable */
 void ucc_profile_range_push(const char *name);
 void ucc_profile_range_pop(void);

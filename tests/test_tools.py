@@ -64,3 +64,41 @@ def test_perftest_persistent_inplace_and_executor_ops():
     assert re.search(r"^\s*64\s", out, re.M)
     out = _perftest(["-c", "memcpy", "-m", "host", "-b", "1024", "-e", "1024", "-n", "10", "-w", "2"], n=1, port=29591)
     assert re.search(r"^\s*1024\s", out, re.M)
+
+
+def test_profile_log_and_reader(tmp_path):
+    """UCC_PROFILE_MODE=log,accum writes the .prof file at exit; tools/read_profile.py turns it into tables / a chrome trace
+    (reference: UCS profile + ucx_read_profile, utils/profile/ucc_profile_on.h:34-96)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    prof = tmp_path / "run.prof"
+    code = (
+        "import numpy as np\n"
+        "from ucc_b200.harness import UccJob, coll_args\n"
+        "j = UccJob(3); t = j.create_team()\n"
+        "for k in range(5):\n"
+        "    s = [np.full(256, r + 1.0, np.float32) for r in range(3)]; d = [np.zeros(256, np.float32) for _ in range(3)]\n"
+        "    q = t.coll([coll_args('allreduce', s[r], d[r]) for r in range(3)]); assert q.run() == 0; q.finalize()\n"
+        "    q = t.coll([coll_args('barrier') for r in range(3)]); assert q.run() == 0; q.finalize()\n"
+        "j.cleanup()\n")
+    env = dict(os.environ, PYTHONPATH=root, UCC_PROFILE_MODE="log,accum", UCC_PROFILE_FILE=str(prof))
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert prof.exists()
+    chrome = tmp_path / "t.json"
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "read_profile.py"), str(prof), "--json", "--chrome", str(chrome)],
+                       capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stderr
+    rep = json.loads(r.stdout)
+    names = {a["name"]: a for a in rep["accum"]}
+    assert names["ucc_collective_init"]["count"] >= 30 and names["ucc_collective_post"]["count"] >= 30
+    # 15 user allreduces + the service allreduces of team creation
+    assert names["shm_allreduce_start"]["count"] == names["shm_allreduce_done"]["count"] >= 15
+    assert rep["latency_us"]["shm_allreduce"]["n"] >= 15 and rep["latency_us"]["shm_barrier"]["n"] == 15
+    assert rep["latency_us"]["shm_allreduce"]["min"] >= 0
+    tr = json.loads(chrome.read_text())
+    assert len(tr["traceEvents"]) == rep["n_log"] > 0
+    txt = subprocess.run([sys.executable, os.path.join(root, "tools", "read_profile.py"), str(prof)], capture_output=True, text=True, timeout=60)
+    assert "shm_allreduce" in txt.stdout and "ucc_collective_post" in txt.stdout
