@@ -284,7 +284,14 @@ static void handle_cell(ucc_tl_shm_context_t *ctx, shm_cell_hdr_t *c)
         return;
     }
     /* nobody waits for it yet: stash */
-    u = c->type == SHM_CELL_DATA ? unexp_find(ctx, c->src_ep, c->tag) : NULL;
+    /* a later cell of a message that is already being stashed joins it; a NEW message with the same (source, tag) - a
+     * persistent collective posted again before the receiver caught up - must get its own entry (per-source FIFO order
+     * guarantees the messages do not interleave) */
+    u = NULL;
+    if (c->type == SHM_CELL_DATA) {
+        shm_unexp_t *it;
+        ucc_list_for_each(it, &ctx->unexpected, list) if (it->src_ep == c->src_ep && it->tag == c->tag && !it->is_rts && it->received < it->total_len) { u = it; break; }
+    }
     if (!u) {
         u = (shm_unexp_t *)calloc(1, sizeof(*u));
         u->tag = c->tag; u->src_ep = c->src_ep; u->total_len = c->total_len;

@@ -47,3 +47,19 @@ def test_torchrun_host_onesided_cma():
     env = dict(os.environ, PYTHONPATH=ROOT, CUDA_VISIBLE_DEVICES="", UCC_TL_SHM_TUNE="alltoall:@onesided#alltoallv:@onesided#allreduce:@sliding_window", UCC_TL_SHM_CMA="y")
     out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert "DIST_WORKER_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
+
+
+@pytest.mark.parametrize("n,extra", [(3, []), (4, ["-c", "allreduce,alltoallv,reduce_scatter,bcast,gatherv", "-P", "2", "-i", "3"])])
+def test_ucc_test_dist_tool(n, extra):
+    """tools/ucc_test_dist.py (the `ucc_test_mpi` role): team kinds world/half/odd_even/reverse x collectives x dtypes x ops x
+    in-place x roots, every case checked against the locally computed oracle; the report must show no failures."""
+    port = 29690 + n
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tools", "ucc_test_dist.py"), "-t", "world,half,odd_even,reverse",
+           "-I", "2", "-m", "8:70000:90", "-r", "all", "-d", "int32,bfloat16,uint8,float64", "-o", "sum,max,lor,band,avg", "-s", "17"] + extra
+    env = dict(os.environ, PYTHONPATH=ROOT, CUDA_VISIBLE_DEVICES="")
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+    assert "UCC_TEST_DIST_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+    rep = out.stdout[out.stdout.index("TEST REPORT"):]
+    nums = {ln.split(":")[0].strip(): int(ln.split(":")[1]) for ln in rep.splitlines() if ":" in ln and ln.split(":")[1].strip().isdigit()}
+    assert nums["failed"] == 0 and nums["passed"] > 500, nums
