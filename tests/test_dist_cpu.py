@@ -63,3 +63,20 @@ def test_ucc_test_dist_tool(n, extra):
     rep = out.stdout[out.stdout.index("TEST REPORT"):]
     nums = {ln.split(":")[0].strip(): int(ln.split(":")[1]) for ln in rep.splitlines() if ":" in ln and ln.split(":")[1].strip().isdigit()}
     assert nums["failed"] == 0 and nums["passed"] > 500, nums
+
+
+@pytest.mark.parametrize("n,ppn,tune", [(4, 2, "allreduce:0-inf:@rab"), (6, 3, "allreduce:0-inf:@split_rail"), (5, 2, None)])
+def test_cl_hier_multiprocess(n, ppn, tune):
+    """cl/hier schedules with real processes: UCC_B200_FAKE_PPN spreads the ranks of one box over pretend nodes."""
+    port = 29710 + n
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tools", "ucc_test_dist.py"), "-t", "world,reverse",
+           "-c", "allreduce,bcast,reduce,alltoall,alltoallv,allgatherv,barrier", "-I", "2", "-P", "2", "-i", "2",
+           "-m", "8:200000:50", "-r", "all", "-d", "int32,float32", "-o", "sum,max", "-s", "3"]
+    env = dict(os.environ, PYTHONPATH=ROOT, CUDA_VISIBLE_DEVICES="", UCC_B200_FAKE_PPN=str(ppn), UCC_CLS="hier,basic",
+               UCC_CL_HIER_TLS="shm,self", UCC_CL_BASIC_TLS="shm,self", UCC_COLL_TRACE="info")
+    if tune:
+        env["UCC_CL_HIER_TUNE"] = tune
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+    assert "UCC_TEST_DIST_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "CL_HIER" in out.stdout + out.stderr      # the hierarchical CL really took collectives

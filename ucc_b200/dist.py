@@ -138,8 +138,11 @@ class Request:
 class Communicator:
     """lib + context + one team spanning `group` (default: all ranks)."""
 
-    def __init__(self, group=None, thread_mode=U.UCC_THREAD_SINGLE, lib_modify=(), ctx_modify=(), store=None, rank=None, size=None, perm=None):
-        """`perm[g]` = UCC rank of group rank g (default identity): lets a team use any rank order (e.g. reversed)."""
+    def __init__(self, group=None, thread_mode=U.UCC_THREAD_SINGLE, lib_modify=(), ctx_modify=(), store=None, rank=None, size=None, perm=None,
+                 fake_ppn=None):
+        """`perm[g]` = UCC rank of group rank g (default identity): lets a team use any rank order (e.g. reversed).
+        `fake_ppn` (or env UCC_B200_FAKE_PPN): pretend the ranks are spread over nodes of that many processes each - a
+        single-box way to exercise the hierarchical (cl/hier) schedules with real processes."""
         if store is not None:
             self.rank, self.size = rank, size
             self.oob = _StoreOob(store, rank, size)
@@ -169,7 +172,13 @@ class Communicator:
             cp.mask = U.UCC_CONTEXT_PARAM_FIELD_OOB
             cp.oob = self.oob.struct()
         self.ctx = U.handle()
-        st = U.ucc_context_create(self.lib, C.byref(cp), ccfg, C.byref(self.ctx))
+        fake_ppn = fake_ppn or int(os.environ.get("UCC_B200_FAKE_PPN", "0"))
+        if fake_ppn:
+            from .harness import fake_proc_info
+            pi = fake_proc_info(self.rank, fake_ppn)
+            st = U.ucc_context_create_proc_info(self.lib, C.byref(cp), ccfg, C.byref(self.ctx), C.byref(pi))
+        else:
+            st = U.ucc_context_create(self.lib, C.byref(cp), ccfg, C.byref(self.ctx))
         U.ucc_context_config_release(ccfg)
         U.check(st, "context_create")
         tp = U.ucc_team_params_t()
