@@ -255,8 +255,11 @@ have_task:
     if (ucc_global_config.coll_trace.log_level >= UCC_LOG_LEVEL_INFO && !(task->flags & UCC_COLL_TASK_FLAG_INTERNAL)) {
         if (team->rank == 0 || ucc_global_config.coll_trace.log_level >= UCC_LOG_LEVEL_DEBUG) {
             char buf[512]; ucc_coll_args_str(&op_args.args, team->rank, team->size, buf, sizeof(buf));
+            /* a TL task was selected straight through cl/basic's score map; a CL task (cl/hier schedule) names itself */
+            const char *tn = task->team ? ucc_base_team_name(task->team) : "-";
+            int is_cl = !strncmp(tn, "CL_", 3) || !strncmp(tn, "cl_", 3);
             COLL_TRACE(UCC_LOG_LEVEL_INFO, "coll_init: %s; %s {%s}, team_id %u, req %p, seq_num %u", buf,
-                       task->team ? "CL_BASIC" : "STUB", task->team ? ucc_base_team_name(task->team) : "-", team->id, (void *)task, task->seq_num);
+                       !task->team ? "STUB" : (is_cl ? tn : "CL_BASIC"), is_cl ? "schedule" : tn, team->id, (void *)task, task->seq_num);
         }
     }
     UCC_PROFILE_FUNC_END();
