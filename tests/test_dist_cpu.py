@@ -49,7 +49,7 @@ def test_torchrun_host_onesided_cma():
     assert "DIST_WORKER_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
 
 
-@pytest.mark.parametrize("n,extra", [(3, []), (4, ["-c", "allreduce,alltoallv,reduce_scatter,bcast,gatherv", "-P", "2", "-i", "3"])])
+@pytest.mark.parametrize("n,extra", [(3, []), (4, ["-c", "allreduce,alltoallv,reduce_scatter,bcast,gatherv", "-P", "2", "-i", "3", "-N", "8"])])
 def test_ucc_test_dist_tool(n, extra):
     """tools/ucc_test_dist.py (the `ucc_test_mpi` role): team kinds world/half/odd_even/reverse x collectives x dtypes x ops x
     in-place x roots, every case checked against the locally computed oracle; the report must show no failures."""

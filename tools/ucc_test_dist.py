@@ -335,41 +335,52 @@ def build_case(coll, team, urank, n, seed, case, dt, op, mtype, count, root, inp
     raise ValueError(coll)
 
 
-def run_request(comm, args, persistent, iters, triggered, use_cuda, timeout=120.0):
-    """-> 'ok' | 'skip' | 'fail:<why>'"""
-    if persistent:
-        args.mask |= U.UCC_COLL_ARGS_FIELD_FLAGS
-        args.flags |= U.UCC_COLL_ARGS_FLAG_PERSISTENT
-    r = C.POINTER(U.ucc_coll_req_t)()
-    st = U.ucc_collective_init(C.byref(args), C.byref(r), comm.team)
-    if st in (U.UCC_ERR_NOT_SUPPORTED, U.UCC_ERR_NOT_IMPLEMENTED):
-        return "skip"
-    if st != U.UCC_OK:
-        return f"fail:init {st}"
+def run_batch(comm, batch, iters, use_cuda, timeout=120.0):
+    """Run the cases of `batch` (dicts with args/persistent/triggered) CONCURRENTLY on one team: init all, post all in the same
+    order on every rank, progress until all are done.  Fills case["res"] with 'ok' | 'skip' | 'fail:<why>'."""
     from ucc_b200.dist import Request
-    req = Request(comm, r, (args,))
-    try:
-        for it in range(iters if persistent else 1):
+    live = []
+    for c in batch:
+        args = c["args"]
+        if c["persistent"]:
+            args.mask |= U.UCC_COLL_ARGS_FIELD_FLAGS
+            args.flags |= U.UCC_COLL_ARGS_FLAG_PERSISTENT
+        r = C.POINTER(U.ucc_coll_req_t)()
+        st = U.ucc_collective_init(C.byref(args), C.byref(r), comm.team)
+        if st in (U.UCC_ERR_NOT_SUPPORTED, U.UCC_ERR_NOT_IMPLEMENTED):
+            c["res"] = "skip"
+        elif st != U.UCC_OK:
+            c["res"] = f"fail:init {st}"
+        else:
+            c["res"], c["req"] = "ok", Request(comm, r, (args,))
+            live.append(c)
+    max_it = max([iters if c["persistent"] else 1 for c in live], default=0)
+    for it in range(max_it):
+        cur = [c for c in live if c["res"] == "ok" and it < (iters if c["persistent"] else 1)]
+        for c in cur:
             if it:
-                for b in args._bufs:
+                for b in c["args"]._bufs:
                     b.reset()
-            if triggered and use_cuda:
-                req.post_on_stream()
+            if c["triggered"] and use_cuda:
+                c["req"].post_on_stream()
             else:
-                req.post()
-            t0 = time.time()
-            while req.test() == U.UCC_INPROGRESS:
-                comm.progress()
-                if time.time() - t0 > timeout:
-                    return "fail:timeout"
-            if req.test() != U.UCC_OK:
-                return f"fail:status {req.test()}"
-            if use_cuda:
-                torch.cuda.synchronize()
-    finally:
-        if req.test() != U.UCC_INPROGRESS:
-            req.finalize()
-    return "ok"
+                c["req"].post()
+        t0 = time.time()
+        while any(c["req"].test() == U.UCC_INPROGRESS for c in cur):
+            comm.progress()
+            if time.time() - t0 > timeout:
+                break
+        for c in cur:
+            st = c["req"].test()
+            if st == U.UCC_INPROGRESS:
+                c["res"] = "fail:timeout"
+            elif st != U.UCC_OK:
+                c["res"] = f"fail:status {st}"
+        if use_cuda:
+            torch.cuda.synchronize()
+    for c in live:
+        if c["req"].test() != U.UCC_INPROGRESS:
+            c["req"].finalize()
 
 
 def parse_args(argv):
@@ -385,6 +396,7 @@ def parse_args(argv):
     ap.add_argument("-r", "--root", default="single:0", help="single:<value>, random:<n>, all")
     ap.add_argument("-s", "--seed", type=int, default=None)
     ap.add_argument("-Z", "--max_size", type=int, default=1 << 30, help="cases whose largest buffer exceeds this are skipped")
+    ap.add_argument("-N", "--num_tests", type=int, default=1, help="number of tests to run in parallel (outstanding on the same team)")
     ap.add_argument("-i", "--iter", type=int, default=1)
     ap.add_argument("--triggered", type=int, default=0, help="0 - post, 1 - triggered post (CUDA memory), 2 - both")
     ap.add_argument("-v", "--verbose", action="store_true")
@@ -429,6 +441,32 @@ def main(argv=None):
         rk, rv = (a.root.split(":") + ["0"])[:2]
         roots = list(range(n)) if rk == "all" else ([int(rv) % n] if rk == "single" else
                                                     [int(x) for x in np.random.default_rng([a.seed, 99]).integers(0, n, int(rv))])
+        batch = []
+
+        def flush(batch):
+            """run the pending cases concurrently, agree on the verdicts across the team, tally"""
+            if not batch:
+                return
+            run_batch(comm, batch, a.iter, any(c["cuda"] for c in batch))
+            codes = []
+            for c in batch:
+                if c["res"] == "ok" and not c["check"]():
+                    c["res"] = "fail:data mismatch"
+                codes.append(0 if c["res"] == "ok" else (1 if c["res"] == "skip" else 2))
+            # a case passes only if it passed everywhere; NOT_SUPPORTED must be unanimous too
+            code = torch.tensor(codes)
+            dist.all_reduce(code, op=dist.ReduceOp.MAX, group=team.group)
+            for c, worst in zip(batch, code.tolist()):
+                if worst == 0:
+                    totals[1] += 1
+                elif worst == 1:
+                    totals[2] += 1
+                else:
+                    totals[3] += 1
+                    failures.append(f"{c['name']}: rank {rank} {c['res']}")
+                if a.verbose and rank == 0:
+                    print(f"[{'OK' if worst == 0 else 'SKIP' if worst == 1 else 'FAIL'}] {c['name']}", flush=True)
+            batch.clear()
         for coll in colls:
             dts = ["int32"] if coll in NO_DATA else a.dtypes.split(",")
             ops = a.ops.split(",") if coll in REDUCTIONS else ["sum"]
@@ -452,23 +490,11 @@ def main(argv=None):
                 if built is None:
                     totals[2] += 1
                     continue
-                args, check = built
-                res = run_request(comm, args, persistent, a.iter, trig, mtype == "cuda")
-                if res == "ok" and not check():
-                    res = "fail:data mismatch"
-                # a case passes only if it passed everywhere; NOT_SUPPORTED must be unanimous too
-                code = torch.tensor([0 if res == "ok" else (1 if res == "skip" else 2)])
-                dist.all_reduce(code, op=dist.ReduceOp.MAX, group=team.group)
-                worst = int(code.item())
-                if worst == 0:
-                    totals[1] += 1
-                elif worst == 1:
-                    totals[2] += 1
-                else:
-                    totals[3] += 1
-                    failures.append(f"{name}: rank {rank} {res}")
-                if a.verbose and rank == 0:
-                    print(f"[{'OK' if worst == 0 else 'SKIP' if worst == 1 else 'FAIL'}] {name}", flush=True)
+                batch.append({"name": name, "args": built[0], "check": built[1], "persistent": persistent, "triggered": trig,
+                              "cuda": mtype == "cuda"})
+                if len(batch) >= max(a.num_tests, 1):
+                    flush(batch)
+        flush(batch)
         comm.barrier()
         team.destroy()
     # sub-teams run on a subset of the processes: merge the per-process tallies
