@@ -207,6 +207,14 @@ int main(int argc, char **argv)
     CHECK(ucc_team_create_post(&ctx, 1, &tp, &team));
     { ucc_status_t st; while ((st = ucc_team_create_test(team)) == UCC_INPROGRESS) ucc_context_progress(ctx); CHECK(st); }
 
+    /* iterations are separated by a UCC barrier on the team (reference ucc_pt_comm::barrier): much less arrival skew than a trip over the TCP bootstrap */
+    auto team_barrier = [&]() {
+        ucc_coll_args_t ba{}; ucc_coll_req_h br; ucc_status_t st;
+        ba.coll_type = UCC_COLL_TYPE_BARRIER;
+        CHECK(ucc_collective_init(&ba, &br, team)); CHECK(ucc_collective_post(br));
+        while ((st = ucc_collective_test(br)) > 0) ucc_context_progress(ctx);
+        CHECK(st); CHECK(ucc_collective_finalize(br));
+    };
     const int N = boot.size, me = boot.rank; const size_t dts = ucc_dt_size(cfg.dt);
     ucc_coll_type_t ct = is_exec ? UCC_COLL_TYPE_LAST : ucc_coll_type_from_str(cfg.coll.c_str());
     if (!is_exec && ct == UCC_COLL_TYPE_LAST) { fprintf(stderr, "unknown collective %s\n", cfg.coll.c_str()); return 1; }
@@ -263,7 +271,7 @@ int main(int argc, char **argv)
         if (is_exec) { ucc_ee_executor_params_t ep{UCC_EE_EXECUTOR_PARAM_FIELD_TYPE, need_cuda ? UCC_EE_CUDA_STREAM : UCC_EE_CPU_THREAD, 0}; CHECK(ucc_ee_executor_init(&ep, &exec)); CHECK(ucc_ee_executor_start(exec, nullptr)); }
         if (cfg.persistent && !is_exec) CHECK(ucc_collective_init(&a, &req, team));
         double t_sum = 0, dev_sum = 0;
-        boot.barrier();
+        boot.barrier(); if (!is_exec) team_barrier();
         for (int it = 0; it < warm + iters; it++) {
             if (cfg.root_shift && !is_exec) a.root = (uint64_t)((cfg.root + it * cfg.root_shift) % N);
             if (need_cuda) cuda.DeviceSynchronize();
@@ -286,7 +294,7 @@ int main(int argc, char **argv)
             }
             double t1 = now_us();
             if (it >= warm) t_sum += t1 - t0;
-            if (!is_exec) boot.barrier();
+            if (!is_exec) team_barrier();
         }
         if (cfg.persistent && !is_exec) CHECK(ucc_collective_finalize(req));
         if (exec) { ucc_ee_executor_stop(exec); ucc_ee_executor_finalize(exec); }
