@@ -133,7 +133,8 @@ typedef struct ucc_tl_nvl_team {
 } ucc_tl_nvl_team_t;
 
 typedef enum { NVL_TASK_REDUCE_ONESHOT, NVL_TASK_REDUCE_STAGED, NVL_TASK_REDUCE_STEPS, NVL_TASK_XCHG, NVL_TASK_BARRIER,
-               NVL_TASK_SELF_COPY /* team of one: u.xchg.{dst,src,src_bytes} describe the only data movement */ } nvl_task_kind_t;
+               NVL_TASK_SELF_COPY /* team of one: u.xchg.{dst,src,src_bytes} describe the only data movement */,
+               NVL_TASK_REDUCE_PIPE /* pipelined staged NVLS allreduce (kernels/nvl_pipe.cu) */ } nvl_task_kind_t;
 typedef enum { NVL_TASK_LAUNCHED, NVL_TASK_QUEUED } nvl_task_state_t;
 typedef struct ucc_tl_nvl_task {
     ucc_coll_task_t     super;

@@ -44,6 +44,7 @@ static ucc_status_t nvl_launch(ucc_tl_nvl_task_t *t, cudaStream_t s)
         else e = nvl_launch_reduce_staged(&t->u.red, t->nblocks, t->nthreads, s);
         break;
     case NVL_TASK_REDUCE_STEPS: e = nvl_launch_reduce_steps(&t->u.red, t->nblocks, t->nthreads, s); break;
+    case NVL_TASK_REDUCE_PIPE: e = nvl_launch_reduce_pipe(&t->u.red, t->nblocks, t->nthreads, s); break;
     case NVL_TASK_XCHG: e = nvl_launch_exchange(&t->u.xchg, t->nblocks, t->nthreads, s); break;
     case NVL_TASK_SELF_COPY:
         e = t->u.xchg.src_bytes ? nvl_launch_self_copy(t->u.xchg.dst, t->u.xchg.src, t->u.xchg.src_bytes, t->nblocks, t->nthreads, s) : cudaSuccess;
@@ -277,7 +278,7 @@ static ucc_status_t self_init(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, 
 /* ------------------------------------------------------------------ */
 /* reduce family                                                       */
 /* ------------------------------------------------------------------ */
-typedef enum { RED_ALG_ONESHOT, RED_ALG_TWOSHOT, RED_ALG_NVLS, RED_ALG_RING, RED_ALG_RHD } red_alg_t;
+typedef enum { RED_ALG_ONESHOT, RED_ALG_TWOSHOT, RED_ALG_NVLS, RED_ALG_RING, RED_ALG_RHD, RED_ALG_NVLS_PIPE } red_alg_t;
 
 static ucc_status_t red_init(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, ucc_coll_task_t **task_p, red_alg_t alg)
 {
@@ -316,7 +317,8 @@ static ucc_status_t red_init(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, u
     if (ndt < 0 || nop < 0 || !nvl_dt_supports_op(ndt, nop)) return UCC_ERR_NOT_SUPPORTED;
     bytes = count * ucc_dt_size(dt);
     if (alg == RED_ALG_ONESHOT && (a->coll_type != UCC_COLL_TYPE_ALLREDUCE || bytes > NVL_LL_MAX)) return UCC_ERR_NOT_SUPPORTED;
-    if (alg == RED_ALG_NVLS && (!team->nvls || !nvl_nvls_supports(ndt, nop))) return UCC_ERR_NOT_SUPPORTED;
+    if ((alg == RED_ALG_NVLS || alg == RED_ALG_NVLS_PIPE) && (!team->nvls || !nvl_nvls_supports(ndt, nop))) return UCC_ERR_NOT_SUPPORTED;
+    if (alg == RED_ALG_NVLS_PIPE && a->coll_type != UCC_COLL_TYPE_ALLREDUCE) return UCC_ERR_NOT_SUPPORTED;
     if (alg == RED_ALG_RING || alg == RED_ALG_RHD) {
         /* step-structured kernels: allreduce / reduce_scatter(v) whose slices fit one heap round; rhd pairs ranks by xor */
         size_t slice_cap = (ctx->cfg.symmetric_size / N / 16) * 16, need;
@@ -329,7 +331,7 @@ static ucc_status_t red_init(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, u
     if (st != UCC_OK) return st;
     r = &t->u.red;
     memset(r, 0, sizeof(*r));
-    r->team = team->dev; r->src = src; r->dst = dst; r->count = count; r->dt = ndt; r->op = nop; r->root = (int)a->root; r->use_nvls = (alg == RED_ALG_NVLS);
+    r->team = team->dev; r->src = src; r->dst = dst; r->count = count; r->dt = ndt; r->op = nop; r->root = (int)a->root; r->use_nvls = (alg == RED_ALG_NVLS || alg == RED_ALG_NVLS_PIPE);
     switch (a->coll_type) {
     case UCC_COLL_TYPE_ALLREDUCE: r->kind = NVL_RED_ALLREDUCE; break;
     case UCC_COLL_TYPE_REDUCE: r->kind = NVL_RED_REDUCE; break;
@@ -346,6 +348,7 @@ static ucc_status_t red_init(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, u
     }
     if (alg == RED_ALG_ONESHOT) { t->kind = NVL_TASK_REDUCE_ONESHOT; t->nblocks = pick_blocks(ctx, bytes, 16384); if (t->nblocks > 64) t->nblocks = 64; }
     else if (alg == RED_ALG_RING || alg == RED_ALG_RHD) { t->kind = NVL_TASK_REDUCE_STEPS; r->sched = alg == RED_ALG_RING ? 1 : 2; t->nblocks = pick_blocks(ctx, bytes, 64 * 1024); }
+    else if (alg == RED_ALG_NVLS_PIPE) { t->kind = NVL_TASK_REDUCE_PIPE; t->nblocks = pick_blocks(ctx, bytes, 32 * 1024); }
     else { t->kind = NVL_TASK_REDUCE_STAGED; t->nblocks = pick_blocks(ctx, bytes, 32 * 1024); }
     /* zero-copy: every criterion below is evaluated identically on all ranks (sizes / counts are collective
      * arguments); what only the owner knows (can the buffer be exported? is it aligned?) travels with the exchange */
@@ -370,6 +373,7 @@ static ucc_status_t red_init_twoshot(ucc_base_coll_args_t *b, ucc_base_team_t *t
 static ucc_status_t red_init_nvls(ucc_base_coll_args_t *b, ucc_base_team_t *t, ucc_coll_task_t **p) { return red_init(b, t, p, RED_ALG_NVLS); }
 static ucc_status_t red_init_ring(ucc_base_coll_args_t *b, ucc_base_team_t *t, ucc_coll_task_t **p) { return red_init(b, t, p, RED_ALG_RING); }
 static ucc_status_t red_init_rhd(ucc_base_coll_args_t *b, ucc_base_team_t *t, ucc_coll_task_t **p) { return red_init(b, t, p, RED_ALG_RHD); }
+static ucc_status_t red_init_nvls_pipe(ucc_base_coll_args_t *b, ucc_base_team_t *t, ucc_coll_task_t **p) { return red_init(b, t, p, RED_ALG_NVLS_PIPE); }
 
 /* ------------------------------------------------------------------ */
 /* data movement family                                                */
@@ -554,7 +558,8 @@ static const nvl_alg_t algs_allreduce[] = {
     {"oneshot", "push the whole vector to every peer and reduce locally (latency path, <= 64K)", red_init_oneshot},
     {"nvls", "stage + multimem.ld_reduce / multimem.st through the NVSwitch (in-switch reduction)", red_init_nvls},
     {"ring", "ring reduce-scatter + ring allgather through the heaps, neighbour links only, one kernel", red_init_ring},
-    {"rhd", "recursive halving + recursive doubling (radix-2 scatter-reduce-allgather), power-of-two teams, one kernel", red_init_rhd}, {NULL}};
+    {"rhd", "recursive halving + recursive doubling (radix-2 scatter-reduce-allgather), power-of-two teams, one kernel", red_init_rhd},
+    {"nvls_pipe", "nvls with three heap buffers: staging, in-switch reduction and copy-out of consecutive chunks overlap (opt-in, not yet measured)", red_init_nvls_pipe}, {NULL}};
 static const nvl_alg_t algs_rs[] = {
     {"twoshot", "stage + pull-reduce own slice over NVLink", red_init_twoshot},
     {"nvls", "stage + multimem.ld_reduce own slice in the NVSwitch", red_init_nvls},

@@ -90,3 +90,13 @@ def test_torch_backend_cuda():
            "--master-port", "29795", os.path.join(ROOT, "tests", "pg_worker.py"), "cuda"]
     out = subprocess.run(cmd, env=dict(os.environ, PYTHONPATH=ROOT), capture_output=True, text=True, timeout=900)
     assert "PG_WORKER_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+
+
+@pytest.mark.skipif(os.environ.get("UCC_B200_EXPERIMENTAL_TESTS") != "1", reason="nvls_pipe was written without GPU time left: set UCC_B200_EXPERIMENTAL_TESTS=1")
+@pytest.mark.parametrize("heap", ["128M", "3M"])
+def test_multiproc_nvls_pipe(heap):
+    """Pipelined staged NVLS allreduce (kernels/nvl_pipe.cu); the small heap forces many chunks so the three buffers rotate."""
+    n = min(2, torch.cuda.device_count()) if torch.cuda.is_available() else 0
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    _run(n, {"UCC_TL_NVL_TUNE": "allreduce:cuda:inf:@nvls_pipe", "UCC_TL_NVL_ALLREDUCE_ONESHOT_THRESH": "0", "UCC_TL_NVL_SYMMETRIC_SIZE": heap})
