@@ -1,0 +1,90 @@
+/* In-place NVLS allreduce on SYMMETRIC USER MEMORY (UCC_TL_NVL_USER_SIZE > 0).
+ *
+ * When src and dst live in the user region of the team heap (allocated through ucc_tl_nvl_symm_region(), same offsets on every
+ * member - the NVSHMEM / ncclMemAlloc+register contract), they are already bound to the team's multicast object.  Nothing is
+ * staged and nothing is copied out:
+ *     barrier   (every member's kernel runs => its src is final, its dst may be written)
+ *     my slice: multimem.ld_reduce of src through the switch -> multimem.st into every member's dst
+ *     barrier   (every slice has landed)
+ * Each GPU injects count/N (stores) + answers count*(N-1)/N (loads of the others) and receives the same: one vector's worth
+ * of bytes per direction, the minimum an allreduce can move, and HBM is touched once for reading and once for writing.
+ *
+ * d.src[0] / d.dst[0] carry the LOCAL addresses of src / dst inside my heap mapping; the multicast address is the same offset
+ * in team.mc_heap.  Requires 16-byte aligned offsets (the allocator hands out 256-byte aligned blocks).
+ *
+ * Status: written at the end of round 1 without GPU time left; compiled for sm_100a, NOT yet run (tools/gpu_experimental.sh). */
+#include "nvl_reduce_impl.cuh"
+
+template <typename T, int OP>
+static __device__ __forceinline__ void symm_body(const nvl_red_args_t &a, BlockSync &bs, const SlicePlan &pl)
+{
+    constexpr int E = 16 / sizeof(T);
+    constexpr int U = 8;
+    const nvl_team_dev_t &t = a.team;
+    const int N = t.size, me = t.rank;
+    const size_t so = (size_t)(a.d.src[0] - t.heap[me]), dof = (size_t)(a.d.dst[0] - t.heap[me]);
+    const float inv_n = 1.0f / (float)N;
+    const size_t nt = blockDim.x;
+
+    bs.barrier(t, 1);
+    {
+        const size_t cnt = pl.cnt[me], nfull = cnt / E, nv = (cnt + E - 1) / E;
+        const size_t per = (nv + gridDim.x - 1) / gridDim.x, j0 = dmin((size_t)blockIdx.x * per, nv), j1 = dmin(j0 + per, nv);
+        const size_t jfull = dmin(j1, nfull);                               /* whole vectors of my range */
+        const char *mcs = t.mc_heap + so + pl.off[me] * sizeof(T);
+        char *mcd = t.mc_heap + dof + pl.off[me] * sizeof(T);
+        size_t j = j0 + threadIdx.x;
+        for (; j + (size_t)(U - 1) * nt < jfull; j += (size_t)U * nt) {
+            uint4 r[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) r[u] = McRed<T, OP>::ld(mcs + (j + (size_t)u * nt) * 16);
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                uint4 v = r[u];
+                if (OP == NVL_OP_AVG) { VecAcc<T, OP> acc; acc.set(v); v = acc.get(inv_n); }
+                mc_st_v4(mcd + (j + (size_t)u * nt) * 16, v);
+            }
+        }
+        for (; j < jfull; j += nt) {
+            uint4 v = McRed<T, OP>::ld(mcs + j * 16);
+            if (OP == NVL_OP_AVG) { VecAcc<T, OP> acc; acc.set(v); v = acc.get(inv_n); }
+            mc_st_v4(mcd + j * 16, v);
+        }
+        /* ragged end of the vector (only the last non-empty slice can have one): the 16-byte load stays inside the 256-byte
+         * aligned allocation, but the store must not touch bytes behind dst's last element - write the valid elements to every
+         * member's unicast mapping instead */
+        if (nfull < nv && nfull >= j0 && nfull < j1 && threadIdx.x == 0) {
+            uint4 v = McRed<T, OP>::ld(mcs + nfull * 16);
+            if (OP == NVL_OP_AVG) { VecAcc<T, OP> acc; acc.set(v); v = acc.get(inv_n); }
+            for (int p = 0; p < N; p++)
+                store_dst_vec<T>(reinterpret_cast<T *>(t.heap[p] + dof) + pl.off[me], nfull * E, cnt, false, v);
+        }
+    }
+    bs.barrier(t, 2);
+}
+
+template <typename T> __global__ void __launch_bounds__(NVL_THREADS_MAX, 2) nvl_allreduce_symm_kernel(nvl_red_args_t a)
+{
+    BlockSync bs; bs.init(a.team);
+    SlicePlan pl; make_plan<T>(a, pl);
+#define CALL_SYMM(_T, _OP) symm_body<_T, _OP>(a, bs, pl)
+    NVL_DISPATCH_OP(T, a.op, CALL_SYMM);
+    bs.finish(2);
+}
+
+extern "C" cudaError_t nvl_launch_reduce_symm(const nvl_red_args_t *a, int nblocks, int nthreads, cudaStream_t s)
+{
+    if (nthreads > NVL_THREADS_MAX) nthreads = NVL_THREADS_MAX;
+    if (a->kind != NVL_RED_ALLREDUCE || !a->team.mc_heap || !nvl_nvls_supports(a->dt, a->op) || !a->d.src[0] || !a->d.dst[0]) return cudaErrorInvalidValue;
+    switch (a->dt) {
+    case NVL_DT_F32: nvl_allreduce_symm_kernel<float><<<nblocks, nthreads, 0, s>>>(*a); break;
+    case NVL_DT_F16: nvl_allreduce_symm_kernel<__half><<<nblocks, nthreads, 0, s>>>(*a); break;
+    case NVL_DT_BF16: nvl_allreduce_symm_kernel<__nv_bfloat16><<<nblocks, nthreads, 0, s>>>(*a); break;
+    case NVL_DT_I32: nvl_allreduce_symm_kernel<int32_t><<<nblocks, nthreads, 0, s>>>(*a); break;
+    case NVL_DT_U32: nvl_allreduce_symm_kernel<uint32_t><<<nblocks, nthreads, 0, s>>>(*a); break;
+    case NVL_DT_I64: nvl_allreduce_symm_kernel<int64_t><<<nblocks, nthreads, 0, s>>>(*a); break;
+    case NVL_DT_U64: nvl_allreduce_symm_kernel<uint64_t><<<nblocks, nthreads, 0, s>>>(*a); break;
+    default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}

@@ -24,6 +24,9 @@ ucc_config_field_t ucc_tl_nvl_context_config_table[] = {
      ucc_offsetof(ucc_tl_nvl_context_config_t, zcopy), UCC_CONFIG_TYPE_TERNARY},
     {"ZCOPY_THRESH", "1M", "Messages of at least this size use the zero-copy kernels", ucc_offsetof(ucc_tl_nvl_context_config_t, zcopy_thresh), UCC_CONFIG_TYPE_MEMUNITS},
     {"ALLREDUCE_NVLS_THRESH", "512M", "Allreduce messages of at least this size use NVLS when available", ucc_offsetof(ucc_tl_nvl_context_config_t, nvls_thresh), UCC_CONFIG_TYPE_MEMUNITS},
+    {"USER_SIZE", "0", "Size of a symmetric USER region appended to every team heap (bound to the NVLS multicast object like the rest of the heap). "
+     "Buffers placed there at the same offset on every member (ucc_tl_nvl_symm_region) are reduced in place through the switch: no staging, no copy-out",
+     ucc_offsetof(ucc_tl_nvl_context_config_t, user_size), UCC_CONFIG_TYPE_MEMUNITS},
     {"FD_VIA_PIDFD", "try", "Fetch peers' memory handles with pidfd_getfd before falling back to a unix socket", ucc_offsetof(ucc_tl_nvl_context_config_t, fd_via_pidfd), UCC_CONFIG_TYPE_TERNARY},
     {NULL}};
 

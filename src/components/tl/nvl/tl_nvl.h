@@ -43,6 +43,7 @@ typedef struct ucc_tl_nvl_context_config {
     int      fd_via_pidfd;     /* ternary: try pidfd_getfd before the unix socket */
     int      zcopy;            /* ternary: read / write the members' user buffers in place (CUDA IPC) */
     size_t   zcopy_thresh;     /* ... for messages of at least this size */
+    size_t   user_size;        /* symmetric USER region appended to every team heap (0: none), see ucc_tl_nvl_symm_region() */
 } ucc_tl_nvl_context_config_t;
 
 /* ---- zero-copy buffer exchange board (tl_nvl_direct.c): one single-writer POSIX shm segment per rank ---- */
@@ -134,7 +135,8 @@ typedef struct ucc_tl_nvl_team {
 
 typedef enum { NVL_TASK_REDUCE_ONESHOT, NVL_TASK_REDUCE_STAGED, NVL_TASK_REDUCE_STEPS, NVL_TASK_XCHG, NVL_TASK_BARRIER,
                NVL_TASK_SELF_COPY /* team of one: u.xchg.{dst,src,src_bytes} describe the only data movement */,
-               NVL_TASK_REDUCE_PIPE /* pipelined staged NVLS allreduce (kernels/nvl_pipe.cu) */ } nvl_task_kind_t;
+               NVL_TASK_REDUCE_PIPE /* pipelined staged NVLS allreduce (kernels/nvl_pipe.cu) */,
+               NVL_TASK_REDUCE_SYMM /* in-place NVLS allreduce on symmetric user memory (kernels/nvl_symm.cu) */ } nvl_task_kind_t;
 typedef enum { NVL_TASK_LAUNCHED, NVL_TASK_QUEUED } nvl_task_state_t;
 typedef struct ucc_tl_nvl_task {
     ucc_coll_task_t     super;

@@ -95,7 +95,7 @@ static void unmap_va(char *va, size_t size) { if (!va) return; ucc_cu.cuMemUnmap
 static ucc_status_t heap_alloc(ucc_tl_nvl_team_t *team, int want_mc)
 {
     ucc_tl_nvl_context_t *ctx = NVL_CTX(team);
-    size_t size = NVL_DATA_OFFSET + ctx->cfg.symmetric_size, gran = 2u << 20;
+    size_t size = NVL_DATA_OFFSET + ctx->cfg.symmetric_size + ctx->cfg.user_size, gran = 2u << 20;
     if (team->heap_kind == NVL_HEAP_VMM) {
         CUmemAllocationProp prop; size_t g = 0;
         vmm_prop(ctx->dev, &prop);
@@ -157,6 +157,7 @@ static void team_release(ucc_tl_nvl_team_t *team)
 /* create                                                              */
 /* ------------------------------------------------------------------ */
 static ucc_status_t team_finish(ucc_tl_nvl_team_t *team);
+static void registry_add(ucc_tl_nvl_team_t *team);
 ucc_status_t ucc_tl_nvl_team_create_post(ucc_base_context_t *b_ctx, const ucc_base_team_params_t *params, ucc_base_team_t **team_p)
 {
     ucc_tl_nvl_context_t *ctx = ucc_derived_of(b_ctx, ucc_tl_nvl_context_t);
@@ -288,6 +289,7 @@ static ucc_status_t team_finish(ucc_tl_nvl_team_t *team)
     team->dev.timeout_ns = (uint64_t)(ctx->cfg.timeout * 1e9);
     { void *dptr = NULL; CUDA_CHECK(cudaHostGetDevicePointer(&dptr, team->host_err, 0)); team->dev.host_err = (uint32_t *)dptr; }
     team->state = NVL_TEAM_READY;
+    if (!team->self && ctx->cfg.user_size) registry_add(team);
     tl_debug(NVL_LIB(team), "team %p ready: size %u, heap %s %zu MB, nvls %d", (void *)team, N,
              team->heap_kind == NVL_HEAP_LOCAL ? "local" : team->heap_kind == NVL_HEAP_VMM ? "vmm" : "ipc", team->heap_size >> 20, team->nvls);
     return UCC_OK;
@@ -379,9 +381,42 @@ fail:
     return st < 0 ? st : UCC_ERR_NOT_SUPPORTED;
 }
 
+/* ------------------------------------------------------------------ */
+/* symmetric user region                                               */
+/* ------------------------------------------------------------------ */
+/* ready teams, so that an application holding only the ucc_team_h can ask for the user region of the tl/nvl team that spans it */
+#define NVL_REG_MAX 64
+static ucc_tl_nvl_team_t *g_teams[NVL_REG_MAX];
+static ucc_spinlock_t     g_teams_lock;
+static void registry_add(ucc_tl_nvl_team_t *team)
+{ ucc_spin_lock(&g_teams_lock); for (int i = 0; i < NVL_REG_MAX; i++) if (!g_teams[i]) { g_teams[i] = team; break; } ucc_spin_unlock(&g_teams_lock); }
+static void registry_del(ucc_tl_nvl_team_t *team)
+{ ucc_spin_lock(&g_teams_lock); for (int i = 0; i < NVL_REG_MAX; i++) if (g_teams[i] == team) g_teams[i] = NULL; ucc_spin_unlock(&g_teams_lock); }
+
+/* Base address (in this process) and size of the symmetric user region of the tl/nvl team covering ALL members of `core_team`
+ * (UCC_TL_NVL_USER_SIZE > 0).  *nvls tells whether the region is bound to an NVSwitch multicast object, i.e. whether
+ * allreduce on buffers inside it takes the in-place in-switch path.  The caller sub-allocates; a buffer must sit at the
+ * same offset on every member. */
+UCC_EXPORT ucc_status_t ucc_tl_nvl_symm_region(ucc_team_h core_team, void **base, size_t *size, int *nvls)
+{
+    ucc_status_t st = UCC_ERR_NOT_FOUND;
+    ucc_spin_lock(&g_teams_lock);
+    for (int i = 0; i < NVL_REG_MAX; i++) {
+        ucc_tl_nvl_team_t *t = g_teams[i];
+        if (!t || t->self || (ucc_team_h)t->super.super.params.team != core_team || UCC_TL_TEAM_SIZE(t) != ucc_team_size_(core_team)) continue;
+        if (!NVL_CTX(t)->cfg.user_size) { st = UCC_ERR_NOT_SUPPORTED; continue; }
+        *base = t->heap + NVL_DATA_OFFSET + NVL_CTX(t)->cfg.symmetric_size; *size = NVL_CTX(t)->cfg.user_size;
+        if (nvls) *nvls = t->nvls;
+        st = UCC_OK; break;
+    }
+    ucc_spin_unlock(&g_teams_lock);
+    return st;
+}
+
 ucc_status_t ucc_tl_nvl_team_destroy(ucc_base_team_t *b)
 {
     ucc_tl_nvl_team_t *team = ucc_derived_of(b, ucc_tl_nvl_team_t);
+    registry_del(team);
     team_release(team);
     free(team);
     return UCC_OK;

@@ -100,3 +100,15 @@ def test_multiproc_nvls_pipe(heap):
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
     _run(n, {"UCC_TL_NVL_TUNE": "allreduce:cuda:inf:@nvls_pipe", "UCC_TL_NVL_ALLREDUCE_ONESHOT_THRESH": "0", "UCC_TL_NVL_SYMMETRIC_SIZE": heap})
+
+
+@pytest.mark.skipif(os.environ.get("UCC_B200_EXPERIMENTAL_TESTS") != "1", reason="symmetric-memory allreduce was written without GPU time left: set UCC_B200_EXPERIMENTAL_TESTS=1")
+def test_multiproc_symm():
+    """allreduce on tensors inside the symmetric user region: in-place multimem.ld_reduce / multimem.st (kernels/nvl_symm.cu)"""
+    n = min(2, torch.cuda.device_count()) if torch.cuda.is_available() else 0
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+           "--master-port", "29741", os.path.join(ROOT, "tests", "symm_worker.py")]
+    out = subprocess.run(cmd, env=dict(os.environ, PYTHONPATH=ROOT, SYMM_BENCH_BYTES=str(256 << 20)), capture_output=True, text=True, timeout=900)
+    assert "SYMM_WORKER_OK" in out.stdout or "SYMM_WORKER_SKIP" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]

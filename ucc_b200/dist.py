@@ -139,10 +139,12 @@ class Communicator:
     """lib + context + one team spanning `group` (default: all ranks)."""
 
     def __init__(self, group=None, thread_mode=U.UCC_THREAD_SINGLE, lib_modify=(), ctx_modify=(), store=None, rank=None, size=None, perm=None,
-                 fake_ppn=None):
+                 fake_ppn=None, symm_size=None):
         """`perm[g]` = UCC rank of group rank g (default identity): lets a team use any rank order (e.g. reversed).
         `fake_ppn` (or env UCC_B200_FAKE_PPN): pretend the ranks are spread over nodes of that many processes each - a
-        single-box way to exercise the hierarchical (cl/hier) schedules with real processes."""
+        single-box way to exercise the hierarchical (cl/hier) schedules with real processes.
+        `symm_size` (e.g. "2G"): reserve a symmetric user region in the tl/nvl team heap (UCC_TL_NVL_USER_SIZE); tensors from
+        `symm_empty()` live there and are all-reduced in place through the NVSwitch (no staging, no copy-out)."""
         if store is not None:
             self.rank, self.size = rank, size
             self.oob = _StoreOob(store, rank, size)
@@ -165,6 +167,8 @@ class Communicator:
         U.check(st, "ucc_init")
         ccfg = U.handle()
         U.check(U.ucc_context_config_read(self.lib, None, C.byref(ccfg)), "context_config_read")
+        if symm_size:
+            ctx_modify = tuple(ctx_modify) + (("tl/nvl", "USER_SIZE", str(symm_size)),)
         for comp, name, val in ctx_modify:
             U.check(U.ucc_context_config_modify(ccfg, comp.encode() if comp else None, name.encode(), val.encode()), "ctx_modify")
         cp = U.ucc_context_params_t()
@@ -196,6 +200,49 @@ class Communicator:
             U.ucc_context_progress(self.ctx)
         self._ees = {}
         self._posted = set()
+
+    # ------------------------------------------------------------------ symmetric user memory (tl/nvl)
+    def symm_region(self):
+        """(base pointer, bytes, nvls) of the symmetric user region of this team's tl/nvl heap, or None"""
+        if getattr(self, "_symm", None) is None:
+            self._symm = False
+            path = os.path.join(os.path.dirname(U.LIB_PATH), "ucc", "libucc_tl_nvl.so")
+            try:
+                fn = C.CDLL(path).ucc_tl_nvl_symm_region
+            except (OSError, AttributeError):
+                return None
+            fn.restype = C.c_int
+            fn.argtypes = [U.handle, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_int)]
+            base, size, nvls = C.c_void_p(), C.c_size_t(), C.c_int()
+            if fn(self.team, C.byref(base), C.byref(size), C.byref(nvls)) == U.UCC_OK and base.value:
+                self._symm = (base.value, size.value, bool(nvls.value))
+                self._symm_off = 0
+        return self._symm or None
+
+    def symm_empty(self, shape, dtype=torch.float32):
+        """Tensor inside the symmetric region (bump allocator, 256-byte aligned).  COLLECTIVE in spirit: every member must make
+        the same sequence of calls so that a tensor sits at the same offset everywhere."""
+        reg = self.symm_region()
+        if reg is None:
+            raise RuntimeError("no symmetric region: create the Communicator with symm_size=... (needs tl/nvl on CUDA devices)")
+        shape = (shape,) if isinstance(shape, int) else tuple(shape)
+        numel = 1
+        for d in shape:
+            numel *= d
+        nbytes = numel * torch.empty((), dtype=dtype).element_size()
+        off = (self._symm_off + 255) // 256 * 256
+        if off + nbytes > reg[1]:
+            raise MemoryError(f"symmetric region exhausted ({reg[1]} bytes)")
+        self._symm_off = off + nbytes
+
+        class _Raw:   # zero-copy view of device memory for torch.as_tensor
+            __cuda_array_interface__ = {"shape": (max(nbytes, 1),), "typestr": "|u1", "data": (reg[0] + off, False), "version": 2}
+        raw = torch.as_tensor(_Raw(), device=torch.device("cuda", torch.cuda.current_device()))
+        return raw[:nbytes].view(dtype).view(shape)
+
+    def symm_reset(self):
+        """forget every symm_empty() allocation (the tensors must no longer be used)"""
+        self._symm_off = 0
 
     # ------------------------------------------------------------------ streams
     def ee_for(self, stream=None):

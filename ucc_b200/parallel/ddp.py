@@ -14,10 +14,11 @@ from .. import ops
 
 
 class _Bucket:
-    def __init__(self, params, dtype, device):
+    def __init__(self, params, dtype, device, alloc=None):
         self.params = params
         n = sum(p.numel() for p in params)
-        self.flat = torch.zeros(n, dtype=dtype, device=device)
+        # `alloc`: symmetric-memory allocator of the communicator (gradient buckets are then reduced in place in the switch)
+        self.flat = alloc(n, dtype).zero_() if alloc is not None else torch.zeros(n, dtype=dtype, device=device)
         self.pending = 0
         self.req = None
         self.ready_event = torch.cuda.Event() if device.type == "cuda" else None
@@ -28,10 +29,13 @@ class _Bucket:
 
 
 class DistributedDataParallel(nn.Module):
-    def __init__(self, module: nn.Module, comm=None, bucket_mb: float = 25.0, broadcast_params: bool = True):
+    def __init__(self, module: nn.Module, comm=None, bucket_mb: float = 25.0, broadcast_params: bool = True, symmetric_buckets: bool = False):
+        """`symmetric_buckets`: place the gradient buckets in the communicator's symmetric user region (Communicator(symm_size=...));
+        every rank builds the same buckets in the same order, so they land at the same offsets."""
         super().__init__()
         self.module = module
         self.comm = comm or ops.default_comm()
+        self._alloc = self.comm.symm_empty if symmetric_buckets and getattr(self.comm, "symm_region", lambda: None)() else None
         self.buckets = []
         self._of = {}
         params = [p for p in module.parameters() if p.requires_grad]
@@ -57,7 +61,7 @@ class DistributedDataParallel(nn.Module):
         self._arm()
 
     def _add_bucket(self, params, dtype, dev):
-        b = _Bucket(params, dtype, dev)
+        b = _Bucket(params, dtype, dev, self._alloc if dev.type == "cuda" else None)
         for p in params:
             self._of[p] = b
         self.buckets.append(b)
