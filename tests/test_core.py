@@ -388,3 +388,81 @@ def test_mem_map_export_import():
         # unsupported modes
         assert U.lib.ucc_mem_map(j.procs[0].ctx, 2, C.byref(params), C.byref(size), C.byref(C.c_void_p())) == U.UCC_ERR_NOT_SUPPORTED
         assert U.lib.ucc_mem_unmap(C.byref(memh)) == U.UCC_OK
+
+
+def test_service_collectives_with_subsets():
+    """Internal service collectives (reference test/gtest/core/test_service_coll.cc): allreduce / allgather / bcast over the
+    service team restricted to SUBSETS of a team given as ep maps (full, strided, arbitrary array)."""
+    class _Map(C.Structure):            # ucc_ep_map_t with the union flattened (ctypes cannot pass unions by value)
+        _fields_ = [("type", C.c_int), ("ep_num", C.c_uint64), ("a", C.c_uint64), ("b", C.c_uint64)]
+
+    class _Subset(C.Structure):
+        _fields_ = [("map", _Map), ("myrank", C.c_uint32)]
+    L = U.lib
+    L.ucc_service_allreduce.argtypes = [U.handle, C.c_void_p, C.c_void_p, C.c_uint64, C.c_size_t, C.c_int, _Subset, C.POINTER(C.c_void_p)]
+    L.ucc_service_allgather.argtypes = [U.handle, C.c_void_p, C.c_void_p, C.c_size_t, _Subset, C.POINTER(C.c_void_p)]
+    L.ucc_service_bcast.argtypes = [U.handle, C.c_void_p, C.c_size_t, C.c_uint32, _Subset, C.POINTER(C.c_void_p)]
+    for f in (L.ucc_service_allreduce, L.ucc_service_allgather, L.ucc_service_bcast, L.ucc_service_coll_test, L.ucc_service_coll_finalize):
+        f.restype = C.c_int
+    L.ucc_service_coll_test.argtypes = [C.c_void_p]
+    L.ucc_service_coll_finalize.argtypes = [C.c_void_p]
+    EP_FULL, EP_STRIDED, EP_ARRAY = 1, 2, 3
+    assert (U.UCC_EP_MAP_FULL, U.UCC_EP_MAP_STRIDED, U.UCC_EP_MAP_ARRAY) == (EP_FULL, EP_STRIDED, EP_ARRAY)
+    n = 6
+    with UccJob(n) as j:
+        team = j.create_team()
+
+        def wait_all(reqs):
+            t0 = time.time()
+            pending = dict(reqs)
+            while pending:
+                for r in list(pending):
+                    st = L.ucc_service_coll_test(pending[r])
+                    assert st >= 0, st
+                    if st == U.UCC_OK:
+                        assert L.ucc_service_coll_finalize(pending.pop(r)) == U.UCC_OK
+                for p in j.procs:
+                    U.ucc_context_progress(p.ctx)
+                assert time.time() - t0 < 60
+        arr = np.array([4, 0, 3], dtype=np.uint32)         # arbitrary order: subset rank i = team rank arr[i]
+        subsets = {
+            "full": (list(range(n)), lambda: _Map(EP_FULL, n, 0, 0)),
+            "odd": ([1, 3, 5], lambda: _Map(EP_STRIDED, 3, 1, 2)),
+            "array": ([4, 0, 3], lambda: _Map(EP_ARRAY, 3, arr.ctypes.data, 4)),
+        }
+        for name, (members, mk) in subsets.items():
+            m = len(members)
+            # allreduce MAX + SUM on int64 pairs
+            src = {r: np.array([r + 1, 10 * (r + 1)], np.int64) for r in members}
+            dst = {r: np.zeros(2, np.int64) for r in members}
+            reqs = {}
+            for i, r in enumerate(members):
+                q = C.c_void_p()
+                st = L.ucc_service_allreduce(team.members[r].team, src[r].ctypes.data, dst[r].ctypes.data, U.DT["int64"], 2, U.OP["sum"], _Subset(mk(), i), C.byref(q))
+                assert st == U.UCC_OK, (name, st)
+                reqs[r] = q
+            wait_all(reqs)
+            for r in members:
+                assert dst[r].tolist() == [sum(x + 1 for x in members), 10 * sum(x + 1 for x in members)], (name, r, dst[r])
+            # allgather of 3 bytes per member, in subset-rank order
+            sb = {r: np.array([r, r + 100, r + 200], np.uint8) for r in members}
+            rb = {r: np.zeros(3 * m, np.uint8) for r in members}
+            reqs = {}
+            for i, r in enumerate(members):
+                q = C.c_void_p()
+                assert L.ucc_service_allgather(team.members[r].team, sb[r].ctypes.data, rb[r].ctypes.data, 3, _Subset(mk(), i), C.byref(q)) == U.UCC_OK
+                reqs[r] = q
+            wait_all(reqs)
+            exp = np.concatenate([sb[r] for r in members])
+            for r in members:
+                assert np.array_equal(rb[r], exp), (name, r)
+            # bcast from subset root 1
+            bb = {r: (np.arange(17, dtype=np.uint8) + 5 if i == 1 else np.zeros(17, np.uint8)) for i, r in enumerate(members)}
+            reqs = {}
+            for i, r in enumerate(members):
+                q = C.c_void_p()
+                assert L.ucc_service_bcast(team.members[r].team, bb[r].ctypes.data, 17, 1, _Subset(mk(), i), C.byref(q)) == U.UCC_OK
+                reqs[r] = q
+            wait_all(reqs)
+            for r in members:
+                assert np.array_equal(bb[r], np.arange(17, dtype=np.uint8) + 5), (name, r)
