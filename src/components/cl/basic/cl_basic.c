@@ -146,6 +146,11 @@ static ucc_status_t basic_team_create_test(ucc_base_team_t *b)
     if (st != UCC_OK) goto fail_noreq;
     st = ucc_coll_score_build_map(score, &team->score_map);
     if (st != UCC_OK) { ucc_coll_score_free(score); goto fail_noreq; }
+    if (b->params.rank == 0 && ucc_global_log_component.log_level >= UCC_LOG_LEVEL_INFO) {
+        /* the core prints the CL-level map (one CL_BASIC range per collective); this is what is behind it: TL, score, algorithm */
+        ucc_info("----- cl/basic selection (size %u, scope %d) -----", b->params.size, b->params.scope);
+        ucc_coll_score_map_print_info(team->score_map, UCC_LOG_LEVEL_INFO);
+    }
     return UCC_OK;
 fail:
     ucc_team_multiple_req_free(team->team_create_req);

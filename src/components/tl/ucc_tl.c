@@ -3,6 +3,9 @@
 #include "core/ucc_team.h"
 #include "core/ucc_global_opts.h"
 #include "utils/ucc_string.h"
+#include "utils/ucc_parser.h"
+#include "utils/arch/cpu.h"
+#include "components/topo/ucc_topo.h"
 
 ucc_config_field_t ucc_tl_lib_config_table[] = {
     {"", "", NULL, ucc_offsetof(ucc_tl_lib_config_t, super), UCC_CONFIG_TYPE_TABLE(ucc_base_lib_config_table)}, {NULL}};
@@ -82,6 +85,29 @@ ucc_status_t ucc_tl_apply_tune(ucc_tl_team_t *team, ucc_coll_score_t *score, con
         /* a bad user string is reported but does not disable the component (reference tl_cuda_team.c:620-627) */
         if (st == UCC_ERR_INVALID_PARAM || st == UCC_ERR_NOT_SUPPORTED) tl_warn(lib, "ignoring invalid TUNE string \"%s\"", user_tune);
         else if (st != UCC_OK) return st;
+    }
+    /* [section]s of the configuration file that are predicated on team facts (team_size / ppn / nnodes / sockets / cpu) may carry
+     * a <TL>_TUNE of their own: it is applied last, per team (reference: ucc_add_team_sections, utils/ucc_parser.c:612-655,
+     * called from tl_ucp_team.c:82-88) */
+    if (ucc_global_config.file_cfg && team->super.params.team && team->super.params.scope != UCC_CL_LAST && lib->use_tuning) {
+        ucc_team_t *core = team->super.params.team;
+        ucc_tl_iface_t *iface = UCC_TL_TEAM_IFACE(team);
+        ucc_file_section_filter_t f;
+        char key[128]; const char *sec_tune;
+        memset(&f, 0, sizeof(f));
+        f.vendor = ucc_cpu_vendor_string(ucc_arch_get_cpu_vendor()); f.model = ucc_arch_get_cpu_model_string();
+        f.team_size = (unsigned)team->super.params.size;
+        if (core->topo && team->super.params.size == core->size) {
+            f.ppn = (unsigned)ucc_topo_max_ppn(core->topo); f.nnodes = (unsigned)ucc_topo_nnodes(core->topo); f.sock = (unsigned)core->topo->max_socket_size;
+        } else if (core->size == team->super.params.size && core->contexts[0]->addr_storage.flags) { f.ppn = f.team_size; f.nnodes = 1; }
+        snprintf(key, sizeof(key), "UCC_%sTUNE", iface->tl_context_config.prefix ? iface->tl_context_config.prefix : "");
+        sec_tune = ucc_file_config_lookup(ucc_global_config.file_cfg, key, &f);
+        if (sec_tune && sec_tune[0] && (!user_tune || strcmp(sec_tune, user_tune))) {
+            st = ucc_coll_score_update_from_str(sec_tune, info, &team->super, score);
+            if (st == UCC_ERR_INVALID_PARAM || st == UCC_ERR_NOT_SUPPORTED) tl_warn(lib, "ignoring invalid TUNE string \"%s\" of a configuration file section", sec_tune);
+            else if (st != UCC_OK) return st;
+            else tl_debug(lib, "team size %u: applied section tuning \"%s\"", f.team_size, sec_tune);
+        }
     }
     return UCC_OK;
 }

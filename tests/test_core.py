@@ -466,3 +466,35 @@ def test_service_collectives_with_subsets():
             wait_all(reqs)
             for r in members:
                 assert np.array_equal(bb[r], np.arange(17, dtype=np.uint8) + 5), (name, r)
+
+
+def test_config_file_team_sections(tmp_path):
+    """[sections] predicated on team facts carry per-team TUNE strings (reference ucc_add_team_sections, tl_ucp_team.c:82-88):
+    one process creates teams of 5 and of 3 ranks and each gets the algorithm its section names."""
+    import subprocess
+    import sys
+    f = tmp_path / "ucc.conf"
+    f.write_text("[big team_size=4-64]\nUCC_TL_SHM_TUNE = allreduce:0-inf:@ring\n\n[small team_size=2-3]\nUCC_TL_SHM_TUNE = allreduce:0-inf:@dbt\n\n"
+                 "[never team_size=2-64 nnodes=5-9]\nUCC_TL_SHM_TUNE = allreduce:0-inf:@sliding_window\n")
+    code = (
+        "import numpy as np, sys\n"
+        "from ucc_b200 import capi as U\n"
+        "from ucc_b200.harness import UccJob, coll_args\n"
+        "for n in (5, 3):\n"
+        "    j = UccJob(n); t = j.create_team()\n"
+        "    s = [np.full(4096, r + 1.0, np.float32) for r in range(n)]; d = [np.zeros(4096, np.float32) for _ in range(n)]\n"
+        "    q = t.coll([coll_args('allreduce', s[r], d[r]) for r in range(n)]); assert q.run() == 0; q.finalize()\n"
+        "    assert np.all(d[0] == n * (n + 1) / 2)\n"
+        "    sys.stdout.flush(); sys.stderr.flush(); print('TEAM_DONE', n, flush=True)\n"
+        "    j.cleanup()\n")
+    env = dict(os.environ, UCC_CONFIG_FILE=str(f), UCC_LOG_LEVEL="info", PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    env.pop("UCC_TL_SHM_TUNE", None)
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr[-2000:]
+    txt = out.stdout + out.stderr
+    first, second = txt.split("TEAM_DONE 5")[0], txt.split("TEAM_DONE 5")[1]
+    assert "sliding_window" not in txt
+    # at INFO level cl/basic prints the TL-level map: "allreduce host: {0..4K}:TL_SHM:10:<algorithm> ..."
+    sel = lambda t: [ln for ln in t.splitlines() if "allreduce host:" in ln and "TL_SHM" in ln]  # noqa: E731
+    assert sel(first) and all(":ring" in ln and ":dbt" not in ln for ln in sel(first)), first[-1500:]
+    assert sel(second) and all(":dbt" in ln for ln in sel(second)), second[-1500:]
