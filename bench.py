@@ -31,6 +31,8 @@ def parse():
     ap.add_argument("--dtype", default="float32")
     ap.add_argument("--e2e-chunks", type=int, default=1,
                     help="end-to-end step: > 1 cuts the step into chunks whose H2D copy overlaps the previous chunk's allreduce (not validated on hardware yet)")
+    ap.add_argument("--symm", default="", help="opt-in (not yet measured): put the device buffers into a symmetric user region of this size, "
+                    "e.g. 3G (Communicator(symm_size=...).symm_empty, the ncclMemAlloc analogue): in-place in-switch allreduce")
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-nccl", action="store_true")
@@ -94,7 +96,11 @@ def main():
     dev = torch.device("cuda", torch.cuda.current_device())
     dt = getattr(torch, a.dtype)
     esz = torch.empty(0, dtype=dt).element_size()
-    comm = Communicator()
+    comm = Communicator(symm_size=a.symm) if a.symm else Communicator()
+    use_symm = bool(a.symm) and comm.symm_region() is not None
+
+    def dev_empty(cnt):
+        return comm.symm_empty(cnt, dt) if use_symm else torch.empty(cnt, dtype=dt, device=dev)
     stream = torch.cuda.Stream()
     launches = {"n": 0}
 
@@ -117,8 +123,10 @@ def main():
     def time_ours(nbytes, iters, warm, inplace=False):
         """device time per allreduce (us, max over ranks): `iters` requests posted back to back on one stream"""
         cnt = nbytes // esz
-        src = torch.ones(cnt, dtype=dt, device=dev)
-        dst = src if inplace else torch.empty(cnt, dtype=dt, device=dev)
+        if use_symm:
+            comm.symm_reset()           # earlier buffers are dead by now
+        src = dev_empty(cnt).fill_(1) if use_symm else torch.ones(cnt, dtype=dt, device=dev)
+        dst = src if inplace else dev_empty(cnt)
         reqs = [comm.allreduce_init(src, dst) for _ in range(warm + iters)]
         with torch.cuda.stream(stream):
             for r in reqs[:warm]:
@@ -175,8 +183,10 @@ def main():
     if not a.no_e2e:
         cnt = S // esz
         host = torch.ones(cnt, dtype=dt).pin_memory()
-        src = torch.empty(cnt, dtype=dt, device=dev)
-        dst = torch.empty(cnt, dtype=dt, device=dev)
+        if use_symm:
+            comm.symm_reset()
+        src = dev_empty(cnt)
+        dst = dev_empty(cnt)
         out = torch.empty(16, dtype=dt).pin_memory()
 
         # The step is cut into chunks so that the H2D copy of chunk c+1 (copy engine, its own stream) overlaps the
@@ -248,7 +258,8 @@ def main():
         "data": "synthetic (ones), CUDA device buffers", "impl": "ours",
         "config": {"model": "ucc_perftest allreduce", "collective": "allreduce", "op": "sum", "message_bytes": S, "global_batch": S * N,
                    "seq_len": S // esz, "parallelism": f"dp{N}", "timing": "cuda events on the posting stream, max over ranks",
-                   "l2": "message (1 GiB) is larger than the 126 MB L2", "algorithm": "tl/nvl fused kernel chosen by coll_score"},
+                   "l2": "message (1 GiB) is larger than the 126 MB L2", "algorithm": "tl/nvl fused kernel chosen by coll_score",
+                   "symmetric_memory": use_symm},
         "correct": bool(ok), "clocks": clocks, "gpu_launches": launches["n"],
         "latency_us": round(us, 2), "roofline_frac_of_900": round(value / 900.0, 4) if N > 1 else None, "roofline_frac_of_measured_770": round(value / 770.0, 4) if N > 1 else None,
         "roofline_frac_of_hbm_copy_6478": round(2.0 * value / 6478.3, 4) if N == 1 else None,

@@ -13,6 +13,7 @@ for alg in default nvls nvls_pipe; do
   UCC_TL_NVL_TUNE="$T" UCC_TL_NVL_ALLREDUCE_ONESHOT_THRESH=0 timeout 300 $TR bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/bench_${alg}_$N.log 2>&1
   UCC_TL_NVL_SYMMETRIC_SIZE=384M UCC_TL_NVL_TUNE="$T" UCC_TL_NVL_ALLREDUCE_ONESHOT_THRESH=0 timeout 300 $TR bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/bench_${alg}_heap384_$N.log 2>&1
 done
+timeout 300 $TR bench.py --gpus $N --steps 10 --warmup 3 --symm 3G > gpurun_out/bench_symm_$N.log 2>&1
 timeout 600 $TR tools/ucc_test_dist.py -M cuda -t world,reverse -I 2 -P 2 -i 2 -m 64:4194304:16 -r all -d int32,float32,bfloat16 -o sum,max,avg --triggered 2 > gpurun_out/test_dist_cuda_$N.log 2>&1
 SYMM_SIZE=3G timeout 400 $TR tests/symm_worker.py > gpurun_out/symm_$N.log 2>&1
 timeout 200 python -m pytest tests/test_nvl_gpu.py -x -q -m gpu -k asymmetric 2>&1 | tail -15 > gpurun_out/asym_test.log
