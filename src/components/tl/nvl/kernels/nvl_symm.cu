@@ -1,4 +1,4 @@
-/* In-place NVLS allreduce on SYMMETRIC USER MEMORY (UCC_TL_NVL_USER_SIZE > 0).
+/* In-place NVLS allreduce (and reduce_scatter(v) out of a symmetric source) on SYMMETRIC USER MEMORY (UCC_TL_NVL_USER_SIZE > 0).
  *
  * When src and dst live in the user region of the team heap (allocated through ucc_tl_nvl_symm_region(), same offsets on every
  * member - the NVSHMEM / ncclMemAlloc+register contract), they are already bound to the team's multicast object.  Nothing is
@@ -22,12 +22,36 @@ static __device__ __forceinline__ void symm_body(const nvl_red_args_t &a, BlockS
     constexpr int U = 8;
     const nvl_team_dev_t &t = a.team;
     const int N = t.size, me = t.rank;
-    const size_t so = (size_t)(a.d.src[0] - t.heap[me]), dof = (size_t)(a.d.dst[0] - t.heap[me]);
+    const bool rs = a.kind == NVL_RED_REDUCE_SCATTER;   /* reduce_scatter(v): only src is symmetric, my block goes to the local a.dst */
+    const size_t so = (size_t)(a.d.src[0] - t.heap[me]), dof = rs ? 0 : (size_t)(a.d.dst[0] - t.heap[me]);
     const float inv_n = 1.0f / (float)N;
     const size_t nt = blockDim.x;
 
     bs.barrier(t, 1);
-    {
+    if (rs) {
+        const size_t cnt = pl.cnt[me], nv = (cnt + E - 1) / E;
+        const size_t per = (nv + gridDim.x - 1) / gridDim.x, j0 = dmin((size_t)blockIdx.x * per, nv), j1 = dmin(j0 + per, nv);
+        const char *mcs = t.mc_heap + so + pl.off[me] * sizeof(T);
+        T *db = static_cast<T *>(a.dst);
+        const bool dal = ((uintptr_t)db & 15) == 0;
+        size_t j = j0 + threadIdx.x;
+        for (; j + (size_t)(U - 1) * nt < j1; j += (size_t)U * nt) {
+            uint4 r[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) r[u] = McRed<T, OP>::ld(mcs + (j + (size_t)u * nt) * 16);
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                uint4 v = r[u];
+                if (OP == NVL_OP_AVG) { VecAcc<T, OP> acc; acc.set(v); v = acc.get(inv_n); }
+                store_dst_vec<T>(db, (j + (size_t)u * nt) * E, cnt, dal, v);   /* bounds-checked: the ragged last vector is cut at cnt */
+            }
+        }
+        for (; j < j1; j += nt) {
+            uint4 v = McRed<T, OP>::ld(mcs + j * 16);
+            if (OP == NVL_OP_AVG) { VecAcc<T, OP> acc; acc.set(v); v = acc.get(inv_n); }
+            store_dst_vec<T>(db, j * E, cnt, dal, v);
+        }
+    } else {
         const size_t cnt = pl.cnt[me], nfull = cnt / E, nv = (cnt + E - 1) / E;
         const size_t per = (nv + gridDim.x - 1) / gridDim.x, j0 = dmin((size_t)blockIdx.x * per, nv), j1 = dmin(j0 + per, nv);
         const size_t jfull = dmin(j1, nfull);                               /* whole vectors of my range */
@@ -75,7 +99,8 @@ template <typename T> __global__ void __launch_bounds__(NVL_THREADS_MAX, 2) nvl_
 extern "C" cudaError_t nvl_launch_reduce_symm(const nvl_red_args_t *a, int nblocks, int nthreads, cudaStream_t s)
 {
     if (nthreads > NVL_THREADS_MAX) nthreads = NVL_THREADS_MAX;
-    if (a->kind != NVL_RED_ALLREDUCE || !a->team.mc_heap || !nvl_nvls_supports(a->dt, a->op) || !a->d.src[0] || !a->d.dst[0]) return cudaErrorInvalidValue;
+    if ((a->kind != NVL_RED_ALLREDUCE && a->kind != NVL_RED_REDUCE_SCATTER) || !a->team.mc_heap || !nvl_nvls_supports(a->dt, a->op) || !a->d.src[0]) return cudaErrorInvalidValue;
+    if (a->kind == NVL_RED_ALLREDUCE && !a->d.dst[0]) return cudaErrorInvalidValue;
     switch (a->dt) {
     case NVL_DT_F32: nvl_allreduce_symm_kernel<float><<<nblocks, nthreads, 0, s>>>(*a); break;
     case NVL_DT_F16: nvl_allreduce_symm_kernel<__half><<<nblocks, nthreads, 0, s>>>(*a); break;

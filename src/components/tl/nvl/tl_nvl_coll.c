@@ -363,6 +363,20 @@ static ucc_status_t red_init(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, u
             return UCC_OK;
         }
     }
+    /* reduce_scatter(v) out of a symmetric source (the FSDP / ZeRO gradient shape): every block is reduced in the switch
+     * straight into its owner's destination, which may be any local buffer */
+    if ((alg == RED_ALG_TWOSHOT || alg == RED_ALG_NVLS) && r->kind == NVL_RED_REDUCE_SCATTER && !inplace && team->nvls && ctx->cfg.user_size && nvl_nvls_supports(ndt, nop)) {
+        const char *ub = team->heap + NVL_DATA_OFFSET + ctx->cfg.symmetric_size, *ue = ub + ctx->cfg.user_size;
+        const char *s0 = (const char *)src;
+        int aligned = !((uintptr_t)s0 & 15);
+        for (ucc_rank_t i = 0; i < N; i++) if ((r->rs_offset[i] * ucc_dt_size(dt)) & 15) aligned = 0;
+        if (aligned && s0 >= ub && s0 + ucc_align_up(bytes, 16) <= ue) {
+            t->kind = NVL_TASK_REDUCE_SYMM; r->d.src[0] = s0; r->d.dst[0] = NULL; r->use_nvls = 1;
+            t->nblocks = pick_blocks(ctx, bytes / N, 32 * 1024);
+            *task_p = &t->super;
+            return UCC_OK;
+        }
+    }
     /* zero-copy: every criterion below is evaluated identically on all ranks (sizes / counts are collective
      * arguments); what only the owner knows (can the buffer be exported? is it aligned?) travels with the exchange */
     if ((alg == RED_ALG_TWOSHOT || alg == RED_ALG_NVLS) && team->zcopy && ctx->cfg.zcopy != UCC_NO && bytes >= ctx->cfg.zcopy_thresh) {

@@ -50,6 +50,26 @@ def main():
                 if not bool((guard == 12345).all()):
                     print(f"rank {rank}: guard behind dst overwritten dt {dt} count {count}", flush=True)
                     ok = False
+    # reduce_scatter out of a symmetric source into an ordinary tensor (ZeRO / FSDP gradient shape)
+    for dt, tol in ((torch.float32, 1e-5), (torch.bfloat16, 3e-2)):
+        for blk in (8, 1000, 262144 + 8):
+            comm.symm_reset()
+            g = torch.Generator().manual_seed(5 + blk)
+            alls = [(torch.rand(blk * world, generator=g) * 4 + r).to(dt) for r in range(world)]
+            src = comm.symm_empty(blk * world, dt)
+            src.copy_(alls[rank].to(dev))
+            dst = torch.zeros(blk, dtype=dt, device=dev)
+            torch.cuda.synchronize()
+            comm.barrier()
+            req = comm.coll_init("reduce_scatter", src, dst)
+            req.post_on_stream()
+            req.wait()
+            req.finalize()
+            torch.cuda.synchronize()
+            exp = sum(a.double() for a in alls)[rank * blk:(rank + 1) * blk]
+            if not torch.allclose(dst.cpu().double(), exp, rtol=tol * world, atol=tol * world):
+                print(f"rank {rank}: symm reduce_scatter mismatch dt {dt} blk {blk}", flush=True)
+                ok = False
     # bandwidth: 1 GiB f32 in place, symmetric vs ordinary tensors
     n = int(os.environ.get("SYMM_BENCH_BYTES", str(1 << 30))) // 4
     comm.symm_reset()
