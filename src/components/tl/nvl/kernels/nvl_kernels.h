@@ -119,6 +119,8 @@ cudaError_t  nvl_launch_reduce_steps(const nvl_red_args_t *a, int nblocks, int n
 cudaError_t  nvl_launch_reduce_pipe(const nvl_red_args_t *a, int nblocks, int nthreads, cudaStream_t s);
 /* in-place NVLS allreduce on symmetric user memory: a->d.src[0] / a->d.dst[0] = local addresses inside my heap mapping */
 cudaError_t  nvl_launch_reduce_symm(const nvl_red_args_t *a, int nblocks, int nthreads, cudaStream_t s);
+/* allgather into a symmetric destination: a->src/src_bytes = my block, a->dst = local address of the gathered buffer in my heap, a->push_off = my offset */
+cudaError_t  nvl_launch_allgather_symm(const nvl_xchg_args_t *a, int nblocks, int nthreads, cudaStream_t s);
 cudaError_t  nvl_launch_exchange(const nvl_xchg_args_t *a, int nblocks, int nthreads, cudaStream_t s);
 cudaError_t  nvl_launch_barrier(const nvl_team_dev_t *t, cudaStream_t s);
 cudaError_t  nvl_launch_self_copy(void *dst, const void *src, size_t bytes, int nblocks, int nthreads, cudaStream_t s); /* team of one */

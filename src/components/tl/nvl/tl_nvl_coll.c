@@ -46,6 +46,7 @@ static ucc_status_t nvl_launch(ucc_tl_nvl_task_t *t, cudaStream_t s)
     case NVL_TASK_REDUCE_STEPS: e = nvl_launch_reduce_steps(&t->u.red, t->nblocks, t->nthreads, s); break;
     case NVL_TASK_REDUCE_PIPE: e = nvl_launch_reduce_pipe(&t->u.red, t->nblocks, t->nthreads, s); break;
     case NVL_TASK_REDUCE_SYMM: e = nvl_launch_reduce_symm(&t->u.red, t->nblocks, t->nthreads, s); break;
+    case NVL_TASK_AG_SYMM: e = nvl_launch_allgather_symm(&t->u.xchg, t->nblocks, t->nthreads, s); break;
     case NVL_TASK_XCHG: e = nvl_launch_exchange(&t->u.xchg, t->nblocks, t->nthreads, s); break;
     case NVL_TASK_SELF_COPY:
         e = t->u.xchg.src_bytes ? nvl_launch_self_copy(t->u.xchg.dst, t->u.xchg.src, t->u.xchg.src_bytes, t->nblocks, t->nthreads, s) : cudaSuccess;
@@ -142,7 +143,7 @@ static ucc_status_t nvl_post_on(ucc_tl_nvl_task_t *t, cudaStream_t s)
     if (cudaStreamIsCapturing(s, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusActive) t->captured = 1;
     ucc_spin_lock(&team->launch_lock);
     direct = task_is_direct(t);
-    if (t->kind == NVL_TASK_XCHG) t->u.xchg.direct = 0; else t->u.red.direct = NVL_DIRECT_NONE;
+    if (t->kind == NVL_TASK_XCHG || t->kind == NVL_TASK_AG_SYMM) t->u.xchg.direct = 0; else t->u.red.direct = NVL_DIRECT_NONE;
     if (direct) {
         /* the exchange sequence advances on every rank in post order; a capturing stream cannot wait for the
          * peers, so it tells them "not usable" and everybody takes the staged kernel for this one */
@@ -427,6 +428,20 @@ static ucc_status_t xchg_init(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, 
         if (!is_cuda(a->dst.info.mem_type) || (!inplace && !is_cuda(a->src.info.mem_type))) return UCC_ERR_NOT_SUPPORTED;
         x.dst = a->dst.info.buffer; x.src = inplace ? (char *)x.dst + me * blk : a->src.info.buffer; x.src_bytes = blk;
         for (ucc_rank_t p = 0; p < N; p++) { x.pull_off[p] = 0; x.pull_bytes[p] = blk; x.dst_off[p] = p * blk; }
+        /* destination in the symmetric user region (same offset on every member by contract): multicast my block straight
+         * into everybody's dst - nothing staged, pulled or copied out */
+        if (team->nvls && ctx->cfg.user_size && blk && !(blk & 15) && !(((uintptr_t)x.src | (uintptr_t)x.dst) & 15)) {
+            const char *ub = team->heap + NVL_DATA_OFFSET + ctx->cfg.symmetric_size, *ue = ub + ctx->cfg.user_size, *d0 = (const char *)x.dst;
+            if (d0 >= ub && d0 + blk * N <= ue) {
+                st = task_alloc(b, b_team, &t);
+                if (st != UCC_OK) return st;
+                x.push_off = (size_t)me * blk;
+                t->kind = NVL_TASK_AG_SYMM; t->u.xchg = x;
+                t->nblocks = pick_blocks(ctx, blk, 32 * 1024);
+                *task_p = &t->super;
+                return UCC_OK;
+            }
+        }
         moved = blk * N; break; }
     case UCC_COLL_TYPE_ALLGATHERV: {
         dts = ucc_dt_size(a->dst.info_v.datatype);
@@ -537,6 +552,7 @@ static ucc_status_t xchg_init_nvls(ucc_base_coll_args_t *b, ucc_base_team_t *b_t
     st = xchg_init(b, b_team, task_p);
     if (st != UCC_OK) return st;
     t = ucc_derived_of(*task_p, ucc_tl_nvl_task_t); x = &t->u.xchg;
+    if (t->kind != NVL_TASK_XCHG) return UCC_OK; /* symmetric-destination allgather or single-member copy: already complete */
     t->want_direct = 0;
     if (ct == UCC_COLL_TYPE_BCAST) { x->push_off = 0; off = x->src_bytes; }
     else for (ucc_rank_t p = 0; p < N; p++) { if (p == me) x->push_off = off; x->pull_off[p] = off; off += ucc_align_up(x->pull_bytes[p] ? x->pull_bytes[p] : (p == me ? x->src_bytes : 0), 16); }
@@ -557,6 +573,7 @@ static ucc_status_t xchg_init_ring(ucc_base_coll_args_t *b, ucc_base_team_t *b_t
     st = xchg_init(b, b_team, task_p);
     if (st != UCC_OK) return st;
     t = ucc_derived_of(*task_p, ucc_tl_nvl_task_t); x = &t->u.xchg;
+    if (t->kind != NVL_TASK_XCHG) return UCC_OK; /* symmetric-destination allgather or single-member copy: already complete */
     t->want_direct = 0;
     for (ucc_rank_t p = 0; p < N; p++) { x->pull_off[p] = off; off += ucc_align_up(x->pull_bytes[p], 16); }
     if (off > cap) { (*task_p)->finalize(*task_p); *task_p = NULL; return UCC_ERR_NOT_SUPPORTED; }

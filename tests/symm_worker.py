@@ -70,6 +70,28 @@ def main():
             if not torch.allclose(dst.cpu().double(), exp, rtol=tol * world, atol=tol * world):
                 print(f"rank {rank}: symm reduce_scatter mismatch dt {dt} blk {blk}", flush=True)
                 ok = False
+    # allgather into a symmetric destination (multimem.st of every block), plain and in place
+    for blk in (4, 1000, 262144 + 4):
+        for inplace in (False, True):
+            comm.symm_reset()
+            dst = comm.symm_empty(blk * world, torch.float32)
+            guard = comm.symm_empty(64, torch.int32)
+            guard.fill_(777)
+            dst.zero_()
+            mine = torch.arange(blk, dtype=torch.float32, device=dev) + 1000 * rank
+            if inplace:
+                dst[rank * blk:(rank + 1) * blk].copy_(mine)
+            torch.cuda.synchronize()
+            comm.barrier()
+            req = comm.coll_init("allgather", None if inplace else mine, dst, inplace=inplace)
+            req.post_on_stream()
+            req.wait()
+            req.finalize()
+            torch.cuda.synchronize()
+            exp = torch.cat([torch.arange(blk, dtype=torch.float32) + 1000 * r for r in range(world)])
+            if not torch.equal(dst.cpu(), exp) or not bool((guard == 777).all()):
+                print(f"rank {rank}: symm allgather mismatch blk {blk} inplace {inplace}", flush=True)
+                ok = False
     # bandwidth: 1 GiB f32 in place, symmetric vs ordinary tensors
     n = int(os.environ.get("SYMM_BENCH_BYTES", str(1 << 30))) // 4
     comm.symm_reset()

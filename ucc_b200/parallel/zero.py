@@ -12,7 +12,10 @@ from .. import ops
 
 
 class ZeroRedundancyTrainer:
-    def __init__(self, module: nn.Module, optimizer_cls=torch.optim.SGD, comm=None, **optim_kw):
+    def __init__(self, module: nn.Module, optimizer_cls=torch.optim.SGD, comm=None, symmetric: bool = False, **optim_kw):
+        """`symmetric`: keep the flat parameter and gradient buffers in the communicator's symmetric user region
+        (Communicator(symm_size=...)): the reduce_scatter then reduces in the switch straight out of the gradient buffer and
+        the allgather multicasts the updated shards straight into every member's parameter buffer."""
         self.module = module
         self.comm = comm or ops.default_comm()
         n = self.comm.size
@@ -21,8 +24,12 @@ class ZeroRedundancyTrainer:
         dev, dt = params[0].device, params[0].dtype
         total = sum(p.numel() for p in params)
         self.shard = (total + n - 1) // n
-        self.flat = torch.zeros(self.shard * n, dtype=dt, device=dev)
-        self.flat_grad = torch.zeros_like(self.flat)
+        if symmetric and dev.type == "cuda" and getattr(self.comm, "symm_region", lambda: None)():
+            self.flat = self.comm.symm_empty(self.shard * n, dt).zero_()
+            self.flat_grad = self.comm.symm_empty(self.shard * n, dt).zero_()
+        else:
+            self.flat = torch.zeros(self.shard * n, dtype=dt, device=dev)
+            self.flat_grad = torch.zeros_like(self.flat)
         off = 0
         for p in params:                                  # parameters and gradients become views of the flat buffers
             self.flat[off:off + p.numel()].copy_(p.data.reshape(-1))
