@@ -16,6 +16,10 @@
 /* ------------------------------------------------------------------ */
 /* memory-model primitives                                             */
 /* ------------------------------------------------------------------ */
+#ifdef NVL_HOST_EMU
+/* tests/emu: the kernels compiled as host C++ (one OS thread per CUDA thread); the PTX below is replaced by C++ equivalents */
+#include "nvl_device_emu.h"
+#else
 NVL_DEV void st_release_sys_u32(uint32_t *p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 NVL_DEV void st_relaxed_sys_u32(uint32_t *p, uint32_t v) { asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 NVL_DEV uint32_t ld_acquire_sys_u32(const uint32_t *p) { uint32_t v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
@@ -57,6 +61,7 @@ NVL_MC_RED32(mc_red_xor_b32, "xor.b32")
 NVL_MC_RED64(mc_red_add_u64, "add.u64") NVL_MC_RED64(mc_red_min_s64, "min.s64") NVL_MC_RED64(mc_red_max_s64, "max.s64") NVL_MC_RED64(mc_red_min_u64, "min.u64")
 NVL_MC_RED64(mc_red_max_u64, "max.u64") NVL_MC_RED64(mc_red_and_b64, "and.b64") NVL_MC_RED64(mc_red_or_b64, "or.b64") NVL_MC_RED64(mc_red_xor_b64, "xor.b64")
 NVL_DEV void mc_st_v4(void *mc, uint4 v) { asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); }
+#endif /* NVL_HOST_EMU */
 
 /* ------------------------------------------------------------------ */
 /* per-block inter-GPU barrier                                         */

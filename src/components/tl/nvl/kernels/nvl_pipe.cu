@@ -159,6 +159,7 @@ template <typename T> __global__ void __launch_bounds__(NVL_THREADS_MAX, 2) nvl_
     bs.finish((uint32_t)g.chunks + 1);
 }
 
+#ifndef NVL_HOST_EMU /* the host emulation calls the kernels directly */
 extern "C" cudaError_t nvl_launch_reduce_pipe(const nvl_red_args_t *a, int nblocks, int nthreads, cudaStream_t s)
 {
     if (nthreads > NVL_THREADS_MAX) nthreads = NVL_THREADS_MAX;
@@ -176,3 +177,4 @@ extern "C" cudaError_t nvl_launch_reduce_pipe(const nvl_red_args_t *a, int nbloc
     }
     return cudaGetLastError();
 }
+#endif

@@ -96,6 +96,7 @@ template <typename T> __global__ void __launch_bounds__(NVL_THREADS_MAX, 2) nvl_
     bs.finish(2);
 }
 
+#ifndef NVL_HOST_EMU /* the host emulation calls the kernels directly */
 extern "C" cudaError_t nvl_launch_reduce_symm(const nvl_red_args_t *a, int nblocks, int nthreads, cudaStream_t s)
 {
     if (nthreads > NVL_THREADS_MAX) nthreads = NVL_THREADS_MAX;
@@ -113,6 +114,7 @@ extern "C" cudaError_t nvl_launch_reduce_symm(const nvl_red_args_t *a, int nbloc
     }
     return cudaGetLastError();
 }
+#endif
 
 /* ------------------------------------------------------------------ */
 /* allgather INTO a symmetric destination: every member multicasts its */
@@ -152,6 +154,7 @@ __global__ void __launch_bounds__(NVL_THREADS_MAX, 2) nvl_allgather_symm_kernel(
     bs.finish(2);
 }
 
+#ifndef NVL_HOST_EMU /* the host emulation calls the kernels directly */
 extern "C" cudaError_t nvl_launch_allgather_symm(const nvl_xchg_args_t *a, int nblocks, int nthreads, cudaStream_t s)
 {
     if (nthreads > NVL_THREADS_MAX) nthreads = NVL_THREADS_MAX;
@@ -159,3 +162,4 @@ extern "C" cudaError_t nvl_launch_allgather_symm(const nvl_xchg_args_t *a, int n
     nvl_allgather_symm_kernel<<<nblocks, nthreads, 0, s>>>(*a);
     return cudaGetLastError();
 }
+#endif
