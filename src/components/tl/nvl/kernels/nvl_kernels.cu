@@ -194,6 +194,7 @@ __global__ void __launch_bounds__(NVL_THREADS_MAX, 2) nvl_exchange_kernel(nvl_xc
 /* ------------------------------------------------------------------ */
 /* host-side launchers                                                 */
 /* ------------------------------------------------------------------ */
+#ifndef NVL_HOST_EMU /* tests/emu includes the kernels above and calls them directly */
 extern "C" size_t nvl_dt_size(int dt)
 {
     static const size_t s[NVL_DT_LAST] = {1, 2, 4, 8, 1, 2, 4, 8, 2, 4, 8, 2};
@@ -281,3 +282,4 @@ extern "C" cudaError_t nvl_launch_ctrl_init(void *heap_base, cudaStream_t s)
     nvl_ctrl_init_kernel<<<4, 256, 0, s>>>(static_cast<nvl_ctrl_t *>(heap_base));
     return cudaGetLastError();
 }
+#endif /* NVL_HOST_EMU */

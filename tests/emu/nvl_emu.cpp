@@ -26,6 +26,7 @@ static inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetc
 
 #include "nvl_reduce_impl.cuh"
 nvl_emu_world g_emu;
+#include "nvl_kernels.cu"
 #include "nvl_pipe.cu"
 #include "nvl_symm.cu"
 
@@ -169,6 +170,41 @@ static void run_symm_ag(World &w, size_t blk_bytes, bool inplace, int nb, int nt
     printf("  ok %-40s blk %zu B N %d grid %dx%d%s\n", "symm allgather", blk_bytes, N, nb, nt, inplace ? " inplace" : "");
 }
 
+// exchange kernel (pull / NVLS push / ring), arguments built the way tl_nvl_coll.c:xchg_init* builds them
+enum { XCHG_AG_PULL, XCHG_A2A_PULL, XCHG_AG_MC, XCHG_AG_RING };
+static unsigned char pat(int from, int to, size_t i) { return (unsigned char)(from * 37 + to * 11 + i * 3 + 1); }
+static void run_xchg(World &w, int mode, size_t blk, int nb, int nt, size_t misalign = 0)
+{
+    const int N = w.N; const bool a2a = mode == XCHG_A2A_PULL;
+    const size_t ablk = (blk + 15) / 16 * 16;
+    std::vector<std::vector<unsigned char>> sb(N, std::vector<unsigned char>((a2a ? blk * N : blk) + 64)), db(N, std::vector<unsigned char>(blk * N + 64, 0xee));
+    for (int r = 0; r < N; r++) for (int to = 0; to < (a2a ? N : 1); to++) for (size_t i = 0; i < blk; i++) sb[r][16 + misalign + to * blk + i] = pat(r, a2a ? to : 0, i);
+    for (int rep = 0; rep < 2; rep++) {
+        for (int r = 0; r < N; r++) memset(db[r].data(), 0xee, db[r].size());
+        launch_all(N, nb, nt, [&](int r) {
+            nvl_xchg_args_t a; memset(&a, 0, sizeof(a));
+            a.team = w.team(r, mode == XCHG_AG_MC); a.src = sb[r].data() + 16 + misalign; a.dst = db[r].data() + 16 + misalign;
+            a.src_bytes = a2a ? blk * N : blk;
+            for (int p = 0; p < N; p++) {
+                a.pull_bytes[p] = blk; a.dst_off[p] = (size_t)p * blk;
+                a.pull_off[p] = a2a ? (size_t)r * blk : ((mode == XCHG_AG_MC || mode == XCHG_AG_RING) ? (size_t)p * ablk : 0);
+            }
+            a.self_off = a2a ? (size_t)r * blk : 0;
+            if (mode == XCHG_AG_MC) { a.use_mc = 1; a.push_off = (size_t)r * ablk; }
+            if (mode == XCHG_AG_RING) a.ring = 1;
+            nvl_exchange_kernel(a);
+        });
+        CHECK(w.host_err == 0);
+        for (int r = 0; r < N; r++) {
+            for (int p = 0; p < N; p++) for (size_t i = 0; i < blk; i++)
+                if (db[r][16 + misalign + p * blk + i] != pat(p, a2a ? r : 0, i)) { printf("EMU FAIL xchg mode %d: rank %d block %d byte %zu\n", mode, r, p, i); exit(1); }
+            CHECK(db[r][15 + misalign] == 0xee && db[r][16 + misalign + blk * N] == 0xee);
+        }
+    }
+    static const char *names[] = {"exchange allgather pull (control)", "exchange alltoall pull (control)", "exchange allgather nvls push (control)", "exchange allgather ring (control)"};
+    printf("  ok %-40s blk %zu B N %d grid %dx%d%s\n", names[mode], blk, N, nb, nt, misalign ? " unaligned" : "");
+}
+
 int main(int argc, char **argv)
 {
     const std::string what = argc > 1 ? argv[1] : "all";
@@ -185,6 +221,13 @@ int main(int argc, char **argv)
             if (N == 2) run_allreduce<float>("steps rhd (control)", w, [](nvl_red_args_t a) { a.sched = 2; nvl_reduce_steps_kernel<float>(a); }, 3001, NVL_OP_AVG, false, true, 2, 64, 2);
             if (N == 2) { run_direct<2, 4>(w, 9001, NVL_OP_SUM, false, 2, 64); run_direct<2, 4>(w, 777, NVL_OP_MAX, true, 3, 32); }
             else { run_direct<4, 2>(w, 9001, NVL_OP_SUM, false, 2, 64); run_direct<4, 2>(w, 777, NVL_OP_MAX, true, 3, 32); }
+        }
+        if (what == "all" || what == "xchg") {
+            for (int mode : {XCHG_AG_PULL, XCHG_A2A_PULL, XCHG_AG_MC, XCHG_AG_RING}) {
+                run_xchg(w, mode, 4096, 2, 64);
+                run_xchg(w, mode, 1003, 3, 32);                 // ragged block size
+                if (mode != XCHG_AG_MC) run_xchg(w, mode, 2000, 2, 64, 3);   // unaligned user buffers
+            }
         }
         if (what == "all" || what == "pipe") {
             auto pipe_f = [](nvl_red_args_t a) { nvl_allreduce_nvls_pipe_kernel<float>(a); };
