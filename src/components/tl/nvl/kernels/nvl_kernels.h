@@ -101,6 +101,15 @@ typedef struct nvl_xchg_args {
     nvl_direct_t   d;
 } nvl_xchg_args_t;
 
+/* zero-copy push exchange (kernels/nvl_push.cu): my block for member p = send_bytes[p] bytes at src + send_off[p], stored at
+ * dst_of[p] + land_off[p] (dst_of[p] = p's destination buffer mapped here; dst_of[rank] = my own) */
+typedef struct nvl_push_args {
+    nvl_team_dev_t team;
+    const void    *src;
+    size_t         send_off[NVL_MAX_PEERS], send_bytes[NVL_MAX_PEERS], land_off[NVL_MAX_PEERS];
+    char          *dst_of[NVL_MAX_PEERS];
+} nvl_push_args_t;
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -122,6 +131,7 @@ cudaError_t  nvl_launch_reduce_symm(const nvl_red_args_t *a, int nblocks, int nt
 /* allgather into a symmetric destination: a->src/src_bytes = my block, a->dst = local address of the gathered buffer in my heap, a->push_off = my offset */
 cudaError_t  nvl_launch_allgather_symm(const nvl_xchg_args_t *a, int nblocks, int nthreads, cudaStream_t s);
 cudaError_t  nvl_launch_exchange(const nvl_xchg_args_t *a, int nblocks, int nthreads, cudaStream_t s);
+cudaError_t  nvl_launch_exchange_push(const nvl_push_args_t *a, int nblocks, int nthreads, cudaStream_t s);
 cudaError_t  nvl_launch_barrier(const nvl_team_dev_t *t, cudaStream_t s);
 cudaError_t  nvl_launch_self_copy(void *dst, const void *src, size_t bytes, int nblocks, int nthreads, cudaStream_t s); /* team of one */
 cudaError_t  nvl_launch_ctrl_init(void *heap_base, cudaStream_t s);

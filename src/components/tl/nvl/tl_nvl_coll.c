@@ -47,7 +47,18 @@ static ucc_status_t nvl_launch(ucc_tl_nvl_task_t *t, cudaStream_t s)
     case NVL_TASK_REDUCE_PIPE: e = nvl_launch_reduce_pipe(&t->u.red, t->nblocks, t->nthreads, s); break;
     case NVL_TASK_REDUCE_SYMM: e = nvl_launch_reduce_symm(&t->u.red, t->nblocks, t->nthreads, s); break;
     case NVL_TASK_AG_SYMM: e = nvl_launch_allgather_symm(&t->u.xchg, t->nblocks, t->nthreads, s); break;
-    case NVL_TASK_XCHG: e = nvl_launch_exchange(&t->u.xchg, t->nblocks, t->nthreads, s); break;
+    case NVL_TASK_XCHG:
+        if (t->use_push && t->u.xchg.direct) { /* every member's destination resolved: store my blocks straight into them */
+            nvl_push_args_t pa;
+            memset(&pa, 0, sizeof(pa));
+            pa.team = t->u.xchg.team; pa.src = t->u.xchg.src;
+            for (int p = 0; p < pa.team.size; p++) {
+                pa.send_off[p] = t->push.send_off[p]; pa.send_bytes[p] = t->push.send_bytes[p]; pa.land_off[p] = t->push.land_off[p];
+                pa.dst_of[p] = p == pa.team.rank ? (char *)t->u.xchg.dst : t->u.xchg.d.dst[p];
+            }
+            e = nvl_launch_exchange_push(&pa, t->nblocks, t->nthreads, s);
+        } else e = nvl_launch_exchange(&t->u.xchg, t->nblocks, t->nthreads, s);
+        break;
     case NVL_TASK_SELF_COPY:
         e = t->u.xchg.src_bytes ? nvl_launch_self_copy(t->u.xchg.dst, t->u.xchg.src, t->u.xchg.src_bytes, t->nblocks, t->nthreads, s) : cudaSuccess;
         break;
@@ -213,7 +224,7 @@ static ucc_status_t task_alloc(ucc_base_coll_args_t *b, ucc_base_team_t *b_team,
     ucc_tl_nvl_task_t *t = (ucc_tl_nvl_task_t *)ucc_mpool_get(&ctx->task_mp);
     if (!t) return UCC_ERR_NO_MEMORY;
     ucc_coll_task_init(&t->super, b, b_team);
-    t->team = team; t->event = NULL; t->captured = 0; t->in_event = NULL; t->state = NVL_TASK_LAUNCHED; t->want_direct = 0; t->gated = 0;
+    t->team = team; t->event = NULL; t->captured = 0; t->in_event = NULL; t->state = NVL_TASK_LAUNCHED; t->want_direct = 0; t->gated = 0; t->use_push = 0;
     t->need_src = t->need_dst = 0; t->exp_src = NULL; t->exp_dst = NULL; t->exp_src_len = t->exp_dst_len = 0; t->nblocks_direct = 0;
     t->nthreads = (int)ctx->cfg.nthreads;
     t->super.post = nvl_post; t->super.progress = nvl_progress; t->super.finalize = nvl_finalize; t->super.triggered_post = nvl_triggered_post;
@@ -536,6 +547,37 @@ static ucc_status_t xchg_init(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, 
     return UCC_OK;
 }
 
+/* zero-copy PUSH allgather(v) / alltoall (kernels/nvl_push.cu): the destinations travel over the exchange board and every rank
+ * stores its blocks straight into them; if a destination cannot be mapped the task falls back to the staged pull it also is */
+static ucc_status_t xchg_init_push(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, ucc_coll_task_t **task_p)
+{
+    ucc_tl_nvl_team_t *team = ucc_derived_of(b_team, ucc_tl_nvl_team_t);
+    ucc_tl_nvl_context_t *ctx = NVL_CTX(team);
+    ucc_coll_args_t *a = &b->args;
+    ucc_rank_t N = UCC_TL_TEAM_SIZE(team), me = UCC_TL_TEAM_RANK(team);
+    ucc_coll_type_t ct = a->coll_type;
+    ucc_tl_nvl_task_t *t;
+    nvl_xchg_args_t *x;
+    size_t dst_len = 0;
+    ucc_status_t st;
+    if (ct != UCC_COLL_TYPE_ALLGATHER && ct != UCC_COLL_TYPE_ALLGATHERV && ct != UCC_COLL_TYPE_ALLTOALL) return UCC_ERR_NOT_SUPPORTED;
+    if (!team->self && (!team->zcopy || ctx->cfg.zcopy == UCC_NO)) return UCC_ERR_NOT_SUPPORTED;
+    if (ct == UCC_COLL_TYPE_ALLTOALL && UCC_IS_INPLACE(*a)) return UCC_ERR_NOT_SUPPORTED;
+    st = xchg_init(b, b_team, task_p);
+    if (st != UCC_OK) return st;
+    t = ucc_derived_of(*task_p, ucc_tl_nvl_task_t); x = &t->u.xchg;
+    if (t->kind != NVL_TASK_XCHG) return UCC_OK; /* symmetric destination / single member: nothing to add */
+    for (ucc_rank_t p = 0; p < N; p++) {
+        if (ct == UCC_COLL_TYPE_ALLTOALL) { t->push.send_off[p] = x->dst_off[p]; t->push.send_bytes[p] = x->pull_bytes[p]; t->push.land_off[p] = x->dst_off[me]; }
+        else { t->push.send_off[p] = 0; t->push.send_bytes[p] = x->pull_bytes[me]; t->push.land_off[p] = x->dst_off[me]; } /* my block, at my displacement, in everybody's dst */
+        if (x->dst_off[p] + x->pull_bytes[p] > dst_len) dst_len = x->dst_off[p] + x->pull_bytes[p];
+    }
+    t->use_push = 1;
+    t->want_direct = NVL_DIRECT_FULL; t->need_src = 0; t->need_dst = 1;
+    t->exp_src = NULL; t->exp_src_len = 0; t->exp_dst = x->dst; t->exp_dst_len = dst_len;
+    return UCC_OK;
+}
+
 /* allgather(v) / bcast through the switch: every rank multicasts its block once (multimem.st), everybody then
  * copies out of its OWN heap.  Same bytes into every GPU as the pull variant, 1/(N-1) of the bytes out. */
 static ucc_status_t xchg_init_nvls(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, ucc_coll_task_t **task_p)
@@ -617,10 +659,13 @@ static const nvl_alg_t algs_xchg_mc[] = {{"pull", "stage once, every peer pulls 
     {"nvls", "multicast the own block into every member's heap with multimem.st, copy out locally", xchg_init_nvls}, {NULL}};
 static const nvl_alg_t algs_ag[] = {{"pull", "stage once, every peer pulls its part over NVLink", xchg_init},
     {"nvls", "multicast the own block into every member's heap with multimem.st, copy out locally", xchg_init_nvls},
-    {"ring", "N-1 neighbour-to-neighbour pull steps through the heaps, one kernel", xchg_init_ring}, {NULL}};
+    {"ring", "N-1 neighbour-to-neighbour pull steps through the heaps, one kernel", xchg_init_ring},
+    {"push", "zero-copy push: every rank stores its block straight into the members' mapped destinations (opt-in, not yet measured)", xchg_init_push}, {NULL}};
+static const nvl_alg_t algs_a2a[] = {{"pull", "stage once, every peer pulls its part over NVLink", xchg_init},
+    {"push", "zero-copy push: every rank stores block p straight into member p's mapped destination (opt-in, not yet measured)", xchg_init_push}, {NULL}};
 static const nvl_alg_t algs_barrier[] = {{"flags", "flag exchange in peer memory", barrier_init}, {NULL}};
 static const nvl_alg_t *const nvl_algs[UCC_COLL_TYPE_NUM] = {
-    algs_ag, algs_ag, algs_allreduce, algs_xchg, algs_xchg, algs_barrier, algs_xchg_mc, algs_barrier, algs_barrier,
+    algs_ag, algs_ag, algs_allreduce, algs_a2a, algs_xchg, algs_barrier, algs_xchg_mc, algs_barrier, algs_barrier,
     algs_xchg, algs_xchg, algs_red, algs_rs, algs_rs, algs_xchg, algs_xchg};
 static ucc_base_coll_alg_info_t nvl_alg_info[UCC_COLL_TYPE_NUM][8];
 

@@ -28,6 +28,7 @@ static inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetc
 nvl_emu_world g_emu;
 #include "nvl_kernels.cu"
 #include "nvl_pipe.cu"
+#include "nvl_push.cu"
 #include "nvl_symm.cu"
 
 #define CHECK(c) do { if (!(c)) { printf("EMU FAIL line %d: %s\n", __LINE__, #c); exit(1); } } while (0)
@@ -205,6 +206,36 @@ static void run_xchg(World &w, int mode, size_t blk, int nb, int nt, size_t misa
     printf("  ok %-40s blk %zu B N %d grid %dx%d%s\n", names[mode], blk, N, nb, nt, misalign ? " unaligned" : "");
 }
 
+// zero-copy push exchange: allgather (same block to everybody) and alltoall (block p to member p)
+static void run_push(World &w, bool a2a, size_t blk, int nb, int nt, size_t misalign = 0, bool inplace_ag = false)
+{
+    const int N = w.N;
+    std::vector<std::vector<unsigned char>> sb(N, std::vector<unsigned char>((a2a ? blk * N : blk) + 64)), db(N, std::vector<unsigned char>(blk * N + 64, 0xee));
+    for (int rep = 0; rep < 2; rep++) {
+        for (int r = 0; r < N; r++) {
+            memset(db[r].data(), 0xee, db[r].size());
+            for (int to = 0; to < (a2a ? N : 1); to++) for (size_t i = 0; i < blk; i++) {
+                unsigned char v = pat(r, a2a ? to : 0, i);
+                if (inplace_ag) db[r][16 + misalign + r * blk + i] = v; else sb[r][16 + misalign + to * blk + i] = v;
+            }
+        }
+        launch_all(N, nb, nt, [&](int r) {
+            nvl_push_args_t a; memset(&a, 0, sizeof(a));
+            a.team = w.team(r, false);
+            a.src = inplace_ag ? (const void *)(db[r].data() + 16 + misalign + r * blk) : (const void *)(sb[r].data() + 16 + misalign);
+            for (int p = 0; p < N; p++) { a.send_off[p] = a2a ? (size_t)p * blk : 0; a.send_bytes[p] = blk; a.land_off[p] = (size_t)r * blk; a.dst_of[p] = (char *)db[p].data() + 16 + misalign; }
+            nvl_exchange_push_kernel(a);
+        });
+        CHECK(w.host_err == 0);
+        for (int r = 0; r < N; r++) {
+            for (int p = 0; p < N; p++) for (size_t i = 0; i < blk; i++)
+                if (db[r][16 + misalign + p * blk + i] != pat(p, a2a ? r : 0, i)) { printf("EMU FAIL push: rank %d block %d byte %zu\n", r, p, i); exit(1); }
+            CHECK(db[r][15 + misalign] == 0xee && db[r][16 + misalign + blk * N] == 0xee);
+        }
+    }
+    printf("  ok %-40s blk %zu B N %d grid %dx%d%s%s\n", a2a ? "push alltoall" : "push allgather", blk, N, nb, nt, misalign ? " unaligned" : "", inplace_ag ? " inplace" : "");
+}
+
 int main(int argc, char **argv)
 {
     const std::string what = argc > 1 ? argv[1] : "all";
@@ -228,6 +259,10 @@ int main(int argc, char **argv)
                 run_xchg(w, mode, 1003, 3, 32);                 // ragged block size
                 if (mode != XCHG_AG_MC) run_xchg(w, mode, 2000, 2, 64, 3);   // unaligned user buffers
             }
+        }
+        if (what == "all" || what == "push") {
+            for (bool a2a : {false, true}) { run_push(w, a2a, 4096, 2, 64); run_push(w, a2a, 1003, 3, 32); run_push(w, a2a, 2002, 2, 64, 2); run_push(w, a2a, 777, 2, 64, 3); }
+            run_push(w, false, 4096, 2, 64, 0, true);
         }
         if (what == "all" || what == "pipe") {
             auto pipe_f = [](nvl_red_args_t a) { nvl_allreduce_nvls_pipe_kernel<float>(a); };

@@ -112,3 +112,12 @@ def test_multiproc_symm():
            "--master-port", "29741", os.path.join(ROOT, "tests", "symm_worker.py")]
     out = subprocess.run(cmd, env=dict(os.environ, PYTHONPATH=ROOT, SYMM_BENCH_BYTES=str(256 << 20)), capture_output=True, text=True, timeout=900)
     assert "SYMM_WORKER_OK" in out.stdout or "SYMM_WORKER_SKIP" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+
+
+@pytest.mark.skipif(os.environ.get("UCC_B200_EXPERIMENTAL_TESTS") != "1", reason="push exchange was written without GPU time left: set UCC_B200_EXPERIMENTAL_TESTS=1")
+def test_multiproc_push_exchange():
+    """zero-copy push allgather / alltoall (kernels/nvl_push.cu) instead of the pull kernels"""
+    n = min(2, torch.cuda.device_count()) if torch.cuda.is_available() else 0
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    _run(n, {"UCC_TL_NVL_TUNE": "allgather:cuda:inf:@push#alltoall:cuda:inf:@push"})

@@ -1,7 +1,7 @@
 """tl/nvl collective kernels compiled as host C++ (NVL_HOST_EMU, tests/emu/nvl_emu.cpp): one OS thread per CUDA thread, N heaps
 in one address space, the NVSwitch multicast window emulated.  Checks the indexing / phase / flag logic of every reduction kernel
 without a GPU: the kernels validated on B200s (staged, one-shot, ring / rhd, zero-copy, the exchange kernel's pull / NVLS push / ring modes) as controls, and the ones written after
-the GPU budget ran out (nvls_pipe, symmetric-memory allreduce / reduce_scatter / allgather)."""
+the GPU budget ran out (nvls_pipe, symmetric-memory allreduce / reduce_scatter / allgather, zero-copy push allgather / alltoall)."""
 import os
 import subprocess
 
@@ -23,7 +23,7 @@ def emu(tmp_path_factory):
     return str(exe)
 
 
-@pytest.mark.parametrize("what", ["staged", "xchg", "pipe", "symm"])
+@pytest.mark.parametrize("what", ["staged", "xchg", "pipe", "symm", "push"])
 def test_nvl_kernels_host_emulation(emu, what):
     out = subprocess.run([emu, what], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "NVL_EMU_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-2000:]
