@@ -56,6 +56,7 @@ static ucc_status_t nvl_launch(ucc_tl_nvl_task_t *t, cudaStream_t s)
                 pa.send_off[p] = t->push.send_off[p]; pa.send_bytes[p] = t->push.send_bytes[p]; pa.land_off[p] = t->push.land_off[p];
                 pa.dst_of[p] = p == pa.team.rank ? (char *)t->u.xchg.dst : t->u.xchg.d.dst[p];
             }
+            /* (every member takes this branch or none: `direct` is decided from what all of them published) */
             e = nvl_launch_exchange_push(&pa, t->nblocks, t->nthreads, s);
         } else e = nvl_launch_exchange(&t->u.xchg, t->nblocks, t->nthreads, s);
         break;
