@@ -120,6 +120,8 @@ int          nvl_nvls_supports(int dt, int op);
 cudaError_t  nvl_launch_allreduce_oneshot(const nvl_red_args_t *a, int nblocks, int nthreads, cudaStream_t s);
 /* bandwidth path: staged two-shot (P2P pull or NVLS) for allreduce / reduce_scatter(v) / reduce */
 cudaError_t  nvl_launch_reduce_staged(const nvl_red_args_t *a, int nblocks, int nthreads, cudaStream_t s);
+/* latency path of reduce_scatter(v): one-shot push of every block to its owner, blocks <= NVL_LL_MAX */
+cudaError_t  nvl_launch_reduce_scatter_oneshot(const nvl_red_args_t *a, int nblocks, int nthreads, cudaStream_t s);
 /* zero-copy two-shot: every rank reduces its slice straight out of the members' src buffers into their dst buffers */
 cudaError_t  nvl_launch_reduce_direct(const nvl_red_args_t *a, int nblocks, int nthreads, cudaStream_t s);
 /* ring / recursive halving-doubling allreduce and reduce_scatter(v) through the heaps (a->sched), single round */

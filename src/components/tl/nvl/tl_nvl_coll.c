@@ -38,7 +38,10 @@ static ucc_status_t nvl_launch(ucc_tl_nvl_task_t *t, cudaStream_t s)
 {
     cudaError_t e;
     switch (t->kind) {
-    case NVL_TASK_REDUCE_ONESHOT: e = nvl_launch_allreduce_oneshot(&t->u.red, t->nblocks, t->nthreads, s); break;
+    case NVL_TASK_REDUCE_ONESHOT:
+        e = t->u.red.kind == NVL_RED_REDUCE_SCATTER ? nvl_launch_reduce_scatter_oneshot(&t->u.red, t->nblocks, t->nthreads, s)
+                                                    : nvl_launch_allreduce_oneshot(&t->u.red, t->nblocks, t->nthreads, s);
+        break;
     case NVL_TASK_REDUCE_STAGED:
         if (t->u.red.direct == NVL_DIRECT_FULL) e = nvl_launch_reduce_direct(&t->u.red, t->nblocks_direct, t->nthreads, s);
         else e = nvl_launch_reduce_staged(&t->u.red, t->nblocks, t->nthreads, s);
@@ -330,7 +333,14 @@ static ucc_status_t red_init(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, u
     ndt = to_nvl_dt(dt); nop = to_nvl_op(a->op);
     if (ndt < 0 || nop < 0 || !nvl_dt_supports_op(ndt, nop)) return UCC_ERR_NOT_SUPPORTED;
     bytes = count * ucc_dt_size(dt);
-    if (alg == RED_ALG_ONESHOT && (a->coll_type != UCC_COLL_TYPE_ALLREDUCE || bytes > NVL_LL_MAX)) return UCC_ERR_NOT_SUPPORTED;
+    if (alg == RED_ALG_ONESHOT) {
+        /* allreduce: the whole vector goes into a 1 MB slot; reduce_scatter(v): every block does (kernels/nvl_oneshot_rs.cu) */
+        size_t need = bytes;
+        if (a->coll_type == UCC_COLL_TYPE_REDUCE_SCATTER) need = ucc_div_round_up(count, N) * ucc_dt_size(dt);
+        else if (a->coll_type == UCC_COLL_TYPE_REDUCE_SCATTERV) { need = 0; for (ucc_rank_t i = 0; i < N; i++) need = ucc_max(need, ucc_coll_args_get_count(a, a->dst.info_v.counts, i) * ucc_dt_size(dt)); }
+        else if (a->coll_type != UCC_COLL_TYPE_ALLREDUCE) return UCC_ERR_NOT_SUPPORTED;
+        if (need > NVL_LL_MAX) return UCC_ERR_NOT_SUPPORTED;
+    }
     if ((alg == RED_ALG_NVLS || alg == RED_ALG_NVLS_PIPE) && (!team->nvls || !nvl_nvls_supports(ndt, nop))) return UCC_ERR_NOT_SUPPORTED;
     if (alg == RED_ALG_NVLS_PIPE && a->coll_type != UCC_COLL_TYPE_ALLREDUCE) return UCC_ERR_NOT_SUPPORTED;
     if (alg == RED_ALG_RING || alg == RED_ALG_RHD) {
@@ -651,7 +661,8 @@ static const nvl_alg_t algs_rs[] = {
     {"twoshot", "stage + pull-reduce own slice over NVLink", red_init_twoshot},
     {"nvls", "stage + multimem.ld_reduce own slice in the NVSwitch", red_init_nvls},
     {"ring", "ring reduce-scatter through the heaps, neighbour links only", red_init_ring},
-    {"rhd", "recursive halving, power-of-two teams", red_init_rhd}, {NULL}};
+    {"rhd", "recursive halving, power-of-two teams", red_init_rhd},
+    {"oneshot", "push every block to its owner and reduce locally: one flag exchange (latency path, blocks <= 1 MB; opt-in, not yet measured)", red_init_oneshot}, {NULL}};
 static const nvl_alg_t algs_red[] = {
     {"twoshot", "stage + pull-reduce own slice over NVLink", red_init_twoshot},
     {"nvls", "stage + multimem.ld_reduce own slice in the NVSwitch", red_init_nvls}, {NULL}};

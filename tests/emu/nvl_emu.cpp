@@ -29,6 +29,7 @@ nvl_emu_world g_emu;
 #include "nvl_kernels.cu"
 #include "nvl_pipe.cu"
 #include "nvl_push.cu"
+#include "nvl_oneshot_rs.cu"
 #include "nvl_symm.cu"
 
 #define CHECK(c) do { if (!(c)) { printf("EMU FAIL line %d: %s\n", __LINE__, #c); exit(1); } } while (0)
@@ -236,6 +237,38 @@ static void run_push(World &w, bool a2a, size_t blk, int nb, int nt, size_t misa
     printf("  ok %-40s blk %zu B N %d grid %dx%d%s%s\n", a2a ? "push alltoall" : "push allgather", blk, N, nb, nt, misalign ? " unaligned" : "", inplace_ag ? " inplace" : "");
 }
 
+// one-shot reduce_scatter(v); interleaved with one-shot allreduces, which share the slot parity / sequence counters
+static void run_oneshot_rs(World &w, const std::vector<size_t> &counts, int op, bool inplace, int nb, int nt, size_t misalign = 0)
+{
+    const int N = w.N;
+    std::vector<size_t> off(N); size_t total = 0;
+    for (int p = 0; p < N; p++) { off[p] = total; total += counts[p]; }
+    std::vector<std::vector<float>> sb(N, std::vector<float>(total + 64)), db(N, std::vector<float>(total + 64, -7.f));
+    for (int rep = 0; rep < 3; rep++) {
+        for (int r = 0; r < N; r++) { for (size_t i = 0; i < total; i++) sb[r][16 + misalign + i] = val<float>(r, i + rep); std::fill(db[r].begin(), db[r].end(), -7.f); }
+        launch_all(N, nb, nt, [&](int r) {
+            nvl_red_args_t a; memset(&a, 0, sizeof(a));
+            a.team = w.team(r, false); a.src = sb[r].data() + 16 + misalign; a.count = total; a.op = op; a.kind = NVL_RED_REDUCE_SCATTER;
+            a.dst = inplace ? (void *)(sb[r].data() + 16 + misalign + off[r]) : (void *)(db[r].data() + 16 + misalign);
+            for (int p = 0; p < N; p++) { a.rs_offset[p] = off[p]; a.rs_count[p] = counts[p]; }
+            nvl_reduce_scatter_oneshot_kernel<float>(a);
+        });
+        CHECK(w.host_err == 0);
+        for (int r = 0; r < N; r++) {
+            const float *out = inplace ? sb[r].data() + 16 + misalign + off[r] : db[r].data() + 16 + misalign;
+            for (size_t i = 0; i < counts[r]; i++) {
+                double e = 0; for (int p = 0; p < N; p++) { double v = val<float>(p, off[r] + i + rep); e = p == 0 ? v : (op == NVL_OP_MAX ? std::max(e, v) : e + v); }
+                if (op == NVL_OP_AVG) e /= N;
+                if (std::fabs(out[i] - e) > 1e-3 * std::max(1.0, std::fabs(e))) { printf("EMU FAIL oneshot rs: rank %d elem %zu got %g expected %g\n", r, i, out[i], e); exit(1); }
+            }
+            if (!inplace) CHECK(db[r][15 + misalign] == -7.f && db[r][16 + misalign + counts[r]] == -7.f);
+        }
+        if (rep == 0)   // a one-shot allreduce in between: same parity protocol
+            run_allreduce<float>("oneshot allreduce (interleaved)", w, [](nvl_red_args_t a) { nvl_allreduce_oneshot_kernel<float>(a); }, 515, NVL_OP_SUM, false, false, nb, nt, 1);
+    }
+    printf("  ok %-40s total %zu N %d grid %dx%d%s%s\n", "oneshot reduce_scatter(v)", total, N, nb, nt, inplace ? " inplace" : "", misalign ? " unaligned" : "");
+}
+
 int main(int argc, char **argv)
 {
     const std::string what = argc > 1 ? argv[1] : "all";
@@ -263,6 +296,12 @@ int main(int argc, char **argv)
         if (what == "all" || what == "push") {
             for (bool a2a : {false, true}) { run_push(w, a2a, 4096, 2, 64); run_push(w, a2a, 1003, 3, 32); run_push(w, a2a, 2002, 2, 64, 2); run_push(w, a2a, 777, 2, 64, 3); }
             run_push(w, false, 4096, 2, 64, 0, true);
+        }
+        if (what == "all" || what == "oneshot_rs") {
+            run_oneshot_rs(w, std::vector<size_t>(N, 1000), NVL_OP_SUM, false, 2, 64);
+            run_oneshot_rs(w, std::vector<size_t>(N, 1003), NVL_OP_AVG, true, 2, 64);
+            { std::vector<size_t> c(N); for (int p = 0; p < N; p++) c[p] = 5 + 701 * (size_t)p; run_oneshot_rs(w, c, NVL_OP_MAX, false, 2, 64, 1); }   // reduce_scatterv, unaligned
+            { std::vector<size_t> c(N, 0); c[N - 1] = 64; run_oneshot_rs(w, c, NVL_OP_SUM, false, 2, 32); }                                                // empty blocks
         }
         if (what == "all" || what == "pipe") {
             auto pipe_f = [](nvl_red_args_t a) { nvl_allreduce_nvls_pipe_kernel<float>(a); };
