@@ -108,6 +108,9 @@ typedef struct nvl_push_args {
     const void    *src;
     size_t         send_off[NVL_MAX_PEERS], send_bytes[NVL_MAX_PEERS], land_off[NVL_MAX_PEERS];
     char          *dst_of[NVL_MAX_PEERS];
+    int            lookup;       /* alltoallv: only the receiver knows where a block lands; every rank publishes recv_off[] (offset of
+                                    source p's block inside MY dst) at the start of its heap data region and senders read entry [rank] */
+    size_t         recv_off[NVL_MAX_PEERS];
 } nvl_push_args_t;
 
 #ifdef __cplusplus

@@ -162,7 +162,7 @@ typedef struct ucc_tl_nvl_task {
     int                 nblocks_direct;
     /* zero-copy push exchange (kernels/nvl_push.cu): used instead of the pull kernel when the destinations resolved */
     int                 use_push;
-    struct { size_t send_off[NVL_MAX_PEERS], send_bytes[NVL_MAX_PEERS], land_off[NVL_MAX_PEERS]; } push;
+    struct { size_t send_off[NVL_MAX_PEERS], send_bytes[NVL_MAX_PEERS], land_off[NVL_MAX_PEERS], recv_off[NVL_MAX_PEERS]; int lookup; } push;
 } ucc_tl_nvl_task_t;
 
 ucc_status_t ucc_tl_nvl_xb_create(ucc_tl_nvl_team_t *team);

@@ -56,9 +56,10 @@ static ucc_status_t nvl_launch(ucc_tl_nvl_task_t *t, cudaStream_t s)
             memset(&pa, 0, sizeof(pa));
             pa.team = t->u.xchg.team; pa.src = t->u.xchg.src;
             for (int p = 0; p < pa.team.size; p++) {
-                pa.send_off[p] = t->push.send_off[p]; pa.send_bytes[p] = t->push.send_bytes[p]; pa.land_off[p] = t->push.land_off[p];
+                pa.send_off[p] = t->push.send_off[p]; pa.send_bytes[p] = t->push.send_bytes[p]; pa.land_off[p] = t->push.land_off[p]; pa.recv_off[p] = t->push.recv_off[p];
                 pa.dst_of[p] = p == pa.team.rank ? (char *)t->u.xchg.dst : t->u.xchg.d.dst[p];
             }
+            pa.lookup = t->push.lookup;
             /* (every member takes this branch or none: `direct` is decided from what all of them published) */
             e = nvl_launch_exchange_push(&pa, t->nblocks, t->nthreads, s);
         } else e = nvl_launch_exchange(&t->u.xchg, t->nblocks, t->nthreads, s);
@@ -571,15 +572,23 @@ static ucc_status_t xchg_init_push(ucc_base_coll_args_t *b, ucc_base_team_t *b_t
     nvl_xchg_args_t *x;
     size_t dst_len = 0;
     ucc_status_t st;
-    if (ct != UCC_COLL_TYPE_ALLGATHER && ct != UCC_COLL_TYPE_ALLGATHERV && ct != UCC_COLL_TYPE_ALLTOALL) return UCC_ERR_NOT_SUPPORTED;
+    if (ct != UCC_COLL_TYPE_ALLGATHER && ct != UCC_COLL_TYPE_ALLGATHERV && ct != UCC_COLL_TYPE_ALLTOALL && ct != UCC_COLL_TYPE_ALLTOALLV) return UCC_ERR_NOT_SUPPORTED;
     if (!team->self && (!team->zcopy || ctx->cfg.zcopy == UCC_NO)) return UCC_ERR_NOT_SUPPORTED;
     if (ct == UCC_COLL_TYPE_ALLTOALL && UCC_IS_INPLACE(*a)) return UCC_ERR_NOT_SUPPORTED;
     st = xchg_init(b, b_team, task_p);
     if (st != UCC_OK) return st;
     t = ucc_derived_of(*task_p, ucc_tl_nvl_task_t); x = &t->u.xchg;
     if (t->kind != NVL_TASK_XCHG) return UCC_OK; /* symmetric destination / single member: nothing to add */
+    t->push.lookup = 0;
     for (ucc_rank_t p = 0; p < N; p++) {
-        if (ct == UCC_COLL_TYPE_ALLTOALL) { t->push.send_off[p] = x->dst_off[p]; t->push.send_bytes[p] = x->pull_bytes[p]; t->push.land_off[p] = x->dst_off[me]; }
+        t->push.recv_off[p] = x->dst_off[p];
+        if (ct == UCC_COLL_TYPE_ALLTOALLV) {
+            /* what I send is described by MY send counts / displacements (x->stage_off); where it lands only the receiver knows:
+             * it publishes recv_off[] on the device and the senders look their entry up (the mirror image of the pull kernel's table) */
+            size_t sdt = ucc_dt_size(a->src.info_v.datatype);
+            t->push.send_off[p] = x->stage_off[p]; t->push.send_bytes[p] = ucc_coll_args_get_count(a, a->src.info_v.counts, p) * sdt;
+            t->push.land_off[p] = x->dst_off[me]; t->push.lookup = 1;
+        } else if (ct == UCC_COLL_TYPE_ALLTOALL) { t->push.send_off[p] = x->dst_off[p]; t->push.send_bytes[p] = x->pull_bytes[p]; t->push.land_off[p] = x->dst_off[me]; }
         else { t->push.send_off[p] = 0; t->push.send_bytes[p] = x->pull_bytes[me]; t->push.land_off[p] = x->dst_off[me]; } /* my block, at my displacement, in everybody's dst */
         if (x->dst_off[p] + x->pull_bytes[p] > dst_len) dst_len = x->dst_off[p] + x->pull_bytes[p];
     }
@@ -674,10 +683,10 @@ static const nvl_alg_t algs_ag[] = {{"pull", "stage once, every peer pulls its p
     {"ring", "N-1 neighbour-to-neighbour pull steps through the heaps, one kernel", xchg_init_ring},
     {"push", "zero-copy push: every rank stores its block straight into the members' mapped destinations (opt-in, not yet measured)", xchg_init_push}, {NULL}};
 static const nvl_alg_t algs_a2a[] = {{"pull", "stage once, every peer pulls its part over NVLink", xchg_init},
-    {"push", "zero-copy push: every rank stores block p straight into member p's mapped destination (opt-in, not yet measured)", xchg_init_push}, {NULL}};
+    {"push", "zero-copy push: every rank stores block p straight into member p's mapped destination; alltoallv looks the landing offset up in a table the receiver publishes on the device (opt-in, not yet measured)", xchg_init_push}, {NULL}};
 static const nvl_alg_t algs_barrier[] = {{"flags", "flag exchange in peer memory", barrier_init}, {NULL}};
 static const nvl_alg_t *const nvl_algs[UCC_COLL_TYPE_NUM] = {
-    algs_ag, algs_ag, algs_allreduce, algs_a2a, algs_xchg, algs_barrier, algs_xchg_mc, algs_barrier, algs_barrier,
+    algs_ag, algs_ag, algs_allreduce, algs_a2a, algs_a2a, algs_barrier, algs_xchg_mc, algs_barrier, algs_barrier,
     algs_xchg, algs_xchg, algs_red, algs_rs, algs_rs, algs_xchg, algs_xchg};
 static ucc_base_coll_alg_info_t nvl_alg_info[UCC_COLL_TYPE_NUM][8];
 

@@ -269,6 +269,37 @@ static void run_oneshot_rs(World &w, const std::vector<size_t> &counts, int op, 
     printf("  ok %-40s total %zu N %d grid %dx%d%s%s\n", "oneshot reduce_scatter(v)", total, N, nb, nt, inplace ? " inplace" : "", misalign ? " unaligned" : "");
 }
 
+// alltoallv push with a skewed (MoE-like) traffic matrix: landing offsets are looked up in the receiver's published table
+static void run_push_a2av(World &w, int nb, int nt)
+{
+    const int N = w.N;
+    std::vector<std::vector<size_t>> m(N, std::vector<size_t>(N));           // m[s][d] bytes from s to d; rank 0 is the hot expert
+    for (int s = 0; s < N; s++) for (int d = 0; d < N; d++) m[s][d] = d == 0 ? 3000 + 17 * s : (s == d ? 0 : 40 + 4 * ((s + d) % 3));
+    std::vector<std::vector<unsigned char>> sb(N), db(N);
+    std::vector<std::vector<size_t>> sd(N, std::vector<size_t>(N)), rd(N, std::vector<size_t>(N));
+    for (int r = 0; r < N; r++) {
+        size_t so = 0, ro = 0;
+        for (int p = 0; p < N; p++) { sd[r][p] = so; so += m[r][p] + 5; rd[r][p] = ro; ro += m[p][r] + 3; }   // gaps between blocks
+        sb[r].assign(so + 64, 0); db[r].assign(ro + 64, 0xee);
+        for (int p = 0; p < N; p++) for (size_t i = 0; i < m[r][p]; i++) sb[r][16 + sd[r][p] + i] = pat(r, p, i);
+    }
+    for (int rep = 0; rep < 2; rep++) {
+        for (int r = 0; r < N; r++) std::fill(db[r].begin(), db[r].end(), 0xee);
+        launch_all(N, nb, nt, [&](int r) {
+            nvl_push_args_t a; memset(&a, 0, sizeof(a));
+            a.team = w.team(r, false); a.src = sb[r].data() + 16; a.lookup = 1;
+            for (int p = 0; p < N; p++) { a.send_off[p] = sd[r][p]; a.send_bytes[p] = m[r][p]; a.recv_off[p] = rd[r][p]; a.land_off[p] = rd[r][r]; a.dst_of[p] = (char *)db[p].data() + 16; }
+            nvl_exchange_push_kernel(a);
+        });
+        CHECK(w.host_err == 0);
+        for (int r = 0; r < N; r++) for (int p = 0; p < N; p++) {
+            for (size_t i = 0; i < m[p][r]; i++) if (db[r][16 + rd[r][p] + i] != pat(p, r, i)) { printf("EMU FAIL push a2av: rank %d from %d byte %zu\n", r, p, i); exit(1); }
+            for (size_t i = 0; i < 3; i++) CHECK(db[r][16 + rd[r][p] + m[p][r] + i] == 0xee);   // the gap behind every block is untouched
+        }
+    }
+    printf("  ok %-40s N %d grid %dx%d (hot receiver)\n", "push alltoallv", N, nb, nt);
+}
+
 int main(int argc, char **argv)
 {
     const std::string what = argc > 1 ? argv[1] : "all";
@@ -296,6 +327,7 @@ int main(int argc, char **argv)
         if (what == "all" || what == "push") {
             for (bool a2a : {false, true}) { run_push(w, a2a, 4096, 2, 64); run_push(w, a2a, 1003, 3, 32); run_push(w, a2a, 2002, 2, 64, 2); run_push(w, a2a, 777, 2, 64, 3); }
             run_push(w, false, 4096, 2, 64, 0, true);
+            run_push_a2av(w, 2, 64); run_push_a2av(w, 3, 32);
         }
         if (what == "all" || what == "oneshot_rs") {
             run_oneshot_rs(w, std::vector<size_t>(N, 1000), NVL_OP_SUM, false, 2, 64);

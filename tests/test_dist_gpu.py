@@ -120,4 +120,4 @@ def test_multiproc_push_exchange():
     n = min(2, torch.cuda.device_count()) if torch.cuda.is_available() else 0
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
-    _run(n, {"UCC_TL_NVL_TUNE": "allgather:cuda:inf:@push#alltoall:cuda:inf:@push"})
+    _run(n, {"UCC_TL_NVL_TUNE": "allgather:cuda:inf:@push#alltoall:cuda:inf:@push#alltoallv:cuda:inf:@push"})

@@ -13,10 +13,10 @@ for alg in default nvls nvls_pipe; do
   UCC_TL_NVL_TUNE="$T" UCC_TL_NVL_ALLREDUCE_ONESHOT_THRESH=0 timeout 300 $TR bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/bench_${alg}_$N.log 2>&1
   UCC_TL_NVL_SYMMETRIC_SIZE=384M UCC_TL_NVL_TUNE="$T" UCC_TL_NVL_ALLREDUCE_ONESHOT_THRESH=0 timeout 300 $TR bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/bench_${alg}_heap384_$N.log 2>&1
 done
-UCC_TL_NVL_TUNE="allgather:cuda:inf:@push#alltoall:cuda:inf:@push" timeout 300 $TR tests/dist_worker.py cuda > gpurun_out/push_worker_$N.log 2>&1
+UCC_TL_NVL_TUNE="allgather:cuda:inf:@push#alltoall:cuda:inf:@push#alltoallv:cuda:inf:@push" timeout 300 $TR tests/dist_worker.py cuda > gpurun_out/push_worker_$N.log 2>&1
 UCC_TL_NVL_TUNE="reduce_scatter:cuda:0-inf:@oneshot#reduce_scatterv:cuda:0-inf:@oneshot" timeout 300 $TR tests/dist_worker.py cuda > gpurun_out/oneshot_rs_worker_$N.log 2>&1
 timeout 300 $TR tools/coll_bench.py > gpurun_out/coll_default_$N.log 2>&1
-UCC_TL_NVL_TUNE="allgather:cuda:inf:@push#alltoall:cuda:inf:@push" timeout 300 $TR tools/coll_bench.py > gpurun_out/coll_push_$N.log 2>&1
+UCC_TL_NVL_TUNE="allgather:cuda:inf:@push#alltoall:cuda:inf:@push#alltoallv:cuda:inf:@push" timeout 300 $TR tools/coll_bench.py > gpurun_out/coll_push_$N.log 2>&1
 timeout 300 $TR bench.py --gpus $N --steps 10 --warmup 3 --symm 3G > gpurun_out/bench_symm_$N.log 2>&1
 timeout 600 $TR tools/ucc_test_dist.py -M cuda -t world,reverse -I 2 -P 2 -i 2 -m 64:4194304:16 -r all -d int32,float32,bfloat16 -o sum,max,avg --triggered 2 > gpurun_out/test_dist_cuda_$N.log 2>&1
 SYMM_SIZE=3G timeout 400 $TR tests/symm_worker.py > gpurun_out/symm_$N.log 2>&1
