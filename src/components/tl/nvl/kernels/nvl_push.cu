@@ -45,14 +45,15 @@ __global__ void __launch_bounds__(NVL_THREADS_MAX, 2) nvl_exchange_push_kernel(n
     const int N = t.size, me = t.rank;
     BlockSync bs; bs.init(t);
     const char *src = static_cast<const char *>(a.src);
-    /* alltoallv: publish where every source's block lands in my dst.  Each block writes the (identical) table itself, so the
-     * per-block barrier below is enough for the peer block that reads it */
-    if (a.lookup && (int)threadIdx.x < N) reinterpret_cast<volatile uint64_t *>(data_of(t, me))[threadIdx.x] = (uint64_t)a.recv_off[threadIdx.x];
+    /* alltoallv: publish where every source's block lands in my dst.  Every block keeps its own copy of the table (block b of
+     * a peer reads copy b), so the per-block barrier below orders exactly the accesses that touch it */
+    const size_t tbl = (size_t)blockIdx.x * NVL_MAX_PEERS * sizeof(uint64_t);
+    if (a.lookup && (int)threadIdx.x < N) reinterpret_cast<volatile uint64_t *>(data_of(t, me) + tbl)[threadIdx.x] = (uint64_t)a.recv_off[threadIdx.x];
     bs.barrier(t, 1);
     for (int i = 1; i < N; i++) {   /* start at my right neighbour so the N senders do not converge on one receiver */
         int p = me + i; if (p >= N) p -= N;
         if (!a.send_bytes[p]) continue;
-        const size_t land = a.lookup ? (size_t) * reinterpret_cast<volatile const uint64_t *>(data_of(t, p) + (size_t)me * 8) : a.land_off[p];
+        const size_t land = a.lookup ? (size_t) * reinterpret_cast<volatile const uint64_t *>(data_of(t, p) + tbl + (size_t)me * 8) : a.land_off[p];
         push_bytes_grid(a.dst_of[p] + land, src + a.send_off[p], a.send_bytes[p]);
     }
     if (a.send_bytes[me] && a.dst_of[me] + a.land_off[me] != src + a.send_off[me]) push_bytes_grid(a.dst_of[me] + a.land_off[me], src + a.send_off[me], a.send_bytes[me]);

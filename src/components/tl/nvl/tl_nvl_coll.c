@@ -592,6 +592,8 @@ static ucc_status_t xchg_init_push(ucc_base_coll_args_t *b, ucc_base_team_t *b_t
         else { t->push.send_off[p] = 0; t->push.send_bytes[p] = x->pull_bytes[me]; t->push.land_off[p] = x->dst_off[me]; } /* my block, at my displacement, in everybody's dst */
         if (x->dst_off[p] + x->pull_bytes[p] > dst_len) dst_len = x->dst_off[p] + x->pull_bytes[p];
     }
+    /* alltoallv: one landing-offset table per block at the start of the data region */
+    if (t->push.lookup && (size_t)t->nblocks * NVL_MAX_PEERS * sizeof(uint64_t) > ctx->cfg.symmetric_size) { (*task_p)->finalize(*task_p); *task_p = NULL; return UCC_ERR_NOT_SUPPORTED; }
     t->use_push = 1;
     t->want_direct = NVL_DIRECT_FULL; t->need_src = 0; t->need_dst = 1;
     t->exp_src = NULL; t->exp_src_len = 0; t->exp_dst = x->dst; t->exp_dst_len = dst_len;
