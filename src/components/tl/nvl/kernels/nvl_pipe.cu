@@ -56,7 +56,10 @@ template <typename T> static __device__ __forceinline__ void chunk_range(const S
 {
     constexpr int E = 16 / sizeof(T);
     e0 = (size_t)k * g.cap_e;
-    const size_t rmax = dmin(g.cap_e, pl.slice_max - e0), nvmax = (rmax + E - 1) / E, per = (nvmax + gridDim.x - 1) / gridDim.x;
+    /* the range a block owns must not move between chunks (blocks of one rank are not synchronised with each other and the
+     * roles work on three chunks at once): cut it from the full chunk capacity, a shorter last chunk leaves upper blocks idle */
+    const size_t rmax = dmin(g.cap_e, pl.slice_max - e0), nvmax = (rmax + E - 1) / E;
+    const size_t nvsplit = g.chunks > 1 ? g.cap_e / E : nvmax, per = (nvsplit + gridDim.x - 1) / gridDim.x;
     j0 = dmin((size_t)blockIdx.x * per, nvmax); j1 = dmin(j0 + per, nvmax);
 }
 

@@ -207,7 +207,11 @@ static __device__ __forceinline__ void staged_body(const nvl_red_args_t &a, Bloc
     for (int k = 0; k < pl.rounds; k++) {
         const size_t e0 = (size_t)k * pl.cap_e;                       /* first element of every slice in this round */
         const size_t rmax = dmin(pl.cap_e, pl.slice_max - e0);        /* longest slice part in this round */
-        const size_t nvmax = (rmax + E - 1) / E, per = (nvmax + nb - 1) / nb;
+        /* Blocks only synchronise with the SAME block of the peers, so block b may be a round ahead of block b' of its own rank:
+         * the vector range a block owns must not move between rounds.  With several rounds it is cut from the full round
+         * capacity (a shorter last round leaves the upper blocks idle) - cutting it from the round's own length let block b's
+         * staging of the last round overwrite heap vectors block b' had not copied out yet (found in the host emulation). */
+        const size_t nvmax = (rmax + E - 1) / E, nvsplit = pl.rounds > 1 ? pl.cap_e / E : nvmax, per = (nvsplit + nb - 1) / nb;
         const size_t j0 = dmin((size_t)b * per, nvmax), j1 = dmin(j0 + per, nvmax); /* my vector range inside every slice */
 
         /* phase A: stage vector range [j0,j1) of EVERY slice into my heap */

@@ -357,6 +357,12 @@ int main(int argc, char **argv)
             run_symm_ag(w, 1008, true, 2, 64);
         }
     }
+    if (what == "soak") {   // the geometry of the full-stack emulation (tests/hostemu_worker.py): 4 ranks, 1 MB data region, 4 rounds, many launches
+        World w(4, 1 << 20, 0);
+        run_allreduce<float>("staged p2p multi-round soak", w, [](nvl_red_args_t a) { nvl_reduce_staged_kernel<float>(a); }, 900000, NVL_OP_SUM, false, false, 2, 64, 25);
+        run_allreduce<float>("staged nvls multi-round soak", w, [](nvl_red_args_t a) { nvl_reduce_staged_kernel<float>(a); }, 900000, NVL_OP_SUM, true, false, 2, 64, 25);
+        run_allreduce<float>("nvls_pipe multi-chunk soak", w, [](nvl_red_args_t a) { nvl_allreduce_nvls_pipe_kernel<float>(a); }, 900000, NVL_OP_SUM, true, false, 2, 128, 25);
+    }
     printf("NVL_EMU_OK\n");
     return 0;
 }

@@ -1,0 +1,236 @@
+"""Worker of tests/test_nvl_hostemu.py: the tl/nvl plugin built against the emulated CUDA runtime (tests/emu/build_hostemu.sh),
+N ranks in this process, "device" buffers from the emulated cudaMalloc.  Exercises the HOST side of tl/nvl - team creation with a
+shared-pointer heap, score selection / TUNE, launch ordering, the zero-copy exchange board, deferred launches, persistent requests,
+asymmetric memory staging in the core - together with the emulated kernels, and checks every result against numpy."""
+import ctypes as C
+import faulthandler
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+os.environ["UCC_MODULE_DIR"] = os.path.join(ROOT, "build-emu", "lib", "ucc")
+faulthandler.dump_traceback_later(240, exit=True)
+rt = C.CDLL(os.path.join(ROOT, "build-emu", "lib", "libcudart_emu.so"), mode=C.RTLD_GLOBAL)
+sys.path.insert(0, ROOT)
+from ucc_b200 import capi as U  # noqa: E402
+from ucc_b200.harness import UccJob, coll_args  # noqa: E402
+
+CUDA, HOST = U.UCC_MEMORY_TYPE_CUDA, U.UCC_MEMORY_TYPE_HOST
+BASE = {"UCC_TL_NVL_MAX_BLOCKS": "2", "UCC_TL_NVL_NTHREADS": "64", "UCC_TL_NVL_TIMEOUT": "30s", "UCC_TL_NVL_SYMMETRIC_SIZE": "1Mb", "UCC_TLS": "nvl,shm,self",
+        "UCC_COLL_TRACE": "info"}
+ZC = {"UCC_TL_NVL_ZCOPY": "y", "UCC_TL_NVL_ZCOPY_THRESH": "0"}
+NOZC = {"UCC_TL_NVL_ZCOPY": "n"}
+
+
+class Dev:
+    """numpy view of a buffer allocated with the emulated cudaMalloc"""
+
+    def __init__(self, n, dtype=np.float32, fill=None):
+        p = C.c_void_p()
+        nbytes = max(n, 1) * np.dtype(dtype).itemsize
+        assert rt.cudaMalloc(C.byref(p), C.c_size_t(nbytes)) == 0
+        self.ptr = p.value
+        self.a = np.frombuffer((C.c_char * nbytes).from_address(p.value), dtype=dtype)[:n]
+        if fill is not None:
+            self.a[:] = fill
+
+
+def ca(coll, src, dst, dt="float32", **kw):
+    kw.setdefault("count_src", src.a.size if src is not None else 0)
+    kw.setdefault("count_dst", dst.a.size if dst is not None else 0)
+    return coll_args(coll, dt=dt, mem_type=CUDA, src_ptr=src.ptr if src is not None else None, dst_ptr=dst.ptr if dst is not None else None, **kw)
+
+
+def run(team, args):
+    q = team.coll(args)
+    st = q.run()
+    q.finalize()
+    assert st == U.UCC_OK, U.status_str(st)
+    rt.cudaDeviceSynchronize()
+
+
+def rnd(n, seed, dtype=np.float32):
+    g = np.random.default_rng(seed)
+    return g.integers(0, 9, n).astype(dtype)
+
+
+def allreduce_suite(alg, extra, sizes=(1, 7, 1000, 4097, 70000)):
+    env = dict(BASE, UCC_TL_NVL_TUNE=f"allreduce:cuda:inf:@{alg}", UCC_TL_NVL_ALLREDUCE_ONESHOT_THRESH="0" if alg != "oneshot" else "1M", **extra)
+    with UccJob(4, env=env) as j:
+        teams = {n: j.create_team(range(n)) for n in (2, 3, 4)}
+        for n, team in teams.items():
+            if alg == "rhd" and n == 3:
+                continue
+            for count in sizes:
+                for inplace in (False, True):
+                    src = [Dev(count, fill=rnd(count, 10 * n + r)) for r in range(n)]
+                    exp = sum(s.a.copy() for s in src)
+                    dst = src if inplace else [Dev(count, fill=0) for _ in range(n)]
+                    run(team, [ca("allreduce", None if inplace else src[r], dst[r], inplace=inplace) for r in range(n)])
+                    for r in range(n):
+                        assert np.allclose(dst[r].a, exp), (alg, extra, n, count, inplace, r)
+        # other datatypes / operators through the same path
+        team, n = teams[4], 4
+        for dt, op in (("float64", "avg"), ("int32", "max"), ("int64", "sum"), ("uint8", "min"), ("float32", "prod")):
+            npdt = np.dtype(dt)
+            src = [Dev(515, npdt, fill=rnd(515, r + 3, npdt) % 3 + 1) for r in range(n)]
+            dst = [Dev(515, npdt, fill=0) for _ in range(n)]
+            run(team, [ca("allreduce", src[r], dst[r], dt=dt, op=op) for r in range(n)])
+            st = np.stack([s.a.astype(np.float64) for s in src])
+            exp = {"avg": st.mean(0), "max": st.max(0), "sum": st.sum(0), "min": st.min(0), "prod": st.prod(0)}[op]
+            for r in range(n):
+                assert np.allclose(dst[r].a.astype(np.float64), exp), (alg, dt, op, r)
+    print(f"  allreduce {alg} {'zcopy' if extra is ZC else 'staged'} ok", flush=True)
+
+
+def other_colls(extra, tune=""):
+    env = dict(BASE, **extra)
+    if tune:
+        env["UCC_TL_NVL_TUNE"] = tune
+    with UccJob(4, env=env) as j:
+        for n in (3, 4):
+            team = j.create_team(range(n))
+            for blk in (5, 1000, 30011):
+                # reduce_scatter (+ in place), reduce_scatterv
+                src = [Dev(blk * n, fill=rnd(blk * n, r)) for r in range(n)]
+                exp = sum(s.a.copy() for s in src)
+                dst = [Dev(blk, fill=0) for _ in range(n)]
+                run(team, [ca("reduce_scatter", src[r], dst[r]) for r in range(n)])
+                for r in range(n):
+                    assert np.allclose(dst[r].a, exp[r * blk:(r + 1) * blk]), ("rs", n, blk, r)
+                run(team, [ca("reduce_scatter", None, src[r], inplace=True) for r in range(n)])
+                for r in range(n):
+                    assert np.allclose(src[r].a[r * blk:(r + 1) * blk], exp[r * blk:(r + 1) * blk]), ("rs inplace", n, blk, r)
+                counts = [blk + 3 * r for r in range(n)]
+                offs = np.concatenate([[0], np.cumsum(counts)[:-1]])
+                src = [Dev(sum(counts), fill=rnd(sum(counts), r + 50)) for r in range(n)]
+                exp = sum(s.a.copy() for s in src)
+                dst = [Dev(counts[r], fill=0) for r in range(n)]
+                run(team, [ca("reduce_scatterv", src[r], dst[r], dst_counts=counts, dst_displs=offs) for r in range(n)])
+                for r in range(n):
+                    assert np.allclose(dst[r].a, exp[offs[r]:offs[r] + counts[r]]), ("rsv", n, blk, r)
+                # reduce to a non-zero root
+                src = [Dev(blk, fill=rnd(blk, r + 7)) for r in range(n)]
+                exp = sum(s.a.copy() for s in src)
+                out = Dev(blk, fill=0)
+                run(team, [ca("reduce", src[r], out if r == n - 1 else None, root=n - 1, count_dst=blk if r == n - 1 else 0) for r in range(n)])
+                assert np.allclose(out.a, exp), ("reduce", n, blk)
+                # allgather (+ in place), allgatherv
+                src = [Dev(blk, fill=rnd(blk, r + 20)) for r in range(n)]
+                exp = np.concatenate([s.a for s in src])
+                dst = [Dev(blk * n, fill=0) for _ in range(n)]
+                run(team, [ca("allgather", src[r], dst[r]) for r in range(n)])
+                for r in range(n):
+                    assert np.array_equal(dst[r].a, exp), ("allgather", n, blk, r)
+                for r in range(n):
+                    dst[r].a[:] = 0
+                    dst[r].a[r * blk:(r + 1) * blk] = src[r].a
+                run(team, [ca("allgather", None, dst[r], inplace=True) for r in range(n)])
+                for r in range(n):
+                    assert np.array_equal(dst[r].a, exp), ("allgather inplace", n, blk, r)
+                srcv = [Dev(counts[r], fill=rnd(counts[r], r + 30)) for r in range(n)]
+                expv = np.concatenate([s.a for s in srcv])
+                dstv = [Dev(sum(counts), fill=0) for _ in range(n)]
+                run(team, [ca("allgatherv", srcv[r], dstv[r], dst_counts=counts, dst_displs=offs) for r in range(n)])
+                for r in range(n):
+                    assert np.array_equal(dstv[r].a, expv), ("allgatherv", n, blk, r)
+                # alltoall, skewed alltoallv (rank 0 is the hot receiver)
+                src = [Dev(blk * n, fill=rnd(blk * n, r + 40)) for r in range(n)]
+                dst = [Dev(blk * n, fill=0) for _ in range(n)]
+                run(team, [ca("alltoall", src[r], dst[r]) for r in range(n)])
+                for r in range(n):
+                    assert np.array_equal(dst[r].a, np.concatenate([src[p].a[r * blk:(r + 1) * blk] for p in range(n)])), ("alltoall", n, blk, r)
+                m = np.array([[blk * 2 if d == 0 else (0 if s == d else 3 + (s + d) % 4) for d in range(n)] for s in range(n)])
+                src = [Dev(int(m[r].sum()), fill=rnd(int(m[r].sum()), r + 60)) for r in range(n)]
+                dst = [Dev(int(m[:, r].sum()), fill=0) for r in range(n)]
+                sd = [np.concatenate([[0], np.cumsum(m[r])[:-1]]) for r in range(n)]
+                rd = [np.concatenate([[0], np.cumsum(m[:, r])[:-1]]) for r in range(n)]
+                run(team, [ca("alltoallv", src[r], dst[r], src_counts=m[r], src_displs=sd[r], dst_counts=m[:, r], dst_displs=rd[r]) for r in range(n)])
+                for r in range(n):
+                    exp = np.concatenate([src[p].a[sd[p][r]:sd[p][r] + m[p][r]] for p in range(n)])
+                    assert np.array_equal(dst[r].a, exp), ("alltoallv", n, blk, r)
+                # bcast, gather, scatter
+                b = [Dev(blk, fill=rnd(blk, 99) if r == 1 else 0) for r in range(n)]
+                run(team, [ca("bcast", b[r], None, root=1, count_dst=0) for r in range(n)])
+                for r in range(n):
+                    assert np.array_equal(b[r].a, rnd(blk, 99)), ("bcast", n, blk, r)
+                src = [Dev(blk, fill=rnd(blk, r + 70)) for r in range(n)]
+                g = Dev(blk * n, fill=0)
+                run(team, [ca("gather", src[r], g if r == 0 else None, root=0, count_dst=blk * n if r == 0 else 0) for r in range(n)])
+                assert np.array_equal(g.a, np.concatenate([s.a for s in src])), ("gather", n, blk)
+                big = Dev(blk * n, fill=rnd(blk * n, 5))
+                outs = [Dev(blk, fill=0) for _ in range(n)]
+                run(team, [ca("scatter", big if r == 2 else None, outs[r], root=2, count_src=blk * n if r == 2 else 0) for r in range(n)])
+                for r in range(n):
+                    assert np.array_equal(outs[r].a, big.a[r * blk:(r + 1) * blk]), ("scatter", n, blk, r)
+            run(team, [coll_args("barrier") for _ in range(n)])
+    print(f"  collectives {'zcopy' if extra is ZC else 'staged'} {tune or 'default algorithms'} ok", flush=True)
+
+
+def persistent_and_teams():
+    with UccJob(4, env=dict(BASE, **ZC)) as j:
+        ta, tb = j.create_team(range(4)), j.create_team([3, 1, 0])
+        n, count = 4, 20000
+        src = [Dev(count, fill=0) for _ in range(n)]
+        dst = [Dev(count, fill=0) for _ in range(n)]
+        q = ta.coll([ca("allreduce", src[r], dst[r], persistent=True) for r in range(n)])
+        for it in range(4):
+            for r in range(n):
+                src[r].a[:] = rnd(count, it * 10 + r)
+            assert q.run() == U.UCC_OK
+            rt.cudaDeviceSynchronize()
+            exp = sum(s.a.copy() for s in src)
+            for r in range(n):
+                assert np.allclose(dst[r].a, exp), ("persistent", it, r)
+            # a collective on the second team between the posts (ranks 3,1,0 of the job)
+            x = [Dev(333, fill=float(i + 1)) for i in range(3)]
+            run(tb, [ca("allreduce", None, x[i], inplace=True) for i in range(3)])
+            assert all(np.all(v.a == 6.0) for v in x)
+        q.finalize()
+        # messages larger than the heap data region: several rounds inside one kernel
+        big = 900000
+        src = [Dev(big, fill=rnd(big, r)) for r in range(n)]
+        dst = [Dev(big, fill=0) for _ in range(n)]
+    with UccJob(4, env=dict(BASE, **NOZC)) as j:
+        t = j.create_team(range(4))
+        run(t, [ca("allreduce", src[r], dst[r]) for r in range(n)])
+        exp = sum(s.a.copy() for s in src)
+        for r in range(n):
+            assert np.allclose(dst[r].a, exp), ("multi-round", r)
+    print("  persistent / two teams / multi-round ok", flush=True)
+
+
+def asymmetric_memory():
+    """root's src and dst in different memory types (reference test/gtest/asym_mem): staged by the core around tl/nvl"""
+    with UccJob(4, env=dict(BASE)) as j:
+        t, n, count = j.create_team(range(4)), 4, 3000
+        src = [Dev(count, fill=rnd(count, r)) for r in range(n)]
+        host_dst = np.zeros(count, np.float32)
+        args = [ca("reduce", src[r], None, root=1, count_dst=0) for r in range(n)]
+        args[1] = coll_args("reduce", dt="float32", root=1, src_ptr=src[1].ptr, dst_ptr=host_dst.ctypes.data, count_src=count, count_dst=count, src_mem_type=CUDA, dst_mem_type=HOST)
+        run(t, args)
+        assert np.allclose(host_dst, sum(s.a for s in src))
+        host_src = np.arange(n * 100, dtype=np.float32)
+        dst = [Dev(100, fill=0) for _ in range(n)]
+        args = [coll_args("scatter", dt="float32", root=0, dst_ptr=dst[r].ptr, count_dst=100, count_src=0, mem_type=CUDA) for r in range(n)]
+        args[0] = coll_args("scatter", dt="float32", root=0, src_ptr=host_src.ctypes.data, dst_ptr=dst[0].ptr, count_src=n * 100, count_dst=100, src_mem_type=HOST, dst_mem_type=CUDA)
+        run(t, args)
+        for r in range(n):
+            assert np.array_equal(dst[r].a, host_src[r * 100:(r + 1) * 100])
+    print("  asymmetric memory ok", flush=True)
+
+
+SCENARIOS = {
+    "allreduce": lambda: [allreduce_suite(a, e) for a, e in (("oneshot", NOZC), ("twoshot", NOZC), ("twoshot", ZC), ("ring", NOZC), ("rhd", NOZC))],
+    "colls_staged": lambda: other_colls(NOZC),
+    "colls_zcopy": lambda: other_colls(ZC),
+    "colls_push": lambda: other_colls(ZC, "allgather:cuda:inf:@push#allgatherv:cuda:inf:@push#alltoall:cuda:inf:@push#alltoallv:cuda:inf:@push#reduce_scatter:cuda:inf:@oneshot#reduce_scatterv:cuda:inf:@oneshot"),
+    "colls_ring": lambda: other_colls(NOZC, "allgather:cuda:inf:@ring#allgatherv:cuda:inf:@ring#reduce_scatter:cuda:inf:@ring#reduce_scatterv:cuda:inf:@ring"),
+    "misc": lambda: [persistent_and_teams(), asymmetric_memory()],
+}
+
+if __name__ == "__main__":
+    SCENARIOS[sys.argv[1]]()
+    print("HOSTEMU_WORKER_OK", flush=True)
