@@ -222,6 +222,67 @@ def asymmetric_memory():
     print("  asymmetric memory ok", flush=True)
 
 
+def triggered(extra):
+    """stream-ordered posts (ucc_collective_triggered_post, what ProcessGroupUCC uses): the collective must be ordered behind work
+    already queued on the user's stream, UCC_EVENT_COLLECTIVE_POST must arrive (after the real launch when it is deferred by the
+    zero-copy exchange) and work queued afterwards must see the result"""
+    rt.cudaStreamCreate.argtypes = [C.POINTER(C.c_void_p)]
+    rt.cudaMemcpyAsync.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
+    rt.cudaStreamSynchronize.argtypes = [C.c_void_p]
+    n, count = 4, 50000
+    with UccJob(n, env=dict(BASE, **extra)) as j:
+        team = j.create_team(range(n))
+        streams, ees = [], []
+        for r in range(n):
+            s = C.c_void_p()
+            assert rt.cudaStreamCreate(C.byref(s)) == 0
+            ep = U.ucc_ee_params_t()
+            ep.ee_type, ep.ee_context, ep.ee_context_size = U.UCC_EE_CUDA_STREAM, s.value, C.sizeof(C.c_void_p)
+            ee = U.handle()
+            U.check(U.ucc_ee_create(team.members[r].team, C.byref(ep), C.byref(ee)), "ee_create")
+            streams.append(s)
+            ees.append(ee)
+        for it in range(3):
+            stage = [Dev(count, fill=rnd(count, 7 * it + r)) for r in range(n)]   # what the stream copies into src BEFORE the collective
+            src = [Dev(count, fill=-1) for _ in range(n)]
+            dst = [Dev(count, fill=0) for _ in range(n)]
+            after = [Dev(count, fill=0) for _ in range(n)]                        # copied from dst by the stream AFTER the collective
+            reqs = []
+            for r in range(n):
+                rt.cudaMemcpyAsync(src[r].ptr, stage[r].ptr, count * 4, 3, streams[r])
+                a = ca("allreduce", src[r], dst[r])
+                q = C.POINTER(U.ucc_coll_req_t)()
+                U.check(U.ucc_collective_init(C.byref(a), C.byref(q), team.members[r].team), "init")
+                ev = U.ucc_ev_t()
+                ev.ev_type, ev.req = U.UCC_EVENT_COMPUTE_COMPLETE, C.cast(q, C.c_void_p)
+                U.check(U.ucc_collective_triggered_post(ees[r], C.byref(ev)), "triggered_post")
+                reqs.append((a, q))
+            posted = [False] * n
+            import time
+            t0 = time.time()
+            while not all(posted) or any(q.contents.status == U.UCC_INPROGRESS for _, q in reqs):
+                for r in range(n):
+                    U.ucc_context_progress(j.procs[r].ctx)
+                    e = C.POINTER(U.ucc_ev_t)()
+                    while U.ucc_ee_get_event(ees[r], C.byref(e)) == U.UCC_OK:
+                        if e.contents.ev_type == U.UCC_EVENT_COLLECTIVE_POST:
+                            assert not posted[r]
+                            posted[r] = True
+                            rt.cudaMemcpyAsync(after[r].ptr, dst[r].ptr, count * 4, 3, streams[r])   # ordered behind the collective
+                        U.ucc_ee_ack_event(ees[r], e)
+                assert time.time() - t0 < 120, (posted, [q.contents.status for _, q in reqs])
+            for r in range(n):
+                assert reqs[r][1].contents.status == U.UCC_OK
+                rt.cudaStreamSynchronize(streams[r])
+                U.ucc_collective_finalize(reqs[r][1])
+            exp = sum(s.a.copy() for s in stage)
+            for r in range(n):
+                assert np.allclose(dst[r].a, exp) and np.allclose(after[r].a, exp), ("triggered", it, r)
+        for ee in ees:
+            U.ucc_ee_destroy(ee)
+    print(f"  triggered posts {'zcopy (deferred launches)' if extra is ZC else 'staged'} ok", flush=True)
+
+
 SCENARIOS = {
     "allreduce": lambda: [allreduce_suite(a, e) for a, e in (("oneshot", NOZC), ("twoshot", NOZC), ("twoshot", ZC), ("ring", NOZC), ("rhd", NOZC))],
     "colls_staged": lambda: other_colls(NOZC),
@@ -229,6 +290,7 @@ SCENARIOS = {
     "colls_push": lambda: other_colls(ZC, "allgather:cuda:inf:@push#allgatherv:cuda:inf:@push#alltoall:cuda:inf:@push#alltoallv:cuda:inf:@push#reduce_scatter:cuda:inf:@oneshot#reduce_scatterv:cuda:inf:@oneshot"),
     "colls_ring": lambda: other_colls(NOZC, "allgather:cuda:inf:@ring#allgatherv:cuda:inf:@ring#reduce_scatter:cuda:inf:@ring#reduce_scatterv:cuda:inf:@ring"),
     "misc": lambda: [persistent_and_teams(), asymmetric_memory()],
+    "triggered": lambda: [triggered(NOZC), triggered(ZC)],
 }
 
 if __name__ == "__main__":
