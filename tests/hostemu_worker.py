@@ -283,6 +283,45 @@ def triggered(extra):
     print(f"  triggered posts {'zcopy (deferred launches)' if extra is ZC else 'staged'} ok", flush=True)
 
 
+def cross_team_order(extra):
+    """two teams over the same ranks, collectives posted in opposite team order on odd and even ranks (legal: only the order
+    WITHIN a team must agree), several in flight per team; with zero-copy every launch is deferred until the peers published"""
+    import time
+    n, count, depth = 4, 30000, 3
+    with UccJob(n, env=dict(BASE, **extra)) as j:
+        ta, tb = j.create_team(range(n)), j.create_team(range(n))
+        bufs = {}
+        reqs = {r: [] for r in range(n)}
+        for r in range(n):
+            order = [(ta, "a"), (tb, "b")] if r % 2 == 0 else [(tb, "b"), (ta, "a")]
+            for k in range(depth):
+                for team, name in order:
+                    src = Dev(count, fill=rnd(count, hash((name, k, r)) % 1000))
+                    dst = Dev(count, fill=0)
+                    bufs[(name, k, r)] = (src, dst)
+                    a = ca("allreduce", src, dst)
+                    q = C.POINTER(U.ucc_coll_req_t)()
+                    U.check(U.ucc_collective_init(C.byref(a), C.byref(q), team.members[r].team), "init")
+                    U.check(U.ucc_collective_post(q), "post")
+                    reqs[r].append((a, q))
+        t0 = time.time()
+        while any(q.contents.status == U.UCC_INPROGRESS for r in range(n) for _, q in reqs[r]):
+            for r in range(n):
+                U.ucc_context_progress(j.procs[r].ctx)
+            assert time.time() - t0 < 120, "cross-team posts did not complete"
+        rt.cudaDeviceSynchronize()
+        for r in range(n):
+            for _, q in reqs[r]:
+                assert q.contents.status == U.UCC_OK
+                U.ucc_collective_finalize(q)
+        for name in "ab":
+            for k in range(depth):
+                exp = sum(bufs[(name, k, r)][0].a for r in range(n))
+                for r in range(n):
+                    assert np.allclose(bufs[(name, k, r)][1].a, exp), ("cross team", name, k, r)
+    print(f"  cross-team post order {'zcopy' if extra is ZC else 'staged'} ok", flush=True)
+
+
 SCENARIOS = {
     "allreduce": lambda: [allreduce_suite(a, e) for a, e in (("oneshot", NOZC), ("twoshot", NOZC), ("twoshot", ZC), ("ring", NOZC), ("rhd", NOZC))],
     "colls_staged": lambda: other_colls(NOZC),
@@ -291,6 +330,7 @@ SCENARIOS = {
     "colls_ring": lambda: other_colls(NOZC, "allgather:cuda:inf:@ring#allgatherv:cuda:inf:@ring#reduce_scatter:cuda:inf:@ring#reduce_scatterv:cuda:inf:@ring"),
     "misc": lambda: [persistent_and_teams(), asymmetric_memory()],
     "triggered": lambda: [triggered(NOZC), triggered(ZC)],
+    "cross_team": lambda: [cross_team_order(NOZC), cross_team_order(ZC)],
 }
 
 if __name__ == "__main__":
