@@ -111,7 +111,8 @@ ucc_status_t ucc_task_complete(ucc_coll_task_t *task)
             char buf[256];
             ucc_coll_args_str(&task->bargs.args, task->bargs.team ? ucc_team_rank_(task->bargs.team) : 0,
                               task->bargs.team ? ucc_team_size_(task->bargs.team) : 1, buf, sizeof(buf));
-            ucc_warn("timeout %g sec has expired on %s seq_num %u", task->timeout, buf, task->seq_num);
+            if (task->timeout > 0) ucc_warn("timeout %g sec has expired on %s seq_num %u", task->timeout, buf, task->seq_num);
+            else ucc_warn("%s seq_num %u timed out inside the transport (a team member did not arrive)", buf, task->seq_num);
         } else {
             ucc_error("failure in task %p, %s", (void *)task, ucc_status_string(status));
         }

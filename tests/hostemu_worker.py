@@ -322,6 +322,33 @@ def cross_team_order(extra):
     print(f"  cross-team post order {'zcopy' if extra is ZC else 'staged'} ok", flush=True)
 
 
+def device_timeout():
+    """a member that never posts: the kernels of the others give up after UCC_TL_NVL_TIMEOUT (bounded device-side spin) and their
+    requests complete with an error instead of hanging the device"""
+    import time
+    n, count = 3, 1000
+    with UccJob(n, env=dict(BASE, UCC_TL_NVL_TIMEOUT="2s", **NOZC)) as j:
+        team = j.create_team(range(n))
+        reqs = []
+        for r in (0, 1):                          # rank 2 stays away
+            a = ca("allreduce", Dev(count, fill=1.0), Dev(count, fill=0))
+            q = C.POINTER(U.ucc_coll_req_t)()
+            U.check(U.ucc_collective_init(C.byref(a), C.byref(q), team.members[r].team), "init")
+            U.check(U.ucc_collective_post(q), "post")
+            reqs.append((a, q))
+        t0 = time.time()
+        while any(q.contents.status == U.UCC_INPROGRESS for _, q in reqs):
+            for r in range(n):
+                U.ucc_context_progress(j.procs[r].ctx)
+            assert time.time() - t0 < 60, "requests still in progress long after the device-side timeout"
+        took = time.time() - t0
+        for _, q in reqs:
+            assert q.contents.status < 0, q.contents.status          # UCC_ERR_TIMED_OUT
+            U.ucc_collective_finalize(q)
+        assert 1.0 < took < 30, took
+        print(f"  device-side timeout ok (statuses {[q.contents.status if q else None for _, q in reqs]}, {took:.1f} s)", flush=True)
+
+
 SCENARIOS = {
     "allreduce": lambda: [allreduce_suite(a, e) for a, e in (("oneshot", NOZC), ("twoshot", NOZC), ("twoshot", ZC), ("ring", NOZC), ("rhd", NOZC))],
     "colls_staged": lambda: other_colls(NOZC),
@@ -330,6 +357,7 @@ SCENARIOS = {
     "colls_ring": lambda: other_colls(NOZC, "allgather:cuda:inf:@ring#allgatherv:cuda:inf:@ring#reduce_scatter:cuda:inf:@ring#reduce_scatterv:cuda:inf:@ring"),
     "misc": lambda: [persistent_and_teams(), asymmetric_memory()],
     "triggered": lambda: [triggered(NOZC), triggered(ZC)],
+    "timeout": device_timeout,
     "cross_team": lambda: [cross_team_order(NOZC), cross_team_order(ZC)],
 }
 
