@@ -157,6 +157,22 @@ def test_allreduce_multi_round(job, n):
         assert_close(dst[r], exp, "float32")
 
 
+@pytest.mark.parametrize("n", [2, 4])
+def test_allreduce_multi_round_short_last_round(job, n):
+    """several heap rounds with a SHORTER last round, repeated: the per-block vector ranges must not move between rounds
+    (cross-block race found in the host emulation, tests/emu/nvl_emu.cpp `soak`; blocks of one rank are not synchronised)"""
+    team = job[n]
+    cap = (8 * 1024 * 1024 // n // 16) * 4          # elements of one slice per round (8 MB heap, float32)
+    count = n * (2 * cap + cap // 5 + 3)            # two full rounds + a short, ragged third one
+    for it in range(4):
+        src = [gen("float32", count, 10 * it + r) for r in range(n)]
+        dst = [torch.zeros(count, device="cuda") for _ in range(n)]
+        run(team, [cargs("allreduce", src[r], dst[r], "float32") for r in range(n)])
+        exp = ref_reduce("sum", src)
+        for r in range(n):
+            assert_close(dst[r], exp, "float32")
+
+
 @pytest.mark.parametrize("n", [2, 3, 8])
 @pytest.mark.parametrize("inplace", [False, True])
 def test_reduce_scatter(job, n, inplace):
