@@ -222,7 +222,9 @@ static __device__ __forceinline__ void staged_body(const nvl_red_args_t &a, Bloc
             char *hb = mydata + (size_t)s * cap_bytes;
             if (((uintptr_t)sb & 15) == 0) {
                 copy_vecs<8, false>(hb, reinterpret_cast<const char *>(sb), j0, dmin(jend, nfull));
-                if (nfull >= j0 && nfull < jend && threadIdx.x == 0) st_v4(hb + nfull * 16, load_src_vec<T>(sb, nfull * E, rc, false)); /* ragged tail */
+                /* ragged tail: by the thread that owns this vector index in copy_vecs (v = j0 + tid mod blockDim) - the same thread
+                 * copied the vector out of the heap in the previous round's phase C, and there is no block barrier in between */
+                if (nfull >= j0 && nfull < jend && threadIdx.x == (unsigned)((nfull - j0) % blockDim.x)) st_v4(hb + nfull * 16, load_src_vec<T>(sb, nfull * E, rc, false));
             } else {
                 for (size_t j = j0 + threadIdx.x; j < jend; j += blockDim.x) st_v4(hb + j * 16, load_src_vec<T>(sb, j * E, rc, false));
             }
@@ -252,7 +254,7 @@ static __device__ __forceinline__ void staged_body(const nvl_red_args_t &a, Bloc
                 const char *hb = mydata + (size_t)s * cap_bytes;
                 if (((uintptr_t)db & 15) == 0) {
                     copy_vecs<8, true>(reinterpret_cast<char *>(db), hb, j0, dmin(jend, nfull));
-                    if (nfull >= j0 && nfull < jend && threadIdx.x == 0) store_dst_vec<T>(db, nfull * E, rc, false, ld_peer_v4(hb + nfull * 16));
+                    if (nfull >= j0 && nfull < jend && threadIdx.x == (unsigned)((nfull - j0) % blockDim.x)) store_dst_vec<T>(db, nfull * E, rc, false, ld_peer_v4(hb + nfull * 16));
                 } else {
                     for (size_t j = j0 + threadIdx.x; j < jend; j += blockDim.x) store_dst_vec<T>(db, j * E, rc, false, ld_peer_v4(hb + j * 16));
                 }

@@ -357,6 +357,10 @@ int main(int argc, char **argv)
             run_symm_ag(w, 1008, true, 2, 64);
         }
     }
+    if (what == "soak2") {   // two full rounds + a short RAGGED last round, 2 ranks (the geometry of the GPU regression test)
+        World w(2, 1 << 20, 0);
+        run_allreduce<float>("staged p2p ragged short last round", w, [](nvl_red_args_t a) { nvl_reduce_staged_kernel<float>(a); }, 576722, NVL_OP_SUM, false, false, 2, 64, 30);
+    }
     if (what == "soak") {   // the geometry of the full-stack emulation (tests/hostemu_worker.py): 4 ranks, 1 MB data region, 4 rounds, many launches
         World w(4, 1 << 20, 0);
         run_allreduce<float>("staged p2p multi-round soak", w, [](nvl_red_args_t a) { nvl_reduce_staged_kernel<float>(a); }, 900000, NVL_OP_SUM, false, false, 2, 64, 25);

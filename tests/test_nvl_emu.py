@@ -23,7 +23,7 @@ def emu(tmp_path_factory):
     return str(exe)
 
 
-@pytest.mark.parametrize("what", ["staged", "xchg", "pipe", "symm", "push", "oneshot_rs", "soak"])
+@pytest.mark.parametrize("what", ["staged", "xchg", "pipe", "symm", "push", "oneshot_rs", "soak", "soak2"])
 def test_nvl_kernels_host_emulation(emu, what):
     out = subprocess.run([emu, what], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "NVL_EMU_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-2000:]
