@@ -14,7 +14,13 @@ template <> struct EcOp<EC_OP_PROD, cuDoubleComplex> { static __device__ __force
 
 static_assert((int)EC_OP_SUM == (int)NVL_OP_SUM && (int)EC_OP_BXOR == (int)NVL_OP_BXOR, "operator enums must line up");
 
-template <typename T> __device__ __forceinline__ T scale(T x, double alpha) { return (T)(x * (T)alpha); }
+/* x * alpha: integer accumulators are scaled in double precision and truncated (reference ec_cuda_reduce_ops.h: d[i] * alpha),
+ * casting alpha (1/N for AVG) to the integer type first would make it 0 */
+template <typename T> __device__ __forceinline__ T scale(T x, double alpha)
+{
+    if constexpr (IsIntAcc<T>::v) return (T)((double)x * alpha);
+    else return (T)(x * (T)alpha);
+}
 template <> __device__ __forceinline__ cuFloatComplex scale(cuFloatComplex x, double a) { return make_cuFloatComplex(x.x * (float)a, x.y * (float)a); }
 template <> __device__ __forceinline__ cuDoubleComplex scale(cuDoubleComplex x, double a) { return make_cuDoubleComplex(x.x * a, x.y * a); }
 
@@ -48,9 +54,9 @@ template <typename T, int OP> static __device__ __forceinline__ void reduce_body
         for (int k = 1; k < a.n_srcs; k++) acc.add(ld_src_v4((const char *)src_k(a, k) + v * 16));
         if (a.with_alpha) {
 #pragma unroll
-            for (int i = 0; i < E; i++) acc.a[i] = (A)(acc.a[i] * (A)a.alpha);
+            for (int i = 0; i < E; i++) acc.a[i] = scale<A>(acc.a[i], a.alpha);
         }
-        st_v4((char *)a.dst + v * 16, acc.get(1.0f));
+        st_v4((char *)a.dst + v * 16, acc.get(1.0f, 1));
     }
     reduce_scalar<T, A, OP>(a, nvec * E, a.count, [](T x) { return to_acc<T>(x); }, [](A x) { return from_acc<T>(x); });
 }

@@ -23,6 +23,7 @@ static struct {
     void *h;
     ncclResult_t (*GetUniqueId)(ncclUniqueId *);
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
+    ncclResult_t (*CommInitRankConfig)(ncclComm_t *, int, ncclUniqueId, int, ncclConfig_t *);
     ncclResult_t (*CommDestroy)(ncclComm_t);
     ncclResult_t (*CommAbort)(ncclComm_t);
     ncclResult_t (*CommGetAsyncError)(ncclComm_t, ncclResult_t *);
@@ -42,10 +43,13 @@ typedef enum { NCCL_SYNC_AUTO, NCCL_SYNC_EVENT, NCCL_SYNC_DRIVER } nccl_sync_t;
 typedef struct ucc_tl_nccl_context_config { ucc_tl_context_config_t super; unsigned sync; int blocking, lazy_init; } ucc_tl_nccl_context_config_t;
 typedef struct ucc_tl_nccl_lib { ucc_tl_lib_t super; } ucc_tl_nccl_lib_t;
 typedef struct ucc_tl_nccl_context { ucc_tl_context_t super; ucc_tl_nccl_context_config_t cfg; ucc_mpool_t task_mp; int dev; float *barrier_buf; } ucc_tl_nccl_context_t;
-typedef enum { NCCL_COMM_UNINIT, NCCL_COMM_READY, NCCL_COMM_ERROR } nccl_comm_state_t;
+typedef enum { NCCL_COMM_UNINIT, NCCL_COMM_INITING, NCCL_COMM_READY, NCCL_COMM_ERROR } nccl_comm_state_t;
+/* what every member publishes at team creation: rank 0's unique id + where the member runs, so that all members take
+ * the same decision about teams NCCL cannot serve (two members on one GPU) and about members sharing a process */
+typedef struct nccl_member_info { ncclUniqueId id; uint64_t host_hash; int32_t pid; int32_t dev; char busid[24]; } nccl_member_info_t;
 typedef struct ucc_tl_nccl_team {
-    ucc_tl_team_t super; ncclUniqueId *ids; void *oob_req; ucc_team_oob_coll_t oob; int oob_internal;
-    ncclComm_t comm; nccl_comm_state_t state; cudaStream_t stream; ncclUniqueId my_id;
+    ucc_tl_team_t super; nccl_member_info_t *ids; void *oob_req; ucc_team_oob_coll_t oob; int oob_internal;
+    ncclComm_t comm; nccl_comm_state_t state; cudaStream_t stream; nccl_member_info_t my_id; int inproc_peers;
 } ucc_tl_nccl_team_t;
 typedef struct ucc_tl_nccl_task {
     ucc_coll_task_t super; ucc_tl_nccl_team_t *team; cudaEvent_t event; int captured; int alg;
@@ -76,7 +80,7 @@ static ucc_status_t load_nccl(void)
     if (!nc.h && !getenv("UCC_TL_NCCL_NO_SYSTEM_LIB")) nc.h = dlopen("libnccl.so.2", RTLD_LAZY | RTLD_LOCAL);
     if (!nc.h) return UCC_ERR_NO_RESOURCE;
 #define SYM(_f) *(void **)&nc._f = dlsym(nc.h, "nccl" #_f)
-    SYM(GetUniqueId); SYM(CommInitRank); SYM(CommDestroy); SYM(CommAbort); SYM(CommGetAsyncError); SYM(GetErrorString); SYM(AllReduce); SYM(Broadcast);
+    SYM(GetUniqueId); SYM(CommInitRank); SYM(CommInitRankConfig); SYM(CommDestroy); SYM(CommAbort); SYM(CommGetAsyncError); SYM(GetErrorString); SYM(AllReduce); SYM(Broadcast);
     SYM(Reduce); SYM(AllGather); SYM(ReduceScatter); SYM(Send); SYM(Recv); SYM(GroupStart); SYM(GroupEnd);
     return (nc.GetUniqueId && nc.CommInitRank && nc.AllReduce && nc.Send && nc.GroupStart) ? UCC_OK : UCC_ERR_NO_RESOURCE;
 }
@@ -112,15 +116,38 @@ static ucc_status_t nccl_ctx_get_attr(const ucc_base_context_t *b, ucc_base_ctx_
 { (void)b; if (attr->attr.mask & UCC_CONTEXT_ATTR_FIELD_CTX_ADDR_LEN) attr->attr.ctx_addr_len = 0; attr->topo_required = 0; attr->attr.global_work_buffer_size = 0; return UCC_OK; }
 
 /* ---- team ---- */
-static ucc_status_t nccl_comm_init(ucc_tl_nccl_team_t *team)
+/* Communicator creation.  Blocking mode (default, one member per process): ncclCommInitRank returns when every member
+ * has called it.  Non-blocking mode (UCC_TL_NCCL_BLOCKING=n, or members that share a process - a blocking call issued from
+ * the single thread that drives several members would wait for members that are never reached): ncclCommInitRankConfig
+ * with blocking=0, then ncclCommGetAsyncError is polled; `wait` = spin here until the communicator is usable. */
+static ucc_status_t nccl_comm_init(ucc_tl_nccl_team_t *team, int wait)
 {
+    int nonblocking = (!NCCL_CTX(team)->cfg.blocking || team->inproc_peers) && nc.CommInitRankConfig && nc.CommGetAsyncError;
+    ncclResult_t r, ar;
     if (team->state == NCCL_COMM_READY) return UCC_OK;
     if (team->state == NCCL_COMM_ERROR) return UCC_ERR_NOT_SUPPORTED;
-    if (cudaStreamCreateWithFlags(&team->stream, cudaStreamNonBlocking) != cudaSuccess) { (void)cudaGetLastError(); team->state = NCCL_COMM_ERROR; return UCC_ERR_NOT_SUPPORTED; }
-    if (nc.CommInitRank(&team->comm, (int)UCC_TL_TEAM_SIZE(team), team->ids[0], (int)UCC_TL_TEAM_RANK(team)) != ncclSuccess) {
-        tl_debug(NLIB(team), "ncclCommInitRank failed"); team->state = NCCL_COMM_ERROR; return UCC_ERR_NOT_SUPPORTED; }
-    team->state = NCCL_COMM_READY;
-    return UCC_OK;
+    if (team->state == NCCL_COMM_UNINIT) {
+        if (cudaStreamCreateWithFlags(&team->stream, cudaStreamNonBlocking) != cudaSuccess) { (void)cudaGetLastError(); team->state = NCCL_COMM_ERROR; return UCC_ERR_NOT_SUPPORTED; }
+        if (nonblocking) {
+            ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
+            cfg.blocking = 0;
+            r = nc.CommInitRankConfig(&team->comm, (int)UCC_TL_TEAM_SIZE(team), team->ids[0].id, (int)UCC_TL_TEAM_RANK(team), &cfg);
+            if (r != ncclSuccess && r != ncclInProgress) { tl_debug(NLIB(team), "ncclCommInitRankConfig failed"); team->state = NCCL_COMM_ERROR; return UCC_ERR_NOT_SUPPORTED; }
+            team->state = NCCL_COMM_INITING;
+        } else {
+            if (nc.CommInitRank(&team->comm, (int)UCC_TL_TEAM_SIZE(team), team->ids[0].id, (int)UCC_TL_TEAM_RANK(team)) != ncclSuccess) {
+                tl_debug(NLIB(team), "ncclCommInitRank failed"); team->state = NCCL_COMM_ERROR; return UCC_ERR_NOT_SUPPORTED; }
+            team->state = NCCL_COMM_READY;
+            return UCC_OK;
+        }
+    }
+    do {
+        ar = ncclSuccess;
+        r = nc.CommGetAsyncError(team->comm, &ar);
+        if (r != ncclSuccess || (ar != ncclSuccess && ar != ncclInProgress)) { tl_debug(NLIB(team), "NCCL communicator creation failed"); team->state = NCCL_COMM_ERROR; return UCC_ERR_NOT_SUPPORTED; }
+        if (ar == ncclSuccess) { team->state = NCCL_COMM_READY; return UCC_OK; }
+    } while (wait);
+    return UCC_INPROGRESS;
 }
 static ucc_status_t nccl_team_create_post(ucc_base_context_t *b_ctx, const ucc_base_team_params_t *params, ucc_base_team_t **team_p)
 {
@@ -130,10 +157,12 @@ static ucc_status_t nccl_team_create_post(ucc_base_context_t *b_ctx, const ucc_b
     team->super.super.context = b_ctx; team->super.super.params = *params;
     if (params->params.mask & UCC_TEAM_PARAM_FIELD_OOB) team->oob = params->params.oob;
     else { ucc_subset_t s; s.map = params->map; s.myrank = params->rank; if (ucc_internal_oob_init(params->team, s, &team->oob) != UCC_OK) { free(team); return UCC_ERR_NOT_SUPPORTED; } team->oob_internal = 1; }
-    team->ids = (ncclUniqueId *)calloc(params->size, sizeof(ncclUniqueId));
+    team->ids = (nccl_member_info_t *)calloc(params->size, sizeof(nccl_member_info_t));
     memset(&team->my_id, 0, sizeof(team->my_id));
-    if (params->rank == 0 && nc.GetUniqueId(&team->my_id) != ncclSuccess) { free(team->ids); free(team); return UCC_ERR_NO_MESSAGE; }
-    st = team->oob.allgather(&team->my_id, team->ids, sizeof(ncclUniqueId), team->oob.coll_info, &team->oob_req);
+    if (params->rank == 0 && nc.GetUniqueId(&team->my_id.id) != ncclSuccess) { free(team->ids); free(team); return UCC_ERR_NO_MESSAGE; }
+    team->my_id.host_hash = ucc_local_proc.host_hash; team->my_id.pid = (int32_t)ucc_local_proc.pid; team->my_id.dev = ucc_derived_of(b_ctx, ucc_tl_nccl_context_t)->dev;
+    if (cudaDeviceGetPCIBusId(team->my_id.busid, (int)sizeof(team->my_id.busid), team->my_id.dev) != cudaSuccess) { (void)cudaGetLastError(); snprintf(team->my_id.busid, sizeof(team->my_id.busid), "dev%d", team->my_id.dev); }
+    st = team->oob.allgather(&team->my_id, team->ids, sizeof(nccl_member_info_t), team->oob.coll_info, &team->oob_req);
     if (st != UCC_OK) { free(team->ids); free(team); return st; }
     *team_p = &team->super.super;
     return UCC_OK;
@@ -141,14 +170,35 @@ static ucc_status_t nccl_team_create_post(ucc_base_context_t *b_ctx, const ucc_b
 static ucc_status_t nccl_team_create_test(ucc_base_team_t *b)
 {
     ucc_tl_nccl_team_t *team = ucc_derived_of(b, ucc_tl_nccl_team_t);
+    ucc_rank_t size = UCC_TL_TEAM_SIZE(team), i, j;
     ucc_status_t st;
-    if (!team->oob_req) return UCC_OK;
-    st = team->oob.req_test(team->oob_req);
-    if (st == UCC_INPROGRESS) return st;
-    team->oob.req_free(team->oob_req); team->oob_req = NULL;
-    if (st < 0) { free(team->ids); free(team); return st; }
-    if (!NCCL_CTX(team)->cfg.lazy_init) { st = nccl_comm_init(team); if (st != UCC_OK) { free(team->ids); free(team); return st; } }
+    if (team->oob_req) {
+        st = team->oob.req_test(team->oob_req);
+        if (st == UCC_INPROGRESS) return st;
+        team->oob.req_free(team->oob_req); team->oob_req = NULL;
+        if (st < 0) goto fail;
+        /* decisions every member derives from the same gathered table */
+        for (i = 0; i < size; i++) for (j = i + 1; j < size; j++) {
+            if (team->ids[i].host_hash != team->ids[j].host_hash) continue;
+            if (!strncmp(team->ids[i].busid, team->ids[j].busid, sizeof(team->ids[i].busid))) {
+                tl_debug(NLIB(team), "members %u and %u share GPU %s: NCCL cannot serve this team", (unsigned)i, (unsigned)j, team->ids[i].busid);
+                st = UCC_ERR_NOT_SUPPORTED; goto fail;
+            }
+            if (team->ids[i].pid == team->ids[j].pid) team->inproc_peers = 1;
+        }
+    }
+    if (!NCCL_CTX(team)->cfg.lazy_init || team->inproc_peers) {
+        st = nccl_comm_init(team, 0);
+        if (st == UCC_INPROGRESS) return st;
+        if (st != UCC_OK) goto fail;
+    }
     return UCC_OK;
+fail:
+    if (team->comm && nc.CommAbort) nc.CommAbort(team->comm);
+    if (team->stream) cudaStreamDestroy(team->stream);
+    if (team->oob_internal) ucc_internal_oob_finalize(&team->oob);
+    free(team->ids); free(team);
+    return st;
 }
 static ucc_status_t nccl_team_destroy(ucc_base_team_t *b)
 {
@@ -332,7 +382,7 @@ static ucc_status_t nccl_coll_init_alg(ucc_base_coll_args_t *b, ucc_base_team_t 
     }
     if ((a->coll_type & (UCC_COLL_TYPE_ALLTOALL | UCC_COLL_TYPE_ALLTOALLV)) && UCC_IS_INPLACE(*a)) return UCC_ERR_NOT_SUPPORTED;
     if (UCC_COLL_ARGS_ACTIVE_SET(a) && a->coll_type != UCC_COLL_TYPE_BCAST) return UCC_ERR_NOT_SUPPORTED;
-    st = nccl_comm_init(team); /* lazy */
+    st = nccl_comm_init(team, 1); /* lazy */
     if (st != UCC_OK) return st;
     t = (ucc_tl_nccl_task_t *)ucc_mpool_get(&ctx->task_mp); if (!t) return UCC_ERR_NO_MEMORY;
     ucc_coll_task_init(&t->super, b, b_team);

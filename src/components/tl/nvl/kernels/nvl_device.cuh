@@ -180,6 +180,19 @@ template <typename A> struct OpFn<NVL_OP_BAND, A> { static NVL_DEV A f(A a, A b)
 template <typename A> struct OpFn<NVL_OP_BOR, A> { static NVL_DEV A f(A a, A b) { return (A)(a | b); } };
 template <typename A> struct OpFn<NVL_OP_BXOR, A> { static NVL_DEV A f(A a, A b) { return (A)(a ^ b); } };
 
+/* AVG = SUM scaled by 1/N at the very end.  Floating types multiply by 1/N; integer types divide by N (truncating, i.e. what
+ * the reference's d[i] * (1/N) in double precision yields for every sum a double represents exactly) - casting 1/N to an integer
+ * accumulator would be 0 */
+template <typename A> struct IsIntAcc { static constexpr bool v = true; };
+template <> struct IsIntAcc<float> { static constexpr bool v = false; };
+template <> struct IsIntAcc<double> { static constexpr bool v = false; };
+template <int OP, typename A> NVL_DEV A avg_scale(A x, float inv_n, int n)
+{
+    if (OP != NVL_OP_AVG) return x;
+    if constexpr (IsIntAcc<A>::v) return n > 1 ? (A)(x / (A)n) : x;
+    else return (A)(x * (A)inv_n);
+}
+
 /* accumulator for one 16-byte vector of T */
 template <typename T, int OP> struct VecAcc {
     typedef typename AccOf<T>::type A;
@@ -191,9 +204,9 @@ template <typename T, int OP> struct VecAcc {
     NVL_DEV void add(uint4 x) { Vec<T> u; u.v = x;
 #pragma unroll
         for (int i = 0; i < E; i++) a[i] = OpFn<OP, A>::f(a[i], to_acc<T>(u.e[i])); }
-    NVL_DEV uint4 get(float inv_n) { Vec<T> u;
+    NVL_DEV uint4 get(float inv_n, int n) { Vec<T> u;
 #pragma unroll
-        for (int i = 0; i < E; i++) { A x = a[i]; if (OP == NVL_OP_AVG) x = (A)(x * (A)inv_n); u.e[i] = from_acc<T>(x); }
+        for (int i = 0; i < E; i++) u.e[i] = from_acc<T>(avg_scale<OP, A>(a[i], inv_n, n));
         return u.v; }
 };
 

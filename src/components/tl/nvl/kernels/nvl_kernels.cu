@@ -15,6 +15,8 @@
  */
 #include "nvl_reduce_impl.cuh"
 
+static_assert(sizeof(nvl_ctrl_t) <= NVL_CTRL_SIZE, "control block outgrew its heap region");
+
 __global__ void nvl_ctrl_init_kernel(nvl_ctrl_t *c)
 {
     uint32_t *w = reinterpret_cast<uint32_t *>(c);

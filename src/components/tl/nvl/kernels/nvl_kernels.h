@@ -15,6 +15,10 @@
 #define NVL_MAX_PEERS  16
 #define NVL_MAX_BLOCKS 320
 #define NVL_LL_MAX     (1024 * 1024)         /* bytes per rank in the one-shot (latency) region */
+#define NVL_P2P_MAX_CTAS 16                  /* lanes of a point-to-point channel */
+#define NVL_P2P_SLOTS    4                   /* chunks in flight per channel */
+#define NVL_P2P_CHUNK    (256 * 1024)
+#define NVL_P2P_CHAN_BYTES (NVL_P2P_SLOTS * NVL_P2P_CHUNK)
 
 /* control block at offset 0 of every rank's heap */
 typedef struct nvl_ctrl {
@@ -28,12 +32,19 @@ typedef struct nvl_ctrl {
     uint32_t pad[31];
     uint64_t mc_arrive[NVL_MAX_BLOCKS];               /* NVLS barrier counters (incremented through the multicast mapping) */
     uint64_t mc_epoch[NVL_MAX_BLOCKS];
+    /* point-to-point channels (kernels/nvl_p2p.cu), [peer][lane]; all counters count chunks and only ever grow */
+    uint32_t p2p_head[NVL_MAX_PEERS][NVL_P2P_MAX_CTAS]; /* in the RECEIVER's heap: chunks peer has delivered into my ring (written by peer) */
+    uint32_t p2p_ack[NVL_MAX_PEERS][NVL_P2P_MAX_CTAS];  /* in the SENDER's heap: chunks peer has drained from its ring (written by peer) */
+    uint32_t p2p_tx[NVL_MAX_PEERS][NVL_P2P_MAX_CTAS];   /* local: chunks I produced for peer so far */
+    uint32_t p2p_rx[NVL_MAX_PEERS][NVL_P2P_MAX_CTAS];   /* local: chunks I consumed from peer so far */
 } nvl_ctrl_t;
 
 #define NVL_CTRL_SIZE  (128 * 1024)
 #define NVL_LL_OFFSET  NVL_CTRL_SIZE
 #define NVL_LL_SIZE    (2 * NVL_MAX_PEERS * NVL_LL_MAX)
-#define NVL_DATA_OFFSET (NVL_LL_OFFSET + NVL_LL_SIZE)
+#define NVL_P2P_OFFSET (NVL_LL_OFFSET + NVL_LL_SIZE)       /* per source rank one channel ring */
+#define NVL_P2P_SIZE   (NVL_MAX_PEERS * NVL_P2P_CHAN_BYTES)
+#define NVL_DATA_OFFSET (NVL_P2P_OFFSET + NVL_P2P_SIZE)
 
 typedef struct nvl_team_dev {
     int      rank, size;
@@ -79,6 +90,15 @@ typedef struct nvl_red_args {
     nvl_direct_t   d;
 } nvl_red_args_t;
 
+/* the zero-copy reduction kernel wants the pointer tables relative to the caller: entry i = my i-th right neighbour (i = 0: me) */
+static inline void nvl_direct_rotate(nvl_red_args_t *a)
+{
+    nvl_direct_t r;
+    int i, n = a->team.size, me = a->team.rank;
+    for (i = 0; i < NVL_MAX_PEERS; i++) { r.src[i] = i < n ? a->d.src[(me + i) % n] : 0; r.dst[i] = i < n ? a->d.dst[(me + i) % n] : 0; }
+    a->d = r;
+}
+
 /* generic staged exchange: allgather(v), alltoall(v), bcast, gather, scatter */
 #define NVL_XCHG_TABLE_BYTES 256 /* published offset table in front of the staged payload */
 #define NVL_XCHG_LOOKUP ((size_t)-1)
@@ -113,9 +133,20 @@ typedef struct nvl_push_args {
     size_t         recv_off[NVL_MAX_PEERS];
 } nvl_push_args_t;
 
+/* two-member active-set broadcast = send / recv (kernels/nvl_p2p.cu) */
+typedef struct nvl_p2p_args {
+    nvl_team_dev_t team;
+    void          *buf;
+    size_t         bytes;
+    int            peer;   /* team rank of the other side */
+    int            send;   /* 1: I am the root (sender), 0: receiver */
+} nvl_p2p_args_t;
+
 #ifdef __cplusplus
 extern "C" {
 #endif
+int          nvl_p2p_lanes(size_t bytes);
+cudaError_t  nvl_launch_p2p(const nvl_p2p_args_t *a, int nthreads, cudaStream_t s);
 size_t       nvl_dt_size(int dt);
 int          nvl_dt_supports_op(int dt, int op);
 int          nvl_nvls_supports(int dt, int op);

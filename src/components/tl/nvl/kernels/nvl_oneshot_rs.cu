@@ -54,20 +54,19 @@ static __device__ __forceinline__ void oneshot_rs_body(const nvl_red_args_t &a, 
             VecAcc<T, OP> acc; acc.set(x[0]);
 #pragma unroll
             for (int i = 1; i < NVL_MAX_PEERS; i++) if (i < N) acc.add(x[i]);
-            store_dst_vec<T>(dst, v * E, cnt, dal, acc.get(inv_n));
+            store_dst_vec<T>(dst, v * E, cnt, dal, acc.get(inv_n, N));
         }
     }
 }
 
-template <typename T> __global__ void __launch_bounds__(NVL_THREADS_MAX) nvl_reduce_scatter_oneshot_kernel(nvl_red_args_t a)
+template <typename T, int OP> __global__ void __launch_bounds__(NVL_THREADS_MAX) nvl_reduce_scatter_oneshot_kernel_t(const __grid_constant__ nvl_red_args_t a)
 {
     nvl_ctrl_t *mine = reinterpret_cast<nvl_ctrl_t *>(a.team.heap[a.team.rank]);
-    uint32_t seq = ld_volatile_u32(&mine->ll_seq[blockIdx.x]) + 1;
-#define CALL_ONESHOT_RS(_T, _OP) oneshot_rs_body<_T, _OP>(a, mine, seq)
-    NVL_DISPATCH_OP(T, a.op, CALL_ONESHOT_RS);
-    __syncthreads();
-    if (threadIdx.x == 0) mine->ll_seq[blockIdx.x] = seq;
+    const uint32_t seq = ll_seq_begin(mine);   /* team-wide sequence shared with the one-shot allreduce */
+    oneshot_rs_body<T, OP>(a, mine, seq);
+    ll_seq_end(mine, seq);
 }
+NVL_DEFINE_ENTRY(nvl_reduce_scatter_oneshot_kernel, nvl_red_args_t)
 
 #ifndef NVL_HOST_EMU /* the host emulation calls the kernels directly */
 extern "C" cudaError_t nvl_launch_reduce_scatter_oneshot(const nvl_red_args_t *a, int nblocks, int nthreads, cudaStream_t s)
@@ -75,18 +74,18 @@ extern "C" cudaError_t nvl_launch_reduce_scatter_oneshot(const nvl_red_args_t *a
     if (nthreads > NVL_THREADS_MAX) nthreads = NVL_THREADS_MAX;
     if (a->kind != NVL_RED_REDUCE_SCATTER) return cudaErrorInvalidValue;
     switch (a->dt) {
-    case NVL_DT_I8: nvl_reduce_scatter_oneshot_kernel<int8_t><<<nblocks, nthreads, 0, s>>>(*a); break;
-    case NVL_DT_I16: nvl_reduce_scatter_oneshot_kernel<int16_t><<<nblocks, nthreads, 0, s>>>(*a); break;
-    case NVL_DT_I32: nvl_reduce_scatter_oneshot_kernel<int32_t><<<nblocks, nthreads, 0, s>>>(*a); break;
-    case NVL_DT_I64: nvl_reduce_scatter_oneshot_kernel<int64_t><<<nblocks, nthreads, 0, s>>>(*a); break;
-    case NVL_DT_U8: nvl_reduce_scatter_oneshot_kernel<uint8_t><<<nblocks, nthreads, 0, s>>>(*a); break;
-    case NVL_DT_U16: nvl_reduce_scatter_oneshot_kernel<uint16_t><<<nblocks, nthreads, 0, s>>>(*a); break;
-    case NVL_DT_U32: nvl_reduce_scatter_oneshot_kernel<uint32_t><<<nblocks, nthreads, 0, s>>>(*a); break;
-    case NVL_DT_U64: nvl_reduce_scatter_oneshot_kernel<uint64_t><<<nblocks, nthreads, 0, s>>>(*a); break;
-    case NVL_DT_F16: nvl_reduce_scatter_oneshot_kernel<__half><<<nblocks, nthreads, 0, s>>>(*a); break;
-    case NVL_DT_F32: nvl_reduce_scatter_oneshot_kernel<float><<<nblocks, nthreads, 0, s>>>(*a); break;
-    case NVL_DT_F64: nvl_reduce_scatter_oneshot_kernel<double><<<nblocks, nthreads, 0, s>>>(*a); break;
-    case NVL_DT_BF16: nvl_reduce_scatter_oneshot_kernel<__nv_bfloat16><<<nblocks, nthreads, 0, s>>>(*a); break;
+    case NVL_DT_I8: return nvl_reduce_scatter_oneshot_kernel_launch<int8_t>(a, nblocks, nthreads, s);
+    case NVL_DT_I16: return nvl_reduce_scatter_oneshot_kernel_launch<int16_t>(a, nblocks, nthreads, s);
+    case NVL_DT_I32: return nvl_reduce_scatter_oneshot_kernel_launch<int32_t>(a, nblocks, nthreads, s);
+    case NVL_DT_I64: return nvl_reduce_scatter_oneshot_kernel_launch<int64_t>(a, nblocks, nthreads, s);
+    case NVL_DT_U8: return nvl_reduce_scatter_oneshot_kernel_launch<uint8_t>(a, nblocks, nthreads, s);
+    case NVL_DT_U16: return nvl_reduce_scatter_oneshot_kernel_launch<uint16_t>(a, nblocks, nthreads, s);
+    case NVL_DT_U32: return nvl_reduce_scatter_oneshot_kernel_launch<uint32_t>(a, nblocks, nthreads, s);
+    case NVL_DT_U64: return nvl_reduce_scatter_oneshot_kernel_launch<uint64_t>(a, nblocks, nthreads, s);
+    case NVL_DT_F16: return nvl_reduce_scatter_oneshot_kernel_launch<__half>(a, nblocks, nthreads, s);
+    case NVL_DT_F32: return nvl_reduce_scatter_oneshot_kernel_launch<float>(a, nblocks, nthreads, s);
+    case NVL_DT_F64: return nvl_reduce_scatter_oneshot_kernel_launch<double>(a, nblocks, nthreads, s);
+    case NVL_DT_BF16: return nvl_reduce_scatter_oneshot_kernel_launch<__nv_bfloat16>(a, nblocks, nthreads, s);
     default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

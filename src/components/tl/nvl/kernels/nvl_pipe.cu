@@ -71,9 +71,9 @@ template <typename T> static __device__ __forceinline__ void pipe_stage(const nv
     char *buf = data_of(a.team, a.team.rank) + (size_t)(k % 3) * g.buf_bytes;
     size_t e0, j0, j1; chunk_range<T>(pl, g, k, e0, j0, j1);
     for (int s = 0; s < N; s++) {
-        const size_t rc = pl.cnt[s] > e0 ? dmin(g.cap_e, pl.cnt[s] - e0) : 0;
+        const size_t rc = slice_cnt(a, pl, s) > e0 ? dmin(g.cap_e, slice_cnt(a, pl, s) - e0) : 0;
         const size_t nfull = rc / E, jend = dmin(j1, (rc + E - 1) / E);
-        const T *sb = src + pl.off[s] + e0;
+        const T *sb = src + slice_off(a, pl, s) + e0;
         char *hb = buf + (size_t)s * g.cap_bytes;
         if (((uintptr_t)sb & 15) == 0) {
             role_copy_vecs<4, false>(hb, reinterpret_cast<const char *>(sb), j0, dmin(jend, nfull), rtid, rnt);
@@ -91,7 +91,7 @@ template <typename T, int OP> static __device__ __forceinline__ void pipe_reduce
     const int me = a.team.rank;
     const float inv_n = 1.0f / (float)a.team.size;
     size_t e0, j0, j1; chunk_range<T>(pl, g, k, e0, j0, j1);
-    const size_t rc = pl.cnt[me] > e0 ? dmin(g.cap_e, pl.cnt[me] - e0) : 0;
+    const size_t rc = slice_cnt(a, pl, me) > e0 ? dmin(g.cap_e, slice_cnt(a, pl, me) - e0) : 0;
     const size_t jend = dmin(j1, (rc + E - 1) / E);
     char *mc = a.team.mc_heap + NVL_DATA_OFFSET + (size_t)(k % 3) * g.buf_bytes + (size_t)me * g.cap_bytes;
     size_t j = j0 + rtid;
@@ -103,13 +103,13 @@ template <typename T, int OP> static __device__ __forceinline__ void pipe_reduce
 #pragma unroll
         for (int u = 0; u < U; u++) {
             uint4 v = r[u];
-            if (OP == NVL_OP_AVG) { VecAcc<T, OP> acc; acc.set(v); v = acc.get(inv_n); }
+            if (OP == NVL_OP_AVG) { VecAcc<T, OP> acc; acc.set(v); v = acc.get(inv_n, a.team.size); }
             mc_st_v4(mc + (j + (size_t)u * rnt) * 16, v); /* the padding lanes of a ragged last vector are reduced and stored too: they stay inside the slot */
         }
     }
     for (; j < jend; j += rnt) {
         uint4 v = McRed<T, OP>::ld(mc + j * 16);
-        if (OP == NVL_OP_AVG) { VecAcc<T, OP> acc; acc.set(v); v = acc.get(inv_n); }
+        if (OP == NVL_OP_AVG) { VecAcc<T, OP> acc; acc.set(v); v = acc.get(inv_n, a.team.size); }
         mc_st_v4(mc + j * 16, v);
     }
 }
@@ -122,9 +122,9 @@ template <typename T> static __device__ __forceinline__ void pipe_copy_out(const
     const char *buf = data_of(a.team, a.team.rank) + (size_t)(k % 3) * g.buf_bytes;
     size_t e0, j0, j1; chunk_range<T>(pl, g, k, e0, j0, j1);
     for (int s = 0; s < N; s++) {
-        const size_t rc = pl.cnt[s] > e0 ? dmin(g.cap_e, pl.cnt[s] - e0) : 0;
+        const size_t rc = slice_cnt(a, pl, s) > e0 ? dmin(g.cap_e, slice_cnt(a, pl, s) - e0) : 0;
         const size_t nfull = rc / E, jend = dmin(j1, (rc + E - 1) / E);
-        T *db = dst + pl.off[s] + e0;
+        T *db = dst + slice_off(a, pl, s) + e0;
         const char *hb = buf + (size_t)s * g.cap_bytes;
         if (((uintptr_t)db & 15) == 0) {
             role_copy_vecs<4, true>(reinterpret_cast<char *>(db), hb, j0, dmin(jend, nfull), rtid, rnt);
@@ -152,15 +152,15 @@ static __device__ __forceinline__ void pipe_body(const nvl_red_args_t &a, BlockS
     }
 }
 
-template <typename T> __global__ void __launch_bounds__(NVL_THREADS_MAX, 2) nvl_allreduce_nvls_pipe_kernel(nvl_red_args_t a)
+template <typename T, int OP> __global__ void __launch_bounds__(NVL_THREADS_MAX, 2) nvl_allreduce_nvls_pipe_kernel_t(const __grid_constant__ nvl_red_args_t a)
 {
     BlockSync bs; bs.init(a.team);
     SlicePlan pl; make_plan<T>(a, pl);
     PipeGeom g; pipe_geom<T>(a, pl, g);
-#define CALL_PIPE(_T, _OP) pipe_body<_T, _OP>(a, bs, pl, g)
-    NVL_DISPATCH_OP(T, a.op, CALL_PIPE);
+    pipe_body<T, OP>(a, bs, pl, g);
     bs.finish((uint32_t)g.chunks + 1);
 }
+NVL_DEFINE_ENTRY(nvl_allreduce_nvls_pipe_kernel, nvl_red_args_t)
 
 #ifndef NVL_HOST_EMU /* the host emulation calls the kernels directly */
 extern "C" cudaError_t nvl_launch_reduce_pipe(const nvl_red_args_t *a, int nblocks, int nthreads, cudaStream_t s)
@@ -169,13 +169,13 @@ extern "C" cudaError_t nvl_launch_reduce_pipe(const nvl_red_args_t *a, int nbloc
     if (nthreads < 128 || (nthreads & 127)) return cudaErrorInvalidValue; /* three roles need at least four warps */
     if (a->kind != NVL_RED_ALLREDUCE || !a->use_nvls || !a->team.mc_heap || !nvl_nvls_supports(a->dt, a->op)) return cudaErrorInvalidValue;
     switch (a->dt) {
-    case NVL_DT_F32: nvl_allreduce_nvls_pipe_kernel<float><<<nblocks, nthreads, 0, s>>>(*a); break;
-    case NVL_DT_F16: nvl_allreduce_nvls_pipe_kernel<__half><<<nblocks, nthreads, 0, s>>>(*a); break;
-    case NVL_DT_BF16: nvl_allreduce_nvls_pipe_kernel<__nv_bfloat16><<<nblocks, nthreads, 0, s>>>(*a); break;
-    case NVL_DT_I32: nvl_allreduce_nvls_pipe_kernel<int32_t><<<nblocks, nthreads, 0, s>>>(*a); break;
-    case NVL_DT_U32: nvl_allreduce_nvls_pipe_kernel<uint32_t><<<nblocks, nthreads, 0, s>>>(*a); break;
-    case NVL_DT_I64: nvl_allreduce_nvls_pipe_kernel<int64_t><<<nblocks, nthreads, 0, s>>>(*a); break;
-    case NVL_DT_U64: nvl_allreduce_nvls_pipe_kernel<uint64_t><<<nblocks, nthreads, 0, s>>>(*a); break;
+    case NVL_DT_F32: return nvl_allreduce_nvls_pipe_kernel_launch<float>(a, nblocks, nthreads, s);
+    case NVL_DT_F16: return nvl_allreduce_nvls_pipe_kernel_launch<__half>(a, nblocks, nthreads, s);
+    case NVL_DT_BF16: return nvl_allreduce_nvls_pipe_kernel_launch<__nv_bfloat16>(a, nblocks, nthreads, s);
+    case NVL_DT_I32: return nvl_allreduce_nvls_pipe_kernel_launch<int32_t>(a, nblocks, nthreads, s);
+    case NVL_DT_U32: return nvl_allreduce_nvls_pipe_kernel_launch<uint32_t>(a, nblocks, nthreads, s);
+    case NVL_DT_I64: return nvl_allreduce_nvls_pipe_kernel_launch<int64_t>(a, nblocks, nthreads, s);
+    case NVL_DT_U64: return nvl_allreduce_nvls_pipe_kernel_launch<uint64_t>(a, nblocks, nthreads, s);
     default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

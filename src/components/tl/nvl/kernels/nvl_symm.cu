@@ -29,9 +29,9 @@ static __device__ __forceinline__ void symm_body(const nvl_red_args_t &a, BlockS
 
     bs.barrier(t, 1);
     if (rs) {
-        const size_t cnt = pl.cnt[me], nv = (cnt + E - 1) / E;
+        const size_t cnt = slice_cnt(a, pl, me), nv = (cnt + E - 1) / E;
         const size_t per = (nv + gridDim.x - 1) / gridDim.x, j0 = dmin((size_t)blockIdx.x * per, nv), j1 = dmin(j0 + per, nv);
-        const char *mcs = t.mc_heap + so + pl.off[me] * sizeof(T);
+        const char *mcs = t.mc_heap + so + slice_off(a, pl, me) * sizeof(T);
         T *db = static_cast<T *>(a.dst);
         const bool dal = ((uintptr_t)db & 15) == 0;
         size_t j = j0 + threadIdx.x;
@@ -42,21 +42,21 @@ static __device__ __forceinline__ void symm_body(const nvl_red_args_t &a, BlockS
 #pragma unroll
             for (int u = 0; u < U; u++) {
                 uint4 v = r[u];
-                if (OP == NVL_OP_AVG) { VecAcc<T, OP> acc; acc.set(v); v = acc.get(inv_n); }
+                if (OP == NVL_OP_AVG) { VecAcc<T, OP> acc; acc.set(v); v = acc.get(inv_n, N); }
                 store_dst_vec<T>(db, (j + (size_t)u * nt) * E, cnt, dal, v);   /* bounds-checked: the ragged last vector is cut at cnt */
             }
         }
         for (; j < j1; j += nt) {
             uint4 v = McRed<T, OP>::ld(mcs + j * 16);
-            if (OP == NVL_OP_AVG) { VecAcc<T, OP> acc; acc.set(v); v = acc.get(inv_n); }
+            if (OP == NVL_OP_AVG) { VecAcc<T, OP> acc; acc.set(v); v = acc.get(inv_n, N); }
             store_dst_vec<T>(db, j * E, cnt, dal, v);
         }
     } else {
-        const size_t cnt = pl.cnt[me], nfull = cnt / E, nv = (cnt + E - 1) / E;
+        const size_t cnt = slice_cnt(a, pl, me), nfull = cnt / E, nv = (cnt + E - 1) / E;
         const size_t per = (nv + gridDim.x - 1) / gridDim.x, j0 = dmin((size_t)blockIdx.x * per, nv), j1 = dmin(j0 + per, nv);
         const size_t jfull = dmin(j1, nfull);                               /* whole vectors of my range */
-        const char *mcs = t.mc_heap + so + pl.off[me] * sizeof(T);
-        char *mcd = t.mc_heap + dof + pl.off[me] * sizeof(T);
+        const char *mcs = t.mc_heap + so + slice_off(a, pl, me) * sizeof(T);
+        char *mcd = t.mc_heap + dof + slice_off(a, pl, me) * sizeof(T);
         size_t j = j0 + threadIdx.x;
         for (; j + (size_t)(U - 1) * nt < jfull; j += (size_t)U * nt) {
             uint4 r[U];
@@ -65,13 +65,13 @@ static __device__ __forceinline__ void symm_body(const nvl_red_args_t &a, BlockS
 #pragma unroll
             for (int u = 0; u < U; u++) {
                 uint4 v = r[u];
-                if (OP == NVL_OP_AVG) { VecAcc<T, OP> acc; acc.set(v); v = acc.get(inv_n); }
+                if (OP == NVL_OP_AVG) { VecAcc<T, OP> acc; acc.set(v); v = acc.get(inv_n, N); }
                 mc_st_v4(mcd + (j + (size_t)u * nt) * 16, v);
             }
         }
         for (; j < jfull; j += nt) {
             uint4 v = McRed<T, OP>::ld(mcs + j * 16);
-            if (OP == NVL_OP_AVG) { VecAcc<T, OP> acc; acc.set(v); v = acc.get(inv_n); }
+            if (OP == NVL_OP_AVG) { VecAcc<T, OP> acc; acc.set(v); v = acc.get(inv_n, N); }
             mc_st_v4(mcd + j * 16, v);
         }
         /* ragged end of the vector (only the last non-empty slice can have one): the 16-byte load stays inside the 256-byte
@@ -79,22 +79,22 @@ static __device__ __forceinline__ void symm_body(const nvl_red_args_t &a, BlockS
          * member's unicast mapping instead */
         if (nfull < nv && nfull >= j0 && nfull < j1 && threadIdx.x == 0) {
             uint4 v = McRed<T, OP>::ld(mcs + nfull * 16);
-            if (OP == NVL_OP_AVG) { VecAcc<T, OP> acc; acc.set(v); v = acc.get(inv_n); }
+            if (OP == NVL_OP_AVG) { VecAcc<T, OP> acc; acc.set(v); v = acc.get(inv_n, N); }
             for (int p = 0; p < N; p++)
-                store_dst_vec<T>(reinterpret_cast<T *>(t.heap[p] + dof) + pl.off[me], nfull * E, cnt, false, v);
+                store_dst_vec<T>(reinterpret_cast<T *>(t.heap[p] + dof) + slice_off(a, pl, me), nfull * E, cnt, false, v);
         }
     }
     bs.barrier(t, 2);
 }
 
-template <typename T> __global__ void __launch_bounds__(NVL_THREADS_MAX, 2) nvl_allreduce_symm_kernel(nvl_red_args_t a)
+template <typename T, int OP> __global__ void __launch_bounds__(NVL_THREADS_MAX, 2) nvl_allreduce_symm_kernel_t(const __grid_constant__ nvl_red_args_t a)
 {
     BlockSync bs; bs.init(a.team);
     SlicePlan pl; make_plan<T>(a, pl);
-#define CALL_SYMM(_T, _OP) symm_body<_T, _OP>(a, bs, pl)
-    NVL_DISPATCH_OP(T, a.op, CALL_SYMM);
+    symm_body<T, OP>(a, bs, pl);
     bs.finish(2);
 }
+NVL_DEFINE_ENTRY(nvl_allreduce_symm_kernel, nvl_red_args_t)
 
 #ifndef NVL_HOST_EMU /* the host emulation calls the kernels directly */
 extern "C" cudaError_t nvl_launch_reduce_symm(const nvl_red_args_t *a, int nblocks, int nthreads, cudaStream_t s)
@@ -103,13 +103,13 @@ extern "C" cudaError_t nvl_launch_reduce_symm(const nvl_red_args_t *a, int nbloc
     if ((a->kind != NVL_RED_ALLREDUCE && a->kind != NVL_RED_REDUCE_SCATTER) || !a->team.mc_heap || !nvl_nvls_supports(a->dt, a->op) || !a->d.src[0]) return cudaErrorInvalidValue;
     if (a->kind == NVL_RED_ALLREDUCE && !a->d.dst[0]) return cudaErrorInvalidValue;
     switch (a->dt) {
-    case NVL_DT_F32: nvl_allreduce_symm_kernel<float><<<nblocks, nthreads, 0, s>>>(*a); break;
-    case NVL_DT_F16: nvl_allreduce_symm_kernel<__half><<<nblocks, nthreads, 0, s>>>(*a); break;
-    case NVL_DT_BF16: nvl_allreduce_symm_kernel<__nv_bfloat16><<<nblocks, nthreads, 0, s>>>(*a); break;
-    case NVL_DT_I32: nvl_allreduce_symm_kernel<int32_t><<<nblocks, nthreads, 0, s>>>(*a); break;
-    case NVL_DT_U32: nvl_allreduce_symm_kernel<uint32_t><<<nblocks, nthreads, 0, s>>>(*a); break;
-    case NVL_DT_I64: nvl_allreduce_symm_kernel<int64_t><<<nblocks, nthreads, 0, s>>>(*a); break;
-    case NVL_DT_U64: nvl_allreduce_symm_kernel<uint64_t><<<nblocks, nthreads, 0, s>>>(*a); break;
+    case NVL_DT_F32: return nvl_allreduce_symm_kernel_launch<float>(a, nblocks, nthreads, s);
+    case NVL_DT_F16: return nvl_allreduce_symm_kernel_launch<__half>(a, nblocks, nthreads, s);
+    case NVL_DT_BF16: return nvl_allreduce_symm_kernel_launch<__nv_bfloat16>(a, nblocks, nthreads, s);
+    case NVL_DT_I32: return nvl_allreduce_symm_kernel_launch<int32_t>(a, nblocks, nthreads, s);
+    case NVL_DT_U32: return nvl_allreduce_symm_kernel_launch<uint32_t>(a, nblocks, nthreads, s);
+    case NVL_DT_I64: return nvl_allreduce_symm_kernel_launch<int64_t>(a, nblocks, nthreads, s);
+    case NVL_DT_U64: return nvl_allreduce_symm_kernel_launch<uint64_t>(a, nblocks, nthreads, s);
     default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
@@ -125,7 +125,7 @@ extern "C" cudaError_t nvl_launch_reduce_symm(const nvl_red_args_t *a, int nbloc
 /*   a.dst = LOCAL address of the gathered buffer inside my heap       */
 /*   a.push_off = byte offset of my block inside it (multiple of 16)   */
 /* ------------------------------------------------------------------ */
-__global__ void __launch_bounds__(NVL_THREADS_MAX, 2) nvl_allgather_symm_kernel(nvl_xchg_args_t a)
+__global__ void __launch_bounds__(NVL_THREADS_MAX, 2) nvl_allgather_symm_kernel(const __grid_constant__ nvl_xchg_args_t a)
 {
     const nvl_team_dev_t &t = a.team;
     const int N = t.size, me = t.rank;

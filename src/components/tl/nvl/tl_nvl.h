@@ -137,13 +137,14 @@ typedef enum { NVL_TASK_REDUCE_ONESHOT, NVL_TASK_REDUCE_STAGED, NVL_TASK_REDUCE_
                NVL_TASK_SELF_COPY /* team of one: u.xchg.{dst,src,src_bytes} describe the only data movement */,
                NVL_TASK_REDUCE_PIPE /* pipelined staged NVLS allreduce (kernels/nvl_pipe.cu) */,
                NVL_TASK_REDUCE_SYMM /* in-place NVLS allreduce on symmetric user memory (kernels/nvl_symm.cu) */,
-               NVL_TASK_AG_SYMM /* allgather into a symmetric destination by multimem.st (u.xchg: src, src_bytes, dst, push_off) */ } nvl_task_kind_t;
+               NVL_TASK_AG_SYMM /* allgather into a symmetric destination by multimem.st (u.xchg: src, src_bytes, dst, push_off) */,
+               NVL_TASK_P2P /* two-member active-set bcast = send / recv over a heap channel (kernels/nvl_p2p.cu, u.p2p) */ } nvl_task_kind_t;
 typedef enum { NVL_TASK_LAUNCHED, NVL_TASK_QUEUED } nvl_task_state_t;
 typedef struct ucc_tl_nvl_task {
     ucc_coll_task_t     super;
     ucc_tl_nvl_team_t  *team;
     nvl_task_kind_t     kind;
-    union { nvl_red_args_t red; nvl_xchg_args_t xchg; } u;
+    union { nvl_red_args_t red; nvl_xchg_args_t xchg; nvl_p2p_args_t p2p; } u;
     int                 nblocks, nthreads;
     cudaEvent_t         event;
     cudaStream_t        stream;     /* stream of the current post */

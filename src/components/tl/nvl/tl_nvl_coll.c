@@ -34,9 +34,34 @@ static inline int is_cuda(ucc_memory_type_t mt) { return mt == UCC_MEMORY_TYPE_C
 /* ------------------------------------------------------------------ */
 /* task life cycle                                                     */
 /* ------------------------------------------------------------------ */
+/* what the most recent launch of this process was (benchmarks print it next to their numbers): "<kernel> grid x block" */
+static char nvl_last_launch[128];
+UCC_EXPORT const char *ucc_tl_nvl_last_launch_info(void) { return nvl_last_launch; }
+static void note_launch(const ucc_tl_nvl_task_t *t)
+{
+    const char *k = "barrier"; int nb = t->nblocks;
+    switch (t->kind) {
+    case NVL_TASK_REDUCE_ONESHOT: k = t->u.red.kind == NVL_RED_REDUCE_SCATTER ? "oneshot_rs" : "oneshot"; break;
+    case NVL_TASK_REDUCE_STAGED:
+        if (t->u.red.direct == NVL_DIRECT_FULL) { k = "twoshot_zcopy(direct)"; nb = t->nblocks_direct; }
+        else k = (t->u.red.use_nvls && t->team->nvls) ? "nvls_staged" : "twoshot_staged";
+        break;
+    case NVL_TASK_REDUCE_STEPS: k = t->u.red.sched == 1 ? "ring" : "rhd"; break;
+    case NVL_TASK_REDUCE_PIPE: k = "nvls_pipe"; break;
+    case NVL_TASK_REDUCE_SYMM: k = "nvls_symm_inplace"; break;
+    case NVL_TASK_AG_SYMM: k = "allgather_symm_mc"; break;
+    case NVL_TASK_XCHG: k = (t->use_push && t->u.xchg.direct) ? "exchange_push" : (t->u.xchg.direct ? "exchange_pull_zcopy" : (t->u.xchg.use_mc ? "exchange_nvls" : (t->u.xchg.ring ? "exchange_ring" : "exchange_pull_staged"))); break;
+    case NVL_TASK_SELF_COPY: k = "self_copy"; break;
+    case NVL_TASK_P2P: k = t->u.p2p.send ? "p2p_send" : "p2p_recv"; nb = nvl_p2p_lanes(t->u.p2p.bytes); break;
+    default: nb = 1; break;
+    }
+    snprintf(nvl_last_launch, sizeof(nvl_last_launch), "%s %dx%d", k, nb, t->nthreads);
+}
+
 static ucc_status_t nvl_launch(ucc_tl_nvl_task_t *t, cudaStream_t s)
 {
     cudaError_t e;
+    note_launch(t);
     switch (t->kind) {
     case NVL_TASK_REDUCE_ONESHOT:
         e = t->u.red.kind == NVL_RED_REDUCE_SCATTER ? nvl_launch_reduce_scatter_oneshot(&t->u.red, t->nblocks, t->nthreads, s)
@@ -64,6 +89,7 @@ static ucc_status_t nvl_launch(ucc_tl_nvl_task_t *t, cudaStream_t s)
             e = nvl_launch_exchange_push(&pa, t->nblocks, t->nthreads, s);
         } else e = nvl_launch_exchange(&t->u.xchg, t->nblocks, t->nthreads, s);
         break;
+    case NVL_TASK_P2P: e = nvl_launch_p2p(&t->u.p2p, t->nthreads, s); break;
     case NVL_TASK_SELF_COPY:
         e = t->u.xchg.src_bytes ? nvl_launch_self_copy(t->u.xchg.dst, t->u.xchg.src, t->u.xchg.src_bytes, t->nblocks, t->nthreads, s) : cudaSuccess;
         break;
@@ -80,6 +106,12 @@ static ucc_status_t launch_ordered(ucc_tl_nvl_task_t *t, cudaStream_t s)
     ucc_tl_nvl_team_t *team = t->team;
     ucc_status_t st;
     if (t->captured) return nvl_launch(t, s);
+    if (t->kind == NVL_TASK_P2P) { /* channel counters, no barrier epochs: independent of the team's collective order */
+        st = nvl_launch(t, s);
+        if (st != UCC_OK) return st;
+        CUDA_CHECK(cudaEventRecord(t->event, s));
+        return UCC_OK;
+    }
     if (team->last_event && team->last_stream != s) CUDA_CHECK(cudaStreamWaitEvent(s, team->last_event, 0));
     st = nvl_launch(t, s);
     if (st != UCC_OK) return st;
@@ -94,7 +126,12 @@ static ucc_status_t resolve_direct(ucc_tl_nvl_task_t *t)
 {
     nvl_direct_t d;
     int ok = ucc_tl_nvl_xb_resolve(t->team, t->cseq, t->need_src, t->need_dst, t->kind != NVL_TASK_XCHG, t->exp_src, t->exp_dst, &d);
-    tl_debug(NVL_LIB(t->team), "exchange %lu: %s (src %d dst %d)", (unsigned long)t->cseq, ok ? "zero-copy" : "staged", t->need_src, t->need_dst);
+    tl_debug(NVL_LIB(t->team), "exchange %lu: %s (src %d dst %d)", (unsigned long)t->cseq, ok > 0 ? "zero-copy" : (ok ? "MAPPING FAILED" : "staged"), t->need_src, t->need_dst);
+    if (ok < 0) {
+        tl_error(NVL_LIB(t->team), "cannot map a peer's buffer for the zero-copy kernel (the peers will run it): failing the collective; "
+                 "UCC_TL_NVL_ZCOPY=n avoids the zero-copy path");
+        return UCC_ERR_NO_RESOURCE;
+    }
     if (t->kind == NVL_TASK_XCHG) { t->u.xchg.direct = ok; if (ok) t->u.xchg.d = d; }
     else { t->u.red.direct = ok ? t->want_direct : NVL_DIRECT_NONE; if (ok) t->u.red.d = d; }
     return UCC_OK;
@@ -111,7 +148,8 @@ static ucc_status_t try_launch_queued(ucc_tl_nvl_task_t *t)
     if (task_is_direct(t)) {
         if (!t->published) t->published = ucc_tl_nvl_xb_publish(team, t->cseq, t->exp_src, t->exp_src_len, t->exp_dst, t->exp_dst_len, 1);
         if (!t->published || !ucc_tl_nvl_xb_ready(team, t->cseq)) return UCC_INPROGRESS;
-        resolve_direct(t);
+        st = resolve_direct(t);
+        if (st != UCC_OK) { ucc_list_del(&t->q_elem); t->state = NVL_TASK_LAUNCHED; return st; }
     }
     s = t->stream;
     st = launch_ordered(t, s);
@@ -159,7 +197,7 @@ static ucc_status_t nvl_post_on(ucc_tl_nvl_task_t *t, cudaStream_t s)
     if (cudaStreamIsCapturing(s, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusActive) t->captured = 1;
     ucc_spin_lock(&team->launch_lock);
     direct = task_is_direct(t);
-    if (t->kind == NVL_TASK_XCHG || t->kind == NVL_TASK_AG_SYMM) t->u.xchg.direct = 0; else t->u.red.direct = NVL_DIRECT_NONE;
+    if (t->kind == NVL_TASK_XCHG || t->kind == NVL_TASK_AG_SYMM) t->u.xchg.direct = 0; else if (t->kind != NVL_TASK_P2P) t->u.red.direct = NVL_DIRECT_NONE;
     if (direct) {
         /* the exchange sequence advances on every rank in post order; a capturing stream cannot wait for the
          * peers, so it tells them "not usable" and everybody takes the staged kernel for this one */
@@ -167,9 +205,9 @@ static ucc_status_t nvl_post_on(ucc_tl_nvl_task_t *t, cudaStream_t s)
         t->published = ucc_tl_nvl_xb_publish(team, t->cseq, t->exp_src, t->exp_src_len, t->exp_dst, t->exp_dst_len, !t->captured);
         if (t->captured) { direct = 0; if (team->xb_mine->consumed < t->cseq + 1) ucc_store_release(&team->xb_mine->consumed, t->cseq + 1); }
     }
-    if (t->captured || (ucc_list_is_empty(&team->launch_q) && (!direct || (t->published && ucc_tl_nvl_xb_ready(team, t->cseq))))) {
-        if (direct) resolve_direct(t);
-        st = launch_ordered(t, s);
+    if (t->captured || t->kind == NVL_TASK_P2P || (ucc_list_is_empty(&team->launch_q) && (!direct || (t->published && ucc_tl_nvl_xb_ready(team, t->cseq))))) {
+        st = direct ? resolve_direct(t) : UCC_OK;
+        if (st == UCC_OK) st = launch_ordered(t, s);
     } else {
         /* deferred: the kernel is launched (into the same stream) from progress once the peers' buffers are known and
          * the tasks ahead of it are launched.  As with the reference's triggered post, a stream-ordered consumer
@@ -444,7 +482,24 @@ static ucc_status_t xchg_init(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, 
     if (team->self) return self_init(b, b_team, task_p);
     memset(&x, 0, sizeof(x));
     x.team = team->dev;
-    if (UCC_COLL_ARGS_ACTIVE_SET(a)) return UCC_ERR_NOT_SUPPORTED;
+    if (UCC_COLL_ARGS_ACTIVE_SET(a)) {
+        /* two-member active set = send / recv (reference tl_cuda_coll.h:156-166 supports exactly this shape): one kernel per
+         * side over the pair's heap channel.  Messages between an ordered pair are matched in post order; the tag is not
+         * needed for that and larger active sets go to the next TL */
+        ucc_rank_t r0 = (ucc_rank_t)a->active_set.start, r1 = (ucc_rank_t)(a->active_set.start + a->active_set.stride), root = (ucc_rank_t)a->root;
+        size_t len = a->src.info.count * ucc_dt_size(a->src.info.datatype);
+        if (a->coll_type != UCC_COLL_TYPE_BCAST || a->active_set.size != 2 || !is_cuda(a->src.info.mem_type)) return UCC_ERR_NOT_SUPPORTED;
+        if ((me != r0 && me != r1) || (root != r0 && root != r1) || r0 >= N || r1 >= N || r0 == r1) return UCC_ERR_NOT_SUPPORTED;
+        st = task_alloc(b, b_team, &t);
+        if (st != UCC_OK) return st;
+        t->kind = NVL_TASK_P2P;
+        memset(&t->u.p2p, 0, sizeof(t->u.p2p));
+        t->u.p2p.team = team->dev; t->u.p2p.buf = a->src.info.buffer; t->u.p2p.bytes = len;
+        t->u.p2p.send = me == root; t->u.p2p.peer = (int)(me == r0 ? r1 : r0);
+        t->nblocks = nvl_p2p_lanes(len);
+        *task_p = &t->super;
+        return UCC_OK;
+    }
     switch (a->coll_type) {
     case UCC_COLL_TYPE_ALLGATHER: {
         size_t blk = a->dst.info.count / N * ucc_dt_size(a->dst.info.datatype);

@@ -124,7 +124,8 @@ static char *import_buf(ucc_tl_nvl_team_t *team, ucc_rank_t p, const nvl_xb_buf_
 }
 
 /* all members published: decide (identically on every rank) whether the buffers can be used in place and map
- * them.  need_src / need_dst say which sides the kernel touches remotely.  Marks the entries consumed. */
+ * them.  need_src / need_dst say which sides the kernel touches remotely.  Marks the entries consumed.
+ * Returns 1 = in place, 0 = every member stages (symmetric decision), -1 = local mapping failure (the collective must fail). */
 int ucc_tl_nvl_xb_resolve(ucc_tl_nvl_team_t *team, uint64_t cseq, int need_src, int need_dst, int need_align, const void *my_src, void *my_dst, nvl_direct_t *d)
 {
     ucc_rank_t N = UCC_TL_TEAM_SIZE(team), me = UCC_TL_TEAM_RANK(team);
@@ -138,14 +139,15 @@ int ucc_tl_nvl_xb_resolve(ucc_tl_nvl_team_t *team, uint64_t cseq, int need_src, 
         if (need_align && need_src && e->src.kind != NVL_XB_EMPTY && ((e->src.base + e->src.off) & 15)) ok = 0;
         if (need_align && need_dst && e->dst.kind != NVL_XB_EMPTY && ((e->dst.base + e->dst.off) & 15)) ok = 0;
     }
-    for (ucc_rank_t p = 0; p < N && ok; p++) {
+    /* up to here every member took the same decision (it only depends on what all of them published).  Mapping a peer's
+     * allocation can still fail on THIS rank only; the peers will launch the in-place kernel, so falling back to the staged
+     * one here would mix two protocols and corrupt data silently: report it (-1), the caller fails the collective. */
+    for (ucc_rank_t p = 0; p < N && ok > 0; p++) {
         const nvl_xb_entry_t *e = &team->xb[p]->e[cseq % NVL_XB_SLOTS];
         if (p == me) { d->src[p] = (const char *)my_src; d->dst[p] = (char *)my_dst; continue; }
-        if (need_src && e->src.kind != NVL_XB_EMPTY) { d->src[p] = import_buf(team, p, &e->src); if (!d->src[p]) ok = 0; }
-        if (need_dst && e->dst.kind != NVL_XB_EMPTY) { d->dst[p] = import_buf(team, p, &e->dst); if (!d->dst[p]) ok = 0; }
+        if (need_src && e->src.kind != NVL_XB_EMPTY) { d->src[p] = import_buf(team, p, &e->src); if (!d->src[p]) ok = -1; }
+        if (need_dst && e->dst.kind != NVL_XB_EMPTY) { d->dst[p] = import_buf(team, p, &e->dst); if (!d->dst[p]) ok = -1; }
     }
-    /* NOTE: an import failure is a local event; it is reported as an error by the caller rather than silently
-     * diverging from the peers' choice */
     if (team->xb_mine->consumed < cseq + 1) ucc_store_release(&team->xb_mine->consumed, cseq + 1);
     return ok;
 }

@@ -96,7 +96,7 @@ typedef struct ucc_tl_shm_context {
     shm_ring_hdr_t             *ring;     /* my receive ring */
     size_t                      ring_len;
     ucc_hash_t                  eps;      /* ep_id -> ucc_tl_shm_ep_t* */
-    ucc_list_link_t             posted_recvs, pending_sends, rndv_sends, unexpected;
+    ucc_list_link_t             posted_recvs, pending_sends, rndv_sends, unexpected, pending_acks;
     ucc_mpool_t                 req_mp, task_mp;
     ucc_thread_mode_t           tm;
     ucc_recursive_spinlock_t    lock;     /* THREAD_MULTIPLE */

@@ -69,7 +69,7 @@ ucc_status_t ucc_tl_shm_ctx_p2p_init(ucc_tl_shm_context_t *ctx)
     ctx->ring->magic = SHM_RING_MAGIC;
     ucc_hash_init(&ctx->eps);
     ucc_list_head_init(&ctx->posted_recvs); ucc_list_head_init(&ctx->pending_sends);
-    ucc_list_head_init(&ctx->rndv_sends); ucc_list_head_init(&ctx->unexpected);
+    ucc_list_head_init(&ctx->rndv_sends); ucc_list_head_init(&ctx->unexpected); ucc_list_head_init(&ctx->pending_acks);
     ucc_recursive_spinlock_init(&ctx->lock);
     return ucc_mpool_init(&ctx->req_mp, 0, sizeof(shm_req_t), 0, 64, 64, (unsigned)-1, NULL, ctx->tm, "tl_shm_reqs");
 }
@@ -84,6 +84,7 @@ void ucc_tl_shm_ctx_p2p_cleanup(ucc_tl_shm_context_t *ctx)
     }
     ucc_hash_destroy(&ctx->eps);
     ucc_list_for_each_safe(u, t, &ctx->unexpected, list) { ucc_list_del(&u->list); free(u->data); free(u); }
+    while (!ucc_list_is_empty(&ctx->pending_acks)) { ucc_list_link_t *l = ctx->pending_acks.next; ucc_list_del(l); free(l); } /* list link is the first member */
     if (ctx->ring) { ucc_shm_detach(ctx->ring, ctx->ring_len); ucc_shm_unlink(ctx->addr.name); ctx->ring = NULL; }
     ucc_mpool_cleanup(&ctx->req_mp, 1);
 }
@@ -192,13 +193,33 @@ static void send_push(ucc_tl_shm_context_t *ctx, shm_req_t *r)
     shm_req_complete(r);
 }
 
-static void send_ack(ucc_tl_shm_context_t *ctx, ucc_tl_shm_ep_t *ep, uint64_t cookie)
+/* ACK of a rendezvous: a tiny control cell in the sender's ring.  Never waits: when that ring is full the ACK is parked on
+ * ctx->pending_acks and flushed from progress (two contexts that spin for a cell in each other's full ring while holding
+ * their locks - both rings full of eager cells behind an RTS - would never drain them). */
+typedef struct shm_pending_ack { ucc_list_link_t list; ucc_tl_shm_ep_t *ep; uint64_t cookie; } shm_pending_ack_t;
+static int ack_try(ucc_tl_shm_context_t *ctx, ucc_tl_shm_ep_t *ep, uint64_t cookie)
 {
-    /* ACKs are tiny control cells: spin briefly, the peer drains its ring from its own progress */
-    uint64_t pos; shm_cell_hdr_t *c;
-    while (!(c = ring_reserve(ep->ring, &pos))) { if (ep->ring == ctx->ring) { /* my own ring is full: drain it */ ucc_tl_shm_progress(ctx); } else ucc_cpu_relax(); }
+    uint64_t pos; shm_cell_hdr_t *c = ring_reserve(ep->ring, &pos);
+    if (!c) return 0;
     c->tag = 0; c->src_ep = ctx->addr.ep_id; c->total_len = 0; c->offset = cookie; c->cookie = 0; c->len = 0; c->type = SHM_CELL_ACK; c->src_mt = 0;
     ring_publish(c, pos);
+    return 1;
+}
+static void send_ack(ucc_tl_shm_context_t *ctx, ucc_tl_shm_ep_t *ep, uint64_t cookie)
+{
+    shm_pending_ack_t *pa;
+    if (ucc_list_is_empty(&ctx->pending_acks) && ack_try(ctx, ep, cookie)) return;
+    pa = (shm_pending_ack_t *)malloc(sizeof(*pa));
+    pa->ep = ep; pa->cookie = cookie;
+    ucc_list_add_tail(&ctx->pending_acks, &pa->list);
+}
+static void flush_acks(ucc_tl_shm_context_t *ctx)
+{
+    shm_pending_ack_t *pa, *t;
+    ucc_list_for_each_safe(pa, t, &ctx->pending_acks, list) {
+        if (!ack_try(ctx, pa->ep, pa->cookie)) break;
+        ucc_list_del(&pa->list); free(pa);
+    }
 }
 
 ucc_status_t ucc_tl_shm_send_nb(ucc_tl_shm_team_t *team, ucc_rank_t dst, uint64_t tag, void *buf, size_t len, ucc_memory_type_t mt, shm_req_t **req_p)
@@ -317,6 +338,7 @@ ucc_status_t ucc_tl_shm_progress(void *arg)
         handle_cell(ctx, c);
         ucc_store_release(&c->seq, pos + ring->n_cells);
     }
+    flush_acks(ctx);
     ucc_list_for_each_safe(r, t, &ctx->pending_sends, list) {
         send_push(ctx, r);
         if (r->rndv) { if (r->progressed) { ucc_list_del(&r->list); ucc_list_add_tail(&ctx->rndv_sends, &r->list); } else break; }

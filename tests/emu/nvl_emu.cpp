@@ -115,7 +115,7 @@ template <int NP, int U> static void run_direct(World &w, size_t count, int op, 
         nvl_red_args_t a; memset(&a, 0, sizeof(a));
         a.team = w.team(r, false); a.src = src[r]; a.dst = dst[r]; a.count = count; a.op = op; a.kind = NVL_RED_ALLREDUCE; a.direct = NVL_DIRECT_FULL;
         for (int p = 0; p < N; p++) { a.d.src[p] = (const char *)src[p]; a.d.dst[p] = (char *)dst[p]; }
-        nvl_reduce_direct_kernel<float, NP, U>(a);
+        nvl_reduce_direct_kernel<float>(a);
     });
     CHECK(w.host_err == 0);
     check_allreduce<float>("direct", dst, N, count, op);

@@ -29,6 +29,7 @@ nvl_emu_world g_emu;   /* no multicast in this build: teams never get an mc_heap
 #include "nvl_symm.cu"
 #include "nvl_push.cu"
 #include "nvl_oneshot_rs.cu"
+#include "nvl_p2p.cu"
 
 extern "C" void emu_stream_enqueue(cudaStream_t s, std::function<void()> *f);
 
@@ -65,13 +66,7 @@ template <typename F> static cudaError_t enqueue_grid(cudaStream_t s, int nb, in
     default: return cudaErrorInvalidValue;                                            \
     }
 
-template <typename T> static void direct_any(nvl_red_args_t a)
-{
-    if (a.team.size <= 2) nvl_reduce_direct_kernel<T, 2, 4>(a);
-    else if (a.team.size <= 4) nvl_reduce_direct_kernel<T, 4, 2>(a);
-    else if (a.team.size <= 8) nvl_reduce_direct_kernel<T, 8, 1>(a);
-    else nvl_reduce_direct_kernel<T, NVL_MAX_PEERS, 1>(a);
-}
+template <typename T> static void direct_any(nvl_red_args_t a) { nvl_reduce_direct_kernel<T>(a); }
 
 extern "C" {
 size_t nvl_dt_size(int dt) { static const size_t sz[NVL_DT_LAST] = {1, 2, 4, 8, 1, 2, 4, 8, 2, 4, 8, 2}; return dt >= 0 && dt < NVL_DT_LAST ? sz[dt] : 0; }
@@ -93,6 +88,8 @@ cudaError_t nvl_launch_reduce_symm(const nvl_red_args_t *, int, int, cudaStream_
 cudaError_t nvl_launch_allgather_symm(const nvl_xchg_args_t *, int, int, cudaStream_t) { return cudaErrorInvalidValue; }
 cudaError_t nvl_launch_exchange(const nvl_xchg_args_t *ap, int nb, int nt, cudaStream_t s) { nvl_xchg_args_t a = *ap; return enqueue_grid(s, nb, nt, [a]() { nvl_exchange_kernel(a); }); }
 cudaError_t nvl_launch_exchange_push(const nvl_push_args_t *ap, int nb, int nt, cudaStream_t s) { nvl_push_args_t a = *ap; return enqueue_grid(s, nb, nt, [a]() { nvl_exchange_push_kernel(a); }); }
+int nvl_p2p_lanes(size_t bytes) { size_t n = bytes / (64 * 1024); return n < 1 ? 1 : (n > NVL_P2P_MAX_CTAS ? NVL_P2P_MAX_CTAS : (int)n); }
+cudaError_t nvl_launch_p2p(const nvl_p2p_args_t *ap, int nt, cudaStream_t s) { nvl_p2p_args_t a = *ap; return enqueue_grid(s, nvl_p2p_lanes(a.bytes), nt > 64 ? 64 : nt, [a]() { nvl_p2p_kernel(a); }); }
 cudaError_t nvl_launch_barrier(const nvl_team_dev_t *tp, cudaStream_t s) { nvl_team_dev_t t = *tp; return enqueue_grid(s, 1, 32, [t]() { nvl_barrier_kernel(t); }); }
 cudaError_t nvl_launch_self_copy(void *dst, const void *src, size_t bytes, int, int, cudaStream_t s)
 { return enqueue_grid(s, 1, 1, [=]() { memmove(dst, src, bytes); }); }

@@ -349,6 +349,64 @@ def device_timeout():
         print(f"  device-side timeout ok (statuses {[q.contents.status if q else None for _, q in reqs]}, {took:.1f} s)", flush=True)
 
 
+def p2p_active_set():
+    """two-member active-set bcast on "device" buffers = send / recv through the heap channel kernel (kernels/nvl_p2p.cu): several
+    pairs at once, both directions, a message longer than the channel ring (sender and receiver pipeline), repeated (the channel
+    counters persist across launches) and next to a collective of the same team"""
+    import time
+    n = 4
+    with UccJob(n, env=dict(BASE, **NOZC)) as j:
+        team = j.create_team(range(n))
+        for count in (1, 1000, 70001, 300007):
+            pairs = [(0, 1), (3, 1), (2, 0), (1, 3)]
+            for rep in range(2):
+                bufs, reqs = [], []
+                for i, (s_, d_) in enumerate(pairs):
+                    src, dst = Dev(count, fill=rnd(count, 100 * rep + i)), Dev(count, fill=0)
+                    bufs.append((src, dst))
+                    for r, b in ((s_, src), (d_, dst)):
+                        a = ca("bcast", b, None, root=s_, count_dst=0, active_set=(s_, d_ - s_, 2), tag=7 + i)
+                        q = C.POINTER(U.ucc_coll_req_t)()
+                        U.check(U.ucc_collective_init(C.byref(a), C.byref(q), team.members[r].team), "init")
+                        reqs.append((a, q))
+                for _, q in reqs:
+                    U.check(U.ucc_collective_post(q), "post")
+                t0 = time.time()
+                while any(q.contents.status == U.UCC_INPROGRESS for _, q in reqs):
+                    for r in range(n):
+                        U.ucc_context_progress(j.procs[r].ctx)
+                    assert time.time() - t0 < 120, "p2p did not complete"
+                rt.cudaDeviceSynchronize()
+                for _, q in reqs:
+                    assert q.contents.status == U.UCC_OK, q.contents.status
+                    U.ucc_collective_finalize(q)
+                for i, (src, dst) in enumerate(bufs):
+                    assert np.array_equal(src.a, dst.a), ("p2p", count, rep, pairs[i])
+            src = [Dev(777, fill=rnd(777, r)) for r in range(n)]
+            dst = [Dev(777, fill=0) for _ in range(n)]
+            run(team, [ca("allreduce", src[r], dst[r]) for r in range(n)])
+            assert np.allclose(dst[1].a, sum(s.a for s in src))
+    print("  active-set p2p ok", flush=True)
+
+
+def int_avg():
+    """AVG on integer datatypes = truncated sum / N, on every reduction kernel"""
+    n = 3
+    for alg, extra in (("oneshot", NOZC), ("twoshot", NOZC), ("twoshot", ZC), ("ring", NOZC)):
+        env = dict(BASE, UCC_TL_NVL_TUNE=f"allreduce:cuda:inf:@{alg}", UCC_TL_NVL_ALLREDUCE_ONESHOT_THRESH="0" if alg != "oneshot" else "1M", **extra)
+        with UccJob(n, env=env) as j:
+            team = j.create_team(range(n))
+            for dt in ("int32", "int64"):
+                src = [Dev(1001, np.dtype(dt), fill=(rnd(1001, r + 3, np.dtype(dt)) - 4) * 7) for r in range(n)]
+                dst = [Dev(1001, np.dtype(dt), fill=0) for _ in range(n)]
+                run(team, [ca("allreduce", src[r], dst[r], dt=dt, op="avg") for r in range(n)])
+                tot = sum(s.a.astype(np.int64) for s in src)
+                exp = np.trunc(tot / n).astype(np.int64)
+                for r in range(n):
+                    assert np.array_equal(dst[r].a.astype(np.int64), exp), (alg, dt, r, dst[r].a[:8], exp[:8])
+    print("  integer AVG ok", flush=True)
+
+
 SCENARIOS = {
     "allreduce": lambda: [allreduce_suite(a, e) for a, e in (("oneshot", NOZC), ("twoshot", NOZC), ("twoshot", ZC), ("ring", NOZC), ("rhd", NOZC))],
     "colls_staged": lambda: other_colls(NOZC),
@@ -359,6 +417,7 @@ SCENARIOS = {
     "triggered": lambda: [triggered(NOZC), triggered(ZC)],
     "timeout": device_timeout,
     "cross_team": lambda: [cross_team_order(NOZC), cross_team_order(ZC)],
+    "p2p": lambda: [p2p_active_set(), int_avg()],
 }
 
 if __name__ == "__main__":

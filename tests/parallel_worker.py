@@ -61,6 +61,24 @@ def main():
         print(f"rank {rank}: tensor-parallel mismatch", flush=True)
         ok = False
 
+    # ---- ColumnParallelLinear(gather_output=True): the gathered output must carry gradients back to weight, bias and input
+    from ucc_b200.parallel.tensor_parallel import ColumnParallelLinear
+    torch.manual_seed(200 + rank)
+    col = ColumnParallelLinear(d, 4 * world, comm=comm, gather_output=True, device=dev)
+    xg = torch.randn(3, d, generator=torch.Generator().manual_seed(9)).to(dev).requires_grad_()
+    coef = torch.arange(4 * world, dtype=torch.float32, device=dev) + 1
+    (col(xg) * coef).sum().backward()
+    wf = torch.empty(world, 4, d, device=dev); ops.all_gather_into_tensor(wf, col.weight.data.contiguous(), comm=comm)
+    bf = torch.empty(world, 4, device=dev); ops.all_gather_into_tensor(bf, col.bias.data.contiguous(), comm=comm)
+    wd, bd = wf.reshape(4 * world, d).clone().requires_grad_(), bf.reshape(4 * world).clone().requires_grad_()
+    xr = xg.detach().clone().requires_grad_()
+    (torch.nn.functional.linear(xr, wd, bd) * coef).sum().backward()
+    sl = slice(4 * rank, 4 * rank + 4)
+    if col.weight.grad is None or not torch.allclose(col.weight.grad, wd.grad[sl], rtol=1e-4, atol=1e-5) or not torch.allclose(col.bias.grad, bd.grad[sl], rtol=1e-4, atol=1e-5) \
+            or not torch.allclose(xg.grad, xr.grad, rtol=1e-4, atol=1e-5):
+        print(f"rank {rank}: ColumnParallelLinear(gather_output) gradient mismatch", flush=True)
+        ok = False
+
     # ---- MoE dispatch / combine round trip with skewed routing
     T, H = 50 + 7 * rank, 12
     tok = torch.arange(T * H, dtype=torch.float32, device=dev).view(T, H) + 10000 * rank

@@ -73,6 +73,19 @@ def test_ec_cpu_reduce(lib_alive, dt, op, nsrc):
         assert np.array_equal(dst, exp)
 
 
+def test_ec_cpu_int_avg(lib_alive):
+    """AVG on integers = truncated sum / N (reference: d[i] * (1/N) in double precision); casting 1/N to the integer type gave 0"""
+    n = 1000
+    ex = I.Executor(U.UCC_EE_CPU_THREAD)
+    for dt in ("int32", "int64", "uint8", "int16"):
+        s = [mk(dt, n, 5 * i + 2) for i in range(3)]
+        d = np.zeros(n, NP_DT[dt])
+        ex.run(reduce_args(d.ctypes.data, [x.ctypes.data for x in s], n, dt, "avg", alpha=1.0 / 3))
+        tot = sum(x.astype(np.int64) for x in s).astype(NP_DT[dt]).astype(np.float64)   # the sum wraps in the storage type first
+        assert np.array_equal(d, (tot * (1.0 / 3)).astype(NP_DT[dt])), dt
+    ex.close()
+
+
 def test_ec_cpu_alpha_strided_multi_copy(lib_alive):
     n = 100
     ex = I.Executor(U.UCC_EE_CPU_THREAD)

@@ -56,8 +56,8 @@ def ref_reduce(op, xs):
     a = torch.stack([x.double() if x.dtype.is_floating_point else x.long() for x in xs])
     if op == "sum":
         return a.sum(0)
-    if op == "avg":
-        return a.sum(0) / len(xs)
+    if op == "avg":   # integers: truncated sum / N
+        return a.sum(0) / len(xs) if a.dtype.is_floating_point else torch.div(a.sum(0), len(xs), rounding_mode="trunc")
     if op == "prod":
         return a.prod(0)
     if op == "max":
@@ -102,7 +102,7 @@ def test_allreduce_f32(alg_job, n, count):
 
 
 @pytest.mark.parametrize("dt,op", [("float32", "avg"), ("float64", "sum"), ("float16", "sum"), ("bfloat16", "sum"), ("bfloat16", "max"),
-                                   ("int32", "sum"), ("int64", "max"), ("int8", "min"), ("uint8", "sum"), ("int16", "prod")])
+                                   ("int32", "sum"), ("int64", "max"), ("int8", "min"), ("uint8", "sum"), ("int16", "prod"), ("int32", "avg"), ("int64", "avg")])
 def test_allreduce_dt_op(alg_job, dt, op):
     alg, teams = alg_job
     n, count = 4, 1000
@@ -387,6 +387,58 @@ def test_single_rank_team_copy_kernel():
             run(team, [cargs("allreduce", None, buf[0], "float32", inplace=True)])
             assert torch.equal(buf[0], keep)
         run(team, [coll_args("barrier")])
+
+
+def _p2p_round(j, team, msgs):
+    """msgs: list of (src_rank, dst_rank, tensor_src, tensor_dst, tag): init + post everything, progress until done"""
+    import ctypes as C
+    import time
+    reqs = []
+    for s_, d_, ts, td, tag in msgs:
+        for r, buf in ((s_, ts), (d_, td)):
+            a = cargs("bcast", buf, None, "float32", root=s_, count_dst=0, active_set=(s_, d_ - s_, 2), tag=tag)
+            q = C.POINTER(U.ucc_coll_req_t)()
+            st = U.ucc_collective_init(C.byref(a), C.byref(q), team.members[r].team)
+            assert st == U.UCC_OK, U.status_str(st)
+            reqs.append((q, a))
+    for q, _ in reqs:
+        assert U.ucc_collective_post(q) == U.UCC_OK
+    t0 = time.time()
+    while any(q.contents.status == U.UCC_INPROGRESS for q, _ in reqs) and time.time() - t0 < 20:
+        j.progress()
+    for q, _ in reqs:
+        assert q.contents.status == U.UCC_OK, U.status_str(q.contents.status)
+        U.ucc_collective_finalize(q)
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("count", [1, 1000, 65536 + 3, 700001])
+def test_active_set_p2p(count):
+    """reference test/gtest/active_set/test_active_set.cc:165-184: two-member active-set bcast = send / recv, here on CUDA buffers
+    through the tl/nvl channel kernel (700001 floats > the 1 MB ring: sender and receiver pipeline through the slots)"""
+    need_cuda()
+    n = 4
+    with UccJob(n, env=dict(ENV)) as j:
+        team = j.create_team()
+        pairs = [(0, 1), (3, 1), (2, 0), (1, 3)]
+        srcs = [gen("float32", count, 10 + i) for i in range(len(pairs))]
+        dsts = [torch.zeros(count, device="cuda") for _ in pairs]
+        # several messages, two of them to the same receiver, one pair used in both directions; then again (counters persist)
+        for rep in range(2):
+            for d in dsts:
+                d.zero_()
+            _p2p_round(j, team, [(s_, d_, srcs[i], dsts[i], 3 + i) for i, (s_, d_) in enumerate(pairs)])
+            for i in range(len(pairs)):
+                assert torch.equal(dsts[i], srcs[i]), (rep, pairs[i])
+        # the team's collectives still work next to the channels
+        src = [gen("float32", 5000, r) for r in range(n)]
+        dst = [torch.zeros(5000, device="cuda") for _ in range(n)]
+        run(team, [cargs("allreduce", src[r], dst[r], "float32") for r in range(n)])
+        assert_close(dst[2], ref_reduce("sum", src), "float32")
+    import ctypes as C
+    info = C.CDLL(os.path.join(os.path.dirname(U.LIB_PATH), "ucc", "libucc_tl_nvl.so")).ucc_tl_nvl_last_launch_info
+    info.restype = C.c_char_p
+    assert info() is not None
 
 
 # Opt-in: seen hanging on the host side in the last GPU session of round 1 (asymmetric memory at the root with tl/nvl),

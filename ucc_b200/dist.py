@@ -240,6 +240,18 @@ class Communicator:
         raw = torch.as_tensor(_Raw(), device=torch.device("cuda", torch.cuda.current_device()))
         return raw[:nbytes].view(dtype).view(shape)
 
+    def request_info_last(self):
+        """name and launch geometry of the tl/nvl kernel this process launched last ("" when tl/nvl is not loaded)"""
+        fn = getattr(self, "_last_info_fn", None)
+        if fn is None:
+            try:
+                fn = C.CDLL(os.path.join(os.path.dirname(U.LIB_PATH), "ucc", "libucc_tl_nvl.so")).ucc_tl_nvl_last_launch_info
+                fn.restype = C.c_char_p
+            except (OSError, AttributeError):
+                fn = False
+            self._last_info_fn = fn
+        return fn().decode() if fn else ""
+
     def symm_reset(self):
         """forget every symm_empty() allocation (the tensors must no longer be used)"""
         self._symm_off = 0

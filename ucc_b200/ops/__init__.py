@@ -63,6 +63,58 @@ def all_reduce(tensor, op="sum", comm=None, async_op=False):
     return _launch(comm, comm.allreduce_init(tensor, tensor, op=op), tensor, async_op)
 
 
+_from_host_state = {"chunks": 1}
+
+
+def last_from_host_chunks():
+    """how many chunks the most recent all_reduce_from_host() pipelined"""
+    return _from_host_state["chunks"]
+
+
+def all_reduce_from_host(host, out, staging=None, op="sum", comm=None, chunks=None, stream=None):
+    """All-reduce a vector that lives in (pinned) HOST memory into the CUDA tensor `out` - offloaded gradients / optimizer
+    shards, data-loader statistics.  The host -> device copy runs on its own stream (copy engine) in `chunks` pieces; the
+    NVLink allreduce kernel of piece c is enqueued behind the arrival of piece c only, so PCIe transfer and NVLink
+    reduction overlap instead of adding up.  `staging` (CUDA, same shape) receives the local copy; allocated when omitted.
+    Every member must call with the same sizes (the chunking is derived from them).  Returns when `out` is complete."""
+    comm = comm or default_comm()
+    stream = stream or torch.cuda.current_stream()
+    n = host.numel()
+    nbytes = n * host.element_size()
+    if chunks is None:
+        chunks = 8 if nbytes >= (64 << 20) else (2 if nbytes >= (8 << 20) else 1)
+    align = max(1, 256 // host.element_size())
+    per = (n + chunks - 1) // chunks
+    per = (per + align - 1) // align * align
+    bounds = [(o, min(o + per, n)) for o in range(0, n, per)] if n else []
+    _from_host_state["chunks"] = len(bounds)
+    staging = staging if staging is not None else torch.empty_like(out)
+    st = getattr(comm, "_h2d_stream", None)
+    if st is None:
+        st = comm._h2d_stream = torch.cuda.Stream()
+    hflat, sflat, oflat = host.view(-1), staging.view(-1), out.view(-1)
+    st.wait_stream(stream)                                   # earlier readers of `staging` on the caller's stream
+    evs = []
+    with torch.cuda.stream(st):
+        for lo, hi in bounds:
+            sflat[lo:hi].copy_(hflat[lo:hi], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(st)
+            evs.append(ev)
+    reqs = []
+    for (lo, hi), ev in zip(bounds, evs):
+        stream.wait_event(ev)
+        r = comm.allreduce_init(sflat[lo:hi], oflat[lo:hi], op=op)
+        r.post_on_stream(stream, wait_posted=False)
+        reqs.append(r)
+    for r in reqs:
+        r.wait_posted()
+    for r in reqs:
+        r.wait()
+        r.finalize()
+    return out
+
+
 def reduce(tensor, dst=0, op="sum", comm=None, async_op=False):
     comm = comm or default_comm()
     req = comm.coll_init("reduce", None if comm.rank == dst else tensor, tensor if comm.rank == dst else None, op=op, root=dst, inplace=comm.rank == dst)

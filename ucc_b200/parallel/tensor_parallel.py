@@ -44,9 +44,25 @@ class ColumnParallelLinear(nn.Module):
         y = torch.nn.functional.linear(x, self.weight, self.bias)
         if not self.gather_output:
             return y
-        out = torch.empty((self.comm.size,) + tuple(y.shape), dtype=y.dtype, device=y.device)
-        ops.all_gather_into_tensor(out, y.contiguous(), comm=self.comm)
+        return _AllGatherLastDim.apply(y, self.comm)
+
+
+class _AllGatherLastDim(torch.autograd.Function):
+    """forward: concatenate the members' output-feature shards along the last dimension (allgather); backward: every member
+    keeps the slice of the gradient that belongs to its shard (the downstream computation is replicated, so the incoming
+    gradient is already identical everywhere - Megatron's gather_from_tensor_model_parallel_region)."""
+
+    @staticmethod
+    def forward(ctx, y, comm):
+        ctx.comm, ctx.width = comm, y.shape[-1]
+        out = torch.empty((comm.size,) + tuple(y.shape), dtype=y.dtype, device=y.device)
+        ops.all_gather_into_tensor(out, y.contiguous(), comm=comm)
         return out.movedim(0, -2).reshape(*y.shape[:-1], -1)
+
+    @staticmethod
+    def backward(ctx, grad):
+        w, r = ctx.width, ctx.comm.rank
+        return grad[..., r * w:(r + 1) * w].contiguous(), None
 
 
 class RowParallelLinear(nn.Module):
