@@ -27,6 +27,9 @@ ucc_config_field_t ucc_tl_nvl_context_config_table[] = {
     {"USER_SIZE", "0", "Size of a symmetric USER region appended to every team heap (bound to the NVLS multicast object like the rest of the heap). "
      "Buffers placed there at the same offset on every member (ucc_tl_nvl_symm_region) are reduced in place through the switch: no staging, no copy-out",
      ucc_offsetof(ucc_tl_nvl_context_config_t, user_size), UCC_CONFIG_TYPE_MEMUNITS},
+    {"SLOTS", "1", "Independent collective lanes per team (reference tl/cuda MAX_CONCURRENT): consecutive collectives use consecutive lanes and, when "
+     "posted on different streams, overlap.  Every lane has its own control block, one-shot slots and SYMMETRIC_SIZE of staging space; one "
+     "kernel may use at most (2 x SMs) / SLOTS thread blocks so that all lanes stay co-resident", ucc_offsetof(ucc_tl_nvl_context_config_t, slots), UCC_CONFIG_TYPE_UINT},
     {"FD_VIA_PIDFD", "try", "Fetch peers' memory handles with pidfd_getfd before falling back to a unix socket", ucc_offsetof(ucc_tl_nvl_context_config_t, fd_via_pidfd), UCC_CONFIG_TYPE_TERNARY},
     {NULL}};
 
@@ -78,6 +81,11 @@ static ucc_status_t nvl_ctx_create(const ucc_base_context_params_t *p, const ucc
     if (ctx->cfg.max_blocks > NVL_MAX_BLOCKS) ctx->cfg.max_blocks = NVL_MAX_BLOCKS;
     /* every block of a collective kernel must be resident at once (they wait for each other): 2 CTAs of 512 threads per SM */
     if (ctx->sm_count > 0 && ctx->cfg.max_blocks > 2u * (unsigned)ctx->sm_count) ctx->cfg.max_blocks = 2u * (unsigned)ctx->sm_count;
+    if (ctx->cfg.slots < 1) ctx->cfg.slots = 1;
+    if (ctx->cfg.slots > NVL_MAX_LANES) ctx->cfg.slots = NVL_MAX_LANES;
+    /* kernels of different lanes may run at the same time and their blocks wait for the peers' blocks: everything that can be
+     * in flight together has to fit the device (2 resident blocks per SM) */
+    if (ctx->sm_count > 0 && ctx->cfg.max_blocks > 2u * (unsigned)ctx->sm_count / ctx->cfg.slots) ctx->cfg.max_blocks = 2u * (unsigned)ctx->sm_count / ctx->cfg.slots;
     if (ctx->cfg.max_blocks < 1) ctx->cfg.max_blocks = 1;
     if (ctx->cfg.nthreads < 64) ctx->cfg.nthreads = 64;
     if (ctx->cfg.nthreads > 1024) ctx->cfg.nthreads = 1024;
@@ -108,7 +116,7 @@ ucc_tl_iface_t ucc_tl_nvl = {
     .tl_lib_config = {"TL_NVL lib", "TL_NVL_", tl_nvl_lib_config_table, sizeof(ucc_tl_nvl_lib_config_t), {NULL, NULL}},
     .tl_context_config = {"TL_NVL context", "TL_NVL_", ucc_tl_nvl_context_config_table, sizeof(ucc_tl_nvl_context_config_t), {NULL, NULL}},
     .lib = {nvl_lib_init, nvl_lib_finalize, nvl_lib_get_attr, nvl_lib_get_properties},
-    .context = {nvl_ctx_create, NULL, nvl_ctx_destroy, nvl_ctx_get_attr, NULL, NULL, NULL},
+    .context = {nvl_ctx_create, NULL, nvl_ctx_destroy, nvl_ctx_get_attr, ucc_tl_nvl_mem_map, ucc_tl_nvl_mem_unmap, ucc_tl_nvl_memh_pack},
     .team = {ucc_tl_nvl_team_create_post, ucc_tl_nvl_team_create_test, ucc_tl_nvl_team_destroy, ucc_tl_nvl_team_get_scores},
     .coll = {ucc_tl_nvl_coll_init},
 };

@@ -44,9 +44,11 @@ typedef struct ucc_tl_nvl_context_config {
     int      zcopy;            /* ternary: read / write the members' user buffers in place (CUDA IPC) */
     size_t   zcopy_thresh;     /* ... for messages of at least this size */
     size_t   user_size;        /* symmetric USER region appended to every team heap (0: none), see ucc_tl_nvl_symm_region() */
+    unsigned slots;            /* independent collective lanes per team (reference tl/cuda MAX_CONCURRENT): collectives on different lanes may overlap */
 } ucc_tl_nvl_context_config_t;
 
 /* ---- zero-copy buffer exchange board (tl_nvl_direct.c): one single-writer POSIX shm segment per rank ---- */
+#define NVL_MAX_LANES 8
 #define NVL_XB_SLOTS 64
 #define NVL_GATE_SLOTS 1024
 #define NVL_IPC_CACHE_MAX 64
@@ -68,6 +70,7 @@ typedef struct ucc_tl_nvl_context {
     ucc_tl_nvl_addr_t           addr;
     int                         dev;
     int                         sm_count;
+    unsigned                    lane_blocks;   /* CTAs one collective kernel may use: all lanes of a team together stay co-resident */
     ucc_mpool_t                 task_mp;
     ucc_thread_mode_t           tm;
 } ucc_tl_nvl_context_t;
@@ -126,9 +129,15 @@ typedef struct ucc_tl_nvl_team {
     /* launch ordering: kernels of one team must start in post order on every rank (the device-side epochs assume it) */
     ucc_list_link_t   launch_q;             /* posted tasks whose kernel is not launched yet */
     ucc_spinlock_t    launch_lock;
-    cudaStream_t      last_stream;          /* stream of the most recent launch */
-    cudaEvent_t       order_event;          /* spare event: swapped with a finalized task's event that last_event points to */
-    cudaEvent_t       last_event;           /* completion event of the most recent launch */
+    /* lanes ("slots"): the heap holds `nlanes` complete copies of [control | one-shot | p2p | data]; consecutive collectives take
+     * consecutive lanes (post order, identical on every member), so up to nlanes collectives of a team - posted on different
+     * streams - run concurrently with their own flags, epochs and staging space.  Kernels of ONE lane still start in post order. */
+    unsigned          nlanes;
+    size_t            lane_stride;
+    uint32_t          lane_seq;             /* next lane (advances at post) */
+    cudaStream_t      last_stream[NVL_MAX_LANES];  /* stream of the lane's most recent launch */
+    cudaEvent_t       order_event[NVL_MAX_LANES];  /* spare event: swapped with a finalized task's event that last_event points to */
+    cudaEvent_t       last_event[NVL_MAX_LANES];   /* completion event of the lane's most recent launch */
     uint32_t         *gates;                /* device words user streams wait on while their collective is deferred */
     uint32_t          gate_seq;
 } ucc_tl_nvl_team_t;
@@ -149,6 +158,7 @@ typedef struct ucc_tl_nvl_task {
     cudaEvent_t         event;
     cudaStream_t        stream;     /* stream of the current post */
     int                 captured;   /* posted into a capturing stream: completes immediately */
+    unsigned            lane;       /* lane of the current post */
     /* zero-copy / deferred launch */
     nvl_task_state_t    state;
     ucc_list_link_t     q_elem;
@@ -157,6 +167,10 @@ typedef struct ucc_tl_nvl_task {
     const void         *exp_src; void *exp_dst; size_t exp_src_len, exp_dst_len; /* what is published to the peers */
     uint64_t            cseq;
     int                 published;
+    int                 need_xchg;     /* this post goes through the buffer exchange (0: not zero-copy, or a persistent re-post whose tables are cached) */
+    int                 direct_cached; /* persistent request: the members' buffers were resolved by an earlier post (cached_mode / cached_d) */
+    int                 cached_mode;
+    nvl_direct_t        cached_d;
     int                 gated;         /* the user's stream is parked on gates[gate_idx] until the deferred kernel ran */
     uint32_t            gate_val;
     cudaEvent_t         in_event;
@@ -165,6 +179,18 @@ typedef struct ucc_tl_nvl_task {
     int                 use_push;
     struct { size_t send_off[NVL_MAX_PEERS], send_bytes[NVL_MAX_PEERS], land_off[NVL_MAX_PEERS], recv_off[NVL_MAX_PEERS]; int lookup; } push;
 } ucc_tl_nvl_task_t;
+
+/* tl/nvl part of a ucc_mem_map() handle (tl_nvl_memh.c) */
+typedef struct nvl_memh {
+    uint64_t magic, host_hash, addr, base, off, len;
+    int32_t  pid, dev, has_ipc, imported;
+    cudaIpcMemHandle_t ipc;
+    char    *mapped;   /* address of the segment in THIS process (NULL: unreachable) */
+    void    *opened;   /* cudaIpcOpenMemHandle result to close at unmap */
+} nvl_memh_t;
+ucc_status_t ucc_tl_nvl_mem_map(const ucc_base_context_t *ctx, ucc_mem_map_mode_t mode, void *memh, void *tl_h);
+ucc_status_t ucc_tl_nvl_mem_unmap(const ucc_base_context_t *ctx, ucc_mem_map_mode_t mode, void *tl_h);
+ucc_status_t ucc_tl_nvl_memh_pack(const ucc_base_context_t *ctx, ucc_mem_map_mode_t mode, void *tl_h, void **pack_buffer);
 
 ucc_status_t ucc_tl_nvl_xb_create(ucc_tl_nvl_team_t *team);
 ucc_status_t ucc_tl_nvl_xb_attach(ucc_tl_nvl_team_t *team);

@@ -93,7 +93,7 @@ static ucc_status_t nvl_launch(ucc_tl_nvl_task_t *t, cudaStream_t s)
     case NVL_TASK_SELF_COPY:
         e = t->u.xchg.src_bytes ? nvl_launch_self_copy(t->u.xchg.dst, t->u.xchg.src, t->u.xchg.src_bytes, t->nblocks, t->nthreads, s) : cudaSuccess;
         break;
-    default: e = nvl_launch_barrier(&t->team->dev, s); break;
+    default: e = nvl_launch_barrier(&t->u.red.team, s); break;
     }
     if (e != cudaSuccess) { tl_error(NVL_LIB(t->team), "kernel launch failed: %s", cudaGetErrorString(e)); return UCC_ERR_NO_MESSAGE; }
     return UCC_OK;
@@ -112,12 +112,25 @@ static ucc_status_t launch_ordered(ucc_tl_nvl_task_t *t, cudaStream_t s)
         CUDA_CHECK(cudaEventRecord(t->event, s));
         return UCC_OK;
     }
-    if (team->last_event && team->last_stream != s) CUDA_CHECK(cudaStreamWaitEvent(s, team->last_event, 0));
+    if (team->last_event[t->lane] && team->last_stream[t->lane] != s) CUDA_CHECK(cudaStreamWaitEvent(s, team->last_event[t->lane], 0));
     st = nvl_launch(t, s);
     if (st != UCC_OK) return st;
     CUDA_CHECK(cudaEventRecord(t->event, s));
-    team->last_event = t->event; team->last_stream = s;
+    team->last_event[t->lane] = t->event; team->last_stream[t->lane] = s;
     return UCC_OK;
+}
+
+/* point the task's device descriptor at its lane: a lane is a complete [control | one-shot | p2p | data] image at
+ * lane * lane_stride of every member's heap (and of the multicast mapping), so the kernels need no lane awareness */
+static void task_set_lane(ucc_tl_nvl_task_t *t, unsigned lane)
+{
+    ucc_tl_nvl_team_t *team = t->team;
+    nvl_team_dev_t *d = (t->kind == NVL_TASK_XCHG || t->kind == NVL_TASK_AG_SYMM) ? &t->u.xchg.team : &t->u.red.team;
+    size_t off = (size_t)lane * team->lane_stride;
+    t->lane = lane;
+    if (t->kind == NVL_TASK_SELF_COPY || t->kind == NVL_TASK_P2P) return;
+    for (int p = 0; p < team->dev.size; p++) d->heap[p] = team->dev.heap[p] + off;
+    d->mc_heap = team->dev.mc_heap ? team->dev.mc_heap + off : NULL;
 }
 
 /* every member published its buffers for this collective: pick (identically everywhere) the in-place kernel or
@@ -134,9 +147,53 @@ static ucc_status_t resolve_direct(ucc_tl_nvl_task_t *t)
     }
     if (t->kind == NVL_TASK_XCHG) { t->u.xchg.direct = ok; if (ok) t->u.xchg.d = d; }
     else { t->u.red.direct = ok ? t->want_direct : NVL_DIRECT_NONE; if (ok) t->u.red.d = d; }
+    /* persistent request: the buffers are fixed for the lifetime of the request, so every later post of it (same decision on
+     * every member - they all re-post the same request) launches straight away with these tables: no handle export, no board
+     * round trip, no deferred launch */
+    if (UCC_IS_PERSISTENT(t->super.bargs.args)) { t->direct_cached = 1; t->cached_mode = ok ? 1 : 0; t->cached_d = d; }
     return UCC_OK;
 }
-static inline int task_is_direct(const ucc_tl_nvl_task_t *t) { return t->want_direct && t->team->zcopy; }
+static void apply_cached_direct(ucc_tl_nvl_task_t *t)
+{
+    int ok = t->cached_mode;
+    if (t->kind == NVL_TASK_XCHG) { t->u.xchg.direct = ok; if (ok) t->u.xchg.d = t->cached_d; }
+    else { t->u.red.direct = ok ? t->want_direct : NVL_DIRECT_NONE; if (ok) t->u.red.d = t->cached_d; }
+}
+static inline int task_is_direct(const ucc_tl_nvl_task_t *t) { return t->want_direct && (t->team->zcopy || t->direct_cached); }
+
+/* Registered buffers: when the collective carries GLOBAL memory handles (one imported ucc_mem_map handle per member) for every
+ * side the zero-copy kernel touches, the pointer tables are built right here from the registrations - the per-post exchange is
+ * never used for this request.  Every member evaluates the same handles, flags and sizes, so the outcome is the same everywhere;
+ * a member that cannot reach some segment could break that symmetry, so reachability of ALL segments is required on import
+ * (unreachable -> h->mapped == NULL -> no table, and since the exporter could not produce an IPC handle either, nobody has one). */
+static void memh_direct(ucc_tl_nvl_task_t *t, const ucc_coll_args_t *a, const void *my_src, void *my_dst)
+{
+    ucc_tl_nvl_team_t *team = t->team;
+    const ucc_base_context_t *bctx = team->super.super.context;
+    ucc_rank_t N = UCC_TL_TEAM_SIZE(team), me = UCC_TL_TEAM_RANK(team);
+    int use_src = t->need_src && (a->mask & UCC_COLL_ARGS_FIELD_MEM_MAP_SRC_MEMH) && (a->flags & UCC_COLL_ARGS_FLAG_SRC_MEMH_GLOBAL) && a->src_memh.global_memh;
+    int use_dst = t->need_dst && (a->mask & UCC_COLL_ARGS_FIELD_MEM_MAP_DST_MEMH) && (a->flags & UCC_COLL_ARGS_FLAG_DST_MEMH_GLOBAL) && a->dst_memh.global_memh;
+    nvl_direct_t d;
+    if (!t->want_direct || (t->need_src && !use_src) || (t->need_dst && !use_dst)) return;
+    memset(&d, 0, sizeof(d));
+    for (int side = 0; side < 2; side++) {
+        ucc_mem_map_mem_h *gl = side ? a->dst_memh.global_memh : a->src_memh.global_memh;
+        const char *mine = side ? (const char *)my_dst : (const char *)my_src;
+        nvl_memh_t *hm;
+        size_t off;
+        if (side ? !use_dst : !use_src) continue;
+        hm = (nvl_memh_t *)ucc_mem_map_tl_handle(gl[me], bctx);
+        if (!hm || !hm->mapped || mine < hm->mapped || mine >= hm->mapped + hm->len) return; /* my buffer is not inside my registered segment */
+        off = (size_t)(mine - hm->mapped);
+        if ((uintptr_t)mine & 15) return;
+        for (ucc_rank_t p = 0; p < N; p++) {
+            nvl_memh_t *h = (nvl_memh_t *)ucc_mem_map_tl_handle(gl[p], bctx);
+            if (!h || !h->mapped || off >= h->len || ((uintptr_t)(h->mapped + off) & 15)) return;
+            if (side) d.dst[p] = p == me ? (char *)my_dst : h->mapped + off; else d.src[p] = p == me ? (const char *)my_src : h->mapped + off;
+        }
+    }
+    t->direct_cached = 1; t->cached_mode = 1; t->cached_d = d;
+}
 
 /* head of the launch queue: start it once its buffer exchange (if any) is complete */
 static ucc_status_t try_launch_queued(ucc_tl_nvl_task_t *t)
@@ -145,7 +202,7 @@ static ucc_status_t try_launch_queued(ucc_tl_nvl_task_t *t)
     cudaStream_t s;
     ucc_status_t st;
     if (ucc_list_head(&team->launch_q, ucc_tl_nvl_task_t, q_elem) != t) return UCC_INPROGRESS;
-    if (task_is_direct(t)) {
+    if (t->need_xchg) {
         if (!t->published) t->published = ucc_tl_nvl_xb_publish(team, t->cseq, t->exp_src, t->exp_src_len, t->exp_dst, t->exp_dst_len, 1);
         if (!t->published || !ucc_tl_nvl_xb_ready(team, t->cseq)) return UCC_INPROGRESS;
         st = resolve_direct(t);
@@ -196,14 +253,19 @@ static ucc_status_t nvl_post_on(ucc_tl_nvl_task_t *t, cudaStream_t s)
     t->stream = s; t->captured = 0; t->state = NVL_TASK_LAUNCHED; t->gated = 0; t->published = 0;
     if (cudaStreamIsCapturing(s, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusActive) t->captured = 1;
     ucc_spin_lock(&team->launch_lock);
-    direct = task_is_direct(t);
+    /* lanes advance in post order, which UCC requires to be the same on every member; point-to-point and single-member tasks
+     * involve no team-wide kernel and take no lane */
+    if (t->kind != NVL_TASK_P2P && t->kind != NVL_TASK_SELF_COPY) task_set_lane(t, team->lane_seq++ % team->nlanes);
+    direct = task_is_direct(t) && !t->direct_cached;   /* cached tables: also fine inside a stream capture, nothing to wait for */
+    t->need_xchg = direct;
     if (t->kind == NVL_TASK_XCHG || t->kind == NVL_TASK_AG_SYMM) t->u.xchg.direct = 0; else if (t->kind != NVL_TASK_P2P) t->u.red.direct = NVL_DIRECT_NONE;
+    if (task_is_direct(t) && t->direct_cached) apply_cached_direct(t);
     if (direct) {
         /* the exchange sequence advances on every rank in post order; a capturing stream cannot wait for the
          * peers, so it tells them "not usable" and everybody takes the staged kernel for this one */
         t->cseq = team->xb_seq++;
         t->published = ucc_tl_nvl_xb_publish(team, t->cseq, t->exp_src, t->exp_src_len, t->exp_dst, t->exp_dst_len, !t->captured);
-        if (t->captured) { direct = 0; if (team->xb_mine->consumed < t->cseq + 1) ucc_store_release(&team->xb_mine->consumed, t->cseq + 1); }
+        if (t->captured) { direct = 0; t->need_xchg = 0; if (team->xb_mine->consumed < t->cseq + 1) ucc_store_release(&team->xb_mine->consumed, t->cseq + 1); }
     }
     if (t->captured || t->kind == NVL_TASK_P2P || (ucc_list_is_empty(&team->launch_q) && (!direct || (t->published && ucc_tl_nvl_xb_ready(team, t->cseq))))) {
         st = direct ? resolve_direct(t) : UCC_OK;
@@ -249,8 +311,8 @@ static ucc_status_t nvl_finalize(ucc_coll_task_t *ct)
     if (t->state == NVL_TASK_QUEUED) { /* abandoned before its kernel was launched (timeout / error): release the user's stream */
         ucc_list_del(&t->q_elem); t->state = NVL_TASK_LAUNCHED;
     }
-    if (t->event && team->last_event == t->event) { /* the team still orders the next launch after this event: keep it alive */
-        cudaEvent_t spare = team->order_event; team->order_event = t->event; t->event = spare;
+    if (t->event && team->last_event[t->lane] == t->event) { /* the lane still orders its next launch after this event: keep it alive */
+        cudaEvent_t spare = team->order_event[t->lane]; team->order_event[t->lane] = t->event; t->event = spare;
     }
     ucc_spin_unlock(&team->launch_lock);
     if (t->in_event) cudaEventDestroy(t->in_event);
@@ -267,8 +329,8 @@ static ucc_status_t task_alloc(ucc_base_coll_args_t *b, ucc_base_team_t *b_team,
     ucc_tl_nvl_task_t *t = (ucc_tl_nvl_task_t *)ucc_mpool_get(&ctx->task_mp);
     if (!t) return UCC_ERR_NO_MEMORY;
     ucc_coll_task_init(&t->super, b, b_team);
-    t->team = team; t->event = NULL; t->captured = 0; t->in_event = NULL; t->state = NVL_TASK_LAUNCHED; t->want_direct = 0; t->gated = 0; t->use_push = 0;
-    t->need_src = t->need_dst = 0; t->exp_src = NULL; t->exp_dst = NULL; t->exp_src_len = t->exp_dst_len = 0; t->nblocks_direct = 0;
+    t->team = team; t->event = NULL; t->captured = 0; t->lane = 0; t->in_event = NULL; t->state = NVL_TASK_LAUNCHED; t->want_direct = 0; t->gated = 0; t->use_push = 0;
+    t->need_xchg = 0; t->direct_cached = 0; t->cached_mode = 0; t->need_src = t->need_dst = 0; t->exp_src = NULL; t->exp_dst = NULL; t->exp_src_len = t->exp_dst_len = 0; t->nblocks_direct = 0;
     t->nthreads = (int)ctx->cfg.nthreads;
     t->super.post = nvl_post; t->super.progress = nvl_progress; t->super.finalize = nvl_finalize; t->super.triggered_post = nvl_triggered_post;
     if (cudaEventCreateWithFlags(&t->event, cudaEventDisableTiming) != cudaSuccess) { (void)cudaGetLastError(); ucc_mpool_put(t); return UCC_ERR_NO_RESOURCE; }
@@ -416,7 +478,7 @@ static ucc_status_t red_init(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, u
     /* symmetric user memory (UCC_TL_NVL_USER_SIZE): src and dst sit in the multicast-bound user region of the heap, at the same
      * offset on every member by contract -> reduce in place through the switch, nothing staged, nothing exchanged */
     if ((alg == RED_ALG_TWOSHOT || alg == RED_ALG_NVLS) && r->kind == NVL_RED_ALLREDUCE && team->nvls && ctx->cfg.user_size && nvl_nvls_supports(ndt, nop)) {
-        const char *ub = team->heap + NVL_DATA_OFFSET + ctx->cfg.symmetric_size, *ue = ub + ctx->cfg.user_size;
+        const char *ub = team->heap + team->lane_stride * team->nlanes, *ue = ub + ctx->cfg.user_size;
         const char *s0 = (const char *)src, *d0 = (const char *)dst;
         if (s0 >= ub && s0 + ucc_align_up(bytes, 16) <= ue && d0 >= ub && d0 + bytes <= ue && !(((uintptr_t)s0 | (uintptr_t)d0) & 15)) {
             t->kind = NVL_TASK_REDUCE_SYMM; r->d.src[0] = s0; r->d.dst[0] = (char *)dst; r->use_nvls = 1;
@@ -428,7 +490,7 @@ static ucc_status_t red_init(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, u
     /* reduce_scatter(v) out of a symmetric source (the FSDP / ZeRO gradient shape): every block is reduced in the switch
      * straight into its owner's destination, which may be any local buffer */
     if ((alg == RED_ALG_TWOSHOT || alg == RED_ALG_NVLS) && r->kind == NVL_RED_REDUCE_SCATTER && !inplace && team->nvls && ctx->cfg.user_size && nvl_nvls_supports(ndt, nop)) {
-        const char *ub = team->heap + NVL_DATA_OFFSET + ctx->cfg.symmetric_size, *ue = ub + ctx->cfg.user_size;
+        const char *ub = team->heap + team->lane_stride * team->nlanes, *ue = ub + ctx->cfg.user_size;
         const char *s0 = (const char *)src;
         int aligned = !((uintptr_t)s0 & 15);
         for (ucc_rank_t i = 0; i < N; i++) if ((r->rs_offset[i] * ucc_dt_size(dt)) & 15) aligned = 0;
@@ -454,6 +516,15 @@ static ucc_status_t red_init(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, u
             t->exp_dst = r->kind == NVL_RED_REDUCE_SCATTER ? NULL : dst; t->exp_dst_len = t->exp_dst ? bytes : 0;
         }
     }
+    /* registered buffers make the in-place kernel available without the exchange board (also when it could not be set up) */
+    if ((alg == RED_ALG_TWOSHOT) && !t->want_direct && ctx->cfg.zcopy != UCC_NO && bytes >= ctx->cfg.zcopy_thresh && (a->mask & (UCC_COLL_ARGS_FIELD_MEM_MAP_SRC_MEMH | UCC_COLL_ARGS_FIELD_MEM_MAP_DST_MEMH))) {
+        int mode = NVL_DIRECT_FULL;
+        if (r->kind == NVL_RED_REDUCE_SCATTER) for (ucc_rank_t i = 0; i < N; i++) if ((r->rs_offset[i] * ucc_dt_size(dt)) & 15) mode = NVL_DIRECT_NONE;
+        if (mode) { t->want_direct = mode; t->nblocks_direct = t->nblocks; t->need_src = 1; t->need_dst = r->kind != NVL_RED_REDUCE_SCATTER; t->exp_src = src; t->exp_src_len = bytes;
+                    t->exp_dst = r->kind == NVL_RED_REDUCE_SCATTER ? NULL : dst; t->exp_dst_len = t->exp_dst ? bytes : 0; }
+    }
+    if (t->want_direct && r->kind != NVL_RED_REDUCE) memh_direct(t, a, src, dst);
+    if (t->want_direct && !t->direct_cached && !team->zcopy) t->want_direct = 0;
     *task_p = &t->super;
     return UCC_OK;
 }
@@ -509,7 +580,7 @@ static ucc_status_t xchg_init(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, 
         /* destination in the symmetric user region (same offset on every member by contract): multicast my block straight
          * into everybody's dst - nothing staged, pulled or copied out */
         if (team->nvls && ctx->cfg.user_size && blk && !(blk & 15) && !(((uintptr_t)x.src | (uintptr_t)x.dst) & 15)) {
-            const char *ub = team->heap + NVL_DATA_OFFSET + ctx->cfg.symmetric_size, *ue = ub + ctx->cfg.user_size, *d0 = (const char *)x.dst;
+            const char *ub = team->heap + team->lane_stride * team->nlanes, *ue = ub + ctx->cfg.user_size, *d0 = (const char *)x.dst;
             if (d0 >= ub && d0 + blk * N <= ue) {
                 st = task_alloc(b, b_team, &t);
                 if (st != UCC_OK) return st;
@@ -708,6 +779,7 @@ static ucc_status_t barrier_init(ucc_base_coll_args_t *b, ucc_base_team_t *b_tea
     st = task_alloc(b, b_team, &t);
     if (st != UCC_OK) return st;
     t->kind = NVL_TASK_BARRIER; t->nblocks = 1;
+    memset(&t->u.red, 0, sizeof(t->u.red)); t->u.red.team = ucc_derived_of(b_team, ucc_tl_nvl_team_t)->dev;
     *task_p = &t->super;
     return UCC_OK;
 }

@@ -95,7 +95,10 @@ static void unmap_va(char *va, size_t size) { if (!va) return; ucc_cu.cuMemUnmap
 static ucc_status_t heap_alloc(ucc_tl_nvl_team_t *team, int want_mc)
 {
     ucc_tl_nvl_context_t *ctx = NVL_CTX(team);
-    size_t size = NVL_DATA_OFFSET + ctx->cfg.symmetric_size + ctx->cfg.user_size, gran = 2u << 20;
+    size_t size, gran = 2u << 20;
+    team->nlanes = ctx->cfg.slots;
+    team->lane_stride = ucc_align_up(NVL_DATA_OFFSET + ctx->cfg.symmetric_size, (size_t)2 << 20);
+    size = team->lane_stride * team->nlanes + ctx->cfg.user_size;   /* [lane 0][lane 1]...[user region] */
     if (team->heap_kind == NVL_HEAP_VMM) {
         CUmemAllocationProp prop; size_t g = 0;
         vmm_prop(ctx->dev, &prop);
@@ -117,7 +120,7 @@ static ucc_status_t heap_alloc(ucc_tl_nvl_team_t *team, int want_mc)
         CUDA_CHECK(cudaMalloc((void **)&team->heap, size));
     }
     team->heap_size = size; team->mc_size = size;
-    CUDA_CHECK(cudaMemset(team->heap, 0, NVL_DATA_OFFSET));
+    for (unsigned l = 0; l < team->nlanes; l++) CUDA_CHECK(cudaMemset(team->heap + l * team->lane_stride, 0, NVL_DATA_OFFSET));
     CUDA_CHECK(cudaDeviceSynchronize());
     return UCC_OK;
 }
@@ -146,7 +149,7 @@ static void team_release(ucc_tl_nvl_team_t *team)
     if (team->mc_fd >= 0) { close(team->mc_fd); team->mc_fd = -1; }
     if (team->host_err) { cudaFreeHost(team->host_err); team->host_err = NULL; }
     if (team->gates) { cudaFree(team->gates); team->gates = NULL; }
-    if (team->order_event) { cudaEventDestroy(team->order_event); team->order_event = NULL; }
+    for (unsigned l = 0; l < NVL_MAX_LANES; l++) if (team->order_event[l]) { cudaEventDestroy(team->order_event[l]); team->order_event[l] = NULL; }
     ucc_tl_nvl_xb_release(team);
     if (team->oob_internal) { ucc_internal_oob_finalize(&team->oob); team->oob_internal = 0; }
     free(team->infos); team->infos = NULL; free(team->sync_vals); team->sync_vals = NULL;
@@ -173,7 +176,7 @@ ucc_status_t ucc_tl_nvl_team_create_post(ucc_base_context_t *b_ctx, const ucc_ba
     team->super.super.context = b_ctx; team->super.super.params = *params;
     team->heap_fd = -1; team->mc_fd = -1; team->srv_sock = -1;
     if (N == 1) { /* nothing to share: collectives on CUDA buffers become one copy kernel on the caller's stream */
-        team->self = 1; team->heap_kind = NVL_HEAP_LOCAL;
+        team->self = 1; team->nlanes = 1; team->heap_kind = NVL_HEAP_LOCAL;
         st = team_finish(team);
         if (st != UCC_OK) { team_release(team); free(team); return st; }
         *team_p = &team->super.super;
@@ -278,9 +281,9 @@ static ucc_status_t team_finish(ucc_tl_nvl_team_t *team)
     *team->host_err = 0;
     CUDA_CHECK(cudaMalloc((void **)&team->gates, NVL_GATE_SLOTS * sizeof(uint32_t)));
     CUDA_CHECK(cudaMemset(team->gates, 0, NVL_GATE_SLOTS * sizeof(uint32_t)));
-    CUDA_CHECK(cudaEventCreateWithFlags(&team->order_event, cudaEventDisableTiming));
+    for (unsigned l = 0; l < team->nlanes; l++) CUDA_CHECK(cudaEventCreateWithFlags(&team->order_event[l], cudaEventDisableTiming));
     ucc_list_head_init(&team->launch_q); ucc_spinlock_init(&team->launch_lock);
-    team->last_stream = NULL; team->gate_seq = 0; team->xb_seq = 0;
+    memset(team->last_stream, 0, sizeof(team->last_stream)); memset(team->last_event, 0, sizeof(team->last_event)); team->lane_seq = 0; team->gate_seq = 0; team->xb_seq = 0;
     memset(&team->dev, 0, sizeof(team->dev));
     team->dev.rank = (int)UCC_TL_TEAM_RANK(team); team->dev.size = (int)N;
     for (ucc_rank_t p = 0; p < N; p++) team->dev.heap[p] = team->peer_va[p];
@@ -405,7 +408,7 @@ UCC_EXPORT ucc_status_t ucc_tl_nvl_symm_region(ucc_team_h core_team, void **base
         ucc_tl_nvl_team_t *t = g_teams[i];
         if (!t || t->self || (ucc_team_h)t->super.super.params.team != core_team || UCC_TL_TEAM_SIZE(t) != ucc_team_size_(core_team)) continue;
         if (!NVL_CTX(t)->cfg.user_size) { st = UCC_ERR_NOT_SUPPORTED; continue; }
-        *base = t->heap + NVL_DATA_OFFSET + NVL_CTX(t)->cfg.symmetric_size; *size = NVL_CTX(t)->cfg.user_size;
+        *base = t->heap + t->lane_stride * t->nlanes; *size = NVL_CTX(t)->cfg.user_size;
         if (nvls) *nvls = t->nvls;
         st = UCC_OK; break;
     }

@@ -88,4 +88,5 @@ ucc_status_t ucc_core_addr_exchange(ucc_context_t *context, ucc_oob_coll_t *oob,
 void         ucc_addr_storage_free(ucc_addr_storage_t *s);
 /* component blob of `rank` (ctx rank) or NULL */
 void        *ucc_addr_storage_component_addr(ucc_addr_storage_t *s, ucc_rank_t rank, unsigned long component_id, uint32_t *len);
+void *ucc_mem_map_tl_handle(ucc_mem_map_mem_h memh, const ucc_base_context_t *tl_ctx); /* core/ucc_mem_map.c */
 #endif

@@ -74,6 +74,15 @@ UCC_EXPORT ucc_status_t ucc_mem_map(ucc_context_h ctx, ucc_mem_map_mode_t mode, 
     return UCC_OK;
 }
 
+/* the per-TL part of a handle (what that TL's mem_map returned), for TLs that use registered buffers in their collectives */
+void *ucc_mem_map_tl_handle(ucc_mem_map_mem_h memh, const ucc_base_context_t *tl_ctx)
+{
+    ucc_mem_map_memh_t *h = (ucc_mem_map_memh_t *)memh;
+    if (!h || h->magic != UCC_MEMH_MAGIC || !h->ctx || !h->tl_h) return NULL;
+    for (int i = 0; i < h->ctx->n_tl_ctx; i++) if (&h->ctx->tl_ctx[i]->super == tl_ctx) return h->tl_h[i];
+    return NULL;
+}
+
 UCC_EXPORT ucc_status_t ucc_mem_unmap(ucc_mem_map_mem_h *memh_p)
 {
     ucc_mem_map_memh_t *h;

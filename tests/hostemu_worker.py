@@ -389,6 +389,64 @@ def p2p_active_set():
     print("  active-set p2p ok", flush=True)
 
 
+def registered_buffers():
+    """ucc_mem_map on device buffers + collectives that carry the GLOBAL handles: the zero-copy kernels get the members' buffers
+    from the registrations - here with the exchange board switched OFF (UCC_TL_NVL_ZCOPY would normally need it), so a correct
+    result through the in-place kernel proves the registration path"""
+    U.lib.ucc_mem_map.argtypes = [U.handle, C.c_int, C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_void_p)]
+    U.lib.ucc_mem_map.restype = C.c_int
+    U.lib.ucc_mem_unmap.argtypes = [C.POINTER(C.c_void_p)]
+    n, count = 4, 40000
+    info = C.CDLL(os.path.join(os.environ["UCC_MODULE_DIR"], "libucc_tl_nvl.so")).ucc_tl_nvl_last_launch_info
+    info.restype = C.c_char_p
+    with UccJob(n, env=dict(BASE, UCC_TL_NVL_ZCOPY_THRESH="0", UCC_TL_NVL_ALLREDUCE_ONESHOT_THRESH="0")) as j:
+        team = j.create_team(range(n))
+        seg_src = [Dev(2 * count, fill=0) for _ in range(n)]     # registered segments; the collective uses the second half
+        seg_dst = [Dev(2 * count, fill=0) for _ in range(n)]
+        blobs = {"src": [], "dst": []}
+        keep = []
+        for name, segs in (("src", seg_src), ("dst", seg_dst)):
+            for r in range(n):
+                seg = U.ucc_mem_map_t(segs[r].ptr, 2 * count * 4)
+                params = U.ucc_mem_map_params_t()
+                params.segments, params.n_segments = C.pointer(seg), 1
+                memh, size = C.c_void_p(), C.c_size_t()
+                assert U.lib.ucc_mem_map(j.procs[r].ctx, 0, C.byref(params), C.byref(size), C.byref(memh)) == U.UCC_OK
+                blobs[name].append(C.string_at(memh.value, size.value))
+                keep.append(memh)
+        # every rank imports every member's handle (the application would allgather the blobs)
+        glob = {}
+        for name in ("src", "dst"):
+            for r in range(n):
+                arr = (C.c_void_p * n)()
+                for p in range(n):
+                    b = C.create_string_buffer(blobs[name][p], len(blobs[name][p]))
+                    keep.append(b)
+                    h = C.c_void_p(C.addressof(b))
+                    assert U.lib.ucc_mem_map(j.procs[r].ctx, 1, None, None, C.byref(h)) == U.UCC_OK
+                    arr[p] = h.value
+                glob[(name, r)] = arr
+        for it in range(3):
+            for r in range(n):
+                seg_src[r].a[count:] = rnd(count, 31 * it + r)
+            args = []
+            for r in range(n):
+                a = coll_args("allreduce", dt="float32", mem_type=CUDA, src_ptr=seg_src[r].ptr + count * 4, dst_ptr=seg_dst[r].ptr + count * 4, count_src=count, count_dst=count)
+                a.mask |= U.UCC_COLL_ARGS_FIELD_MEM_MAP_SRC_MEMH | U.UCC_COLL_ARGS_FIELD_MEM_MAP_DST_MEMH
+                a.flags |= U.UCC_COLL_ARGS_FLAG_SRC_MEMH_GLOBAL | U.UCC_COLL_ARGS_FLAG_DST_MEMH_GLOBAL
+                a.mask |= U.UCC_COLL_ARGS_FIELD_FLAGS
+                a.src_memh.global_memh = C.cast(glob[("src", r)], C.POINTER(C.c_void_p))
+                a.dst_memh.global_memh = C.cast(glob[("dst", r)], C.POINTER(C.c_void_p))
+                args.append(a)
+            run(team, args)
+            assert b"zcopy" in info(), info()
+            exp = sum(s.a[count:].copy() for s in seg_src)
+            for r in range(n):
+                assert np.allclose(seg_dst[r].a[count:], exp), ("memh allreduce", it, r)
+                assert np.all(seg_dst[r].a[:count] == 0)
+    print("  registered buffers (ucc_mem_map -> zero-copy without the exchange board) ok", flush=True)
+
+
 def int_avg():
     """AVG on integer datatypes = truncated sum / N, on every reduction kernel"""
     n = 3
@@ -418,6 +476,7 @@ SCENARIOS = {
     "timeout": device_timeout,
     "cross_team": lambda: [cross_team_order(NOZC), cross_team_order(ZC)],
     "p2p": lambda: [p2p_active_set(), int_avg()],
+    "memh": registered_buffers,
 }
 
 if __name__ == "__main__":

@@ -80,6 +80,8 @@ UCC_EP_MAP_FULL, UCC_EP_MAP_STRIDED, UCC_EP_MAP_ARRAY, UCC_EP_MAP_CB = 1, 2, 3, 
  UCC_COLL_ARGS_FLAG_TIMEOUT, UCC_COLL_ARGS_FLAG_MEM_MAPPED_BUFFERS) = [BIT(i) for i in range(8)]
 (UCC_COLL_ARGS_FIELD_FLAGS, UCC_COLL_ARGS_FIELD_TAG, UCC_COLL_ARGS_FIELD_CB, UCC_COLL_ARGS_FIELD_GLOBAL_WORK_BUFFER,
  UCC_COLL_ARGS_FIELD_ACTIVE_SET) = [BIT(i) for i in range(5)]
+UCC_COLL_ARGS_FIELD_MEM_MAP_SRC_MEMH, UCC_COLL_ARGS_FIELD_MEM_MAP_DST_MEMH = BIT(5), BIT(6)
+UCC_COLL_ARGS_FLAG_SRC_MEMH_GLOBAL, UCC_COLL_ARGS_FLAG_DST_MEMH_GLOBAL = BIT(8), BIT(9)
 
 UCC_EE_CUDA_STREAM, UCC_EE_CPU_THREAD = 0, 1
 UCC_EVENT_COLLECTIVE_POST, UCC_EVENT_COLLECTIVE_COMPLETE, UCC_EVENT_COMPUTE_COMPLETE = BIT(0), BIT(1), BIT(2)
