@@ -168,6 +168,8 @@ cudaError_t  nvl_launch_reduce_symm(const nvl_red_args_t *a, int nblocks, int nt
 cudaError_t  nvl_launch_allgather_symm(const nvl_xchg_args_t *a, int nblocks, int nthreads, cudaStream_t s);
 cudaError_t  nvl_launch_exchange(const nvl_xchg_args_t *a, int nblocks, int nthreads, cudaStream_t s);
 cudaError_t  nvl_launch_exchange_push(const nvl_push_args_t *a, int nblocks, int nthreads, cudaStream_t s);
+/* same exchange driven by the TMA engine (cp.async.bulk through shared memory): one-warp CTAs */
+cudaError_t  nvl_launch_exchange_push_bulk(const nvl_push_args_t *a, int nblocks, cudaStream_t s);
 cudaError_t  nvl_launch_barrier(const nvl_team_dev_t *t, cudaStream_t s);
 cudaError_t  nvl_launch_self_copy(void *dst, const void *src, size_t bytes, int nblocks, int nthreads, cudaStream_t s); /* team of one */
 cudaError_t  nvl_launch_ctrl_init(void *heap_base, cudaStream_t s);

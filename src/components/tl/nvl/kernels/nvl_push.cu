@@ -12,6 +12,7 @@
  *
  * Status: written after the round-1 GPU budget was spent; logic checked in the host emulation (tests/emu), not yet run on GPUs. */
 #include "nvl_reduce_impl.cuh"
+#include "nvl_bulk.cuh"
 
 /* grid-strided copy local memory -> (possibly peer) memory, any alignment */
 static __device__ __forceinline__ void push_bytes_grid(char *dst, const char *src, size_t n)
@@ -61,6 +62,50 @@ __global__ void __launch_bounds__(NVL_THREADS_MAX, 2) nvl_exchange_push_kernel(n
     bs.wait_all_blocks(t, 2);
     bs.finish(2);
 }
+
+#ifndef NVL_HOST_EMU
+/* The same exchange with the TMA engine as the data mover (nvl_bulk.cuh): one-warp CTAs, thread 0 of each drives a ring of
+ * shared-memory stages - bulk load of a chunk of my block from local HBM, bulk store of it into the member's destination over
+ * NVLink.  A block whose addresses are not 16-byte aligned (only known on the device for alltoallv, where the receiver
+ * publishes the landing offset) is copied by the warp's threads instead; the barrier protocol is identical either way. */
+static __device__ __forceinline__ void push_job(BulkPipe &pp, char *dst, const char *src, size_t n, int rot)
+{
+    const bool aligned = ((((uintptr_t)dst | (uintptr_t)src) & 15) == 0) && (n & 15) == 0;   /* uniform across the CTA */
+    if (aligned) { if (threadIdx.x == 0) bulk_copy_range(pp, dst, src, n, blockIdx.x, gridDim.x, rot); }
+    else push_bytes_grid(dst, src, n);
+}
+__global__ void __launch_bounds__(32) nvl_exchange_push_bulk_kernel(const __grid_constant__ nvl_push_args_t a)
+{
+    extern __shared__ __align__(128) char bulk_smem[];
+    const nvl_team_dev_t &t = a.team;
+    const int N = t.size, me = t.rank;
+    BlockSync bs; bs.init(t);
+    BulkPipe pp;
+    const char *src = static_cast<const char *>(a.src);
+    const size_t tbl = (size_t)blockIdx.x * NVL_MAX_PEERS * sizeof(uint64_t);
+    if (threadIdx.x == 0) pp.init(bulk_smem);
+    if (a.lookup && (int)threadIdx.x < N) reinterpret_cast<volatile uint64_t *>(data_of(t, me) + tbl)[threadIdx.x] = (uint64_t)a.recv_off[threadIdx.x];
+    bs.barrier(t, 1);
+    for (int i = 1; i < N; i++) {
+        int p = me + i; if (p >= N) p -= N;
+        if (!a.send_bytes[p]) continue;
+        const size_t land = a.lookup ? (size_t) * reinterpret_cast<volatile const uint64_t *>(data_of(t, p) + tbl + (size_t)me * 8) : a.land_off[p];
+        push_job(pp, a.dst_of[p] + land, src + a.send_off[p], a.send_bytes[p], i);
+    }
+    if (a.send_bytes[me] && a.dst_of[me] + a.land_off[me] != src + a.send_off[me]) push_job(pp, a.dst_of[me] + a.land_off[me], src + a.send_off[me], a.send_bytes[me], 0);
+    if (threadIdx.x == 0) { bulk_wait_all(); fence_proxy_async(); fence_sys(); }   /* my bulk stores have landed before anybody sees the flag */
+    bs.signal(t, 2);
+    bs.wait_all_blocks(t, 2);
+    bs.finish(2);
+}
+extern "C" cudaError_t nvl_launch_exchange_push_bulk(const nvl_push_args_t *a, int nblocks, cudaStream_t s)
+{
+    static int attr_set = 0;
+    if (!attr_set) { cudaError_t e = cudaFuncSetAttribute(nvl_exchange_push_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NVL_BULK_SMEM); if (e != cudaSuccess) return e; attr_set = 1; }
+    nvl_exchange_push_bulk_kernel<<<nblocks, 32, NVL_BULK_SMEM, s>>>(*a);
+    return cudaGetLastError();
+}
+#endif
 
 #ifndef NVL_HOST_EMU /* the host emulation calls the kernel directly */
 extern "C" cudaError_t nvl_launch_exchange_push(const nvl_push_args_t *a, int nblocks, int nthreads, cudaStream_t s)

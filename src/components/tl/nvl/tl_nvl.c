@@ -27,6 +27,11 @@ ucc_config_field_t ucc_tl_nvl_context_config_table[] = {
     {"USER_SIZE", "0", "Size of a symmetric USER region appended to every team heap (bound to the NVLS multicast object like the rest of the heap). "
      "Buffers placed there at the same offset on every member (ucc_tl_nvl_symm_region) are reduced in place through the switch: no staging, no copy-out",
      ucc_offsetof(ucc_tl_nvl_context_config_t, user_size), UCC_CONFIG_TYPE_MEMUNITS},
+    {"BULK", "try", "Move the blocks of the zero-copy push exchange (allgather(v) / alltoall(v) algorithm `push`) with TMA bulk copies (cp.async.bulk through "
+     "shared memory, one elected thread per one-warp thread block) instead of per-thread 16-byte loads and stores", ucc_offsetof(ucc_tl_nvl_context_config_t, bulk), UCC_CONFIG_TYPE_TERNARY},
+    {"BULK_THRESH", "1M", "Total bytes from which the bulk-copy kernel is used", ucc_offsetof(ucc_tl_nvl_context_config_t, bulk_thresh), UCC_CONFIG_TYPE_MEMUNITS},
+    {"BULK_CTAS", "16", "Thread blocks (one warp each, 192 KB of shared memory) of a bulk-copy kernel: the SM budget of the collective",
+     ucc_offsetof(ucc_tl_nvl_context_config_t, bulk_ctas), UCC_CONFIG_TYPE_UINT},
     {"SLOTS", "1", "Independent collective lanes per team (reference tl/cuda MAX_CONCURRENT): consecutive collectives use consecutive lanes and, when "
      "posted on different streams, overlap.  Every lane has its own control block, one-shot slots and SYMMETRIC_SIZE of staging space; one "
      "kernel may use at most (2 x SMs) / SLOTS thread blocks so that all lanes stay co-resident", ucc_offsetof(ucc_tl_nvl_context_config_t, slots), UCC_CONFIG_TYPE_UINT},

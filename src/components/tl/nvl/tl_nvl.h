@@ -44,6 +44,9 @@ typedef struct ucc_tl_nvl_context_config {
     int      zcopy;            /* ternary: read / write the members' user buffers in place (CUDA IPC) */
     size_t   zcopy_thresh;     /* ... for messages of at least this size */
     size_t   user_size;        /* symmetric USER region appended to every team heap (0: none), see ucc_tl_nvl_symm_region() */
+    int      bulk;             /* ternary: TMA bulk copies (cp.async.bulk) as the data mover of the zero-copy push exchange */
+    size_t   bulk_thresh;
+    unsigned bulk_ctas;        /* one-warp CTAs of a bulk-copy kernel */
     unsigned slots;            /* independent collective lanes per team (reference tl/cuda MAX_CONCURRENT): collectives on different lanes may overlap */
 } ucc_tl_nvl_context_config_t;
 
@@ -54,7 +57,7 @@ typedef struct ucc_tl_nvl_context_config {
 #define NVL_IPC_CACHE_MAX 64
 typedef enum { NVL_XB_NONE = 0, NVL_XB_EMPTY, NVL_XB_RAW, NVL_XB_IPC } nvl_xb_kind_t;
 typedef struct nvl_xb_buf { int32_t kind; int32_t pad; uint64_t base, off, len, alloc_len; cudaIpcMemHandle_t handle; } nvl_xb_buf_t;
-typedef struct nvl_xb_entry { uint64_t seq; nvl_xb_buf_t src, dst; } nvl_xb_entry_t;
+typedef struct nvl_xb_entry { uint64_t seq; nvl_xb_buf_t src, dst; uint64_t aux[NVL_MAX_PEERS]; /* alltoallv: byte offset of source p's block inside my dst */ } nvl_xb_entry_t;
 typedef struct nvl_xb_seg { uint64_t consumed; uint64_t pad[7]; nvl_xb_entry_t e[NVL_XB_SLOTS]; } nvl_xb_seg_t;
 typedef struct nvl_ipc_cache { unsigned n; struct { uint64_t base; cudaIpcMemHandle_t handle; void *mapped; } e[NVL_IPC_CACHE_MAX]; } nvl_ipc_cache_t;
 
@@ -176,8 +179,10 @@ typedef struct ucc_tl_nvl_task {
     cudaEvent_t         in_event;
     int                 nblocks_direct;
     /* zero-copy push exchange (kernels/nvl_push.cu): used instead of the pull kernel when the destinations resolved */
+    int                 use_bulk;      /* push exchange driven by the TMA engine (nvl_exchange_push_bulk_kernel) */
+    int                 use_ce;        /* push exchange executed by the copy engines (cudaMemcpyAsync between two barrier kernels) */
     int                 use_push;
-    struct { size_t send_off[NVL_MAX_PEERS], send_bytes[NVL_MAX_PEERS], land_off[NVL_MAX_PEERS], recv_off[NVL_MAX_PEERS]; int lookup; } push;
+    struct { size_t send_off[NVL_MAX_PEERS], send_bytes[NVL_MAX_PEERS], land_off[NVL_MAX_PEERS], recv_off[NVL_MAX_PEERS], peer_land[NVL_MAX_PEERS]; int lookup; } push;
 } ucc_tl_nvl_task_t;
 
 /* tl/nvl part of a ucc_mem_map() handle (tl_nvl_memh.c) */
@@ -196,9 +201,9 @@ ucc_status_t ucc_tl_nvl_xb_create(ucc_tl_nvl_team_t *team);
 ucc_status_t ucc_tl_nvl_xb_attach(ucc_tl_nvl_team_t *team);
 void         ucc_tl_nvl_xb_unlink(ucc_tl_nvl_team_t *team);
 void         ucc_tl_nvl_xb_release(ucc_tl_nvl_team_t *team);
-int          ucc_tl_nvl_xb_publish(ucc_tl_nvl_team_t *team, uint64_t cseq, const void *src, size_t src_len, void *dst, size_t dst_len, int usable);
+int          ucc_tl_nvl_xb_publish(ucc_tl_nvl_team_t *team, uint64_t cseq, const void *src, size_t src_len, void *dst, size_t dst_len, int usable, const size_t *aux);
 int          ucc_tl_nvl_xb_ready(ucc_tl_nvl_team_t *team, uint64_t cseq);
-int          ucc_tl_nvl_xb_resolve(ucc_tl_nvl_team_t *team, uint64_t cseq, int need_src, int need_dst, int need_align, const void *my_src, void *my_dst, nvl_direct_t *d);
+int          ucc_tl_nvl_xb_resolve(ucc_tl_nvl_team_t *team, uint64_t cseq, int need_src, int need_dst, int need_align, const void *my_src, void *my_dst, nvl_direct_t *d, size_t *aux_for_me);
 
 #define NVL_CTX(_team) ucc_derived_of((_team)->super.super.context, ucc_tl_nvl_context_t)
 extern ucc_tl_iface_t ucc_tl_nvl;

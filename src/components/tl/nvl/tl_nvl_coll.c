@@ -50,7 +50,7 @@ static void note_launch(const ucc_tl_nvl_task_t *t)
     case NVL_TASK_REDUCE_PIPE: k = "nvls_pipe"; break;
     case NVL_TASK_REDUCE_SYMM: k = "nvls_symm_inplace"; break;
     case NVL_TASK_AG_SYMM: k = "allgather_symm_mc"; break;
-    case NVL_TASK_XCHG: k = (t->use_push && t->u.xchg.direct) ? "exchange_push" : (t->u.xchg.direct ? "exchange_pull_zcopy" : (t->u.xchg.use_mc ? "exchange_nvls" : (t->u.xchg.ring ? "exchange_ring" : "exchange_pull_staged"))); break;
+    case NVL_TASK_XCHG: k = (t->use_push && t->u.xchg.direct) ? (t->use_ce ? "exchange_push_copy_engine" : (t->use_bulk ? "exchange_push_bulk(tma)" : "exchange_push")) : (t->u.xchg.direct ? "exchange_pull_zcopy" : (t->u.xchg.use_mc ? "exchange_nvls" : (t->u.xchg.ring ? "exchange_ring" : "exchange_pull_staged"))); break;
     case NVL_TASK_SELF_COPY: k = "self_copy"; break;
     case NVL_TASK_P2P: k = t->u.p2p.send ? "p2p_send" : "p2p_recv"; nb = nvl_p2p_lanes(t->u.p2p.bytes); break;
     default: nb = 1; break;
@@ -86,7 +86,22 @@ static ucc_status_t nvl_launch(ucc_tl_nvl_task_t *t, cudaStream_t s)
             }
             pa.lookup = t->push.lookup;
             /* (every member takes this branch or none: `direct` is decided from what all of them published) */
-            e = nvl_launch_exchange_push(&pa, t->nblocks, t->nthreads, s);
+            if (t->use_ce) {
+                /* copy-engine variant (reference tl/cuda alltoallv_ce.c:202-439: cudaMemcpyAsync per peer after an IPC handle
+                 * exchange and a host barrier): barrier kernel (every member's stream reached the collective: its dst may be
+                 * written) -> one DMA per peer, straight into the mapped destinations; no SM moves a byte -> barrier kernel
+                 * (everything has landed).  The landing offsets of alltoallv travelled with the buffer exchange (peer_land). */
+                e = nvl_launch_barrier(&t->u.xchg.team, s);
+                for (int i = 1; i <= pa.team.size && e == cudaSuccess; i++) {
+                    int p = (pa.team.rank + i) % pa.team.size;
+                    size_t land = pa.lookup ? t->push.peer_land[p] : pa.land_off[p];
+                    if (!pa.send_bytes[p] || pa.dst_of[p] + land == (const char *)pa.src + pa.send_off[p]) continue;
+                    e = cudaMemcpyAsync(pa.dst_of[p] + land, (const char *)pa.src + pa.send_off[p], pa.send_bytes[p], cudaMemcpyDeviceToDevice, s);
+                }
+                if (e == cudaSuccess) e = nvl_launch_barrier(&t->u.xchg.team, s);
+                break;
+            }
+            e = t->use_bulk ? nvl_launch_exchange_push_bulk(&pa, t->nblocks, s) : nvl_launch_exchange_push(&pa, t->nblocks, t->nthreads, s);
         } else e = nvl_launch_exchange(&t->u.xchg, t->nblocks, t->nthreads, s);
         break;
     case NVL_TASK_P2P: e = nvl_launch_p2p(&t->u.p2p, t->nthreads, s); break;
@@ -138,7 +153,7 @@ static void task_set_lane(ucc_tl_nvl_task_t *t, unsigned lane)
 static ucc_status_t resolve_direct(ucc_tl_nvl_task_t *t)
 {
     nvl_direct_t d;
-    int ok = ucc_tl_nvl_xb_resolve(t->team, t->cseq, t->need_src, t->need_dst, t->kind != NVL_TASK_XCHG, t->exp_src, t->exp_dst, &d);
+    int ok = ucc_tl_nvl_xb_resolve(t->team, t->cseq, t->need_src, t->need_dst, t->kind != NVL_TASK_XCHG, t->exp_src, t->exp_dst, &d, (t->kind == NVL_TASK_XCHG && t->use_push) ? t->push.peer_land : NULL);
     tl_debug(NVL_LIB(t->team), "exchange %lu: %s (src %d dst %d)", (unsigned long)t->cseq, ok > 0 ? "zero-copy" : (ok ? "MAPPING FAILED" : "staged"), t->need_src, t->need_dst);
     if (ok < 0) {
         tl_error(NVL_LIB(t->team), "cannot map a peer's buffer for the zero-copy kernel (the peers will run it): failing the collective; "
@@ -203,7 +218,7 @@ static ucc_status_t try_launch_queued(ucc_tl_nvl_task_t *t)
     ucc_status_t st;
     if (ucc_list_head(&team->launch_q, ucc_tl_nvl_task_t, q_elem) != t) return UCC_INPROGRESS;
     if (t->need_xchg) {
-        if (!t->published) t->published = ucc_tl_nvl_xb_publish(team, t->cseq, t->exp_src, t->exp_src_len, t->exp_dst, t->exp_dst_len, 1);
+        if (!t->published) t->published = ucc_tl_nvl_xb_publish(team, t->cseq, t->exp_src, t->exp_src_len, t->exp_dst, t->exp_dst_len, 1, (t->kind == NVL_TASK_XCHG && t->use_push) ? t->push.recv_off : NULL);
         if (!t->published || !ucc_tl_nvl_xb_ready(team, t->cseq)) return UCC_INPROGRESS;
         st = resolve_direct(t);
         if (st != UCC_OK) { ucc_list_del(&t->q_elem); t->state = NVL_TASK_LAUNCHED; return st; }
@@ -264,7 +279,7 @@ static ucc_status_t nvl_post_on(ucc_tl_nvl_task_t *t, cudaStream_t s)
         /* the exchange sequence advances on every rank in post order; a capturing stream cannot wait for the
          * peers, so it tells them "not usable" and everybody takes the staged kernel for this one */
         t->cseq = team->xb_seq++;
-        t->published = ucc_tl_nvl_xb_publish(team, t->cseq, t->exp_src, t->exp_src_len, t->exp_dst, t->exp_dst_len, !t->captured);
+        t->published = ucc_tl_nvl_xb_publish(team, t->cseq, t->exp_src, t->exp_src_len, t->exp_dst, t->exp_dst_len, !t->captured, (t->kind == NVL_TASK_XCHG && t->use_push) ? t->push.recv_off : NULL);
         if (t->captured) { direct = 0; t->need_xchg = 0; if (team->xb_mine->consumed < t->cseq + 1) ucc_store_release(&team->xb_mine->consumed, t->cseq + 1); }
     }
     if (t->captured || t->kind == NVL_TASK_P2P || (ucc_list_is_empty(&team->launch_q) && (!direct || (t->published && ucc_tl_nvl_xb_ready(team, t->cseq))))) {
@@ -329,7 +344,7 @@ static ucc_status_t task_alloc(ucc_base_coll_args_t *b, ucc_base_team_t *b_team,
     ucc_tl_nvl_task_t *t = (ucc_tl_nvl_task_t *)ucc_mpool_get(&ctx->task_mp);
     if (!t) return UCC_ERR_NO_MEMORY;
     ucc_coll_task_init(&t->super, b, b_team);
-    t->team = team; t->event = NULL; t->captured = 0; t->lane = 0; t->in_event = NULL; t->state = NVL_TASK_LAUNCHED; t->want_direct = 0; t->gated = 0; t->use_push = 0;
+    t->team = team; t->event = NULL; t->captured = 0; t->lane = 0; t->in_event = NULL; t->state = NVL_TASK_LAUNCHED; t->want_direct = 0; t->gated = 0; t->use_push = 0; t->use_bulk = 0; t->use_ce = 0;
     t->need_xchg = 0; t->direct_cached = 0; t->cached_mode = 0; t->need_src = t->need_dst = 0; t->exp_src = NULL; t->exp_dst = NULL; t->exp_src_len = t->exp_dst_len = 0; t->nblocks_direct = 0;
     t->nthreads = (int)ctx->cfg.nthreads;
     t->super.post = nvl_post; t->super.progress = nvl_progress; t->super.finalize = nvl_finalize; t->super.triggered_post = nvl_triggered_post;
@@ -721,8 +736,26 @@ static ucc_status_t xchg_init_push(ucc_base_coll_args_t *b, ucc_base_team_t *b_t
     /* alltoallv: one landing-offset table per block at the start of the data region */
     if (t->push.lookup && (size_t)t->nblocks * NVL_MAX_PEERS * sizeof(uint64_t) > ctx->cfg.symmetric_size) { (*task_p)->finalize(*task_p); *task_p = NULL; return UCC_ERR_NOT_SUPPORTED; }
     t->use_push = 1;
+    /* data mover: the TMA engine for big transfers (the choice may only depend on what every member knows - sizes of the
+     * v-collectives are private, those always take it) */
+    { size_t total = 0; int symmetric = ct == UCC_COLL_TYPE_ALLGATHER || ct == UCC_COLL_TYPE_ALLTOALL || ct == UCC_COLL_TYPE_ALLGATHERV;
+      for (ucc_rank_t p = 0; p < N; p++) total += x->pull_bytes[p];
+      t->use_bulk = ctx->cfg.bulk != UCC_NO && (symmetric ? total >= ctx->cfg.bulk_thresh : 1);
+      if (t->use_bulk) t->nblocks = (int)ucc_max(1u, ucc_min(ctx->cfg.bulk_ctas, ctx->cfg.max_blocks)); }
     t->want_direct = NVL_DIRECT_FULL; t->need_src = 0; t->need_dst = 1;
     t->exp_src = NULL; t->exp_src_len = 0; t->exp_dst = x->dst; t->exp_dst_len = dst_len;
+    return UCC_OK;
+}
+
+/* copy-engine push exchange: same buffer resolution as `push`, the copies are DMAs issued by the host (see nvl_launch) */
+static ucc_status_t xchg_init_ce(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, ucc_coll_task_t **task_p)
+{
+    ucc_tl_nvl_task_t *t;
+    ucc_status_t st = xchg_init_push(b, b_team, task_p);
+    if (st != UCC_OK) return st;
+    t = ucc_derived_of(*task_p, ucc_tl_nvl_task_t);
+    if (t->kind != NVL_TASK_XCHG) return UCC_OK;
+    t->use_ce = 1; t->use_bulk = 0; t->nblocks = 1;
     return UCC_OK;
 }
 
@@ -810,9 +843,11 @@ static const nvl_alg_t algs_xchg_mc[] = {{"pull", "stage once, every peer pulls 
 static const nvl_alg_t algs_ag[] = {{"pull", "stage once, every peer pulls its part over NVLink", xchg_init},
     {"nvls", "multicast the own block into every member's heap with multimem.st, copy out locally", xchg_init_nvls},
     {"ring", "N-1 neighbour-to-neighbour pull steps through the heaps, one kernel", xchg_init_ring},
-    {"push", "zero-copy push: every rank stores its block straight into the members' mapped destinations (opt-in, not yet measured)", xchg_init_push}, {NULL}};
+    {"push", "zero-copy push: every rank stores its block straight into the members' mapped destinations (TMA bulk copies from BULK_THRESH)", xchg_init_push},
+    {"ce", "zero-copy push by the copy engines: cudaMemcpyAsync into the members' mapped destinations between two barrier kernels", xchg_init_ce}, {NULL}};
 static const nvl_alg_t algs_a2a[] = {{"pull", "stage once, every peer pulls its part over NVLink", xchg_init},
-    {"push", "zero-copy push: every rank stores block p straight into member p's mapped destination; alltoallv looks the landing offset up in a table the receiver publishes on the device (opt-in, not yet measured)", xchg_init_push}, {NULL}};
+    {"push", "zero-copy push: every rank stores block p straight into member p's mapped destination; alltoallv looks the landing offset up in a table the receiver publishes on the device", xchg_init_push},
+    {"ce", "zero-copy push by the copy engines (reference ALLTOALL_USE_COPY_ENGINE): one cudaMemcpyAsync per peer between two barrier kernels", xchg_init_ce}, {NULL}};
 static const nvl_alg_t algs_barrier[] = {{"flags", "flag exchange in peer memory", barrier_init}, {NULL}};
 static const nvl_alg_t *const nvl_algs[UCC_COLL_TYPE_NUM] = {
     algs_ag, algs_ag, algs_allreduce, algs_a2a, algs_a2a, algs_barrier, algs_xchg_mc, algs_barrier, algs_barrier,

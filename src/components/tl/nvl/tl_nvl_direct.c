@@ -76,7 +76,7 @@ static void export_buf(ucc_tl_nvl_team_t *team, const void *ptr, size_t len, nvl
 }
 
 /* returns 0 when the slot is still in use by a slow peer (caller retries later) */
-int ucc_tl_nvl_xb_publish(ucc_tl_nvl_team_t *team, uint64_t cseq, const void *src, size_t src_len, void *dst, size_t dst_len, int usable)
+int ucc_tl_nvl_xb_publish(ucc_tl_nvl_team_t *team, uint64_t cseq, const void *src, size_t src_len, void *dst, size_t dst_len, int usable, const size_t *aux)
 {
     ucc_rank_t N = UCC_TL_TEAM_SIZE(team), me = UCC_TL_TEAM_RANK(team);
     nvl_xb_entry_t *e = &team->xb_mine->e[cseq % NVL_XB_SLOTS];
@@ -84,6 +84,7 @@ int ucc_tl_nvl_xb_publish(ucc_tl_nvl_team_t *team, uint64_t cseq, const void *sr
         for (ucc_rank_t p = 0; p < N; p++) if (p != me && ucc_load_acquire(&team->xb[p]->consumed) + NVL_XB_SLOTS <= cseq) return 0;
     if (usable) { export_buf(team, src, src_len, &e->src); export_buf(team, dst, dst_len, &e->dst); }
     else { memset(&e->src, 0, sizeof(e->src)); memset(&e->dst, 0, sizeof(e->dst)); e->src.kind = e->dst.kind = NVL_XB_NONE; }
+    for (ucc_rank_t p = 0; p < N && p < NVL_MAX_PEERS; p++) e->aux[p] = aux ? (uint64_t)aux[p] : 0;
     ucc_store_release(&e->seq, cseq + 1);
     return 1;
 }
@@ -126,11 +127,12 @@ static char *import_buf(ucc_tl_nvl_team_t *team, ucc_rank_t p, const nvl_xb_buf_
 /* all members published: decide (identically on every rank) whether the buffers can be used in place and map
  * them.  need_src / need_dst say which sides the kernel touches remotely.  Marks the entries consumed.
  * Returns 1 = in place, 0 = every member stages (symmetric decision), -1 = local mapping failure (the collective must fail). */
-int ucc_tl_nvl_xb_resolve(ucc_tl_nvl_team_t *team, uint64_t cseq, int need_src, int need_dst, int need_align, const void *my_src, void *my_dst, nvl_direct_t *d)
+int ucc_tl_nvl_xb_resolve(ucc_tl_nvl_team_t *team, uint64_t cseq, int need_src, int need_dst, int need_align, const void *my_src, void *my_dst, nvl_direct_t *d, size_t *aux_for_me)
 {
     ucc_rank_t N = UCC_TL_TEAM_SIZE(team), me = UCC_TL_TEAM_RANK(team);
     int ok = 1;
     memset(d, 0, sizeof(*d));
+    if (aux_for_me) for (ucc_rank_t p = 0; p < N; p++) aux_for_me[p] = (size_t)team->xb[p]->e[cseq % NVL_XB_SLOTS].aux[me];
     for (ucc_rank_t p = 0; p < N && ok; p++) {
         const nvl_xb_entry_t *e = &team->xb[p]->e[cseq % NVL_XB_SLOTS];
         if (need_src && e->src.kind != NVL_XB_EMPTY && e->src.kind != NVL_XB_RAW && e->src.kind != NVL_XB_IPC) ok = 0;

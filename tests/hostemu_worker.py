@@ -470,6 +470,7 @@ SCENARIOS = {
     "colls_staged": lambda: other_colls(NOZC),
     "colls_zcopy": lambda: other_colls(ZC),
     "colls_push": lambda: other_colls(ZC, "allgather:cuda:inf:@push#allgatherv:cuda:inf:@push#alltoall:cuda:inf:@push#alltoallv:cuda:inf:@push#reduce_scatter:cuda:inf:@oneshot#reduce_scatterv:cuda:inf:@oneshot"),
+    "colls_ce": lambda: other_colls(ZC, "allgather:cuda:inf:@ce#allgatherv:cuda:inf:@ce#alltoall:cuda:inf:@ce#alltoallv:cuda:inf:@ce"),
     "colls_ring": lambda: other_colls(NOZC, "allgather:cuda:inf:@ring#allgatherv:cuda:inf:@ring#reduce_scatter:cuda:inf:@ring#reduce_scatterv:cuda:inf:@ring"),
     "misc": lambda: [persistent_and_teams(), asymmetric_memory()],
     "triggered": lambda: [triggered(NOZC), triggered(ZC)],
