@@ -119,6 +119,21 @@ tsan:
 	$(MAKE) core CC=/usr/bin/gcc BUILD=build-tsan/obj OUT=build-tsan/lib BINDIR=build-tsan/bin \
 	  EXTRA_CFLAGS="-fsanitize=thread -fno-omit-frame-pointer -O1" LDFLAGS="-shared -fsanitize=thread -lpthread -ldl -lrt -lm"
 
+# ---- install: headers, libraries, plugin modules, tools, pkg-config file and CMake package (what a consumer of
+#      openucx/ucc finds after `make install`: include/ucc/api/*.h, lib/libucc.so, lib/ucc/*.so, lib/pkgconfig/ucc.pc, lib/cmake/ucc) ----
+PREFIX  ?= /usr/local
+VERSION := $(shell sed -n 's/.*UCC_API_MAJOR *\([0-9][0-9]*\).*/\1/p' include/ucc/api/ucc_version.h | head -1).$(shell sed -n 's/.*UCC_API_MINOR *\([0-9][0-9]*\).*/\1/p' include/ucc/api/ucc_version.h | head -1).0
+.PHONY: install
+install: core tools
+	@mkdir -p $(PREFIX)/include/ucc/api $(PREFIX)/lib/ucc $(PREFIX)/lib/pkgconfig $(PREFIX)/lib/cmake/ucc $(PREFIX)/bin
+	cp include/ucc/api/*.h $(PREFIX)/include/ucc/api/
+	cp $(OUT)/libucc.so $(PREFIX)/lib/
+	@if ls $(MODDIR)/*.so > /dev/null 2>&1; then cp $(MODDIR)/*.so $(PREFIX)/lib/ucc/; fi
+	@if ls $(BINDIR)/* > /dev/null 2>&1; then cp $(BINDIR)/* $(PREFIX)/bin/; fi
+	sed -e 's|@PREFIX@|$(abspath $(PREFIX))|g' -e 's|@VERSION@|$(VERSION)|g' ucc.pc.in > $(PREFIX)/lib/pkgconfig/ucc.pc
+	sed -e 's|@VERSION@|$(VERSION)|g' cmake/ucc-config.cmake.in > $(PREFIX)/lib/cmake/ucc/ucc-config.cmake
+	sed -e 's|@VERSION@|$(VERSION)|g' cmake/ucc-config-version.cmake.in > $(PREFIX)/lib/cmake/ucc/ucc-config-version.cmake
+
 clean:
 	rm -rf $(BUILD) $(OUT) $(BINDIR) build-asan build-tsan
 

@@ -75,7 +75,7 @@ static __device__ __forceinline__ void store_any16(char *d, uint4 x, size_t nbyt
 static __device__ void exchange_ring(const nvl_xchg_args_t &a, BlockSync &bs)
 {
     const nvl_team_dev_t &t = a.team;
-    const int N = t.size, me = t.rank, L = (me + N - 1) % N;
+    const int N = t.size, me = t.rank, pos = a.ring_pos, L = a.ring_order[(pos + N - 1) % N];   /* my left neighbour ON THE RING (link-aware order) */
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (size_t)gridDim.x * blockDim.x;
     char *mine = data_of(t, me) + NVL_XCHG_TABLE_BYTES;
     const char *left = data_of(t, L) + NVL_XCHG_TABLE_BYTES;
@@ -94,7 +94,7 @@ static __device__ void exchange_ring(const nvl_xchg_args_t &a, BlockSync &bs)
         }
     }
     for (int s = 0; s + 1 < N; s++) {
-        const int c = (me - 1 - s + 2 * N) % N;
+        const int c = a.ring_order[(pos - 1 - s + 2 * N) % N];   /* the block that has travelled s + 1 hops towards me */
         const size_t n = a.pull_bytes[c], nv = (n + 15) / 16;
         char *d = static_cast<char *>(a.dst) + a.dst_off[c];
         bs.barrier(t, (uint32_t)s + 1);

@@ -117,6 +117,7 @@ typedef struct nvl_xchg_args {
     int            use_mc;       /* NVLS push: phase A multimem.st's my bytes to offset push_off of EVERY heap, phase B reads my own heap */
     size_t         push_off;
     int            ring;         /* allgather(v) over neighbour links only: pull_off[] is the common heap layout, N-1 pull steps */
+    int            ring_order[NVL_MAX_PEERS], ring_pos; /* topology-aware visit order of the ring (ring_order[ring_pos] == rank) */
     int            direct;       /* pull from the peers' user buffers (d.src[p]) instead of their staged copies */
     nvl_direct_t   d;
 } nvl_xchg_args_t;

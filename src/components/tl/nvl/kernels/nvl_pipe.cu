@@ -87,7 +87,7 @@ template <typename T> static __device__ __forceinline__ void pipe_stage(const nv
 template <typename T, int OP> static __device__ __forceinline__ void pipe_reduce(const nvl_red_args_t &a, const SlicePlan &pl, const PipeGeom &g, int k, int rtid, int rnt)
 {
     constexpr int E = 16 / sizeof(T);
-    constexpr int U = 8;
+    constexpr int U = NVL_BW_U;
     const int me = a.team.rank;
     const float inv_n = 1.0f / (float)a.team.size;
     size_t e0, j0, j1; chunk_range<T>(pl, g, k, e0, j0, j1);

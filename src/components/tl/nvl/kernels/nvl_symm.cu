@@ -19,7 +19,7 @@ template <typename T, int OP>
 static __device__ __forceinline__ void symm_body(const nvl_red_args_t &a, BlockSync &bs, const SlicePlan &pl)
 {
     constexpr int E = 16 / sizeof(T);
-    constexpr int U = 8;
+    constexpr int U = NVL_BW_U;
     const nvl_team_dev_t &t = a.team;
     const int N = t.size, me = t.rank;
     const bool rs = a.kind == NVL_RED_REDUCE_SCATTER;   /* reduce_scatter(v): only src is symmetric, my block goes to the local a.dst */

@@ -27,6 +27,9 @@ ucc_config_field_t ucc_tl_nvl_context_config_table[] = {
     {"USER_SIZE", "0", "Size of a symmetric USER region appended to every team heap (bound to the NVLS multicast object like the rest of the heap). "
      "Buffers placed there at the same offset on every member (ucc_tl_nvl_symm_region) are reduced in place through the switch: no staging, no copy-out",
      ucc_offsetof(ucc_tl_nvl_context_config_t, user_size), UCC_CONFIG_TYPE_MEMUNITS},
+    {"REQUIRE_NVLINK", "try", "Refuse teams in which some pair of GPUs has no NVLink path (such a team goes to the next TL): y = also when the topology "
+     "could not be determined, try = only when the sysinfo graph says so, n = accept any pair with CUDA peer access", ucc_offsetof(ucc_tl_nvl_context_config_t, require_nvlink), UCC_CONFIG_TYPE_TERNARY},
+    {"RING_REVERSE", "n", "Walk rings in the opposite direction (test knob for topology-ordered rings)", ucc_offsetof(ucc_tl_nvl_context_config_t, ring_reverse), UCC_CONFIG_TYPE_BOOL},
     {"BULK", "try", "Move the blocks of the zero-copy push exchange (allgather(v) / alltoall(v) algorithm `push`) with TMA bulk copies (cp.async.bulk through "
      "shared memory, one elected thread per one-warp thread block) instead of per-thread 16-byte loads and stores", ucc_offsetof(ucc_tl_nvl_context_config_t, bulk), UCC_CONFIG_TYPE_TERNARY},
     {"BULK_THRESH", "1M", "Total bytes from which the bulk-copy kernel is used", ucc_offsetof(ucc_tl_nvl_context_config_t, bulk_thresh), UCC_CONFIG_TYPE_MEMUNITS},
@@ -72,6 +75,10 @@ static ucc_status_t nvl_ctx_create(const ucc_base_context_params_t *p, const ucc
     ctx->addr.ep_id = ((uint64_t)(uint32_t)ctx->addr.pid << 32) | ucc_atomic_fadd32(&seq, 1);
     ucc_cu_api_load();
     ctx->addr.vmm_ok = 0; ctx->addr.mc_ok = 0;
+    { char bus[32]; unsigned dom = 0, b = 0, d = 0;
+      ctx->addr.pci_domain = ctx->addr.pci_bus = ctx->addr.pci_device = -1;
+      if (cudaDeviceGetPCIBusId(bus, (int)sizeof(bus), dev) == cudaSuccess && sscanf(bus, "%x:%x:%x", &dom, &b, &d) == 3) { ctx->addr.pci_domain = (int32_t)dom; ctx->addr.pci_bus = (int32_t)b; ctx->addr.pci_device = (int32_t)d; }
+      else (void)cudaGetLastError(); }
     if (ucc_cu.cuDeviceGetAttribute && ucc_cu.cuMemCreate) {
         CUdevice cudev;
         if (ucc_cu.cuDeviceGet(&cudev, dev) == CUDA_SUCCESS) {

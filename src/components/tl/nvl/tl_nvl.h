@@ -44,6 +44,8 @@ typedef struct ucc_tl_nvl_context_config {
     int      zcopy;            /* ternary: read / write the members' user buffers in place (CUDA IPC) */
     size_t   zcopy_thresh;     /* ... for messages of at least this size */
     size_t   user_size;        /* symmetric USER region appended to every team heap (0: none), see ucc_tl_nvl_symm_region() */
+    int      ring_reverse;     /* debug / test knob: walk the ring in the opposite direction (exercises non-identity ring orders) */
+    int      require_nvlink;   /* ternary: refuse teams with a GPU pair that has no NVLink path (try: only when the topology is known) */
     int      bulk;             /* ternary: TMA bulk copies (cp.async.bulk) as the data mover of the zero-copy push exchange */
     size_t   bulk_thresh;
     unsigned bulk_ctas;        /* one-warp CTAs of a bulk-copy kernel */
@@ -65,6 +67,7 @@ typedef struct ucc_tl_nvl_lib { ucc_tl_lib_t super; } ucc_tl_nvl_lib_t;
 
 typedef struct ucc_tl_nvl_addr { /* published through the core address exchange */
     uint64_t host_hash; int32_t pid; int32_t dev; uint64_t ep_id; int32_t vmm_ok, mc_ok;
+    int32_t  pci_domain, pci_bus, pci_device; /* identifies the GPU on its host whatever CUDA_VISIBLE_DEVICES says (-1: unknown) */
 } ucc_tl_nvl_addr_t;
 
 typedef struct ucc_tl_nvl_context {
@@ -132,6 +135,11 @@ typedef struct ucc_tl_nvl_team {
     /* launch ordering: kernels of one team must start in post order on every rank (the device-side epochs assume it) */
     ucc_list_link_t   launch_q;             /* posted tasks whose kernel is not launched yet */
     ucc_spinlock_t    launch_lock;
+    /* NVLink topology of the team (sysinfo graph: topo/cuda/sysinfo_cuda.c -> ucc_local_host): links[r][q] = NVLinks between the GPUs
+     * of members r and q (0: unknown / none), ring_order = visit order in which consecutive members share the most links */
+    uint8_t           links[NVL_MAX_PEERS][NVL_MAX_PEERS];
+    int               topo_known, nvswitch;
+    ucc_rank_t        ring_order[NVL_MAX_PEERS];
     /* lanes ("slots"): the heap holds `nlanes` complete copies of [control | one-shot | p2p | data]; consecutive collectives take
      * consecutive lanes (post order, identical on every member), so up to nlanes collectives of a team - posted on different
      * streams - run concurrently with their own flags, epochs and staging space.  Kernels of ONE lane still start in post order. */

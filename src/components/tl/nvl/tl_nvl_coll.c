@@ -801,6 +801,7 @@ static ucc_status_t xchg_init_ring(ucc_base_coll_args_t *b, ucc_base_team_t *b_t
     for (ucc_rank_t p = 0; p < N; p++) { x->pull_off[p] = off; off += ucc_align_up(x->pull_bytes[p], 16); }
     if (off > cap) { (*task_p)->finalize(*task_p); *task_p = NULL; return UCC_ERR_NOT_SUPPORTED; }
     x->ring = 1;
+    for (ucc_rank_t p = 0; p < N; p++) { x->ring_order[p] = (int)team->ring_order[p]; if (team->ring_order[p] == UCC_TL_TEAM_RANK(team)) x->ring_pos = (int)p; }
     return UCC_OK;
 }
 

@@ -2,6 +2,9 @@
  * peer mapping, optional NVLS multicast binding.  Every decision that could differ between
  * ranks is agreed through an OOB allgather so all members end up in the same mode. */
 #include "tl_nvl.h"
+#include "coll_patterns/ring.h"
+#include "core/ucc_lib.h"
+static inline int same_pid_pair_unknown(int topo_known) { return !topo_known; }
 #include "core/ucc_service_coll.h"
 #include "utils/ucc_sys.h"
 #include "utils/ucc_math.h"
@@ -167,7 +170,7 @@ ucc_status_t ucc_tl_nvl_team_create_post(ucc_base_context_t *b_ctx, const ucc_ba
     ucc_tl_nvl_team_t *team;
     ucc_rank_t N = params->size;
     int same_pid = 1, all_vmm = 1, all_mc = 1, distinct_dev = 1, want_mc, dev;
-    int devs[NVL_MAX_PEERS];
+    int devs[NVL_MAX_PEERS], gpu_idx[NVL_MAX_PEERS];
     ucc_status_t st;
     if (N < 1 || N > NVL_MAX_PEERS) return UCC_ERR_NOT_SUPPORTED;
     if (cudaGetDevice(&dev) != cudaSuccess || dev != ctx->dev) { (void)cudaGetLastError(); tl_debug(b_ctx->lib, "current device differs from the context's device"); return UCC_ERR_NOT_SUPPORTED; }
@@ -191,7 +194,34 @@ ucc_status_t ucc_tl_nvl_team_create_post(ucc_base_context_t *b_ctx, const ucc_ba
         if (!a->mc_ok) all_mc = 0;
         devs[r] = a->dev;
         for (ucc_rank_t q = 0; q < r; q++) if (devs[q] == a->dev) distinct_dev = 0;
+        /* the member's GPU in this host's sysinfo table (all members are on this host, see above) */
+        gpu_idx[r] = -1;
+        for (int g = 0; g < ucc_local_host.n_gpus; g++)
+            if (a->pci_bus >= 0 && ucc_local_host.gpus[g].pci.domain == (uint16_t)a->pci_domain && ucc_local_host.gpus[g].pci.bus == (uint8_t)a->pci_bus && ucc_local_host.gpus[g].pci.device == (uint8_t)a->pci_device) gpu_idx[r] = g;
     }
+    /* NVLink graph of the team (reference tl_cuda_team_topo.c:119-429 builds the same from its own NVML scan): a pair of
+     * different GPUs without an NVLink path would make every kernel crawl over PCIe - such a team is left to the next TL */
+    team->topo_known = 0; team->nvswitch = 0;
+    /* "known" only when the NVML scan saw NVLinks at all: a container that hides the link state must not make every pair look unconnected */
+    for (int g = 0; g < ucc_local_host.n_gpus; g++) if (ucc_local_host.gpus[g].caps & (UCC_GPU_CAP_NVLINK | UCC_GPU_CAP_NVSWITCH)) team->topo_known = 1;
+    for (ucc_rank_t r = 0; r < N; r++) {
+        if (gpu_idx[r] < 0) team->topo_known = 0;
+        else if (ucc_local_host.gpus[gpu_idx[r]].caps & UCC_GPU_CAP_NVSWITCH) team->nvswitch = 1;
+    }
+    for (ucc_rank_t r = 0; r < N; r++) for (ucc_rank_t q = 0; q < N; q++) {
+        team->links[r][q] = (team->topo_known && r != q && gpu_idx[r] != gpu_idx[q]) ? ucc_local_host.nvlink_matrix[gpu_idx[r]][gpu_idx[q]] : 0;
+        if (r != q && devs[r] != devs[q] && !same_pid_pair_unknown(team->topo_known) && team->links[r][q] == 0 && ctx->cfg.require_nvlink != UCC_NO) {
+            tl_debug(b_ctx->lib, "members %u and %u have no NVLink path: tl/nvl does not serve this team", r, q); free(team); return UCC_ERR_NOT_SUPPORTED;
+        }
+    }
+    if (!team->topo_known && ctx->cfg.require_nvlink == UCC_YES && N > 1 && distinct_dev) { tl_debug(b_ctx->lib, "NVLink topology unknown and REQUIRE_NVLINK=y"); free(team); return UCC_ERR_NOT_SUPPORTED; }
+    /* ring order: consecutive members share the most links (identity behind an NVSwitch, where every pair is equivalent) */
+    if (team->topo_known && !team->nvswitch && N > 2) {
+        uint8_t flat[NVL_MAX_PEERS * NVL_MAX_PEERS];
+        for (ucc_rank_t r = 0; r < N; r++) for (ucc_rank_t q = 0; q < N; q++) flat[r * N + q] = team->links[r][q];
+        ucc_ring_build_from_links(flat, N, team->ring_order);
+    } else for (ucc_rank_t r = 0; r < N; r++) team->ring_order[r] = r;
+    if (ctx->cfg.ring_reverse) for (ucc_rank_t r = 0; r < N / 2; r++) { ucc_rank_t x = team->ring_order[r]; team->ring_order[r] = team->ring_order[N - 1 - r]; team->ring_order[N - 1 - r] = x; }
     team->heap_kind = same_pid ? NVL_HEAP_LOCAL : (all_vmm ? NVL_HEAP_VMM : NVL_HEAP_IPC);
     want_mc = (team->heap_kind == NVL_HEAP_VMM) && all_mc && distinct_dev && ctx->cfg.use_nvls != UCC_NO;
     team->nvls = 0;

@@ -5,6 +5,9 @@
  * here is a new formulation on top of the program builder. */
 #include "tl_shm_coll.h"
 #include "coll_patterns/knomial_tree.h"
+#include "coll_patterns/sra_knomial.h"
+#include "coll_patterns/bruck_alltoall.h"
+#include "coll_patterns/ring.h"
 #include "coll_patterns/double_binary_tree.h"
 
 #define CHK(_x) do { st = (_x); if (ucc_unlikely(st != UCC_OK)) goto err; } while (0)
@@ -200,11 +203,11 @@ err:
 /* reduce-scatter ring on `buf` (count elems split in N blocks), result block (vrank+shift)%N complete on each rank */
 static ucc_status_t prog_rs_ring(ucc_tl_shm_task_t *t, char *buf, void *scratch, size_t count, ucc_memory_type_t mt, int final_block_is_own, unsigned step0)
 {
-    ucc_rank_t N = t->vsize, r = t->vrank, next = (r + 1) % N, prev = (r + N - 1) % N;
+    ucc_rank_t N = t->vsize, r = t->vrank, next = ucc_ring_next(r, N), prev = ucc_ring_prev(r, N);   /* coll_patterns/ring.h */
     size_t dts = ucc_dt_size(t->dt); ucc_status_t st = UCC_OK;
     int sh = final_block_is_own ? 1 : 0; /* own: last received block == r; else == r+1 */
     for (ucc_rank_t s = 0; s + 1 < N; s++) {
-        ucc_rank_t sb = (r + 2 * N - s - sh) % N, rb = (r + 2 * N - s - 1 - sh) % N;
+        ucc_rank_t sb = ucc_ring_rs_send_block(r, N, s, !sh), rb = ucc_ring_rs_recv_block(r, N, s, !sh);
         size_t rc = ucc_buffer_block_count(count, N, rb);
         CHK(shm_prog_send(t, next, buf + ucc_buffer_block_offset(count, N, sb) * dts, ucc_buffer_block_count(count, N, sb) * dts, mt, step0 + s));
         CHK(shm_prog_recv(t, prev, scratch, rc * dts, mt, step0 + s));
@@ -217,7 +220,7 @@ err:
 /* allgather ring where rank r starts owning block (r+own_shift)%N */
 static ucc_status_t prog_ag_ring(ucc_tl_shm_task_t *t, char *buf, size_t count, size_t dts, ucc_memory_type_t mt, int own_shift, unsigned step0)
 {
-    ucc_rank_t N = t->vsize, r = t->vrank, next = (r + 1) % N, prev = (r + N - 1) % N;
+    ucc_rank_t N = t->vsize, r = t->vrank, next = ucc_ring_next(r, N), prev = ucc_ring_prev(r, N);
     ucc_status_t st = UCC_OK;
     for (ucc_rank_t s = 0; s + 1 < N; s++) {
         ucc_rank_t sb = (r + own_shift + 2 * N - s) % N, rb = (r + own_shift + 2 * N - s - 1) % N;
@@ -307,9 +310,11 @@ ucc_status_t ucc_tl_shm_allreduce_sra(ucc_tl_shm_task_t *t)
     if (p.type == UCC_KN_NODE_PROXY) { CHK(shm_prog_recv(t, p.partner, scratch, len, mt, 1)); CHK(shm_prog_wait(t)); CHK(shm_prog_reduce(t, dst, dst, scratch, count, mt, 0)); }
     for (ucc_rank_t mask = p.n_full >> 1; mask > 0; mask >>= 1, step++, nsteps++) {
         ucc_rank_t peer = t->vrank ^ mask;
-        size_t h1 = seg_cnt / 2, h2 = seg_cnt - h1;
-        if (!(t->vrank & mask)) { off[nsteps] = seg_off; cnt[nsteps] = h1; soff[nsteps] = seg_off + h1; scnt[nsteps] = h2; }
-        else { off[nsteps] = seg_off + h1; cnt[nsteps] = h2; soff[nsteps] = seg_off; scnt[nsteps] = h1; }
+        /* the round splits the owned segment in two (coll_patterns/sra_knomial.h): I keep the half my digit selects, the peer the other */
+        const ucc_sra_seg_t seg = {seg_off, seg_cnt};
+        const unsigned digit = (t->vrank & mask) ? 1 : 0;
+        const ucc_sra_seg_t keep = ucc_sra_part(seg, 2, digit), give = ucc_sra_part(seg, 2, 1 - digit);
+        off[nsteps] = keep.off; cnt[nsteps] = keep.cnt; soff[nsteps] = give.off; scnt[nsteps] = give.cnt;
         CHK(shm_prog_send(t, peer, dst + soff[nsteps] * dts, scnt[nsteps] * dts, mt, step));
         CHK(shm_prog_recv(t, peer, scratch, cnt[nsteps] * dts, mt, step));
         CHK(shm_prog_wait(t));
@@ -726,24 +731,25 @@ err:
 ucc_status_t ucc_tl_shm_alltoall_onesided(ucc_tl_shm_task_t *t) { return a2a_onesided(t, 0); }
 ucc_status_t ucc_tl_shm_alltoallv_onesided(ucc_tl_shm_task_t *t) { return a2a_onesided(t, 1); }
 /* Bruck alltoall: log2(N) rounds, each moving the blocks whose index has bit k set (latency optimal for small blocks) */
+#define UCC_TL_SHM_MAX_BRUCK 1024
 ucc_status_t ucc_tl_shm_alltoall_bruck(ucc_tl_shm_task_t *t)
 {
     ucc_coll_args_t *a = ARGS(t); ucc_rank_t N = t->vsize, r = t->vrank; int inplace = UCC_IS_INPLACE(*a);
     size_t blk = a->dst.info.count / N * ucc_dt_size(a->dst.info.datatype);
     ucc_memory_type_t mt = a->dst.info.mem_type; char *dst = (char *)a->dst.info.buffer, *src = inplace ? dst : (char *)a->src.info.buffer;
     void *wv, *pv; char *w, *pk; ucc_status_t st; unsigned step = 1;
-    if (!inplace && a->src.info.mem_type != mt) return UCC_ERR_NOT_SUPPORTED;
+    if ((!inplace && a->src.info.mem_type != mt) || N > UCC_TL_SHM_MAX_BRUCK) return UCC_ERR_NOT_SUPPORTED;
     CHK(shm_task_scratch(t, blk * N, mt, &wv)); CHK(shm_task_scratch(t, blk * N, mt, &pv)); w = (char *)wv; pk = (char *)pv;
     /* phase 1: local rotation, w[i] = src[(r+i)%N] */
     CHK(shm_prog_copy(t, w, src + (size_t)r * blk, (N - r) * blk, mt, mt)); if (r) CHK(shm_prog_copy(t, w + (size_t)(N - r) * blk, src, (size_t)r * blk, mt, mt));
-    for (ucc_rank_t d = 1; d < N; d *= 2, step++) {
-        ucc_rank_t to = (r + d) % N, from = (r + N - d) % N, n = 0;
-        for (ucc_rank_t i = 0; i < N; i++) if (i & d) { CHK(shm_prog_copy(t, pk + (size_t)n * blk, w + (size_t)i * blk, blk, mt, mt)); n++; }
-        CHK(shm_prog_send(t, to, pk, (size_t)n * blk, mt, step)); CHK(shm_prog_recv(t, from, pk + (size_t)n * blk, (size_t)n * blk, mt, step)); CHK(shm_prog_wait(t));
-        n = 0; { ucc_rank_t cntb = 0; for (ucc_rank_t i = 0; i < N; i++) if (i & d) cntb++; for (ucc_rank_t i = 0; i < N; i++) if (i & d) { CHK(shm_prog_copy(t, w + (size_t)i * blk, pk + (size_t)(cntb + n) * blk, blk, mt, mt)); n++; } }
+    for (unsigned k = 0; k < ucc_bruck_n_steps(N); k++, step++) {   /* index math: coll_patterns/bruck_alltoall.h */
+        ucc_rank_t idx[UCC_TL_SHM_MAX_BRUCK], n = ucc_bruck_step_blocks(N, k, idx);
+        for (ucc_rank_t j = 0; j < n; j++) CHK(shm_prog_copy(t, pk + (size_t)j * blk, w + (size_t)idx[j] * blk, blk, mt, mt));
+        CHK(shm_prog_send(t, ucc_bruck_send_peer(r, N, k), pk, (size_t)n * blk, mt, step)); CHK(shm_prog_recv(t, ucc_bruck_recv_peer(r, N, k), pk + (size_t)n * blk, (size_t)n * blk, mt, step)); CHK(shm_prog_wait(t));
+        for (ucc_rank_t j = 0; j < n; j++) CHK(shm_prog_copy(t, w + (size_t)idx[j] * blk, pk + (size_t)(n + j) * blk, blk, mt, mt));
     }
     /* phase 3: inverse rotation, dst[(r - i + N) % N] = w[i] */
-    for (ucc_rank_t i = 0; i < N; i++) CHK(shm_prog_copy(t, dst + (size_t)((r + N - i) % N) * blk, w + (size_t)i * blk, blk, mt, mt));
+    for (ucc_rank_t i = 0; i < N; i++) CHK(shm_prog_copy(t, dst + (size_t)ucc_bruck_final_src(r, N, i) * blk, w + (size_t)i * blk, blk, mt, mt));
 err:
     return st;
 }

@@ -102,3 +102,15 @@ def test_profile_log_and_reader(tmp_path):
     assert len(tr["traceEvents"]) == rep["n_log"] > 0
     txt = subprocess.run([sys.executable, os.path.join(root, "tools", "read_profile.py"), str(prof)], capture_output=True, text=True, timeout=60)
     assert "shm_allreduce" in txt.stdout and "ucc_collective_post" in txt.stdout
+
+
+def test_install_and_consumer_exports(tmp_path):
+    """`make install` + the pkg-config file and the CMake package a consumer of openucx/ucc expects (reference ucc.pc.in, cmake/*.in)"""
+    prefix = str(tmp_path / "inst")
+    r = subprocess.run(["make", "-C", ROOT, "install", f"PREFIX={prefix}"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    pc = open(os.path.join(prefix, "lib", "pkgconfig", "ucc.pc")).read()
+    assert "-lucc" in pc and prefix in pc
+    assert os.path.exists(os.path.join(prefix, "lib", "cmake", "ucc", "ucc-config.cmake"))
+    r = subprocess.run(["bash", os.path.join(ROOT, "tools", "test_consumer_export.sh"), prefix], capture_output=True, text=True, timeout=600)
+    assert "CONSUMER_EXPORT_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
