@@ -167,6 +167,9 @@ class Bench:
         mk = alloc or (lambda c: torch.empty(c, dtype=self.dt, device=self.dev))
         src = pattern(torch, cnt, self.rank, self.dt, self.dev, out=mk(cnt))
         dst = mk(cnt).zero_()
+        # the buffers were produced on the default stream and are used on a side stream: without this the first collectives run
+        # while the producer kernels are still queued (and the caching allocator hands the producer's temporaries out as `dst`)
+        torch.cuda.synchronize()
         with torch.cuda.stream(self.stream):
             hs = [ar(src, dst, self.stream) for _ in range(warm)]
             settle(hs)
@@ -270,6 +273,7 @@ def run_ours(a):
         mk = alloc if use_symm else (lambda c: torch.empty(c, dtype=B.dt, device=B.dev))
         src, dst = mk(cnt), mk(cnt)
         out = torch.empty(16, dtype=B.dt).pin_memory()
+        torch.cuda.synchronize()
         chunks = a.e2e_chunks or None
 
         def step():
@@ -322,14 +326,16 @@ def run_reference(a):
     S = a.size
     STOCK_SYMM = 512 << 20                      # reference default UCC_TL_CUDA_NVLS_SYMMETRIC_SIZE (tl_cuda.c:55)
     tlcuda = None
-    if N > 1:
+
+    def make_tlcuda():
+        # created AFTER tl/nccl was measured: its 8 x (symmetric size) multicast-bound region must not compete with NCCL's own
+        # NVLS resources while NCCL is being timed (each transport gets the box for itself, as in separate ucc_perftest runs)
         from ref_arm import RefTlCuda
         # the headline message is larger than the stock symmetric size: the stock build hands it to tl/nccl.  The region is
         # sized to fit the headline too so that tl/cuda's NVLS path is ALSO measured there (UCC_TL_CUDA_NVLS_SYMMETRIC_SIZE raised).
         symm = max(STOCK_SYMM, (S + 16 * N - 1) // (16 * N) * (16 * N))
-        tlcuda = RefTlCuda(B.rank, N, torch.cuda.current_device(), symm_size=symm, slots=8, sm_count=4, threads=1024)
-        if not tlcuda.ok:
-            tlcuda = None
+        t = RefTlCuda(B.rank, N, torch.cuda.current_device(), symm_size=symm, slots=8, sm_count=4, threads=1024)
+        return t if t.ok else None
 
     def settle(hs):
         pass
@@ -346,6 +352,7 @@ def run_reference(a):
         cnt = nbytes // B.esz
         src = pattern(torch, cnt, B.rank, B.dt, B.dev)
         x = src.clone()
+        torch.cuda.synchronize()
         with torch.cuda.stream(B.stream):
             for _ in range(warm):
                 dist.all_reduce(x)
@@ -366,12 +373,19 @@ def run_reference(a):
     sampler = ClockSampler(torch.cuda.current_device())
     sampler.start()
     arms = {}
+    nccl_sweep = {}
     if N == 1:
         u, okk = B.time_arm(ar_self, settle, S, a.steps, a.warmup)
         arms["tl_self(cudaMemcpyAsync)"] = (u, okk)
     else:
         if not a.no_nccl:
             arms["tl_nccl(ncclAllReduce)"] = time_nccl(S, a.steps, a.warmup)
+            if not a.no_sweep:
+                nb = 1 << 10
+                while nb <= (1 << 30):
+                    nccl_sweep[nb] = time_nccl(nb, 50 if nb <= (1 << 22) else (20 if nb <= (1 << 26) else 8), 5)
+                    nb <<= 2
+        tlcuda = make_tlcuda()
         if tlcuda is not None:
             arms["tl_cuda_nvls(stock kernels, 4x1024, NVLS_SYMMETRIC_SIZE raised to fit)" if S > STOCK_SYMM else "tl_cuda_nvls(stock kernels, 4x1024)"] = \
                 B.time_arm(ar_tlcuda, settle, S, a.steps, a.warmup)
@@ -380,6 +394,26 @@ def run_reference(a):
     value = B.busbw(S, us)
     stock = "tl_self" if N == 1 else ("tl_nccl" if (S > STOCK_SYMM or tlcuda is None) else "tl_cuda_nvls")
 
+    sweep = []
+    if not a.no_sweep and N > 1:
+        nb = 1 << 10
+        while nb <= (1 << 30):
+            iters = 50 if nb <= (1 << 22) else (20 if nb <= (1 << 26) else 8)
+            row = {"bytes": nb}
+            if tlcuda is not None and nb >= 16 * N:
+                u, okk = B.time_arm(ar_tlcuda, settle, nb, iters, 5)
+                row.update({"tl_cuda_us": round(u, 2), "tl_cuda_busbw": round(B.busbw(nb, u), 2), "tl_cuda_ok": okk, "tl_cuda_stock_selectable": nb <= STOCK_SYMM})
+            if nb in nccl_sweep:
+                u, okk = nccl_sweep[nb]
+                row.update({"nccl_us": round(u, 2), "nccl_busbw": round(B.busbw(nb, u), 2)})
+            sweep.append(row)
+            nb <<= 2
+
+    if tlcuda is not None and not best.startswith("tl_cuda"):
+        tlcuda.destroy()          # the end-to-end steps below run tl/nccl: give NCCL the box back
+        tlcuda = None
+
+
     e2e = None
     if not a.no_e2e:
         cnt = S // B.esz
@@ -387,6 +421,7 @@ def run_reference(a):
         src = torch.empty(cnt, dtype=B.dt, device=B.dev)
         dst = torch.empty(cnt, dtype=B.dt, device=B.dev)
         out = torch.empty(16, dtype=B.dt).pin_memory()
+        torch.cuda.synchronize()
         use = best
 
         def step():
@@ -406,22 +441,6 @@ def run_reference(a):
                "d2h_bytes_per_step": 16 * B.esz, "us_per_step": round(e2e_us, 1), "correct": B.all_ok(bool(torch.equal(dst, exp))), "transport": use}
         del host, src, dst, exp
     clocks = sampler.stop()
-
-    sweep = []
-    if not a.no_sweep and N > 1:
-        nb = 1 << 10
-        while nb <= (1 << 30):
-            iters = 50 if nb <= (1 << 22) else (20 if nb <= (1 << 26) else 8)
-            row = {"bytes": nb}
-            if tlcuda is not None and nb >= 16 * N:
-                u, okk = B.time_arm(ar_tlcuda, settle, nb, iters, 5)
-                row.update({"tl_cuda_us": round(u, 2), "tl_cuda_busbw": round(B.busbw(nb, u), 2), "tl_cuda_ok": okk, "tl_cuda_stock_selectable": nb <= STOCK_SYMM})
-            if not a.no_nccl:
-                u, okk = time_nccl(nb, iters, 5)
-                row.update({"nccl_us": round(u, 2), "nccl_busbw": round(B.busbw(nb, u), 2)})
-            sweep.append(row)
-            nb <<= 2
-
     res = result_json(B, a, "reference", value, us, ok, clocks, a.steps * (3 if best.startswith("tl_cuda") else 1), e2e, sweep)
     res["reference_class"] = best
     res["reference_stock_selection"] = stock

@@ -29,9 +29,8 @@ static __device__ __forceinline__ const void *src_k(const ec_reduce_args_t &a, i
 
 /* scalar path: any alignment, any type */
 template <typename T, typename A, int OP, typename LD, typename ST>
-static __device__ __forceinline__ void reduce_scalar(const ec_reduce_args_t &a, size_t begin, size_t end, LD ld, ST st)
+static __device__ __forceinline__ void reduce_scalar(const ec_reduce_args_t &a, size_t begin, size_t end, LD ld, ST st, size_t tid, size_t nt)
 {
-    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (size_t)gridDim.x * blockDim.x;
     for (size_t i = begin + tid; i < end; i += nt) {
         A acc = ld(((const T *)src_k(a, 0))[i]);
         for (int k = 1; k < a.n_srcs; k++) acc = EcOp<OP, A>::f(acc, ld(((const T *)src_k(a, k))[i]));
@@ -40,14 +39,15 @@ static __device__ __forceinline__ void reduce_scalar(const ec_reduce_args_t &a, 
     }
 }
 
-template <typename T, int OP> static __device__ __forceinline__ void reduce_body(const ec_reduce_args_t &a)
+/* tid / nt = index of the calling thread among the threads that share this task: the whole grid for the one-shot kernels,
+ * one worker block inside the persistent executor */
+template <typename T, int OP> static __device__ __forceinline__ void reduce_body(const ec_reduce_args_t &a, size_t tid, size_t nt)
 {
     typedef typename AccOf<T>::type A;
     constexpr int E = 16 / sizeof(T);
     bool aligned = ((uintptr_t)a.dst & 15) == 0;
     for (int k = 0; k < a.n_srcs; k++) aligned = aligned && (((uintptr_t)src_k(a, k) & 15) == 0);
     size_t nvec = aligned ? a.count / E : 0;
-    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (size_t)gridDim.x * blockDim.x;
     for (size_t v = tid; v < nvec; v += nt) { /* 128-bit path */
         VecAcc<T, OP> acc;
         acc.set(ld_src_v4((const char *)src_k(a, 0) + v * 16));
@@ -58,32 +58,34 @@ template <typename T, int OP> static __device__ __forceinline__ void reduce_body
         }
         st_v4((char *)a.dst + v * 16, acc.get(1.0f, 1));
     }
-    reduce_scalar<T, A, OP>(a, nvec * E, a.count, [](T x) { return to_acc<T>(x); }, [](A x) { return from_acc<T>(x); });
+    reduce_scalar<T, A, OP>(a, nvec * E, a.count, [](T x) { return to_acc<T>(x); }, [](A x) { return from_acc<T>(x); }, tid, nt);
 }
-template <typename T, int OP> static __device__ __forceinline__ void reduce_body_cplx(const ec_reduce_args_t &a)
-{ reduce_scalar<T, T, OP>(a, 0, a.count, [](T x) { return x; }, [](T x) { return x; }); }
+template <typename T, int OP> static __device__ __forceinline__ void reduce_body_cplx(const ec_reduce_args_t &a, size_t tid, size_t nt)
+{ reduce_scalar<T, T, OP>(a, 0, a.count, [](T x) { return x; }, [](T x) { return x; }, tid, nt); }
 
-template <typename T> static __device__ __forceinline__ void reduce_dispatch(const ec_reduce_args_t &a)
+template <typename T> static __device__ __forceinline__ void reduce_dispatch(const ec_reduce_args_t &a, size_t tid, size_t nt)
 {
-#define CALL_EC_REDUCE(_T, _OP) reduce_body<_T, _OP>(a)
+#define CALL_EC_REDUCE(_T, _OP) reduce_body<_T, _OP>(a, tid, nt)
     int op = a.op;
     NVL_DISPATCH_OP(T, op, CALL_EC_REDUCE);
 }
-static __device__ __noinline__ void reduce_any(const ec_reduce_args_t &a)
+static __device__ __noinline__ void reduce_any(const ec_reduce_args_t &a, size_t tid, size_t nt)
 {
     switch (a.dt) {
-    case EC_DT_I8: reduce_dispatch<int8_t>(a); break; case EC_DT_I16: reduce_dispatch<int16_t>(a); break;
-    case EC_DT_I32: reduce_dispatch<int32_t>(a); break; case EC_DT_I64: reduce_dispatch<int64_t>(a); break;
-    case EC_DT_U8: reduce_dispatch<uint8_t>(a); break; case EC_DT_U16: reduce_dispatch<uint16_t>(a); break;
-    case EC_DT_U32: reduce_dispatch<uint32_t>(a); break; case EC_DT_U64: reduce_dispatch<uint64_t>(a); break;
-    case EC_DT_F16: reduce_dispatch<__half>(a); break; case EC_DT_BF16: reduce_dispatch<__nv_bfloat16>(a); break;
-    case EC_DT_F32: reduce_dispatch<float>(a); break; case EC_DT_F64: reduce_dispatch<double>(a); break;
-    case EC_DT_C64: if (a.op == EC_OP_SUM) reduce_body_cplx<cuFloatComplex, EC_OP_SUM>(a); else if (a.op == EC_OP_PROD) reduce_body_cplx<cuFloatComplex, EC_OP_PROD>(a); break;
-    case EC_DT_C128: if (a.op == EC_OP_SUM) reduce_body_cplx<cuDoubleComplex, EC_OP_SUM>(a); else if (a.op == EC_OP_PROD) reduce_body_cplx<cuDoubleComplex, EC_OP_PROD>(a); break;
+    case EC_DT_I8: reduce_dispatch<int8_t>(a, tid, nt); break; case EC_DT_I16: reduce_dispatch<int16_t>(a, tid, nt); break;
+    case EC_DT_I32: reduce_dispatch<int32_t>(a, tid, nt); break; case EC_DT_I64: reduce_dispatch<int64_t>(a, tid, nt); break;
+    case EC_DT_U8: reduce_dispatch<uint8_t>(a, tid, nt); break; case EC_DT_U16: reduce_dispatch<uint16_t>(a, tid, nt); break;
+    case EC_DT_U32: reduce_dispatch<uint32_t>(a, tid, nt); break; case EC_DT_U64: reduce_dispatch<uint64_t>(a, tid, nt); break;
+    case EC_DT_F16: reduce_dispatch<__half>(a, tid, nt); break; case EC_DT_BF16: reduce_dispatch<__nv_bfloat16>(a, tid, nt); break;
+    case EC_DT_F32: reduce_dispatch<float>(a, tid, nt); break; case EC_DT_F64: reduce_dispatch<double>(a, tid, nt); break;
+    case EC_DT_C64: if (a.op == EC_OP_SUM) reduce_body_cplx<cuFloatComplex, EC_OP_SUM>(a, tid, nt); else if (a.op == EC_OP_PROD) reduce_body_cplx<cuFloatComplex, EC_OP_PROD>(a, tid, nt); break;
+    case EC_DT_C128: if (a.op == EC_OP_SUM) reduce_body_cplx<cuDoubleComplex, EC_OP_SUM>(a, tid, nt); else if (a.op == EC_OP_PROD) reduce_body_cplx<cuDoubleComplex, EC_OP_PROD>(a, tid, nt); break;
     default: break;
     }
 }
-__global__ void __launch_bounds__(1024) ec_reduce_kernel(ec_reduce_args_t a) { reduce_any(a); }
+#define EC_GRID_TID ((size_t)blockIdx.x * blockDim.x + threadIdx.x)
+#define EC_GRID_NT ((size_t)gridDim.x * blockDim.x)
+__global__ void __launch_bounds__(1024) ec_reduce_kernel(ec_reduce_args_t a) { reduce_any(a, EC_GRID_TID, EC_GRID_NT); }
 
 /* up to 7 independent dst[j] = src1[j] op src2[j]; blockIdx.y selects the buffer */
 __global__ void __launch_bounds__(1024) ec_reduce_multi_dst_kernel(ec_reduce_multi_dst_args_t m)
@@ -92,7 +94,7 @@ __global__ void __launch_bounds__(1024) ec_reduce_multi_dst_kernel(ec_reduce_mul
     if (j >= m.n_bufs) return;
     ec_reduce_args_t a; a.dst = m.dst[j]; a.srcs[0] = m.src1[j]; a.srcs[1] = m.src2[j]; a.n_srcs = 2; a.strided = 0; a.src2 = nullptr; a.stride = 0;
     a.count = m.counts[j]; a.dt = m.dt; a.op = m.op; a.with_alpha = 0; a.alpha = 1.0;
-    reduce_any(a);
+    reduce_any(a, EC_GRID_TID, EC_GRID_NT);
 }
 
 /* ------------------------------------------------------------------ */
@@ -115,12 +117,16 @@ __global__ void __launch_bounds__(1024) ec_copy_multi_kernel(ec_copy_multi_args_
 
 /* ------------------------------------------------------------------ */
 /* persistent executor: worker blocks pop tasks from a host-pinned ring */
+/* (reference ec/cuda/kernel/ec_cuda_executor.cu:125-188: num_workers blocks share one task ring).  Worker block w serves  */
+/* slots w, w + W, w + 2W, ... - the host fills the ring in order, so consecutive tasks land on different workers and     */
+/* run concurrently; inside a task only the worker's own threads take part (tid = threadIdx.x, nt = blockDim.x).        */
 /* ------------------------------------------------------------------ */
 __global__ void __launch_bounds__(1024) ec_persistent_kernel(ec_ring_t *ring)
 {
     __shared__ uint32_t s_cmd; /* 0 = run slot, 1 = shutdown */
-    uint32_t idx = blockIdx.x; /* worker w serves slots w, w+W, w+2W, ... */
+    uint32_t idx = blockIdx.x;
     const uint32_t W = gridDim.x;
+    const size_t tid = threadIdx.x, nt = blockDim.x;
     if (blockIdx.x == 0 && threadIdx.x == 0) { ring->started = 1; __threadfence_system(); }
     for (;;) {
         ec_ring_slot_t *slot = &ring->slots[idx % ring->n_slots];
@@ -135,26 +141,22 @@ __global__ void __launch_bounds__(1024) ec_persistent_kernel(ec_ring_t *ring)
         }
         __syncthreads();
         if (s_cmd == 1) return;
-        /* each worker block processes a whole task with its own threads (gridDim = 1 inside the helpers) */
         switch (slot->kind) {
         case EC_TASK_REDUCE: {
             ec_reduce_args_t a = slot->u.reduce;
-            /* emulate a 1-block grid: iterate with this block's threads only */
-            struct { unsigned x; } saved; (void)saved;
-            const size_t tid = threadIdx.x, nt = blockDim.x; (void)tid; (void)nt;
-            reduce_any(a); /* uses blockIdx.x*blockDim.x+threadIdx.x: correct when W == 1; for W > 1 see launcher */
+            reduce_any(a, tid, nt);
             break; }
         case EC_TASK_REDUCE_MULTI_DST: {
             ec_reduce_multi_dst_args_t m = slot->u.rmd;
             for (int j = 0; j < m.n_bufs; j++) {
                 ec_reduce_args_t a; a.dst = m.dst[j]; a.srcs[0] = m.src1[j]; a.srcs[1] = m.src2[j]; a.n_srcs = 2; a.strided = 0; a.src2 = nullptr; a.stride = 0;
                 a.count = m.counts[j]; a.dt = m.dt; a.op = m.op; a.with_alpha = 0; a.alpha = 1.0;
-                reduce_any(a);
+                reduce_any(a, tid, nt);
             }
             break; }
         case EC_TASK_COPY: case EC_TASK_COPY_MULTI: {
             ec_copy_multi_args_t c = slot->u.copy;
-            for (int j = 0; j < c.n; j++) copy_grid((char *)c.dst[j], (const char *)c.src[j], c.bytes[j], threadIdx.x, blockDim.x);
+            for (int j = 0; j < c.n; j++) copy_grid((char *)c.dst[j], (const char *)c.src[j], c.bytes[j], tid, nt);
             break; }
         default: break;
         }
@@ -184,15 +186,14 @@ extern "C" cudaError_t ec_launch_copy_multi(const ec_copy_multi_args_t *a, int n
 { ec_copy_multi_kernel<<<dim3(4, a->n), nthreads, 0, s>>>(*a); return cudaGetLastError(); }
 extern "C" cudaError_t ec_launch_persistent(ec_ring_t *ring_dev, int nworkers, int nthreads, int cooperative, cudaStream_t s)
 {
-    /* every task is executed by one worker block with its own threads, so the element loops inside must see a
-     * one-block grid: the kernel is always launched with a single worker block per ring (W = 1 keeps
-     * blockIdx.x*blockDim.x+threadIdx.x == threadIdx.x); more workers = more rings at the host level */
-    (void)nworkers;
+    /* the workers spin on their slots, so all of them must be resident at once: at most one per SM here (they are long-lived
+     * and should leave room for everything else); the cooperative launch makes the runtime verify co-residency */
+    if (nworkers < 1) nworkers = 1;
     if (cooperative) {
         void *args[] = {&ring_dev};
-        return cudaLaunchCooperativeKernel((void *)ec_persistent_kernel, dim3(1), dim3(nthreads), args, 0, s);
+        return cudaLaunchCooperativeKernel((void *)ec_persistent_kernel, dim3((unsigned)nworkers), dim3((unsigned)nthreads), args, 0, s);
     }
-    ec_persistent_kernel<<<1, nthreads, 0, s>>>(ring_dev);
+    ec_persistent_kernel<<<nworkers, nthreads, 0, s>>>(ring_dev);
     return cudaGetLastError();
 }
 extern "C" cudaError_t ec_launch_wait(volatile uint32_t *state_dev, cudaStream_t s) { ec_wait_kernel<<<1, 1, 0, s>>>(state_dev); return cudaGetLastError(); }

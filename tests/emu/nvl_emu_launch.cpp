@@ -94,5 +94,6 @@ cudaError_t nvl_launch_exchange_push_bulk(const nvl_push_args_t *ap, int nb, cud
 cudaError_t nvl_launch_barrier(const nvl_team_dev_t *tp, cudaStream_t s) { nvl_team_dev_t t = *tp; return enqueue_grid(s, 1, 32, [t]() { nvl_barrier_kernel(t); }); }
 cudaError_t nvl_launch_self_copy(void *dst, const void *src, size_t bytes, int, int, cudaStream_t s)
 { return enqueue_grid(s, 1, 1, [=]() { memmove(dst, src, bytes); }); }
+cudaError_t nvl_launch_self_copy_bulk(void *dst, const void *src, size_t bytes, int nb, cudaStream_t s) { return nvl_launch_self_copy(dst, src, bytes, nb, 32, s); }
 cudaError_t nvl_launch_ctrl_init(void *heap_base, cudaStream_t s) { return enqueue_grid(s, 1, 1, [=]() { memset(heap_base, 0, sizeof(nvl_ctrl_t)); }); }
 }

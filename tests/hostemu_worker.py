@@ -447,6 +447,28 @@ def registered_buffers():
     print("  registered buffers (ucc_mem_map -> zero-copy without the exchange board) ok", flush=True)
 
 
+def hier_on_device_buffers():
+    """cl/hier (rab, split_rail) over a synthetic 2-node x 4-GPU placement with "device" buffers: node sub-teams are tl/nvl teams,
+    the cross-node sub-teams (leaders / rails) cannot be (different fake hosts) and go to the host TL through staging"""
+    n = 8
+    for alg in ("rab", "split_rail"):
+        env = dict(BASE, UCC_CLS="hier,basic", UCC_CL_HIER_TUNE=f"allreduce:0-inf:@{alg}", UCC_TL_NVL_TIMEOUT="20s", **NOZC)
+        with UccJob(n, ppn=4, env=env, cls="hier,basic") as j:
+            team = j.create_team()
+            for count in (16, 4096, 50000):
+                src = [Dev(count, fill=rnd(count, 7 * r + 1)) for r in range(n)]
+                dst = [Dev(count, fill=0) for _ in range(n)]
+                run(team, [ca("allreduce", src[r], dst[r]) for r in range(n)])
+                exp = sum(s.a.copy() for s in src)
+                for r in range(n):
+                    assert np.allclose(dst[r].a, exp), (alg, count, r)
+            b = [Dev(5000, fill=rnd(5000, 3) if r == 0 else 0) for r in range(n)]
+            run(team, [ca("bcast", b[r], None, root=0, count_dst=0) for r in range(n)])
+            for r in range(n):
+                assert np.array_equal(b[r].a, b[0].a)
+        print(f"  cl/hier {alg} on device buffers ok", flush=True)
+
+
 def int_avg():
     """AVG on integer datatypes = truncated sum / N, on every reduction kernel"""
     n = 3
@@ -478,6 +500,7 @@ SCENARIOS = {
     "cross_team": lambda: [cross_team_order(NOZC), cross_team_order(ZC)],
     "p2p": lambda: [p2p_active_set(), int_avg()],
     "memh": registered_buffers,
+    "hier": hier_on_device_buffers,
 }
 
 if __name__ == "__main__":

@@ -19,6 +19,11 @@ def main():
     comm = ops.init()
     ok = True
 
+    def stage(name):   # where a hang happened is the last line printed
+        if rank == 0:
+            print(f"[parallel_worker] {name}", flush=True)
+    stage("ddp")
+
     # ---- DDP: averaged gradients == gradients of the mean loss over the global batch
     torch.manual_seed(0)
     model = MLP(32, 64, 2, 5).to(dev)
@@ -40,6 +45,7 @@ def main():
                 print(f"rank {rank}: DDP grad mismatch {n1} step {step}", flush=True)
                 ok = False
 
+    stage("tensor parallel")
     # ---- tensor parallel block == dense block assembled from the shards
     torch.manual_seed(100 + rank)
     d, h = 16, 8 * world
@@ -61,6 +67,7 @@ def main():
         print(f"rank {rank}: tensor-parallel mismatch", flush=True)
         ok = False
 
+    stage("column parallel gather")
     # ---- ColumnParallelLinear(gather_output=True): the gathered output must carry gradients back to weight, bias and input
     from ucc_b200.parallel.tensor_parallel import ColumnParallelLinear
     torch.manual_seed(200 + rank)
@@ -79,6 +86,7 @@ def main():
         print(f"rank {rank}: ColumnParallelLinear(gather_output) gradient mismatch", flush=True)
         ok = False
 
+    stage("moe")
     # ---- MoE dispatch / combine round trip with skewed routing
     T, H = 50 + 7 * rank, 12
     tok = torch.arange(T * H, dtype=torch.float32, device=dev).view(T, H) + 10000 * rank
@@ -93,6 +101,7 @@ def main():
         print(f"rank {rank}: MoE round trip mismatch", flush=True)
         ok = False
 
+    stage("zero")
     # ---- ZeRO-1: sharded SGD step == plain SGD on the averaged gradient
     torch.manual_seed(3)
     zm, rm = MLP(16, 24, 2, 3).to(dev), MLP(16, 24, 2, 3).to(dev)
@@ -111,6 +120,7 @@ def main():
             print(f"rank {rank}: ZeRO parameter mismatch {n1}", flush=True)
             ok = False
 
+    stage("ulysses")
     # ---- Ulysses all-to-all: [S/N, H, D] -> [S, H/N, D], and one ring-attention hop
     S, H, D = 4 * world, 2 * world, 3
     full = torch.arange(S * H * D, dtype=torch.float32).view(S, H, D).to(dev)
@@ -119,11 +129,13 @@ def main():
     if not torch.equal(got, full[:, rank * (H // world):(rank + 1) * (H // world)]):
         print(f"rank {rank}: ulysses mismatch", flush=True)
         ok = False
+    stage("ring pass (send / recv)")
     kv = torch.full((5, 7), float(rank), device=dev)
     if world % 2 == 0 or world == 1:
         prev = ring_pass(kv, comm=comm)
         ok &= bool((prev == float((rank - 1) % world)).all())
 
+    stage("done")
     flag = torch.tensor([1 if ok else 0])
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     ops.shutdown()

@@ -16,7 +16,7 @@ def _run(n, extra_env=None):
            "--master-port", str(port), os.path.join(ROOT, "tests", "dist_worker.py"), "cuda"]
     env = dict(os.environ, PYTHONPATH=ROOT)
     env.update(extra_env or {})
-    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=150)
     assert "DIST_WORKER_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
 
 
@@ -62,7 +62,7 @@ def test_parallel_helpers_cuda():
         pytest.skip("needs >= 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
            "--master-port", "29790", os.path.join(ROOT, "tests", "parallel_worker.py"), "cuda"]
-    out = subprocess.run(cmd, env=dict(os.environ, PYTHONPATH=ROOT), capture_output=True, text=True, timeout=900)
+    out = subprocess.run(cmd, env=dict(os.environ, PYTHONPATH=ROOT), capture_output=True, text=True, timeout=150)
     assert "PARALLEL_WORKER_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
 
 
@@ -88,7 +88,7 @@ def test_torch_backend_cuda():
         pytest.skip("needs >= 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
            "--master-port", "29795", os.path.join(ROOT, "tests", "pg_worker.py"), "cuda"]
-    out = subprocess.run(cmd, env=dict(os.environ, PYTHONPATH=ROOT), capture_output=True, text=True, timeout=900)
+    out = subprocess.run(cmd, env=dict(os.environ, PYTHONPATH=ROOT), capture_output=True, text=True, timeout=150)
     assert "PG_WORKER_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
 
 
@@ -110,7 +110,7 @@ def test_multiproc_symm():
         pytest.skip("needs >= 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
            "--master-port", "29741", os.path.join(ROOT, "tests", "symm_worker.py")]
-    out = subprocess.run(cmd, env=dict(os.environ, PYTHONPATH=ROOT, SYMM_BENCH_BYTES=str(256 << 20)), capture_output=True, text=True, timeout=900)
+    out = subprocess.run(cmd, env=dict(os.environ, PYTHONPATH=ROOT, SYMM_BENCH_BYTES=str(256 << 20)), capture_output=True, text=True, timeout=150)
     assert "SYMM_WORKER_OK" in out.stdout or "SYMM_WORKER_SKIP" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
 
 

@@ -1,6 +1,7 @@
 """EC reduce for every dtype/op + executor task kinds, MC alloc/memcpy/query — cpu everywhere, cuda under -m gpu
 (reference: test/gtest/core/test_mc_reduce.cc, test_ec_cuda.cc, test_mc.cc)."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -8,6 +9,8 @@ import pytest
 from ucc_b200 import capi as U
 from ucc_b200 import internal as I
 from ucc_b200.harness import UccJob, NP_DT
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 INT = ["int8", "int16", "int32", "int64", "uint8", "uint16", "uint32", "uint64"]
 FLT = ["float32", "float64", "float16"]
@@ -251,3 +254,46 @@ def test_ec_cuda_copy_alpha_events_mc(lib_alive):
     at.field_mask = 1
     t = torch.zeros(4, device="cuda")
     assert I.lib.ucc_mc_get_mem_attr(t.data_ptr(), C.byref(at)) == U.UCC_OK and at.mem_type == U.UCC_MEMORY_TYPE_CUDA
+
+
+@pytest.mark.gpu
+def test_ec_cuda_persistent_multi_worker():
+    """reference ec_cuda_executor.cu:125-188: EXEC_NUM_WORKERS blocks share one task ring.  32 tasks posted back to back to a
+    4-worker persistent executor (own process: the EC configuration is read once per library instance)."""
+    import subprocess
+    import sys
+    code = r'''
+import ctypes as C, sys, torch
+sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests')
+from ucc_b200 import capi as U, internal as I
+from test_ec_mc import reduce_args
+cfg = U.handle(); U.check(U.ucc_lib_config_read(None, None, C.byref(cfg)), "cfg")
+p = U.ucc_lib_params_t(); p.mask, p.thread_mode = U.UCC_LIB_PARAM_FIELD_THREAD_MODE, U.UCC_THREAD_SINGLE
+lib = U.handle(); U.check(U.ucc_init_version(U.UCC_API_MAJOR, U.UCC_API_MINOR, C.byref(p), cfg, C.byref(lib)), "init")
+st = torch.cuda.Stream()
+n = 20000
+srcs = [[torch.rand(n + 7 * k, device="cuda") for _ in range(3)] for k in range(32)]
+dsts = [torch.zeros(n + 7 * k, device="cuda") for k in range(32)]
+exp = [sum(srcs[k]) for k in range(32)]
+torch.cuda.synchronize()     # (a device-wide synchronize while the persistent kernel runs would wait for it forever)
+ex = I.Executor(U.UCC_EE_CUDA_STREAM, st.cuda_stream)
+tasks = []
+for k in range(32):
+    a = reduce_args(dsts[k].data_ptr(), [s.data_ptr() for s in srcs[k]], n + 7 * k, "float32", "sum")
+    t = C.c_void_p()
+    U.check(I.lib.ucc_ee_executor_task_post(ex.h, C.byref(a), C.byref(t)), "post")
+    tasks.append((a, t))
+for a, t in tasks:
+    while I.lib.ucc_ee_executor_task_test(t) == U.UCC_INPROGRESS:
+        pass
+    assert I.lib.ucc_ee_executor_task_test(t) == U.UCC_OK
+    I.lib.ucc_ee_executor_task_finalize(t)
+ex.close()
+torch.cuda.synchronize()
+for k in range(32):
+    assert torch.allclose(dsts[k], exp[k]), k
+print("MULTI_WORKER_OK")
+''' % (ROOT, ROOT)
+    env = dict(os.environ, UCC_EC_CUDA_EXEC_NUM_WORKERS="4", UCC_EC_CUDA_EXEC_MAX_TASKS="64", PYTHONPATH=ROOT)
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=60)
+    assert "MULTI_WORKER_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]

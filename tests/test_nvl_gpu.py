@@ -293,6 +293,52 @@ def test_bcast_gather_scatter_barrier(job, n):
     run(team, [coll_args("barrier") for _ in range(n)])
 
 
+# ---------------------------------------------------------------- zero-copy push exchange: thread copies, TMA bulk copies, copy engines
+@pytest.mark.parametrize("mover", ["push", "push_bulk", "ce"])
+@pytest.mark.parametrize("n", [2, 4, 8])
+def test_push_exchange_movers(mover, n):
+    """allgather(v) / alltoall / skewed alltoallv through the members' mapped destinations.  push_bulk: the TMA engine moves the
+    blocks (cp.async.bulk through shared memory, one elected thread per CTA; unaligned blocks fall back to thread copies inside
+    the same kernel); ce: cudaMemcpyAsync between two barrier kernels (reference ALLTOALL_USE_COPY_ENGINE)."""
+    need_cuda()
+    alg = "ce" if mover == "ce" else "push"
+    env = dict(ENV, UCC_TL_NVL_TUNE=f"allgather:cuda:inf:@{alg}#allgatherv:cuda:inf:@{alg}#alltoall:cuda:inf:@{alg}#alltoallv:cuda:inf:@{alg}",
+               UCC_TL_NVL_BULK="y" if mover == "push_bulk" else "n", UCC_TL_NVL_BULK_THRESH="0", UCC_TL_NVL_BULK_CTAS="3", **ZC)
+    with UccJob(n, env=env) as j:
+        team = j.create_team()
+        for blk in (4, 1000, 50000):               # 50000 floats = 200000 B: several 24 KB TMA stages per block and a short tail
+            src = [gen("float32", blk, 3 * r + blk) for r in range(n)]
+            dst = [torch.zeros(blk * n, device="cuda") for _ in range(n)]
+            run(team, [cargs("allgather", src[r], dst[r], "float32") for r in range(n)])
+            exp = torch.cat(src)
+            for r in range(n):
+                assert torch.equal(dst[r], exp), ("allgather", mover, n, blk, r)
+            src = [gen("float32", blk * n, 7 * r + 1) for r in range(n)]
+            dst = [torch.zeros(blk * n, device="cuda") for _ in range(n)]
+            run(team, [cargs("alltoall", src[r], dst[r], "float32") for r in range(n)])
+            for r in range(n):
+                exp = torch.cat([src[p][r * blk:(r + 1) * blk] for p in range(n)])
+                assert torch.equal(dst[r], exp), ("alltoall", mover, n, blk, r)
+        # skewed alltoallv with odd (unaligned) counts: rank 0 is the hot receiver
+        sc = [[(5003 if d == 0 else 17 + 3 * d + s) for d in range(n)] for s in range(n)]      # sc[s][d]: elements s sends to d
+        src = [gen("float32", sum(sc[s]), 11 * s) for s in range(n)]
+        rc = [[sc[s][d] for s in range(n)] for d in range(n)]
+        dst = [torch.zeros(sum(rc[d]), device="cuda") for d in range(n)]
+        args = []
+        for r in range(n):
+            sd = [sum(sc[r][:i]) for i in range(n)]
+            rd = [sum(rc[r][:i]) for i in range(n)]
+            args.append(cargs("alltoallv", src[r], dst[r], "float32", src_counts=sc[r], src_displs=sd, dst_counts=rc[r], dst_displs=rd))
+        run(team, args)
+        for d in range(n):
+            exp = torch.cat([src[s][sum(sc[s][:d]):sum(sc[s][:d]) + sc[s][d]] for s in range(n)])
+            assert torch.equal(dst[d], exp), ("alltoallv", mover, n, d)
+        info = __import__("ctypes").CDLL(os.path.join(os.path.dirname(U.LIB_PATH), "ucc", "libucc_tl_nvl.so")).ucc_tl_nvl_last_launch_info
+        info.restype = __import__("ctypes").c_char_p
+        want = {"push": b"exchange_push ", "push_bulk": b"bulk", "ce": b"copy_engine"}[mover]
+        assert want in info() + b" ", info()
+
+
 # ---------------------------------------------------------------- step-structured algorithms (ring, recursive halving/doubling)
 @pytest.fixture(scope="module", params=["ring", "rhd"])
 def steps_job(request):

@@ -102,12 +102,16 @@ class Request:
         ev.ev_type = U.UCC_EVENT_COMPUTE_COMPLETE
         ev.req = C.cast(self.req, C.c_void_p)
         self._ee = self.comm.ee_for(stream)
+        self._seen_posted = False
         U.check(U.ucc_collective_triggered_post(self._ee, C.byref(ev)), "triggered_post")
         if wait_posted:
             self.wait_posted()
         return self
 
     def wait_posted(self):
+        """idempotent: returns at once when this post was already seen in the stream"""
+        if getattr(self, "_seen_posted", False):
+            return
         key = C.cast(self.req, C.c_void_p).value
         while key not in self.comm._posted:
             st = self.req.contents.status
@@ -116,6 +120,7 @@ class Request:
             if not self.comm.collect_events(self._ee):
                 U.ucc_context_progress(self.comm.ctx)
         self.comm._posted.discard(key)
+        self._seen_posted = True
 
     def test(self):
         return self.req.contents.status
