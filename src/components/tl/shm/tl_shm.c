@@ -26,6 +26,8 @@ static ucc_config_field_t tl_shm_context_config_table[] = {
     {"GATHER_KN_RADIX", "auto", "Radix of the k-nomial gather / scatter", ucc_offsetof(ucc_tl_shm_context_config_t, gather_kn_radix), UCC_CONFIG_TYPE_UINT_RANGED},
     {"ALLTOALL_PAIRWISE_NUM_POSTS", "auto", "Maximum number of outstanding send/recv pairs in pairwise alltoall(v) (auto/0: unlimited)",
      ucc_offsetof(ucc_tl_shm_context_config_t, alltoall_pairwise_num_posts), UCC_CONFIG_TYPE_UINT},
+    {"ALLTOALLV_HYBRID_THRESH", "256", "alltoallv algorithm `hybrid`: messages of at most this many bytes are aggregated into log2(N) Bruck rounds, larger ones go pairwise",
+     ucc_offsetof(ucc_tl_shm_context_config_t, alltoallv_hybrid_thresh), UCC_CONFIG_TYPE_MEMUNITS},
     {"REDUCE_AVG_PRE_OP", "n", "Apply the 1/N scaling of AVG before (y) or after (n) the reduction", ucc_offsetof(ucc_tl_shm_context_config_t, reduce_avg_pre_op), UCC_CONFIG_TYPE_BOOL},
     {"ALLREDUCE_SRA_KN_PIPELINE", "n", "Pipelining of the SRA allreduce", ucc_offsetof(ucc_tl_shm_context_config_t, allreduce_sra_kn_pipeline), UCC_CONFIG_TYPE_PIPELINE_PARAMS},
     {NULL}};
@@ -41,10 +43,10 @@ static const shm_alg_t algs_allreduce[] = {A("knomial", "recursive k-nomial exch
 static const shm_alg_t algs_allgather[] = {A("knomial", "recursive doubling", allgather_knomial), A("ring", "ring", allgather_ring), A("neighbor", "neighbor exchange (even team size)", allgather_neighbor),
                                            A("bruck", "O(log N) Bruck allgather", allgather_bruck), A("sparbit", "O(log N) data-locality aware allgather", allgather_sparbit),
                                            A("linear", "everyone sends to everyone", allgather_linear), A("batched", "linear with bounded outstanding messages", allgather_batched), {NULL}};
-static const shm_alg_t algs_allgatherv[] = {A("ring", "ring", allgatherv_ring), A("knomial", "direct exchange for small messages", allgatherv_knomial), A("linear", "everyone sends to everyone", allgatherv_linear), {NULL}};
+static const shm_alg_t algs_allgatherv[] = {A("ring", "ring", allgatherv_ring), A("knomial", "recursive doubling of block sets (extra ranks through proxies)", allgatherv_knomial), A("linear", "everyone sends to everyone", allgatherv_linear), {NULL}};
 static const shm_alg_t algs_alltoall[] = {A("pairwise", "pairwise exchange", alltoall_pairwise), A("bruck", "O(log N) Bruck alltoall", alltoall_bruck),
                                           A("onesided", "every rank reads its blocks directly from the peers' source buffers (pointer / CMA)", alltoall_onesided), {NULL}};
-static const shm_alg_t algs_alltoallv[] = {A("pairwise", "pairwise exchange", alltoallv_pairwise), A("hybrid", "pairwise exchange (alias kept for TUNE compatibility)", alltoallv_pairwise),
+static const shm_alg_t algs_alltoallv[] = {A("pairwise", "pairwise exchange", alltoallv_pairwise), A("hybrid", "small messages in fixed slots through Bruck's log2(N) rounds, big ones pairwise", alltoallv_hybrid),
                                            A("onesided", "every rank reads its blocks directly from the peers' source buffers (pointer / CMA)", alltoallv_onesided), {NULL}};
 static const shm_alg_t algs_barrier[] = {A("knomial", "k-nomial fanin + fanout", barrier_knomial), {NULL}};
 static const shm_alg_t algs_bcast[] = {A("knomial", "k-nomial tree", bcast_knomial), A("sag_knomial", "scatter + ring allgather", bcast_sag), A("dbt", "double binary tree", bcast_dbt), {NULL}};

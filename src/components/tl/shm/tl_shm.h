@@ -66,6 +66,7 @@ typedef struct ucc_tl_shm_context_config {
     int       cma;               /* ternary: cross-memory-attach rendezvous between processes */
     ucc_mrange_uint_t allreduce_kn_radix, bcast_kn_radix, reduce_kn_radix, barrier_kn_radix, allgather_kn_radix, gather_kn_radix;
     unsigned  alltoall_pairwise_num_posts;
+    size_t    alltoallv_hybrid_thresh;   /* alltoallv `hybrid`: messages up to this size ride the Bruck rounds */
     int       reduce_avg_pre_op;
     ucc_pipeline_params_t allreduce_sra_kn_pipeline;
 } ucc_tl_shm_context_config_t;

@@ -661,7 +661,43 @@ ucc_status_t ucc_tl_shm_allgather_sparbit(ucc_tl_shm_task_t *t)
 err:
     return st;
 }
-ucc_status_t ucc_tl_shm_allgatherv_knomial(ucc_tl_shm_task_t *t) { return allgather_linear_common(t, 1, 0); }
+/* allgatherv by recursive doubling (radix-2 k-nomial exchange, role of reference tl/ucp allgatherv knomial): log2(N) rounds, in round
+ * k a rank swaps everything its group of 2^k ranks has collected so far with the partner group - blocks keep their (arbitrary)
+ * displacements, so a round is a set of block-sized messages.  Ranks beyond the largest power of two hand their block to a proxy
+ * first and get the complete vector from it at the end (coll_patterns/knomial_tree.h: EXTRA / PROXY). */
+ucc_status_t ucc_tl_shm_allgatherv_knomial(ucc_tl_shm_task_t *t)
+{
+    size_t *cnt, *off, dts; ucc_memory_type_t mt; char *dst; ucc_status_t st;
+    ucc_rank_t N = t->vsize, r = t->vrank; ucc_kn_pattern_t p; unsigned round = 1;
+    ucc_kn_pattern_init(&p, r, N, 2);
+    if ((uint64_t)N * 24 > 65000) return UCC_ERR_NOT_SUPPORTED; /* message ids: (round, block) must fit 16 bits */
+    CHK(ag_layout(t, 1, &cnt, &off, &dts, &mt, &dst));
+    CHK(ag_own_block(t, dst, cnt, off, mt));
+#define AGV_ID(_round, _b) ((unsigned)((_round) * N + (_b)))
+    if (p.type == UCC_KN_NODE_EXTRA) {
+        CHK(shm_prog_send(t, p.partner, dst + off[r], cnt[r], mt, AGV_ID(0, r))); CHK(shm_prog_wait(t));
+        for (ucc_rank_t b = 0; b < N; b++) if (b != r) CHK(shm_prog_recv(t, p.partner, dst + off[b], cnt[b], mt, AGV_ID(23, b)));
+        CHK(shm_prog_wait(t));
+        return UCC_OK;
+    }
+    if (p.type == UCC_KN_NODE_PROXY) { CHK(shm_prog_recv(t, p.partner, dst + off[p.partner], cnt[p.partner], mt, AGV_ID(0, p.partner))); CHK(shm_prog_wait(t)); }
+    for (ucc_rank_t mask = 1; mask < p.n_full; mask <<= 1, round++) {
+        ucc_rank_t peer = r ^ mask, mine = (r / mask) * mask, theirs = (peer / mask) * mask;
+        for (ucc_rank_t q = 0; q < mask; q++) {
+            /* every base rank q of a group stands for itself and, if it is a proxy, for rank q + n_full */
+            for (ucc_rank_t b = mine + q; b < N; b += p.n_full) CHK(shm_prog_send(t, peer, dst + off[b], cnt[b], mt, AGV_ID(round, b)));
+            for (ucc_rank_t b = theirs + q; b < N; b += p.n_full) CHK(shm_prog_recv(t, peer, dst + off[b], cnt[b], mt, AGV_ID(round, b)));
+        }
+        CHK(shm_prog_wait(t));
+    }
+    if (p.type == UCC_KN_NODE_PROXY) {
+        for (ucc_rank_t b = 0; b < N; b++) if (b != p.partner) CHK(shm_prog_send(t, p.partner, dst + off[b], cnt[b], mt, AGV_ID(23, b)));
+        CHK(shm_prog_wait(t));
+    }
+#undef AGV_ID
+err:
+    return st;
+}
 
 /* ================================================================== */
 /* alltoall(v)                                                         */
@@ -732,24 +768,69 @@ ucc_status_t ucc_tl_shm_alltoall_onesided(ucc_tl_shm_task_t *t) { return a2a_one
 ucc_status_t ucc_tl_shm_alltoallv_onesided(ucc_tl_shm_task_t *t) { return a2a_onesided(t, 1); }
 /* Bruck alltoall: log2(N) rounds, each moving the blocks whose index has bit k set (latency optimal for small blocks) */
 #define UCC_TL_SHM_MAX_BRUCK 1024
-ucc_status_t ucc_tl_shm_alltoall_bruck(ucc_tl_shm_task_t *t)
+/* the log2(N) exchange rounds of Bruck's alltoall on N slots of `blk` bytes: on entry w[i] = data for rank (r + i) % N, on exit
+ * w[i] = data from rank (r - i + N) % N (index math: coll_patterns/bruck_alltoall.h) */
+static ucc_status_t bruck_rounds(ucc_tl_shm_task_t *t, char *w, char *pk, size_t blk, ucc_memory_type_t mt, unsigned step)
 {
-    ucc_coll_args_t *a = ARGS(t); ucc_rank_t N = t->vsize, r = t->vrank; int inplace = UCC_IS_INPLACE(*a);
-    size_t blk = a->dst.info.count / N * ucc_dt_size(a->dst.info.datatype);
-    ucc_memory_type_t mt = a->dst.info.mem_type; char *dst = (char *)a->dst.info.buffer, *src = inplace ? dst : (char *)a->src.info.buffer;
-    void *wv, *pv; char *w, *pk; ucc_status_t st; unsigned step = 1;
-    if ((!inplace && a->src.info.mem_type != mt) || N > UCC_TL_SHM_MAX_BRUCK) return UCC_ERR_NOT_SUPPORTED;
-    CHK(shm_task_scratch(t, blk * N, mt, &wv)); CHK(shm_task_scratch(t, blk * N, mt, &pv)); w = (char *)wv; pk = (char *)pv;
-    /* phase 1: local rotation, w[i] = src[(r+i)%N] */
-    CHK(shm_prog_copy(t, w, src + (size_t)r * blk, (N - r) * blk, mt, mt)); if (r) CHK(shm_prog_copy(t, w + (size_t)(N - r) * blk, src, (size_t)r * blk, mt, mt));
-    for (unsigned k = 0; k < ucc_bruck_n_steps(N); k++, step++) {   /* index math: coll_patterns/bruck_alltoall.h */
+    ucc_rank_t N = t->vsize, r = t->vrank; ucc_status_t st = UCC_OK;
+    for (unsigned k = 0; k < ucc_bruck_n_steps(N); k++, step++) {
         ucc_rank_t idx[UCC_TL_SHM_MAX_BRUCK], n = ucc_bruck_step_blocks(N, k, idx);
         for (ucc_rank_t j = 0; j < n; j++) CHK(shm_prog_copy(t, pk + (size_t)j * blk, w + (size_t)idx[j] * blk, blk, mt, mt));
         CHK(shm_prog_send(t, ucc_bruck_send_peer(r, N, k), pk, (size_t)n * blk, mt, step)); CHK(shm_prog_recv(t, ucc_bruck_recv_peer(r, N, k), pk + (size_t)n * blk, (size_t)n * blk, mt, step)); CHK(shm_prog_wait(t));
         for (ucc_rank_t j = 0; j < n; j++) CHK(shm_prog_copy(t, w + (size_t)idx[j] * blk, pk + (size_t)(n + j) * blk, blk, mt, mt));
     }
+err:
+    return st;
+}
+/* Bruck alltoall: log2(N) rounds, each moving the blocks whose index has bit k set (latency optimal for small blocks) */
+ucc_status_t ucc_tl_shm_alltoall_bruck(ucc_tl_shm_task_t *t)
+{
+    ucc_coll_args_t *a = ARGS(t); ucc_rank_t N = t->vsize, r = t->vrank; int inplace = UCC_IS_INPLACE(*a);
+    size_t blk = a->dst.info.count / N * ucc_dt_size(a->dst.info.datatype);
+    ucc_memory_type_t mt = a->dst.info.mem_type; char *dst = (char *)a->dst.info.buffer, *src = inplace ? dst : (char *)a->src.info.buffer;
+    void *wv, *pv; char *w, *pk; ucc_status_t st;
+    if ((!inplace && a->src.info.mem_type != mt) || N > UCC_TL_SHM_MAX_BRUCK) return UCC_ERR_NOT_SUPPORTED;
+    CHK(shm_task_scratch(t, blk * N, mt, &wv)); CHK(shm_task_scratch(t, blk * N, mt, &pv)); w = (char *)wv; pk = (char *)pv;
+    /* phase 1: local rotation, w[i] = src[(r+i)%N] */
+    CHK(shm_prog_copy(t, w, src + (size_t)r * blk, (N - r) * blk, mt, mt)); if (r) CHK(shm_prog_copy(t, w + (size_t)(N - r) * blk, src, (size_t)r * blk, mt, mt));
+    CHK(bruck_rounds(t, w, pk, blk, mt, 1));
     /* phase 3: inverse rotation, dst[(r - i + N) % N] = w[i] */
     for (ucc_rank_t i = 0; i < N; i++) CHK(shm_prog_copy(t, dst + (size_t)ucc_bruck_final_src(r, N, i) * blk, w + (size_t)i * blk, blk, mt, mt));
+err:
+    return st;
+}
+/* hybrid alltoallv (role of reference tl/ucp alltoallv_hybrid.c): a message of at most ALLTOALLV_HYBRID_THRESH bytes travels in a
+ * fixed slot through Bruck's log2(N) rounds together with all the other small ones (N-1 latencies become log2 N), everything
+ * bigger goes pairwise, straight from the send to the receive buffer.  Sender and receiver classify a message by its size, which
+ * both know (what s sends to d is what d receives from s), so the two paths never disagree. */
+ucc_status_t ucc_tl_shm_alltoallv_hybrid(ucc_tl_shm_task_t *t)
+{
+    ucc_coll_args_t *a = ARGS(t); ucc_rank_t N = t->vsize, r = t->vrank;
+    size_t T = SHM_CTX(t->team)->cfg.alltoallv_hybrid_thresh, sdt = ucc_dt_size(a->src.info_v.datatype), ddt = ucc_dt_size(a->dst.info_v.datatype);
+    ucc_memory_type_t smt = a->src.info_v.mem_type, dmt = a->dst.info_v.mem_type;
+    char *src = (char *)a->src.info_v.buffer, *dst = (char *)a->dst.info_v.buffer, *w, *pk; void *wv, *pv; ucc_status_t st; int any_small = 0;
+    if (UCC_IS_INPLACE(*a) || smt != dmt || N > UCC_TL_SHM_MAX_BRUCK || N < 3 || !T) return UCC_ERR_NOT_SUPPORTED;
+#define HS(_i) (ucc_coll_args_get_count(a, a->src.info_v.counts, _i) * sdt)
+#define HSO(_i) (ucc_coll_args_get_displacement(a, a->src.info_v.displacements, _i) * sdt)
+#define HD(_i) (ucc_coll_args_get_count(a, a->dst.info_v.counts, _i) * ddt)
+#define HDO(_i) (ucc_coll_args_get_displacement(a, a->dst.info_v.displacements, _i) * ddt)
+    T = ucc_align_up(T, 8);
+    CHK(shm_task_scratch(t, T * N, dmt, &wv)); CHK(shm_task_scratch(t, T * N, dmt, &pv)); w = (char *)wv; pk = (char *)pv;
+    /* big messages first: they are in flight while the small ones hop */
+    for (ucc_rank_t s = 1; s < N; s++) {
+        ucc_rank_t to = (r + s) % N, from = (r + N - s) % N;
+        if (HD(from) > T) CHK(shm_prog_recv(t, from, dst + HDO(from), HD(from), dmt, 100));
+        if (HS(to) > T) CHK(shm_prog_send(t, to, src + HSO(to), HS(to), smt, 100));
+    }
+    for (ucc_rank_t i = 0; i < N; i++) { ucc_rank_t d = (r + i) % N; if (HS(d) <= T) { any_small = 1; if (HS(d) != 0) CHK(shm_prog_copy(t, w + (size_t)i * T, src + HSO(d), HS(d), dmt, smt)); } }
+    (void)any_small; /* the rounds run even if I have nothing small to send: other ranks' small blocks are routed through me */
+    CHK(bruck_rounds(t, w, pk, T, dmt, 1));
+    for (ucc_rank_t i = 0; i < N; i++) { ucc_rank_t s_ = ucc_bruck_final_src(r, N, i); if (HD(s_) <= T && HD(s_) != 0) CHK(shm_prog_copy(t, dst + HDO(s_), w + (size_t)i * T, HD(s_), dmt, dmt)); }
+    CHK(shm_prog_wait(t));
+#undef HS
+#undef HSO
+#undef HD
+#undef HDO
 err:
     return st;
 }

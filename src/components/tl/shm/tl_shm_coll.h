@@ -12,7 +12,7 @@ SHM_ALG(reduce_scatter_ring); SHM_ALG(reduce_scatter_knomial); SHM_ALG(reduce_sc
 SHM_ALG(allgather_knomial); SHM_ALG(allgather_ring); SHM_ALG(allgather_neighbor); SHM_ALG(allgather_bruck);
 SHM_ALG(allgather_sparbit); SHM_ALG(allgather_linear); SHM_ALG(allgather_batched);
 SHM_ALG(allgatherv_ring); SHM_ALG(allgatherv_knomial); SHM_ALG(allgatherv_linear);
-SHM_ALG(alltoall_pairwise); SHM_ALG(alltoall_bruck); SHM_ALG(alltoallv_pairwise); SHM_ALG(alltoall_onesided); SHM_ALG(alltoallv_onesided);
+SHM_ALG(alltoall_pairwise); SHM_ALG(alltoall_bruck); SHM_ALG(alltoallv_pairwise); SHM_ALG(alltoallv_hybrid); SHM_ALG(alltoall_onesided); SHM_ALG(alltoallv_onesided);
 SHM_ALG(gather_knomial); SHM_ALG(gather_linear); SHM_ALG(gatherv_linear);
 SHM_ALG(scatter_knomial); SHM_ALG(scatter_linear); SHM_ALG(scatterv_linear);
 ucc_status_t ucc_tl_shm_bcast_knomial_prog(ucc_tl_shm_task_t *t, void *buf, size_t len, ucc_memory_type_t mt, ucc_rank_t root, unsigned radix);

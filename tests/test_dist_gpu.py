@@ -81,6 +81,16 @@ def test_multiproc_ring_rhd():
     _run(n, {"UCC_TL_NVL_TUNE": "allreduce:cuda:inf:@ring#reduce_scatter:cuda:inf:@rhd#allgather:cuda:inf:@ring", "UCC_TL_NVL_ZCOPY": "n"})
 
 
+@pytest.mark.parametrize("alg", ["rab", "split_rail"])
+def test_multiproc_hier_fake_nodes(alg):
+    """cl/hier schedules on CUDA buffers with real processes: every GPU pretends to be its own node (UCC_B200_FAKE_PPN=1), so node
+    sub-teams are single-member tl/nvl teams and the leaders / rail sub-teams cross "nodes" (host TL + mc/ec staging)."""
+    n = min(2, torch.cuda.device_count()) if torch.cuda.is_available() else 0
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    _run(n, {"UCC_B200_FAKE_PPN": "1", "UCC_CLS": "hier,basic", "UCC_CL_HIER_TUNE": f"allreduce:0-inf:@{alg}"})
+
+
 def test_torch_backend_cuda():
     """init_process_group("ucc_b200"): c10d collectives and torch DDP on CUDA tensors run on the tl/nvl kernels."""
     n = min(2, torch.cuda.device_count()) if torch.cuda.is_available() else 0   # validated on 2 GPUs
@@ -93,7 +103,7 @@ def test_torch_backend_cuda():
 
 
 @pytest.mark.skipif(os.environ.get("UCC_B200_EXPERIMENTAL_TESTS") != "1", reason="nvls_pipe was written without GPU time left: set UCC_B200_EXPERIMENTAL_TESTS=1")
-@pytest.mark.parametrize("heap", ["128M", "3M"])
+@pytest.mark.parametrize("heap", ["128M", "24M"])
 def test_multiproc_nvls_pipe(heap):
     """Pipelined staged NVLS allreduce (kernels/nvl_pipe.cu); the small heap forces many chunks so the three buffers rotate."""
     n = min(2, torch.cuda.device_count()) if torch.cuda.is_available() else 0

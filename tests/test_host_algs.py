@@ -160,3 +160,48 @@ def test_sliding_window_multi_window_inplace(n):
             run(team, [coll_args("allreduce", None if inplace else src[r], dst[r], dt="float64", op="sum", inplace=inplace) for r in range(n)])
             for r in range(n):
                 assert np.allclose(dst[r], exp), (inplace, r)
+
+
+@pytest.mark.parametrize("n", [3, 4, 5, 8, 11])
+def test_alltoallv_hybrid_mixed_sizes(n):
+    """hybrid alltoallv: messages below ALLTOALLV_HYBRID_THRESH ride Bruck's rounds in fixed slots, bigger ones go pairwise; sizes
+    on both sides of the threshold, empty messages, and a threshold that is not a multiple of the element size"""
+    for thresh in ("256", "100"):
+        env = {"UCC_TL_SHM_TUNE": "alltoallv:@hybrid", "UCC_TL_SHM_ALLTOALLV_HYBRID_THRESH": thresh, "UCC_TLS": "shm,self"}
+        with UccJob(n, env=env) as j:
+            team = j.create_team()
+            rng = np.random.default_rng(n)
+
+            def cnt(s, d):       # elements s sends to d: 0, a few, around the threshold, far above
+                return [0, 3, 24, 25, 26, 64, 65, 500][(3 * s + 5 * d + s * d) % 8]
+            sc = [[cnt(r, p) for p in range(n)] for r in range(n)]
+            rc = [[cnt(p, r) for p in range(n)] for r in range(n)]
+            sd = [np.concatenate([[0], np.cumsum(c)[:-1]]) for c in sc]
+            rd = [np.concatenate([[0], np.cumsum(c)[:-1]]) for c in rc]
+            src = [rng.random(max(1, sum(sc[r]))).astype(np.float32) for r in range(n)]
+            dst = [np.full(max(1, sum(rc[r])), -1, np.float32) for r in range(n)]
+            run(team, [coll_args("alltoallv", src[r], dst[r], src_counts=sc[r], src_displs=sd[r], dst_counts=rc[r], dst_displs=rd[r]) for r in range(n)])
+            for r in range(n):
+                exp = np.concatenate([src[p][sd[p][r]:sd[p][r] + sc[p][r]] for p in range(n)])
+                assert np.array_equal(dst[r][:len(exp)], exp), (n, thresh, r)
+
+
+@pytest.mark.parametrize("n", [2, 3, 5, 6, 7, 8, 13])
+def test_allgatherv_knomial_shuffled_displacements(n):
+    """recursive-doubling allgatherv with extra ranks (non power-of-two teams) and blocks that are NOT laid out in rank order"""
+    with UccJob(n, env={"UCC_TL_SHM_TUNE": "allgatherv:@knomial", "UCC_TLS": "shm,self"}) as j:
+        team = j.create_team()
+        rng = np.random.default_rng(7 * n)
+        counts = [int(c) for c in rng.integers(0, 300, n)]
+        order = list(rng.permutation(n))
+        displs = [0] * n
+        o = 0
+        for r in order:                      # block of rank `r` sits where the permutation puts it, with gaps
+            displs[r] = o
+            o += counts[r] + 3
+        src = [rng.integers(0, 1000, counts[r]).astype(np.int32) for r in range(n)]
+        dst = [np.full(o, -7, np.int32) for _ in range(n)]
+        run(team, [coll_args("allgatherv", src[r], dst[r], dt="int32", dst_counts=counts, dst_displs=displs) for r in range(n)])
+        for r in range(n):
+            for p in range(n):
+                assert np.array_equal(dst[r][displs[p]:displs[p] + counts[p]], src[p]), (n, r, p)

@@ -551,6 +551,13 @@ EXPERIMENTAL = pytest.mark.skipif(os.environ.get("UCC_B200_EXPERIMENTAL_TESTS") 
 def test_cl_hier_on_cuda_buffers(alg):
     """cl/hier with a synthetic 2-node x 4-GPU placement: node / leaders / rail sub-teams are tl/nvl teams over sub-group maps."""
     need_cuda()
+    if alg == "rab":
+        # rab lets the non-leaders enter the node bcast while the leaders still run their cross-node allreduce through the host TL
+        # (device buffers staged through mc/ec).  With ALL eight ranks emulated on ONE device, the leaders' device-wide
+        # synchronisations (cudaFree / synchronous copies of that staging) wait for the other ranks' spinning bcast kernels, which
+        # wait for the leaders: it only resolves through the device-side timeout.  One process per GPU has no such coupling: the
+        # schedule is covered with real processes by tests/test_dist_gpu.py::test_multiproc_hier_fake_nodes.
+        pytest.skip("single-device emulation couples the ranks through device-wide synchronisation; covered by test_multiproc_hier_fake_nodes")
     env = dict(ENV, UCC_CLS="hier,basic", UCC_CL_HIER_TUNE=f"allreduce:0-inf:@{alg}", **NOZC)
     with UccJob(8, ppn=4, env=env, cls="hier,basic") as j:
         team = j.create_team()

@@ -1,23 +1,50 @@
 #!/bin/bash
-# Round-2 validation on N GPUs:  gpurun --gpus N --timeout 1500 -- 'bash tools/gpu_r2_validate.sh N'
-# 1. the whole GPU suite incl. the kernels that had never run on hardware (UCC_B200_EXPERIMENTAL_TESTS=1)
-# 2. reference arm + our arm of bench.py   3. allreduce algorithm matrix   4. the other collectives (default vs push)
-export PYTHONPATH=$PWD UCC_HANDLE_ERRORS=bt
+# Round-2 validation on N GPUs:  gpurun --gpus N --timeout 900 -- 'bash tools/gpu_r2_validate.sh N [sections]'
+# sections: tests  = the whole multi-process GPU suite            smoke = only test_multiproc_all_gpus
+#           bench  = both arms of bench.py                        matrix = allreduce algorithm / SM-budget matrix (one launch)
+#           colls  = the other collectives, default / push / ce variants (one launch)
+export PYTHONPATH=$PWD
 N=${1:-2}
+SECT=${2:-"tests bench matrix colls"}
 O=gpurun_out/r2v$N
 mkdir -p $O
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29821"
-nvidia-smi topo -m > $O/topo.txt 2>&1
-UCC_B200_EXPERIMENTAL_TESTS=1 timeout 900 python -m pytest tests -m gpu -q --durations=15 -p no:cacheprovider > $O/pytest.log 2>&1; echo "rc=$?" >> $O/pytest.log
-timeout 300 $TR bench.py --impl reference --gpus $N --steps 10 --warmup 3 --out $O/bench_ref.json > $O/bench_ref.log 2>&1
-timeout 400 $TR bench.py --gpus $N --steps 10 --warmup 3 --out $O/bench_ours.json > $O/bench_ours.log 2>&1
-for alg in nvls nvls_pipe twoshot; do
-  UCC_TL_NVL_TUNE="allreduce:cuda:inf:@$alg" UCC_TL_NVL_ALLREDUCE_ONESHOT_THRESH=0 timeout 200 $TR bench.py --gpus $N --steps 10 --warmup 3 --no-sweep --no-e2e --out $O/bench_$alg.json > $O/bench_$alg.log 2>&1
-done
-UCC_TL_NVL_SYMMETRIC_SIZE=384M UCC_TL_NVL_TUNE="allreduce:cuda:inf:@nvls_pipe" UCC_TL_NVL_ALLREDUCE_ONESHOT_THRESH=0 timeout 200 $TR bench.py --gpus $N --steps 10 --warmup 3 --no-sweep --no-e2e --out $O/bench_nvls_pipe_384.json > $O/bench_nvls_pipe_384.log 2>&1
-timeout 200 $TR bench.py --gpus $N --steps 10 --warmup 3 --symm 3G --no-sweep --no-e2e --out $O/bench_symm.json > $O/bench_symm.log 2>&1
-timeout 200 $TR tools/coll_bench.py > $O/coll_default.log 2>&1
-UCC_TL_NVL_TUNE="allgather:cuda:inf:@push#alltoall:cuda:inf:@push#alltoallv:cuda:inf:@push" timeout 200 $TR tools/coll_bench.py > $O/coll_push.log 2>&1
-tail -4 $O/pytest.log
-for f in $O/bench_*.log; do echo "$f: $(tail -c 700 $f | tr '\n' ' ' | cut -c1-700)"; done
-tail -n 2 $O/coll_default.log | cut -c1-600; tail -n 2 $O/coll_push.log | cut -c1-600
+has() { [[ " $SECT " == *" $1 "* ]]; }
+if has tests; then
+  UCC_B200_EXPERIMENTAL_TESTS=1 timeout 600 python -m pytest tests/test_dist_gpu.py -m gpu -q --durations=20 -p no:cacheprovider > $O/pytest_dist.log 2>&1; echo "rc=$?" >> $O/pytest_dist.log
+  tail -25 $O/pytest_dist.log | cut -c1-400
+fi
+if has smoke; then
+  timeout 150 python -m pytest tests/test_dist_gpu.py -m gpu -q -k "all_gpus" -p no:cacheprovider > $O/pytest_smoke.log 2>&1; echo "rc=$?" >> $O/pytest_smoke.log
+  tail -6 $O/pytest_smoke.log | cut -c1-400
+fi
+if has bench; then
+  timeout 240 $TR bench.py --impl reference --gpus $N --steps 10 --warmup 3 --out $O/bench_ref.json > $O/bench_ref.log 2>&1
+  timeout 240 $TR bench.py --gpus $N --steps 10 --warmup 3 --out $O/bench_ours.json > $O/bench_ours.log 2>&1
+fi
+if has matrix; then
+  timeout 300 $TR tools/alg_matrix.py > $O/matrix.log 2>&1
+  grep '^{' $O/matrix.log | cut -c1-900
+fi
+if has colls; then
+  COLL_VARIANTS=${COLL_VARIANTS:-default,push,ce,nvls_ag,rs_nvls} timeout 300 $TR tools/coll_bench.py > $O/colls.log 2>&1
+  grep '^{' $O/colls.log | python -c "
+import json,sys
+for l in sys.stdin:
+    d=json.loads(l)
+    for r in d['rows']:
+        print({k:v for k,v in r.items() if k!='kernels'}, '|', r.get('kernels'))
+" | cut -c1-1200
+fi
+python - <<PY
+import glob, json, os
+for f in sorted(glob.glob("$O/bench_*.json")):
+    try:
+        d = json.load(open(f))
+        print(os.path.basename(f), "busbw/gpu", d.get("busbw_per_gpu_GBps"), "us", d.get("latency_us"), "ok", d.get("correct"), d.get("config", {}).get("algorithm", "")[-60:], "| e2e", (d.get("e2e") or {}).get("us_per_step"), "| ref", d.get("reference_arms"), "| nccl", d.get("nccl_same_box"))
+        for r in d.get("sweep", []):
+            print("   ", {k: r[k] for k in r if k in ("bytes", "us", "busbw", "ok", "alg", "nccl_us", "nccl_busbw", "tl_cuda_us", "tl_cuda_busbw")})
+    except Exception as e:
+        print(f, "unreadable", e)
+PY
+for f in $O/bench_*.log; do [ -s ${f%.log}.json ] || { echo "--- $f (no json)"; tail -c 800 $f; }; done

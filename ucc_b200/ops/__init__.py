@@ -105,10 +105,10 @@ def all_reduce_from_host(host, out, staging=None, op="sum", comm=None, chunks=No
     for (lo, hi), ev in zip(bounds, evs):
         stream.wait_event(ev)
         r = comm.allreduce_init(sflat[lo:hi], oflat[lo:hi], op=op)
-        r.post_on_stream(stream, wait_posted=False)
+        # wait until the kernel really is in the stream (a zero-copy collective launches once the members' buffers are known):
+        # the wait for the NEXT piece must be enqueued behind this kernel, not in front of it
+        r.post_on_stream(stream, wait_posted=True)
         reqs.append(r)
-    for r in reqs:
-        r.wait_posted()
     for r in reqs:
         r.wait()
         r.finalize()
