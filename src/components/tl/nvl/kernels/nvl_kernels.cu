@@ -155,19 +155,34 @@ __global__ void __launch_bounds__(NVL_THREADS_MAX, 2) nvl_exchange_kernel(nvl_xc
     /* phase B: pull.  Resolve every remote block first; when all of them are 16-byte aligned the vectors of up to eight
      * peers are requested together (one NVLink round trip instead of one per peer - what matters for the 1..64 MB range
      * where a thread owns only a few vectors of each block) */
-    const char *sp[NVL_MAX_PEERS]; char *dp[NVL_MAX_PEERS]; size_t nb[NVL_MAX_PEERS]; int np = 0; bool vec = true; size_t nvmax = 0;
-    for (int i = 1; i < N; i++) {
-        int p = me + i; if (p >= N) p -= N;
-        const size_t n = a.pull_bytes[p];
-        if (!n) continue;
-        size_t off = a.pull_off[p];
-        if (off == NVL_XCHG_LOOKUP) off = (size_t) * reinterpret_cast<volatile const uint64_t *>(data_of(t, p) + (size_t)me * 8);
-        sp[np] = (a.direct ? a.d.src[p] : (a.use_mc ? mydata : data_of(t, p)) + NVL_XCHG_TABLE_BYTES) + off;
-        dp[np] = static_cast<char *>(a.dst) + a.dst_off[p]; nb[np] = n;
-        if (((uintptr_t)sp[np] | (uintptr_t)dp[np]) & 15) vec = false;
-        if (n / 16 > nvmax) nvmax = n / 16;
-        np++;
+    /* the per-peer source / destination / length tables live in shared memory (built by one thread): they are indexed with
+     * run-time values in the batched loop below, which would put per-thread copies on the local-memory stack */
+#ifdef NVL_HOST_EMU   /* host emulation: no shared memory, every (OS) thread builds its own copy */
+    const char *sp[NVL_MAX_PEERS]; char *dp[NVL_MAX_PEERS]; size_t nb[NVL_MAX_PEERS]; int s_np; int s_vec; size_t s_nvmax;
+    const bool fill = true;
+#else
+    __shared__ const char *sp[NVL_MAX_PEERS]; __shared__ char *dp[NVL_MAX_PEERS]; __shared__ size_t nb[NVL_MAX_PEERS];
+    __shared__ int s_np; __shared__ int s_vec; __shared__ size_t s_nvmax;
+    const bool fill = threadIdx.x == 0;
+#endif
+    if (fill) {
+        int np_ = 0; int vec_ = 1; size_t nvmax_ = 0;
+        for (int i = 1; i < N; i++) {
+            int p = me + i; if (p >= N) p -= N;
+            const size_t n = a.pull_bytes[p];
+            if (!n) continue;
+            size_t off = a.pull_off[p];
+            if (off == NVL_XCHG_LOOKUP) off = (size_t) * reinterpret_cast<volatile const uint64_t *>(data_of(t, p) + (size_t)me * 8);
+            sp[np_] = (a.direct ? a.d.src[p] : (a.use_mc ? mydata : data_of(t, p)) + NVL_XCHG_TABLE_BYTES) + off;
+            dp[np_] = static_cast<char *>(a.dst) + a.dst_off[p]; nb[np_] = n;
+            if (((uintptr_t)sp[np_] | (uintptr_t)dp[np_]) & 15) vec_ = 0;
+            if (n / 16 > nvmax_) nvmax_ = n / 16;
+            np_++;
+        }
+        s_np = np_; s_vec = vec_; s_nvmax = nvmax_;
     }
+    __syncthreads();
+    const int np = s_np; const bool vec = s_vec != 0; const size_t nvmax = s_nvmax;
     if (a.pull_bytes[me]) { /* own block: a local copy */
         char *d = static_cast<char *>(a.dst) + a.dst_off[me];
         if (d != static_cast<const char *>(a.src) + a.self_off) copy_bytes_grid<false>(d, static_cast<const char *>(a.src) + a.self_off, a.pull_bytes[me]);

@@ -193,7 +193,7 @@ static void run_xchg(World &w, int mode, size_t blk, int nb, int nt, size_t misa
             }
             a.self_off = a2a ? (size_t)r * blk : 0;
             if (mode == XCHG_AG_MC) { a.use_mc = 1; a.push_off = (size_t)r * ablk; }
-            if (mode == XCHG_AG_RING) a.ring = 1;
+            if (mode == XCHG_AG_RING) { a.ring = 1; a.ring_pos = r; for (int q = 0; q < N; q++) a.ring_order[q] = q; }
             nvl_exchange_kernel(a);
         });
         CHECK(w.host_err == 0);

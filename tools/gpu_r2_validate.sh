@@ -36,6 +36,16 @@ for l in sys.stdin:
         print({k:v for k,v in r.items() if k!='kernels'}, '|', r.get('kernels'))
 " | cut -c1-1200
 fi
+if has colls || has nvlink; then
+  timeout 200 $TR tools/nvlink_traffic.py > $O/nvlink.log 2>&1
+  grep '^{' $O/nvlink.log | python -c "
+import json,sys
+for l in sys.stdin:
+    d=json.loads(l)
+    r=(d.get('per_rank') or [d])[0]
+    print(d.get('case'), '|', {k:r.get(k) for k in ('kernel','us','alg_tx_MB','nvlink_tx_MB','nvlink_rx_MB','tx_GBps','frac_of_900_tx','nvlink_counters','error') if r.get(k) is not None})
+"
+fi
 python - <<PY
 import glob, json, os
 for f in sorted(glob.glob("$O/bench_*.json")):
