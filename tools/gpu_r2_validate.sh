@@ -9,25 +9,29 @@ SECT=${2:-"tests bench matrix colls"}
 O=gpurun_out/r2v$N
 mkdir -p $O
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29821"
-has() { [[ " $SECT " == *" $1 "* ]]; }
+T0=$(date +%s)
+BUDGET=${BUDGET:-430}      # seconds: sections that would start after this are skipped (an N-GPU box is charged N x wall time)
+left() { echo $(( BUDGET - ($(date +%s) - T0) )); }
+has() { [[ " $SECT " == *" $1 "* ]] && [ $(left) -gt 20 ]; }
+cap() { local want=$1; local l=$(left); [ $l -lt $want ] && echo $l || echo $want; }
 if has tests; then
   UCC_B200_EXPERIMENTAL_TESTS=1 timeout 600 python -m pytest tests/test_dist_gpu.py -m gpu -q --durations=20 -p no:cacheprovider > $O/pytest_dist.log 2>&1; echo "rc=$?" >> $O/pytest_dist.log
   tail -25 $O/pytest_dist.log | cut -c1-400
 fi
 if has smoke; then
-  timeout 150 python -m pytest tests/test_dist_gpu.py -m gpu -q -k "all_gpus" -p no:cacheprovider > $O/pytest_smoke.log 2>&1; echo "rc=$?" >> $O/pytest_smoke.log
+  timeout $(cap 60) python -m pytest tests/test_dist_gpu.py -m gpu -q -k "all_gpus" -p no:cacheprovider > $O/pytest_smoke.log 2>&1; echo "rc=$?" >> $O/pytest_smoke.log
   tail -6 $O/pytest_smoke.log | cut -c1-400
 fi
 if has bench; then
-  timeout 240 $TR bench.py --impl reference --gpus $N --steps 10 --warmup 3 --out $O/bench_ref.json > $O/bench_ref.log 2>&1
-  timeout 240 $TR bench.py --gpus $N --steps 10 --warmup 3 --out $O/bench_ours.json > $O/bench_ours.log 2>&1
+  timeout $(cap 150) $TR bench.py --impl reference --gpus $N --steps 10 --warmup 3 --out $O/bench_ref.json > $O/bench_ref.log 2>&1
+  timeout $(cap 150) $TR bench.py --gpus $N --steps 10 --warmup 3 --out $O/bench_ours.json > $O/bench_ours.log 2>&1
 fi
 if has matrix; then
-  timeout 300 $TR tools/alg_matrix.py > $O/matrix.log 2>&1
+  MATRIX_VARIANTS=${MATRIX_VARIANTS:-default,twoshot,nvls,nvls_pipe,nvls_pipe384,symm,symm_nb32,symm_nb64,default_nb64} timeout $(cap 120) $TR tools/alg_matrix.py > $O/matrix.log 2>&1
   grep '^{' $O/matrix.log | cut -c1-900
 fi
 if has colls; then
-  COLL_VARIANTS=${COLL_VARIANTS:-default,push,ce,nvls_ag,rs_nvls} timeout 300 $TR tools/coll_bench.py > $O/colls.log 2>&1
+  COLL_VARIANTS=${COLL_VARIANTS:-default,push,ce} timeout $(cap 100) $TR tools/coll_bench.py > $O/colls.log 2>&1
   grep '^{' $O/colls.log | python -c "
 import json,sys
 for l in sys.stdin:
@@ -37,7 +41,7 @@ for l in sys.stdin:
 " | cut -c1-1200
 fi
 if has colls || has nvlink; then
-  timeout 200 $TR tools/nvlink_traffic.py > $O/nvlink.log 2>&1
+  timeout $(cap 80) $TR tools/nvlink_traffic.py > $O/nvlink.log 2>&1
   grep '^{' $O/nvlink.log | python -c "
 import json,sys
 for l in sys.stdin:
