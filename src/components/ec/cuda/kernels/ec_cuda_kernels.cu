@@ -85,7 +85,16 @@ static __device__ __noinline__ void reduce_any(const ec_reduce_args_t &a, size_t
 }
 #define EC_GRID_TID ((size_t)blockIdx.x * blockDim.x + threadIdx.x)
 #define EC_GRID_NT ((size_t)gridDim.x * blockDim.x)
-__global__ void __launch_bounds__(1024) ec_reduce_kernel(ec_reduce_args_t a) { reduce_any(a, EC_GRID_TID, EC_GRID_NT); }
+/* one-shot reduce: (datatype, operator) picked on the HOST at launch - one body per kernel; the persistent executor below has to
+ * switch at run time (reduce_any) because its tasks arrive while it is running */
+template <typename T, int OP> __global__ void __launch_bounds__(1024) ec_reduce_kernel_t(const __grid_constant__ ec_reduce_args_t a) { reduce_body<T, OP>(a, EC_GRID_TID, EC_GRID_NT); }
+template <typename T, int OP> __global__ void __launch_bounds__(1024) ec_reduce_cplx_kernel_t(const __grid_constant__ ec_reduce_args_t a) { reduce_body_cplx<T, OP>(a, EC_GRID_TID, EC_GRID_NT); }
+template <typename T> static cudaError_t ec_launch_reduce_t(const ec_reduce_args_t *a, int nb, int nt, cudaStream_t s)
+{
+#define CALL_EC_LAUNCH(_T, _OP) ec_reduce_kernel_t<_T, _OP><<<nb, nt, 0, s>>>(*a)
+    NVL_DISPATCH_OP(T, a->op, CALL_EC_LAUNCH);
+    return cudaGetLastError();
+}
 
 /* up to 7 independent dst[j] = src1[j] op src2[j]; blockIdx.y selects the buffer */
 __global__ void __launch_bounds__(1024) ec_reduce_multi_dst_kernel(ec_reduce_multi_dst_args_t m)
@@ -179,7 +188,27 @@ extern "C" int ec_dt_supports_op(int dt, int op)
     return 1;
 }
 extern "C" cudaError_t ec_launch_reduce(const ec_reduce_args_t *a, int nblocks, int nthreads, cudaStream_t s)
-{ ec_reduce_kernel<<<nblocks, nthreads, 0, s>>>(*a); return cudaGetLastError(); }
+{
+    switch (a->dt) {
+    case EC_DT_I8: return ec_launch_reduce_t<int8_t>(a, nblocks, nthreads, s); case EC_DT_I16: return ec_launch_reduce_t<int16_t>(a, nblocks, nthreads, s);
+    case EC_DT_I32: return ec_launch_reduce_t<int32_t>(a, nblocks, nthreads, s); case EC_DT_I64: return ec_launch_reduce_t<int64_t>(a, nblocks, nthreads, s);
+    case EC_DT_U8: return ec_launch_reduce_t<uint8_t>(a, nblocks, nthreads, s); case EC_DT_U16: return ec_launch_reduce_t<uint16_t>(a, nblocks, nthreads, s);
+    case EC_DT_U32: return ec_launch_reduce_t<uint32_t>(a, nblocks, nthreads, s); case EC_DT_U64: return ec_launch_reduce_t<uint64_t>(a, nblocks, nthreads, s);
+    case EC_DT_F16: return ec_launch_reduce_t<__half>(a, nblocks, nthreads, s); case EC_DT_BF16: return ec_launch_reduce_t<__nv_bfloat16>(a, nblocks, nthreads, s);
+    case EC_DT_F32: return ec_launch_reduce_t<float>(a, nblocks, nthreads, s); case EC_DT_F64: return ec_launch_reduce_t<double>(a, nblocks, nthreads, s);
+    case EC_DT_C64:
+        if (a->op == EC_OP_SUM) ec_reduce_cplx_kernel_t<cuFloatComplex, EC_OP_SUM><<<nblocks, nthreads, 0, s>>>(*a);
+        else if (a->op == EC_OP_PROD) ec_reduce_cplx_kernel_t<cuFloatComplex, EC_OP_PROD><<<nblocks, nthreads, 0, s>>>(*a);
+        else return cudaErrorInvalidValue;
+        return cudaGetLastError();
+    case EC_DT_C128:
+        if (a->op == EC_OP_SUM) ec_reduce_cplx_kernel_t<cuDoubleComplex, EC_OP_SUM><<<nblocks, nthreads, 0, s>>>(*a);
+        else if (a->op == EC_OP_PROD) ec_reduce_cplx_kernel_t<cuDoubleComplex, EC_OP_PROD><<<nblocks, nthreads, 0, s>>>(*a);
+        else return cudaErrorInvalidValue;
+        return cudaGetLastError();
+    default: return cudaErrorInvalidValue;
+    }
+}
 extern "C" cudaError_t ec_launch_reduce_multi_dst(const ec_reduce_multi_dst_args_t *a, int nthreads, cudaStream_t s)
 { ec_reduce_multi_dst_kernel<<<dim3(4, a->n_bufs), nthreads, 0, s>>>(*a); return cudaGetLastError(); }
 extern "C" cudaError_t ec_launch_copy_multi(const ec_copy_multi_args_t *a, int nthreads, cudaStream_t s)
