@@ -69,6 +69,7 @@ static ucc_status_t nvl_ctx_create(const ucc_base_context_params_t *p, const ucc
     ctx = (ucc_tl_nvl_context_t *)calloc(1, sizeof(*ctx));
     if (!ctx) return UCC_ERR_NO_MEMORY;
     ctx->super.super.ucc_context = p->context; ctx->super.super.lib = config->lib; ctx->tm = p->thread_mode;
+    ctx->n_ev_cache = 0; ucc_spinlock_init(&ctx->ev_lock);
     if (ucc_config_parser_clone_opts(config, &ctx->cfg, ucc_tl_nvl_context_config_table) != UCC_OK) { free(ctx); return UCC_ERR_NO_MEMORY; }
     ctx->dev = dev; ctx->sm_count = prop.multiProcessorCount;
     ctx->addr.host_hash = p->context->proc_info.host_hash; ctx->addr.pid = (int32_t)getpid(); ctx->addr.dev = dev;
@@ -110,6 +111,7 @@ static void nvl_ctx_destroy(ucc_base_context_t *b)
 {
     ucc_tl_nvl_context_t *ctx = ucc_derived_of(b, ucc_tl_nvl_context_t);
     ucc_mpool_cleanup(&ctx->task_mp, 1);
+    for (unsigned i = 0; i < ctx->n_ev_cache; i++) cudaEventDestroy(ctx->ev_cache[i]);
     ucc_config_parser_release_opts(&ctx->cfg, ucc_tl_nvl_context_config_table);
     free(ctx);
 }

@@ -54,6 +54,7 @@ typedef struct ucc_tl_nvl_context_config {
 
 /* ---- zero-copy buffer exchange board (tl_nvl_direct.c): one single-writer POSIX shm segment per rank ---- */
 #define NVL_MAX_LANES 8
+#define NVL_EVENT_CACHE 256
 #define NVL_XB_SLOTS 64
 #define NVL_GATE_SLOTS 1024
 #define NVL_IPC_CACHE_MAX 64
@@ -79,6 +80,10 @@ typedef struct ucc_tl_nvl_context {
     unsigned                    lane_blocks;   /* CTAs one collective kernel may use: all lanes of a team together stay co-resident */
     ucc_mpool_t                 task_mp;
     ucc_thread_mode_t           tm;
+    /* completion events are recycled: creating / destroying one per request costs more host time than launching a small collective */
+    cudaEvent_t                 ev_cache[NVL_EVENT_CACHE];
+    unsigned                    n_ev_cache;
+    ucc_spinlock_t              ev_lock;
 } ucc_tl_nvl_context_t;
 
 typedef enum { NVL_HEAP_LOCAL, NVL_HEAP_VMM, NVL_HEAP_IPC } nvl_heap_kind_t;

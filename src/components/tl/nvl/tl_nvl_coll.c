@@ -320,6 +320,7 @@ static ucc_status_t nvl_triggered_post(ucc_ee_h ee, ucc_ev_t *ev, ucc_coll_task_
     ucc_ee_set_event_internal(ee, &post_event, &ee->event_out_queue);
     return UCC_OK;
 }
+static void event_put(ucc_tl_nvl_context_t *ctx, cudaEvent_t e);
 static ucc_status_t nvl_finalize(ucc_coll_task_t *ct)
 {
     ucc_tl_nvl_task_t *t = ucc_derived_of(ct, ucc_tl_nvl_task_t);
@@ -333,12 +334,28 @@ static ucc_status_t nvl_finalize(ucc_coll_task_t *ct)
     }
     ucc_spin_unlock(&team->launch_lock);
     if (t->in_event) cudaEventDestroy(t->in_event);
-    if (t->event) cudaEventDestroy(t->event);
+    if (t->event) event_put(NVL_CTX(team), t->event);
     ucc_coll_task_destruct(ct);
     ucc_mpool_put(t);
     return UCC_OK;
 }
 
+static cudaEvent_t event_get(ucc_tl_nvl_context_t *ctx)
+{
+    cudaEvent_t e = NULL;
+    ucc_spin_lock(&ctx->ev_lock);
+    if (ctx->n_ev_cache) e = ctx->ev_cache[--ctx->n_ev_cache];
+    ucc_spin_unlock(&ctx->ev_lock);
+    if (!e && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { (void)cudaGetLastError(); return NULL; }
+    return e;
+}
+static void event_put(ucc_tl_nvl_context_t *ctx, cudaEvent_t e)
+{
+    ucc_spin_lock(&ctx->ev_lock);
+    if (ctx->n_ev_cache < NVL_EVENT_CACHE) { ctx->ev_cache[ctx->n_ev_cache++] = e; e = NULL; }
+    ucc_spin_unlock(&ctx->ev_lock);
+    if (e) cudaEventDestroy(e);
+}
 static ucc_status_t task_alloc(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, ucc_tl_nvl_task_t **tp)
 {
     ucc_tl_nvl_team_t *team = ucc_derived_of(b_team, ucc_tl_nvl_team_t);
@@ -350,7 +367,8 @@ static ucc_status_t task_alloc(ucc_base_coll_args_t *b, ucc_base_team_t *b_team,
     t->need_xchg = 0; t->direct_cached = 0; t->cached_mode = 0; t->need_src = t->need_dst = 0; t->exp_src = NULL; t->exp_dst = NULL; t->exp_src_len = t->exp_dst_len = 0; t->nblocks_direct = 0;
     t->nthreads = (int)ctx->cfg.nthreads;
     t->super.post = nvl_post; t->super.progress = nvl_progress; t->super.finalize = nvl_finalize; t->super.triggered_post = nvl_triggered_post;
-    if (cudaEventCreateWithFlags(&t->event, cudaEventDisableTiming) != cudaSuccess) { (void)cudaGetLastError(); ucc_mpool_put(t); return UCC_ERR_NO_RESOURCE; }
+    t->event = event_get(ctx);
+    if (!t->event) { ucc_mpool_put(t); return UCC_ERR_NO_RESOURCE; }
     *tp = t;
     return UCC_OK;
 }
