@@ -44,6 +44,8 @@ def main():
         ok &= other_colls(comm, rank, world, dev, use_cuda, blk)
     if not use_cuda:   # (validated on host memory; on GPUs the WORLD team below is what the 2/4/8-GPU sessions exercised)
         ok &= team_kinds(rank, world, dev, use_cuda)
+    if use_cuda and os.environ.get("DW_ASYM") == "1":
+        ok &= asymmetric_root(comm, rank, world, dev)
     comm.barrier()
     flag = torch.tensor([1 if ok else 0])
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
@@ -52,6 +54,44 @@ def main():
         print("DIST_WORKER_OK" if flag.item() == 1 else "DIST_WORKER_FAIL", flush=True)
     dist.destroy_process_group()
     sys.exit(0 if flag.item() == 1 else 1)
+
+
+def asymmetric_root(comm, rank, world, dev):
+    """reference test/gtest/asym_mem: at the ROOT src and dst live in different memory types (the core stages through a
+    temporary of the other type around the TL collective).  reduce: CUDA contributions, the root wants the result on the HOST;
+    scatter: the root's source is on the HOST, every destination is CUDA."""
+    from ucc_b200.harness import coll_args
+    ok, count, root = True, 5000, world - 1
+    src = torch.arange(count, dtype=torch.float32, device=dev) + rank
+    host_dst = torch.zeros(count, dtype=torch.float32)
+    if rank == root:
+        a = coll_args("reduce", dt="float32", root=root, src_ptr=src.data_ptr(), dst_ptr=host_dst.data_ptr(), count_src=count, count_dst=count,
+                      src_mem_type=U.UCC_MEMORY_TYPE_CUDA, dst_mem_type=U.UCC_MEMORY_TYPE_HOST)
+    else:
+        a = coll_args("reduce", dt="float32", root=root, src_ptr=src.data_ptr(), count_src=count, count_dst=0, mem_type=U.UCC_MEMORY_TYPE_CUDA)
+    r = comm.init(a, (src, host_dst))
+    r.post(); r.wait(); r.finalize()
+    torch.cuda.synchronize()
+    if rank == root:
+        exp = torch.arange(count, dtype=torch.float32) * world + sum(range(world))
+        if not torch.allclose(host_dst, exp):
+            print(f"rank {rank}: asymmetric reduce mismatch", flush=True)
+            ok = False
+    blk = 700
+    host_src = torch.arange(blk * world, dtype=torch.float32) * 3
+    dst = torch.zeros(blk, dtype=torch.float32, device=dev)
+    if rank == 0:
+        a = coll_args("scatter", dt="float32", root=0, src_ptr=host_src.data_ptr(), dst_ptr=dst.data_ptr(), count_src=blk * world, count_dst=blk,
+                      src_mem_type=U.UCC_MEMORY_TYPE_HOST, dst_mem_type=U.UCC_MEMORY_TYPE_CUDA)
+    else:
+        a = coll_args("scatter", dt="float32", root=0, dst_ptr=dst.data_ptr(), count_dst=blk, count_src=0, mem_type=U.UCC_MEMORY_TYPE_CUDA)
+    r = comm.init(a, (host_src, dst))
+    r.post(); r.wait(); r.finalize()
+    torch.cuda.synchronize()
+    if not torch.equal(dst.cpu(), host_src[rank * blk:(rank + 1) * blk]):
+        print(f"rank {rank}: asymmetric scatter mismatch", flush=True)
+        ok = False
+    return ok
 
 
 def team_kinds(rank, world, dev, use_cuda):

@@ -91,6 +91,15 @@ def test_multiproc_hier_fake_nodes(alg):
     _run(n, {"UCC_B200_FAKE_PPN": "1", "UCC_CLS": "hier,basic", "UCC_CL_HIER_TUNE": f"allreduce:0-inf:@{alg}"})
 
 
+def test_multiproc_asymmetric_memory_at_root():
+    """reference asym_mem tests with one process per GPU: root's src / dst in different memory types around tl/nvl collectives
+    (in the one-device emulation this couples the ranks through device-wide synchronisation, see tests/test_nvl_gpu.py)"""
+    n = min(2, torch.cuda.device_count()) if torch.cuda.is_available() else 0
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    _run(n, {"DW_ASYM": "1"})
+
+
 def test_torch_backend_cuda():
     """init_process_group("ucc_b200"): c10d collectives and torch DDP on CUDA tensors run on the tl/nvl kernels."""
     n = min(2, torch.cuda.device_count()) if torch.cuda.is_available() else 0   # validated on 2 GPUs
