@@ -84,6 +84,8 @@ V = {
     "default_nb64": ([("MAX_BLOCKS", "64")], None), "default_nb128": ([("MAX_BLOCKS", "128")], None),
     "twoshot_nb64": (FORCE("twoshot") + [("MAX_BLOCKS", "64")], None), "twoshot_nb128": (FORCE("twoshot") + [("MAX_BLOCKS", "128")], None),
     "nvls_nb64": (FORCE("nvls") + [("MAX_BLOCKS", "64")], None),
+    "nvls512": (FORCE("nvls") + [("SYMMETRIC_SIZE", "512M")], None), "nvls1g": (FORCE("nvls") + [("SYMMETRIC_SIZE", "1G")], None),
+    "nvls_pipe1g": (FORCE("nvls_pipe") + [("SYMMETRIC_SIZE", "1G")], None),
 }
 for name in which:
     if name in V:

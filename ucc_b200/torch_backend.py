@@ -166,7 +166,9 @@ class ProcessGroupUCCB200(dist.ProcessGroup):
         req = self._comm.coll_init("alltoallv", input.contiguous(), output, src_counts=sc, src_displs=sd, dst_counts=rc, dst_displs=rd)
         return self._run([req], [input], output)
 
-    # ---- point to point: a two-member active-set broadcast, exactly how ProcessGroupUCC maps send/recv onto UCC
+    # ---- point to point: a two-member active-set broadcast, exactly how ProcessGroupUCC maps send/recv onto UCC.
+    # CUDA tensors travel over tl/nvl's heap channels: messages between an ordered pair of ranks are matched in POST ORDER (the NCCL
+    # contract: the tag does not reorder them); host tensors go through tl/shm, which matches by tag.
     def _p2p(self, tensors, src, dst, tag):
         reqs = [self._comm.coll_init("bcast", t, None, root=src, active_set=(src, dst - src, 2), tag=int(tag) & 0x3fff) for t in tensors]
         return self._run(reqs, tensors, tensors)
