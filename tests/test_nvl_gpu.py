@@ -192,6 +192,39 @@ def test_reduce_scatter(job, n, inplace):
             assert_close(dst[r], exp[r * blk:(r + 1) * blk], "float32")
 
 
+@pytest.mark.parametrize("n", [2, 3, 8])
+def test_reduce_scatter_oneshot_mixed_with_allreduce(n):
+    """one-shot reduce_scatter(v) (push every block to its owner's latency slot, one flag exchange) interleaved with one-shot allreduces
+    of different grid sizes: both share the slot parity / team-wide sequence (kernels/nvl_oneshot_rs.cu)"""
+    need_cuda()
+    env = dict(ENV, UCC_TL_NVL_TUNE="reduce_scatter:cuda:0-inf:@oneshot#reduce_scatterv:cuda:0-inf:@oneshot", **NOZC)
+    with UccJob(n, env=env) as j:
+        team = j.create_team()
+        for it, blk in enumerate((5, 1237, 40001, 3, 20000)):
+            for dt, op in (("float32", "sum"), ("bfloat16", "max"), ("int32", "avg")):
+                src = [gen(dt, blk * n, 10 * it + r) for r in range(n)]
+                dst = [torch.zeros(blk, dtype=TDT[dt], device="cuda") for _ in range(n)]
+                run(team, [cargs("reduce_scatter", src[r], dst[r], dt, op=op) for r in range(n)])
+                exp = ref_reduce(op, src)
+                for r in range(n):
+                    assert_close(dst[r], exp[r * blk:(r + 1) * blk], dt)
+            # an allreduce with another grid size in between (the bug the team-wide sequence fixed: per-block parities diverged)
+            cnt = 4096 * (it + 1) + 7
+            a = [gen("float32", cnt, 77 + r) for r in range(n)]
+            b = [torch.zeros(cnt, device="cuda") for _ in range(n)]
+            run(team, [cargs("allreduce", a[r], b[r], "float32") for r in range(n)])
+            for r in range(n):
+                assert_close(b[r], ref_reduce("sum", a), "float32")
+        counts = [100 + 33 * r for r in range(n)]
+        offs = np.concatenate([[0], np.cumsum(counts)[:-1]])
+        src = [gen("float32", sum(counts), r) for r in range(n)]
+        dst = [torch.zeros(counts[r], device="cuda") for r in range(n)]
+        run(team, [cargs("reduce_scatterv", src[r], dst[r], "float32", dst_counts=counts, dst_displs=offs) for r in range(n)])
+        exp = ref_reduce("sum", src)
+        for r in range(n):
+            assert_close(dst[r], exp[offs[r]:offs[r] + counts[r]], "float32")
+
+
 @pytest.mark.parametrize("n", [2, 4])
 def test_reduce_scatterv(job, n):
     team = job[n]
