@@ -69,6 +69,44 @@ static ucc_config_field_t ucc_ec_cuda_config_table[] = {
     {NULL}};
 
 static void event_obj_init(ucc_mpool_t *mp, void *obj, void *chunk) { (void)mp; (void)chunk; if (cudaEventCreateWithFlags((cudaEvent_t *)obj, cudaEventDisableTiming) != cudaSuccess) { (void)cudaGetLastError(); *(cudaEvent_t *)obj = NULL; } }
+/* Pinned, device-mapped control blocks of the persistent executors (task ring / wait word) are RECYCLED: cudaHostAlloc and above all
+ * cudaFreeHost synchronise the whole device, so an executor started or stopped by one collective stalled on every kernel running
+ * on the GPU - e.g. on the spinning kernels of collectives that wait for this very rank (a hierarchical allreduce whose leaders
+ * reduce through the host TL while the other ranks already sit in the node broadcast). */
+typedef struct ec_pin_blk { struct ec_pin_blk *next; } ec_pin_blk_t;
+static ec_pin_blk_t  *ec_pin_free;
+static size_t         ec_pin_size;
+static ucc_spinlock_t ec_pin_lock;
+static int            ec_pin_lock_init;
+static void *ec_pin_get(size_t sz)
+{
+    ec_pin_blk_t *b = NULL;
+    void *p = NULL;
+    if (!ec_pin_lock_init) { ucc_spinlock_init(&ec_pin_lock); ec_pin_lock_init = 1; }
+    ucc_spin_lock(&ec_pin_lock);
+    if (ec_pin_free && ec_pin_size >= sz) { b = ec_pin_free; ec_pin_free = b->next; }
+    ucc_spin_unlock(&ec_pin_lock);
+    if (b) return b;
+    if (sz < ec_pin_size) sz = ec_pin_size;
+    if (cudaHostAlloc(&p, sz, cudaHostAllocMapped) != cudaSuccess) { (void)cudaGetLastError(); return NULL; }
+    ucc_spin_lock(&ec_pin_lock);
+    if (sz > ec_pin_size) ec_pin_size = sz; /* blocks already on the list keep their (smaller) size: only handed out while sizes agree */
+    ucc_spin_unlock(&ec_pin_lock);
+    return p;
+}
+static void ec_pin_put(void *p)
+{
+    ec_pin_blk_t *b = (ec_pin_blk_t *)p;
+    ucc_spin_lock(&ec_pin_lock);
+    b->next = ec_pin_free; ec_pin_free = b;
+    ucc_spin_unlock(&ec_pin_lock);
+}
+static void ec_pin_drain(void)
+{
+    while (ec_pin_free) { ec_pin_blk_t *b = ec_pin_free; ec_pin_free = b->next; cudaFreeHost(b); }
+    ec_pin_size = 0;
+}
+
 static void event_obj_cleanup(ucc_mpool_t *mp, void *obj) { (void)mp; if (*(cudaEvent_t *)obj) cudaEventDestroy(*(cudaEvent_t *)obj); }
 
 static ucc_status_t ec_cuda_init(const ucc_ec_params_t *p)
@@ -89,6 +127,7 @@ static ucc_status_t ec_cuda_finalize(void)
     for (unsigned i = 0; i < ucc_ec_cuda.n_streams; i++) cudaStreamDestroy(ucc_ec_cuda.streams[i]);
     free(ucc_ec_cuda.streams); ucc_ec_cuda.streams = NULL; ucc_ec_cuda.n_streams = 0;
     ucc_mpool_cleanup(&ucc_ec_cuda.events, 0); ucc_mpool_cleanup(&ucc_ec_cuda.executors, 1); ucc_mpool_cleanup(&ucc_ec_cuda.tasks, 1);
+    ec_pin_drain();
     (void)cudaGetLastError();
     return UCC_OK;
 }
@@ -221,7 +260,8 @@ static ucc_status_t exec_start(ucc_ee_executor_t *xe, void *ee_context)
     if (x->task_types == 0) { /* nothing to execute: just keep the stream busy until stop() */
         void *dp = NULL;
         x->mode = EXEC_MODE_PERSISTENT_WAIT;
-        CUDA_CHECK(cudaHostAlloc((void **)&x->wait_state, sizeof(uint32_t), cudaHostAllocMapped));
+        x->wait_state = (volatile uint32_t *)ec_pin_get(sizeof(ec_ring_t) + (size_t)(EC_CFG->exec_max_tasks ? EC_CFG->exec_max_tasks : 128) * sizeof(ec_ring_slot_t));
+        if (!x->wait_state) return UCC_ERR_NO_MEMORY;
         *x->wait_state = 0;
         CUDA_CHECK(cudaHostGetDevicePointer(&dp, (void *)x->wait_state, 0)); x->wait_state_dev = (volatile uint32_t *)dp;
         if (ec_launch_wait(x->wait_state_dev, (cudaStream_t)ee_context) != cudaSuccess) { (void)cudaGetLastError(); return UCC_ERR_NO_MESSAGE; }
@@ -232,11 +272,12 @@ static ucc_status_t exec_start(ucc_ee_executor_t *xe, void *ee_context)
         unsigned n = EC_CFG->exec_max_tasks ? EC_CFG->exec_max_tasks : 128; size_t sz = sizeof(ec_ring_t) + (size_t)n * sizeof(ec_ring_slot_t);
         void *dp = NULL;
         x->mode = EXEC_MODE_PERSISTENT;
-        CUDA_CHECK(cudaHostAlloc((void **)&x->ring, sz, cudaHostAllocMapped));
+        x->ring = (ec_ring_t *)ec_pin_get(sz);
+        if (!x->ring) return UCC_ERR_NO_MEMORY;
         memset(x->ring, 0, sz); x->ring->n_slots = n; x->pidx = 0;
         CUDA_CHECK(cudaHostGetDevicePointer(&dp, x->ring, 0)); x->ring_dev = (ec_ring_t *)dp;
         if (ec_launch_persistent(x->ring_dev, (int)EC_CFG->exec_num_workers, (int)ucc_min(EC_CFG->exec_num_threads, 1024u), EC_CFG->use_cooperative_launch, (cudaStream_t)ee_context) != cudaSuccess) {
-            (void)cudaGetLastError(); cudaFreeHost(x->ring); x->ring = NULL; return UCC_ERR_NO_MESSAGE; }
+            (void)cudaGetLastError(); ec_pin_put(x->ring); x->ring = NULL; return UCC_ERR_NO_MESSAGE; }
         x->state = EXEC_POSTED;
     }
     return UCC_OK;
@@ -247,11 +288,11 @@ static ucc_status_t exec_stop(ucc_ee_executor_t *xe)
     if (x->mode == EXEC_MODE_PERSISTENT && x->ring) {
         x->ring->shutdown = 1; ucc_memory_cpu_store_fence();
         cudaStreamSynchronize((cudaStream_t)x->super.ee_context); /* the worker kernel observes the flag and retires */
-        cudaFreeHost(x->ring); x->ring = NULL;
+        ec_pin_put(x->ring); x->ring = NULL;
     } else if (x->mode == EXEC_MODE_PERSISTENT_WAIT && x->wait_state) {
         *x->wait_state = 1; ucc_memory_cpu_store_fence();
         cudaStreamSynchronize((cudaStream_t)x->super.ee_context);
-        cudaFreeHost((void *)x->wait_state); x->wait_state = NULL;
+        ec_pin_put((void *)x->wait_state); x->wait_state = NULL;
     }
     x->state = EXEC_INITIALIZED; x->super.ee_context = NULL; x->mode = EXEC_MODE_INTERRUPTIBLE;
     return UCC_OK;

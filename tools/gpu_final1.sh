@@ -4,6 +4,7 @@ export PYTHONPATH=$PWD
 O=gpurun_out/final1
 mkdir -p $O
 timeout 300 python -m pytest tests -m gpu -q --durations=8 -p no:cacheprovider > $O/pytest.log 2>&1; echo rc=$? >> $O/pytest.log
+UCC_B200_RUN_RAB_EMU=1 timeout 60 python -m pytest tests/test_nvl_gpu.py -m gpu -q -k "cl_hier and rab" -p no:cacheprovider > $O/pytest_rab_emu.log 2>&1; echo rc=$? >> $O/pytest_rab_emu.log; tail -3 $O/pytest_rab_emu.log | cut -c1-200
 timeout 60 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; echo rc=$? >> $O/smoke.log
 timeout 100 python bench.py --impl reference --steps 10 --warmup 3 --out $O/bench_ref.json > $O/bench_ref.log 2>&1
 timeout 120 python bench.py --steps 10 --warmup 3 --out $O/bench_ours.json > $O/bench_ours.log 2>&1
