@@ -55,7 +55,7 @@ static void note_launch(const ucc_tl_nvl_task_t *t)
     case NVL_TASK_P2P: k = t->u.p2p.send ? "p2p_send" : "p2p_recv"; nb = nvl_p2p_lanes(t->u.p2p.bytes); break;
     default: nb = 1; break;
     }
-    snprintf(nvl_last_launch, sizeof(nvl_last_launch), "%s %dx%d", k, nb, t->nthreads);
+    snprintf(nvl_last_launch, sizeof(nvl_last_launch), "%s %dx%d", k, nb, (t->use_bulk && !t->use_ce && (t->kind == NVL_TASK_SELF_COPY || (t->use_push && t->u.xchg.direct))) ? 32 : t->nthreads);
 }
 
 static ucc_status_t nvl_launch(ucc_tl_nvl_task_t *t, cudaStream_t s)
