@@ -469,6 +469,63 @@ def hier_on_device_buffers():
         print(f"  cl/hier {alg} on device buffers ok", flush=True)
 
 
+def lanes():
+    """UCC_TL_NVL_SLOTS=4: consecutive collectives of one team take consecutive lanes (own control block, one-shot slots, staging space) and,
+    posted stream-ordered on different streams, run CONCURRENTLY (emulated streams are worker threads) - two-shot, one-shot and zero-copy
+    kernels, three rounds so that every lane is reused"""
+    import time
+    rt.cudaStreamCreate.argtypes = [C.POINTER(C.c_void_p)]
+    n, K = 3, 4
+    for alg, extra, count in (("twoshot", NOZC, 30000), ("oneshot", NOZC, 2000), ("twoshot", ZC, 30000)):
+        env = dict(BASE, UCC_TL_NVL_SLOTS="4", UCC_TL_NVL_TUNE=f"allreduce:cuda:inf:@{alg}", UCC_TL_NVL_ALLREDUCE_ONESHOT_THRESH="0" if alg != "oneshot" else "1M", **extra)
+        with UccJob(n, env=env) as j:
+            team = j.create_team(range(n))
+            ees = [[None] * K for _ in range(n)]
+            for r in range(n):
+                for k in range(K):
+                    s = C.c_void_p()
+                    assert rt.cudaStreamCreate(C.byref(s)) == 0
+                    ep = U.ucc_ee_params_t()
+                    ep.ee_type, ep.ee_context, ep.ee_context_size = U.UCC_EE_CUDA_STREAM, s.value, C.sizeof(C.c_void_p)
+                    ee = U.handle()
+                    U.check(U.ucc_ee_create(team.members[r].team, C.byref(ep), C.byref(ee)), "ee_create")
+                    ees[r][k] = ee
+            for rnd_ in range(3):
+                src = [[Dev(count, fill=rnd(count, 100 * rnd_ + 10 * r + k)) for k in range(K)] for r in range(n)]
+                dst = [[Dev(count, fill=0) for _ in range(K)] for _ in range(n)]
+                reqs = []
+                for k in range(K):
+                    for r in range(n):
+                        a = ca("allreduce", src[r][k], dst[r][k])
+                        q = C.POINTER(U.ucc_coll_req_t)()
+                        U.check(U.ucc_collective_init(C.byref(a), C.byref(q), team.members[r].team), "init")
+                        ev = U.ucc_ev_t()
+                        ev.ev_type, ev.req = U.UCC_EVENT_COMPUTE_COMPLETE, C.cast(q, C.c_void_p)
+                        U.check(U.ucc_collective_triggered_post(ees[r][k], C.byref(ev)), "triggered_post")
+                        reqs.append((a, q))
+                t0 = time.time()
+                while any(q.contents.status == U.UCC_INPROGRESS for _, q in reqs):
+                    for r in range(n):
+                        U.ucc_context_progress(j.procs[r].ctx)
+                        for k in range(K):
+                            e = C.POINTER(U.ucc_ev_t)()
+                            while U.ucc_ee_get_event(ees[r][k], C.byref(e)) == U.UCC_OK:
+                                U.ucc_ee_ack_event(ees[r][k], e)
+                    assert time.time() - t0 < 120, "lanes: collectives did not complete"
+                rt.cudaDeviceSynchronize()
+                for _, q in reqs:
+                    assert q.contents.status == U.UCC_OK, q.contents.status
+                    U.ucc_collective_finalize(q)
+                for k in range(K):
+                    exp = sum(src[r][k].a for r in range(n))
+                    for r in range(n):
+                        assert np.allclose(dst[r][k].a, exp), ("lanes", alg, rnd_, k, r)
+            for r in range(n):
+                for k in range(K):
+                    U.ucc_ee_destroy(ees[r][k])
+        print(f"  lanes {alg} {'zcopy' if extra is ZC else 'staged'} ok", flush=True)
+
+
 def int_avg():
     """AVG on integer datatypes = truncated sum / N, on every reduction kernel"""
     n = 3
@@ -501,6 +558,7 @@ SCENARIOS = {
     "p2p": lambda: [p2p_active_set(), int_avg()],
     "memh": registered_buffers,
     "hier": hier_on_device_buffers,
+    "lanes": lanes,
 }
 
 if __name__ == "__main__":
