@@ -9,7 +9,7 @@ for san in thread address; do
   EMU_EXTRA="-fsanitize=$san -g" tests/emu/build_hostemu.sh > /dev/null 2>&1 || { echo "build failed ($san)"; exit 1; }
   rm -f /tmp/ucc_b200_he_$san.*
   lib=$(/usr/bin/gcc -print-file-name=$([ $san = thread ] && echo libtsan.so || echo libasan.so))
-  for s in allreduce colls_staged colls_zcopy colls_push misc triggered; do
+  for s in ${HOSTEMU_SCENARIOS:-allreduce colls_staged colls_zcopy colls_push colls_ce misc triggered p2p memh lanes}; do
     LD_PRELOAD=$lib TSAN_OPTIONS="log_path=/tmp/ucc_b200_he_$san:halt_on_error=0:report_signal_unsafe=0" \
       ASAN_OPTIONS="detect_leaks=0:detect_odr_violation=0:log_path=/tmp/ucc_b200_he_$san" timeout 1500 python tests/hostemu_worker.py $s > /tmp/ucc_b200_he_${san}_$s.log 2>&1
     ok=$(grep -c HOSTEMU_WORKER_OK /tmp/ucc_b200_he_${san}_$s.log)
