@@ -14,6 +14,7 @@ tail -12 $O/pytest_dist.log | cut -c1-300
 [ $(left) -gt 40 ] && timeout $(cap 60) $TR tools/p2p_bench.py > $O/p2p.log 2>&1
 [ $(left) -gt 40 ] && timeout $(cap 70) $TR tools/lanes_bench.py > $O/lanes.log 2>&1
 [ $(left) -gt 40 ] && timeout $(cap 80) $TR tools/nvlink_traffic.py > $O/nvlink.log 2>&1
+[ $(left) -gt 40 ] && COLL_VARIANTS=default,push,push_nobulk,push_bulk32,ce timeout $(cap 90) $TR tools/coll_bench.py > $O/colls.log 2>&1
 [ $(left) -gt 60 ] && timeout $(cap 150) bash tools/gpu_perftest.sh 2 > $O/perftest.log 2>&1
 [ $(left) -gt 50 ] && timeout $(cap 120) $TR tools/ucc_test_dist.py -M cuda -t world,reverse -I 2 -P 2 -i 2 -m 64:4194304:32 -r all -d int32,float32,bfloat16 -o sum,max,avg --triggered 2 > $O/test_dist_cuda.log 2>&1
 grep -A8 "TEST REPORT" $O/test_dist_cuda.log | cut -c1-200
@@ -26,4 +27,10 @@ for f in ("ref", "ours"):
     except Exception as e:
         print(f, "no json", e)
 PY
+grep '^{' $O/colls.log | python -c "
+import json,sys
+for l in sys.stdin:
+    for r in json.loads(l)['rows']:
+        print({k:v for k,v in r.items() if k!='kernels'})
+" | cut -c1-700
 grep '^{' $O/p2p.log; grep '^{' $O/lanes.log; grep '^{' $O/nvlink.log | cut -c1-700; grep -v WARN $O/perftest.log | tail -n 60 | cut -c1-200
