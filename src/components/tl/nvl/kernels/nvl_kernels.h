@@ -37,6 +37,9 @@ typedef struct nvl_ctrl {
     uint32_t p2p_ack[NVL_MAX_PEERS][NVL_P2P_MAX_CTAS];  /* in the SENDER's heap: chunks peer has drained from its ring (written by peer) */
     uint32_t p2p_tx[NVL_MAX_PEERS][NVL_P2P_MAX_CTAS];   /* local: chunks I produced for peer so far */
     uint32_t p2p_rx[NVL_MAX_PEERS][NVL_P2P_MAX_CTAS];   /* local: chunks I consumed from peer so far */
+    /* rendezvous (zero-copy) messages: the sender stores straight into the receiver's buffer */
+    uint32_t p2p_rz_done[NVL_MAX_PEERS];                /* in the RECEIVER's heap: zero-copy messages of peer that have completely landed (written by peer) */
+    uint32_t p2p_rz_blocks[NVL_MAX_PEERS];              /* local: CTAs of the running push kernel towards peer that are finished */
 } nvl_ctrl_t;
 
 #define NVL_CTRL_SIZE  (128 * 1024)
@@ -141,12 +144,21 @@ typedef struct nvl_p2p_args {
     size_t         bytes;
     int            peer;   /* team rank of the other side */
     int            send;   /* 1: I am the root (sender), 0: receiver */
+    int            mode;   /* nvl_p2p_mode_t */
+    uint32_t       rz_seq; /* NVL_P2P_PUSH / NVL_P2P_WAIT: index of this zero-copy message between the pair (in post order) */
+    char          *remote; /* NVL_P2P_PUSH: the receiver's buffer, mapped here */
 } nvl_p2p_args_t;
+/* NVL_P2P_RING: through the pair's heap channel (eager: the sender never needs the receiver's address);
+ * NVL_P2P_PUSH / NVL_P2P_WAIT: rendezvous - the receiver published its buffer, the sender's kernel stores into it directly and
+ * bumps p2p_rz_done in the receiver's heap; the receiver's stream only carries a one-warp kernel that waits for that counter */
+typedef enum { NVL_P2P_RING = 0, NVL_P2P_PUSH, NVL_P2P_WAIT } nvl_p2p_mode_t;
+#define NVL_P2P_PUSH_MAX_CTAS 64
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 int          nvl_p2p_lanes(size_t bytes);
+int          nvl_p2p_push_ctas(size_t bytes);
 cudaError_t  nvl_launch_p2p(const nvl_p2p_args_t *a, int nthreads, cudaStream_t s);
 size_t       nvl_dt_size(int dt);
 int          nvl_dt_supports_op(int dt, int op);

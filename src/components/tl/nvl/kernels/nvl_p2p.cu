@@ -80,13 +80,50 @@ __global__ void __launch_bounds__(NVL_THREADS_MAX) nvl_p2p_kernel(const __grid_c
             const char *slot = ring + (size_t)(seq % NVL_P2P_SLOTS) * chunk + (size_t)b * lane;
             if (n) p2p_copy<true>(ubuf + off, slot, n, (((uintptr_t)(ubuf + off)) & 15) == 0);
             __syncthreads();   /* every thread's loads of the slot have returned (their values were stored) */
-            if (threadIdx.x == 0) { fence_sys(); st_relaxed_sys_u32(&theirs->p2p_ack[me][b], seq + 1); }
+            if (threadIdx.x == 0) st_relaxed_sys_u32(&theirs->p2p_ack[me][b], seq + 1);   /* (no fence: nothing the sender reads was written here) */
         }
         if (threadIdx.x == 0) mine->p2p_rx[peer][b] = rx0 + nchunks;
     }
 }
 
+/* Rendezvous sender: the receiver's buffer is mapped here (a.remote) and the receiver's stream has reached its recv (the host
+ * published the buffer only then), so this kernel never waits: every CTA stores its contiguous part over NVLink, the last CTA
+ * to finish makes the message visible - fence, then the message counter in the receiver's heap. */
+__global__ void __launch_bounds__(NVL_THREADS_MAX) nvl_p2p_push_kernel(const __grid_constant__ nvl_p2p_args_t a)
+{
+    const nvl_team_dev_t &t = a.team;
+    const int me = t.rank, peer = a.peer, b = blockIdx.x, nb = gridDim.x;
+    nvl_ctrl_t *mine = reinterpret_cast<nvl_ctrl_t *>(t.heap[me]);
+    nvl_ctrl_t *theirs = reinterpret_cast<nvl_ctrl_t *>(t.heap[peer]);
+    const char *src = static_cast<const char *>(a.buf);
+    const bool aligned = ((((uintptr_t)src) | ((uintptr_t)a.remote)) & 15) == 0;
+    const size_t seg = ((a.bytes + nb - 1) / nb + 15) / 16 * 16;
+    const size_t off = (size_t)b * seg;
+    if (off < a.bytes) p2p_copy<false>(a.remote + off, src + off, dmin(seg, a.bytes - off), aligned);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        fence_sys();
+        if (atomicAdd(&mine->p2p_rz_blocks[peer], 1u) == (uint32_t)nb - 1) {
+            mine->p2p_rz_blocks[peer] = 0;
+            fence_sys();
+            st_relaxed_sys_u32(&theirs->p2p_rz_done[me], a.rz_seq + 1);
+        }
+    }
+}
+
+/* Rendezvous receiver: the data is written into a.buf by the peer's kernel; later work in this stream starts after it landed */
+__global__ void __launch_bounds__(32) nvl_p2p_wait_kernel(const __grid_constant__ nvl_p2p_args_t a)
+{
+    nvl_ctrl_t *mine = reinterpret_cast<nvl_ctrl_t *>(a.team.heap[a.team.rank]);
+    if (threadIdx.x == 0) p2p_spin(a.team, mine, &mine->p2p_rz_done[a.peer], a.rz_seq + 1);
+}
+
 #ifndef NVL_HOST_EMU
+extern "C" int nvl_p2p_push_ctas(size_t bytes)
+{
+    size_t n = bytes / (64 * 1024);
+    return n < 1 ? 1 : (n > NVL_P2P_PUSH_MAX_CTAS ? NVL_P2P_PUSH_MAX_CTAS : (int)n);
+}
 extern "C" int nvl_p2p_lanes(size_t bytes)
 {
     size_t n = bytes / (64 * 1024);
@@ -96,7 +133,9 @@ extern "C" cudaError_t nvl_launch_p2p(const nvl_p2p_args_t *a, int nthreads, cud
 {
     if (nthreads > NVL_THREADS_MAX) nthreads = NVL_THREADS_MAX;
     if (a->peer < 0 || a->peer >= a->team.size || a->peer == a->team.rank) return cudaErrorInvalidValue;
-    nvl_p2p_kernel<<<nvl_p2p_lanes(a->bytes), nthreads, 0, s>>>(*a);
+    if (a->mode == NVL_P2P_PUSH) nvl_p2p_push_kernel<<<nvl_p2p_push_ctas(a->bytes), nthreads, 0, s>>>(*a);
+    else if (a->mode == NVL_P2P_WAIT) nvl_p2p_wait_kernel<<<1, 32, 0, s>>>(*a);
+    else nvl_p2p_kernel<<<nvl_p2p_lanes(a->bytes), nthreads, 0, s>>>(*a);
     return cudaGetLastError();
 }
 #endif

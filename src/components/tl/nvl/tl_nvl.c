@@ -8,7 +8,8 @@ static ucc_config_field_t tl_nvl_lib_config_table[] = {
 
 ucc_config_field_t ucc_tl_nvl_context_config_table[] = {
     {"", "", NULL, ucc_offsetof(ucc_tl_nvl_context_config_t, super), UCC_CONFIG_TYPE_TABLE(ucc_tl_context_config_table)},
-    {"SYMMETRIC_SIZE", "128Mb", "Size of the data region of the per-team symmetric heap; larger messages are processed in rounds inside one kernel",
+    {"SYMMETRIC_SIZE", "384Mb", "Size of the data region of the per-team symmetric heap; larger messages are processed in rounds inside one kernel "
+     "(384 MB = three 128 MB round buffers of the pipelined NVLS allreduce, the fastest geometry measured on 8 x B200)",
      ucc_offsetof(ucc_tl_nvl_context_config_t, symmetric_size), UCC_CONFIG_TYPE_MEMUNITS},
     {"NBLOCKS", "auto", "Thread blocks per collective kernel (auto: chosen from the message size)", ucc_offsetof(ucc_tl_nvl_context_config_t, nblocks), UCC_CONFIG_TYPE_UINT},
     {"MAX_BLOCKS", "256", "Upper bound of thread blocks per collective kernel (all blocks of all ranks sharing a GPU must be co-resident)",
@@ -35,6 +36,9 @@ ucc_config_field_t ucc_tl_nvl_context_config_table[] = {
     {"BULK_THRESH", "1M", "Total bytes from which the bulk-copy kernel is used", ucc_offsetof(ucc_tl_nvl_context_config_t, bulk_thresh), UCC_CONFIG_TYPE_MEMUNITS},
     {"BULK_CTAS", "16", "Thread blocks (one warp each, 192 KB of shared memory) of a bulk-copy kernel: the SM budget of the collective",
      ucc_offsetof(ucc_tl_nvl_context_config_t, bulk_ctas), UCC_CONFIG_TYPE_UINT},
+    {"P2P_RNDV_THRESH", "256K", "Send / recv (two-member active-set bcast) of at least this size uses the rendezvous protocol: the receiver publishes its "
+     "buffer, the sender's kernel stores straight into it over NVLink (no ring, no copy on the receiving GPU); smaller messages go through the "
+     "pair's eager ring in the heap", ucc_offsetof(ucc_tl_nvl_context_config_t, p2p_rndv_thresh), UCC_CONFIG_TYPE_MEMUNITS},
     {"SLOTS", "1", "Independent collective lanes per team (reference tl/cuda MAX_CONCURRENT): consecutive collectives use consecutive lanes and, when "
      "posted on different streams, overlap.  Every lane has its own control block, one-shot slots and SYMMETRIC_SIZE of staging space; one "
      "kernel may use at most (2 x SMs) / SLOTS thread blocks so that all lanes stay co-resident", ucc_offsetof(ucc_tl_nvl_context_config_t, slots), UCC_CONFIG_TYPE_UINT},

@@ -49,6 +49,7 @@ typedef struct ucc_tl_nvl_context_config {
     int      bulk;             /* ternary: TMA bulk copies (cp.async.bulk) as the data mover of the zero-copy push exchange */
     size_t   bulk_thresh;
     unsigned bulk_ctas;        /* one-warp CTAs of a bulk-copy kernel */
+    size_t   p2p_rndv_thresh;  /* send / recv of at least this size: rendezvous (sender stores into the receiver's buffer) */
     unsigned slots;            /* independent collective lanes per team (reference tl/cuda MAX_CONCURRENT): collectives on different lanes may overlap */
 } ucc_tl_nvl_context_config_t;
 
@@ -61,7 +62,12 @@ typedef struct ucc_tl_nvl_context_config {
 typedef enum { NVL_XB_NONE = 0, NVL_XB_EMPTY, NVL_XB_RAW, NVL_XB_IPC } nvl_xb_kind_t;
 typedef struct nvl_xb_buf { int32_t kind; int32_t pad; uint64_t base, off, len, alloc_len; cudaIpcMemHandle_t handle; } nvl_xb_buf_t;
 typedef struct nvl_xb_entry { uint64_t seq; nvl_xb_buf_t src, dst; uint64_t aux[NVL_MAX_PEERS]; /* alltoallv: byte offset of source p's block inside my dst */ } nvl_xb_entry_t;
-typedef struct nvl_xb_seg { uint64_t consumed; uint64_t pad[7]; nvl_xb_entry_t e[NVL_XB_SLOTS]; } nvl_xb_seg_t;
+/* rendezvous send / recv: rz[p][k % NVL_XB_RZ_SLOTS] is written by the board's owner (the RECEIVER) for its k-th large receive from
+ * member p (seq = k + 1); rz_consumed[p] is written by the owner as SENDER: how many receive posts of member p it has used */
+#define NVL_XB_RZ_SLOTS 4
+typedef struct nvl_xb_rz { uint64_t seq; nvl_xb_buf_t buf; } nvl_xb_rz_t;
+typedef struct nvl_xb_seg { uint64_t consumed; uint64_t pad[7]; nvl_xb_entry_t e[NVL_XB_SLOTS];
+                            uint64_t rz_consumed[NVL_MAX_PEERS]; nvl_xb_rz_t rz[NVL_MAX_PEERS][NVL_XB_RZ_SLOTS]; } nvl_xb_seg_t;
 typedef struct nvl_ipc_cache { unsigned n; struct { uint64_t base; cudaIpcMemHandle_t handle; void *mapped; } e[NVL_IPC_CACHE_MAX]; } nvl_ipc_cache_t;
 
 typedef struct ucc_tl_nvl_lib { ucc_tl_lib_t super; } ucc_tl_nvl_lib_t;
@@ -154,6 +160,15 @@ typedef struct ucc_tl_nvl_team {
     cudaStream_t      last_stream[NVL_MAX_LANES];  /* stream of the lane's most recent launch */
     cudaEvent_t       order_event[NVL_MAX_LANES];  /* spare event: swapped with a finalized task's event that last_event points to */
     cudaEvent_t       last_event[NVL_MAX_LANES];   /* completion event of the lane's most recent launch */
+    /* send / recv (two-member active sets).  Sends to one peer are launched in post order (p2p_post_seq / p2p_launch_seq); sends
+     * that had to wait for the receiver (rendezvous) run on a per-peer side stream, the user's stream then waits for their event */
+    uint32_t          p2p_post_seq[NVL_MAX_PEERS], p2p_launch_seq[NVL_MAX_PEERS];
+    uint64_t          rz_tx[NVL_MAX_PEERS];     /* large sends posted to peer (index into the receiver's board entries) */
+    uint64_t          rz_rx[NVL_MAX_PEERS];     /* large receives posted from peer */
+    uint64_t          rz_pub[NVL_MAX_PEERS];    /* large receives from peer already published */
+    uint32_t          rz_zc_tx[NVL_MAX_PEERS], rz_zc_rx[NVL_MAX_PEERS]; /* ... of those, the ones that really go zero-copy (device counter p2p_rz_done) */
+    cudaStream_t      p2p_stream[NVL_MAX_PEERS];
+    cudaEvent_t       p2p_side_event[NVL_MAX_PEERS]; int p2p_side_used[NVL_MAX_PEERS];
     uint32_t         *gates;                /* device words user streams wait on while their collective is deferred */
     uint32_t          gate_seq;
 } ucc_tl_nvl_team_t;
@@ -164,7 +179,7 @@ typedef enum { NVL_TASK_REDUCE_ONESHOT, NVL_TASK_REDUCE_STAGED, NVL_TASK_REDUCE_
                NVL_TASK_REDUCE_SYMM /* in-place NVLS allreduce on symmetric user memory (kernels/nvl_symm.cu) */,
                NVL_TASK_AG_SYMM /* allgather into a symmetric destination by multimem.st (u.xchg: src, src_bytes, dst, push_off) */,
                NVL_TASK_P2P /* two-member active-set bcast = send / recv over a heap channel (kernels/nvl_p2p.cu, u.p2p) */ } nvl_task_kind_t;
-typedef enum { NVL_TASK_LAUNCHED, NVL_TASK_QUEUED } nvl_task_state_t;
+typedef enum { NVL_TASK_LAUNCHED, NVL_TASK_QUEUED, NVL_TASK_P2P_WAIT /* send waiting for its turn / for the receiver's buffer */ } nvl_task_state_t;
 typedef struct ucc_tl_nvl_task {
     ucc_coll_task_t     super;
     ucc_tl_nvl_team_t  *team;
@@ -191,6 +206,13 @@ typedef struct ucc_tl_nvl_task {
     uint32_t            gate_val;
     cudaEvent_t         in_event;
     int                 nblocks_direct;
+    /* send / recv */
+    int                 p2p_rndv;      /* large message: rendezvous protocol */
+    uint32_t            p2p_order;     /* send: position among the sends to this peer */
+    uint64_t            rz_seq;        /* rendezvous: index among the large messages of the pair */
+    int                 p2p_ee_done;   /* the UCC_EVENT_COLLECTIVE_POST of this post was delivered */
+    int                 rz_pub_pending;/* recv: the buffer is not on the board yet (stream not there yet / slot busy / not my turn) */
+    nvl_xb_buf_t        rz_buf;        /* recv: what will be published */
     /* zero-copy push exchange (kernels/nvl_push.cu): used instead of the pull kernel when the destinations resolved */
     int                 use_bulk;      /* push exchange driven by the TMA engine (nvl_exchange_push_bulk_kernel) */
     int                 use_ce;        /* push exchange executed by the copy engines (cudaMemcpyAsync between two barrier kernels) */
@@ -215,6 +237,8 @@ ucc_status_t ucc_tl_nvl_xb_attach(ucc_tl_nvl_team_t *team);
 void         ucc_tl_nvl_xb_unlink(ucc_tl_nvl_team_t *team);
 void         ucc_tl_nvl_xb_release(ucc_tl_nvl_team_t *team);
 int          ucc_tl_nvl_xb_publish(ucc_tl_nvl_team_t *team, uint64_t cseq, const void *src, size_t src_len, void *dst, size_t dst_len, int usable, const size_t *aux);
+void         ucc_tl_nvl_xb_export(ucc_tl_nvl_team_t *team, const void *ptr, size_t len, nvl_xb_buf_t *b);
+char        *ucc_tl_nvl_xb_import(ucc_tl_nvl_team_t *team, ucc_rank_t p, const nvl_xb_buf_t *b);
 int          ucc_tl_nvl_xb_ready(ucc_tl_nvl_team_t *team, uint64_t cseq);
 int          ucc_tl_nvl_xb_resolve(ucc_tl_nvl_team_t *team, uint64_t cseq, int need_src, int need_dst, int need_align, const void *my_src, void *my_dst, nvl_direct_t *d, size_t *aux_for_me);
 

@@ -35,6 +35,7 @@ static inline int is_cuda(ucc_memory_type_t mt) { return mt == UCC_MEMORY_TYPE_C
 /* task life cycle                                                     */
 /* ------------------------------------------------------------------ */
 /* what the most recent launch of this process was (benchmarks print it next to their numbers): "<kernel> grid x block" */
+static cudaEvent_t event_get(ucc_tl_nvl_context_t *ctx);
 static char nvl_last_launch[128];
 UCC_EXPORT const char *ucc_tl_nvl_last_launch_info(void) { return nvl_last_launch; }
 static void note_launch(const ucc_tl_nvl_task_t *t)
@@ -52,7 +53,11 @@ static void note_launch(const ucc_tl_nvl_task_t *t)
     case NVL_TASK_AG_SYMM: k = "allgather_symm_mc"; break;
     case NVL_TASK_XCHG: k = (t->use_push && t->u.xchg.direct) ? (t->use_ce ? "exchange_push_copy_engine" : (t->use_bulk ? "exchange_push_bulk(tma)" : "exchange_push")) : (t->u.xchg.direct ? "exchange_pull_zcopy" : (t->u.xchg.use_mc ? "exchange_nvls" : (t->u.xchg.ring ? "exchange_ring" : "exchange_pull_staged"))); break;
     case NVL_TASK_SELF_COPY: k = t->use_bulk ? "self_copy_bulk(tma)" : "self_copy"; break;
-    case NVL_TASK_P2P: k = t->u.p2p.send ? "p2p_send" : "p2p_recv"; nb = nvl_p2p_lanes(t->u.p2p.bytes); break;
+    case NVL_TASK_P2P:
+        if (t->u.p2p.mode == NVL_P2P_PUSH) { k = "p2p_send_rndv(push)"; nb = nvl_p2p_push_ctas(t->u.p2p.bytes); }
+        else if (t->u.p2p.mode == NVL_P2P_WAIT) { k = "p2p_recv_rndv(wait)"; nb = 1; }
+        else { k = t->u.p2p.send ? "p2p_send" : "p2p_recv"; nb = nvl_p2p_lanes(t->u.p2p.bytes); }
+        break;
     default: nb = 1; break;
     }
     snprintf(nvl_last_launch, sizeof(nvl_last_launch), "%s %dx%d", k, nb, (t->use_bulk && !t->use_ce && (t->kind == NVL_TASK_SELF_COPY || (t->use_push && t->u.xchg.direct))) ? 32 : t->nthreads);
@@ -212,6 +217,122 @@ static void memh_direct(ucc_tl_nvl_task_t *t, const ucc_coll_args_t *a, const vo
     t->direct_cached = 1; t->cached_mode = 1; t->cached_d = d;
 }
 
+/* ------------------------------------------------------------------ */
+/* send / recv.  Small messages: eager, through the pair's ring in the receiver's heap, one kernel per side, launched at post.
+ * Large messages (P2P_RNDV_THRESH): rendezvous.  The receiver puts (IPC handle, offset) of its buffer on its board - but only
+ * once its stream has reached the recv (the sender may write from then on) - and parks a one-warp kernel on its stream that
+ * waits for the pair's message counter.  The sender maps the buffer (cached) and launches a kernel that stores into it
+ * directly and bumps that counter.  That kernel never waits for anything on the device, and it runs on a per-peer side stream
+ * behind an event of the user's stream, so an exchange posted as send + recv on ONE stream on both sides cannot deadlock
+ * (with NCCL that shape needs a group).  A receiver whose buffer cannot be exported says so on the board and both sides use
+ * the ring for that message.  Sends to one peer are launched strictly in post order. */
+static ucc_status_t p2p_side_stream(ucc_tl_nvl_team_t *team, int peer)
+{
+    if (team->p2p_stream[peer]) return UCC_OK;
+    CUDA_CHECK(cudaStreamCreateWithFlags(&team->p2p_stream[peer], cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreateWithFlags(&team->p2p_side_event[peer], cudaEventDisableTiming));
+    return UCC_OK;
+}
+static inline int xb_kind_mappable(int kind) { return kind == NVL_XB_RAW || kind == NVL_XB_IPC; }
+
+static void p2p_try_publish(ucc_tl_nvl_task_t *t)
+{
+    ucc_tl_nvl_team_t *team = t->team;
+    int peer = t->u.p2p.peer;
+    ucc_rank_t me = UCC_TL_TEAM_RANK(team);
+    nvl_xb_rz_t *e = &team->xb_mine->rz[peer][t->rz_seq % NVL_XB_RZ_SLOTS];
+    if (!t->rz_pub_pending || t->rz_seq != team->rz_pub[peer]) return;
+    if (t->rz_seq >= NVL_XB_RZ_SLOTS && ucc_load_acquire(&team->xb[peer]->rz_consumed[me]) + NVL_XB_RZ_SLOTS <= t->rz_seq) return;
+    if (xb_kind_mappable(t->rz_buf.kind)) { /* my stream must be at the recv: earlier work in it may still use the buffer */
+        cudaError_t ce = cudaEventQuery(t->in_event);
+        if (ce == cudaErrorNotReady) { (void)cudaGetLastError(); return; }
+    }
+    e->buf = t->rz_buf;
+    ucc_store_release(&e->seq, t->rz_seq + 1);
+    team->rz_pub[peer]++; t->rz_pub_pending = 0;
+}
+
+/* UCC_OK: launched; UCC_INPROGRESS: not its turn / the receiver has not published yet */
+static ucc_status_t p2p_try_send(ucc_tl_nvl_task_t *t, int at_post)
+{
+    ucc_tl_nvl_team_t *team = t->team;
+    int peer = t->u.p2p.peer, side = !at_post;
+    ucc_rank_t me = UCC_TL_TEAM_RANK(team);
+    ucc_status_t st;
+    if (t->p2p_order != team->p2p_launch_seq[peer]) return UCC_INPROGRESS;
+    t->u.p2p.mode = NVL_P2P_RING;
+    if (t->p2p_rndv && !t->captured) {
+        const nvl_xb_rz_t *e = &team->xb[peer]->rz[me][t->rz_seq % NVL_XB_RZ_SLOTS];
+        if (ucc_load_acquire(&e->seq) != t->rz_seq + 1) return UCC_INPROGRESS;
+        if (xb_kind_mappable(e->buf.kind)) {
+            char *remote = e->buf.len == t->u.p2p.bytes ? ucc_tl_nvl_xb_import(team, (ucc_rank_t)peer, &e->buf) : NULL;
+            if (!remote) {
+                tl_error(NVL_LIB(team), "send to %d: %s", peer, e->buf.len == t->u.p2p.bytes ? "cannot map the receiver's buffer" : "message size differs from the posted receive");
+                ucc_store_release(&team->xb_mine->rz_consumed[peer], t->rz_seq + 1);
+                team->p2p_launch_seq[peer]++;
+                return UCC_ERR_NO_RESOURCE;
+            }
+            t->u.p2p.mode = NVL_P2P_PUSH; t->u.p2p.remote = remote; t->u.p2p.rz_seq = team->rz_zc_tx[peer]++;
+            side = 1;   /* all zero-copy sends to a peer share one stream: their completion counter must advance in order */
+        }
+        ucc_store_release(&team->xb_mine->rz_consumed[peer], t->rz_seq + 1);
+    }
+    if (side) {
+        st = p2p_side_stream(team, peer);
+        if (st != UCC_OK) return st;
+        CUDA_CHECK(cudaStreamWaitEvent(team->p2p_stream[peer], t->in_event, 0));
+        st = nvl_launch(t, team->p2p_stream[peer]);
+        if (st != UCC_OK) return st;
+        CUDA_CHECK(cudaEventRecord(t->event, team->p2p_stream[peer]));
+        CUDA_CHECK(cudaEventRecord(team->p2p_side_event[peer], team->p2p_stream[peer]));
+        team->p2p_side_used[peer] = 1;
+        CUDA_CHECK(cudaStreamWaitEvent(t->stream, t->event, 0));   /* the send is "in" the user's stream from here on */
+    } else {
+        if (team->p2p_side_used[peer] && !t->captured) CUDA_CHECK(cudaStreamWaitEvent(t->stream, team->p2p_side_event[peer], 0));
+        st = nvl_launch(t, t->stream);
+        if (st != UCC_OK) return st;
+        if (!t->captured) CUDA_CHECK(cudaEventRecord(t->event, t->stream));
+    }
+    team->p2p_launch_seq[peer]++;
+    return UCC_OK;
+}
+
+static ucc_status_t p2p_post(ucc_tl_nvl_task_t *t, cudaStream_t s)
+{
+    ucc_tl_nvl_team_t *team = t->team;
+    int peer = t->u.p2p.peer, rndv = t->p2p_rndv && !t->captured;
+    ucc_status_t st;
+    t->u.p2p.mode = NVL_P2P_RING; t->rz_pub_pending = 0;
+    if (!t->captured && !t->in_event) { t->in_event = event_get(NVL_CTX(team)); if (!t->in_event) return UCC_ERR_NO_RESOURCE; }
+    if (t->u.p2p.send) {
+        t->p2p_order = team->p2p_post_seq[peer]++;
+        if (rndv) t->rz_seq = team->rz_tx[peer]++;
+        if (t->captured && t->p2p_order != team->p2p_launch_seq[peer]) {
+            tl_error(NVL_LIB(team), "send to %d posted into a capturing stream while earlier sends to it are still waiting for the receiver", peer);
+            team->p2p_post_seq[peer]--;
+            return UCC_ERR_NOT_SUPPORTED;
+        }
+        if (!t->captured) CUDA_CHECK(cudaEventRecord(t->in_event, s));
+        st = p2p_try_send(t, 1);
+        if (st == UCC_INPROGRESS) { t->state = NVL_TASK_P2P_WAIT; st = UCC_OK; }
+        return st;
+    }
+    if (rndv) {
+        t->rz_seq = team->rz_rx[peer]++;
+        ucc_tl_nvl_xb_export(team, t->u.p2p.buf, t->u.p2p.bytes, &t->rz_buf);
+        if (xb_kind_mappable(t->rz_buf.kind)) {
+            t->u.p2p.mode = NVL_P2P_WAIT; t->u.p2p.rz_seq = team->rz_zc_rx[peer]++;
+            CUDA_CHECK(cudaEventRecord(t->in_event, s));
+        }
+        t->rz_pub_pending = 1;
+        p2p_try_publish(t);
+    }
+    st = nvl_launch(t, s);
+    if (st != UCC_OK) return st;
+    if (!t->captured) CUDA_CHECK(cudaEventRecord(t->event, s));
+    return UCC_OK;
+}
+
 /* head of the launch queue: start it once its buffer exchange (if any) is complete */
 static ucc_status_t try_launch_queued(ucc_tl_nvl_task_t *t)
 {
@@ -241,6 +362,24 @@ static void nvl_progress(ucc_coll_task_t *ct)
 {
     ucc_tl_nvl_task_t *t = ucc_derived_of(ct, ucc_tl_nvl_task_t);
     cudaError_t e;
+    if (t->kind == NVL_TASK_P2P && (t->rz_pub_pending || t->state == NVL_TASK_P2P_WAIT)) {
+        ucc_status_t st = UCC_OK;
+        ucc_spin_lock(&t->team->launch_lock);
+        p2p_try_publish(t);
+        if (t->state == NVL_TASK_P2P_WAIT) {
+            st = p2p_try_send(t, 0);
+            if (st != UCC_INPROGRESS) t->state = NVL_TASK_LAUNCHED;
+        }
+        ucc_spin_unlock(&t->team->launch_lock);
+        if (st == UCC_INPROGRESS) return;
+        if (st != UCC_OK) { ct->status = st; return; }
+        if (t->state == NVL_TASK_LAUNCHED && t->u.p2p.send && t->super.ee && !t->p2p_ee_done) {
+            ucc_ev_t post_event;
+            t->p2p_ee_done = 1;
+            post_event.ev_type = UCC_EVENT_COLLECTIVE_POST; post_event.ev_context = NULL; post_event.ev_context_size = 0; post_event.req = &t->super.super;
+            ucc_ee_set_event_internal(t->super.ee, &post_event, &t->super.ee->event_out_queue);
+        }
+    }
     if (t->state == NVL_TASK_QUEUED) {
         ucc_status_t st;
         ucc_spin_lock(&t->team->launch_lock);
@@ -272,7 +411,14 @@ static ucc_status_t nvl_post_on(ucc_tl_nvl_task_t *t, cudaStream_t s)
     ucc_spin_lock(&team->launch_lock);
     /* lanes advance in post order, which UCC requires to be the same on every member; point-to-point and single-member tasks
      * involve no team-wide kernel and take no lane */
-    if (t->kind != NVL_TASK_P2P && t->kind != NVL_TASK_SELF_COPY) task_set_lane(t, team->lane_seq++ % team->nlanes);
+    if (t->kind == NVL_TASK_P2P) {
+        t->p2p_ee_done = 0;
+        st = p2p_post(t, s);
+        ucc_spin_unlock(&team->launch_lock);
+        if (st != UCC_OK) return st;
+        return ucc_progress_queue_enqueue(UCC_TL_CORE_CTX(t->team)->pq, &t->super);
+    }
+    if (t->kind != NVL_TASK_SELF_COPY) task_set_lane(t, team->lane_seq++ % team->nlanes);
     direct = task_is_direct(t) && !t->direct_cached;   /* cached tables: also fine inside a stream capture, nothing to wait for */
     t->need_xchg = direct;
     if (t->kind == NVL_TASK_XCHG || t->kind == NVL_TASK_AG_SYMM) t->u.xchg.direct = 0; else if (t->kind != NVL_TASK_P2P) t->u.red.direct = NVL_DIRECT_NONE;
@@ -315,7 +461,8 @@ static ucc_status_t nvl_triggered_post(ucc_ee_h ee, ucc_ev_t *ev, ucc_coll_task_
     ct->ee = ee;
     st = nvl_post_on(t, (cudaStream_t)ee->ee_context);
     if (st != UCC_OK) return st;
-    if (t->state == NVL_TASK_QUEUED) return UCC_OK; /* the post event follows the deferred launch */
+    if (t->state == NVL_TASK_QUEUED || t->state == NVL_TASK_P2P_WAIT) return UCC_OK; /* the post event follows the deferred launch */
+    t->p2p_ee_done = 1;
     post_event.ev_type = UCC_EVENT_COLLECTIVE_POST; post_event.ev_context = NULL; post_event.ev_context_size = 0; post_event.req = &ct->super;
     ucc_ee_set_event_internal(ee, &post_event, &ee->event_out_queue);
     return UCC_OK;
@@ -329,11 +476,15 @@ static ucc_status_t nvl_finalize(ucc_coll_task_t *ct)
     if (t->state == NVL_TASK_QUEUED) { /* abandoned before its kernel was launched (timeout / error): release the user's stream */
         ucc_list_del(&t->q_elem); t->state = NVL_TASK_LAUNCHED;
     }
+    if (t->state == NVL_TASK_P2P_WAIT) { /* a send given up before the receiver showed up: let the sends behind it proceed */
+        if (t->p2p_order == team->p2p_launch_seq[t->u.p2p.peer]) team->p2p_launch_seq[t->u.p2p.peer]++;
+        t->state = NVL_TASK_LAUNCHED;
+    }
     if (t->event && team->last_event[t->lane] == t->event) { /* the lane still orders its next launch after this event: keep it alive */
         cudaEvent_t spare = team->order_event[t->lane]; team->order_event[t->lane] = t->event; t->event = spare;
     }
     ucc_spin_unlock(&team->launch_lock);
-    if (t->in_event) cudaEventDestroy(t->in_event);
+    if (t->in_event) { event_put(NVL_CTX(team), t->in_event); t->in_event = NULL; }
     if (t->event) event_put(NVL_CTX(team), t->event);
     ucc_coll_task_destruct(ct);
     ucc_mpool_put(t);
@@ -609,6 +760,7 @@ static ucc_status_t xchg_init(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, 
         t->u.p2p.team = team->dev; t->u.p2p.buf = a->src.info.buffer; t->u.p2p.bytes = len;
         t->u.p2p.send = me == root; t->u.p2p.peer = (int)(me == r0 ? r1 : r0);
         t->nblocks = nvl_p2p_lanes(len);
+        t->p2p_rndv = team->zcopy && len && len >= ctx->cfg.p2p_rndv_thresh;
         *task_p = &t->super;
         return UCC_OK;
     }
@@ -929,7 +1081,12 @@ ucc_status_t ucc_tl_nvl_team_get_scores(ucc_base_team_t *b_team, ucc_coll_score_
     /* 4 x B200: zero-copy two-shot stays ahead at every size (634 GB/s at 256 MB vs 605 for NVLS at 1 GiB), and the
      * NVLS reduce_scatter loses to it because of the staging pass (390 vs NCCL 525 GB/s at 256 MB) - so NVLS is the
      * default only for very large allreduce on teams of more than four; `@nvls` remains selectable for everything */
-    if (team->nvls && UCC_TL_TEAM_SIZE(team) > 4) snprintf(sel, sizeof(sel), "allreduce:0-%s:@oneshot#allreduce:%s-inf:@nvls", a, n);
+    /* round 2, 8 x B200, 1 GiB f32 (profiles/r2_n8/matrix.jsonl): staged NVLS 706-716 GB/s, zero-copy two-shot 651, pipelined NVLS
+     * (stage / multimem / copy-out of consecutive rounds overlapped, kernels/nvl_pipe.cu) 690 with a 128 MB heap, 770 with 384 MB
+     * (three 128 MB round buffers) and 632 with 1 GB; NCCL 723.  Hence the 384 MB default heap and `nvls_pipe` above the threshold
+     * whenever the heap is big enough for its round buffers; at 256 MB all four are within 2 % (628-637) and two-shot stays */
+    if (team->nvls && UCC_TL_TEAM_SIZE(team) > 4)
+        snprintf(sel, sizeof(sel), "allreduce:0-%s:@oneshot#allreduce:%s-inf:@%s", a, n, ctx->cfg.symmetric_size >= ((size_t)192 << 20) ? "nvls_pipe" : "nvls");
     else snprintf(sel, sizeof(sel), "allreduce:0-%s:@oneshot", a);
     st = ucc_tl_apply_tune(&team->super, score, &info, sel, ctx->cfg.super.super.score_str);
     if (st != UCC_OK) { ucc_coll_score_free(score); return st; }

@@ -75,6 +75,8 @@ static void export_buf(ucc_tl_nvl_team_t *team, const void *ptr, size_t len, nvl
     }
 }
 
+void ucc_tl_nvl_xb_export(ucc_tl_nvl_team_t *team, const void *ptr, size_t len, nvl_xb_buf_t *b) { export_buf(team, ptr, len, b); }
+
 /* returns 0 when the slot is still in use by a slow peer (caller retries later) */
 int ucc_tl_nvl_xb_publish(ucc_tl_nvl_team_t *team, uint64_t cseq, const void *src, size_t src_len, void *dst, size_t dst_len, int usable, const size_t *aux)
 {
@@ -123,6 +125,8 @@ static char *import_buf(ucc_tl_nvl_team_t *team, ucc_rank_t p, const nvl_xb_buf_
     c->e[c->n].base = b->base; c->e[c->n].handle = b->handle; c->e[c->n].mapped = mapped; c->n++;
     return (char *)mapped + b->off;
 }
+
+char *ucc_tl_nvl_xb_import(ucc_tl_nvl_team_t *team, ucc_rank_t p, const nvl_xb_buf_t *b) { return import_buf(team, p, b); }
 
 /* all members published: decide (identically on every rank) whether the buffers can be used in place and map
  * them.  need_src / need_dst say which sides the kernel touches remotely.  Marks the entries consumed.

@@ -133,6 +133,10 @@ static void team_release(ucc_tl_nvl_team_t *team)
     int N = (int)UCC_TL_TEAM_SIZE(team), me = (int)UCC_TL_TEAM_RANK(team);
     fd_server_stop(team);
     if (team->stream) { cudaStreamSynchronize(team->stream); cudaStreamDestroy(team->stream); team->stream = NULL; }
+    for (int p = 0; p < NVL_MAX_PEERS; p++) {
+        if (team->p2p_stream[p]) { cudaStreamSynchronize(team->p2p_stream[p]); cudaStreamDestroy(team->p2p_stream[p]); team->p2p_stream[p] = NULL; }
+        if (team->p2p_side_event[p]) { cudaEventDestroy(team->p2p_side_event[p]); team->p2p_side_event[p] = NULL; }
+    }
     if (team->mc_va) { unmap_va(team->mc_va, team->mc_size); team->mc_va = NULL; }
     if (team->nvls || team->mc_handle) {
         if (team->mc_handle) { CUdevice d; if (ucc_cu.cuDeviceGet(&d, NVL_CTX(team)->dev) == CUDA_SUCCESS && ucc_cu.cuMulticastUnbind) ucc_cu.cuMulticastUnbind(team->mc_handle, d, 0, team->mc_size);

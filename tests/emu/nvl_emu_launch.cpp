@@ -89,7 +89,14 @@ cudaError_t nvl_launch_allgather_symm(const nvl_xchg_args_t *, int, int, cudaStr
 cudaError_t nvl_launch_exchange(const nvl_xchg_args_t *ap, int nb, int nt, cudaStream_t s) { nvl_xchg_args_t a = *ap; return enqueue_grid(s, nb, nt, [a]() { nvl_exchange_kernel(a); }); }
 cudaError_t nvl_launch_exchange_push(const nvl_push_args_t *ap, int nb, int nt, cudaStream_t s) { nvl_push_args_t a = *ap; return enqueue_grid(s, nb, nt, [a]() { nvl_exchange_push_kernel(a); }); }
 int nvl_p2p_lanes(size_t bytes) { size_t n = bytes / (64 * 1024); return n < 1 ? 1 : (n > NVL_P2P_MAX_CTAS ? NVL_P2P_MAX_CTAS : (int)n); }
-cudaError_t nvl_launch_p2p(const nvl_p2p_args_t *ap, int nt, cudaStream_t s) { nvl_p2p_args_t a = *ap; return enqueue_grid(s, nvl_p2p_lanes(a.bytes), nt > 64 ? 64 : nt, [a]() { nvl_p2p_kernel(a); }); }
+int nvl_p2p_push_ctas(size_t bytes) { size_t n = bytes / (64 * 1024); return n < 1 ? 1 : (n > 4 ? 4 : (int)n); }
+cudaError_t nvl_launch_p2p(const nvl_p2p_args_t *ap, int nt, cudaStream_t s)
+{
+    nvl_p2p_args_t a = *ap;
+    if (a.mode == NVL_P2P_PUSH) return enqueue_grid(s, nvl_p2p_push_ctas(a.bytes), nt > 64 ? 64 : nt, [a]() { nvl_p2p_push_kernel(a); });
+    if (a.mode == NVL_P2P_WAIT) return enqueue_grid(s, 1, 32, [a]() { nvl_p2p_wait_kernel(a); });
+    return enqueue_grid(s, nvl_p2p_lanes(a.bytes), nt > 64 ? 64 : nt, [a]() { nvl_p2p_kernel(a); });
+}
 cudaError_t nvl_launch_exchange_push_bulk(const nvl_push_args_t *ap, int nb, cudaStream_t s) { return nvl_launch_exchange_push(ap, nb, 32, s); }   /* no TMA here: the thread-copy kernel */
 cudaError_t nvl_launch_barrier(const nvl_team_dev_t *tp, cudaStream_t s) { nvl_team_dev_t t = *tp; return enqueue_grid(s, 1, 32, [t]() { nvl_barrier_kernel(t); }); }
 cudaError_t nvl_launch_self_copy(void *dst, const void *src, size_t bytes, int, int, cudaStream_t s)

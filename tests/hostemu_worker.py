@@ -350,43 +350,72 @@ def device_timeout():
 
 
 def p2p_active_set():
-    """two-member active-set bcast on "device" buffers = send / recv through the heap channel kernel (kernels/nvl_p2p.cu): several
-    pairs at once, both directions, a message longer than the channel ring (sender and receiver pipeline), repeated (the channel
-    counters persist across launches) and next to a collective of the same team"""
+    """two-member active-set bcast on "device" buffers = send / recv (kernels/nvl_p2p.cu): several pairs at once, both directions,
+    a message longer than the channel ring (sender and receiver pipeline), repeated (the channel counters persist across launches)
+    and next to a collective of the same team.  Run twice: eager ring only (ZCOPY=n), and with the rendezvous protocol for
+    messages >= 64 KB (the sender stores into the receiver's published buffer), incl. more large messages in flight between one
+    pair than the board has slots and a small message posted behind a large one (sends keep their post order)."""
     import time
     n = 4
-    with UccJob(n, env=dict(BASE, **NOZC)) as j:
-        team = j.create_team(range(n))
-        for count in (1, 1000, 70001, 300007):
-            pairs = [(0, 1), (3, 1), (2, 0), (1, 3)]
-            for rep in range(2):
-                bufs, reqs = [], []
-                for i, (s_, d_) in enumerate(pairs):
-                    src, dst = Dev(count, fill=rnd(count, 100 * rep + i)), Dev(count, fill=0)
-                    bufs.append((src, dst))
-                    for r, b in ((s_, src), (d_, dst)):
-                        a = ca("bcast", b, None, root=s_, count_dst=0, active_set=(s_, d_ - s_, 2), tag=7 + i)
-                        q = C.POINTER(U.ucc_coll_req_t)()
-                        U.check(U.ucc_collective_init(C.byref(a), C.byref(q), team.members[r].team), "init")
-                        reqs.append((a, q))
-                for _, q in reqs:
-                    U.check(U.ucc_collective_post(q), "post")
-                t0 = time.time()
-                while any(q.contents.status == U.UCC_INPROGRESS for _, q in reqs):
-                    for r in range(n):
-                        U.ucc_context_progress(j.procs[r].ctx)
-                    assert time.time() - t0 < 120, "p2p did not complete"
-                rt.cudaDeviceSynchronize()
-                for _, q in reqs:
-                    assert q.contents.status == U.UCC_OK, q.contents.status
-                    U.ucc_collective_finalize(q)
-                for i, (src, dst) in enumerate(bufs):
-                    assert np.array_equal(src.a, dst.a), ("p2p", count, rep, pairs[i])
-            src = [Dev(777, fill=rnd(777, r)) for r in range(n)]
-            dst = [Dev(777, fill=0) for _ in range(n)]
-            run(team, [ca("allreduce", src[r], dst[r]) for r in range(n)])
-            assert np.allclose(dst[1].a, sum(s.a for s in src))
-    print("  active-set p2p ok", flush=True)
+
+    def drive(j, reqs):
+        t0 = time.time()
+        while any(q.contents.status == U.UCC_INPROGRESS for _, q in reqs):
+            for r in range(n):
+                U.ucc_context_progress(j.procs[r].ctx)
+            assert time.time() - t0 < 120, "p2p did not complete"
+        rt.cudaDeviceSynchronize()
+        for _, q in reqs:
+            assert q.contents.status == U.UCC_OK, q.contents.status
+            U.ucc_collective_finalize(q)
+
+    def msg(team, s_, d_, src, dst, tag):
+        out = []
+        for r, b in ((s_, src), (d_, dst)):
+            a = ca("bcast", b, None, root=s_, count_dst=0, active_set=(s_, d_ - s_, 2), tag=tag)
+            q = C.POINTER(U.ucc_coll_req_t)()
+            U.check(U.ucc_collective_init(C.byref(a), C.byref(q), team.members[r].team), "init")
+            out.append((a, q))
+        return out
+    for mode, env in (("ring", NOZC), ("rndv", dict(ZC, UCC_TL_NVL_P2P_RNDV_THRESH="64K"))):
+        with UccJob(n, env=dict(BASE, **env)) as j:
+            team = j.create_team(range(n))
+            for count in (1, 1000, 70001, 300007):
+                pairs = [(0, 1), (3, 1), (2, 0), (1, 3)]
+                for rep in range(2):
+                    bufs, reqs = [], []
+                    for i, (s_, d_) in enumerate(pairs):
+                        src, dst = Dev(count, fill=rnd(count, 100 * rep + i)), Dev(count, fill=0)
+                        bufs.append((src, dst))
+                        reqs += msg(team, s_, d_, src, dst, 7 + i)
+                    for _, q in reqs:
+                        U.check(U.ucc_collective_post(q), "post")
+                    drive(j, reqs)
+                    for i, (src, dst) in enumerate(bufs):
+                        assert np.array_equal(src.a, dst.a), ("p2p", mode, count, rep, pairs[i])
+                src = [Dev(777, fill=rnd(777, r)) for r in range(n)]
+                dst = [Dev(777, fill=0) for _ in range(n)]
+                run(team, [ca("allreduce", src[r], dst[r]) for r in range(n)])
+                assert np.allclose(dst[1].a, sum(s.a for s in src))
+            # seven messages 2 -> 3 back to back, large and small interleaved; all sends are posted before any receive
+            counts = [40000, 3, 50000, 60000, 17, 70000, 45000]
+            bufs = [(Dev(c, fill=rnd(c, 900 + i)), Dev(c, fill=0)) for i, c in enumerate(counts)]
+            pairs_q = [msg(team, 2, 3, s_, d_, 40 + i) for i, (s_, d_) in enumerate(bufs)]
+            for snd, _ in pairs_q:
+                U.check(U.ucc_collective_post(snd[1]), "post")
+            for _ in range(50):
+                for r in range(n):
+                    U.ucc_context_progress(j.procs[r].ctx)
+            for _, rcv in pairs_q:
+                U.check(U.ucc_collective_post(rcv[1]), "post")
+            drive(j, [x for pq in pairs_q for x in pq])
+            for i, (s_, d_) in enumerate(bufs):
+                assert np.array_equal(s_.a, d_.a), ("p2p burst", mode, i)
+            info = C.CDLL(os.path.join(os.environ["UCC_MODULE_DIR"], "libucc_tl_nvl.so")).ucc_tl_nvl_last_launch_info
+            info.restype = C.c_char_p
+            last = info().decode()
+            assert ("rndv" in last) == (mode == "rndv"), (mode, last)   # the last message (45000 floats) is above the threshold
+            print(f"  active-set p2p [{mode}] ok", flush=True)
 
 
 def registered_buffers():

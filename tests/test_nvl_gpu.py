@@ -491,13 +491,15 @@ def _p2p_round(j, team, msgs):
     torch.cuda.synchronize()
 
 
+@pytest.mark.parametrize("thresh", ["inf", "64K"])
 @pytest.mark.parametrize("count", [1, 1000, 65536 + 3, 700001])
-def test_active_set_p2p(count):
+def test_active_set_p2p(count, thresh):
     """reference test/gtest/active_set/test_active_set.cc:165-184: two-member active-set bcast = send / recv, here on CUDA buffers
-    through the tl/nvl channel kernel (700001 floats > the 1 MB ring: sender and receiver pipeline through the slots)"""
+    through the tl/nvl channel kernel (700001 floats > the 1 MB ring: sender and receiver pipeline through the slots) and, with
+    P2P_RNDV_THRESH=64K, through the rendezvous kernels (the sender stores into the receiver's buffer)"""
     need_cuda()
     n = 4
-    with UccJob(n, env=dict(ENV)) as j:
+    with UccJob(n, env=dict(ENV, UCC_TL_NVL_P2P_RNDV_THRESH=thresh)) as j:
         team = j.create_team()
         pairs = [(0, 1), (3, 1), (2, 0), (1, 3)]
         srcs = [gen("float32", count, 10 + i) for i in range(len(pairs))]
@@ -514,10 +516,38 @@ def test_active_set_p2p(count):
         dst = [torch.zeros(5000, device="cuda") for _ in range(n)]
         run(team, [cargs("allreduce", src[r], dst[r], "float32") for r in range(n)])
         assert_close(dst[2], ref_reduce("sum", src), "float32")
-    import ctypes as C
-    info = C.CDLL(os.path.join(os.path.dirname(U.LIB_PATH), "ucc", "libucc_tl_nvl.so")).ucc_tl_nvl_last_launch_info
-    info.restype = C.c_char_p
-    assert info() is not None
+        import ctypes as C
+        info = C.CDLL(os.path.join(os.path.dirname(U.LIB_PATH), "ucc", "libucc_tl_nvl.so")).ucc_tl_nvl_last_launch_info
+        info.restype = C.c_char_p
+        if count == 700001:
+            # burst 2 -> 3: more large messages than board slots, small ones in between, every send posted before any receive
+            counts = [40000, 3, 50000, 60000, 17, 70000, 45000]
+            bs = [gen("float32", c, 70 + i) for i, c in enumerate(counts)]
+            bd = [torch.zeros(c, device="cuda") for c in counts]
+            import time
+            sends, recvs = [], []
+            for i in range(len(counts)):
+                for r, buf, lst in ((2, bs[i], sends), (3, bd[i], recvs)):
+                    a = cargs("bcast", buf, None, "float32", root=2, count_dst=0, active_set=(2, 1, 2), tag=30 + i)
+                    q = C.POINTER(U.ucc_coll_req_t)()
+                    assert U.ucc_collective_init(C.byref(a), C.byref(q), team.members[r].team) == U.UCC_OK
+                    lst.append((q, a))
+            for q, _ in sends:
+                assert U.ucc_collective_post(q) == U.UCC_OK
+            for _ in range(20):
+                j.progress()
+            for q, _ in recvs:
+                assert U.ucc_collective_post(q) == U.UCC_OK
+            t0 = time.time()
+            while any(q.contents.status == U.UCC_INPROGRESS for q, _ in sends + recvs) and time.time() - t0 < 20:
+                j.progress()
+            for q, _ in sends + recvs:
+                assert q.contents.status == U.UCC_OK, U.status_str(q.contents.status)
+                U.ucc_collective_finalize(q)
+            torch.cuda.synchronize()
+            for i in range(len(counts)):
+                assert torch.equal(bd[i], bs[i]), ("burst", i)
+            assert ("rndv" in info().decode()) == (thresh == "64K"), info()
 
 
 @pytest.mark.parametrize("slots", [1, 4])

@@ -12,6 +12,7 @@ The report at the end has the reference's shape (total / passed / skipped / fail
 from __future__ import annotations
 
 import argparse
+import faulthandler
 import ctypes as C
 import itertools
 import os
@@ -404,6 +405,7 @@ def parse_args(argv):
 
 
 def main(argv=None):
+    faulthandler.enable()
     a = parse_args(argv)
     colls = ALL_COLLS if a.colls == "all" else a.colls.split(",")
     for c in colls:
