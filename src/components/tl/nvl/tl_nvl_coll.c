@@ -373,7 +373,9 @@ static void nvl_progress(ucc_coll_task_t *ct)
         ucc_spin_unlock(&t->team->launch_lock);
         if (st == UCC_INPROGRESS) return;
         if (st != UCC_OK) { ct->status = st; return; }
-        if (t->state == NVL_TASK_LAUNCHED && t->u.p2p.send && t->super.ee && !t->p2p_ee_done) {
+        /* stream-ordered post: a send is in the user's stream once launched; a receive counts as posted once its buffer is on
+         * the board (until then the owner has to keep progressing, nobody else can publish it) */
+        if (t->state == NVL_TASK_LAUNCHED && !t->rz_pub_pending && t->super.ee && !t->p2p_ee_done) {
             ucc_ev_t post_event;
             t->p2p_ee_done = 1;
             post_event.ev_type = UCC_EVENT_COLLECTIVE_POST; post_event.ev_context = NULL; post_event.ev_context_size = 0; post_event.req = &t->super.super;
@@ -461,7 +463,7 @@ static ucc_status_t nvl_triggered_post(ucc_ee_h ee, ucc_ev_t *ev, ucc_coll_task_
     ct->ee = ee;
     st = nvl_post_on(t, (cudaStream_t)ee->ee_context);
     if (st != UCC_OK) return st;
-    if (t->state == NVL_TASK_QUEUED || t->state == NVL_TASK_P2P_WAIT) return UCC_OK; /* the post event follows the deferred launch */
+    if (t->state == NVL_TASK_QUEUED || t->state == NVL_TASK_P2P_WAIT || (t->kind == NVL_TASK_P2P && t->rz_pub_pending)) return UCC_OK; /* the post event follows the deferred launch / publication */
     t->p2p_ee_done = 1;
     post_event.ev_type = UCC_EVENT_COLLECTIVE_POST; post_event.ev_context = NULL; post_event.ev_context_size = 0; post_event.req = &ct->super;
     ucc_ee_set_event_internal(ee, &post_event, &ee->event_out_queue);

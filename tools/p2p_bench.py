@@ -37,7 +37,7 @@ for nbytes in (4096, 65536, 1 << 20, 16 << 20, 128 << 20):
         # ---- ours: rank 0 -> rank 1, ITERS messages back to back
         with torch.cuda.stream(stream):
             for _ in range(3):
-                r = p2p_req(buf, 0, 1); r.post_on_stream(stream); r.wait(); r.finalize()
+                r = p2p_req(buf, 0, 1); r.post_on_stream(stream, wait_posted=False); r.wait(); r.finalize()
             torch.cuda.synchronize()
     dist.barrier()
     if rank < 2:
@@ -46,7 +46,7 @@ for nbytes in (4096, 65536, 1 << 20, 16 << 20, 128 << 20):
             reqs = [p2p_req(buf, 0, 1) for _ in range(ITERS)]
             e0.record(stream)
             for r in reqs:
-                r.post_on_stream(stream)
+                r.post_on_stream(stream, wait_posted=False)
             e1.record(stream)
             for r in reqs:
                 r.wait(); r.finalize()

@@ -47,9 +47,9 @@ class Work:
         return True
 
 
-def _launch(comm, req, tensor, async_op, keep=()):
+def _launch(comm, req, tensor, async_op, keep=(), wait_posted=True):
     if tensor is not None and tensor.is_cuda:
-        req.post_on_stream()
+        req.post_on_stream(wait_posted=wait_posted)
     else:
         req.post()
     w = Work(req, keep)
@@ -175,7 +175,9 @@ def barrier(comm=None):
 # ---- point to point (pipeline / ring-attention shapes): a two-member active-set broadcast, the way ProcessGroupUCC does it
 def _p2p(tensor, src, dst, tag, comm, async_op):
     req = comm.coll_init("bcast", tensor, None, root=src, active_set=(src, dst - src, 2), tag=int(tag) & 0x3fff)
-    return _launch(comm, req, tensor, async_op)
+    # a large send is launched only once the receiver has published its buffer (rendezvous): never block in the post, or two
+    # ranks that both send first would wait for each other's receive forever; Work.wait() drives the progress
+    return _launch(comm, req, tensor, async_op, wait_posted=False)
 
 
 def send(tensor, dst, tag=0, comm=None, async_op=False):

@@ -41,6 +41,8 @@ class _Work(dist._Work):
         for r in self._reqs:
             if not self._cuda:
                 r.wait()            # host buffers: completion == data valid
+            else:
+                r.wait_posted()     # the kernel is in the stream (idempotent; immediate for everything but p2p)
             r.finalize_later() if self._cuda else r.finalize()
         self._done = True
         self._fut.set_result(self._result)
@@ -73,11 +75,11 @@ class ProcessGroupUCCB200(dist.ProcessGroup):
         return "ucc_b200"
 
     # ---- helpers
-    def _run(self, reqs, tensors, result):
+    def _run(self, reqs, tensors, result, wait_posted=True):
         cuda = bool(tensors) and tensors[0].is_cuda
         for r in reqs:
             if cuda:
-                r.post_on_stream()          # returns once the kernel is in the current stream
+                r.post_on_stream(wait_posted=wait_posted)   # returns once the kernel is in the current stream
                 r.finalize_later = lambda r=r: self._pending.append(r)
             else:
                 r.post()
@@ -171,7 +173,9 @@ class ProcessGroupUCCB200(dist.ProcessGroup):
     # contract: the tag does not reorder them); host tensors go through tl/shm, which matches by tag.
     def _p2p(self, tensors, src, dst, tag):
         reqs = [self._comm.coll_init("bcast", t, None, root=src, active_set=(src, dst - src, 2), tag=int(tag) & 0x3fff) for t in tensors]
-        return self._run(reqs, tensors, tensors)
+        # rendezvous: a large send enters the stream when the receiver has published its buffer, a receive is published when the
+        # stream reaches it - both need progress, which Work.wait() provides (isend + irecv + wait, as with every backend)
+        return self._run(reqs, tensors, tensors, wait_posted=False)
 
     def send(self, tensors, dstRank, tag=0):
         return self._p2p(tensors, self.rank(), dstRank, tag)
