@@ -1090,6 +1090,15 @@ ucc_status_t ucc_tl_nvl_team_get_scores(ucc_base_team_t *b_team, ucc_coll_score_
     if (team->nvls && UCC_TL_TEAM_SIZE(team) > 4)
         snprintf(sel, sizeof(sel), "allreduce:0-%s:@oneshot#allreduce:%s-inf:@%s", a, n, ctx->cfg.symmetric_size >= ((size_t)192 << 20) ? "nvls_pipe" : "nvls");
     else snprintf(sel, sizeof(sel), "allreduce:0-%s:@oneshot", a);
+    /* data movement on teams of more than four (8 x B200, profiles/r2_n8/colls.jsonl): at 16 MB the zero-copy push exchange is at
+     * NCCL's speed (allgather 54.8 us, alltoall 56.1 us; NCCL 53.9 / 56.6) where the pull kernel needs 69.3 / 66.7 us; at 1 MB and at
+     * 256 MB pull is as good or better; push falls back to pull when a destination cannot be mapped.  (The skewed MoE alltoallv is
+     * fastest on the copy engines from a few MB on - 16 MB: 93.9 us vs 144.3 us pull, NCCL 94.6 - but its sizes are private to each
+     * member, so the score map cannot select by size (msgsize 0): `UCC_TL_NVL_TUNE=alltoallv:@ce` is the user's call) */
+    if (UCC_TL_TEAM_SIZE(team) > 4 && team->zcopy) {
+        size_t l = strlen(sel);
+        snprintf(sel + l, sizeof(sel) - l, "#allgather:4M-64M:@push#alltoall:4M-64M:@push");
+    }
     st = ucc_tl_apply_tune(&team->super, score, &info, sel, ctx->cfg.super.super.score_str);
     if (st != UCC_OK) { ucc_coll_score_free(score); return st; }
     *score_p = score;

@@ -573,7 +573,37 @@ def int_avg():
     print("  integer AVG ok", flush=True)
 
 
+def default_selection():
+    """score-map defaults of a team of more than four (tl_nvl_coll.c get_scores): allgather / alltoall of 4-64 MB take the zero-copy
+    push kernel, everything else (incl. alltoallv, whose sizes are private: no size-based choice) the pull kernel - checked through the launch note"""
+    n = 6
+    info = C.CDLL(os.path.join(os.environ["UCC_MODULE_DIR"], "libucc_tl_nvl.so")).ucc_tl_nvl_last_launch_info
+    info.restype = C.c_char_p
+    with UccJob(n, env=dict(BASE, UCC_TL_NVL_ZCOPY="y", UCC_TL_NVL_SYMMETRIC_SIZE="32Mb")) as j:
+        team = j.create_team(range(n))
+        for blk, want_ag, want_a2av in ((1000, "exchange_pull", "exchange_pull"), (200000, "exchange_push", "exchange_pull"), (400000, "exchange_push", "exchange_pull")):
+            count = blk * n
+            src = [Dev(blk, fill=rnd(blk, r)) for r in range(n)]
+            dst = [Dev(count, fill=0) for _ in range(n)]
+            run(team, [ca("allgather", src[r], dst[r]) for r in range(n)])
+            assert want_ag in info().decode(), (count, info())
+            assert np.array_equal(dst[2].a, np.concatenate([s_.a for s_ in src]))
+            src = [Dev(count, fill=rnd(count, 10 + r)) for r in range(n)]
+            dst = [Dev(count, fill=0) for _ in range(n)]
+            run(team, [ca("alltoall", src[r], dst[r]) for r in range(n)])
+            assert want_ag in info().decode(), (count, info())
+            assert np.array_equal(dst[3].a, np.concatenate([s_.a[3 * blk:4 * blk] for s_ in src]))
+            cnt = [blk] * n
+            dsp = [i * blk for i in range(n)]
+            dst = [Dev(count, fill=0) for _ in range(n)]
+            run(team, [ca("alltoallv", src[r], dst[r], src_counts=cnt, src_displs=dsp, dst_counts=cnt, dst_displs=dsp) for r in range(n)])
+            assert want_a2av in info().decode(), (count, info())
+            assert np.array_equal(dst[1].a, np.concatenate([s_.a[blk:2 * blk] for s_ in src]))
+    print("  default selection ok", flush=True)
+
+
 SCENARIOS = {
+    "defaults": default_selection,
     "allreduce": lambda: [allreduce_suite(a, e) for a, e in (("oneshot", NOZC), ("twoshot", NOZC), ("twoshot", ZC), ("ring", NOZC), ("rhd", NOZC))],
     "colls_staged": lambda: other_colls(NOZC),
     "colls_zcopy": lambda: other_colls(ZC),
