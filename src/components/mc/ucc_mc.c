@@ -67,16 +67,21 @@ ucc_status_t ucc_mc_memcpy(void *dst, const void *src, size_t len, ucc_memory_ty
 ucc_status_t ucc_mc_memset(void *ptr, int value, size_t size, ucc_memory_type_t mt) { CHECK_MT(mt); return mc_ops[mt]->ops.memset(ptr, value, size); }
 ucc_status_t ucc_mc_finalize(void)
 {
+    /* CUDA_MANAGED is served by the cuda component (an alias entry, not a reference of its own): it must neither be counted
+     * twice nor dropped while another lib instance still holds the component.  (Counting it after the CUDA entry had been
+     * cleared drove ref_cnt below zero, so the NEXT ucc_init in the process skipped the component's init and used it without a
+     * config - found by tools/ucc_test_dist.py -M cuda, which creates one lib per team kind.) */
+    ucc_mc_base_t *cuda = mc_ops[UCC_MEMORY_TYPE_CUDA];
+    int managed_alias = cuda && mc_ops[UCC_MEMORY_TYPE_CUDA_MANAGED] == cuda;
     for (int mt = 0; mt < UCC_MEMORY_TYPE_LAST; mt++) {
         ucc_mc_base_t *mc = mc_ops[mt];
-        if (!mc) continue;
-        if (mt == UCC_MEMORY_TYPE_CUDA_MANAGED && mc == mc_ops[UCC_MEMORY_TYPE_CUDA]) { mc_ops[mt] = NULL; continue; }
+        if (!mc || (mt == UCC_MEMORY_TYPE_CUDA_MANAGED && managed_alias)) continue;
         if (--mc->ref_cnt == 0) {
             mc->finalize();
             ucc_config_parser_release_opts(mc->config, mc->config_table.table);
             free(mc->config); mc->config = NULL; mc_ops[mt] = NULL;
         }
     }
-    if (!mc_ops[UCC_MEMORY_TYPE_CUDA]) mc_ops[UCC_MEMORY_TYPE_CUDA_MANAGED] = NULL;
+    if (managed_alias && !mc_ops[UCC_MEMORY_TYPE_CUDA]) mc_ops[UCC_MEMORY_TYPE_CUDA_MANAGED] = NULL;
     return UCC_OK;
 }

@@ -211,6 +211,7 @@ typedef struct ucc_tl_nvl_task {
     uint32_t            p2p_order;     /* send: position among the sends to this peer */
     uint64_t            rz_seq;        /* rendezvous: index among the large messages of the pair */
     int                 p2p_ee_done;   /* the UCC_EVENT_COLLECTIVE_POST of this post was delivered */
+    int                 rz_stream_idle;/* recv: the stream had nothing queued at post time */
     int                 rz_pub_pending;/* recv: the buffer is not on the board yet (stream not there yet / slot busy / not my turn) */
     nvl_xb_buf_t        rz_buf;        /* recv: what will be published */
     /* zero-copy push exchange (kernels/nvl_push.cu): used instead of the pull kernel when the destinations resolved */

@@ -243,7 +243,7 @@ static void p2p_try_publish(ucc_tl_nvl_task_t *t)
     nvl_xb_rz_t *e = &team->xb_mine->rz[peer][t->rz_seq % NVL_XB_RZ_SLOTS];
     if (!t->rz_pub_pending || t->rz_seq != team->rz_pub[peer]) return;
     if (t->rz_seq >= NVL_XB_RZ_SLOTS && ucc_load_acquire(&team->xb[peer]->rz_consumed[me]) + NVL_XB_RZ_SLOTS <= t->rz_seq) return;
-    if (xb_kind_mappable(t->rz_buf.kind)) { /* my stream must be at the recv: earlier work in it may still use the buffer */
+    if (xb_kind_mappable(t->rz_buf.kind) && !t->rz_stream_idle) { /* my stream must be at the recv: earlier work in it may still use the buffer */
         cudaError_t ce = cudaEventQuery(t->in_event);
         if (ce == cudaErrorNotReady) { (void)cudaGetLastError(); return; }
     }
@@ -322,7 +322,9 @@ static ucc_status_t p2p_post(ucc_tl_nvl_task_t *t, cudaStream_t s)
         ucc_tl_nvl_xb_export(team, t->u.p2p.buf, t->u.p2p.bytes, &t->rz_buf);
         if (xb_kind_mappable(t->rz_buf.kind)) {
             t->u.p2p.mode = NVL_P2P_WAIT; t->u.p2p.rz_seq = team->rz_zc_rx[peer]++;
-            CUDA_CHECK(cudaEventRecord(t->in_event, s));
+            /* an idle stream is at the recv already: publish right away (saves one host poll of the handshake) */
+            t->rz_stream_idle = cudaStreamQuery(s) == cudaSuccess;
+            if (!t->rz_stream_idle) { (void)cudaGetLastError(); CUDA_CHECK(cudaEventRecord(t->in_event, s)); }
         }
         t->rz_pub_pending = 1;
         p2p_try_publish(t);

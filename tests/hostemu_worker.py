@@ -602,6 +602,30 @@ def default_selection():
     print("  default selection ok", flush=True)
 
 
+def mc_lifecycle():
+    """memory-component reference counting across lib instances (src/components/mc/ucc_mc.c): CUDA_MANAGED is an alias of the cuda
+    component.  One lib created, destroyed and created again in the same process must find the component initialised (a negative
+    reference count once made the second ucc_init skip its init: NULL config, SIGSEGV in the first pooled allocation - seen with
+    tools/ucc_test_dist.py -M cuda on two GPUs); and with two libs alive, destroying one must not drop the alias of the other."""
+    L = U.lib
+    hdr = C.c_void_p()
+    MANAGED = U.UCC_MEMORY_TYPE_CUDA_MANAGED
+    L.ucc_mc_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t, C.c_int]
+    L.ucc_mc_free.argtypes = [C.c_void_p]
+    L.ucc_mc_available.argtypes = [C.c_int]
+    for rep in range(3):
+        with UccJob(1, env=dict(BASE)) as j:
+            assert L.ucc_mc_alloc(C.byref(hdr), 4096, CUDA) == 0, rep
+            assert L.ucc_mc_free(hdr) == 0
+            assert L.ucc_mc_available(MANAGED) == 0
+    with UccJob(1, env=dict(BASE)) as a:
+        with UccJob(1, env=dict(BASE)) as b:
+            assert L.ucc_mc_available(MANAGED) == 0
+        assert L.ucc_mc_available(MANAGED) == 0, "alias dropped while a lib is alive"
+        assert L.ucc_mc_alloc(C.byref(hdr), 4096, CUDA) == 0 and L.ucc_mc_free(hdr) == 0
+    print("  mc lifecycle ok", flush=True)
+
+
 SCENARIOS = {
     "defaults": default_selection,
     "allreduce": lambda: [allreduce_suite(a, e) for a, e in (("oneshot", NOZC), ("twoshot", NOZC), ("twoshot", ZC), ("ring", NOZC), ("rhd", NOZC))],
@@ -610,7 +634,7 @@ SCENARIOS = {
     "colls_push": lambda: other_colls(ZC, "allgather:cuda:inf:@push#allgatherv:cuda:inf:@push#alltoall:cuda:inf:@push#alltoallv:cuda:inf:@push#reduce_scatter:cuda:inf:@oneshot#reduce_scatterv:cuda:inf:@oneshot"),
     "colls_ce": lambda: other_colls(ZC, "allgather:cuda:inf:@ce#allgatherv:cuda:inf:@ce#alltoall:cuda:inf:@ce#alltoallv:cuda:inf:@ce"),
     "colls_ring": lambda: other_colls(NOZC, "allgather:cuda:inf:@ring#allgatherv:cuda:inf:@ring#reduce_scatter:cuda:inf:@ring#reduce_scatterv:cuda:inf:@ring"),
-    "misc": lambda: [persistent_and_teams(), asymmetric_memory()],
+    "misc": lambda: [mc_lifecycle(), persistent_and_teams(), asymmetric_memory()],
     "triggered": lambda: [triggered(NOZC), triggered(ZC)],
     "timeout": device_timeout,
     "cross_team": lambda: [cross_team_order(NOZC), cross_team_order(ZC)],
