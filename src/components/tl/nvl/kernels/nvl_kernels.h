@@ -19,6 +19,7 @@
 #define NVL_P2P_SLOTS    4                   /* chunks in flight per channel */
 #define NVL_P2P_CHUNK    (256 * 1024)
 #define NVL_P2P_CHAN_BYTES (NVL_P2P_SLOTS * NVL_P2P_CHUNK)
+#define NVL_P2P_LANE_BYTES (NVL_P2P_CHUNK / NVL_P2P_MAX_CTAS)   /* 16 KB: what one CTA moves per ring step */
 
 /* control block at offset 0 of every rank's heap */
 typedef struct nvl_ctrl {

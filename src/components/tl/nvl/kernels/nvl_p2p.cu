@@ -48,8 +48,11 @@ __global__ void __launch_bounds__(NVL_THREADS_MAX) nvl_p2p_kernel(const __grid_c
     const int me = t.rank, peer = a.peer, b = blockIdx.x, nb = gridDim.x;
     nvl_ctrl_t *mine = reinterpret_cast<nvl_ctrl_t *>(t.heap[me]);
     nvl_ctrl_t *theirs = reinterpret_cast<nvl_ctrl_t *>(t.heap[peer]);
-    /* lane b of a chunk: bytes [b * lane, (b + 1) * lane) of the chunk, lane a multiple of 16 */
-    const size_t chunk = NVL_P2P_CHUNK, lane = chunk / nb / 16 * 16;
+    /* lane b of a chunk: bytes [b * lane, (b + 1) * lane) of the chunk.  The lane WIDTH is fixed (chunk / max lanes), only the
+     * number of lanes a message uses follows from its size: every lane is then an independent ring with its own byte range and
+     * its own counters.  (With a width of chunk / nb, messages of different lane counts that were in flight together overlapped in
+     * the slots: lane 1 of a 4-lane message could land on unconsumed data of lane 0 of a 3-lane one.) */
+    const size_t chunk = NVL_P2P_CHUNK, lane = NVL_P2P_LANE_BYTES;
     const size_t per_chunk = lane * nb;                              /* payload bytes one chunk carries with this lane count */
     const uint32_t nchunks = (uint32_t)((a.bytes + per_chunk - 1) / per_chunk);
     char *ubuf = static_cast<char *>(a.buf);
@@ -126,7 +129,7 @@ extern "C" int nvl_p2p_push_ctas(size_t bytes)
 }
 extern "C" int nvl_p2p_lanes(size_t bytes)
 {
-    size_t n = bytes / (64 * 1024);
+    size_t n = (bytes + NVL_P2P_LANE_BYTES - 1) / NVL_P2P_LANE_BYTES;
     return n < 1 ? 1 : (n > NVL_P2P_MAX_CTAS ? NVL_P2P_MAX_CTAS : (int)n);
 }
 extern "C" cudaError_t nvl_launch_p2p(const nvl_p2p_args_t *a, int nthreads, cudaStream_t s)

@@ -679,6 +679,10 @@ static ucc_status_t red_init(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, u
         if (s0 >= ub && s0 + ucc_align_up(bytes, 16) <= ue && d0 >= ub && d0 + bytes <= ue && !(((uintptr_t)s0 | (uintptr_t)d0) & 15)) {
             t->kind = NVL_TASK_REDUCE_SYMM; r->d.src[0] = s0; r->d.dst[0] = (char *)dst; r->use_nvls = 1;
             t->nblocks = pick_blocks(ctx, bytes, 32 * 1024);
+            /* nothing is staged here, every thread only issues multimem.ld_reduce / multimem.st: the switch is saturated by few CTAs
+             * and slowed down by many (8 x B200, 1 GiB: 32 CTAs 839 GB/s, 64: 837, 256: 705; 64 MB: 700 / 669 / 562 -
+             * profiles/r2_n8/matrix.jsonl) */
+            if (N > 4 && t->nblocks > 32) t->nblocks = 32;
             *task_p = &t->super;
             return UCC_OK;
         }

@@ -406,6 +406,7 @@ def p2p_active_set():
             for _ in range(50):
                 for r in range(n):
                     U.ucc_context_progress(j.procs[r].ctx)
+            time.sleep(0.5)   # let the sender's kernels run as far as they can without the receiver (they fill the ring)
             for _, rcv in pairs_q:
                 U.check(U.ucc_collective_post(rcv[1]), "post")
             drive(j, [x for pq in pairs_q for x in pq])

@@ -473,6 +473,7 @@ def _p2p_round(j, team, msgs):
     import ctypes as C
     import time
     reqs = []
+    torch.cuda.synchronize()   # the tensors were filled on torch's stream; the (non-blocking) team streams do not wait for it
     for s_, d_, ts, td, tag in msgs:
         for r, buf in ((s_, ts), (d_, td)):
             a = cargs("bcast", buf, None, "float32", root=s_, count_dst=0, active_set=(s_, d_ - s_, 2), tag=tag)
@@ -524,6 +525,7 @@ def test_active_set_p2p(count, thresh):
             counts = [40000, 3, 50000, 60000, 17, 70000, 45000]
             bs = [gen("float32", c, 70 + i) for i, c in enumerate(counts)]
             bd = [torch.zeros(c, device="cuda") for c in counts]
+            torch.cuda.synchronize()   # the team streams are non-blocking: they do not wait for the stream that fills these tensors
             import time
             sends, recvs = [], []
             for i in range(len(counts)):
