@@ -63,11 +63,12 @@ typedef enum { NVL_XB_NONE = 0, NVL_XB_EMPTY, NVL_XB_RAW, NVL_XB_IPC } nvl_xb_ki
 typedef struct nvl_xb_buf { int32_t kind; int32_t pad; uint64_t base, off, len, alloc_len; cudaIpcMemHandle_t handle; } nvl_xb_buf_t;
 typedef struct nvl_xb_entry { uint64_t seq; nvl_xb_buf_t src, dst; uint64_t aux[NVL_MAX_PEERS]; /* alltoallv: byte offset of source p's block inside my dst */ } nvl_xb_entry_t;
 /* rendezvous send / recv: rz[p][k % NVL_XB_RZ_SLOTS] is written by the board's owner (the RECEIVER) for its k-th large receive from
- * member p (seq = k + 1); rz_consumed[p] is written by the owner as SENDER: how many receive posts of member p it has used */
+ * member p (seq = k + 1); rz_consumed[p] is written by the owner as SENDER: how many receive posts of member p it has used;
+ * rz_launched[p], also written as sender: how many zero-copy push kernels towards member p have been launched */
 #define NVL_XB_RZ_SLOTS 4
 typedef struct nvl_xb_rz { uint64_t seq; nvl_xb_buf_t buf; } nvl_xb_rz_t;
 typedef struct nvl_xb_seg { uint64_t consumed; uint64_t pad[7]; nvl_xb_entry_t e[NVL_XB_SLOTS];
-                            uint64_t rz_consumed[NVL_MAX_PEERS]; nvl_xb_rz_t rz[NVL_MAX_PEERS][NVL_XB_RZ_SLOTS]; } nvl_xb_seg_t;
+                            uint64_t rz_consumed[NVL_MAX_PEERS]; uint32_t rz_launched[NVL_MAX_PEERS]; nvl_xb_rz_t rz[NVL_MAX_PEERS][NVL_XB_RZ_SLOTS]; } nvl_xb_seg_t;
 typedef struct nvl_ipc_cache { unsigned n; struct { uint64_t base; cudaIpcMemHandle_t handle; void *mapped; } e[NVL_IPC_CACHE_MAX]; } nvl_ipc_cache_t;
 
 typedef struct ucc_tl_nvl_lib { ucc_tl_lib_t super; } ucc_tl_nvl_lib_t;
@@ -211,6 +212,7 @@ typedef struct ucc_tl_nvl_task {
     uint32_t            p2p_order;     /* send: position among the sends to this peer */
     uint64_t            rz_seq;        /* rendezvous: index among the large messages of the pair */
     int                 p2p_ee_done;   /* the UCC_EVENT_COLLECTIVE_POST of this post was delivered */
+    int                 rz_wait_pending;/* recv: the wait kernel is not in the stream yet (it follows the launch of the sender's push) */
     int                 rz_stream_idle;/* recv: the stream had nothing queued at post time */
     int                 rz_pub_pending;/* recv: the buffer is not on the board yet (stream not there yet / slot busy / not my turn) */
     nvl_xb_buf_t        rz_buf;        /* recv: what will be published */

@@ -252,6 +252,21 @@ static void p2p_try_publish(ucc_tl_nvl_task_t *t)
     team->rz_pub[peer]++; t->rz_pub_pending = 0;
 }
 
+static ucc_status_t p2p_try_wait(ucc_tl_nvl_task_t *t)
+{
+    ucc_tl_nvl_team_t *team = t->team;
+    int peer = t->u.p2p.peer;
+    ucc_rank_t me = UCC_TL_TEAM_RANK(team);
+    ucc_status_t st;
+    if (!t->rz_wait_pending || t->rz_pub_pending) return UCC_OK;
+    if ((int32_t)(ucc_load_acquire(&team->xb[peer]->rz_launched[me]) - (t->u.p2p.rz_seq + 1)) < 0) return UCC_OK;
+    st = nvl_launch(t, t->stream);
+    if (st != UCC_OK) return st;
+    CUDA_CHECK(cudaEventRecord(t->event, t->stream));
+    t->rz_wait_pending = 0;
+    return UCC_OK;
+}
+
 /* UCC_OK: launched; UCC_INPROGRESS: not its turn / the receiver has not published yet */
 static ucc_status_t p2p_try_send(ucc_tl_nvl_task_t *t, int at_post)
 {
@@ -286,6 +301,7 @@ static ucc_status_t p2p_try_send(ucc_tl_nvl_task_t *t, int at_post)
         CUDA_CHECK(cudaEventRecord(t->event, team->p2p_stream[peer]));
         CUDA_CHECK(cudaEventRecord(team->p2p_side_event[peer], team->p2p_stream[peer]));
         team->p2p_side_used[peer] = 1;
+        if (t->u.p2p.mode == NVL_P2P_PUSH) ucc_store_release(&team->xb_mine->rz_launched[peer], t->u.p2p.rz_seq + 1);
         CUDA_CHECK(cudaStreamWaitEvent(t->stream, t->event, 0));   /* the send is "in" the user's stream from here on */
     } else {
         if (team->p2p_side_used[peer] && !t->captured) CUDA_CHECK(cudaStreamWaitEvent(t->stream, team->p2p_side_event[peer], 0));
@@ -302,7 +318,9 @@ static ucc_status_t p2p_post(ucc_tl_nvl_task_t *t, cudaStream_t s)
     ucc_tl_nvl_team_t *team = t->team;
     int peer = t->u.p2p.peer, rndv = t->p2p_rndv && !t->captured;
     ucc_status_t st;
-    t->u.p2p.mode = NVL_P2P_RING; t->rz_pub_pending = 0;
+    t->u.p2p.mode = NVL_P2P_RING; t->rz_pub_pending = 0; t->rz_wait_pending = 0;
+    tl_debug(NVL_LIB(team), "%s %zu bytes %s %d: %s (P2P_RNDV_THRESH %zu, zero-copy boards %d)", t->u.p2p.send ? "send" : "recv", t->u.p2p.bytes,
+             t->u.p2p.send ? "to" : "from", peer, rndv ? "rendezvous" : "eager ring", NVL_CTX(team)->cfg.p2p_rndv_thresh, team->zcopy);
     if (!t->captured && !t->in_event) { t->in_event = event_get(NVL_CTX(team)); if (!t->in_event) return UCC_ERR_NO_RESOURCE; }
     if (t->u.p2p.send) {
         t->p2p_order = team->p2p_post_seq[peer]++;
@@ -328,6 +346,11 @@ static ucc_status_t p2p_post(ucc_tl_nvl_task_t *t, cudaStream_t s)
         }
         t->rz_pub_pending = 1;
         p2p_try_publish(t);
+        /* the wait kernel goes into the stream only once the sender's push kernel has been LAUNCHED (p2p_try_wait, from progress):
+         * a kernel that spins for an unbounded time can stall unrelated streams that share its hardware queue - among them the
+         * side stream of this rank's own push, which the peer's wait kernel is waiting for.  The push never waits for anything
+         * on the device, so a wait kernel enqueued after its launch spins for the duration of the transfer at most */
+        if (t->u.p2p.mode == NVL_P2P_WAIT) { t->rz_wait_pending = 1; return UCC_OK; }
     }
     st = nvl_launch(t, s);
     if (st != UCC_OK) return st;
@@ -364,10 +387,12 @@ static void nvl_progress(ucc_coll_task_t *ct)
 {
     ucc_tl_nvl_task_t *t = ucc_derived_of(ct, ucc_tl_nvl_task_t);
     cudaError_t e;
-    if (t->kind == NVL_TASK_P2P && (t->rz_pub_pending || t->state == NVL_TASK_P2P_WAIT)) {
+    if (t->kind == NVL_TASK_P2P && (t->rz_pub_pending || t->rz_wait_pending || t->state == NVL_TASK_P2P_WAIT)) {
         ucc_status_t st = UCC_OK;
         ucc_spin_lock(&t->team->launch_lock);
         p2p_try_publish(t);
+        st = p2p_try_wait(t);
+        if (st != UCC_OK) { ucc_spin_unlock(&t->team->launch_lock); ct->status = st; return; }
         if (t->state == NVL_TASK_P2P_WAIT) {
             st = p2p_try_send(t, 0);
             if (st != UCC_INPROGRESS) t->state = NVL_TASK_LAUNCHED;
@@ -377,13 +402,14 @@ static void nvl_progress(ucc_coll_task_t *ct)
         if (st != UCC_OK) { ct->status = st; return; }
         /* stream-ordered post: a send is in the user's stream once launched; a receive counts as posted once its buffer is on
          * the board (until then the owner has to keep progressing, nobody else can publish it) */
-        if (t->state == NVL_TASK_LAUNCHED && !t->rz_pub_pending && t->super.ee && !t->p2p_ee_done) {
+        if (t->state == NVL_TASK_LAUNCHED && !t->rz_pub_pending && !t->rz_wait_pending && t->super.ee && !t->p2p_ee_done) {
             ucc_ev_t post_event;
             t->p2p_ee_done = 1;
             post_event.ev_type = UCC_EVENT_COLLECTIVE_POST; post_event.ev_context = NULL; post_event.ev_context_size = 0; post_event.req = &t->super.super;
             ucc_ee_set_event_internal(t->super.ee, &post_event, &t->super.ee->event_out_queue);
         }
     }
+    if (t->kind == NVL_TASK_P2P && t->rz_wait_pending) return;   /* its event is not recorded yet */
     if (t->state == NVL_TASK_QUEUED) {
         ucc_status_t st;
         ucc_spin_lock(&t->team->launch_lock);
@@ -465,7 +491,7 @@ static ucc_status_t nvl_triggered_post(ucc_ee_h ee, ucc_ev_t *ev, ucc_coll_task_
     ct->ee = ee;
     st = nvl_post_on(t, (cudaStream_t)ee->ee_context);
     if (st != UCC_OK) return st;
-    if (t->state == NVL_TASK_QUEUED || t->state == NVL_TASK_P2P_WAIT || (t->kind == NVL_TASK_P2P && t->rz_pub_pending)) return UCC_OK; /* the post event follows the deferred launch / publication */
+    if (t->state == NVL_TASK_QUEUED || t->state == NVL_TASK_P2P_WAIT || (t->kind == NVL_TASK_P2P && (t->rz_pub_pending || t->rz_wait_pending))) return UCC_OK; /* the post event follows the deferred launch / publication */
     t->p2p_ee_done = 1;
     post_event.ev_type = UCC_EVENT_COLLECTIVE_POST; post_event.ev_context = NULL; post_event.ev_context_size = 0; post_event.req = &ct->super;
     ucc_ee_set_event_internal(ee, &post_event, &ee->event_out_queue);

@@ -47,9 +47,11 @@ for nbytes in (4096, 65536, 1 << 20, 16 << 20, 128 << 20):
             e0.record(stream)
             for r in reqs:
                 r.post_on_stream(stream, wait_posted=False)
-            e1.record(stream)
             for r in reqs:
                 r.wait(); r.finalize()
+            # large messages enter the streams from progress (rendezvous: the push after the receiver published its buffer, the
+            # receiver's wait kernel after the push was launched), so the closing event is recorded after the host-side waits
+            e1.record(stream)
             torch.cuda.synchronize()
         us = e0.elapsed_time(e1) * 1e3 / ITERS
         ok = bool((buf == 1.0).all()) if rank == 1 else True
