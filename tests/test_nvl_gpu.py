@@ -500,7 +500,8 @@ def test_active_set_p2p(count, thresh):
     P2P_RNDV_THRESH=64K, through the rendezvous kernels (the sender stores into the receiver's buffer)"""
     need_cuda()
     n = 4
-    with UccJob(n, env=dict(ENV, UCC_TL_NVL_P2P_RNDV_THRESH=thresh)) as j:
+    # (ZCOPY is set explicitly: module-scoped fixtures of this file keep their own environment alive while other tests run)
+    with UccJob(n, env=dict(ENV, UCC_TL_NVL_P2P_RNDV_THRESH=thresh, UCC_TL_NVL_ZCOPY="y")) as j:
         team = j.create_team()
         pairs = [(0, 1), (3, 1), (2, 0), (1, 3)]
         srcs = [gen("float32", count, 10 + i) for i in range(len(pairs))]
