@@ -13,7 +13,7 @@ C.CDLL(os.path.join(ROOT, "ucc_b200", "lib", "libucc.so"), mode=C.RTLD_GLOBAL)
 nvl = C.CDLL(os.path.join(ROOT, "ucc_b200", "lib", "ucc", "libucc_tl_nvl.so"))
 nvl.nvl_launch_self_copy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p]
 nvl.nvl_launch_self_copy_bulk.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
-n = 1 << 30
+n = 1 << 28   # 256 MB: twice the L2, keeps the ncu save/restore passes short
 src = torch.ones(n // 4, device="cuda"); dst = torch.zeros(n // 4, device="cuda")
 torch.cuda.synchronize()
 for _ in range(3):
