@@ -335,7 +335,7 @@ ucc_tl_iface_t ucc_tl_shm = {
     .tl_lib_config = {"TL_SHM lib", "TL_SHM_", tl_shm_lib_config_table, sizeof(ucc_tl_shm_lib_config_t), {NULL, NULL}},
     .tl_context_config = {"TL_SHM context", "TL_SHM_", tl_shm_context_config_table, sizeof(ucc_tl_shm_context_config_t), {NULL, NULL}},
     .lib = {shm_lib_init, shm_lib_finalize, shm_lib_get_attr, shm_lib_get_properties},
-    .context = {shm_ctx_create, NULL, shm_ctx_destroy, shm_ctx_get_attr, NULL, NULL, NULL},
+    .context = {shm_ctx_create, NULL, shm_ctx_destroy, shm_ctx_get_attr, ucc_tl_shm_mem_map, ucc_tl_shm_mem_unmap, ucc_tl_shm_memh_pack},
     .team = {shm_team_create_post, shm_team_create_test, shm_team_destroy, shm_team_get_scores},
     .coll = {shm_coll_init},
     .scoll = {shm_service_allreduce, shm_service_allgather, shm_service_bcast, shm_service_update_id},

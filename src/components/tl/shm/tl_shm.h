@@ -128,6 +128,15 @@ ucc_status_t ucc_tl_shm_recv_nb(ucc_tl_shm_team_t *team, ucc_rank_t src, uint64_
 void         ucc_tl_shm_req_free(ucc_tl_shm_context_t *ctx, shm_req_t *req);
 int          ucc_tl_shm_can_get(ucc_tl_shm_team_t *team, ucc_rank_t rank); /* direct (one-sided) reads from that rank's memory possible? */
 ucc_status_t ucc_tl_shm_get(ucc_tl_shm_team_t *team, ucc_rank_t rank, void *dst, ucc_memory_type_t dmt, uint64_t remote_addr, size_t len);
+int          ucc_tl_shm_can_put(ucc_tl_shm_team_t *team, ucc_rank_t rank); /* direct writes into that rank's host memory possible? */
+ucc_status_t ucc_tl_shm_put(ucc_tl_shm_team_t *team, ucc_rank_t rank, const void *src, ucc_memory_type_t smt, uint64_t remote_addr, size_t len);
+
+/* tl/shm part of a ucc_mem_map() handle (tl_shm_memh.c) */
+#define UCC_TL_SHM_MEMH_MAGIC 0x53484d4d454d4831ull /* "SHMMEMH1" */
+typedef struct shm_memh { uint64_t magic, host_hash, addr, len; int32_t pid, imported, reachable, pad; } shm_memh_t;
+ucc_status_t ucc_tl_shm_mem_map(const ucc_base_context_t *ctx, ucc_mem_map_mode_t mode, void *memh, void *tl_h);
+ucc_status_t ucc_tl_shm_mem_unmap(const ucc_base_context_t *ctx, ucc_mem_map_mode_t mode, void *tl_h);
+ucc_status_t ucc_tl_shm_memh_pack(const ucc_base_context_t *ctx, ucc_mem_map_mode_t mode, void *tl_h, void **pack_buffer);
 ucc_status_t ucc_tl_shm_progress(void *ctx); /* registered with the core context */
 
 extern ucc_tl_iface_t ucc_tl_shm;

@@ -748,6 +748,39 @@ static ucc_status_t a2a_onesided(ucc_tl_shm_task_t *t, int is_v)
     for (ucc_rank_t p = 0; p < N; p++) if (p != r && !ucc_tl_shm_can_get(t->team, ucc_ep_map_eval(t->vmap, p))) return UCC_ERR_NOT_SUPPORTED;
     CHK(shm_task_scratch(t, (size_t)N * 18, UCC_MEMORY_TYPE_HOST, &sv));
     out = (uint64_t *)sv; in = out + N; tok = (char *)(in + N);
+    /* registered destinations (ucc_mem_map handles of every member, UCC_COLL_ARGS_FLAG_DST_MEMH_GLOBAL): PUT variant, the shape of
+     * the reference's alltoall_onesided.c - every rank writes its blocks straight into the members' destination buffers, whose
+     * addresses follow from the handles (same offset inside the registered segment on every member), then tells each peer "my
+     * block is in".  One message round instead of two.  One-sided contract: a destination may be written as soon as ANY member
+     * has entered the collective - the application orders that (e.g. with a barrier), as with the reference. */
+    if (!is_v && (a->mask & UCC_COLL_ARGS_FIELD_MEM_MAP_DST_MEMH) && (a->flags & UCC_COLL_ARGS_FLAG_DST_MEMH_GLOBAL) && a->dst_memh.global_memh &&
+        N == UCC_TL_TEAM_SIZE(t->team)) {
+        const ucc_base_context_t *bctx = t->team->super.super.context;
+        ucc_mem_map_mem_h *gl = a->dst_memh.global_memh;
+        shm_memh_t *mine = (shm_memh_t *)ucc_mem_map_tl_handle(gl[r], bctx);
+        size_t blk = DCNT(0), off = 0; int ok = mine && mine->magic == UCC_TL_SHM_MEMH_MAGIC && (uint64_t)(uintptr_t)dst >= mine->addr && (uint64_t)(uintptr_t)dst + blk * N <= mine->addr + mine->len;
+        if (ok) off = (size_t)((uint64_t)(uintptr_t)dst - mine->addr);
+        for (ucc_rank_t p = 0; p < N && ok; p++) {
+            shm_memh_t *h = (shm_memh_t *)ucc_mem_map_tl_handle(gl[p], bctx);
+            if (!h || h->magic != UCC_TL_SHM_MEMH_MAGIC || (p != r && !h->reachable) || off + blk * N > h->len || (p != r && !ucc_tl_shm_can_put(t->team, ucc_ep_map_eval(t->vmap, p)))) ok = 0;
+        }
+        if (ok) {
+            tl_debug(UCC_TL_TEAM_LIB(t->team), "alltoall onesided: put into the members' registered destinations (offset %zu in the segment)", off);
+            for (ucc_rank_t s = 1; s < N; s++) {
+                ucc_rank_t p = (r + s) % N;
+                shm_memh_t *h = (shm_memh_t *)ucc_mem_map_tl_handle(gl[p], bctx);
+                CHK(shm_prog_put(t, p, src + SOFF(p), h->addr + off + (size_t)r * blk, blk, smt));
+            }
+            CHK(shm_prog_copy(t, dst + DOFF(r), src + SOFF(r), blk, dmt, smt));
+            for (ucc_rank_t p = 0; p < N; p++) {
+                if (p == r) continue;
+                tok[p] = 1;
+                CHK(shm_prog_send(t, p, &tok[p], 1, UCC_MEMORY_TYPE_HOST, 2)); CHK(shm_prog_recv(t, p, &tok[N + p], 1, UCC_MEMORY_TYPE_HOST, 2));
+            }
+            CHK(shm_prog_wait(t));
+            return UCC_OK;
+        }
+    }
     for (ucc_rank_t p = 0; p < N; p++) {
         if (p == r) continue;
         out[p] = (uint64_t)(uintptr_t)(src + SOFF(p)); tok[p] = 1;

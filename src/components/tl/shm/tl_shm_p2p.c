@@ -29,6 +29,17 @@ static int cma_read(int pid, void *local, const void *remote, size_t len)
     }
     return 0;
 }
+static int cma_write(int pid, const void *local, void *remote, size_t len)
+{
+    size_t done = 0;
+    while (done < len) {
+        struct iovec l = {(char *)(uintptr_t)local + done, len - done}, r = {(char *)remote + done, len - done};
+        ssize_t n = process_vm_writev((pid_t)pid, &l, 1, &r, 1, 0);
+        if (n <= 0) return -1;
+        done += (size_t)n;
+    }
+    return 0;
+}
 /* payload of a rendezvous: the source lives in this process (plain copy) or in a peer process (CMA, host memory only) */
 static void rndv_fetch(ucc_tl_shm_context_t *ctx, ucc_tl_shm_ep_t *ep, void *dst, ucc_memory_type_t dmt, const void *src, ucc_memory_type_t smt, size_t len)
 {
@@ -145,6 +156,20 @@ ucc_status_t ucc_tl_shm_get(ucc_tl_shm_team_t *team, ucc_rank_t rank, void *dst,
     UCC_CHECK_RET(ucc_tl_shm_get_ep(team, rank, &ep));
     if (!ep->same_process && !ep->cma_ok) return UCC_ERR_NOT_SUPPORTED;
     rndv_fetch(SHM_CTX(team), ep, dst, dmt, (const void *)(uintptr_t)remote_addr, UCC_MEMORY_TYPE_HOST, len);
+    return UCC_OK;
+}
+
+/* one-sided write into a peer's HOST memory (registered destination of a put-based collective): pointer inside one process,
+ * process_vm_writev otherwise; the permission is the one probed for reads (ptrace access is symmetric in read / write) */
+int ucc_tl_shm_can_put(ucc_tl_shm_team_t *team, ucc_rank_t rank) { return ucc_tl_shm_can_get(team, rank); }
+ucc_status_t ucc_tl_shm_put(ucc_tl_shm_team_t *team, ucc_rank_t rank, const void *src, ucc_memory_type_t smt, uint64_t remote_addr, size_t len)
+{
+    ucc_tl_shm_ep_t *ep;
+    UCC_CHECK_RET(ucc_tl_shm_get_ep(team, rank, &ep));
+    if (!len) return UCC_OK;
+    if (ep->same_process) { shm_copy((void *)(uintptr_t)remote_addr, src, len, UCC_MEMORY_TYPE_HOST, smt); return UCC_OK; }
+    if (!ep->cma_ok || smt != UCC_MEMORY_TYPE_HOST) return UCC_ERR_NOT_SUPPORTED;
+    if (cma_write(ep->addr.pid, src, (void *)(uintptr_t)remote_addr, len)) { tl_error(SHM_CTX(team)->super.super.lib, "process_vm_writev to pid %d failed: %m", ep->addr.pid); return UCC_ERR_NO_MESSAGE; }
     return UCC_OK;
 }
 

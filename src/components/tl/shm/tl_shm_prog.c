@@ -41,6 +41,13 @@ ucc_status_t shm_prog_get_off(ucc_tl_shm_task_t *t, ucc_rank_t peer, void *dst, 
 }
 ucc_status_t shm_prog_get(ucc_tl_shm_task_t *t, ucc_rank_t peer, void *dst, const uint64_t *remote_addr_slot, size_t len, ucc_memory_type_t mt)
 { return shm_prog_get_off(t, peer, dst, remote_addr_slot, 0, len, mt); }
+ucc_status_t shm_prog_put(ucc_tl_shm_task_t *t, ucc_rank_t peer, const void *src, uint64_t remote_addr, size_t len, ucc_memory_type_t smt)
+{
+    shm_op_t op; memset(&op, 0, sizeof(op));
+    if (!len) return UCC_OK;
+    op.type = SHM_OP_PUT; op.peer = peer; op.dst = (void *)(uintptr_t)src; op.src2 = (void *)(uintptr_t)remote_addr; op.len = len; op.mt = smt;
+    return op_push(t, &op);
+}
 ucc_status_t shm_task_scratch(ucc_tl_shm_task_t *t, size_t len, ucc_memory_type_t mt, void **ptr)
 {
     ucc_status_t st;
@@ -144,6 +151,11 @@ void ucc_tl_shm_task_progress(ucc_coll_task_t *ct)
         }
         case SHM_OP_GET:
             st = ucc_tl_shm_get(team, ucc_ep_map_eval(t->vmap, op->peer), op->dst, op->mt, *(const uint64_t *)op->src1 + (uint64_t)(uintptr_t)op->src2, op->len);
+            if (st != UCC_OK) { ct->status = st; return; }
+            t->pc++;
+            break;
+        case SHM_OP_PUT:
+            st = ucc_tl_shm_put(team, ucc_ep_map_eval(t->vmap, op->peer), op->dst, op->mt, (uint64_t)(uintptr_t)op->src2, op->len);
             if (st != UCC_OK) { ct->status = st; return; }
             t->pc++;
             break;

@@ -8,7 +8,8 @@
 #include "tl_shm.h"
 
 typedef enum { SHM_OP_SEND, SHM_OP_RECV, SHM_OP_WAIT, SHM_OP_REDUCE, SHM_OP_COPY,
-               SHM_OP_GET /* one-sided read of `len` bytes from address *(uint64_t *)src1 in `peer` (same process: pointer, other process: CMA) into dst */ } shm_op_type_t;
+               SHM_OP_GET /* one-sided read of `len` bytes from address *(uint64_t *)src1 in `peer` (same process: pointer, other process: CMA) into dst */,
+               SHM_OP_PUT /* one-sided write of `len` bytes at dst (local) to the address src2 in `peer`'s registered memory */ } shm_op_type_t;
 
 typedef struct shm_op {
     uint8_t           type;
@@ -55,6 +56,8 @@ ucc_status_t shm_prog_wait(ucc_tl_shm_task_t *t);
 /* dst <- len bytes at the remote address that will be stored in *remote_addr_slot by the time the step runs */
 ucc_status_t shm_prog_get(ucc_tl_shm_task_t *t, ucc_rank_t peer, void *dst, const uint64_t *remote_addr_slot, size_t len, ucc_memory_type_t mt);
 ucc_status_t shm_prog_get_off(ucc_tl_shm_task_t *t, ucc_rank_t peer, void *dst, const uint64_t *remote_addr_slot, size_t off, size_t len, ucc_memory_type_t mt);
+/* len bytes at `src` -> address `remote_addr` inside peer's host memory (known at build time: registered buffers) */
+ucc_status_t shm_prog_put(ucc_tl_shm_task_t *t, ucc_rank_t peer, const void *src, uint64_t remote_addr, size_t len, ucc_memory_type_t smt);
 ucc_status_t shm_prog_reduce(ucc_tl_shm_task_t *t, void *dst, const void *src1, const void *src2, size_t count, ucc_memory_type_t mt, int with_alpha);
 ucc_status_t shm_prog_copy(ucc_tl_shm_task_t *t, void *dst, const void *src, size_t len, ucc_memory_type_t dmt, ucc_memory_type_t smt);
 ucc_status_t shm_task_scratch(ucc_tl_shm_task_t *t, size_t len, ucc_memory_type_t mt, void **ptr);

@@ -42,6 +42,8 @@ def main():
     # allgather + alltoall + bcast + reduce_scatter: small (staged kernels) and large (zero-copy kernels on CUDA)
     for blk in (1000, 300000):
         ok &= other_colls(comm, rank, world, dev, use_cuda, blk)
+    if os.environ.get("DW_MEMH") == "1":
+        ok &= registered_alltoall(comm, rank, world, dev)
     if not use_cuda:   # (validated on host memory; on GPUs the WORLD team below is what the 2/4/8-GPU sessions exercised)
         ok &= team_kinds(rank, world, dev, use_cuda)
     if use_cuda and os.environ.get("DW_ASYM") == "1":
@@ -91,6 +93,31 @@ def asymmetric_root(comm, rank, world, dev):
     if not torch.equal(dst.cpu(), host_src[rank * blk:(rank + 1) * blk]):
         print(f"rank {rank}: asymmetric scatter mismatch", flush=True)
         ok = False
+    return ok
+
+
+def registered_alltoall(comm, rank, world, dev):
+    """Communicator.register (ucc_mem_map export + OOB exchange + import) and an alltoall whose destination is part of the
+    registered segment: with UCC_TL_SHM_TUNE=alltoall:@onesided the blocks are written straight into the peers' memory
+    (process_vm_writev between processes) - no address exchange."""
+    blk, pad = 5000, 128
+    seg = torch.full((pad + blk * world + 7,), -1, dtype=torch.int32, device=dev)
+    h = comm.register(seg)
+    ok = True
+    for it in range(3):
+        g = torch.Generator().manual_seed(77 + it)
+        alls = [torch.randint(0, 1 << 30, (blk * world,), generator=g, dtype=torch.int32) for _ in range(world)]
+        seg.fill_(-1)
+        comm.barrier()                                      # one-sided contract: every destination is ready before anybody writes
+        dst = seg[pad:pad + blk * world]
+        req = comm.coll_init("alltoall", alls[rank].to(dev), dst, dst_memh=h)
+        req.post(); req.wait(); req.finalize()
+        exp = torch.cat([alls[p][rank * blk:(rank + 1) * blk] for p in range(world)])
+        if not torch.equal(dst.cpu(), exp) or not bool((seg[:pad] == -1).all()) or not bool((seg[pad + blk * world:] == -1).all()):
+            print(f"rank {rank}: registered alltoall mismatch (iteration {it})", flush=True)
+            ok = False
+        comm.barrier()
+    h.close()
     return ok
 
 

@@ -80,3 +80,14 @@ def test_cl_hier_multiprocess(n, ppn, tune):
     out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
     assert "UCC_TEST_DIST_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
     assert "CL_HIER" in out.stdout + out.stderr      # the hierarchical CL really took collectives
+
+
+def test_torchrun_host_registered_alltoall_cma():
+    """Communicator.register + put-based one-sided alltoall between processes (tl/shm mem_map, process_vm_writev)"""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=3", "--master-addr", "127.0.0.1",
+           "--master-port", "29613", os.path.join(ROOT, "tests", "dist_worker.py"), "cpu"]
+    env = dict(os.environ, PYTHONPATH=ROOT, CUDA_VISIBLE_DEVICES="", UCC_TL_SHM_TUNE="alltoall:@onesided", UCC_TL_SHM_CMA="y", DW_MEMH="1",
+               UCC_TL_SHM_LOG_LEVEL="debug")
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert "DIST_WORKER_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
+    assert "put into the members' registered destinations" in out.stdout + out.stderr   # (lines of the three processes interleave: no counting)

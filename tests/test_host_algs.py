@@ -205,3 +205,68 @@ def test_allgatherv_knomial_shuffled_displacements(n):
         for r in range(n):
             for p in range(n):
                 assert np.array_equal(dst[r][displs[p]:displs[p] + counts[p]], src[p]), (n, r, p)
+
+
+def _mem_map_fns():
+    import ctypes as C
+    U.lib.ucc_mem_map.argtypes = [U.handle, C.c_int, C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_void_p)]
+    U.lib.ucc_mem_map.restype = C.c_int
+    U.lib.ucc_mem_unmap.argtypes = [C.POINTER(C.c_void_p)]
+    U.lib.ucc_mem_unmap.restype = C.c_int
+
+
+@pytest.mark.parametrize("n", [2, 4, 7])
+def test_alltoall_onesided_registered_destinations(n, capfd):
+    """ucc_mem_map on HOST buffers (tl/shm mem_map / memh_pack, the role of reference tl_ucp_context.c:506-577) + alltoall `onesided`
+    with UCC_COLL_ARGS_FLAG_DST_MEMH_GLOBAL: the blocks are PUT straight into the members' registered destinations (the shape of
+    reference alltoall_onesided.c), at the same offset inside every member's segment; without the handles the same algorithm takes
+    the get-based variant.  The trace shows which one ran (the put variant sends 1-byte tokens only, no 8-byte addresses)."""
+    import ctypes as C
+    _mem_map_fns()
+    count, pad = 257, 64
+    with UccJob(n, env={"UCC_TLS": "shm,self", "UCC_TL_SHM_TUNE": "alltoall:@onesided:inf", "UCC_TL_SHM_LOG_LEVEL": "trace"}) as j:
+        team = j.create_team(range(n))
+        segs = [np.zeros(pad + count * n + 5, np.int32) for _ in range(n)]     # registered segment; the collective's dst starts at `pad`
+        blobs, keep = [], []
+        for r in range(n):
+            seg = U.ucc_mem_map_t(segs[r].ctypes.data, segs[r].nbytes)
+            params = U.ucc_mem_map_params_t()
+            params.segments, params.n_segments = C.pointer(seg), 1
+            memh, size = C.c_void_p(), C.c_size_t()
+            assert U.lib.ucc_mem_map(j.procs[r].ctx, 0, C.byref(params), C.byref(size), C.byref(memh)) == U.UCC_OK
+            blob = C.string_at(memh.value, size.value)
+            assert b"shm" in blob                                             # the host TL contributed a record
+            blobs.append(blob); keep.append(memh)
+        glob = []
+        for r in range(n):
+            arr = (C.c_void_p * n)()
+            for p in range(n):
+                b = C.create_string_buffer(blobs[p], len(blobs[p]))
+                keep.append(b)
+                h = C.c_void_p(C.addressof(b))
+                assert U.lib.ucc_mem_map(j.procs[r].ctx, 1, None, None, C.byref(h)) == U.UCC_OK
+                arr[p] = h.value
+            glob.append(arr)
+        rng = np.random.default_rng(n)
+        for registered in (True, False, True):
+            src = [rng.integers(0, 1 << 30, count * n).astype(np.int32) for _ in range(n)]
+            for s in segs:
+                s[:] = -1
+            args = []
+            for r in range(n):
+                a = coll_args("alltoall", src[r], segs[r][pad:pad + count * n], dt="int32")
+                if registered:
+                    a.mask |= U.UCC_COLL_ARGS_FIELD_MEM_MAP_DST_MEMH | U.UCC_COLL_ARGS_FIELD_FLAGS
+                    a.flags |= U.UCC_COLL_ARGS_FLAG_DST_MEMH_GLOBAL
+                    a.dst_memh.global_memh = C.cast(glob[r], C.POINTER(C.c_void_p))
+                args.append(a)
+            capfd.readouterr()
+            run(team, args)
+            log = capfd.readouterr()
+            log = log.out + log.err
+            for r in range(n):
+                assert np.array_equal(segs[r][pad:pad + count * n], np.concatenate([src[p][r * count:(r + 1) * count] for p in range(n)])), (registered, r)
+                assert np.all(segs[r][:pad] == -1) and np.all(segs[r][pad + count * n:] == -1)
+            assert ("len 8" in log) == (not registered), "the put variant must not exchange addresses"
+        for m in keep[:n]:
+            assert U.lib.ucc_mem_unmap(C.byref(m)) == U.UCC_OK

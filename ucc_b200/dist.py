@@ -54,6 +54,15 @@ class _TorchOob:
         self._test = U.OOB_REQ_FN(lambda req: U.UCC_OK)
         self._free = U.OOB_REQ_FN(lambda req: U.UCC_OK)
 
+    def allgather_bytes(self, blob):
+        """every member's `blob` (same length everywhere), through the same OOB allgather the library uses"""
+        n = len(blob)
+        src = C.create_string_buffer(bytes(blob), n)
+        recv = C.create_string_buffer(n * self.size)
+        req = (C.c_void_p * 1)()
+        U.check(self._ag(C.cast(src, C.c_void_p).value, C.cast(recv, C.c_void_p).value, n, None, req), "oob allgather")
+        return [recv.raw[r * n:(r + 1) * n] for r in range(self.size)]
+
     def struct(self):
         o = U.ucc_oob_coll_t()
         o.allgather, o.req_test, o.req_free = self._ag, self._test, self._free
@@ -82,6 +91,21 @@ class _StoreOob(_TorchOob):
         self._ag = U.OOB_ALLGATHER_FN(allgather)
         self._test = U.OOB_REQ_FN(lambda req: U.UCC_OK)
         self._free = U.OOB_REQ_FN(lambda req: U.UCC_OK)
+
+
+class MemHandles:
+    """A registered segment: the local ucc_mem_map(EXPORT) handle plus one imported handle per team member (what collectives take
+    as `global_memh`).  Keep it alive while requests that use it exist; `close()` unmaps everything."""
+
+    def __init__(self, comm, tensor, local, imported, blobs):
+        self.comm, self.tensor, self._local, self._imported, self._blobs = comm, tensor, local, imported, blobs
+        self.array = (C.c_void_p * len(imported))(*[h.value for h in imported])
+
+    def close(self):
+        for h in self._imported:
+            U.lib.ucc_mem_unmap(C.byref(h))
+        U.lib.ucc_mem_unmap(C.byref(self._local))
+        self._imported, self._blobs = [], []
 
 
 class Request:
@@ -309,12 +333,48 @@ class Communicator:
                          count_src=src.numel() if src is not None else 0, count_dst=dst.numel() if dst is not None else 0,
                          mem_type=mem_type_of(ref), **kw)
 
+    def register(self, tensor):
+        """ucc_mem_map: register the memory of `tensor` (a whole segment; collectives may later use any part of it, at the same
+        offset on every member) with every TL that supports registration - tl/nvl for CUDA memory (zero-copy kernels without
+        the per-post buffer exchange), tl/shm for host memory (put-based one-sided alltoall) - exchange the relocatable handles
+        over the team's OOB channel and import every member's.  Collective on the team.  Returns MemHandles for
+        `coll_init(..., src_memh= / dst_memh=)`."""
+        U.lib.ucc_mem_map.argtypes = [U.handle, C.c_int, C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_void_p)]
+        U.lib.ucc_mem_map.restype = C.c_int
+        U.lib.ucc_mem_unmap.argtypes = [C.POINTER(C.c_void_p)]
+        U.lib.ucc_mem_unmap.restype = C.c_int
+        seg = U.ucc_mem_map_t(tensor.data_ptr(), tensor.numel() * tensor.element_size())
+        params = U.ucc_mem_map_params_t()
+        params.segments, params.n_segments = C.pointer(seg), 1
+        local, size = C.c_void_p(), C.c_size_t()
+        U.check(U.lib.ucc_mem_map(self.ctx, 0, C.byref(params), C.byref(size), C.byref(local)), "ucc_mem_map export")
+        mine = C.string_at(local.value, size.value)
+        sizes = [int.from_bytes(b, "little") for b in self.oob.allgather_bytes(len(mine).to_bytes(8, "little"))]
+        width = max(sizes)
+        blobs = [C.create_string_buffer(b[:sizes[r]], sizes[r]) for r, b in enumerate(self.oob.allgather_bytes(mine.ljust(width, b"\0")))]
+        imported = []
+        for b in blobs:   # the imported handle lives inside the received buffer (kept in MemHandles)
+            h = C.c_void_p(C.addressof(b))
+            U.check(U.lib.ucc_mem_map(self.ctx, 1, None, None, C.byref(h)), "ucc_mem_map import")
+            imported.append(h)
+        return MemHandles(self, tensor, local, imported, blobs)
+
     def allreduce_init(self, src, dst, op="sum", persistent=False):
         inplace = src is None or src.data_ptr() == dst.data_ptr()
         return self.init(self._args("allreduce", None if inplace else src, dst, op=op, inplace=inplace, persistent=persistent), (src, dst))
 
-    def coll_init(self, coll, src=None, dst=None, **kw):
-        return self.init(self._args(coll, src, dst, **kw), (src, dst))
+    def coll_init(self, coll, src=None, dst=None, src_memh=None, dst_memh=None, **kw):
+        """`src_memh` / `dst_memh`: MemHandles from register() - the buffers are parts of registered segments"""
+        a = self._args(coll, src, dst, **kw)
+        if src_memh is not None:
+            a.mask |= U.UCC_COLL_ARGS_FIELD_MEM_MAP_SRC_MEMH | U.UCC_COLL_ARGS_FIELD_FLAGS
+            a.flags |= U.UCC_COLL_ARGS_FLAG_SRC_MEMH_GLOBAL
+            a.src_memh.global_memh = C.cast(src_memh.array, C.POINTER(C.c_void_p))
+        if dst_memh is not None:
+            a.mask |= U.UCC_COLL_ARGS_FIELD_MEM_MAP_DST_MEMH | U.UCC_COLL_ARGS_FIELD_FLAGS
+            a.flags |= U.UCC_COLL_ARGS_FLAG_DST_MEMH_GLOBAL
+            a.dst_memh.global_memh = C.cast(dst_memh.array, C.POINTER(C.c_void_p))
+        return self.init(a, (src, dst, src_memh, dst_memh))
 
     def run(self, req, stream=None):
         """Convenience: post, wait (host), finalize."""
