@@ -188,3 +188,32 @@ def test_memunits_parser():
         assert lib.ucc_str_to_memunits(s.encode(), C.byref(v)) == 0, s
         assert v.value == exp, (s, v.value)
     assert lib.ucc_str_to_memunits(b"12q", C.byref(v)) != 0
+
+
+def test_tl_nvl_default_selection_strings_parse():
+    """The built-in selection strings of tl/nvl (tl_nvl_coll.c get_scores), incl. the NVLS branch that only real multi-GPU NVSwitch
+    teams take: every token must parse and every algorithm name must resolve through the TL's own alg_id_to_init - a typo there
+    would make team creation fail on exactly the machines the CPU suite cannot emulate."""
+    import os
+    path = os.path.join(os.path.dirname(U.LIB_PATH), "ucc", "libucc_tl_nvl.so")
+    if not os.path.exists(path):
+        pytest.skip("tl/nvl plugin not built")
+    try:
+        nvl = C.CDLL(path)
+    except OSError as e:
+        pytest.skip(f"tl/nvl plugin not loadable here: {e}")
+    alg_fn = C.cast(nvl.ucc_tl_nvl_alg_id_to_init, I.ALG_FN)
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "src", "components", "tl", "nvl", "tl_nvl_coll.c")).read()
+    import re
+    fmts = re.findall(r'snprintf\(sel[^;]*?"([^"]*)"', src)
+    assert len(fmts) >= 3, fmts
+    for f in fmts:
+        s = f.replace("%s-inf:@%s", "512M-inf:@nvls_pipe").replace("0-%s", "0-1048577").replace("%s-inf", "512M-inf").lstrip("#")
+        assert "%" not in s, (f, s)
+        st, p = from_str(s, size=8, alg_fn=alg_fn)
+        assert st == 0, (s, st)
+        lib.ucc_coll_score_free(p)
+    for alg in ("nvls", "nvls_pipe", "twoshot", "oneshot", "ring", "rhd"):
+        st, p = from_str(f"allreduce:cuda:512M-inf:@{alg}", size=8, alg_fn=alg_fn)
+        assert st == 0, alg
+        lib.ucc_coll_score_free(p)
