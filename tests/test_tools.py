@@ -122,7 +122,8 @@ def test_reference_arm_builds_from_unmodified_reference_sources(tmp_path):
     ref = os.environ.get("REFERENCE_DIR", "/root/reference")
     if not os.path.isdir(os.path.join(ref, "src", "components", "tl", "cuda", "kernels")) or not os.path.exists("/usr/local/cuda/bin/nvcc"):
         pytest.skip("reference tree or nvcc not available")
-    r = subprocess.run(["bash", os.path.join(ROOT, "baseline", "ref_arm", "build.sh")], capture_output=True, text=True, timeout=900)
+    env = {k: v for k, v in os.environ.items() if k != "LD_PRELOAD"}   # (tools/run_asan.sh preloads libasan; nvcc does not survive that)
+    r = subprocess.run(["bash", os.path.join(ROOT, "baseline", "ref_arm", "build.sh")], capture_output=True, text=True, timeout=900, env=env)
     assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
     out = os.path.join(ROOT, "baseline", "_ref")
     assert os.path.exists(os.path.join(out, "libref_tlcuda.so"))
