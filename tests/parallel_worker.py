@@ -135,6 +135,34 @@ def main():
         prev = ring_pass(kv, comm=comm)
         ok &= bool((prev == float((rank - 1) % world)).all())
 
+    stage("pipeline (GPipe / 1F1B over send / recv)")
+    # ---- pipeline parallel: every rank owns two layers of a 2 * world layer MLP; loss and gradients must equal the unsplit model's
+    from ucc_b200.parallel import PipelineStage
+    torch.manual_seed(7)
+    width, n_micro, mb = 24, 5, 6
+    layers = [torch.nn.Sequential(torch.nn.Linear(width, width), torch.nn.Tanh()) for _ in range(2 * world)]
+    full = torch.nn.Sequential(*layers).to(dev)
+    g = torch.Generator().manual_seed(8)
+    xs = [torch.randn(mb, width, generator=g).to(dev) for _ in range(n_micro)]
+    ys = [torch.randn(mb, width, generator=g).to(dev) for _ in range(n_micro)]
+    lf = torch.nn.functional.mse_loss
+    ref_loss = sum(lf(full(xs[i]), ys[i]) for i in range(n_micro)) / n_micro
+    ref_loss.backward()
+    ref_grads = [p.grad.clone() for lyr in layers[2 * rank:2 * rank + 2] for p in lyr.parameters()]
+    mine = torch.nn.Sequential(*layers[2 * rank:2 * rank + 2])
+    for sched in ("gpipe", "1f1b"):
+        for p in mine.parameters():
+            p.grad = None
+        pp = PipelineStage(mine, act_shape=(mb, width), comm=comm, device=dev)
+        loss = pp.run(n_micro, inputs=xs, targets=ys, loss_fn=lf, schedule=sched)
+        if rank == world - 1 and not torch.allclose(loss, ref_loss.detach(), rtol=1e-5, atol=1e-6):
+            print(f"rank {rank}: pipeline {sched} loss {loss.item()} != {ref_loss.item()}", flush=True)
+            ok = False
+        for p, rg in zip(mine.parameters(), ref_grads):
+            if p.grad is None or not torch.allclose(p.grad, rg, rtol=1e-4, atol=1e-6):
+                print(f"rank {rank}: pipeline {sched} gradient mismatch", flush=True)
+                ok = False
+
     stage("done")
     flag = torch.tensor([1 if ok else 0])
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
