@@ -131,9 +131,25 @@ def main():
         ok = False
     stage("ring pass (send / recv)")
     kv = torch.full((5, 7), float(rank), device=dev)
-    if world % 2 == 0 or world == 1:
-        prev = ring_pass(kv, comm=comm)
-        ok &= bool((prev == float((rank - 1) % world)).all())
+    prev = ring_pass(kv, comm=comm)
+    ok &= bool((prev == float((rank - 1) % world)).all())
+
+    stage("ring attention (context parallel)")
+    # ---- ring attention: every rank's rows of softmax(QK^T) V over the sharded sequence == full attention on the gathered sequence
+    from ucc_b200.parallel import ring_attention
+    Sb, Hh, Dd = 6, 3, 8
+    g = torch.Generator().manual_seed(11)
+    Q, K, V = (torch.randn(Sb * world, Hh, Dd, generator=g).to(dev) for _ in range(3))
+    sl = slice(rank * Sb, (rank + 1) * Sb)
+    for causal in (False, True):
+        got = ring_attention(Q[sl].contiguous(), K[sl].contiguous(), V[sl].contiguous(), comm=comm, causal=causal)
+        att = torch.einsum("qhd,khd->hqk", Q, K) * Dd ** -0.5
+        if causal:
+            att = att.masked_fill(torch.ones(Sb * world, Sb * world, dtype=torch.bool, device=dev).triu(1), float("-inf"))
+        exp = torch.einsum("hqk,khd->qhd", torch.softmax(att, dim=-1), V)[sl]
+        if not torch.allclose(got, exp, rtol=1e-4, atol=1e-5):
+            print(f"rank {rank}: ring attention mismatch (causal={causal}) max err {(got - exp).abs().max().item()}", flush=True)
+            ok = False
 
     stage("pipeline (GPipe / 1F1B over send / recv)")
     # ---- pipeline parallel: every rank owns two layers of a 2 * world layer MLP; loss and gradients must equal the unsplit model's
