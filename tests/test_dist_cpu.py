@@ -91,3 +91,12 @@ def test_torchrun_host_registered_alltoall_cma():
     out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert "DIST_WORKER_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
     assert "put into the members' registered destinations" in out.stdout + out.stderr   # (lines of the three processes interleave: no counting)
+
+
+def test_example_long_context_pipeline():
+    """examples/long_context_pipeline.py: ring attention + 1F1B pipeline over send / recv, 4 processes on host tensors"""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=4", "--master-addr", "127.0.0.1",
+           "--master-port", "29621", os.path.join(ROOT, "examples", "long_context_pipeline.py")]
+    env = dict(os.environ, PYTHONPATH=ROOT, CUDA_VISIBLE_DEVICES="")
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert "EXAMPLE_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
