@@ -120,6 +120,35 @@ def main():
             print(f"rank {rank}: ZeRO parameter mismatch {n1}", flush=True)
             ok = False
 
+    stage("fsdp (ZeRO-3 units: allgather before forward / backward, reduce_scatter of the gradients)")
+    from ucc_b200.parallel import FullyShardedModule
+    torch.manual_seed(21)
+    blocks = [torch.nn.Sequential(torch.nn.Linear(20, 20), torch.nn.Tanh()) for _ in range(3)]
+    ref_model = torch.nn.Sequential(*[torch.nn.Sequential(torch.nn.Linear(20, 20), torch.nn.Tanh()) for _ in range(3)]).to(dev)
+    ref_model.load_state_dict(torch.nn.Sequential(*blocks).state_dict())
+    units = [FullyShardedModule(b.to(dev), comm=comm) for b in blocks]
+    fsdp = torch.nn.Sequential(*units)
+    opt = torch.optim.SGD([u.shard_param for u in units], lr=0.1)
+    ropt = torch.optim.SGD(ref_model.parameters(), lr=0.1)
+    g = torch.Generator().manual_seed(22)
+    for step in range(3):
+        xb = torch.randn(world, 4, 20, generator=g).to(dev)
+        yb = torch.randn(world, 4, 20, generator=g).to(dev)
+        opt.zero_grad()
+        torch.nn.functional.mse_loss(fsdp(xb[rank]), yb[rank]).backward()
+        opt.step()
+        ropt.zero_grad()
+        torch.nn.functional.mse_loss(ref_model(xb.reshape(-1, 20)), yb.reshape(-1, 20)).backward()   # mean over the global batch
+        ropt.step()
+    for u, rb in zip(units, ref_model):
+        want = torch.cat([p.detach().reshape(-1) for p in rb.parameters()])
+        if not torch.allclose(u.full_parameters(), want, rtol=1e-4, atol=1e-6):
+            print(f"rank {rank}: FSDP parameters differ from the reference after 3 steps", flush=True)
+            ok = False
+        if u._full.untyped_storage().nbytes() != 0:
+            print(f"rank {rank}: FSDP unit kept its full parameters resident", flush=True)
+            ok = False
+
     stage("ulysses")
     # ---- Ulysses all-to-all: [S/N, H, D] -> [S, H/N, D], and one ring-attention hop
     S, H, D = 4 * world, 2 * world, 3

@@ -4,6 +4,6 @@ ring-attention hops (alltoall / neighbour p2p), pipeline stages (GPipe / 1F1B ov
 from .ddp import DistributedDataParallel  # noqa: F401
 from .tensor_parallel import ColumnParallelLinear, RowParallelLinear  # noqa: F401
 from .moe import moe_dispatch, moe_combine  # noqa: F401
-from .zero import ZeroRedundancyTrainer  # noqa: F401
+from .zero import ZeroRedundancyTrainer, FullyShardedModule  # noqa: F401
 from .sequence import ulysses_all_to_all, ring_pass, ring_attention  # noqa: F401
 from .pipeline import PipelineStage  # noqa: F401
