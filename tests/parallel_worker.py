@@ -86,6 +86,31 @@ def main():
         print(f"rank {rank}: ColumnParallelLinear(gather_output) gradient mismatch", flush=True)
         ok = False
 
+    stage("sequence-parallel tensor parallelism (allgather in, reduce_scatter out)")
+    # ---- Megatron-SP MLP: sequence-sharded input -> ColumnParallel(sequence_parallel) -> gelu -> RowParallel(sequence_parallel) ->
+    #      sequence-sharded output; output and input gradient must equal the dense MLP's rows of this rank
+    from ucc_b200.parallel.tensor_parallel import RowParallelLinear
+    torch.manual_seed(300 + rank)
+    sq, hd = 3, 4 * world
+    up = ColumnParallelLinear(d, hd, comm=comm, device=dev, sequence_parallel=True)
+    down = RowParallelLinear(hd, d, comm=comm, device=dev, sequence_parallel=True)
+    with torch.no_grad():
+        ops.broadcast(down.bias.data, 0, comm=comm)
+    xfull = torch.randn(sq * world, d, generator=torch.Generator().manual_seed(13)).to(dev)
+    xs_ = xfull[rank * sq:(rank + 1) * sq].clone().requires_grad_()
+    ys_ = down(torch.nn.functional.gelu(up(xs_)))
+    wgt = torch.arange(sq * world * d, dtype=torch.float32, device=dev).view(sq * world, d) / 100
+    (ys_ * wgt[rank * sq:(rank + 1) * sq]).sum().backward()
+    w1 = torch.empty(world, hd // world, d, device=dev); ops.all_gather_into_tensor(w1, up.weight.data.contiguous(), comm=comm)
+    b1 = torch.empty(world, hd // world, device=dev); ops.all_gather_into_tensor(b1, up.bias.data.contiguous(), comm=comm)
+    w2 = torch.empty(world, d, hd // world, device=dev); ops.all_gather_into_tensor(w2, down.weight.data.contiguous(), comm=comm)
+    xd = xfull.clone().requires_grad_()
+    yd = torch.nn.functional.linear(torch.nn.functional.gelu(torch.nn.functional.linear(xd, w1.reshape(hd, d), b1.reshape(hd))), torch.cat(list(w2), dim=1), down.bias)
+    (yd * wgt).sum().backward()
+    if not torch.allclose(ys_, yd[rank * sq:(rank + 1) * sq], rtol=1e-4, atol=1e-5) or not torch.allclose(xs_.grad, xd.grad[rank * sq:(rank + 1) * sq], rtol=1e-4, atol=1e-5):
+        print(f"rank {rank}: sequence-parallel TP mismatch", flush=True)
+        ok = False
+
     stage("moe")
     # ---- MoE dispatch / combine round trip with skewed routing
     T, H = 50 + 7 * rank, 12
