@@ -217,3 +217,42 @@ def test_tl_nvl_default_selection_strings_parse():
         st, p = from_str(f"allreduce:cuda:512M-inf:@{alg}", size=8, alg_fn=alg_fn)
         assert st == 0, alg
         lib.ucc_coll_score_free(p)
+
+
+def test_merge_random_maps_against_a_pointwise_oracle():
+    """Property test (hypothesis): for random disjoint range lists in two score maps, the merged map is sorted and disjoint and, at
+    every probe point, its winner is the covering range with the highest score (map 1 on ties) and its fallback list holds the
+    other covering range - the boundary-sweep merge (ucc_coll_score.c) against a point-by-point oracle."""
+    from hypothesis import given, settings, strategies as st
+
+    def disjoint(cuts, scores, inits):
+        cuts = sorted(set(cuts))
+        out = []
+        for i in range(0, len(cuts) - 1, 2):                   # every other gap is a range
+            out.append((cuts[i], cuts[i + 1], scores[i % len(scores)], INITS[inits[i % len(inits)]]))
+        return out
+
+    lists = st.lists(st.integers(0, 200), min_size=2, max_size=12)
+    sc = st.lists(st.integers(1, 50), min_size=1, max_size=6)
+
+    @settings(max_examples=150, deadline=None)
+    @given(lists, sc, lists, sc)
+    def check(c1, s1, c2, s2):
+        r1, r2 = disjoint(c1, s1, [0, 1, 2]), disjoint(c2, s2, [3, 4, 5])
+        m = merged(r1, r2)
+        got = ranges(m)
+        lib.ucc_coll_score_free(m)
+        assert all(a < b for a, b, *_ in got)
+        assert all(got[i][1] <= got[i + 1][0] for i in range(len(got) - 1))
+        for x in range(0, 201):
+            cover = [(s_, addr(f), k) for k, rs in enumerate((r1, r2)) for (a, b, s_, f) in rs if a <= x < b]
+            hit = [g for g in got if g[0] <= x < g[1]]
+            assert len(hit) == (1 if cover else 0), (x, cover, got)
+            if cover:
+                best = max(cover, key=lambda c: (c[0], -c[2]))
+                assert hit[0][2] == best[0], (x, cover, hit)
+                if len(cover) == 2 and cover[0][0] != cover[1][0]:
+                    assert hit[0][3] == best[1]
+                    loser = min(cover, key=lambda c: (c[0], -c[2]))
+                    assert (loser[0], loser[1]) in [(f[0], f[1]) for f in hit[0][4]], (x, cover, hit)
+    check()
