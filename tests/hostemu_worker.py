@@ -716,6 +716,89 @@ def p2p_fuzz():
     print("  p2p fuzz ok", flush=True)
 
 
+def coll_fuzz():
+    """random programs on the tl/nvl plugin: for several seeds, 40 collectives of random kind / size / datatype / operator / root on a
+    4-member team and on a 3-member sub-team, up to three of them outstanding at once (posted back to back in the same order on every
+    member, as UCC requires), once with the staged kernels and once with the zero-copy exchange (deferred launches) and a heap so small
+    that large messages take several rounds; every result is checked against numpy."""
+    kinds = ["allreduce", "allgather", "alltoall", "reduce_scatter", "bcast", "reduce", "barrier", "gather", "scatter"]
+    for mode, extra in (("staged", NOZC), ("zcopy", dict(ZC, UCC_TL_NVL_ZCOPY_THRESH="64K"))):
+        with UccJob(4, env=dict(BASE, **extra)) as j:
+            teams = [j.create_team(range(4)), j.create_team([3, 0, 2])]
+            for seed in range(4):
+                rng = np.random.default_rng(500 + seed)
+                window = []
+
+                def retire(k):
+                    while len(window) > k:
+                        q, check, what = window.pop(0)
+                        st = q.wait()
+                        assert st == U.UCC_OK, (mode, seed, what, U.status_str(st))
+                        q.finalize()
+                        check()    # (no device-wide synchronisation here: other collectives are outstanding and a zero-copy one may still need host progress to be launched)
+                for step in range(40):
+                    team = teams[int(rng.integers(0, 2))]
+                    n = len(team.members)
+                    kind = kinds[int(rng.integers(0, len(kinds)))]
+                    blk = int(rng.choice([1, 3, 100, 4097, 30011, 120001]))
+                    if kind not in ("allreduce", "reduce_scatter", "reduce") and blk > 30011:
+                        blk = 30011      # the data-movement kernels stage the whole message in the (here 1 MB) heap; only reductions work in rounds
+                    dt = "float32" if rng.integers(0, 2) else "int32"
+                    npdt = np.dtype(dt)
+                    op = "sum" if rng.integers(0, 3) else "max"
+                    root = int(rng.integers(0, n))
+                    what = (step, kind, n, blk, dt, op, root)
+                    mk = lambda c, sd: Dev(c, npdt, fill=(rnd(c, sd, npdt) if dt == "float32" else (rnd(c, sd, npdt) % 1000)))  # noqa: E731
+                    red = (lambda arrs: np.sum(arrs, 0)) if op == "sum" else (lambda arrs: np.max(arrs, 0))
+                    if kind == "allreduce":
+                        src = [mk(blk, 10 * step + r) for r in range(n)]; dst = [Dev(blk, npdt, fill=0) for _ in range(n)]
+                        args = [ca(kind, src[r], dst[r], dt=dt, op=op) for r in range(n)]
+                        exp = red([x.a.copy() for x in src])
+                        check = lambda dst=dst, exp=exp, what=what: [np.testing.assert_allclose(d.a, exp, rtol=1e-5, err_msg=str(what)) for d in dst]  # noqa: E731
+                    elif kind == "allgather":
+                        src = [mk(blk, 10 * step + r) for r in range(n)]; dst = [Dev(blk * n, npdt, fill=0) for _ in range(n)]
+                        args = [ca(kind, src[r], dst[r], dt=dt) for r in range(n)]
+                        exp = np.concatenate([x.a for x in src])
+                        check = lambda dst=dst, exp=exp, what=what: [np.testing.assert_array_equal(d.a, exp, err_msg=str(what)) for d in dst]  # noqa: E731
+                    elif kind == "alltoall":
+                        src = [mk(blk * n, 10 * step + r) for r in range(n)]; dst = [Dev(blk * n, npdt, fill=0) for _ in range(n)]
+                        args = [ca(kind, src[r], dst[r], dt=dt) for r in range(n)]
+                        check = lambda src=src, dst=dst, n=n, blk=blk, what=what: [np.testing.assert_array_equal(dst[r].a, np.concatenate([src[p].a[r * blk:(r + 1) * blk] for p in range(n)]), err_msg=str(what)) for r in range(n)]  # noqa: E731
+                    elif kind == "reduce_scatter":
+                        src = [mk(blk * n, 10 * step + r) for r in range(n)]; dst = [Dev(blk, npdt, fill=0) for _ in range(n)]
+                        args = [ca(kind, src[r], dst[r], dt=dt, op=op) for r in range(n)]
+                        exp = red([x.a.copy() for x in src])
+                        check = lambda dst=dst, exp=exp, blk=blk, n=n, what=what: [np.testing.assert_allclose(dst[r].a, exp[r * blk:(r + 1) * blk], rtol=1e-5, err_msg=str(what)) for r in range(n)]  # noqa: E731
+                    elif kind == "bcast":
+                        b = [mk(blk, 10 * step + 7) if r == root else Dev(blk, npdt, fill=0) for r in range(n)]
+                        exp = b[root].a.copy()
+                        args = [ca(kind, b[r], None, dt=dt, root=root, count_dst=0) for r in range(n)]
+                        check = lambda b=b, exp=exp, what=what: [np.testing.assert_array_equal(x.a, exp, err_msg=str(what)) for x in b]  # noqa: E731
+                    elif kind == "reduce":
+                        src = [mk(blk, 10 * step + r) for r in range(n)]; out = Dev(blk, npdt, fill=0)
+                        args = [ca(kind, src[r], out if r == root else None, dt=dt, op=op, root=root, count_dst=blk if r == root else 0) for r in range(n)]
+                        exp = red([x.a.copy() for x in src])
+                        check = lambda out=out, exp=exp, what=what: np.testing.assert_allclose(out.a, exp, rtol=1e-5, err_msg=str(what))  # noqa: E731
+                    elif kind == "gather":
+                        src = [mk(blk, 10 * step + r) for r in range(n)]; g = Dev(blk * n, npdt, fill=0)
+                        args = [ca(kind, src[r], g if r == root else None, dt=dt, root=root, count_dst=blk * n if r == root else 0) for r in range(n)]
+                        exp = np.concatenate([x.a for x in src])
+                        check = lambda g=g, exp=exp, what=what: np.testing.assert_array_equal(g.a, exp, err_msg=str(what))  # noqa: E731
+                    elif kind == "scatter":
+                        big = mk(blk * n, 10 * step + 3); outs = [Dev(blk, npdt, fill=0) for _ in range(n)]
+                        args = [ca(kind, big if r == root else None, outs[r], dt=dt, root=root, count_src=blk * n if r == root else 0) for r in range(n)]
+                        check = lambda big=big, outs=outs, blk=blk, n=n, what=what: [np.testing.assert_array_equal(outs[r].a, big.a[r * blk:(r + 1) * blk], err_msg=str(what)) for r in range(n)]  # noqa: E731
+                    else:
+                        args = [coll_args("barrier") for _ in range(n)]
+                        check = lambda: None  # noqa: E731
+                    q = team.coll(args)
+                    q.post()
+                    window.append((q, check, what))
+                    retire(int(rng.integers(0, 3)))
+                retire(0)
+        print(f"  collective fuzz [{mode}] ok", flush=True)
+
+
 SCENARIOS = {
     "defaults": default_selection,
     "allreduce": lambda: [allreduce_suite(a, e) for a, e in (("oneshot", NOZC), ("twoshot", NOZC), ("twoshot", ZC), ("ring", NOZC), ("rhd", NOZC))],
@@ -730,6 +813,7 @@ SCENARIOS = {
     "cross_team": lambda: [cross_team_order(NOZC), cross_team_order(ZC)],
     "p2p": lambda: [p2p_active_set(), int_avg()],
     "p2p_fuzz": p2p_fuzz,
+    "coll_fuzz": coll_fuzz,
     "memh": registered_buffers,
     "hier": hier_on_device_buffers,
     "lanes": lanes,

@@ -21,7 +21,7 @@ def emu_build():
     assert "HOSTEMU_BUILD_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
 
 
-@pytest.mark.parametrize("scenario", ["allreduce", "colls_staged", "colls_zcopy", "colls_push", "colls_ce", "colls_ring", "misc", "triggered", "cross_team", "timeout", "p2p", "p2p_fuzz", "memh", "lanes", "defaults"])
+@pytest.mark.parametrize("scenario", ["allreduce", "colls_staged", "colls_zcopy", "colls_push", "colls_ce", "colls_ring", "misc", "triggered", "cross_team", "timeout", "p2p", "p2p_fuzz", "coll_fuzz", "memh", "lanes", "defaults"])
 def test_tl_nvl_host_emulation(emu_build, scenario):
     env = dict(os.environ, PYTHONPATH=ROOT)
     for k in ("UCC_TL_NVL_TUNE", "UCC_MODULE_DIR", "UCC_TLS"):
