@@ -720,10 +720,12 @@ def p2p_fuzz():
 def coll_fuzz():
     """random programs on the tl/nvl plugin: for several seeds, 40 collectives of random kind / size / datatype / operator / root on a
     4-member team and on a 3-member sub-team, up to three of them outstanding at once (posted back to back in the same order on every
-    member, as UCC requires), once with the staged kernels and once with the zero-copy exchange (deferred launches) and a heap so small
-    that large messages take several rounds; every result is checked against numpy."""
+    member, as UCC requires), with the staged kernels, with the zero-copy exchange (deferred launches), and both again on several lanes
+    (UCC_TL_NVL_SLOTS: consecutive collectives use consecutive heap images), always with a heap so small that large messages take several
+    rounds; every result is checked against numpy."""
     kinds = ["allreduce", "allgather", "alltoall", "reduce_scatter", "bcast", "reduce", "barrier", "gather", "scatter"]
-    for mode, extra in (("staged", NOZC), ("zcopy", dict(ZC, UCC_TL_NVL_ZCOPY_THRESH="64K"))):
+    for mode, extra in (("staged", NOZC), ("zcopy", dict(ZC, UCC_TL_NVL_ZCOPY_THRESH="64K")), ("staged, 4 lanes", dict(NOZC, UCC_TL_NVL_SLOTS="4")),
+                        ("zcopy, 3 lanes", dict(ZC, UCC_TL_NVL_ZCOPY_THRESH="64K", UCC_TL_NVL_SLOTS="3"))):
         with UccJob(4, env=dict(BASE, **extra)) as j:
             teams = [j.create_team(range(4)), j.create_team([3, 0, 2])]
             for seed in range(4):
