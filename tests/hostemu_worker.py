@@ -635,85 +635,88 @@ def p2p_fuzz():
     import time
     n = 4
     rt.cudaStreamCreate.argtypes = [C.POINTER(C.c_void_p)]
-    for thresh in ("64K", "inf"):       # inf: everything through the eager ring, incl. messages larger than the ring (1 MB)
-      with UccJob(n, env=dict(BASE, **dict(ZC, UCC_TL_NVL_P2P_RNDV_THRESH=thresh))) as j:
-          team = j.create_team(range(n))
-          # stream-ordered posts, one stream per (rank, peer, direction): a kernel of the eager ring may wait for its peer, so - exactly as
-          # with NCCL - two operations that must not wait for each other must not share a stream
-          ees = {}
-          for r in range(n):
-              for p_ in range(n):
-                  for kind in ("send", "recv"):
-                      if p_ == r:
-                          continue
-                      s_ = C.c_void_p()
-                      assert rt.cudaStreamCreate(C.byref(s_)) == 0
-                      ep = U.ucc_ee_params_t()
-                      ep.ee_type, ep.ee_context, ep.ee_context_size = U.UCC_EE_CUDA_STREAM, s_.value, C.sizeof(C.c_void_p)
-                      ee = U.handle()
-                      U.check(U.ucc_ee_create(team.members[r].team, C.byref(ep), C.byref(ee)), "ee_create")
-                      ees[(r, p_, kind)] = ee
 
-          def drain():
-              for ee in ees.values():
-                  e = C.POINTER(U.ucc_ev_t)()
-                  while U.ucc_ee_get_event(ee, C.byref(e)) == U.UCC_OK:
-                      U.ucc_ee_ack_event(ee, e)
-          for seed in range(6 if thresh == "64K" else 3):
-              rng = np.random.default_rng(1000 + seed)
-              msgs = []
-              for i in range(30):
-                  s_, d_ = rng.choice(n, 2, replace=False)
-                  count = int(rng.choice([1, 7, 300, 5000, 16384, 20000, 70001, 150000, 300007]))
-                  src, dst = Dev(count, fill=rnd(count, 50 * seed + i)), Dev(count, fill=0)
-                  reqs = {}
-                  for r, b, key in ((s_, src, "send"), (d_, dst, "recv")):
-                      a = ca("bcast", b, None, root=int(s_), count_dst=0, active_set=(int(s_), int(d_) - int(s_), 2), tag=i)
-                      q = C.POINTER(U.ucc_coll_req_t)()
-                      U.check(U.ucc_collective_init(C.byref(a), C.byref(q), team.members[r].team), "init")
-                      reqs[key] = (a, q)
-                  msgs.append((int(s_), int(d_), src, dst, reqs))
-              # global post order: a random interleaving in which, per ordered pair, sends keep their order and receives keep theirs
-              events = [(i, "send") for i in range(len(msgs))] + [(i, "recv") for i in range(len(msgs))]
-              order = list(rng.permutation(len(events)))
-              pending = [events[k] for k in order]
-              nxt = {}
-              posted = []
-              while pending:
-                  progressed = False
-                  for k, (i, kind) in enumerate(pending):
-                      pair = (msgs[i][0], msgs[i][1], kind)
-                      first = min(m for m, (mm, kk) in [(e[0], e) for e in pending] if (msgs[m][0], msgs[m][1], kk) == pair)
-                      if i != first:
-                          continue
-                      ev = U.ucc_ev_t()
-                      ev.ev_type, ev.req = U.UCC_EVENT_COMPUTE_COMPLETE, C.cast(msgs[i][4][kind][1], C.c_void_p)
-                      me_, peer_ = (msgs[i][0], msgs[i][1]) if kind == "send" else (msgs[i][1], msgs[i][0])
-                      U.check(U.ucc_collective_triggered_post(ees[(me_, peer_, kind)], C.byref(ev)), "triggered_post")
-                      posted.append((i, kind))
-                      pending.pop(k)
-                      progressed = True
-                      break
-                  assert progressed
-                  for _ in range(int(rng.integers(0, 4))):
-                      for r in range(n):
-                          U.ucc_context_progress(j.procs[r].ctx)
-              t0 = time.time()
-              allq = [m[4][k][1] for m in msgs for k in ("send", "recv")]
-              while any(q.contents.status == U.UCC_INPROGRESS for q in allq):
-                  for r in range(n):
-                      U.ucc_context_progress(j.procs[r].ctx)
-                  drain()
-                  assert time.time() - t0 < 180, ("p2p fuzz did not complete", seed)
-              rt.cudaDeviceSynchronize()
-              for i, m in enumerate(msgs):
-                  for k in ("send", "recv"):
-                      assert m[4][k][1].contents.status == U.UCC_OK, (seed, i, k)
-                      U.ucc_collective_finalize(m[4][k][1])
-                  assert np.array_equal(m[2].a, m[3].a), ("p2p fuzz data", seed, i, m[0], m[1], m[2].a.size)
-              drain()
-          for ee in ees.values():
-              U.ucc_ee_destroy(ee)
+    def traffic(thresh, seeds):
+        with UccJob(n, env=dict(BASE, **dict(ZC, UCC_TL_NVL_P2P_RNDV_THRESH=thresh))) as j:
+            team = j.create_team(range(n))
+            # stream-ordered posts, one stream per (rank, peer, direction): a kernel of the eager ring may wait for its peer, so - exactly as
+            # with NCCL - two operations that must not wait for each other must not share a stream
+            ees = {}
+            for r in range(n):
+                for p_ in range(n):
+                    for kind in ("send", "recv"):
+                        if p_ == r:
+                            continue
+                        s_ = C.c_void_p()
+                        assert rt.cudaStreamCreate(C.byref(s_)) == 0
+                        ep = U.ucc_ee_params_t()
+                        ep.ee_type, ep.ee_context, ep.ee_context_size = U.UCC_EE_CUDA_STREAM, s_.value, C.sizeof(C.c_void_p)
+                        ee = U.handle()
+                        U.check(U.ucc_ee_create(team.members[r].team, C.byref(ep), C.byref(ee)), "ee_create")
+                        ees[(r, p_, kind)] = ee
+
+            def drain():
+                for ee in ees.values():
+                    e = C.POINTER(U.ucc_ev_t)()
+                    while U.ucc_ee_get_event(ee, C.byref(e)) == U.UCC_OK:
+                        U.ucc_ee_ack_event(ee, e)
+            for seed in range(seeds):
+                rng = np.random.default_rng(1000 + seed)
+                msgs = []
+                for i in range(30):
+                    s_, d_ = rng.choice(n, 2, replace=False)
+                    count = int(rng.choice([1, 7, 300, 5000, 16384, 20000, 70001, 150000, 300007]))
+                    src, dst = Dev(count, fill=rnd(count, 50 * seed + i)), Dev(count, fill=0)
+                    reqs = {}
+                    for r, b, key in ((s_, src, "send"), (d_, dst, "recv")):
+                        a = ca("bcast", b, None, root=int(s_), count_dst=0, active_set=(int(s_), int(d_) - int(s_), 2), tag=i)
+                        q = C.POINTER(U.ucc_coll_req_t)()
+                        U.check(U.ucc_collective_init(C.byref(a), C.byref(q), team.members[r].team), "init")
+                        reqs[key] = (a, q)
+                    msgs.append((int(s_), int(d_), src, dst, reqs))
+                # global post order: a random interleaving in which, per ordered pair, sends keep their order and receives keep theirs
+                events = [(i, "send") for i in range(len(msgs))] + [(i, "recv") for i in range(len(msgs))]
+                order = list(rng.permutation(len(events)))
+                pending = [events[k] for k in order]
+                nxt = {}
+                posted = []
+                while pending:
+                    progressed = False
+                    for k, (i, kind) in enumerate(pending):
+                        pair = (msgs[i][0], msgs[i][1], kind)
+                        first = min(m for m, (mm, kk) in [(e[0], e) for e in pending] if (msgs[m][0], msgs[m][1], kk) == pair)
+                        if i != first:
+                            continue
+                        ev = U.ucc_ev_t()
+                        ev.ev_type, ev.req = U.UCC_EVENT_COMPUTE_COMPLETE, C.cast(msgs[i][4][kind][1], C.c_void_p)
+                        me_, peer_ = (msgs[i][0], msgs[i][1]) if kind == "send" else (msgs[i][1], msgs[i][0])
+                        U.check(U.ucc_collective_triggered_post(ees[(me_, peer_, kind)], C.byref(ev)), "triggered_post")
+                        posted.append((i, kind))
+                        pending.pop(k)
+                        progressed = True
+                        break
+                    assert progressed
+                    for _ in range(int(rng.integers(0, 4))):
+                        for r in range(n):
+                            U.ucc_context_progress(j.procs[r].ctx)
+                t0 = time.time()
+                allq = [m[4][k][1] for m in msgs for k in ("send", "recv")]
+                while any(q.contents.status == U.UCC_INPROGRESS for q in allq):
+                    for r in range(n):
+                        U.ucc_context_progress(j.procs[r].ctx)
+                    drain()
+                    assert time.time() - t0 < 180, ("p2p fuzz did not complete", seed)
+                rt.cudaDeviceSynchronize()
+                for i, m in enumerate(msgs):
+                    for k in ("send", "recv"):
+                        assert m[4][k][1].contents.status == U.UCC_OK, (seed, i, k)
+                        U.ucc_collective_finalize(m[4][k][1])
+                    assert np.array_equal(m[2].a, m[3].a), ("p2p fuzz data", seed, i, m[0], m[1], m[2].a.size)
+                drain()
+            for ee in ees.values():
+                U.ucc_ee_destroy(ee)
+    traffic("64K", 6)
+    traffic("inf", 3)      # everything through the eager ring, incl. messages larger than the ring (1 MB)
     print("  p2p fuzz ok", flush=True)
 
 
