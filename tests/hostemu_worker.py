@@ -678,8 +678,6 @@ def p2p_fuzz():
                 events = [(i, "send") for i in range(len(msgs))] + [(i, "recv") for i in range(len(msgs))]
                 order = list(rng.permutation(len(events)))
                 pending = [events[k] for k in order]
-                nxt = {}
-                posted = []
                 while pending:
                     progressed = False
                     for k, (i, kind) in enumerate(pending):
@@ -691,7 +689,6 @@ def p2p_fuzz():
                         ev.ev_type, ev.req = U.UCC_EVENT_COMPUTE_COMPLETE, C.cast(msgs[i][4][kind][1], C.c_void_p)
                         me_, peer_ = (msgs[i][0], msgs[i][1]) if kind == "send" else (msgs[i][1], msgs[i][0])
                         U.check(U.ucc_collective_triggered_post(ees[(me_, peer_, kind)], C.byref(ev)), "triggered_post")
-                        posted.append((i, kind))
                         pending.pop(k)
                         progressed = True
                         break
