@@ -190,16 +190,31 @@ def recv(tensor, src, tag=0, comm=None, async_op=False):
     return _p2p(tensor, src, comm.rank, tag, comm, async_op)
 
 
+def batch_p2p(batch, comm=None):
+    """The role of torch.distributed.batch_isend_irecv / an NCCL group: `batch` is a list of ("send" | "recv", tensor, peer[, tag]).
+    All sends are posted before all receives (each kind in list order): a kernel of the eager ring may wait for its peer, so a
+    receive must never be queued in front of a send that another rank is waiting for.  Returns the Work objects in `batch` order."""
+    comm = comm or default_comm()
+    works = [None] * len(batch)
+    for want in ("send", "recv"):
+        for i, item in enumerate(batch):
+            kind, tensor, peer = item[0], item[1], item[2]
+            tag = item[3] if len(item) > 3 else 0
+            if kind != want:
+                continue
+            works[i] = send(tensor, peer, tag, comm, async_op=True) if kind == "send" else recv(tensor, peer, tag, comm, async_op=True)
+    assert all(w is not None for w in works), "batch entries are ('send' | 'recv', tensor, peer[, tag])"
+    return works
+
+
 def ring_exchange(send_tensor, recv_tensor, shift=1, tag=0, comm=None):
-    """Every rank sends to (rank + shift) and receives from (rank - shift): one hop of ring attention / a pipeline bubble step.
-    Even ranks send first, odd ranks receive first; with an odd ring the last rank pairs up with rank 0 afterwards."""
+    """Every rank sends to (rank + shift) and receives from (rank - shift): one hop of ring attention / a pipeline bubble step
+    (a batch: the send is posted before the receive on every rank)."""
     comm = comm or default_comm()
     n, r = comm.size, comm.rank
     to, frm = (r + shift) % n, (r - shift) % n
     if n == 1:
         recv_tensor.copy_(send_tensor)
         return
-    w_s = send(send_tensor, to, tag, comm, async_op=True)
-    w_r = recv(recv_tensor, frm, tag, comm, async_op=True)
-    w_s.wait()
-    w_r.wait()
+    for w in batch_p2p([("recv", recv_tensor, frm, tag), ("send", send_tensor, to, tag)], comm):
+        w.wait()
