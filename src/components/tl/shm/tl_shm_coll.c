@@ -855,6 +855,9 @@ ucc_status_t ucc_tl_shm_alltoallv_hybrid(ucc_tl_shm_task_t *t)
         if (HD(from) > T) CHK(shm_prog_recv(t, from, dst + HDO(from), HD(from), dmt, 100));
         if (HS(to) > T) CHK(shm_prog_send(t, to, src + HSO(to), HS(to), smt, 100));
     }
+    /* my own block: small ones ride in slot 0 of the Bruck rounds (which never leaves this rank), a big one is a plain copy
+     * (found by the random-program test: it was simply missing) */
+    if (HS(r) > T) CHK(shm_prog_copy(t, dst + HDO(r), src + HSO(r), ucc_min(HS(r), HD(r)), dmt, smt));
     for (ucc_rank_t i = 0; i < N; i++) { ucc_rank_t d = (r + i) % N; if (HS(d) <= T) { any_small = 1; if (HS(d) != 0) CHK(shm_prog_copy(t, w + (size_t)i * T, src + HSO(d), HS(d), dmt, smt)); } }
     (void)any_small; /* the rounds run even if I have nothing small to send: other ranks' small blocks are routed through me */
     CHK(bruck_rounds(t, w, pk, T, dmt, 1));
