@@ -712,8 +712,9 @@ def p2p_fuzz():
                 drain()
             for ee in ees.values():
                 U.ucc_ee_destroy(ee)
-    traffic("64K", 6)
-    traffic("inf", 3)      # everything through the eager ring, incl. messages larger than the ring (1 MB)
+    more = int(os.environ.get("B200_FUZZ_SEEDS", "0"))
+    traffic("64K", max(6, more))
+    traffic("inf", max(3, more // 2))      # everything through the eager ring, incl. messages larger than the ring (1 MB)
     print("  p2p fuzz ok", flush=True)
 
 
@@ -728,7 +729,7 @@ def coll_fuzz():
                         ("zcopy, 3 lanes", dict(ZC, UCC_TL_NVL_ZCOPY_THRESH="64K", UCC_TL_NVL_SLOTS="3"))):
         with UccJob(4, env=dict(BASE, **extra)) as j:
             teams = [j.create_team(range(4)), j.create_team([3, 0, 2])]
-            for seed in range(4):
+            for seed in range(int(os.environ.get("B200_FUZZ_SEEDS", "4"))):
                 rng = np.random.default_rng(500 + seed)
                 window = []
 

@@ -272,7 +272,7 @@ def test_alltoall_onesided_registered_destinations(n, capfd):
             assert U.lib.ucc_mem_unmap(C.byref(m)) == U.UCC_OK
 
 
-@pytest.mark.parametrize("seed", range(int(__import__("os").environ.get("UCC_B200_FUZZ_SEEDS", "10"))))
+@pytest.mark.parametrize("seed", range(int(__import__("os").environ.get("B200_FUZZ_SEEDS", "10"))))
 def test_random_programs_with_random_algorithms(seed):
     """Fuzz of the host transport: a random algorithm is forced for every collective type (UCC_TL_SHM_TUNE, unsupported shapes fall
     back through the score chain), then 50 collectives of random kind / count / datatype / operator / root run on a team of random
