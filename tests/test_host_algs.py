@@ -272,6 +272,95 @@ def test_alltoall_onesided_registered_destinations(n, capfd):
             assert U.lib.ucc_mem_unmap(C.byref(m)) == U.UCC_OK
 
 
+def _random_program(teams, rng, tune, steps=50):
+    """`steps` random collectives on randomly chosen teams of `teams`, up to three outstanding, each checked against numpy"""
+    kinds = ["allreduce", "allgather", "alltoall", "reduce_scatter", "bcast", "reduce", "barrier", "gather", "scatter", "allgatherv", "alltoallv"]
+    window = []
+
+    def retire(k):
+        while len(window) > k:
+            q, check, what = window.pop(0)
+            st = q.wait()
+            assert st == U.UCC_OK, (tune, what, U.status_str(st))
+            q.finalize()
+            check()
+    for step in range(steps):
+        team = teams[int(rng.integers(0, 2)) % len(teams)]
+        n = len(team.members)
+        kind = kinds[int(rng.integers(0, len(kinds)))]
+        blk = int(rng.choice([1, 2, 17, 256, 4099, 50001]))
+        dt = ["float64", "int32", "float32"][int(rng.integers(0, 3))]
+        npdt = np.dtype(dt)
+        op = ["sum", "max", "min"][int(rng.integers(0, 3))]
+        root = int(rng.integers(0, n))
+        what = (step, kind, n, blk, dt, op, root)
+        mk = lambda c: rng.integers(0, 50, c).astype(npdt)                                           # noqa: E731
+        red = {"sum": lambda a: np.sum(a, 0), "max": lambda a: np.max(a, 0), "min": lambda a: np.min(a, 0)}[op]
+        eq = lambda got, exp, what=what: np.testing.assert_allclose(got, exp, rtol=1e-6, err_msg=str((tune, what)))   # noqa: E731
+        if kind == "allreduce":
+            src = [mk(blk) for _ in range(n)]; dst = [np.zeros(blk, npdt) for _ in range(n)]
+            args = [coll_args(kind, src[r], dst[r], dt=dt, op=op) for r in range(n)]
+            exp = red(src)
+            check = lambda dst=dst, exp=exp, eq=eq: [eq(d, exp) for d in dst]                        # noqa: E731
+        elif kind == "allgather":
+            src = [mk(blk) for _ in range(n)]; dst = [np.zeros(blk * n, npdt) for _ in range(n)]
+            args = [coll_args(kind, src[r], dst[r], dt=dt) for r in range(n)]
+            exp = np.concatenate(src)
+            check = lambda dst=dst, exp=exp, eq=eq: [eq(d, exp) for d in dst]                        # noqa: E731
+        elif kind == "allgatherv":
+            counts = [int(rng.integers(0, blk + 1)) for _ in range(n)]
+            displs = np.concatenate([[0], np.cumsum(counts)[:-1]]).astype(int)
+            src = [mk(counts[r]) if counts[r] else np.zeros(1, npdt)[:0] for r in range(n)]
+            dst = [np.zeros(max(sum(counts), 1), npdt) for _ in range(n)]
+            args = [coll_args(kind, src[r] if counts[r] else None, dst[r], dt=dt, count_src=counts[r], dst_counts=counts, dst_displs=displs) for r in range(n)]
+            exp = np.concatenate(src) if sum(counts) else np.zeros(0, npdt)
+            check = lambda dst=dst, exp=exp, eq=eq, tot=sum(counts): [eq(d[:tot], exp) for d in dst]  # noqa: E731
+        elif kind == "alltoall":
+            src = [mk(blk * n) for _ in range(n)]; dst = [np.zeros(blk * n, npdt) for _ in range(n)]
+            args = [coll_args(kind, src[r], dst[r], dt=dt) for r in range(n)]
+            check = lambda src=src, dst=dst, n=n, blk=blk, eq=eq: [eq(dst[r], np.concatenate([src[p][r * blk:(r + 1) * blk] for p in range(n)])) for r in range(n)]  # noqa: E731
+        elif kind == "alltoallv":
+            m = rng.integers(0, min(blk, 3000) + 1, (n, n))
+            sd = [np.concatenate([[0], np.cumsum(m[r])[:-1]]).astype(int) for r in range(n)]
+            rd = [np.concatenate([[0], np.cumsum(m[:, r])[:-1]]).astype(int) for r in range(n)]
+            src = [mk(max(int(m[r].sum()), 1)) for r in range(n)]
+            dst = [np.zeros(max(int(m[:, r].sum()), 1), npdt) for r in range(n)]
+            args = [coll_args(kind, src[r], dst[r], dt=dt, src_counts=m[r], src_displs=sd[r], dst_counts=m[:, r], dst_displs=rd[r]) for r in range(n)]
+            check = lambda src=src, dst=dst, m=m, sd=sd, n=n, eq=eq: [eq(dst[r][:int(m[:, r].sum())], np.concatenate([src[p][sd[p][r]:sd[p][r] + m[p][r]] for p in range(n)])) for r in range(n)]  # noqa: E731
+        elif kind == "reduce_scatter":
+            src = [mk(blk * n) for _ in range(n)]; dst = [np.zeros(blk, npdt) for _ in range(n)]
+            args = [coll_args(kind, src[r], dst[r], dt=dt, op=op) for r in range(n)]
+            exp = red(src)
+            check = lambda dst=dst, exp=exp, blk=blk, n=n, eq=eq: [eq(dst[r], exp[r * blk:(r + 1) * blk]) for r in range(n)]  # noqa: E731
+        elif kind == "bcast":
+            b = [mk(blk) if r == root else np.zeros(blk, npdt) for r in range(n)]
+            exp = b[root].copy()
+            args = [coll_args(kind, b[r], None, dt=dt, root=root) for r in range(n)]
+            check = lambda b=b, exp=exp, eq=eq: [eq(x, exp) for x in b]                              # noqa: E731
+        elif kind == "reduce":
+            src = [mk(blk) for _ in range(n)]; out = np.zeros(blk, npdt)
+            args = [coll_args(kind, src[r], out if r == root else None, dt=dt, op=op, root=root, count_dst=blk) for r in range(n)]
+            exp = red(src)
+            check = lambda out=out, exp=exp, eq=eq: eq(out, exp)                                     # noqa: E731
+        elif kind == "gather":
+            src = [mk(blk) for _ in range(n)]; g = np.zeros(blk * n, npdt)
+            args = [coll_args(kind, src[r], g if r == root else None, dt=dt, root=root, count_dst=blk * n) for r in range(n)]
+            exp = np.concatenate(src)
+            check = lambda g=g, exp=exp, eq=eq: eq(g, exp)                                           # noqa: E731
+        elif kind == "scatter":
+            big = mk(blk * n); outs = [np.zeros(blk, npdt) for _ in range(n)]
+            args = [coll_args(kind, big if r == root else None, outs[r], dt=dt, root=root, count_src=blk * n) for r in range(n)]
+            check = lambda big=big, outs=outs, blk=blk, n=n, eq=eq: [eq(outs[r], big[r * blk:(r + 1) * blk]) for r in range(n)]  # noqa: E731
+        else:
+            args = [coll_args("barrier") for _ in range(n)]
+            check = lambda: None                                                                     # noqa: E731
+        q = team.coll(args)
+        q.post()
+        window.append((q, check, what))
+        retire(int(rng.integers(0, 3)))
+    retire(0)
+
+
 @pytest.mark.parametrize("seed", range(int(__import__("os").environ.get("B200_FUZZ_SEEDS", "10"))))
 def test_random_programs_with_random_algorithms(seed):
     """Fuzz of the host transport: a random algorithm is forced for every collective type (UCC_TL_SHM_TUNE, unsupported shapes fall
@@ -282,89 +371,18 @@ def test_random_programs_with_random_algorithms(seed):
     n_all = int(rng.integers(3, 10))
     with UccJob(n_all, env={"UCC_TL_SHM_TUNE": tune, "UCC_TLS": "shm,self"}) as job:
         sub = sorted(rng.choice(n_all, size=int(rng.integers(2, n_all)), replace=False).tolist())
-        teams = [job.create_team(range(n_all)), job.create_team(sub)]
-        kinds = ["allreduce", "allgather", "alltoall", "reduce_scatter", "bcast", "reduce", "barrier", "gather", "scatter", "allgatherv", "alltoallv"]
-        window = []
+        _random_program([job.create_team(range(n_all)), job.create_team(sub)], rng, tune)
 
-        def retire(k):
-            while len(window) > k:
-                q, check, what = window.pop(0)
-                st = q.wait()
-                assert st == U.UCC_OK, (tune, what, U.status_str(st))
-                q.finalize()
-                check()
-        for step in range(50):
-            team = teams[int(rng.integers(0, 2))]
-            n = len(team.members)
-            kind = kinds[int(rng.integers(0, len(kinds)))]
-            blk = int(rng.choice([1, 2, 17, 256, 4099, 50001]))
-            dt = ["float64", "int32", "float32"][int(rng.integers(0, 3))]
-            npdt = np.dtype(dt)
-            op = ["sum", "max", "min"][int(rng.integers(0, 3))]
-            root = int(rng.integers(0, n))
-            what = (step, kind, n, blk, dt, op, root)
-            mk = lambda c: rng.integers(0, 50, c).astype(npdt)                                           # noqa: E731
-            red = {"sum": lambda a: np.sum(a, 0), "max": lambda a: np.max(a, 0), "min": lambda a: np.min(a, 0)}[op]
-            eq = lambda got, exp, what=what: np.testing.assert_allclose(got, exp, rtol=1e-6, err_msg=str((tune, what)))   # noqa: E731
-            if kind == "allreduce":
-                src = [mk(blk) for _ in range(n)]; dst = [np.zeros(blk, npdt) for _ in range(n)]
-                args = [coll_args(kind, src[r], dst[r], dt=dt, op=op) for r in range(n)]
-                exp = red(src)
-                check = lambda dst=dst, exp=exp, eq=eq: [eq(d, exp) for d in dst]                        # noqa: E731
-            elif kind == "allgather":
-                src = [mk(blk) for _ in range(n)]; dst = [np.zeros(blk * n, npdt) for _ in range(n)]
-                args = [coll_args(kind, src[r], dst[r], dt=dt) for r in range(n)]
-                exp = np.concatenate(src)
-                check = lambda dst=dst, exp=exp, eq=eq: [eq(d, exp) for d in dst]                        # noqa: E731
-            elif kind == "allgatherv":
-                counts = [int(rng.integers(0, blk + 1)) for _ in range(n)]
-                displs = np.concatenate([[0], np.cumsum(counts)[:-1]]).astype(int)
-                src = [mk(counts[r]) if counts[r] else np.zeros(1, npdt)[:0] for r in range(n)]
-                dst = [np.zeros(max(sum(counts), 1), npdt) for _ in range(n)]
-                args = [coll_args(kind, src[r] if counts[r] else None, dst[r], dt=dt, count_src=counts[r], dst_counts=counts, dst_displs=displs) for r in range(n)]
-                exp = np.concatenate(src) if sum(counts) else np.zeros(0, npdt)
-                check = lambda dst=dst, exp=exp, eq=eq, tot=sum(counts): [eq(d[:tot], exp) for d in dst]  # noqa: E731
-            elif kind == "alltoall":
-                src = [mk(blk * n) for _ in range(n)]; dst = [np.zeros(blk * n, npdt) for _ in range(n)]
-                args = [coll_args(kind, src[r], dst[r], dt=dt) for r in range(n)]
-                check = lambda src=src, dst=dst, n=n, blk=blk, eq=eq: [eq(dst[r], np.concatenate([src[p][r * blk:(r + 1) * blk] for p in range(n)])) for r in range(n)]  # noqa: E731
-            elif kind == "alltoallv":
-                m = rng.integers(0, min(blk, 3000) + 1, (n, n))
-                sd = [np.concatenate([[0], np.cumsum(m[r])[:-1]]).astype(int) for r in range(n)]
-                rd = [np.concatenate([[0], np.cumsum(m[:, r])[:-1]]).astype(int) for r in range(n)]
-                src = [mk(max(int(m[r].sum()), 1)) for r in range(n)]
-                dst = [np.zeros(max(int(m[:, r].sum()), 1), npdt) for r in range(n)]
-                args = [coll_args(kind, src[r], dst[r], dt=dt, src_counts=m[r], src_displs=sd[r], dst_counts=m[:, r], dst_displs=rd[r]) for r in range(n)]
-                check = lambda src=src, dst=dst, m=m, sd=sd, n=n, eq=eq: [eq(dst[r][:int(m[:, r].sum())], np.concatenate([src[p][sd[p][r]:sd[p][r] + m[p][r]] for p in range(n)])) for r in range(n)]  # noqa: E731
-            elif kind == "reduce_scatter":
-                src = [mk(blk * n) for _ in range(n)]; dst = [np.zeros(blk, npdt) for _ in range(n)]
-                args = [coll_args(kind, src[r], dst[r], dt=dt, op=op) for r in range(n)]
-                exp = red(src)
-                check = lambda dst=dst, exp=exp, blk=blk, n=n, eq=eq: [eq(dst[r], exp[r * blk:(r + 1) * blk]) for r in range(n)]  # noqa: E731
-            elif kind == "bcast":
-                b = [mk(blk) if r == root else np.zeros(blk, npdt) for r in range(n)]
-                exp = b[root].copy()
-                args = [coll_args(kind, b[r], None, dt=dt, root=root) for r in range(n)]
-                check = lambda b=b, exp=exp, eq=eq: [eq(x, exp) for x in b]                              # noqa: E731
-            elif kind == "reduce":
-                src = [mk(blk) for _ in range(n)]; out = np.zeros(blk, npdt)
-                args = [coll_args(kind, src[r], out if r == root else None, dt=dt, op=op, root=root, count_dst=blk) for r in range(n)]
-                exp = red(src)
-                check = lambda out=out, exp=exp, eq=eq: eq(out, exp)                                     # noqa: E731
-            elif kind == "gather":
-                src = [mk(blk) for _ in range(n)]; g = np.zeros(blk * n, npdt)
-                args = [coll_args(kind, src[r], g if r == root else None, dt=dt, root=root, count_dst=blk * n) for r in range(n)]
-                exp = np.concatenate(src)
-                check = lambda g=g, exp=exp, eq=eq: eq(g, exp)                                           # noqa: E731
-            elif kind == "scatter":
-                big = mk(blk * n); outs = [np.zeros(blk, npdt) for _ in range(n)]
-                args = [coll_args(kind, big if r == root else None, outs[r], dt=dt, root=root, count_src=blk * n) for r in range(n)]
-                check = lambda big=big, outs=outs, blk=blk, n=n, eq=eq: [eq(outs[r], big[r * blk:(r + 1) * blk]) for r in range(n)]  # noqa: E731
-            else:
-                args = [coll_args("barrier") for _ in range(n)]
-                check = lambda: None                                                                     # noqa: E731
-            q = team.coll(args)
-            q.post()
-            window.append((q, check, what))
-            retire(int(rng.integers(0, 3)))
-        retire(0)
+
+@pytest.mark.parametrize("seed", range(int(__import__("os").environ.get("B200_FUZZ_SEEDS", "8"))))
+def test_random_programs_on_cl_hier(seed):
+    """The same random programs through the hierarchical CL on a synthetic multi-node placement (random node size, random cl/hier
+    algorithm per collective: allreduce rab / split_rail, bcast / reduce 2step, alltoall(v) node_split, allgatherv gab; everything the
+    hierarchy declines falls back to cl/basic)."""
+    rng = np.random.default_rng(9000 + seed)
+    n = int(rng.integers(4, 10))
+    ppn = int(rng.integers(1, n))
+    tune = "allreduce:0-inf:@" + ["rab", "split_rail"][int(rng.integers(0, 2))]
+    env = {"UCC_CLS": "hier,basic", "UCC_CL_HIER_TLS": "shm,self", "UCC_CL_BASIC_TLS": "shm,self", "UCC_CL_HIER_TUNE": tune}
+    with UccJob(n, ppn=ppn, env=env, cls="hier,basic") as job:
+        _random_program([job.create_team()], rng, (tune, n, ppn), steps=40)
