@@ -754,14 +754,19 @@ def coll_fuzz():
                     what = (step, kind, n, blk, dt, op, root)
                     mk = lambda c, sd: Dev(c, npdt, fill=(rnd(c, sd, npdt) if dt == "float32" else (rnd(c, sd, npdt) % 1000)))  # noqa: E731
                     red = (lambda arrs: np.sum(arrs, 0)) if op == "sum" else (lambda arrs: np.max(arrs, 0))
+                    inplace = kind in ("allreduce", "allgather", "reduce_scatter") and rng.integers(0, 3) == 0
+                    what = what + (("inplace",) if inplace else ())
                     if kind == "allreduce":
-                        src = [mk(blk, 10 * step + r) for r in range(n)]; dst = [Dev(blk, npdt, fill=0) for _ in range(n)]
-                        args = [ca(kind, src[r], dst[r], dt=dt, op=op) for r in range(n)]
+                        src = [mk(blk, 10 * step + r) for r in range(n)]; dst = [Dev(blk, npdt, fill=(src[r].a if inplace else 0)) for r in range(n)]
+                        args = [ca(kind, None if inplace else src[r], dst[r], dt=dt, op=op, inplace=inplace) for r in range(n)]
                         exp = red([x.a.copy() for x in src])
                         check = lambda dst=dst, exp=exp, what=what: [np.testing.assert_allclose(d.a, exp, rtol=1e-5, err_msg=str(what)) for d in dst]  # noqa: E731
                     elif kind == "allgather":
                         src = [mk(blk, 10 * step + r) for r in range(n)]; dst = [Dev(blk * n, npdt, fill=0) for _ in range(n)]
-                        args = [ca(kind, src[r], dst[r], dt=dt) for r in range(n)]
+                        if inplace:
+                            for r in range(n):
+                                dst[r].a[r * blk:(r + 1) * blk] = src[r].a
+                        args = [ca(kind, None if inplace else src[r], dst[r], dt=dt, inplace=inplace) for r in range(n)]
                         exp = np.concatenate([x.a for x in src])
                         check = lambda dst=dst, exp=exp, what=what: [np.testing.assert_array_equal(d.a, exp, err_msg=str(what)) for d in dst]  # noqa: E731
                     elif kind == "alltoall":
@@ -770,9 +775,14 @@ def coll_fuzz():
                         check = lambda src=src, dst=dst, n=n, blk=blk, what=what: [np.testing.assert_array_equal(dst[r].a, np.concatenate([src[p].a[r * blk:(r + 1) * blk] for p in range(n)]), err_msg=str(what)) for r in range(n)]  # noqa: E731
                     elif kind == "reduce_scatter":
                         src = [mk(blk * n, 10 * step + r) for r in range(n)]; dst = [Dev(blk, npdt, fill=0) for _ in range(n)]
-                        args = [ca(kind, src[r], dst[r], dt=dt, op=op) for r in range(n)]
                         exp = red([x.a.copy() for x in src])
-                        check = lambda dst=dst, exp=exp, blk=blk, n=n, what=what: [np.testing.assert_allclose(dst[r].a, exp[r * blk:(r + 1) * blk], rtol=1e-5, err_msg=str(what)) for r in range(n)]  # noqa: E731
+                        if inplace:   # the whole vector is in dst, the result block stays at its offset
+                            dst = [Dev(blk * n, npdt, fill=src[r].a) for r in range(n)]
+                            args = [ca(kind, None, dst[r], dt=dt, op=op, inplace=True) for r in range(n)]
+                            check = lambda dst=dst, exp=exp, blk=blk, n=n, what=what: [np.testing.assert_allclose(dst[r].a[r * blk:(r + 1) * blk], exp[r * blk:(r + 1) * blk], rtol=1e-5, err_msg=str(what)) for r in range(n)]  # noqa: E731
+                        else:
+                            args = [ca(kind, src[r], dst[r], dt=dt, op=op) for r in range(n)]
+                            check = lambda dst=dst, exp=exp, blk=blk, n=n, what=what: [np.testing.assert_allclose(dst[r].a, exp[r * blk:(r + 1) * blk], rtol=1e-5, err_msg=str(what)) for r in range(n)]  # noqa: E731
                     elif kind == "bcast":
                         b = [mk(blk, 10 * step + 7) if r == root else Dev(blk, npdt, fill=0) for r in range(n)]
                         exp = b[root].a.copy()

@@ -297,14 +297,19 @@ def _random_program(teams, rng, tune, steps=50):
         mk = lambda c: rng.integers(0, 50, c).astype(npdt)                                           # noqa: E731
         red = {"sum": lambda a: np.sum(a, 0), "max": lambda a: np.max(a, 0), "min": lambda a: np.min(a, 0)}[op]
         eq = lambda got, exp, what=what: np.testing.assert_allclose(got, exp, rtol=1e-6, err_msg=str((tune, what)))   # noqa: E731
+        inplace = kind in ("allreduce", "allgather", "reduce_scatter") and rng.integers(0, 3) == 0
+        what = what + (("inplace",) if inplace else ())
         if kind == "allreduce":
-            src = [mk(blk) for _ in range(n)]; dst = [np.zeros(blk, npdt) for _ in range(n)]
-            args = [coll_args(kind, src[r], dst[r], dt=dt, op=op) for r in range(n)]
+            src = [mk(blk) for _ in range(n)]; dst = [s_.copy() if inplace else np.zeros(blk, npdt) for s_ in src]
+            args = [coll_args(kind, None if inplace else src[r], dst[r], dt=dt, op=op, inplace=inplace) for r in range(n)]
             exp = red(src)
             check = lambda dst=dst, exp=exp, eq=eq: [eq(d, exp) for d in dst]                        # noqa: E731
         elif kind == "allgather":
             src = [mk(blk) for _ in range(n)]; dst = [np.zeros(blk * n, npdt) for _ in range(n)]
-            args = [coll_args(kind, src[r], dst[r], dt=dt) for r in range(n)]
+            if inplace:
+                for r in range(n):
+                    dst[r][r * blk:(r + 1) * blk] = src[r]
+            args = [coll_args(kind, None if inplace else src[r], dst[r], dt=dt, inplace=inplace) for r in range(n)]
             exp = np.concatenate(src)
             check = lambda dst=dst, exp=exp, eq=eq: [eq(d, exp) for d in dst]                        # noqa: E731
         elif kind == "allgatherv":
@@ -329,9 +334,14 @@ def _random_program(teams, rng, tune, steps=50):
             check = lambda src=src, dst=dst, m=m, sd=sd, n=n, eq=eq: [eq(dst[r][:int(m[:, r].sum())], np.concatenate([src[p][sd[p][r]:sd[p][r] + m[p][r]] for p in range(n)])) for r in range(n)]  # noqa: E731
         elif kind == "reduce_scatter":
             src = [mk(blk * n) for _ in range(n)]; dst = [np.zeros(blk, npdt) for _ in range(n)]
-            args = [coll_args(kind, src[r], dst[r], dt=dt, op=op) for r in range(n)]
             exp = red(src)
-            check = lambda dst=dst, exp=exp, blk=blk, n=n, eq=eq: [eq(dst[r], exp[r * blk:(r + 1) * blk]) for r in range(n)]  # noqa: E731
+            if inplace:   # the total vector is in dst, the result block stays at its offset
+                dst = [s_.copy() for s_ in src]
+                args = [coll_args(kind, None, dst[r], dt=dt, op=op, inplace=True) for r in range(n)]
+                check = lambda dst=dst, exp=exp, blk=blk, n=n, eq=eq: [eq(dst[r][r * blk:(r + 1) * blk], exp[r * blk:(r + 1) * blk]) for r in range(n)]  # noqa: E731
+            else:
+                args = [coll_args(kind, src[r], dst[r], dt=dt, op=op) for r in range(n)]
+                check = lambda dst=dst, exp=exp, blk=blk, n=n, eq=eq: [eq(dst[r], exp[r * blk:(r + 1) * blk]) for r in range(n)]  # noqa: E731
         elif kind == "bcast":
             b = [mk(blk) if r == root else np.zeros(blk, npdt) for r in range(n)]
             exp = b[root].copy()
