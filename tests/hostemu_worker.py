@@ -754,6 +754,28 @@ def coll_fuzz():
                     what = (step, kind, n, blk, dt, op, root)
                     mk = lambda c, sd: Dev(c, npdt, fill=(rnd(c, sd, npdt) if dt == "float32" else (rnd(c, sd, npdt) % 1000)))  # noqa: E731
                     red = (lambda arrs: np.sum(arrs, 0)) if op == "sum" else (lambda arrs: np.max(arrs, 0))
+                    if kind in ("allreduce", "allgather", "alltoall") and rng.integers(0, 5) == 0:
+                        # persistent request: posted three times with new input each time (zero-copy: the pointer tables are cached after the first post)
+                        retire(0)
+                        mult = 1 if kind == "allreduce" else n
+                        src = [mk(blk * (n if kind == "alltoall" else 1), 10 * step + r) for r in range(n)]
+                        dst = [Dev(blk * mult, npdt, fill=0) for _ in range(n)]
+                        q = team.coll([ca(kind, src[r], dst[r], dt=dt, op=op, persistent=True) for r in range(n)])
+                        for rep in range(3):
+                            for r in range(n):
+                                src[r].a[:] = rnd(src[r].a.size, 1000 * rep + 10 * step + r, npdt)
+                                dst[r].a[:] = 0
+                            q.post()
+                            assert q.wait() == U.UCC_OK, (mode, seed, what, "persistent", rep)
+                            for r in range(n):
+                                if kind == "allreduce":
+                                    np.testing.assert_allclose(dst[r].a, red([x.a.copy() for x in src]), rtol=1e-5, err_msg=str((what, rep)))
+                                elif kind == "allgather":
+                                    np.testing.assert_array_equal(dst[r].a, np.concatenate([x.a for x in src]), err_msg=str((what, rep)))
+                                else:
+                                    np.testing.assert_array_equal(dst[r].a, np.concatenate([src[p_].a[r * blk:(r + 1) * blk] for p_ in range(n)]), err_msg=str((what, rep)))
+                        q.finalize()
+                        continue
                     inplace = kind in ("allreduce", "allgather", "reduce_scatter") and rng.integers(0, 3) == 0
                     what = what + (("inplace",) if inplace else ())
                     if kind == "allreduce":

@@ -297,6 +297,27 @@ def _random_program(teams, rng, tune, steps=50):
         mk = lambda c: rng.integers(0, 50, c).astype(npdt)                                           # noqa: E731
         red = {"sum": lambda a: np.sum(a, 0), "max": lambda a: np.max(a, 0), "min": lambda a: np.min(a, 0)}[op]
         eq = lambda got, exp, what=what: np.testing.assert_allclose(got, exp, rtol=1e-6, err_msg=str((tune, what)))   # noqa: E731
+        if kind in ("allreduce", "allgather", "alltoall") and rng.integers(0, 5) == 0:
+            # persistent request: posted three times, new input every time
+            retire(0)
+            src = [mk(blk * (n if kind == "alltoall" else 1)) for _ in range(n)]
+            dst = [np.zeros(blk * (1 if kind == "allreduce" else n), npdt) for _ in range(n)]
+            q = team.coll([coll_args(kind, src[r], dst[r], dt=dt, op=op, persistent=True) for r in range(n)])
+            for rep in range(3):
+                for r in range(n):
+                    src[r][:] = mk(src[r].size)
+                    dst[r][:] = 0
+                q.post()
+                assert q.wait() == U.UCC_OK, (tune, what, "persistent", rep)
+                for r in range(n):
+                    if kind == "allreduce":
+                        eq(dst[r], red(src))
+                    elif kind == "allgather":
+                        eq(dst[r], np.concatenate(src))
+                    else:
+                        eq(dst[r], np.concatenate([src[p_][r * blk:(r + 1) * blk] for p_ in range(n)]))
+            q.finalize()
+            continue
         inplace = kind in ("allreduce", "allgather", "reduce_scatter") and rng.integers(0, 3) == 0
         what = what + (("inplace",) if inplace else ())
         if kind == "allreduce":
