@@ -724,7 +724,7 @@ def coll_fuzz():
     member, as UCC requires), with the staged kernels, with the zero-copy exchange (deferred launches), and both again on several lanes
     (UCC_TL_NVL_SLOTS: consecutive collectives use consecutive heap images), always with a heap so small that large messages take several
     rounds; every result is checked against numpy."""
-    kinds = ["allreduce", "allgather", "alltoall", "reduce_scatter", "bcast", "reduce", "barrier", "gather", "scatter"]
+    kinds = ["allreduce", "allgather", "alltoall", "reduce_scatter", "bcast", "reduce", "barrier", "gather", "scatter", "allgatherv", "alltoallv", "reduce_scatterv"]
     for mode, extra in (("staged", NOZC), ("zcopy", dict(ZC, UCC_TL_NVL_ZCOPY_THRESH="64K")), ("staged, 4 lanes", dict(NOZC, UCC_TL_NVL_SLOTS="4")),
                         ("zcopy, 3 lanes", dict(ZC, UCC_TL_NVL_ZCOPY_THRESH="64K", UCC_TL_NVL_SLOTS="3"))):
         with UccJob(4, env=dict(BASE, **extra)) as j:
@@ -745,7 +745,7 @@ def coll_fuzz():
                     n = len(team.members)
                     kind = kinds[int(rng.integers(0, len(kinds)))]
                     blk = int(rng.choice([1, 3, 100, 4097, 30011, 120001]))
-                    if kind not in ("allreduce", "reduce_scatter", "reduce") and blk > 30011:
+                    if kind not in ("allreduce", "reduce_scatter", "reduce", "reduce_scatterv") and blk > 30011:
                         blk = 30011      # the data-movement kernels stage the whole message in the (here 1 MB) heap; only reductions work in rounds
                     dt = "float32" if rng.integers(0, 2) else "int32"
                     npdt = np.dtype(dt)
@@ -805,6 +805,29 @@ def coll_fuzz():
                         else:
                             args = [ca(kind, src[r], dst[r], dt=dt, op=op) for r in range(n)]
                             check = lambda dst=dst, exp=exp, blk=blk, n=n, what=what: [np.testing.assert_allclose(dst[r].a, exp[r * blk:(r + 1) * blk], rtol=1e-5, err_msg=str(what)) for r in range(n)]  # noqa: E731
+                    elif kind == "allgatherv":
+                        counts = [int(rng.integers(0, blk + 1)) for _ in range(n)]
+                        offs = np.concatenate([[0], np.cumsum(counts)[:-1]]).astype(int)
+                        src = [mk(counts[r], 10 * step + r) for r in range(n)]; dst = [Dev(max(sum(counts), 1), npdt, fill=0) for _ in range(n)]
+                        args = [ca(kind, src[r], dst[r], dt=dt, count_src=counts[r], dst_counts=counts, dst_displs=offs) for r in range(n)]
+                        exp = np.concatenate([x.a[:counts[r]] for r, x in enumerate(src)])
+                        check = lambda dst=dst, exp=exp, tot=sum(counts), what=what: [np.testing.assert_array_equal(d.a[:tot], exp, err_msg=str(what)) for d in dst]  # noqa: E731
+                    elif kind == "alltoallv":
+                        m = rng.integers(0, min(blk, 20000) + 1, (n, n))
+                        sd = [np.concatenate([[0], np.cumsum(m[r])[:-1]]).astype(int) for r in range(n)]
+                        rd = [np.concatenate([[0], np.cumsum(m[:, r])[:-1]]).astype(int) for r in range(n)]
+                        src = [mk(max(int(m[r].sum()), 1), 10 * step + r) for r in range(n)]
+                        dst = [Dev(max(int(m[:, r].sum()), 1), npdt, fill=0) for r in range(n)]
+                        args = [ca(kind, src[r], dst[r], dt=dt, src_counts=m[r], src_displs=sd[r], dst_counts=m[:, r], dst_displs=rd[r]) for r in range(n)]
+                        check = lambda src=src, dst=dst, m=m, sd=sd, n=n, what=what: [np.testing.assert_array_equal(dst[r].a[:int(m[:, r].sum())], np.concatenate([src[p_].a[sd[p_][r]:sd[p_][r] + m[p_][r]] for p_ in range(n)]), err_msg=str(what)) for r in range(n)]  # noqa: E731
+                    elif kind == "reduce_scatterv":
+                        counts = [int(rng.integers(0, blk + 1)) for _ in range(n)]
+                        offs = np.concatenate([[0], np.cumsum(counts)[:-1]]).astype(int)
+                        tot = max(sum(counts), 1)
+                        src = [mk(tot, 10 * step + r) for r in range(n)]; dst = [Dev(max(counts[r], 1), npdt, fill=0) for r in range(n)]
+                        args = [ca(kind, src[r], dst[r], dt=dt, op=op, count_src=sum(counts), dst_counts=counts, dst_displs=offs) for r in range(n)]
+                        exp = red([x.a.copy() for x in src])
+                        check = lambda dst=dst, exp=exp, counts=counts, offs=offs, n=n, what=what: [np.testing.assert_allclose(dst[r].a[:counts[r]], exp[offs[r]:offs[r] + counts[r]], rtol=1e-5, err_msg=str(what)) for r in range(n)]  # noqa: E731
                     elif kind == "bcast":
                         b = [mk(blk, 10 * step + 7) if r == root else Dev(blk, npdt, fill=0) for r in range(n)]
                         exp = b[root].a.copy()
