@@ -725,8 +725,19 @@ def coll_fuzz():
     (UCC_TL_NVL_SLOTS: consecutive collectives use consecutive heap images), always with a heap so small that large messages take several
     rounds; every result is checked against numpy."""
     kinds = ["allreduce", "allgather", "alltoall", "reduce_scatter", "bcast", "reduce", "barrier", "gather", "scatter", "allgatherv", "alltoallv", "reduce_scatterv"]
+    def random_tune(seed):
+        """a random (non-NVLS) algorithm for every collective type; what an algorithm declines goes down the score chain"""
+        g = np.random.default_rng(seed)
+        pick = lambda *names: names[int(g.integers(0, len(names)))]  # noqa: E731
+        return "#".join([f"allreduce:cuda:inf:@{pick('twoshot', 'oneshot', 'ring', 'rhd')}", f"reduce_scatter:cuda:inf:@{pick('twoshot', 'ring', 'rhd', 'oneshot')}",
+                         f"reduce_scatterv:cuda:inf:@{pick('twoshot', 'ring', 'oneshot')}", f"allgather:cuda:inf:@{pick('pull', 'ring', 'push', 'ce')}",
+                         f"allgatherv:cuda:inf:@{pick('pull', 'ring', 'push', 'ce')}", f"alltoall:cuda:inf:@{pick('pull', 'push', 'ce')}",
+                         f"alltoallv:cuda:inf:@{pick('pull', 'push', 'ce')}"])
     for mode, extra in (("staged", NOZC), ("zcopy", dict(ZC, UCC_TL_NVL_ZCOPY_THRESH="64K")), ("staged, 4 lanes", dict(NOZC, UCC_TL_NVL_SLOTS="4")),
-                        ("zcopy, 3 lanes", dict(ZC, UCC_TL_NVL_ZCOPY_THRESH="64K", UCC_TL_NVL_SLOTS="3"))):
+                        ("zcopy, 3 lanes", dict(ZC, UCC_TL_NVL_ZCOPY_THRESH="64K", UCC_TL_NVL_SLOTS="3")),
+                        ("zcopy, random algorithms A", dict(ZC, UCC_TL_NVL_ZCOPY_THRESH="0", UCC_TL_NVL_TUNE=random_tune(1))),
+                        ("zcopy, random algorithms B", dict(ZC, UCC_TL_NVL_ZCOPY_THRESH="64K", UCC_TL_NVL_TUNE=random_tune(int(os.environ.get("B200_FUZZ_TUNE", "2"))))),
+                        ("staged, random algorithms C", dict(NOZC, UCC_TL_NVL_TUNE=random_tune(3)))):
         with UccJob(4, env=dict(BASE, **extra)) as j:
             teams = [j.create_team(range(4)), j.create_team([3, 0, 2])]
             for seed in range(int(os.environ.get("B200_FUZZ_SEEDS", "4"))):
