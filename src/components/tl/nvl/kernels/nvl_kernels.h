@@ -148,6 +148,7 @@ typedef struct nvl_p2p_args {
     int            mode;   /* nvl_p2p_mode_t */
     uint32_t       rz_seq; /* NVL_P2P_PUSH / NVL_P2P_WAIT: index of this zero-copy message between the pair (in post order) */
     char          *remote; /* NVL_P2P_PUSH: the receiver's buffer, mapped here */
+    uint64_t       spin_ns;/* budget of a wait for the peer (0: no deadline) */
 } nvl_p2p_args_t;
 /* NVL_P2P_RING: through the pair's heap channel (eager: the sender never needs the receiver's address);
  * NVL_P2P_PUSH / NVL_P2P_WAIT: rendezvous - the receiver published its buffer, the sender's kernel stores into it directly and

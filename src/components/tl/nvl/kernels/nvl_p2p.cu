@@ -15,10 +15,19 @@
  * team's collectives - a send / recv can be in flight next to an allreduce of the same team. */
 #include "nvl_reduce_impl.cuh"
 
-static __device__ __forceinline__ void p2p_spin(const nvl_team_dev_t &t, nvl_ctrl_t *mine, const uint32_t *f, uint32_t target)
+/* Waiting for the OTHER side of a message is not bounded by anything the library controls - a receive may be posted long before
+ * its send (pre-posted receives of a pipeline stage) - so, like NCCL, the channel kernels wait without a deadline unless
+ * P2P_TIMEOUT is set (args.spin_ns != 0); the TIMEOUT of the collectives, whose members all launch the same kernel, does not apply */
+static __device__ __forceinline__ void p2p_spin(const nvl_p2p_args_t &a, nvl_ctrl_t *mine, const uint32_t *f, uint32_t target)
 {
-    BlockSync bs; bs.mine = mine;
-    bs.spin(t, f, target);
+    uint64_t t0 = 0; uint32_t spins = 0;
+    while ((int32_t)(ld_acquire_sys_u32(f) - target) < 0) {
+        if (a.spin_ns && (++spins & 0x3ff) == 0) {
+            uint64_t now = globaltimer_ns();
+            if (!t0) t0 = now;
+            else if (now - t0 > a.spin_ns) { if (a.team.host_err) *a.team.host_err = 1; mine->error = 1; break; }
+        }
+    }
 }
 
 /* CTA-wide copy of n bytes; `aligned` = both pointers 16-byte aligned.  PEER: the source is written by another GPU during the kernel */
@@ -63,7 +72,7 @@ __global__ void __launch_bounds__(NVL_THREADS_MAX) nvl_p2p_kernel(const __grid_c
             const uint32_t seq = tx0 + c;
             const size_t off = (size_t)c * per_chunk + (size_t)b * lane;
             const size_t n = off < a.bytes ? dmin(lane, a.bytes - off) : 0;
-            if (threadIdx.x == 0) p2p_spin(t, mine, &mine->p2p_ack[peer][b], seq + 1 - NVL_P2P_SLOTS);   /* ring slot free again */
+            if (threadIdx.x == 0) p2p_spin(a, mine, &mine->p2p_ack[peer][b], seq + 1 - NVL_P2P_SLOTS);   /* ring slot free again */
             __syncthreads();
             char *slot = ring + (size_t)(seq % NVL_P2P_SLOTS) * chunk + (size_t)b * lane;
             if (n) p2p_copy<false>(slot, ubuf + off, n, (((uintptr_t)(ubuf + off)) & 15) == 0);
@@ -78,7 +87,7 @@ __global__ void __launch_bounds__(NVL_THREADS_MAX) nvl_p2p_kernel(const __grid_c
             const uint32_t seq = rx0 + c;
             const size_t off = (size_t)c * per_chunk + (size_t)b * lane;
             const size_t n = off < a.bytes ? dmin(lane, a.bytes - off) : 0;
-            if (threadIdx.x == 0) p2p_spin(t, mine, &mine->p2p_head[peer][b], seq + 1);
+            if (threadIdx.x == 0) p2p_spin(a, mine, &mine->p2p_head[peer][b], seq + 1);
             __syncthreads();
             const char *slot = ring + (size_t)(seq % NVL_P2P_SLOTS) * chunk + (size_t)b * lane;
             if (n) p2p_copy<true>(ubuf + off, slot, n, (((uintptr_t)(ubuf + off)) & 15) == 0);
@@ -118,7 +127,7 @@ __global__ void __launch_bounds__(NVL_THREADS_MAX) nvl_p2p_push_kernel(const __g
 __global__ void __launch_bounds__(32) nvl_p2p_wait_kernel(const __grid_constant__ nvl_p2p_args_t a)
 {
     nvl_ctrl_t *mine = reinterpret_cast<nvl_ctrl_t *>(a.team.heap[a.team.rank]);
-    if (threadIdx.x == 0) p2p_spin(a.team, mine, &mine->p2p_rz_done[a.peer], a.rz_seq + 1);
+    if (threadIdx.x == 0) p2p_spin(a, mine, &mine->p2p_rz_done[a.peer], a.rz_seq + 1);
 }
 
 #ifndef NVL_HOST_EMU

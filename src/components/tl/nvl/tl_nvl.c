@@ -40,6 +40,9 @@ ucc_config_field_t ucc_tl_nvl_context_config_table[] = {
      "buffer, the sender's kernel stores straight into it over NVLink (no ring, no copy on the receiving GPU); smaller messages go through the "
      "pair's eager ring in the heap (two B200: the ring needs 8.7 us for 64 KB and 28.5 us for 1 MB, the rendezvous ~29 us for 1 MB, 48 us for 16 MB, "
      "209 us = 642 GB/s for 128 MB; NCCL 20 / 21.6 / 39.6 / 249 us)", ucc_offsetof(ucc_tl_nvl_context_config_t, p2p_rndv_thresh), UCC_CONFIG_TYPE_MEMUNITS},
+    {"P2P_TIMEOUT", "0", "How long a send / recv kernel waits for the other side before it gives up and the request fails with UCC_ERR_TIMED_OUT; 0 = no "
+     "deadline (a receive may legitimately be posted long before its send; NCCL waits forever, too).  TIMEOUT, the budget of the collectives, does not apply",
+     ucc_offsetof(ucc_tl_nvl_context_config_t, p2p_timeout), UCC_CONFIG_TYPE_TIME},
     {"SLOTS", "1", "Independent collective lanes per team (reference tl/cuda MAX_CONCURRENT): consecutive collectives use consecutive lanes and, when "
      "posted on different streams, overlap.  Every lane has its own control block, one-shot slots and SYMMETRIC_SIZE of staging space; one "
      "kernel may use at most (2 x SMs) / SLOTS thread blocks so that all lanes stay co-resident", ucc_offsetof(ucc_tl_nvl_context_config_t, slots), UCC_CONFIG_TYPE_UINT},

@@ -49,6 +49,7 @@ typedef struct ucc_tl_nvl_context_config {
     int      bulk;             /* ternary: TMA bulk copies (cp.async.bulk) as the data mover of the zero-copy push exchange */
     size_t   bulk_thresh;
     unsigned bulk_ctas;        /* one-warp CTAs of a bulk-copy kernel */
+    double   p2p_timeout;      /* seconds a send / recv kernel waits for the peer (0: forever) */
     size_t   p2p_rndv_thresh;  /* send / recv of at least this size: rendezvous (sender stores into the receiver's buffer) */
     unsigned slots;            /* independent collective lanes per team (reference tl/cuda MAX_CONCURRENT): collectives on different lanes may overlap */
 } ucc_tl_nvl_context_config_t;

@@ -795,6 +795,7 @@ static ucc_status_t xchg_init(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, 
         t->u.p2p.send = me == root; t->u.p2p.peer = (int)(me == r0 ? r1 : r0);
         t->nblocks = nvl_p2p_lanes(len);
         t->p2p_rndv = team->zcopy && len && len >= ctx->cfg.p2p_rndv_thresh;
+        t->u.p2p.spin_ns = (uint64_t)(ctx->cfg.p2p_timeout * 1e9);
         *task_p = &t->super;
         return UCC_OK;
     }

@@ -419,6 +419,50 @@ def p2p_active_set():
             print(f"  active-set p2p [{mode}] ok", flush=True)
 
 
+def p2p_late_sender():
+    """a receive posted seconds before its send: the channel kernels wait without a deadline (TIMEOUT = 1 s here applies to the
+    collectives only), the message arrives and the team's later collectives work; with P2P_TIMEOUT = 1 s the same receive fails"""
+    import time
+    n = 2
+    for p2p_to, expect_ok in (("0", True), ("1s", False)):
+        with UccJob(n, env=dict(BASE, **dict(NOZC, UCC_TL_NVL_TIMEOUT="1s", UCC_TL_NVL_P2P_TIMEOUT=p2p_to))) as j:
+            team = j.create_team(range(n))
+            src, dst = Dev(1000, fill=rnd(1000, 5)), Dev(1000, fill=0)
+            reqs = []
+            for r, b in ((0, src), (1, dst)):
+                a = ca("bcast", b, None, root=0, count_dst=0, active_set=(0, 1, 2), tag=1)
+                q = C.POINTER(U.ucc_coll_req_t)()
+                U.check(U.ucc_collective_init(C.byref(a), C.byref(q), team.members[r].team), "init")
+                reqs.append((a, q))
+            U.check(U.ucc_collective_post(reqs[1][1]), "post recv")
+            t0 = time.time()
+            while time.time() - t0 < 2.5:
+                for r in range(n):
+                    U.ucc_context_progress(j.procs[r].ctx)
+                time.sleep(0.01)
+            if expect_ok:
+                assert reqs[1][1].contents.status == U.UCC_INPROGRESS
+                U.check(U.ucc_collective_post(reqs[0][1]), "post send")
+                t0 = time.time()
+                while any(q.contents.status == U.UCC_INPROGRESS for _, q in reqs):
+                    for r in range(n):
+                        U.ucc_context_progress(j.procs[r].ctx)
+                    assert time.time() - t0 < 60
+                assert all(q.contents.status == U.UCC_OK for _, q in reqs)
+                assert np.array_equal(src.a, dst.a)
+                s2 = [Dev(100, fill=rnd(100, r)) for r in range(n)]
+                d2 = [Dev(100, fill=0) for _ in range(n)]
+                run(team, [ca("allreduce", s2[r], d2[r]) for r in range(n)])
+                assert np.allclose(d2[0].a, s2[0].a + s2[1].a)
+                for _, q in reqs:
+                    U.ucc_collective_finalize(q)
+            else:
+                assert reqs[1][1].contents.status == U.UCC_ERR_TIMED_OUT, reqs[1][1].contents.status
+                U.ucc_collective_finalize(reqs[1][1])
+                U.ucc_collective_finalize(reqs[0][1])
+    print("  p2p late sender ok", flush=True)
+
+
 def registered_buffers():
     """ucc_mem_map on device buffers + collectives that carry the GLOBAL handles: the zero-copy kernels get the members' buffers
     from the registrations - here with the exchange board switched OFF (UCC_TL_NVL_ZCOPY would normally need it), so a correct
@@ -696,6 +740,14 @@ def p2p_fuzz():
                     for _ in range(int(rng.integers(0, 4))):
                         for r in range(n):
                             U.ucc_context_progress(j.procs[r].ctx)
+                    if rng.integers(0, 8) == 0:   # a collective of the same team while messages are in flight (channels and collectives share nothing)
+                        cnt = int(rng.choice([5, 3000, 90000]))
+                        csrc = [Dev(cnt, fill=rnd(cnt, 7000 + len(pending) + r)) for r in range(n)]
+                        cdst = [Dev(cnt, fill=0) for _ in range(n)]
+                        cq = team.coll([ca("allreduce", csrc[r], cdst[r]) for r in range(n)])   # (no device-wide sync as in run(): receives may be parked)
+                        assert cq.run() == U.UCC_OK
+                        cq.finalize()
+                        assert np.allclose(cdst[int(rng.integers(0, n))].a, sum(x.a for x in csrc)), ("allreduce next to p2p traffic", thresh, seed)
                 t0 = time.time()
                 allq = [m[4][k][1] for m in msgs for k in ("send", "recv")]
                 while any(q.contents.status == U.UCC_INPROGRESS for q in allq):
@@ -881,7 +933,7 @@ SCENARIOS = {
     "triggered": lambda: [triggered(NOZC), triggered(ZC)],
     "timeout": device_timeout,
     "cross_team": lambda: [cross_team_order(NOZC), cross_team_order(ZC)],
-    "p2p": lambda: [p2p_active_set(), int_avg()],
+    "p2p": lambda: [p2p_active_set(), p2p_late_sender(), int_avg()],
     "p2p_fuzz": p2p_fuzz,
     "coll_fuzz": coll_fuzz,
     "memh": registered_buffers,
