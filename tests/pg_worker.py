@@ -51,6 +51,16 @@ def main():
         dist.send(torch.full((7,), float(rank), device=dev), nxt)
     if world % 2 == 0 or rank not in (0, world - 1):     # (odd rings would need non-blocking p2p to avoid the wrap-around wait)
         ok &= bool((got == float(prv)).all())
+    # batch_isend_irecv with the RECEIVE listed first on every rank (torch issues the ops one after the other): works on host tensors
+    # (tag-matched, non-blocking transport) and on CUDA tensors (the backend keeps one internal stream per peer and direction)
+    big, small = torch.zeros(70001, device=dev), torch.zeros(5, device=dev)
+    msg_b, msg_s = torch.full((70001,), float(rank + 1), device=dev), torch.full((5,), float(rank + 10), device=dev)
+    ops_ = [dist.P2POp(dist.irecv, big, prv), dist.P2POp(dist.irecv, small, prv), dist.P2POp(dist.isend, msg_b, nxt), dist.P2POp(dist.isend, msg_s, nxt)]
+    for w in dist.batch_isend_irecv(ops_):
+        w.wait()
+    if use_cuda:
+        torch.cuda.synchronize()
+    ok &= bool((big == float(prv + 1)).all()) and bool((small == float(prv + 10)).all())
     # torch's own DDP on top of the backend
     torch.manual_seed(0)
     model = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.ReLU(), torch.nn.Linear(32, 4)).to(dev)

@@ -29,9 +29,10 @@ def _op(o):
 
 
 class _Work(dist._Work):
-    def __init__(self, pg, reqs, result, cuda):
+    def __init__(self, pg, reqs, result, cuda, side_stream=None):
         super().__init__()
         self._pg, self._reqs, self._result, self._cuda = pg, reqs, result, cuda
+        self._side = side_stream      # CUDA p2p runs on an internal stream; wait() makes the caller's stream wait for it
         self._fut = torch.futures.Future()
         self._done = False
 
@@ -44,6 +45,8 @@ class _Work(dist._Work):
             else:
                 r.wait_posted()     # the kernel is in the stream (idempotent; immediate for everything but p2p)
             r.finalize_later() if self._cuda else r.finalize()
+        if self._side is not None:
+            torch.cuda.current_stream().wait_stream(self._side)
         self._done = True
         self._fut.set_result(self._result)
 
@@ -70,6 +73,7 @@ class ProcessGroupUCCB200(dist.ProcessGroup):
         super().__init__(rank, size)
         self._comm = Communicator(store=store, rank=rank, size=size)
         self._pending = []   # CUDA requests whose kernels are in flight; finalized lazily
+        self._p2p_streams = {}
 
     def getBackendName(self):
         return "ucc_b200"
@@ -175,7 +179,22 @@ class ProcessGroupUCCB200(dist.ProcessGroup):
         reqs = [self._comm.coll_init("bcast", t, None, root=src, active_set=(src, dst - src, 2), tag=int(tag) & 0x3fff) for t in tensors]
         # rendezvous: a large send enters the stream when the receiver has published its buffer, a receive is published when the
         # stream reaches it - both need progress, which Work.wait() provides (isend + irecv + wait, as with every backend)
-        return self._run(reqs, tensors, tensors, wait_posted=False)
+        if not (tensors and tensors[0].is_cuda):
+            return self._run(reqs, tensors, tensors, wait_posted=False)
+        # CUDA: one internal stream per (peer, direction), as ProcessGroupNCCL keeps per-peer streams - a kernel of the eager ring
+        # may wait for its peer (a receive posted before its send), and torch issues the ops of batch_isend_irecv one after the
+        # other on the caller's stream: an irecv in front of an isend there would deadlock a ring of ranks
+        peer, is_send = (dst, True) if src == self.rank() else (src, False)
+        side = self._p2p_streams.get((peer, is_send))
+        if side is None:
+            side = self._p2p_streams[(peer, is_send)] = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        for r, t in zip(reqs, tensors):
+            r.post_on_stream(side, wait_posted=False)
+            r.finalize_later = lambda r=r: self._pending.append(r)
+            t.record_stream(side)
+        self._reap()
+        return _Work(self, reqs, tensors, True, side_stream=side)
 
     def send(self, tensors, dstRank, tag=0):
         return self._p2p(tensors, self.rank(), dstRank, tag)
