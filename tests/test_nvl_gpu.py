@@ -21,7 +21,8 @@ TDT = {"float32": torch.float32, "float64": torch.float64, "float16": torch.floa
 # zero-copy kernels (members' user buffers used in place) forced for every size / never used
 ZC = {"UCC_TL_NVL_ZCOPY": "y", "UCC_TL_NVL_ZCOPY_THRESH": "0"}
 NOZC = {"UCC_TL_NVL_ZCOPY": "n"}
-ENV = {"UCC_TL_NVL_MAX_BLOCKS": "4", "UCC_TL_NVL_TIMEOUT": "5s", "UCC_TL_NVL_SYMMETRIC_SIZE": "8Mb"}
+ENV = {"UCC_TL_NVL_MAX_BLOCKS": "4", "UCC_TL_NVL_TIMEOUT": "5s", "UCC_TL_NVL_SYMMETRIC_SIZE": "8Mb",
+       "UCC_TL_NVL_P2P_TIMEOUT": "20s"}   # (send / recv kernels wait without a deadline by default: keep a hang from eating the whole run)
 
 
 def need_cuda():
