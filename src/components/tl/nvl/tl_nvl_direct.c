@@ -23,7 +23,9 @@ ucc_status_t ucc_tl_nvl_xb_create(ucc_tl_nvl_team_t *team)
     static uint32_t counter = 0;
     void *addr = NULL;
     ucc_status_t st;
-    snprintf(team->xb_name, sizeof(team->xb_name), "/ucc_b200_nvlxb.%d.%u", (int)getpid(), ucc_atomic_fadd32(&counter, 1));
+    uint32_t my = ucc_atomic_fadd32(&counter, 1);
+    if (my == 0) ucc_shm_reap_stale("ucc_b200_nvlxb.");
+    snprintf(team->xb_name, sizeof(team->xb_name), "/ucc_b200_nvlxb.%d.%u", (int)getpid(), my);
     st = ucc_shm_create(team->xb_name, sizeof(nvl_xb_seg_t), &addr);
     if (st != UCC_OK) { team->xb_name[0] = 0; return st; }
     memset(addr, 0, sizeof(nvl_xb_seg_t));

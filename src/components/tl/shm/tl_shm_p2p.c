@@ -70,6 +70,7 @@ ucc_status_t ucc_tl_shm_ctx_p2p_init(ucc_tl_shm_context_t *ctx)
 #ifdef PR_SET_PTRACER
     if (ctx->cfg.cma != UCC_NO) prctl(PR_SET_PTRACER, PR_SET_PTRACER_ANY, 0, 0, 0); /* yama ptrace_scope=1: let the peers read my buffers */
 #endif
+    if (my_seq == 0) ucc_shm_reap_stale("ucc_b200.");   /* first context of the process: collect the rings of processes that died without cleanup */
     snprintf(ctx->addr.name, sizeof(ctx->addr.name), "/ucc_b200.%d.%u.%llx", (int)getpid(), my_seq, (unsigned long long)(ctx->addr.ep_id & 0xffffff));
     st = ucc_shm_create(ctx->addr.name, ctx->ring_len, (void **)&ctx->ring);
     if (st != UCC_OK) { ucc_shm_unlink(ctx->addr.name); st = ucc_shm_create(ctx->addr.name, ctx->ring_len, (void **)&ctx->ring); }

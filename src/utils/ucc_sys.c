@@ -2,11 +2,15 @@
 #include "ucc_log.h"
 #include "ucc_string.h"
 #include "ucc_time.h"
+#include <dirent.h>
 #include <dlfcn.h>
 #include <errno.h>
 #include <fcntl.h>
 #include <libgen.h>
 #include <poll.h>
+#include <pthread.h>
+#include <signal.h>
+#include <sys/file.h>
 #include <sys/ipc.h>
 #include <sys/mman.h>
 #include <sys/shm.h>
@@ -39,6 +43,26 @@ ucc_status_t ucc_sysv_attach(int shmid, void **addr)
 }
 ucc_status_t ucc_sysv_free(void *addr) { return shmdt(addr) == 0 ? UCC_OK : UCC_ERR_INVALID_PARAM; }
 
+/* The creator of a named segment keeps its descriptor open with a shared flock until it unlinks the name: the kernel drops the lock
+ * when the process dies, however it dies, and the lock is visible across pid namespaces - the liveness proof ucc_shm_reap_stale needs */
+static struct { char name[64]; int fd; } shm_owned[256];
+static pthread_mutex_t shm_owned_lock = PTHREAD_MUTEX_INITIALIZER;
+static void shm_owned_add(const char *name, int fd)
+{
+    pthread_mutex_lock(&shm_owned_lock);
+    for (size_t i = 0; i < sizeof(shm_owned) / sizeof(shm_owned[0]); i++)
+        if (!shm_owned[i].name[0]) { snprintf(shm_owned[i].name, sizeof(shm_owned[i].name), "%s", name); shm_owned[i].fd = fd; fd = -1; break; }
+    pthread_mutex_unlock(&shm_owned_lock);
+    if (fd >= 0) close(fd);   /* table full: the segment simply is not protected by a lock (its pid still is checked) */
+}
+static void shm_owned_drop(const char *name)
+{
+    pthread_mutex_lock(&shm_owned_lock);
+    for (size_t i = 0; i < sizeof(shm_owned) / sizeof(shm_owned[0]); i++)
+        if (shm_owned[i].name[0] && !strcmp(shm_owned[i].name, name)) { close(shm_owned[i].fd); shm_owned[i].name[0] = 0; break; }
+    pthread_mutex_unlock(&shm_owned_lock);
+}
+
 ucc_status_t ucc_shm_create(const char *name, size_t size, void **addr)
 {
     int   fd = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
@@ -46,8 +70,8 @@ ucc_status_t ucc_shm_create(const char *name, size_t size, void **addr)
     if (fd < 0) { ucc_debug("shm_open(%s, create) failed: %s", name, strerror(errno)); return UCC_ERR_NO_RESOURCE; }
     if (ftruncate(fd, (off_t)size) != 0) { close(fd); shm_unlink(name); return UCC_ERR_NO_MEMORY; }
     p = mmap(NULL, size, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
-    close(fd);
-    if (p == MAP_FAILED) { shm_unlink(name); return UCC_ERR_NO_MEMORY; }
+    if (p == MAP_FAILED) { close(fd); shm_unlink(name); return UCC_ERR_NO_MEMORY; }
+    if (flock(fd, LOCK_SH | LOCK_NB) == 0) shm_owned_add(name, fd); else close(fd);
     *addr = p; return UCC_OK;
 }
 ucc_status_t ucc_shm_attach(const char *name, size_t size, void **addr)
@@ -63,7 +87,38 @@ ucc_status_t ucc_shm_attach(const char *name, size_t size, void **addr)
     *addr = p; return UCC_OK;
 }
 ucc_status_t ucc_shm_detach(void *addr, size_t size) { return munmap(addr, size) == 0 ? UCC_OK : UCC_ERR_INVALID_PARAM; }
-ucc_status_t ucc_shm_unlink(const char *name) { return shm_unlink(name) == 0 ? UCC_OK : UCC_ERR_NOT_FOUND; }
+ucc_status_t ucc_shm_unlink(const char *name) { shm_owned_drop(name); return shm_unlink(name) == 0 ? UCC_OK : UCC_ERR_NOT_FOUND; }
+
+/* Named POSIX segments survive a process that dies without its destructors (SIGKILL, a crash, a job scheduler's timeout).  Every
+ * segment name of this library starts with `prefix` followed by the owner's pid: remove the ones whose owner no longer exists.
+ * (The reference uses SysV segments marked IPC_RMID right after creation; POSIX names have to stay visible until the peers have
+ * attached, which may be at any later team creation, hence this reaper.)  Returns the number of segments removed. */
+int ucc_shm_reap_stale(const char *prefix)
+{
+    const char *dir = "/dev/shm";
+    size_t plen = strlen(prefix);
+    struct dirent *de;
+    DIR *d = opendir(dir);
+    int n = 0;
+    if (!d) return 0;
+    while ((de = readdir(d)) != NULL) {
+        char name[300]; char *e; long pid;
+        if (strncmp(de->d_name, prefix, plen)) continue;
+        pid = strtol(de->d_name + plen, &e, 10);
+        if (e == de->d_name + plen || pid <= 0 || (*e != '.' && *e != '\0')) continue;
+        if (kill((pid_t)pid, 0) == 0 || errno != ESRCH) continue;        /* alive (or not ours to judge) */
+        snprintf(name, sizeof(name), "/%s", de->d_name);
+        {   /* a pid of another pid namespace looks dead from here: the owner's flock is the second proof */
+            int fd = shm_open(name, O_RDWR, 0600);
+            if (fd < 0) continue;
+            if (flock(fd, LOCK_EX | LOCK_NB) == 0 && shm_unlink(name) == 0) n++;
+            close(fd);
+        }
+    }
+    closedir(d);
+    if (n) ucc_debug("removed %d shared-memory segments of dead processes (%s*)", n, prefix);
+    return n;
+}
 
 const char *ucc_sys_get_lib_path(void)
 {

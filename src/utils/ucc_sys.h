@@ -9,6 +9,7 @@ ucc_status_t ucc_shm_create(const char *name, size_t size, void **addr);   /* PO
 ucc_status_t ucc_shm_attach(const char *name, size_t size, void **addr);
 ucc_status_t ucc_shm_detach(void *addr, size_t size);
 ucc_status_t ucc_shm_unlink(const char *name);
+int          ucc_shm_reap_stale(const char *prefix); /* unlink /dev/shm/<prefix><pid>... whose pid is dead; returns how many */
 const char  *ucc_sys_get_lib_path(void);   /* absolute path of the .so containing this function */
 const char  *ucc_sys_dirname_of_lib(void);
 uint64_t     ucc_sys_host_hash(void);

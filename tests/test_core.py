@@ -498,3 +498,31 @@ def test_config_file_team_sections(tmp_path):
     sel = lambda t: [ln for ln in t.splitlines() if "allreduce host:" in ln and "TL_SHM" in ln]  # noqa: E731
     assert sel(first) and all(":ring" in ln and ":dbt" not in ln for ln in sel(first)), first[-1500:]
     assert sel(second) and all(":dbt" in ln for ln in sel(second)), second[-1500:]
+
+
+def test_stale_shared_memory_segments_are_reaped():
+    """A process killed with SIGKILL cannot unlink its named POSIX segments.  The first context of a later process removes the
+    segments whose owner is dead (pid gone AND the owner's flock gone), and never those of a live process (src/utils/ucc_sys.c
+    ucc_shm_reap_stale; the reference avoids the problem with SysV segments marked IPC_RMID at creation)."""
+    import glob
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PYTHONPATH=root)
+    child = ("from ucc_b200.harness import UccJob\nimport time\nj = UccJob(2, env={'UCC_TLS': 'shm,self'}); t = j.create_team(range(2))\n"
+             "print('UP', flush=True); time.sleep(120)")
+    other = "from ucc_b200.harness import UccJob\nj = UccJob(2, env={'UCC_TLS': 'shm,self'}); j.cleanup()"
+    p = subprocess.Popen([sys.executable, "-c", child], stdout=subprocess.PIPE, text=True, env=env)
+    try:
+        assert p.stdout.readline().strip() == "UP"
+        mine = lambda: glob.glob(f"/dev/shm/ucc_b200.{p.pid}.*")   # noqa: E731
+        assert len(mine()) == 2
+        subprocess.run([sys.executable, "-c", other], check=True, env=env, timeout=120)
+        assert len(mine()) == 2, "segments of a LIVE process were removed"
+    finally:
+        p.kill()
+        p.wait()
+    assert len(mine()) == 2          # SIGKILL: nobody cleaned up
+    subprocess.run([sys.executable, "-c", other], check=True, env=env, timeout=120)
+    assert mine() == []
