@@ -106,6 +106,8 @@ cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t st) { S(st)->
 cudaError_t cudaDeviceSynchronize(void)
 { std::vector<EmuStream *> all; { std::lock_guard<std::mutex> l(g_lock); all = g_streams; } for (auto *s : all) s->sync(); return cudaSuccess; }
 
+/* leak checks of the tests: objects currently alive (what = 0 streams, 1 events, 2 device / pinned allocations) */
+long emu_live_objects(int what);
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { auto *e = new EmuStream(); { std::lock_guard<std::mutex> l(g_lock); g_streams.push_back(e); } *s = reinterpret_cast<cudaStream_t>(e); return cudaSuccess; }
 cudaError_t cudaStreamCreate(cudaStream_t *s) { return cudaStreamCreateWithFlags(s, 0); }
 cudaError_t cudaStreamDestroy(cudaStream_t s)
@@ -114,9 +116,12 @@ cudaError_t cudaStreamSynchronize(cudaStream_t s) { S(s)->sync(); return cudaSuc
 cudaError_t cudaStreamQuery(cudaStream_t s) { auto *e = S(s); std::lock_guard<std::mutex> l(e->m); return e->q.empty() && !e->busy ? cudaSuccess : cudaErrorNotReady; }
 cudaError_t cudaStreamIsCapturing(cudaStream_t, cudaStreamCaptureStatus *st) { *st = cudaStreamCaptureStatusNone; return cudaSuccess; }
 
-cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { *e = reinterpret_cast<cudaEvent_t>(new EmuEvent()); return cudaSuccess; }
+static std::atomic<long> g_live_events{0};
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { *e = reinterpret_cast<cudaEvent_t>(new EmuEvent()); g_live_events++; return cudaSuccess; }
 cudaError_t cudaEventCreate(cudaEvent_t *e) { return cudaEventCreateWithFlags(e, 0); }
-cudaError_t cudaEventDestroy(cudaEvent_t e) { delete reinterpret_cast<EmuEvent *>(e); return cudaSuccess; }   // (callers destroy only completed events)
+cudaError_t cudaEventDestroy(cudaEvent_t e) { delete reinterpret_cast<EmuEvent *>(e); g_live_events--; return cudaSuccess; }   // (callers destroy only completed events)
+long emu_live_objects(int what)
+{ std::lock_guard<std::mutex> l(g_lock); return what == 0 ? (long)g_streams.size() : what == 1 ? g_live_events.load() : (long)g_allocs.size(); }
 cudaError_t cudaEventRecord(cudaEvent_t ev, cudaStream_t s)
 { auto *e = reinterpret_cast<EmuEvent *>(ev); uint64_t seq = ++e->recorded; S(s)->push([e, seq] { uint64_t c = e->completed.load(); while (c < seq && !e->completed.compare_exchange_weak(c, seq)) {} }); return cudaSuccess; }
 cudaError_t cudaEventQuery(cudaEvent_t ev) { auto *e = reinterpret_cast<EmuEvent *>(ev); return e->completed.load() >= e->recorded.load() ? cudaSuccess : fail(cudaErrorNotReady); }

@@ -27,7 +27,10 @@ NOZC = {"UCC_TL_NVL_ZCOPY": "n"}
 class Dev:
     """numpy view of a buffer allocated with the emulated cudaMalloc"""
 
+    created = 0     # (buffers are never freed: leak checks subtract this)
+
     def __init__(self, n, dtype=np.float32, fill=None):
+        Dev.created += 1
         p = C.c_void_p()
         nbytes = max(n, 1) * np.dtype(dtype).itemsize
         assert rt.cudaMalloc(C.byref(p), C.c_size_t(nbytes)) == 0
@@ -921,6 +924,57 @@ def coll_fuzz():
         print(f"  collective fuzz [{mode}] ok", flush=True)
 
 
+def resource_cycles():
+    """team / context life cycle of the tl/nvl plugin: jobs and teams (random subsets, zero-copy boards, p2p side streams, EEs) created,
+    used and destroyed many times - file descriptors, POSIX segments and emulated device allocations must not accumulate"""
+    import glob
+    rt.cudaStreamCreate.argtypes = [C.POINTER(C.c_void_p)]
+
+    def nfd():
+        return len(os.listdir("/proc/self/fd"))
+
+    def cycle(i):
+        rng = np.random.default_rng(i)
+        with UccJob(4, env=dict(BASE, **dict(ZC, UCC_TL_NVL_P2P_RNDV_THRESH="64K"))) as j:
+            for _ in range(3):
+                ranks = sorted(rng.choice(4, size=int(rng.integers(2, 5)), replace=False).tolist())
+                team = j.create_team(ranks)
+                n = len(ranks)
+                src = [Dev(30000, fill=rnd(30000, r)) for r in range(n)]
+                dst = [Dev(30000, fill=0) for _ in range(n)]
+                run(team, [ca("allreduce", src[r], dst[r]) for r in range(n)])
+                assert np.allclose(dst[0].a, sum(x.a for x in src))
+                big_s, big_d = Dev(40000, fill=rnd(40000, 9)), Dev(40000, fill=0)      # one rendezvous message: side stream + board entry
+                reqs = []
+                for r, b in ((0, big_s), (1, big_d)):
+                    a = ca("bcast", b, None, root=0, count_dst=0, active_set=(0, 1, 2), tag=1)
+                    q = C.POINTER(U.ucc_coll_req_t)()
+                    U.check(U.ucc_collective_init(C.byref(a), C.byref(q), team.members[r].team), "init")
+                    U.check(U.ucc_collective_post(q), "post")
+                    reqs.append((a, q))
+                while any(q.contents.status == U.UCC_INPROGRESS for _, q in reqs):
+                    for p_ in j.procs:
+                        p_.progress()
+                for _, q in reqs:
+                    assert q.contents.status == U.UCC_OK
+                    U.ucc_collective_finalize(q)
+                assert np.array_equal(big_s.a, big_d.a)
+                team.destroy()
+    rt.emu_live_objects.restype = C.c_long
+    live = lambda: tuple(rt.emu_live_objects(k) for k in range(3))   # noqa: E731  streams, events, allocations of the emulated runtime
+    for i in range(3):
+        cycle(i)
+    f0, s0, l0, d0 = nfd(), len(glob.glob(f"/dev/shm/ucc_b200*.{os.getpid()}.*")), live(), Dev.created
+    for i in range(3, 15):
+        cycle(i)
+    f1, s1, l1, d1 = nfd(), len(glob.glob(f"/dev/shm/ucc_b200*.{os.getpid()}.*")), live(), Dev.created
+    assert f1 <= f0 + 2, ("file descriptors leak", f0, f1)
+    assert s1 <= s0, ("shared-memory segments leak", s0, s1)
+    assert l1[0] <= l0[0] and l1[1] <= l0[1], ("CUDA streams / events leak", l0, l1)
+    assert l1[2] - l0[2] <= d1 - d0, ("device / pinned allocations leak (beyond the test's own, never freed, buffers)", l0, l1, d1 - d0)
+    print(f"  resource cycles ok (fds {f0} -> {f1}, segments {s0} -> {s1}, streams / events / allocations {l0} -> {l1})", flush=True)
+
+
 SCENARIOS = {
     "defaults": default_selection,
     "allreduce": lambda: [allreduce_suite(a, e) for a, e in (("oneshot", NOZC), ("twoshot", NOZC), ("twoshot", ZC), ("ring", NOZC), ("rhd", NOZC))],
@@ -929,7 +983,7 @@ SCENARIOS = {
     "colls_push": lambda: other_colls(ZC, "allgather:cuda:inf:@push#allgatherv:cuda:inf:@push#alltoall:cuda:inf:@push#alltoallv:cuda:inf:@push#reduce_scatter:cuda:inf:@oneshot#reduce_scatterv:cuda:inf:@oneshot"),
     "colls_ce": lambda: other_colls(ZC, "allgather:cuda:inf:@ce#allgatherv:cuda:inf:@ce#alltoall:cuda:inf:@ce#alltoallv:cuda:inf:@ce"),
     "colls_ring": lambda: other_colls(NOZC, "allgather:cuda:inf:@ring#allgatherv:cuda:inf:@ring#reduce_scatter:cuda:inf:@ring#reduce_scatterv:cuda:inf:@ring"),
-    "misc": lambda: [mc_lifecycle(), persistent_and_teams(), asymmetric_memory()],
+    "misc": lambda: [mc_lifecycle(), resource_cycles(), persistent_and_teams(), asymmetric_memory()],
     "triggered": lambda: [triggered(NOZC), triggered(ZC)],
     "timeout": device_timeout,
     "cross_team": lambda: [cross_team_order(NOZC), cross_team_order(ZC)],
