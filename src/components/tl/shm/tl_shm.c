@@ -96,8 +96,7 @@ static ucc_status_t shm_task_setup(ucc_tl_shm_task_t *t)
         t->vmap.type = UCC_EP_MAP_STRIDED; t->vmap.ep_num = a->active_set.size; t->vmap.strided.start = a->active_set.start; t->vmap.strided.stride = a->active_set.stride;
         t->vsize = (ucc_rank_t)a->active_set.size; t->vrank = ucc_ep_map_local_rank(t->vmap, rank);
         if (t->vrank == UCC_RANK_INVALID) return UCC_ERR_INVALID_PARAM;
-        t->team->seq_num--;
-        t->coll_seq = 0xC000u | ((a->mask & UCC_COLL_ARGS_FIELD_TAG) ? (a->tag & 0x3fff) : 0);
+        t->coll_seq = 0xC000u | ((a->mask & UCC_COLL_ARGS_FIELD_TAG) ? (a->tag & 0x3fff) : 0);   /* (the caller takes the team sequence back) */
     }
     return UCC_OK;
 }
@@ -110,7 +109,12 @@ static ucc_status_t shm_coll_init_alg(ucc_base_coll_args_t *bargs, ucc_base_team
     st = shm_task_setup(t);
     t->build = fn;
     if (st == UCC_OK) st = fn(t);
+    /* task_alloc advanced the team sequence.  A task that is not created gives it back - and so does an active-set task, which only
+     * some members create (the others must not fall behind): exactly ONE decrement in either case.  (It used to be taken back in
+     * shm_task_setup AND here when the algorithm then declined the active set - sag_knomial, the default for bcasts >= 32 KB, does -
+     * so the members of such a bcast ran one sequence number behind the rest of the team afterwards.) */
     if (st != UCC_OK) { t->team->seq_num--; ucc_tl_shm_task_finalize(&t->super); return st; }
+    if (UCC_COLL_ARGS_ACTIVE_SET(&bargs->args)) t->team->seq_num--;
     *task_p = &t->super;
     return UCC_OK;
 }

@@ -222,6 +222,44 @@ def test_active_set_bcast():
         assert np.all(dst[3] == n)
 
 
+def test_active_set_bcast_large_keeps_team_sequence():
+    """An active-set bcast whose size selects an algorithm that declines active sets (sag_knomial, the default from 32 KB) falls back to
+    the knomial tree - and must leave the team's collective sequence untouched on its members: the declined attempt used to take the
+    sequence number back twice, after which the members' messages of the next full-team collectives no longer matched the others'
+    (found by the random-program test).  Default algorithms, 100 KB, then ring allreduce + reduce_scatter in flight together."""
+    n = 6
+    with UccJob(n, env={"UCC_TLS": "shm,self"}) as j:
+        team = j.create_team()
+        for start, stride, size, root in ((1, 2, 3, 3), (0, 1, 2, 0)):
+            members = [start + i * stride for i in range(size)]
+            bufs = {r: (np.arange(25000, dtype=np.int32) + root if r == root else np.zeros(25000, np.int32)) for r in members}
+            reqs = []
+            for r in members:
+                a = coll_args("bcast", bufs[r], None, dt="int32", root=root, active_set=(start, stride, size), tag=9)
+                q = C.POINTER(U.ucc_coll_req_t)()
+                assert U.ucc_collective_init(C.byref(a), C.byref(q), team.members[r].team) == U.UCC_OK
+                reqs.append((q, a))
+            for q, _ in reqs:
+                assert U.ucc_collective_post(q) == U.UCC_OK
+            t0 = time.time()
+            while any(q.contents.status == U.UCC_INPROGRESS for q, _ in reqs) and time.time() - t0 < 20:
+                j.progress()
+            for q, _ in reqs:
+                assert q.contents.status == U.UCC_OK
+                U.ucc_collective_finalize(q)
+            for r in members:
+                assert np.array_equal(bufs[r], np.arange(25000, dtype=np.int32) + root)
+            # two full-team collectives in flight: their messages are told apart by the sequence number only
+            s1 = [np.full(30000, r + 1.0) for r in range(n)]; d1 = [np.zeros(30000) for _ in range(n)]
+            s2 = [np.full(6000 * n, r + 2.0) for r in range(n)]; d2 = [np.zeros(6000) for _ in range(n)]
+            q1 = team.coll([coll_args("allreduce", s1[r], d1[r], dt="float64") for r in range(n)])
+            q2 = team.coll([coll_args("reduce_scatter", s2[r], d2[r], dt="float64") for r in range(n)])
+            q1.post(); q2.post()
+            assert q1.wait() == U.UCC_OK and q2.wait() == U.UCC_OK
+            q1.finalize(); q2.finalize()
+            assert all(np.all(d == n * (n + 1) / 2) for d in d1) and all(np.all(d == n * (n + 3) / 2) for d in d2)
+
+
 def test_callback_on_completion():
     with UccJob(2) as j:
         team = j.create_team()

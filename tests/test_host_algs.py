@@ -297,6 +297,46 @@ def _random_program(teams, rng, tune, steps=50):
         mk = lambda c: rng.integers(0, 50, c).astype(npdt)                                           # noqa: E731
         red = {"sum": lambda a: np.sum(a, 0), "max": lambda a: np.max(a, 0), "min": lambda a: np.min(a, 0)}[op]
         eq = lambda got, exp, what=what: np.testing.assert_allclose(got, exp, rtol=1e-6, err_msg=str((tune, what)))   # noqa: E731
+        if rng.integers(0, 8) == 0 and n >= 3:
+            # active-set broadcasts (the send / recv and sub-group bcast shape): up to three with different tags in flight, random
+            # start / stride / size / root; only the members take part (reference test/gtest/active_set/test_active_set.cc)
+            import ctypes as C
+            retire(0)
+            sets = []
+            for k in range(int(rng.integers(1, 4))):
+                size = int(rng.integers(2, n + 1))
+                stride = int(rng.choice([1, 1, 2, -1])) if size * 2 <= n + 1 else int(rng.choice([1, -1]))
+                span = (size - 1) * abs(stride)
+                if span >= n:
+                    stride, span = (1 if stride > 0 else -1), size - 1
+                start = int(rng.integers(0, n - span)) + (span if stride < 0 else 0)
+                members = [start + i * stride for i in range(size)]
+                root = members[int(rng.integers(0, size))]
+                cnt = int(rng.choice([1, 33, 5000, 70001]))
+                bufs = {r: (mk(cnt) if r == root else np.zeros(cnt, npdt)) for r in members}
+                exp = bufs[root].copy()
+                reqs = []
+                for r in members:
+                    a = coll_args("bcast", bufs[r], None, dt=dt, root=root, active_set=(start, stride, size), tag=100 + k)
+                    q = C.POINTER(U.ucc_coll_req_t)()
+                    assert U.ucc_collective_init(C.byref(a), C.byref(q), team.members[r].team) == U.UCC_OK, (tune, what, members)
+                    reqs.append((q, a))
+                sets.append((members, bufs, exp, reqs))
+            for _, _, _, reqs in sets:
+                for q, _ in reqs:
+                    assert U.ucc_collective_post(q) == U.UCC_OK
+            import time
+            t0 = time.time()
+            while any(q.contents.status == U.UCC_INPROGRESS for *_, reqs in sets for q, _ in reqs):
+                team.job.progress()
+                assert time.time() - t0 < 60, (tune, what, "active set")
+            for members, bufs, exp, reqs in sets:
+                for q, _ in reqs:
+                    assert q.contents.status == U.UCC_OK, (tune, what, members)
+                    U.ucc_collective_finalize(q)
+                for r in members:
+                    eq(bufs[r], exp)
+            continue
         if kind in ("allreduce", "allgather", "alltoall") and rng.integers(0, 5) == 0:
             # persistent request: posted three times, new input every time
             retire(0)
