@@ -274,7 +274,8 @@ def test_alltoall_onesided_registered_destinations(n, capfd):
 
 def _random_program(teams, rng, tune, steps=50):
     """`steps` random collectives on randomly chosen teams of `teams`, up to three outstanding, each checked against numpy"""
-    kinds = ["allreduce", "allgather", "alltoall", "reduce_scatter", "bcast", "reduce", "barrier", "gather", "scatter", "allgatherv", "alltoallv"]
+    kinds = ["allreduce", "allgather", "alltoall", "reduce_scatter", "bcast", "reduce", "barrier", "gather", "scatter", "allgatherv", "alltoallv",
+             "gatherv", "scatterv", "reduce_scatterv", "fanin", "fanout"]
     window = []
 
     def retire(k):
@@ -422,6 +423,30 @@ def _random_program(teams, rng, tune, steps=50):
             big = mk(blk * n); outs = [np.zeros(blk, npdt) for _ in range(n)]
             args = [coll_args(kind, big if r == root else None, outs[r], dt=dt, root=root, count_src=blk * n) for r in range(n)]
             check = lambda big=big, outs=outs, blk=blk, n=n, eq=eq: [eq(outs[r], big[r * blk:(r + 1) * blk]) for r in range(n)]  # noqa: E731
+        elif kind in ("gatherv", "scatterv"):
+            counts = [int(rng.integers(0, blk + 1)) for _ in range(n)]
+            displs = np.concatenate([[0], np.cumsum(counts)[:-1]]).astype(int)
+            tot = max(sum(counts), 1)
+            if kind == "gatherv":
+                src = [mk(max(counts[r], 1)) for r in range(n)]; g = np.zeros(tot, npdt)
+                args = [coll_args(kind, src[r], g if r == root else None, dt=dt, root=root, count_src=counts[r], dst_counts=counts, dst_displs=displs) for r in range(n)]
+                exp = np.concatenate([src[r][:counts[r]] for r in range(n)]) if sum(counts) else np.zeros(0, npdt)
+                check = lambda g=g, exp=exp, eq=eq, t_=sum(counts): eq(g[:t_], exp)                       # noqa: E731
+            else:
+                big = mk(tot); outs = [np.zeros(max(counts[r], 1), npdt) for r in range(n)]
+                args = [coll_args(kind, big if r == root else None, outs[r], dt=dt, root=root, count_dst=counts[r], src_counts=counts, src_displs=displs) for r in range(n)]
+                check = lambda big=big, outs=outs, counts=counts, displs=displs, n=n, eq=eq: [eq(outs[r][:counts[r]], big[displs[r]:displs[r] + counts[r]]) for r in range(n)]  # noqa: E731
+        elif kind == "reduce_scatterv":
+            counts = [int(rng.integers(0, blk + 1)) for _ in range(n)]
+            displs = np.concatenate([[0], np.cumsum(counts)[:-1]]).astype(int)
+            tot = max(sum(counts), 1)
+            src = [mk(tot) for _ in range(n)]; dst = [np.zeros(max(counts[r], 1), npdt) for r in range(n)]
+            args = [coll_args(kind, src[r], dst[r], dt=dt, op=op, count_src=sum(counts), dst_counts=counts, dst_displs=displs) for r in range(n)]
+            exp = red(src)
+            check = lambda dst=dst, exp=exp, counts=counts, displs=displs, n=n, eq=eq: [eq(dst[r][:counts[r]], exp[displs[r]:displs[r] + counts[r]]) for r in range(n)]  # noqa: E731
+        elif kind in ("fanin", "fanout"):
+            args = [coll_args(kind, root=root) for _ in range(n)]
+            check = lambda: None                                                                     # noqa: E731
         else:
             args = [coll_args("barrier") for _ in range(n)]
             check = lambda: None                                                                     # noqa: E731
