@@ -219,6 +219,50 @@ ucc_status_t ucc_topo_get_all_nodes(ucc_topo_t *topo, ucc_sbgp_t **sbgps, int *n
     if (!topo->all_nodes) UCC_CHECK_RET(all_groups(topo, same_node, 0, UCC_SBGP_NODE, &topo->all_nodes, &topo->n_nodes_all));
     *sbgps = topo->all_nodes; *n = topo->n_nodes_all; return UCC_OK;
 }
+int ucc_topo_n_numas(ucc_topo_t *topo)
+{
+    ucc_sbgp_t *g; int n;
+    return ucc_topo_get_all_numas(topo, &g, &n) == UCC_OK ? n : 0;
+}
+ucc_rank_t ucc_topo_get_node_host_id(ucc_topo_t *topo, ucc_rank_t team_rank)
+{
+    for (int k = 0; k < topo->n_nodes_all; k++) if (same_node(topo, topo->all_nodes[k].rank_map[0], team_rank)) return (ucc_rank_t)k;
+    return UCC_RANK_INVALID;
+}
+ucc_status_t ucc_topo_get_all_node_nvlinks(ucc_topo_t *topo, ucc_sbgp_t **sbgps, int *n_out)
+{
+    ucc_rank_t size = (ucc_rank_t)topo->set.map.ep_num, me = topo->set.myrank, nm = 0, *mem, *comp, *stack;
+    ucc_sbgp_t *arr;
+    int n = 0;
+    if (topo->all_node_nvlinks) { *sbgps = topo->all_node_nvlinks; *n_out = topo->n_node_nvlinks; return UCC_OK; }
+    if (ucc_topo_rank_gpu(topo, me, NULL) < 0) return UCC_ERR_NOT_FOUND;
+    mem = (ucc_rank_t *)malloc(sizeof(ucc_rank_t) * size * 3);
+    if (!mem) return UCC_ERR_NO_MEMORY;
+    comp = mem + size; stack = comp + size;
+    for (ucc_rank_t r = 0; r < size; r++) if (same_node(topo, r, me) && ucc_topo_rank_gpu(topo, r, NULL) >= 0) { comp[nm] = UCC_RANK_INVALID; mem[nm++] = r; }
+    arr = (ucc_sbgp_t *)calloc(nm, sizeof(ucc_sbgp_t));
+    if (!arr) { free(mem); return UCC_ERR_NO_MEMORY; }
+    for (ucc_rank_t i = 0; i < nm; i++) { /* flood fill over the NVLink adjacency of the node's GPU members */
+        ucc_rank_t top = 0, cnt = 0, *ranks;
+        if (comp[i] != UCC_RANK_INVALID) continue;
+        comp[i] = (ucc_rank_t)n; stack[top++] = i;
+        while (top) {
+            ucc_rank_t a = stack[--top];
+            for (ucc_rank_t b = 0; b < nm; b++) if (comp[b] == UCC_RANK_INVALID && ucc_topo_nvlink_connected(topo, mem[a], mem[b])) { comp[b] = (ucc_rank_t)n; stack[top++] = b; }
+        }
+        ranks = (ucc_rank_t *)malloc(sizeof(ucc_rank_t) * nm);
+        for (ucc_rank_t b = 0; b < nm; b++) if (comp[b] == (ucc_rank_t)n) ranks[cnt++] = mem[b];
+        arr[n].type = UCC_SBGP_NODE_NVLINK; arr[n].rank_map = ranks; arr[n].group_size = cnt; arr[n].group_rank = UCC_RANK_INVALID;
+        for (ucc_rank_t k = 0; k < cnt; k++) if (ranks[k] == me) arr[n].group_rank = k;
+        arr[n].map = ucc_ep_map_from_array(&arr[n].rank_map, cnt, size, 0);
+        arr[n].status = UCC_SBGP_ENABLED;
+        n++;
+    }
+    free(mem);
+    topo->all_node_nvlinks = arr; topo->n_node_nvlinks = n;
+    *sbgps = arr; *n_out = n;
+    return UCC_OK;
+}
 ucc_status_t ucc_topo_get_node_leaders(ucc_topo_t *topo, ucc_rank_t **node_leaders)
 {
     ucc_rank_t size = (ucc_rank_t)topo->set.map.ep_num;
@@ -272,7 +316,7 @@ void ucc_topo_cleanup(ucc_topo_t *t)
 {
     if (!t) return;
     for (int i = 0; i < UCC_SBGP_LAST; i++) free(t->sbgps[i].rank_map);
-    free_groups(t->all_sockets, t->n_sockets); free_groups(t->all_numas, t->n_numas); free_groups(t->all_nodes, t->n_nodes_all);
+    free_groups(t->all_sockets, t->n_sockets); free_groups(t->all_numas, t->n_numas); free_groups(t->all_nodes, t->n_nodes_all); free_groups(t->all_node_nvlinks, t->n_node_nvlinks);
     free(t->node_leaders); free(t);
 }
 void ucc_sbgp_print(const ucc_sbgp_t *s)

@@ -48,6 +48,8 @@ typedef struct ucc_topo {
     int                 n_numas;
     ucc_sbgp_t         *all_nodes;    /* every node group of the team */
     int                 n_nodes_all;
+    ucc_sbgp_t         *all_node_nvlinks; /* NVLink islands (connected components) among the GPU members of my node */
+    int                 n_node_nvlinks;
     ucc_rank_t          node_leader_rank_id; /* which local rank acts as leader (default 0) */
     ucc_rank_t          node_leader_rank;
     ucc_rank_t         *node_leaders; /* team rank -> team rank of its node leader */
@@ -74,6 +76,20 @@ static inline ucc_rank_t ucc_topo_max_ppn(const ucc_topo_t *t) { return t->max_p
 static inline int ucc_topo_is_single_node(const ucc_topo_t *t) { return t->nnodes == 1; }
 static inline int ucc_topo_isoppn(const ucc_topo_t *t) { return t->min_ppn == t->max_ppn; }
 static inline ucc_rank_t ucc_topo_n_sockets(const ucc_topo_t *t) { return t->max_n_sockets; }
+/* further statistics of the reference's inline family (topo/ucc_topo.h:148-282) */
+static inline int ucc_topo_is_single_ppn(const ucc_topo_t *t) { return t->max_ppn == 1; }
+static inline ucc_rank_t ucc_topo_min_socket_size(const ucc_topo_t *t) { return t->min_socket_size; }
+static inline ucc_rank_t ucc_topo_max_socket_size(const ucc_topo_t *t) { return t->max_socket_size; }
+static inline ucc_rank_t ucc_topo_min_numa_size(const ucc_topo_t *t) { return t->min_numa_size; }
+static inline ucc_rank_t ucc_topo_max_numa_size(const ucc_topo_t *t) { return t->max_numa_size; }
+int          ucc_topo_n_numas(ucc_topo_t *topo);                 /* numa domains used on my node, 0 when processes are not bound */
+/* dense id (0 .. nnodes-1, order of first appearance in the team) of the node a team rank lives on */
+ucc_rank_t   ucc_topo_get_node_host_id(ucc_topo_t *topo, ucc_rank_t team_rank);
+/* NVLink islands of my node: one group per connected component of the NVLink graph over the node's GPU members
+ * (reference ucc_sbgp_create_all_node_nvlinks, topo/ucc_sbgp.h:90); UCC_ERR_NOT_FOUND without device information */
+ucc_status_t ucc_topo_get_all_node_nvlinks(ucc_topo_t *topo, ucc_sbgp_t **sbgps, int *n_sbgps);
+/* a sub-group as a subset of the team it was cut from (for sub-team creation and service collectives) */
+static inline ucc_subset_t ucc_sbgp_to_subset(const ucc_sbgp_t *sbgp) { ucc_subset_t s; s.map = sbgp->map; s.myrank = sbgp->group_rank; return s; }
 /* device predicates */
 int ucc_topo_has_device_info(const ucc_topo_t *topo);           /* every member reports a GPU */
 int ucc_topo_is_nvlink_fully_connected(const ucc_topo_t *topo); /* every pair of members is NVLink reachable */

@@ -69,6 +69,11 @@ static void test_blocked(void)
     CHECK(ucc_topo_get_all_sockets(t, &all, &n) == UCC_OK && n == 2 && has(&all[0], 4) && has(&all[1], 7));
     CHECK(ucc_topo_get_node_leaders(t, &nl) == UCC_OK && nl[0] == 0 && nl[3] == 0 && nl[5] == 4 && nl[9] == 8 && t->node_leader_rank == 4);
     CHECK(t->min_socket_size == 1 && t->max_socket_size == 2);
+    CHECK(ucc_topo_min_socket_size(t) == 1 && ucc_topo_max_socket_size(t) == 2 && ucc_topo_min_numa_size(t) == 1 && ucc_topo_max_numa_size(t) == 2);
+    CHECK(!ucc_topo_is_single_ppn(t) && ucc_topo_n_numas(t) == 2 && ucc_topo_n_sockets(t) == 2);
+    CHECK(ucc_topo_get_node_host_id(t, 0) == 0 && ucc_topo_get_node_host_id(t, 6) == 1 && ucc_topo_get_node_host_id(t, 9) == 2);
+    { ucc_subset_t ss = ucc_sbgp_to_subset(ucc_topo_get_sbgp(t, UCC_SBGP_NODE)); CHECK(ss.myrank == 1 && ss.map.ep_num == 4 && ucc_ep_map_eval(ss.map, 3) == 7); }
+    CHECK(ucc_topo_get_all_node_nvlinks(t, &all, &n) == UCC_ERR_NOT_FOUND);   /* no device information */
     CHECK(ucc_topo_get_sbgp(t, UCC_SBGP_LAST) == NULL);
     ucc_topo_cleanup(t);
     t = team_topo(ct, 10, 4);   /* a node leader and socket leader */
@@ -90,7 +95,7 @@ static void test_round_robin(void)
     CHECK(ucc_context_topo_init(st, &ct) == UCC_OK);
     CHECK(ct->nnodes == 3 && ct->min_ppn == 3 && ct->max_ppn == 3 && !ct->sock_bound);
     t = team_topo(ct, 9, 4);
-    CHECK(ucc_topo_isoppn(t));
+    CHECK(ucc_topo_isoppn(t) && ucc_topo_n_numas(t) == 0 && ucc_topo_get_node_host_id(t, 5) == 2);
     EXPECT(ucc_topo_get_sbgp(t, UCC_SBGP_NODE), 1, 4, 7);
     EXPECT(ucc_topo_get_sbgp(t, UCC_SBGP_NET), 3, 4, 5);                       /* second process of every node */
     CHECK(ucc_topo_get_sbgp(t, UCC_SBGP_SOCKET)->status == UCC_SBGP_NOT_EXISTS);
@@ -125,6 +130,10 @@ static void test_nvlink(void)
         CHECK(ucc_topo_nvlink_connected(t, 2, 3) && !ucc_topo_nvlink_connected(t, 2, 6));
         if (nvswitch) { CHECK(ucc_topo_nvlink_connected(t, 0, 3)); EXPECT(ucc_topo_get_sbgp(t, UCC_SBGP_NODE_NVLINK), 0, 1, 2, 3); }
         else { CHECK(!ucc_topo_nvlink_connected(t, 0, 3)); EXPECT(ucc_topo_get_sbgp(t, UCC_SBGP_NODE_NVLINK), 2, 3); }
+        { ucc_sbgp_t *isl; int ni;   /* NVLink islands of my node: one with a switch, the two pairs without */
+          CHECK(ucc_topo_get_all_node_nvlinks(t, &isl, &ni) == UCC_OK && ni == (nvswitch ? 1 : 2));
+          if (nvswitch) { EXPECT(&isl[0], 0, 1, 2, 3); CHECK(isl[0].group_rank == 2); }
+          else { EXPECT(&isl[0], 0, 1); EXPECT(&isl[1], 2, 3); CHECK(isl[0].group_rank == UCC_RANK_INVALID && isl[1].group_rank == 0); } }
         ucc_topo_cleanup(t);
         /* one node only: with a switch the 4 GPUs are one NVLink domain */
         { ucc_subset_t sub; ucc_rank_t first[4] = {0, 1, 2, 3}, *arr = first; sub.map = ucc_ep_map_from_array(&arr, 4, 8, 0); sub.myrank = 0;
