@@ -535,10 +535,12 @@ ucc_status_t ucc_coll_init_as(ucc_score_map_t *map, ucc_base_coll_args_t *bargs,
     ucc_status_t st = map_lookup_as(map, bargs, rank, size, &r);
     if (st != UCC_OK) return st;
     st = r->super.init(bargs, r->super.team, task);
+    if (st == UCC_OK && !(*task)->init_fn && (*task)->team == r->super.team) (*task)->init_fn = r->super.init; /* innermost (TL) entry wins */
     if (st != UCC_ERR_NOT_SUPPORTED && st != UCC_ERR_NOT_IMPLEMENTED) return st;
     ucc_list_for_each(fb, &r->fallback, list_elem) {
         ucc_debug("coll_init: falling back to the next candidate (score %u)", fb->score);
         st = fb->init(bargs, fb->team, task);
+        if (st == UCC_OK && !(*task)->init_fn && (*task)->team == fb->team) (*task)->init_fn = fb->init;
         if (st != UCC_ERR_NOT_SUPPORTED && st != UCC_ERR_NOT_IMPLEMENTED) return st;
     }
     return st;

@@ -24,9 +24,11 @@ typedef enum { HIER_SBGP_NODE, HIER_SBGP_NODE_LEADERS, HIER_SBGP_NET, HIER_SBGP_
 static const ucc_sbgp_type_t hier_to_topo[HIER_SBGP_LAST] = {UCC_SBGP_NODE, UCC_SBGP_NODE_LEADERS, UCC_SBGP_NET, UCC_SBGP_FULL};
 static const char *hier_sbgp_names[HIER_SBGP_LAST] = {"node", "node_leaders", "net", "full"};
 
-typedef struct ucc_cl_hier_lib_config { ucc_cl_lib_config_t super; ucc_config_allow_list_t sbgp_tls[HIER_SBGP_LAST]; ucc_pipeline_params_t allreduce_rab_pipeline; } ucc_cl_hier_lib_config_t;
+typedef struct ucc_cl_hier_lib_config { ucc_cl_lib_config_t super; ucc_config_allow_list_t sbgp_tls[HIER_SBGP_LAST]; size_t a2av_node_thresh;
+    ucc_pipeline_params_t allreduce_rab_pipeline, allreduce_split_rail_pipeline, bcast_2step_pipeline, reduce_2step_pipeline; } ucc_cl_hier_lib_config_t;
 typedef struct ucc_cl_hier_context_config { ucc_cl_context_config_t super; } ucc_cl_hier_context_config_t;
-typedef struct ucc_cl_hier_lib { ucc_cl_lib_t super; ucc_config_names_list_t sbgp_tls[HIER_SBGP_LAST]; ucc_pipeline_params_t allreduce_rab_pipeline; } ucc_cl_hier_lib_t;
+typedef struct ucc_cl_hier_lib { ucc_cl_lib_t super; ucc_config_names_list_t sbgp_tls[HIER_SBGP_LAST]; size_t a2av_node_thresh;
+    ucc_pipeline_params_t allreduce_rab_pipeline, allreduce_split_rail_pipeline, bcast_2step_pipeline, reduce_2step_pipeline; } ucc_cl_hier_lib_t;
 typedef struct ucc_cl_hier_context { ucc_cl_context_t super; ucc_tl_context_t **tl_ctxs; unsigned n_tl_ctxs; char *tune; } ucc_cl_hier_context_t;
 typedef struct hier_sbgp {
     int enabled; ucc_sbgp_t *sbgp; ucc_tl_team_t **tl_teams; unsigned n_tl_teams; ucc_coll_score_t *score; ucc_score_map_t *map;
@@ -44,6 +46,12 @@ static ucc_config_field_t cl_hier_lib_config_table[] = {
     {"FULL_SBGP_TLS", "all", "TLs used on the full team", ucc_offsetof(ucc_cl_hier_lib_config_t, sbgp_tls[HIER_SBGP_FULL]), UCC_CONFIG_TYPE_ALLOW_LIST},
     {"ALLREDUCE_RAB_PIPELINE", "n", "Pipelining of the RAB allreduce: thresh=<size>:fragsize=<size>:nfrags=<n>:pdepth=<n>:<parallel|ordered|sequential>",
      ucc_offsetof(ucc_cl_hier_lib_config_t, allreduce_rab_pipeline), UCC_CONFIG_TYPE_PIPELINE_PARAMS},
+    {"ALLREDUCE_SPLIT_RAIL_PIPELINE", "n", "Pipelining of the split_rail allreduce (fragments are multiples of the node size)",
+     ucc_offsetof(ucc_cl_hier_lib_config_t, allreduce_split_rail_pipeline), UCC_CONFIG_TYPE_PIPELINE_PARAMS},
+    {"BCAST_2STEP_PIPELINE", "n", "Pipelining of the 2step bcast", ucc_offsetof(ucc_cl_hier_lib_config_t, bcast_2step_pipeline), UCC_CONFIG_TYPE_PIPELINE_PARAMS},
+    {"REDUCE_2STEP_PIPELINE", "n", "Pipelining of the 2step reduce", ucc_offsetof(ucc_cl_hier_lib_config_t, reduce_2step_pipeline), UCC_CONFIG_TYPE_PIPELINE_PARAMS},
+    {"ALLTOALLV_SPLIT_NODE_THRESH", "0", "node_split alltoall(v): blocks for node peers larger than this many bytes go through the NODE sub-team, smaller ones stay in the full exchange",
+     ucc_offsetof(ucc_cl_hier_lib_config_t, a2av_node_thresh), UCC_CONFIG_TYPE_MEMUNITS},
     {NULL}};
 static ucc_config_field_t cl_hier_context_config_table[] = {{"", "", NULL, 0, UCC_CONFIG_TYPE_TABLE(ucc_cl_context_config_table)}, {NULL}};
 
@@ -56,7 +64,8 @@ static ucc_status_t hier_lib_init(const ucc_base_lib_params_t *p, const ucc_base
     if (!lib) return UCC_ERR_NO_MEMORY;
     if (ucc_cl_lib_init_base(&lib->super, &ucc_cl_hier, &cfg->super) != UCC_OK) { free(lib); return UCC_ERR_NO_MEMORY; }
     for (int i = 0; i < HIER_SBGP_LAST; i++) ucc_config_allow_list_process(&cfg->sbgp_tls[i], &lib->super.tls.array, &lib->sbgp_tls[i]);
-    lib->allreduce_rab_pipeline = cfg->allreduce_rab_pipeline;
+    lib->allreduce_rab_pipeline = cfg->allreduce_rab_pipeline; lib->allreduce_split_rail_pipeline = cfg->allreduce_split_rail_pipeline;
+    lib->bcast_2step_pipeline = cfg->bcast_2step_pipeline; lib->reduce_2step_pipeline = cfg->reduce_2step_pipeline; lib->a2av_node_thresh = cfg->a2av_node_thresh;
     *lib_p = &lib->super.super;
     return UCC_OK;
 }
@@ -216,196 +225,124 @@ static void free_tasks(ucc_coll_task_t **t, int n) { for (int i = 0; i < n; i++)
 static int is_leader(ucc_cl_hier_team_t *team) { ucc_sbgp_t *l = team->sb[HIER_SBGP_NODE_LEADERS].sbgp; return l && l->status == UCC_SBGP_ENABLED && l->group_rank != UCC_RANK_INVALID; }
 static int node_multi(ucc_cl_hier_team_t *team) { return team->sb[HIER_SBGP_NODE].enabled; }
 
-static ucc_status_t hier_allreduce_rab_frag(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, ucc_coll_task_t **task_p)
-{
-    ucc_cl_hier_team_t *team = ucc_derived_of(b_team, ucc_cl_hier_team_t);
-    ucc_coll_args_t *a = &b->args, sub;
-    ucc_coll_task_t *tasks[3] = {NULL, NULL, NULL}; int n = 0; hier_schedule_t *hs; ucc_status_t st;
-    int leader = is_leader(team), inplace = UCC_IS_INPLACE(*a);
-    if (a->op == UCC_OP_AVG) return UCC_ERR_NOT_SUPPORTED; /* averaging over sub-groups needs the global size: left to cl/basic */
-    if (node_multi(team)) { /* node reduce to the leader (local rank 0) */
-        sub = *a; sub.coll_type = UCC_COLL_TYPE_REDUCE; sub.root = 0; sub.mask |= UCC_COLL_ARGS_FIELD_FLAGS;
-        if (inplace) { if (!leader) { sub.flags &= ~(uint64_t)UCC_COLL_ARGS_FLAG_IN_PLACE; sub.src.info = a->dst.info; } }
-        st = sub_coll(team, HIER_SBGP_NODE, b, &sub, &tasks[n]); if (st != UCC_OK) goto err; n++;
-    }
-    if (leader && team->sb[HIER_SBGP_NODE_LEADERS].enabled) {
-        sub = *a; sub.mask |= UCC_COLL_ARGS_FIELD_FLAGS;
-        if (node_multi(team)) sub.flags |= UCC_COLL_ARGS_FLAG_IN_PLACE; /* result of the node reduce is already in dst */
-        st = sub_coll(team, HIER_SBGP_NODE_LEADERS, b, &sub, &tasks[n]); if (st != UCC_OK) goto err; n++;
-    }
-    if (node_multi(team)) {
-        sub = *a; sub.coll_type = UCC_COLL_TYPE_BCAST; sub.root = 0; sub.src.info = a->dst.info; sub.mask |= UCC_COLL_ARGS_FIELD_FLAGS; sub.flags &= ~(uint64_t)UCC_COLL_ARGS_FLAG_IN_PLACE;
-        st = sub_coll(team, HIER_SBGP_NODE, b, &sub, &tasks[n]); if (st != UCC_OK) goto err; n++;
-    }
-    if (n == 0) return UCC_ERR_NOT_SUPPORTED;
-    st = hier_sched_alloc(b, b_team, &hs); if (st != UCC_OK) goto err;
-    st = chain(hs, tasks, n); if (st != UCC_OK) { free(hs); goto err; }
-    *task_p = &hs->super.super;
-    return UCC_OK;
-err:
-    free_tasks(tasks, 3);
-    return st == UCC_ERR_NOT_IMPLEMENTED ? UCC_ERR_NOT_SUPPORTED : st;
-}
-
-
-/* pipelined rab: the vector is cut into fragments, up to pdepth rab chains are in flight and re-armed round robin
- * (reference allreduce_rab.c:79-270 does the same on top of its pipelined schedule) */
-typedef struct hier_rab_pipe {
-    ucc_schedule_pipelined_t super;
-    void  *src0[UCC_SCHEDULE_PIPELINED_MAX_FRAGS][3], *dst0[UCC_SCHEDULE_PIPELINED_MAX_FRAGS][3]; /* buffers of each sub task for fragment offset 0 */
-    size_t total, dts;
-} hier_rab_pipe_t;
-static ucc_status_t rab_frag_init(ucc_base_coll_args_t *b, ucc_schedule_pipelined_t *sp, ucc_base_team_t *team, ucc_schedule_t **frag)
-{
-    hier_rab_pipe_t *rp = (hier_rab_pipe_t *)sp;
-    ucc_base_coll_args_t fb = *b; ucc_coll_task_t *t; ucc_schedule_t *f; ucc_status_t st; int slot = 0;
-    size_t fc = ucc_buffer_block_count(rp->total, (unsigned)sp->n_frags_total, 0); /* largest fragment */
-    fb.args.dst.info.count = fc; if (!UCC_IS_INPLACE(fb.args)) fb.args.src.info.count = fc;
-    st = hier_allreduce_rab_frag(&fb, team, &t); if (st != UCC_OK) return st;
-    f = (ucc_schedule_t *)t;
-    while (slot < UCC_SCHEDULE_PIPELINED_MAX_FRAGS && rp->src0[slot][0] != (void *)(uintptr_t)1) slot++; /* first unused slot */
-    if (slot == UCC_SCHEDULE_PIPELINED_MAX_FRAGS) { t->finalize(t); return UCC_ERR_NO_RESOURCE; }
-    for (unsigned j = 0; j < f->n_tasks && j < 3; j++) { rp->src0[slot][j] = f->tasks[j]->bargs.args.src.info.buffer; rp->dst0[slot][j] = f->tasks[j]->bargs.args.dst.info.buffer; }
-    *frag = f;
-    return UCC_OK;
-}
-static ucc_status_t rab_frag_setup(ucc_schedule_pipelined_t *sp, ucc_schedule_t *frag, int frag_num)
-{
-    hier_rab_pipe_t *rp = (hier_rab_pipe_t *)sp;
-    size_t off = ucc_buffer_block_offset(rp->total, (unsigned)sp->n_frags_total, (unsigned)frag_num) * rp->dts, cnt = ucc_buffer_block_count(rp->total, (unsigned)sp->n_frags_total, (unsigned)frag_num);
-    int slot = 0;
-    while (slot < sp->n_frags && sp->frags[slot] != frag) slot++;
-    for (unsigned j = 0; j < frag->n_tasks && j < 3; j++) {
-        ucc_coll_args_t *a = &frag->tasks[j]->bargs.args;
-        if (rp->src0[slot][j]) a->src.info.buffer = PTR_OFFSET(rp->src0[slot][j], off);
-        if (rp->dst0[slot][j]) a->dst.info.buffer = PTR_OFFSET(rp->dst0[slot][j], off);
-        a->src.info.count = cnt; a->dst.info.count = cnt;
-        frag->tasks[j]->flags |= UCC_COLL_TASK_FLAG_ARGS_UPDATED;
-    }
-    return UCC_OK;
-}
-static ucc_status_t rab_pipe_finalize(ucc_coll_task_t *t) { ucc_status_t st = ucc_schedule_pipelined_finalize(t); free(t); return st; }
-
-static ucc_status_t hier_allreduce_rab(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, ucc_coll_task_t **task_p)
-{
-    ucc_cl_hier_team_t *team = ucc_derived_of(b_team, ucc_cl_hier_team_t);
-    ucc_cl_hier_lib_t *lib = ucc_derived_of(HLIB(team), ucc_cl_hier_lib_t);
-    const ucc_pipeline_params_t *pp = &lib->allreduce_rab_pipeline;
-    size_t count = b->args.dst.info.count, dts = ucc_dt_size(b->args.dst.info.datatype), fcount;
-    hier_rab_pipe_t *rp; int n_total, depth; ucc_status_t st;
-    if (!pp->n_frags || !pp->pdepth || pp->threshold == UCC_MEMUNITS_INF || pp->threshold == UCC_MEMUNITS_AUTO || count * dts < pp->threshold || b->args.op == UCC_OP_AVG ||
-        UCC_DT_IS_GENERIC(b->args.dst.info.datatype))
-        return hier_allreduce_rab_frag(b, b_team, task_p);
-    fcount = (pp->frag_size == UCC_MEMUNITS_INF || pp->frag_size == UCC_MEMUNITS_AUTO) ? ucc_div_round_up(count, pp->n_frags) : ucc_max(1, pp->frag_size / dts);
-    n_total = (int)ucc_div_round_up(count, fcount);
-    if (n_total < 2) return hier_allreduce_rab_frag(b, b_team, task_p);
-    depth = (int)ucc_min(ucc_min(pp->pdepth, (unsigned)n_total), UCC_SCHEDULE_PIPELINED_MAX_FRAGS);
-    rp = (hier_rab_pipe_t *)calloc(1, sizeof(*rp));
-    if (!rp) return UCC_ERR_NO_MEMORY;
-    rp->total = count; rp->dts = dts;
-    for (int s2 = 0; s2 < UCC_SCHEDULE_PIPELINED_MAX_FRAGS; s2++) rp->src0[s2][0] = (void *)(uintptr_t)1; /* "slot unused" marker consumed by rab_frag_init */
-    rp->super.n_frags_total = n_total; /* frag_init needs it before pipelined_init stores it */
-    st = ucc_schedule_pipelined_init(b, b_team, rab_frag_init, rab_frag_setup, depth, n_total, pp->order, &rp->super);
-    if (st != UCC_OK) { free(rp); return st == UCC_ERR_NOT_IMPLEMENTED ? UCC_ERR_NOT_SUPPORTED : st; }
-    rp->super.super.super.finalize = rab_pipe_finalize;
-    *task_p = &rp->super.super.super;
-    return UCC_OK;
-}
-
-static ucc_status_t hier_allreduce_split_rail(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, ucc_coll_task_t **task_p)
-{
-    ucc_cl_hier_team_t *team = ucc_derived_of(b_team, ucc_cl_hier_team_t);
-    ucc_coll_args_t *a = &b->args, sub;
-    ucc_coll_task_t *tasks[3] = {NULL, NULL, NULL}; int n = 0; hier_schedule_t *hs; ucc_status_t st;
-    ucc_sbgp_t *node = team->sb[HIER_SBGP_NODE].sbgp;
-    size_t count = a->dst.info.count, dts = ucc_dt_size(a->dst.info.datatype), ppn, off, cnt;
-    if (a->op == UCC_OP_AVG || !ucc_topo_isoppn(team->super.super.params.team->topo) || ucc_topo_min_ppn(team->super.super.params.team->topo) < 2 ||
-        !node_multi(team) || !team->sb[HIER_SBGP_NET].enabled) return UCC_ERR_NOT_SUPPORTED;
-    ppn = node->group_size;
-    if (count < ppn) return UCC_ERR_NOT_SUPPORTED;
-    off = ucc_buffer_block_offset(count, (unsigned)ppn, node->group_rank); cnt = ucc_buffer_block_count(count, (unsigned)ppn, node->group_rank);
-    if (count % ppn) return UCC_ERR_NOT_SUPPORTED; /* equal blocks keep reduce_scatter / allgather plain */
-    /* 1) node reduce_scatter in place on dst (copy src first through the sub collective's non-inplace form) */
-    sub = *a; sub.coll_type = UCC_COLL_TYPE_REDUCE_SCATTER; sub.mask |= UCC_COLL_ARGS_FIELD_FLAGS;
-    if (UCC_IS_INPLACE(*a)) { sub.dst.info = a->dst.info; }
-    else { sub.flags &= ~(uint64_t)UCC_COLL_ARGS_FLAG_IN_PLACE; sub.src.info = a->src.info; sub.dst.info = a->dst.info; sub.dst.info.buffer = PTR_OFFSET(a->dst.info.buffer, off * dts); sub.dst.info.count = cnt; }
-    st = sub_coll(team, HIER_SBGP_NODE, b, &sub, &tasks[n]); if (st != UCC_OK) goto err; n++;
-    /* 2) rail allreduce of my block */
-    sub = *a; sub.mask |= UCC_COLL_ARGS_FIELD_FLAGS; sub.flags |= UCC_COLL_ARGS_FLAG_IN_PLACE;
-    sub.dst.info.buffer = PTR_OFFSET(a->dst.info.buffer, off * dts); sub.dst.info.count = cnt; sub.src.info = sub.dst.info;
-    st = sub_coll(team, HIER_SBGP_NET, b, &sub, &tasks[n]); if (st != UCC_OK) goto err; n++;
-    /* 3) node allgather in place */
-    sub = *a; sub.coll_type = UCC_COLL_TYPE_ALLGATHER; sub.mask |= UCC_COLL_ARGS_FIELD_FLAGS; sub.flags |= UCC_COLL_ARGS_FLAG_IN_PLACE; sub.dst.info = a->dst.info; sub.src.info = a->dst.info; sub.src.info.count = cnt;
-    st = sub_coll(team, HIER_SBGP_NODE, b, &sub, &tasks[n]); if (st != UCC_OK) goto err; n++;
-    st = hier_sched_alloc(b, b_team, &hs); if (st != UCC_OK) goto err;
-    st = chain(hs, tasks, n); if (st != UCC_OK) { free(hs); goto err; }
-    *task_p = &hs->super.super;
-    return UCC_OK;
-err:
-    free_tasks(tasks, 3);
-    return st == UCC_ERR_NOT_IMPLEMENTED ? UCC_ERR_NOT_SUPPORTED : st;
-}
-
 /* is the (team-rank) root its node's leader?  rooted 2-step algorithms need that */
 static int root_is_leader(ucc_cl_hier_team_t *team, ucc_rank_t root, ucc_rank_t *root_leader_rank)
 {
-    ucc_sbgp_t *l = ucc_topo_get_sbgp(team->super.super.params.team->topo, UCC_SBGP_NODE_LEADERS);
     /* all ranks must be able to evaluate this: the leaders list is global knowledge (topology) */
     ucc_rank_t *nl = NULL;
     if (ucc_topo_get_node_leaders(team->super.super.params.team->topo, &nl) != UCC_OK) return 0;
     if (nl[root] != root) return 0;
-    (void)l;
-    if (root_leader_rank) {
-        /* rank of root inside the leaders group = number of leaders with a smaller team rank */
-        ucc_rank_t r = 0, size = team->super.super.params.size;
+    if (root_leader_rank) { /* rank of root inside the leaders group = number of leaders with a smaller team rank */
+        ucc_rank_t r = 0;
         for (ucc_rank_t i = 0; i < root; i++) if (nl[i] == i) r++;
-        (void)size; *root_leader_rank = r;
+        *root_leader_rank = r;
     }
     return 1;
 }
 
-static ucc_status_t hier_bcast_2step(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, ucc_coll_task_t **task_p)
-{
-    ucc_cl_hier_team_t *team = ucc_derived_of(b_team, ucc_cl_hier_team_t);
-    ucc_coll_args_t *a = &b->args, sub;
-    ucc_coll_task_t *tasks[2] = {NULL, NULL}; int n = 0; hier_schedule_t *hs; ucc_status_t st; ucc_rank_t lroot = 0;
-    if (UCC_COLL_ARGS_ACTIVE_SET(a) || !root_is_leader(team, (ucc_rank_t)a->root, &lroot)) return UCC_ERR_NOT_SUPPORTED;
-    if (is_leader(team) && team->sb[HIER_SBGP_NODE_LEADERS].enabled) { sub = *a; sub.root = lroot; st = sub_coll(team, HIER_SBGP_NODE_LEADERS, b, &sub, &tasks[n]); if (st != UCC_OK) goto err; n++; }
-    if (node_multi(team)) { sub = *a; sub.root = 0; st = sub_coll(team, HIER_SBGP_NODE, b, &sub, &tasks[n]); if (st != UCC_OK) goto err; n++; }
-    if (!n) return UCC_ERR_NOT_SUPPORTED;
-    st = hier_sched_alloc(b, b_team, &hs); if (st != UCC_OK) goto err;
-    st = chain(hs, tasks, n); if (st != UCC_OK) { free(hs); goto err; }
-    *task_p = &hs->super.super;
-    return UCC_OK;
-err:
-    free_tasks(tasks, 2);
-    return st == UCC_ERR_NOT_IMPLEMENTED ? UCC_ERR_NOT_SUPPORTED : st;
-}
+/* ---- chains of up to three sub-collectives (rab, split_rail, 2step bcast / reduce) ----
+ * An algorithm is an "args function": from the collective's arguments it derives the arguments and the sub-group of every step.  The same
+ * function builds the schedule and, for the pipelined variants, re-derives the steps of a fragment (offset buffers, its count) each time the
+ * fragment is re-armed - so a fragment of any algorithm is just the algorithm on a shorter vector.
+ * Returns the number of steps of THIS rank (0: nothing to do here), < 0: not supported.  *need: bytes of scratch the rank wants (asked
+ * with scratch == NULL first). */
+#define HIER_CHAIN_MAX 3
+typedef int (*hier_args_fn_t)(ucc_cl_hier_team_t *team, const ucc_coll_args_t *a, void *scratch, size_t *need, ucc_coll_args_t *sub, int *sb);
 
-static ucc_status_t hier_reduce_2step(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, ucc_coll_task_t **task_p)
+/* allreduce rab: node reduce to the leader -> leaders allreduce -> node bcast (reference allreduce/allreduce_rab.c:79-270) */
+static int rab_args(ucc_cl_hier_team_t *team, const ucc_coll_args_t *a, void *scratch, size_t *need, ucc_coll_args_t *sub, int *sb)
 {
-    ucc_cl_hier_team_t *team = ucc_derived_of(b_team, ucc_cl_hier_team_t);
-    ucc_coll_args_t *a = &b->args, sub;
-    ucc_coll_task_t *tasks[2] = {NULL, NULL}; int n = 0; hier_schedule_t *hs; ucc_status_t st; ucc_rank_t lroot = 0;
-    ucc_rank_t me = team->super.super.params.rank; int root = (ucc_rank_t)a->root == me, leader = is_leader(team);
-    ucc_mc_buffer_header_t *scratch = NULL;
-    if (a->op == UCC_OP_AVG || !root_is_leader(team, (ucc_rank_t)a->root, &lroot)) return UCC_ERR_NOT_SUPPORTED;
-    /* leaders that are not the root need a place for their node's partial result */
-    if (leader && !root && node_multi(team)) {
-        size_t len = a->src.info.count * ucc_dt_size(a->src.info.datatype);
-        if (ucc_mc_alloc(&scratch, len ? len : 1, a->src.info.mem_type) != UCC_OK) return UCC_ERR_NO_MEMORY;
-    }
-    if (node_multi(team)) {
-        sub = *a; sub.root = 0; sub.mask |= UCC_COLL_ARGS_FIELD_FLAGS;
-        if (leader && !root) { sub.dst.info = a->src.info; sub.dst.info.buffer = scratch->addr; sub.flags &= ~(uint64_t)UCC_COLL_ARGS_FLAG_IN_PLACE; }
-        st = sub_coll(team, HIER_SBGP_NODE, b, &sub, &tasks[n]); if (st != UCC_OK) goto err; n++;
+    int n = 0, leader = is_leader(team), inplace = UCC_IS_INPLACE(*a);
+    (void)scratch; (void)need;
+    if (a->op == UCC_OP_AVG) return -1; /* averaging over sub-groups needs the global size: left to cl/basic */
+    if (node_multi(team)) { /* node reduce to the leader (local rank 0) */
+        sub[n] = *a; sub[n].coll_type = UCC_COLL_TYPE_REDUCE; sub[n].root = 0; sub[n].mask |= UCC_COLL_ARGS_FIELD_FLAGS;
+        if (inplace && !leader) { sub[n].flags &= ~(uint64_t)UCC_COLL_ARGS_FLAG_IN_PLACE; sub[n].src.info = a->dst.info; }
+        sb[n++] = HIER_SBGP_NODE;
     }
     if (leader && team->sb[HIER_SBGP_NODE_LEADERS].enabled) {
-        sub = *a; sub.root = lroot; sub.mask |= UCC_COLL_ARGS_FIELD_FLAGS;
-        if (node_multi(team)) { if (root) sub.flags |= UCC_COLL_ARGS_FLAG_IN_PLACE; else sub.src.info.buffer = scratch->addr; }
-        st = sub_coll(team, HIER_SBGP_NODE_LEADERS, b, &sub, &tasks[n]); if (st != UCC_OK) goto err; n++;
+        sub[n] = *a; sub[n].mask |= UCC_COLL_ARGS_FIELD_FLAGS;
+        if (node_multi(team)) sub[n].flags |= UCC_COLL_ARGS_FLAG_IN_PLACE; /* result of the node reduce is already in dst */
+        sb[n++] = HIER_SBGP_NODE_LEADERS;
     }
-    if (!n) { st = UCC_ERR_NOT_SUPPORTED; goto err; }
+    if (node_multi(team)) {
+        sub[n] = *a; sub[n].coll_type = UCC_COLL_TYPE_BCAST; sub[n].root = 0; sub[n].src.info = a->dst.info; sub[n].mask |= UCC_COLL_ARGS_FIELD_FLAGS;
+        sub[n].flags &= ~(uint64_t)UCC_COLL_ARGS_FLAG_IN_PLACE;
+        sb[n++] = HIER_SBGP_NODE;
+    }
+    return n;
+}
+
+/* allreduce split_rail: node reduce_scatter -> PPN concurrent rail allreduces -> node allgather (reference allreduce/allreduce_split_rail.c) */
+static int split_rail_args(ucc_cl_hier_team_t *team, const ucc_coll_args_t *a, void *scratch, size_t *need, ucc_coll_args_t *sub, int *sb)
+{
+    ucc_topo_t *topo = team->super.super.params.team->topo;
+    ucc_sbgp_t *node = team->sb[HIER_SBGP_NODE].sbgp;
+    size_t count = a->dst.info.count, dts = ucc_dt_size(a->dst.info.datatype), ppn, off, cnt;
+    (void)scratch; (void)need;
+    if (a->op == UCC_OP_AVG || !ucc_topo_isoppn(topo) || ucc_topo_min_ppn(topo) < 2 || !node_multi(team) || !team->sb[HIER_SBGP_NET].enabled) return -1;
+    ppn = node->group_size;
+    if (count < ppn || count % ppn) return -1; /* equal blocks keep reduce_scatter / allgather plain */
+    cnt = count / ppn; off = cnt * node->group_rank;
+    /* 1) node reduce_scatter: my block lands at its final place in dst */
+    sub[0] = *a; sub[0].coll_type = UCC_COLL_TYPE_REDUCE_SCATTER; sub[0].mask |= UCC_COLL_ARGS_FIELD_FLAGS;
+    if (!UCC_IS_INPLACE(*a)) { sub[0].flags &= ~(uint64_t)UCC_COLL_ARGS_FLAG_IN_PLACE; sub[0].dst.info.buffer = PTR_OFFSET(a->dst.info.buffer, off * dts); sub[0].dst.info.count = cnt; }
+    sb[0] = HIER_SBGP_NODE;
+    /* 2) rail allreduce of my block */
+    sub[1] = *a; sub[1].mask |= UCC_COLL_ARGS_FIELD_FLAGS; sub[1].flags |= UCC_COLL_ARGS_FLAG_IN_PLACE;
+    sub[1].dst.info.buffer = PTR_OFFSET(a->dst.info.buffer, off * dts); sub[1].dst.info.count = cnt; sub[1].src.info = sub[1].dst.info;
+    sb[1] = HIER_SBGP_NET;
+    /* 3) node allgather in place */
+    sub[2] = *a; sub[2].coll_type = UCC_COLL_TYPE_ALLGATHER; sub[2].mask |= UCC_COLL_ARGS_FIELD_FLAGS; sub[2].flags |= UCC_COLL_ARGS_FLAG_IN_PLACE;
+    sub[2].dst.info = a->dst.info; sub[2].src.info = a->dst.info; sub[2].src.info.count = cnt;
+    sb[2] = HIER_SBGP_NODE;
+    return 3;
+}
+
+/* bcast 2step: leaders bcast -> node bcast (reference bcast/bcast_2step.c); the root has to be its node's leader */
+static int bcast_2step_args(ucc_cl_hier_team_t *team, const ucc_coll_args_t *a, void *scratch, size_t *need, ucc_coll_args_t *sub, int *sb)
+{
+    ucc_rank_t lroot = 0; int n = 0;
+    (void)scratch; (void)need;
+    if (UCC_COLL_ARGS_ACTIVE_SET(a) || !root_is_leader(team, (ucc_rank_t)a->root, &lroot)) return -1;
+    if (is_leader(team) && team->sb[HIER_SBGP_NODE_LEADERS].enabled) { sub[n] = *a; sub[n].root = lroot; sb[n++] = HIER_SBGP_NODE_LEADERS; }
+    if (node_multi(team)) { sub[n] = *a; sub[n].root = 0; sb[n++] = HIER_SBGP_NODE; }
+    return n;
+}
+
+/* reduce 2step: node reduce -> leaders reduce (reference reduce/reduce_2step.c); leaders other than the root keep their node's partial result
+ * in a scratch buffer */
+static int reduce_2step_args(ucc_cl_hier_team_t *team, const ucc_coll_args_t *a, void *scratch, size_t *need, ucc_coll_args_t *sub, int *sb)
+{
+    ucc_rank_t lroot = 0, me = team->super.super.params.rank; int n = 0, root = (ucc_rank_t)a->root == me, leader = is_leader(team);
+    if (a->op == UCC_OP_AVG || !root_is_leader(team, (ucc_rank_t)a->root, &lroot)) return -1;
+    if (leader && !root && node_multi(team)) { size_t len = a->src.info.count * ucc_dt_size(a->src.info.datatype); *need = len ? len : 1; }
+    if (node_multi(team)) {
+        sub[n] = *a; sub[n].root = 0; sub[n].mask |= UCC_COLL_ARGS_FIELD_FLAGS;
+        if (leader && !root) { sub[n].dst.info = a->src.info; sub[n].dst.info.buffer = scratch; sub[n].flags &= ~(uint64_t)UCC_COLL_ARGS_FLAG_IN_PLACE; }
+        sb[n++] = HIER_SBGP_NODE;
+    }
+    if (leader && team->sb[HIER_SBGP_NODE_LEADERS].enabled) {
+        sub[n] = *a; sub[n].root = lroot; sub[n].mask |= UCC_COLL_ARGS_FIELD_FLAGS;
+        if (node_multi(team)) { if (root) sub[n].flags |= UCC_COLL_ARGS_FLAG_IN_PLACE; else sub[n].src.info.buffer = scratch; }
+        sb[n++] = HIER_SBGP_NODE_LEADERS;
+    }
+    return n;
+}
+
+static ucc_status_t hier_chain_build(hier_args_fn_t fn, ucc_base_coll_args_t *b, ucc_base_team_t *b_team, ucc_coll_task_t **task_p)
+{
+    ucc_cl_hier_team_t *team = ucc_derived_of(b_team, ucc_cl_hier_team_t);
+    ucc_coll_args_t sub[HIER_CHAIN_MAX]; int sb[HIER_CHAIN_MAX], n;
+    ucc_coll_task_t *tasks[HIER_CHAIN_MAX] = {NULL, NULL, NULL}; hier_schedule_t *hs; ucc_status_t st;
+    ucc_mc_buffer_header_t *scratch = NULL; size_t need = 0;
+    n = fn(team, &b->args, NULL, &need, sub, sb);
+    if (n <= 0) return UCC_ERR_NOT_SUPPORTED;
+    if (need) {
+        if (ucc_mc_alloc(&scratch, need, b->args.src.info.mem_type) != UCC_OK) return UCC_ERR_NO_MEMORY;
+        n = fn(team, &b->args, scratch->addr, &need, sub, sb);
+    }
+    for (int i = 0; i < n; i++) { st = sub_coll(team, sb[i], b, &sub[i], &tasks[i]); if (st != UCC_OK) goto err; }
     st = hier_sched_alloc(b, b_team, &hs); if (st != UCC_OK) goto err;
     st = chain(hs, tasks, n); if (st != UCC_OK) { free(hs); goto err; }
     hs->scratch = scratch; /* released with the schedule */
@@ -413,8 +350,96 @@ static ucc_status_t hier_reduce_2step(ucc_base_coll_args_t *b, ucc_base_team_t *
     return UCC_OK;
 err:
     if (scratch) ucc_mc_free(scratch);
-    free_tasks(tasks, 2);
+    free_tasks(tasks, HIER_CHAIN_MAX);
     return st == UCC_ERR_NOT_IMPLEMENTED ? UCC_ERR_NOT_SUPPORTED : st;
+}
+
+/* pipelined chains: the vector is cut into fragments of `fcount` elements (the last one shorter), up to pdepth chains are in flight and
+ * re-armed round robin on top of the pipelined schedule (reference: allreduce_rab.c:79-270, allreduce_split_rail.c, bcast_2step.c,
+ * reduce_2step.c each carry their own frag_init / frag_setup pair; here one pair serves every args function) */
+typedef struct hier_pipe { ucc_schedule_pipelined_t super; hier_args_fn_t fn; size_t total, dts, fcount; } hier_pipe_t;
+/* the collective restricted to elements [off, off + cnt) */
+static void hier_frag_args(const ucc_coll_args_t *a, size_t off_bytes, size_t cnt, ucc_coll_args_t *f)
+{
+    *f = *a;
+    if (f->src.info.buffer) f->src.info.buffer = PTR_OFFSET(f->src.info.buffer, off_bytes);
+    if (f->dst.info.buffer) f->dst.info.buffer = PTR_OFFSET(f->dst.info.buffer, off_bytes);
+    f->src.info.count = cnt; f->dst.info.count = cnt;
+}
+static ucc_status_t hier_pipe_frag_init(ucc_base_coll_args_t *b, ucc_schedule_pipelined_t *sp, ucc_base_team_t *team, ucc_schedule_t **frag)
+{
+    hier_pipe_t *hp = (hier_pipe_t *)sp;
+    ucc_base_coll_args_t fb = *b; ucc_coll_task_t *t; ucc_status_t st;
+    hier_frag_args(&b->args, 0, hp->fcount, &fb.args); /* the largest fragment: sizes the scratch and picks the algorithms of the steps */
+    st = hier_chain_build(hp->fn, &fb, team, &t); if (st != UCC_OK) return st;
+    *frag = (ucc_schedule_t *)t;
+    return UCC_OK;
+}
+static ucc_status_t hier_pipe_frag_setup(ucc_schedule_pipelined_t *sp, ucc_schedule_t *frag, int frag_num)
+{
+    hier_pipe_t *hp = (hier_pipe_t *)sp;
+    hier_schedule_t *hs = (hier_schedule_t *)frag;
+    ucc_cl_hier_team_t *team = ucc_derived_of(frag->super.team, ucc_cl_hier_team_t);
+    size_t off = (size_t)frag_num * hp->fcount, cnt = ucc_min(hp->fcount, hp->total - off), need = 0;
+    ucc_coll_args_t fa, sub[HIER_CHAIN_MAX]; int sb[HIER_CHAIN_MAX], n;
+    hier_frag_args(&sp->super.super.bargs.args, off * hp->dts, cnt, &fa);
+    n = hp->fn(team, &fa, hs->scratch ? hs->scratch->addr : NULL, &need, sub, sb);
+    if (n < 0 || (unsigned)n != frag->n_tasks) return UCC_ERR_NOT_SUPPORTED; /* the steps of a rank do not depend on the fragment */
+    for (int j = 0; j < n; j++) {
+        ucc_coll_args_t *ta = &frag->tasks[j]->bargs.args;
+        ta->src = sub[j].src; ta->dst = sub[j].dst;
+        frag->tasks[j]->flags |= UCC_COLL_TASK_FLAG_ARGS_UPDATED; /* TLs rebuild what they derived from the arguments at init */
+    }
+    return UCC_OK;
+}
+static ucc_status_t hier_pipe_finalize(ucc_coll_task_t *t) { ucc_status_t st = ucc_schedule_pipelined_finalize(t); free(t); return st; }
+
+/* `count` elements of `dts` bytes; fragments are multiples of `align` elements (split_rail: the node size) */
+static ucc_status_t hier_chain_init(hier_args_fn_t fn, const ucc_pipeline_params_t *pp, size_t count, size_t dts, size_t align, int plain_dt,
+                                    ucc_base_coll_args_t *b, ucc_base_team_t *b_team, ucc_coll_task_t **task_p)
+{
+    hier_pipe_t *hp; size_t fcount; int n_total, depth; ucc_status_t st;
+    if (!pp->n_frags || !pp->pdepth || pp->threshold == UCC_MEMUNITS_INF || pp->threshold == UCC_MEMUNITS_AUTO || count * dts < pp->threshold || !plain_dt || !dts)
+        return hier_chain_build(fn, b, b_team, task_p);
+    fcount = (pp->frag_size == UCC_MEMUNITS_INF || pp->frag_size == UCC_MEMUNITS_AUTO) ? ucc_div_round_up(count, pp->n_frags) : ucc_max(1, pp->frag_size / dts);
+    fcount = ucc_div_round_up(fcount, align) * align;
+    n_total = (int)ucc_div_round_up(count, fcount);
+    if (n_total < 2) return hier_chain_build(fn, b, b_team, task_p);
+    depth = (int)ucc_min(ucc_min(pp->pdepth, (unsigned)n_total), UCC_SCHEDULE_PIPELINED_MAX_FRAGS);
+    hp = (hier_pipe_t *)calloc(1, sizeof(*hp));
+    if (!hp) return UCC_ERR_NO_MEMORY;
+    hp->fn = fn; hp->total = count; hp->dts = dts; hp->fcount = fcount;
+    st = ucc_schedule_pipelined_init(b, b_team, hier_pipe_frag_init, hier_pipe_frag_setup, depth, n_total, pp->order, &hp->super);
+    if (st != UCC_OK) { free(hp); return st == UCC_ERR_NOT_IMPLEMENTED ? UCC_ERR_NOT_SUPPORTED : st; }
+    hp->super.super.super.finalize = hier_pipe_finalize;
+    *task_p = &hp->super.super.super;
+    return UCC_OK;
+}
+#define HIER_LIB_OF(_b_team) ucc_derived_of(HLIB(ucc_derived_of(_b_team, ucc_cl_hier_team_t)), ucc_cl_hier_lib_t)
+
+static ucc_status_t hier_allreduce_rab(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, ucc_coll_task_t **task_p)
+{
+    return hier_chain_init(rab_args, &HIER_LIB_OF(b_team)->allreduce_rab_pipeline, b->args.dst.info.count, ucc_dt_size(b->args.dst.info.datatype), 1,
+                           !UCC_DT_IS_GENERIC(b->args.dst.info.datatype), b, b_team, task_p);
+}
+static ucc_status_t hier_allreduce_split_rail(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, ucc_coll_task_t **task_p)
+{
+    ucc_cl_hier_team_t *team = ucc_derived_of(b_team, ucc_cl_hier_team_t);
+    size_t ppn = node_multi(team) ? team->sb[HIER_SBGP_NODE].sbgp->group_size : 1;
+    return hier_chain_init(split_rail_args, &HIER_LIB_OF(b_team)->allreduce_split_rail_pipeline, b->args.dst.info.count, ucc_dt_size(b->args.dst.info.datatype), ppn,
+                           !UCC_DT_IS_GENERIC(b->args.dst.info.datatype), b, b_team, task_p);
+}
+static ucc_status_t hier_bcast_2step(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, ucc_coll_task_t **task_p)
+{
+    return hier_chain_init(bcast_2step_args, &HIER_LIB_OF(b_team)->bcast_2step_pipeline, b->args.src.info.count, ucc_dt_size(b->args.src.info.datatype), 1,
+                           !UCC_DT_IS_GENERIC(b->args.src.info.datatype), b, b_team, task_p);
+}
+static ucc_status_t hier_reduce_2step(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, ucc_coll_task_t **task_p)
+{
+    ucc_cl_hier_team_t *team = ucc_derived_of(b_team, ucc_cl_hier_team_t);
+    /* a root working in place describes the vector by dst only; everyone else by src */
+    const ucc_coll_buffer_info_t *i = ((ucc_rank_t)b->args.root == team->super.super.params.rank && UCC_IS_INPLACE(b->args)) ? &b->args.dst.info : &b->args.src.info;
+    return hier_chain_init(reduce_2step_args, &HIER_LIB_OF(b_team)->reduce_2step_pipeline, i->count, ucc_dt_size(i->datatype), 1, !UCC_DT_IS_GENERIC(i->datatype), b, b_team, task_p);
 }
 
 static ucc_status_t hier_barrier(ucc_base_coll_args_t *b, ucc_base_team_t *b_team, ucc_coll_task_t **task_p)
@@ -447,6 +472,8 @@ static ucc_status_t hier_a2av_node_split(ucc_base_coll_args_t *b, ucc_base_team_
     ucc_rank_t N = team->super.super.params.size, nn, i; int is_v = a->coll_type == UCC_COLL_TYPE_ALLTOALLV;
     uint64_t *arr, *nsc, *nsd, *nrc, *nrd, *fsc, *fsd, *frc, *frd;
     if (UCC_IS_INPLACE(*a) || !team->sb[HIER_SBGP_FULL].enabled) return UCC_ERR_NOT_SUPPORTED; /* both conditions are the same on every rank */
+    size_t thresh = HIER_LIB_OF(b_team)->a2av_node_thresh, sdts = ucc_dt_size(is_v ? a->src.info_v.datatype : a->src.info.datatype), rdts = ucc_dt_size(is_v ? a->dst.info_v.datatype : a->dst.info.datatype);
+    if (thresh == UCC_MEMUNITS_AUTO) thresh = 0;
     nn = node_multi(team) ? node->group_size : 0; /* alone on my node: everything goes through the FULL exchange */
     arr = (uint64_t *)calloc(4 * (size_t)nn + 4 * (size_t)N, sizeof(uint64_t));
     if (!arr) return UCC_ERR_NO_MEMORY;
@@ -460,8 +487,11 @@ static ucc_status_t hier_a2av_node_split(ucc_base_coll_args_t *b, ucc_base_team_
     for (i = 0; i < nn; i++) {
         ucc_rank_t r = node->rank_map[i], fi = r; /* node member's index inside FULL */
         if (full->rank_map) for (fi = 0; fi < N && full->rank_map[fi] != r; fi++) ;
-        nsc[i] = fsc[fi]; nsd[i] = fsd[fi]; nrc[i] = frc[fi]; nrd[i] = frd[fi];
-        fsc[fi] = 0; frc[fi] = 0;
+        nsd[i] = fsd[fi]; nrd[i] = frd[fi];
+        /* ALLTOALLV_SPLIT_NODE_THRESH: only blocks above the threshold leave the full exchange (sender and receiver judge the same block;
+         * reference alltoallv/alltoallv.c SET_FULL_COUNTS / SET_NODE_COUNTS) */
+        if (fsc[fi] * sdts > thresh) { nsc[i] = fsc[fi]; fsc[fi] = 0; }
+        if (frc[fi] * rdts > thresh) { nrc[i] = frc[fi]; frc[fi] = 0; }
     }
     sub = *a; sub.coll_type = UCC_COLL_TYPE_ALLTOALLV; sub.mask |= UCC_COLL_ARGS_FIELD_FLAGS; sub.flags |= UCC_COLL_ARGS_FLAG_COUNT_64BIT | UCC_COLL_ARGS_FLAG_DISPLACEMENTS_64BIT;
     if (!is_v) { sub.src.info_v.buffer = a->src.info.buffer; sub.src.info_v.datatype = a->src.info.datatype; sub.src.info_v.mem_type = a->src.info.mem_type;

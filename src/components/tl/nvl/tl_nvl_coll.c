@@ -429,6 +429,25 @@ static void nvl_progress(ucc_coll_task_t *ct)
     ct->status = UCC_OK;
 }
 
+/* A pipelined parent (cl/hier fragments) changed bargs.args since the last post (UCC_COLL_TASK_FLAG_ARGS_UPDATED).  tl/nvl tasks capture
+ * buffers, counts, grids and push tables at init, so the task is rebuilt through the algorithm entry that made it and takes over the fresh
+ * state; the core part (listeners, schedule links, callbacks) stays.  Sequence numbers are taken at post, never at init, so nothing is skipped. */
+static ucc_status_t nvl_finalize(ucc_coll_task_t *ct);
+static ucc_status_t nvl_rebuild(ucc_tl_nvl_task_t *t)
+{
+    const size_t off = offsetof(ucc_tl_nvl_task_t, team), len = sizeof(*t) - off;
+    char tmp[sizeof(ucc_tl_nvl_task_t)];
+    ucc_coll_task_t *nct = NULL;
+    ucc_status_t st;
+    if (!t->super.init_fn) return UCC_ERR_NOT_SUPPORTED;
+    st = t->super.init_fn(&t->super.bargs, t->super.team, &nct);
+    if (st != UCC_OK) return st;
+    if (nct->finalize != nvl_finalize) { nct->finalize(nct); return UCC_ERR_NOT_SUPPORTED; }
+    memcpy(tmp, (char *)nct + off, len); memcpy((char *)nct + off, (char *)t + off, len); memcpy((char *)t + off, tmp, len);
+    t->super.flags &= ~(uint32_t)UCC_COLL_TASK_FLAG_ARGS_UPDATED;
+    return nct->finalize(nct); /* releases the previous state (events go back to the cache, a lane's ordering event is kept alive) */
+}
+
 static ucc_status_t nvl_post_on(ucc_tl_nvl_task_t *t, cudaStream_t s)
 {
     enum cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
@@ -436,6 +455,7 @@ static ucc_status_t nvl_post_on(ucc_tl_nvl_task_t *t, cudaStream_t s)
     UCC_PROFILE_REQUEST_EVENT(t, "nvl_coll_start", 0);
     ucc_tl_nvl_team_t *team = t->team;
     int direct;
+    if (ucc_unlikely(t->super.flags & UCC_COLL_TASK_FLAG_ARGS_UPDATED)) { st = nvl_rebuild(t); if (st != UCC_OK) return st; }
     t->stream = s; t->captured = 0; t->state = NVL_TASK_LAUNCHED; t->gated = 0; t->published = 0;
     if (cudaStreamIsCapturing(s, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusActive) t->captured = 1;
     ucc_spin_lock(&team->launch_lock);

@@ -58,7 +58,7 @@ ucc_status_t ucc_coll_task_init(ucc_coll_task_t *task, ucc_base_coll_args_t *bar
     task->em.listeners = task->em.inl; task->em.n = 0; task->em.cap = 4;
     task->executor = NULL;
     task->n_deps = task->n_deps_satisfied = task->n_deps_base = 0;
-    task->start_time = 0; task->timeout = 0; task->seq_num = 0; task->progress_queue = NULL; task->generation = 0;
+    task->start_time = 0; task->timeout = 0; task->seq_num = 0; task->progress_queue = NULL; task->generation = 0; task->init_fn = NULL;
     if (bargs) memcpy(&task->bargs, bargs, sizeof(*bargs)); else memset(&task->bargs, 0, sizeof(task->bargs));
     return UCC_OK;
 }

@@ -105,6 +105,8 @@ struct ucc_coll_task {
     uint32_t                           seq_num;
     uint32_t                           generation; /* bumped each time a pipelined fragment re-arms the task */
     void                              *progress_queue; /* ucc_progress_queue_t the task is enqueued to */
+    ucc_base_coll_init_fn_t            init_fn; /* algorithm entry that built the task (set by ucc_coll_init_as): a TL that captures its arguments at
+                                                 * init rebuilds the task through it when a pipelined parent set UCC_COLL_TASK_FLAG_ARGS_UPDATED */
 };
 
 struct ucc_schedule {

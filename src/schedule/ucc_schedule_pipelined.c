@@ -33,6 +33,28 @@ static ucc_status_t launch_frag(ucc_schedule_pipelined_t *sp, int slot, int glob
     return ucc_event_manager_notify(&f->super, UCC_EVENT_SCHEDULE_STARTED);
 }
 
+/* Fragment g always runs in slot g % n_frags and fragments are launched in order: the slot decides the message tags of the
+ * fragment's tasks (TL tasks take theirs at init), so every rank must use the same slot for the same fragment - also a rank
+ * whose fragments complete inline (a bcast root) or out of order.  A slot that finished early therefore waits for its turn. */
+static ucc_status_t pump(ucc_schedule_pipelined_t *sp, int *done)
+{
+    ucc_status_t st = UCC_OK;
+    *done = 0;
+    if (sp->done_ptr) return UCC_OK; /* a fragment completed inside its own launch: the frame that is launching goes on (no recursion) */
+    sp->done_ptr = done;
+    while (st == UCC_OK && !*done && sp->n_frags_started < sp->n_frags_total) {
+        int g = sp->n_frags_started, s = g % sp->n_frags;
+        if (!sp->slot_idle[s]) break;
+        sp->slot_idle[s] = 0; sp->n_frags_started = g + 1;
+        st = launch_frag(sp, s, g);
+    }
+    sp->done_ptr = NULL;
+    return st;
+}
+/* the last fragment completed: the schedule is completed by the outermost frame, after it released the lock (the user may finalize the
+ * request as soon as its status is final) */
+static void complete_schedule(ucc_schedule_pipelined_t *sp) { sp->super.super.status = UCC_OK; ucc_task_complete(&sp->super.super); }
+
 static void find_task(ucc_schedule_pipelined_t *sp, ucc_coll_task_t *t, int *slot, int *j)
 {
     for (int s = 0; s < sp->n_frags; s++)
@@ -78,15 +100,16 @@ static ucc_status_t frag_completed_handler(ucc_coll_task_t *parent, ucc_coll_tas
     ucc_schedule_pipelined_t *sp   = ucc_derived_of(task, ucc_schedule_pipelined_t);
     ucc_schedule_t           *frag = ucc_derived_of(parent, ucc_schedule_t);
     ucc_status_t              st   = UCC_OK;
-    int                       slot = -1;
+    int                       slot = -1, done = 0;
     ucc_recursive_spin_lock(&sp->lock);
     for (int s = 0; s < sp->n_frags; s++) if (sp->frags[s] == frag) slot = s;
     sp->n_frags_completed++;
     if (sp->n_frags_completed == sp->n_frags_total) {
+        int nested = sp->done_ptr != NULL;
         for (int s = 0; s < sp->n_frags; s++) sp->slot_global[s] = -1;
+        if (nested) *sp->done_ptr = 1;
         ucc_recursive_spin_unlock(&sp->lock);
-        sp->super.super.status = UCC_OK;
-        ucc_task_complete(&sp->super.super);
+        if (!nested) complete_schedule(sp);
         return UCC_OK;
     }
     /* deliver any ordering event of the finished incarnation that was not delivered yet
@@ -94,15 +117,13 @@ static ucc_status_t frag_completed_handler(ucc_coll_task_t *parent, ucc_coll_tas
     if (sp->order != UCC_PIPELINE_PARALLEL && sp->n_frags > 1)
         for (unsigned j = 0; j < frag->n_tasks && st == UCC_OK; j++) st = fire(sp, slot, (int)j);
     if (st == UCC_OK) {
-        if (sp->n_frags_started < sp->n_frags_total) {
-            int g = sp->n_frags_started++;
-            st = launch_frag(sp, slot, g); /* round-robin: slot == g % n_frags */
-        } else {
-            for (unsigned j = 0; j < frag->n_tasks; j++) sp->fired[slot][j] = 1;
-            sp->slot_global[slot] = sp->n_frags_total + slot; /* idle: not a predecessor of anything */
-        }
+        for (unsigned j = 0; j < frag->n_tasks; j++) sp->fired[slot][j] = 1;
+        sp->slot_global[slot] = sp->n_frags_total + slot; /* idle: not a predecessor of anything */
+        sp->slot_idle[slot] = 1;
+        st = pump(sp, &done);
     }
     ucc_recursive_spin_unlock(&sp->lock);
+    if (done) complete_schedule(sp);
     return st;
 }
 
@@ -115,23 +136,19 @@ static ucc_status_t frag_error_handler(ucc_coll_task_t *parent, ucc_coll_task_t 
 ucc_status_t ucc_schedule_pipelined_post(ucc_coll_task_t *task)
 {
     ucc_schedule_pipelined_t *sp = ucc_derived_of(task, ucc_schedule_pipelined_t);
-    int n = sp->n_frags < sp->n_frags_total ? sp->n_frags : sp->n_frags_total;
     ucc_status_t st = UCC_OK;
+    int done = 0;
     sp->super.super.status = UCC_INPROGRESS; sp->super.super.super.status = UCC_INPROGRESS;
     sp->n_frags_completed = 0; sp->n_frags_started = 0;
     ucc_recursive_spin_lock(&sp->lock);
-    for (int s = 0; s < sp->n_frags; s++) { sp->slot_global[s] = -1; memset(sp->fired[s], 0, sizeof(sp->fired[s])); }
+    for (int s = 0; s < sp->n_frags; s++) { sp->slot_global[s] = -1; sp->slot_idle[s] = 1; memset(sp->fired[s], 0, sizeof(sp->fired[s])); }
     if (sp->n_frags_total == 0) {
         ucc_recursive_spin_unlock(&sp->lock);
         sp->super.super.status = UCC_OK; ucc_task_complete(&sp->super.super); return UCC_OK;
     }
-    for (int s = 0; s < n && st == UCC_OK; s++) {
-        if (sp->super.super.super.status != UCC_INPROGRESS) break; /* finished/failed inline */
-        if (sp->n_frags_started > s) continue; /* slot was already re-armed by an inline completion */
-        sp->n_frags_started = s + 1;
-        st = launch_frag(sp, s, s);
-    }
+    st = pump(sp, &done);
     ucc_recursive_spin_unlock(&sp->lock);
+    if (done) complete_schedule(sp);
     return st;
 }
 
@@ -159,7 +176,7 @@ ucc_status_t ucc_schedule_pipelined_init(ucc_base_coll_args_t *coll_args, ucc_ba
     sp->super.super.post = ucc_schedule_pipelined_post;
     sp->super.super.finalize = ucc_schedule_pipelined_finalize;
     sp->n_frags = n_frags; sp->n_frags_total = n_frags_total; sp->order = order; sp->frag_setup = frag_setup;
-    sp->n_frags_started = sp->n_frags_completed = 0;
+    sp->n_frags_started = sp->n_frags_completed = 0; sp->done_ptr = NULL;
     ucc_recursive_spinlock_init(&sp->lock);
     for (int s = 0; s < n_frags; s++) {
         st = frag_init(coll_args, sp, team, &sp->frags[s]);

@@ -30,6 +30,8 @@ struct ucc_schedule_pipelined {
     ucc_schedule_frag_setup_fn_t frag_setup;
     int                          slot_global[UCC_SCHEDULE_PIPELINED_MAX_FRAGS]; /* global frag index running in slot, -1 idle */
     uint8_t                      fired[UCC_SCHEDULE_PIPELINED_MAX_FRAGS][UCC_SCHEDULE_MAX_TASKS];
+    uint8_t                      slot_idle[UCC_SCHEDULE_PIPELINED_MAX_FRAGS];   /* the slot's fragment completed (or none was launched yet) */
+    int                         *done_ptr;  /* set while a frame is launching fragments: where a nested completion of the LAST fragment is reported */
     ucc_recursive_spinlock_t     lock;
 };
 

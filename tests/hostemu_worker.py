@@ -525,25 +525,35 @@ def registered_buffers():
 
 
 def hier_on_device_buffers():
-    """cl/hier (rab, split_rail) over a synthetic 2-node x 4-GPU placement with "device" buffers: node sub-teams are tl/nvl teams,
-    the cross-node sub-teams (leaders / rails) cannot be (different fake hosts) and go to the host TL through staging"""
+    """cl/hier over a synthetic 2-node x 4-GPU placement with "device" buffers: node sub-teams are tl/nvl teams, the cross-node sub-team
+    (leaders) cannot be (different fake hosts) and goes to the host TL.  Only the data-movement chain (2step bcast, plain and pipelined)
+    runs here: the reductions of rab / split_rail between the nodes need ec/cuda, which has no host emulation (GPU coverage:
+    tests/test_nvl_gpu.py::test_cl_hier_on_cuda_buffers, tests/test_dist_gpu.py fake nodes).  The pipelined variant re-targets the
+    fragments' sub-collectives between posts (UCC_COLL_TASK_FLAG_ARGS_UPDATED): tl/nvl tasks capture their arguments at init and are
+    rebuilt at post (nvl_rebuild) - a stale task would broadcast the first fragment again."""
     n = 8
-    for alg in ("rab", "split_rail"):
-        env = dict(BASE, UCC_CLS="hier,basic", UCC_CL_HIER_TUNE=f"allreduce:0-inf:@{alg}", UCC_TL_NVL_TIMEOUT="20s", **NOZC)
+    for extra in ({}, {"UCC_CL_HIER_BCAST_2STEP_PIPELINE": "thresh=1k:fragsize=16k:nfrags=2:pdepth=2:sequential"},
+                  {"UCC_CL_HIER_BCAST_2STEP_PIPELINE": "thresh=1k:fragsize=8k:nfrags=2:pdepth=3:parallel"}):
+        # NODE sub-teams may only be tl/nvl teams: were tl/nvl unable to serve them, cl/hier would decline and the trace would show CL_BASIC
+        env = dict(BASE, UCC_CLS="hier,basic", UCC_TL_NVL_TIMEOUT="20s", UCC_CL_HIER_NODE_SBGP_TLS="nvl", **NOZC, **extra)
         with UccJob(n, ppn=4, env=env, cls="hier,basic") as j:
             team = j.create_team()
-            for count in (16, 4096, 50000):
-                src = [Dev(count, fill=rnd(count, 7 * r + 1)) for r in range(n)]
-                dst = [Dev(count, fill=0) for _ in range(n)]
-                run(team, [ca("allreduce", src[r], dst[r]) for r in range(n)])
-                exp = sum(s.a.copy() for s in src)
-                for r in range(n):
-                    assert np.allclose(dst[r].a, exp), (alg, count, r)
-            b = [Dev(5000, fill=rnd(5000, 3) if r == 0 else 0) for r in range(n)]
-            run(team, [ca("bcast", b[r], None, root=0, count_dst=0) for r in range(n)])
-            for r in range(n):
-                assert np.array_equal(b[r].a, b[0].a)
-        print(f"  cl/hier {alg} on device buffers ok", flush=True)
+            for count in (16, 5000, 50001):
+                for root in (0, 4):
+                    b = [Dev(count, fill=rnd(count, 3 + root) if r == root else 0) for r in range(n)]
+                    args = [ca("bcast", b[r], None, root=root, count_dst=0, persistent=True) for r in range(n)]
+                    q = team.coll(args)
+                    for rep in range(2):
+                        if rep:
+                            for r in range(n):
+                                if r != root:
+                                    b[r].a[:] = 0
+                        assert q.run() == U.UCC_OK
+                        rt.cudaDeviceSynchronize()
+                        for r in range(n):
+                            assert np.array_equal(b[r].a, b[root].a), (extra, count, root, rep, r)
+                    q.finalize()
+        print(f"  cl/hier 2step bcast on device buffers ok{' (pipelined: ' + list(extra.values())[0] + ')' if extra else ''}", flush=True)
 
 
 def lanes():

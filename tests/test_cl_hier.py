@@ -145,3 +145,79 @@ def test_hier_allreduce_rab_pipelined(n, ppn, order):
                     for r in range(n):
                         assert np.array_equal(dst[r], exp), (count, inplace, rep, r)
                 req.finalize()
+
+
+@pytest.mark.parametrize("order", ["parallel", "sequential"])
+@pytest.mark.parametrize("n,ppn", [(4, 2), (6, 3), (8, 4)])
+def test_hier_allreduce_split_rail_pipelined(n, ppn, order):
+    """ALLREDUCE_SPLIT_RAIL_PIPELINE (reference cl_hier.c:68-71): fragments are multiples of the node size, the last one is shorter"""
+    env = {"UCC_CLS": "hier,basic", "UCC_CL_HIER_TLS": "shm,self", "UCC_CL_BASIC_TLS": "shm,self", "UCC_CL_HIER_TUNE": "allreduce:0-inf:@split_rail",
+           "UCC_CL_HIER_ALLREDUCE_SPLIT_RAIL_PIPELINE": f"thresh=1k:fragsize=4k:nfrags=3:pdepth=2:{order}"}
+    with UccJob(n, ppn=ppn, env=env, cls="hier,basic") as j:
+        team = j.create_team()
+        rng = np.random.default_rng(9)
+        for count in (8 * ppn, 300 * ppn, 1037 * ppn):   # below the threshold, a few fragments, ragged last fragment
+            for inplace in (False, True):
+                src = [rng.integers(-50, 50, count).astype(np.int64) for _ in range(n)]
+                exp = np.sum(src, 0)
+                dst = [s.copy() for s in src] if inplace else [np.zeros(count, np.int64) for _ in range(n)]
+                req = team.coll([coll_args("allreduce", None if inplace else src[r], dst[r], dt="int64", op="sum", inplace=inplace, persistent=True) for r in range(n)])
+                for rep in range(2):
+                    if inplace and rep:
+                        for r in range(n):
+                            dst[r][:] = src[r]
+                    assert req.run() == U.UCC_OK
+                    for r in range(n):
+                        assert np.array_equal(dst[r], exp), (count, inplace, rep, r)
+                req.finalize()
+
+
+@pytest.mark.parametrize("order", ["parallel", "ordered", "sequential"])
+@pytest.mark.parametrize("n,ppn", [(4, 2), (7, 3)])
+def test_hier_bcast_reduce_2step_pipelined(n, ppn, order):
+    """BCAST_2STEP_PIPELINE / REDUCE_2STEP_PIPELINE (reference cl_hier.c:72-79): leader roots run the pipelined 2step chains (non-root
+    leaders keep one scratch per fragment in flight), other roots fall back to cl/basic"""
+    pipe = f"thresh=1k:fragsize=2k:nfrags=3:pdepth=2:{order}"
+    env = {"UCC_CLS": "hier,basic", "UCC_CL_HIER_TLS": "shm,self", "UCC_CL_BASIC_TLS": "shm,self", "UCC_CL_HIER_BCAST_2STEP_PIPELINE": pipe, "UCC_CL_HIER_REDUCE_2STEP_PIPELINE": pipe}
+    with UccJob(n, ppn=ppn, env=env, cls="hier,basic") as j:
+        team = j.create_team()
+        rng = np.random.default_rng(n)
+        for count in (50, 1500, 4099):
+            for root in (0, ppn, 1):
+                bufs = [rng.random(count).astype(np.float32) if r == root else np.zeros(count, np.float32) for r in range(n)]
+                exp = bufs[root].copy()
+                run(team, [coll_args("bcast", bufs[r], None, root=root) for r in range(n)])
+                for r in range(n):
+                    assert np.array_equal(bufs[r], exp), ("bcast", count, root, r)
+                for inplace in (False, True):
+                    src = [rng.integers(0, 100, count).astype(np.int32) for _ in range(n)]
+                    keep = [s.copy() for s in src]
+                    dst = [np.zeros(count, np.int32) for _ in range(n)]
+                    if inplace:
+                        dst[root][:] = src[root]
+                    args = [coll_args("reduce", None if (inplace and r == root) else src[r], dst[r] if r == root else None, dt="int32", op="sum", root=root,
+                                      inplace=inplace and r == root) for r in range(n)]
+                    run(team, args)
+                    assert np.array_equal(dst[root], np.sum(keep, 0)), ("reduce", count, root, inplace)
+                    for r in range(n):
+                        assert np.array_equal(src[r], keep[r])
+
+
+@pytest.mark.parametrize("thresh", ["0", "8", "inf"])
+def test_hier_alltoallv_split_node_thresh(thresh):
+    """ALLTOALLV_SPLIT_NODE_THRESH (reference cl_hier.c:63-66): only node-peer blocks above the threshold go through the NODE sub-team"""
+    n, ppn = 6, 3
+    env = {"UCC_CLS": "hier,basic", "UCC_CL_HIER_TLS": "shm,self", "UCC_CL_BASIC_TLS": "shm,self", "UCC_CL_HIER_ALLTOALLV_SPLIT_NODE_THRESH": thresh}
+    with UccJob(n, ppn=ppn, env=env, cls="hier,basic") as j:
+        team = j.create_team()
+        rng = np.random.default_rng(3)
+        sc = [[(r + 3 * p) % 5 for p in range(n)] for r in range(n)]     # 0..4 float32 = 0..16 bytes: both sides of the 8-byte threshold
+        rc = [[sc[p][r] for p in range(n)] for r in range(n)]
+        sd = [np.concatenate([[0], np.cumsum(c)[:-1]]) for c in sc]
+        rd = [np.concatenate([[0], np.cumsum(c)[:-1]]) for c in rc]
+        src = [rng.random(max(1, sum(sc[r]))).astype(np.float32) for r in range(n)]
+        dst = [np.zeros(max(1, sum(rc[r])), np.float32) for r in range(n)]
+        run(team, [coll_args("alltoallv", src[r], dst[r], src_counts=sc[r], src_displs=sd[r], dst_counts=rc[r], dst_displs=rd[r]) for r in range(n)])
+        for r in range(n):
+            exp = np.concatenate([src[p][sd[p][r]:sd[p][r] + sc[p][r]] for p in range(n)])
+            assert np.array_equal(dst[r][:len(exp)], exp), r
