@@ -24,6 +24,23 @@ static ucc_config_field_t tl_shm_context_config_table[] = {
     {"BARRIER_KN_RADIX", "auto", "Radix of the k-nomial barrier / fanin / fanout", ucc_offsetof(ucc_tl_shm_context_config_t, barrier_kn_radix), UCC_CONFIG_TYPE_UINT_RANGED},
     {"ALLGATHER_KN_RADIX", "auto", "Radix of the k-nomial allgather", ucc_offsetof(ucc_tl_shm_context_config_t, allgather_kn_radix), UCC_CONFIG_TYPE_UINT_RANGED},
     {"GATHER_KN_RADIX", "auto", "Radix of the k-nomial gather / scatter", ucc_offsetof(ucc_tl_shm_context_config_t, gather_kn_radix), UCC_CONFIG_TYPE_UINT_RANGED},
+    {"KN_RADIX", "0", "Radix of every k-nomial algorithm whose own *_KN_RADIX is left on auto (0: built-in defaults)", ucc_offsetof(ucc_tl_shm_context_config_t, kn_radix), UCC_CONFIG_TYPE_UINT},
+    {"FANIN_KN_RADIX", "auto", "Radix of the k-nomial fanin (auto: BARRIER_KN_RADIX)", ucc_offsetof(ucc_tl_shm_context_config_t, fanin_kn_radix), UCC_CONFIG_TYPE_UINT},
+    {"FANOUT_KN_RADIX", "auto", "Radix of the k-nomial fanout (auto: BARRIER_KN_RADIX)", ucc_offsetof(ucc_tl_shm_context_config_t, fanout_kn_radix), UCC_CONFIG_TYPE_UINT},
+    {"SCATTER_KN_RADIX", "auto", "Radix of the k-nomial scatter (auto: GATHER_KN_RADIX)", ucc_offsetof(ucc_tl_shm_context_config_t, scatter_kn_radix), UCC_CONFIG_TYPE_UINT},
+    {"BCAST_SAG_KN_RADIX", "auto", "Radix of the scatter tree of the scatter-allgather bcast", ucc_offsetof(ucc_tl_shm_context_config_t, bcast_sag_kn_radix), UCC_CONFIG_TYPE_UINT_RANGED},
+    {"ALLTOALLV_PAIRWISE_NUM_POSTS", "auto", "Maximum number of outstanding send/recv pairs in pairwise alltoallv (auto/0: unlimited)",
+     ucc_offsetof(ucc_tl_shm_context_config_t, alltoallv_pairwise_num_posts), UCC_CONFIG_TYPE_UINT},
+    {"ALLGATHER_BATCHED_NUM_POSTS", "auto", "Maximum number of outstanding send/recv pairs in the batched allgather (auto: 4, 0: unlimited)",
+     ucc_offsetof(ucc_tl_shm_context_config_t, allgather_batched_num_posts), UCC_CONFIG_TYPE_UINT},
+    {"GATHERV_LINEAR_NUM_POSTS", "0", "Maximum number of receives the root of a linear gatherv keeps outstanding (0: all)",
+     ucc_offsetof(ucc_tl_shm_context_config_t, gatherv_linear_num_posts), UCC_CONFIG_TYPE_UINT},
+    {"SCATTERV_LINEAR_NUM_POSTS", "0", "Maximum number of sends the root of a linear scatterv keeps outstanding (0: all)",
+     ucc_offsetof(ucc_tl_shm_context_config_t, scatterv_linear_num_posts), UCC_CONFIG_TYPE_UINT},
+    {"REDUCE_SCATTER_RING_BIDIRECTIONAL", "y", "Ring reduce_scatter: the two halves of every block travel around two inverted rings concurrently",
+     ucc_offsetof(ucc_tl_shm_context_config_t, reduce_scatter_ring_bidirectional), UCC_CONFIG_TYPE_BOOL},
+    {"REDUCE_SCATTERV_RING_BIDIRECTIONAL", "y", "Ring reduce_scatterv: the two halves of every block travel around two inverted rings concurrently",
+     ucc_offsetof(ucc_tl_shm_context_config_t, reduce_scatterv_ring_bidirectional), UCC_CONFIG_TYPE_BOOL},
     {"ALLTOALL_PAIRWISE_NUM_POSTS", "auto", "Maximum number of outstanding send/recv pairs in pairwise alltoall(v) (auto/0: unlimited)",
      ucc_offsetof(ucc_tl_shm_context_config_t, alltoall_pairwise_num_posts), UCC_CONFIG_TYPE_UINT},
     {"ALLTOALLV_HYBRID_THRESH", "256", "alltoallv algorithm `hybrid`: messages of at most this many bytes are aggregated into log2(N) Bruck rounds, larger ones go pairwise",

@@ -23,6 +23,16 @@ static unsigned cfg_radix(const ucc_mrange_uint_t *r, size_t msg, ucc_memory_typ
     return v < 2 ? 2 : v;
 }
 
+#define KN_DFLT(_t) (SHM_CTX((_t)->team)->cfg.kn_radix >= 2 ? SHM_CTX((_t)->team)->cfg.kn_radix : 4u) /* KN_RADIX: default of the radixes left on auto */
+static unsigned cfg_radix_u(unsigned v, unsigned dflt, ucc_rank_t size)
+{
+    if (v == UCC_UUNITS_AUTO || v < 2) v = dflt;
+    if (v > size) v = size;
+    if (v > 64) v = 64;
+    return v < 2 ? 2 : v;
+}
+#define NPOSTS(_v) (((_v) == UCC_UUNITS_AUTO) ? 0u : (_v))
+
 /* ================================================================== */
 /* barrier / fanin / fanout                                            */
 /* ================================================================== */
@@ -49,7 +59,7 @@ err:
 ucc_status_t ucc_tl_shm_barrier_knomial(ucc_tl_shm_task_t *t)
 {
     ucc_tl_shm_context_t *ctx = SHM_CTX(t->team);
-    unsigned radix = cfg_radix(&ctx->cfg.barrier_kn_radix, 0, UCC_MEMORY_TYPE_HOST, 4, t->vsize);
+    unsigned radix = cfg_radix(&ctx->cfg.barrier_kn_radix, 0, UCC_MEMORY_TYPE_HOST, KN_DFLT(t), t->vsize);
     ucc_status_t st;
     CHK(prog_fanin(t, 0, radix, 1));
     CHK(prog_fanout(t, 0, radix, 2));
@@ -57,9 +67,9 @@ err:
     return st;
 }
 ucc_status_t ucc_tl_shm_fanin_knomial(ucc_tl_shm_task_t *t)
-{ return prog_fanin(t, (ucc_rank_t)ARGS(t)->root, cfg_radix(&SHM_CTX(t->team)->cfg.barrier_kn_radix, 0, UCC_MEMORY_TYPE_HOST, 4, t->vsize), 1); }
+{ return prog_fanin(t, (ucc_rank_t)ARGS(t)->root, cfg_radix_u(SHM_CTX(t->team)->cfg.fanin_kn_radix, cfg_radix(&SHM_CTX(t->team)->cfg.barrier_kn_radix, 0, UCC_MEMORY_TYPE_HOST, KN_DFLT(t), t->vsize), t->vsize), 1); }
 ucc_status_t ucc_tl_shm_fanout_knomial(ucc_tl_shm_task_t *t)
-{ return prog_fanout(t, (ucc_rank_t)ARGS(t)->root, cfg_radix(&SHM_CTX(t->team)->cfg.barrier_kn_radix, 0, UCC_MEMORY_TYPE_HOST, 4, t->vsize), 1); }
+{ return prog_fanout(t, (ucc_rank_t)ARGS(t)->root, cfg_radix_u(SHM_CTX(t->team)->cfg.fanout_kn_radix, cfg_radix(&SHM_CTX(t->team)->cfg.barrier_kn_radix, 0, UCC_MEMORY_TYPE_HOST, KN_DFLT(t), t->vsize), t->vsize), 1); }
 
 /* ================================================================== */
 /* bcast                                                               */
@@ -78,7 +88,7 @@ ucc_status_t ucc_tl_shm_bcast_knomial(ucc_tl_shm_task_t *t)
 {
     ucc_coll_args_t *a = ARGS(t);
     size_t len = a->src.info.count * ucc_dt_size(a->src.info.datatype);
-    unsigned radix = cfg_radix(&SHM_CTX(t->team)->cfg.bcast_kn_radix, len, a->src.info.mem_type, 4, t->vsize);
+    unsigned radix = cfg_radix(&SHM_CTX(t->team)->cfg.bcast_kn_radix, len, a->src.info.mem_type, KN_DFLT(t), t->vsize);
     ucc_rank_t root = (ucc_rank_t)a->root;
     if (UCC_COLL_ARGS_ACTIVE_SET(a)) root = (ucc_rank_t)(((int64_t)a->root - (int64_t)a->active_set.start) / a->active_set.stride);
     return ucc_tl_shm_bcast_knomial_prog(t, a->src.info.buffer, len, a->src.info.mem_type, root, radix);
@@ -93,16 +103,17 @@ ucc_status_t ucc_tl_shm_bcast_sag(ucc_tl_shm_task_t *t)
     char *buf = (char *)a->src.info.buffer;
     ucc_status_t st = UCC_OK;
     ucc_kn_tree_t tr;
+    unsigned radix = cfg_radix(&SHM_CTX(t->team)->cfg.bcast_sag_kn_radix, count * dts, mt, SHM_CTX(t->team)->cfg.kn_radix >= 2 ? SHM_CTX(t->team)->cfg.kn_radix : 2u, N);
     if (UCC_COLL_ARGS_ACTIVE_SET(a)) return UCC_ERR_NOT_SUPPORTED;
     /* scatter: a rank receives the blocks of its whole subtree [vr, vr+span), forwards sub-ranges to children */
-    ucc_kn_tree_init(&tr, t->vrank, N, root, 2);
+    ucc_kn_tree_init(&tr, t->vrank, N, root, radix);
     if (tr.parent != UCC_RANK_INVALID) {
-        ucc_rank_t span = ucc_kn_subtree_size(vr, N, 2);
+        ucc_rank_t span = ucc_kn_subtree_size(vr, N, radix);
         size_t off = ucc_buffer_block_offset(count, N, vr), end = ucc_buffer_block_offset(count, N, vr + span - 1) + ucc_buffer_block_count(count, N, vr + span - 1);
         CHK(shm_prog_recv(t, tr.parent, buf + off * dts, (end - off) * dts, mt, 1)); CHK(shm_prog_wait(t));
     }
     for (unsigned i = 0; i < tr.n_children; i++) {
-        ucc_rank_t cvr = (tr.children[i] + N - root) % N, span = ucc_kn_subtree_size(cvr, N, 2);
+        ucc_rank_t cvr = (tr.children[i] + N - root) % N, span = ucc_kn_subtree_size(cvr, N, radix);
         size_t off = ucc_buffer_block_offset(count, N, cvr), end = ucc_buffer_block_offset(count, N, cvr + span - 1) + ucc_buffer_block_count(count, N, cvr + span - 1);
         CHK(shm_prog_send(t, tr.children[i], buf + off * dts, (end - off) * dts, mt, 1));
     }
@@ -191,7 +202,7 @@ ucc_status_t ucc_tl_shm_allreduce_knomial(ucc_tl_shm_task_t *t)
     ucc_coll_args_t *a = ARGS(t);
     size_t count = a->dst.info.count, len = count * ucc_dt_size(a->dst.info.datatype);
     ucc_memory_type_t mt = a->dst.info.mem_type;
-    unsigned radix = cfg_radix(&SHM_CTX(t->team)->cfg.allreduce_kn_radix, len, mt, 4, t->vsize);
+    unsigned radix = cfg_radix(&SHM_CTX(t->team)->cfg.allreduce_kn_radix, len, mt, KN_DFLT(t), t->vsize);
     void *scratch; ucc_status_t st;
     CHK(shm_task_scratch(t, (size_t)(radix - 1) * len, mt, &scratch));
     if (!UCC_IS_INPLACE(*a)) CHK(shm_prog_copy(t, a->dst.info.buffer, a->src.info.buffer, len, mt, a->src.info.mem_type));
@@ -373,7 +384,7 @@ ucc_status_t ucc_tl_shm_reduce_knomial(ucc_tl_shm_task_t *t)
     ucc_datatype_t dt = is_root ? a->dst.info.datatype : a->src.info.datatype;
     ucc_memory_type_t mt = is_root ? a->dst.info.mem_type : a->src.info.mem_type;
     size_t len = count * ucc_dt_size(dt);
-    unsigned radix = cfg_radix(&SHM_CTX(t->team)->cfg.reduce_kn_radix, len, mt, 4, t->vsize);
+    unsigned radix = cfg_radix(&SHM_CTX(t->team)->cfg.reduce_kn_radix, len, mt, KN_DFLT(t), t->vsize);
     ucc_kn_tree_t tr; void *acc, *scratch = NULL; const void *first; ucc_status_t st;
     ucc_kn_tree_init(&tr, t->vrank, t->vsize, root, radix);
     first = (is_root && UCC_IS_INPLACE(*a)) ? a->dst.info.buffer : a->src.info.buffer;
@@ -454,17 +465,29 @@ err:
 /* ================================================================== */
 /* reduce_scatter(v)                                                   */
 /* ================================================================== */
-static ucc_status_t prog_rsv_ring(ucc_tl_shm_task_t *t, char *work, void *scratch, const size_t *cnt, const size_t *off, ucc_memory_type_t mt)
+static ucc_status_t prog_rsv_ring(ucc_tl_shm_task_t *t, char *work, void *scratch, const size_t *cnt, const size_t *off, ucc_memory_type_t mt, int bidir, size_t maxc)
 {
     ucc_rank_t N = t->vsize, r = t->vrank, next = (r + 1) % N, prev = (r + N - 1) % N;
     size_t dts = ucc_dt_size(t->dt); ucc_status_t st = UCC_OK;
+    /* bidirectional (reference reduce_scatter_ring.c, REDUCE_SCATTER_RING_BIDIRECTIONAL): the first half of every block is reduced around the
+     * ring r -> r+1, the second half around the inverted ring r -> r-1, both at once; a step moves half the bytes per direction */
+#define LO(_b) (bidir ? cnt[_b] - cnt[_b] / 2 : cnt[_b])
+#define HI(_b) (cnt[_b] / 2)
+    char *scr2 = (char *)scratch + (maxc - maxc / 2) * dts;
     for (ucc_rank_t s = 0; s + 1 < N; s++) {
-        ucc_rank_t sb = (r + 2 * N - s - 1) % N, rb = (r + 2 * N - s - 2) % N;
-        CHK(shm_prog_send(t, next, work + off[sb] * dts, cnt[sb] * dts, mt, 1 + s));
-        CHK(shm_prog_recv(t, prev, scratch, cnt[rb] * dts, mt, 1 + s));
+        ucc_rank_t sb = (r + 2 * N - s - 1) % N, rb = (r + 2 * N - s - 2) % N, sb2 = (r + s + 1) % N, rb2 = (r + s + 2) % N;
+        CHK(shm_prog_send(t, next, work + off[sb] * dts, LO(sb) * dts, mt, 1 + s));
+        CHK(shm_prog_recv(t, prev, scratch, LO(rb) * dts, mt, 1 + s));
+        if (bidir) {
+            CHK(shm_prog_send(t, prev, work + (off[sb2] + LO(sb2)) * dts, HI(sb2) * dts, mt, N + 1 + s));
+            CHK(shm_prog_recv(t, next, scr2, HI(rb2) * dts, mt, N + 1 + s));
+        }
         CHK(shm_prog_wait(t));
-        CHK(shm_prog_reduce(t, work + off[rb] * dts, work + off[rb] * dts, scratch, cnt[rb], mt, 0));
+        CHK(shm_prog_reduce(t, work + off[rb] * dts, work + off[rb] * dts, scratch, LO(rb), mt, 0));
+        if (bidir && HI(rb2)) CHK(shm_prog_reduce(t, work + (off[rb2] + LO(rb2)) * dts, work + (off[rb2] + LO(rb2)) * dts, scr2, HI(rb2), mt, 0));
     }
+#undef LO
+#undef HI
 err:
     return st;
 }
@@ -486,7 +509,7 @@ static ucc_status_t reduce_scatter_common(ucc_tl_shm_task_t *t, int is_v)
     CHK(shm_task_scratch(t, maxc * dts, mt, &scratch));
     if (inplace) work = dstbuf;
     else { CHK(shm_task_scratch(t, total * dts, mt, &work)); CHK(shm_prog_copy(t, work, a->src.info.buffer, total * dts, mt, a->src.info.mem_type)); }
-    CHK(prog_rsv_ring(t, (char *)work, scratch, cnt, off, mt));
+    CHK(prog_rsv_ring(t, (char *)work, scratch, cnt, off, mt, N > 2 && (is_v ? SHM_CTX(t->team)->cfg.reduce_scatterv_ring_bidirectional : SHM_CTX(t->team)->cfg.reduce_scatter_ring_bidirectional), maxc));
     if (t->op == UCC_OP_AVG) CHK(shm_prog_reduce(t, OFF(work, off[r] * dts), OFF(work, off[r] * dts), NULL, cnt[r], mt, 1));
     if (!inplace) CHK(shm_prog_copy(t, dstbuf, OFF(work, off[r] * dts), cnt[r] * dts, mt, mt));
 err:
@@ -579,7 +602,8 @@ err:
     return st;
 }
 ucc_status_t ucc_tl_shm_allgather_linear(ucc_tl_shm_task_t *t) { return allgather_linear_common(t, 0, 0); }
-ucc_status_t ucc_tl_shm_allgather_batched(ucc_tl_shm_task_t *t) { return allgather_linear_common(t, 0, 4); }
+ucc_status_t ucc_tl_shm_allgather_batched(ucc_tl_shm_task_t *t)
+{ unsigned np = SHM_CTX(t->team)->cfg.allgather_batched_num_posts; return allgather_linear_common(t, 0, np == UCC_UUNITS_AUTO ? 4 : np); }
 ucc_status_t ucc_tl_shm_allgatherv_linear(ucc_tl_shm_task_t *t) { return allgather_linear_common(t, 1, 0); }
 /* neighbor exchange (even team sizes): N/2 steps, pairs alternate left/right */
 ucc_status_t ucc_tl_shm_allgather_neighbor(ucc_tl_shm_task_t *t)
@@ -705,7 +729,7 @@ err:
 static ucc_status_t a2a_common(ucc_tl_shm_task_t *t, int is_v)
 {
     ucc_coll_args_t *a = ARGS(t); ucc_rank_t N = t->vsize, r = t->vrank; int inplace = UCC_IS_INPLACE(*a);
-    unsigned nposts = SHM_CTX(t->team)->cfg.alltoall_pairwise_num_posts;
+    unsigned nposts = is_v ? SHM_CTX(t->team)->cfg.alltoallv_pairwise_num_posts : SHM_CTX(t->team)->cfg.alltoall_pairwise_num_posts;
     size_t sdt, ddt; ucc_memory_type_t smt, dmt; char *src, *dst; ucc_status_t st = UCC_OK;
     if (is_v) { sdt = ucc_dt_size(a->src.info_v.datatype); ddt = ucc_dt_size(a->dst.info_v.datatype); smt = a->src.info_v.mem_type; dmt = a->dst.info_v.mem_type; src = (char *)a->src.info_v.buffer; dst = (char *)a->dst.info_v.buffer; }
     else { sdt = ucc_dt_size(a->src.info.datatype); ddt = ucc_dt_size(a->dst.info.datatype); smt = a->src.info.mem_type; dmt = a->dst.info.mem_type; src = (char *)a->src.info.buffer; dst = (char *)a->dst.info.buffer; }
@@ -893,7 +917,7 @@ ucc_status_t ucc_tl_shm_gather_knomial(ucc_tl_shm_task_t *t)
     int is_root = r == root; ucc_kn_tree_t tr; ucc_status_t st = UCC_OK;
     size_t blk = is_root ? a->dst.info.count / N * ucc_dt_size(a->dst.info.datatype) : a->src.info.count * ucc_dt_size(a->src.info.datatype);
     ucc_memory_type_t mt = is_root ? a->dst.info.mem_type : a->src.info.mem_type;
-    unsigned radix = cfg_radix(&SHM_CTX(t->team)->cfg.gather_kn_radix, blk * N, mt, 4, N);
+    unsigned radix = cfg_radix_u(SHM_CTX(t->team)->cfg.scatter_kn_radix, cfg_radix(&SHM_CTX(t->team)->cfg.gather_kn_radix, blk * N, mt, KN_DFLT(t), N), N);
     ucc_rank_t span = ucc_kn_subtree_size(vr, N, radix);
     void *sv; char *s;
     ucc_kn_tree_init(&tr, r, N, root, radix);
@@ -918,12 +942,13 @@ err:
 ucc_status_t ucc_tl_shm_gatherv_linear(ucc_tl_shm_task_t *t)
 {
     ucc_coll_args_t *a = ARGS(t); ucc_rank_t N = t->vsize, r = t->vrank, root = (ucc_rank_t)a->root; ucc_status_t st = UCC_OK;
+    unsigned np = NPOSTS(SHM_CTX(t->team)->cfg.gatherv_linear_num_posts), posted = 0;
     if (r == root) {
         size_t dts = ucc_dt_size(a->dst.info_v.datatype); char *dst = (char *)a->dst.info_v.buffer;
         for (ucc_rank_t i = 0; i < N; i++) {
             size_t c = ucc_coll_args_get_count(a, a->dst.info_v.counts, i) * dts, o = ucc_coll_args_get_displacement(a, a->dst.info_v.displacements, i) * dts;
             if (i == root) { if (!UCC_IS_INPLACE(*a)) CHK(shm_prog_copy(t, dst + o, a->src.info.buffer, c, a->dst.info_v.mem_type, a->src.info.mem_type)); }
-            else CHK(shm_prog_recv(t, i, dst + o, c, a->dst.info_v.mem_type, 1));
+            else { CHK(shm_prog_recv(t, i, dst + o, c, a->dst.info_v.mem_type, 1)); if (np && ++posted % np == 0) CHK(shm_prog_wait(t)); }
         }
     } else CHK(shm_prog_send(t, root, a->src.info.buffer, a->src.info.count * ucc_dt_size(a->src.info.datatype), a->src.info.mem_type, 1));
     CHK(shm_prog_wait(t));
@@ -948,7 +973,7 @@ ucc_status_t ucc_tl_shm_scatter_knomial(ucc_tl_shm_task_t *t)
     int is_root = r == root; ucc_kn_tree_t tr; ucc_status_t st = UCC_OK;
     size_t blk = is_root ? a->src.info.count / N * ucc_dt_size(a->src.info.datatype) : a->dst.info.count * ucc_dt_size(a->dst.info.datatype);
     ucc_memory_type_t mt = is_root ? a->src.info.mem_type : a->dst.info.mem_type;
-    unsigned radix = cfg_radix(&SHM_CTX(t->team)->cfg.gather_kn_radix, blk * N, mt, 4, N);
+    unsigned radix = cfg_radix(&SHM_CTX(t->team)->cfg.gather_kn_radix, blk * N, mt, KN_DFLT(t), N);
     ucc_rank_t span = ucc_kn_subtree_size(vr, N, radix);
     void *sv; char *s;
     ucc_kn_tree_init(&tr, r, N, root, radix);
@@ -970,12 +995,13 @@ err:
 ucc_status_t ucc_tl_shm_scatterv_linear(ucc_tl_shm_task_t *t)
 {
     ucc_coll_args_t *a = ARGS(t); ucc_rank_t N = t->vsize, r = t->vrank, root = (ucc_rank_t)a->root; ucc_status_t st = UCC_OK;
+    unsigned np = NPOSTS(SHM_CTX(t->team)->cfg.scatterv_linear_num_posts), posted = 0;
     if (r == root) {
         size_t dts = ucc_dt_size(a->src.info_v.datatype); char *src = (char *)a->src.info_v.buffer;
         for (ucc_rank_t i = 0; i < N; i++) {
             size_t c = ucc_coll_args_get_count(a, a->src.info_v.counts, i) * dts, o = ucc_coll_args_get_displacement(a, a->src.info_v.displacements, i) * dts;
             if (i == root) { if (!UCC_IS_INPLACE(*a)) CHK(shm_prog_copy(t, a->dst.info.buffer, src + o, c, a->dst.info.mem_type, a->src.info_v.mem_type)); }
-            else CHK(shm_prog_send(t, i, src + o, c, a->src.info_v.mem_type, 1));
+            else { CHK(shm_prog_send(t, i, src + o, c, a->src.info_v.mem_type, 1)); if (np && ++posted % np == 0) CHK(shm_prog_wait(t)); }
         }
     } else CHK(shm_prog_recv(t, root, a->dst.info.buffer, a->dst.info.count * ucc_dt_size(a->dst.info.datatype), a->dst.info.mem_type, 1));
     CHK(shm_prog_wait(t));

@@ -482,3 +482,62 @@ def test_random_programs_on_cl_hier(seed):
     env = {"UCC_CLS": "hier,basic", "UCC_CL_HIER_TLS": "shm,self", "UCC_CL_BASIC_TLS": "shm,self", "UCC_CL_HIER_TUNE": tune}
     with UccJob(n, ppn=ppn, env=env, cls="hier,basic") as job:
         _random_program([job.create_team()], rng, (tune, n, ppn), steps=40)
+
+
+KNOBS = {
+    "UCC_TL_SHM_KN_RADIX": ["0", "2", "3", "8"],
+    "UCC_TL_SHM_FANIN_KN_RADIX": ["auto", "2", "5"],
+    "UCC_TL_SHM_FANOUT_KN_RADIX": ["auto", "3"],
+    "UCC_TL_SHM_SCATTER_KN_RADIX": ["auto", "2", "3"],
+    "UCC_TL_SHM_BCAST_SAG_KN_RADIX": ["auto", "3", "0-1k:2,1k-inf:4"],
+    "UCC_TL_SHM_ALLTOALLV_PAIRWISE_NUM_POSTS": ["auto", "1", "3"],
+    "UCC_TL_SHM_ALLTOALL_PAIRWISE_NUM_POSTS": ["auto", "1", "2"],
+    "UCC_TL_SHM_ALLGATHER_BATCHED_NUM_POSTS": ["auto", "0", "1", "3"],
+    "UCC_TL_SHM_GATHERV_LINEAR_NUM_POSTS": ["0", "1", "2"],
+    "UCC_TL_SHM_SCATTERV_LINEAR_NUM_POSTS": ["0", "1", "3"],
+    "UCC_TL_SHM_REDUCE_SCATTER_RING_BIDIRECTIONAL": ["y", "n"],
+    "UCC_TL_SHM_REDUCE_SCATTERV_RING_BIDIRECTIONAL": ["y", "n"],
+}
+
+
+@pytest.mark.parametrize("seed", range(int(__import__("os").environ.get("B200_FUZZ_SEEDS", "6"))))
+def test_random_programs_with_random_knobs(seed):
+    """The tuning knobs of the host transport that mirror tl/ucp's (reference tl_ucp.c:55-250: radixes, outstanding-message limits,
+    bidirectional rings): a random value for each, the algorithms they act on forced, then a random program checked against numpy"""
+    rng = np.random.default_rng(9000 + seed)
+    env = {k: v[int(rng.integers(0, len(v)))] for k, v in KNOBS.items()}
+    tune = "allgather:inf:@batched#bcast:inf:@sag_knomial#scatter:inf:@knomial#gather:inf:@knomial#reduce_scatter:inf:@ring#alltoall:inf:@pairwise#alltoallv:inf:@pairwise"
+    n_all = int(rng.integers(3, 10))
+    with UccJob(n_all, env=dict(env, UCC_TL_SHM_TUNE=tune, UCC_TLS="shm,self")) as job:
+        sub = sorted(rng.choice(n_all, size=int(rng.integers(2, n_all)), replace=False).tolist())
+        _random_program([job.create_team(range(n_all)), job.create_team(sub)], rng, str(env))
+
+
+@pytest.mark.parametrize("bidir", ["y", "n"])
+@pytest.mark.parametrize("n", [3, 4, 7])
+def test_reduce_scatterv_ring_bidirectional(n, bidir):
+    """two inverted rings, each carrying one half of every block (reference reduce_scatterv_ring.c); blocks of 0, 1 and odd counts"""
+    with UccJob(n, env={"UCC_TL_SHM_REDUCE_SCATTERV_RING_BIDIRECTIONAL": bidir, "UCC_TL_SHM_REDUCE_SCATTER_RING_BIDIRECTIONAL": bidir, "UCC_TLS": "shm,self"}) as j:
+        team = j.create_team()
+        rng = np.random.default_rng(n)
+        for counts in ([0, 1, 7, 2, 9, 0, 33][:n], [1] * n, [1001 + 2 * r for r in range(n)]):
+            for inplace in (False, True):
+                src = [rng.integers(-100, 100, sum(counts)).astype(np.int64) for _ in range(n)]
+                keep = [s.copy() for s in src]
+                displs = np.concatenate([[0], np.cumsum(counts)[:-1]]).astype(int)
+                dst = [np.zeros(max(1, counts[r]), np.int64) for r in range(n)]
+                if inplace:
+                    args = [coll_args("reduce_scatterv", None, src[r], dt="int64", op="sum", dst_counts=counts, dst_displs=displs, inplace=True) for r in range(n)]
+                else:
+                    args = [coll_args("reduce_scatterv", src[r], dst[r], dt="int64", op="sum", dst_counts=counts, dst_displs=displs) for r in range(n)]
+                run(team, args)
+                exp = np.sum(keep, 0)
+                for r in range(n):
+                    got = src[r][displs[r]:displs[r] + counts[r]] if inplace else dst[r][:counts[r]]
+                    assert np.array_equal(got, exp[displs[r]:displs[r] + counts[r]]), (counts, inplace, r)
+        for count in (1, 5, 4096):
+            src = [rng.random(count * n) for _ in range(n)]
+            dst = [np.zeros(count) for _ in range(n)]
+            run(team, [coll_args("reduce_scatter", src[r], dst[r], dt="float64", op="avg") for r in range(n)])
+            for r in range(n):
+                assert np.allclose(dst[r], np.mean(src, 0)[r * count:(r + 1) * count])
