@@ -2,6 +2,8 @@
  * score publication, service collectives. */
 #include "tl_shm_coll.h"
 #include "core/ucc_global_opts.h"
+#include "core/ucc_team.h"
+#include "components/topo/ucc_topo.h"
 #include <strings.h>
 
 /* ------------------------------------------------------------------ */
@@ -45,6 +47,9 @@ static ucc_config_field_t tl_shm_context_config_table[] = {
      ucc_offsetof(ucc_tl_shm_context_config_t, alltoall_pairwise_num_posts), UCC_CONFIG_TYPE_UINT},
     {"ALLTOALLV_HYBRID_THRESH", "256", "alltoallv algorithm `hybrid`: messages of at most this many bytes are aggregated into log2(N) Bruck rounds, larger ones go pairwise",
      ucc_offsetof(ucc_tl_shm_context_config_t, alltoallv_hybrid_thresh), UCC_CONFIG_TYPE_MEMUNITS},
+    {"USE_TOPO", "try", "Allow the transport to use the team topology (y: a team without topology is refused)", ucc_offsetof(ucc_tl_shm_context_config_t, use_topo), UCC_CONFIG_TYPE_TERNARY},
+    {"RANKS_REORDERING", "y", "Ring algorithms visit the members host by host (and socket by socket) instead of in rank order; needs USE_TOPO",
+     ucc_offsetof(ucc_tl_shm_context_config_t, ranks_reordering), UCC_CONFIG_TYPE_BOOL},
     {"REDUCE_AVG_PRE_OP", "n", "Apply the 1/N scaling of AVG before (y) or after (n) the reduction", ucc_offsetof(ucc_tl_shm_context_config_t, reduce_avg_pre_op), UCC_CONFIG_TYPE_BOOL},
     {"ALLREDUCE_SRA_KN_PIPELINE", "n", "Pipelining of the SRA allreduce", ucc_offsetof(ucc_tl_shm_context_config_t, allreduce_sra_kn_pipeline), UCC_CONFIG_TYPE_PIPELINE_PARAMS},
     {NULL}};
@@ -254,12 +259,34 @@ static ucc_status_t shm_team_create_post(ucc_base_context_t *b_ctx, const ucc_ba
         }
         memb = ucc_hash_mix(memb ^ ep->addr.ep_id);
     }
+    /* RANKS_REORDERING (reference tl_ucp allgather_ring.c:120-124, reduce_scatter_ring.c:378-381: UCC_SBGP_FULL_HOST_ORDERED): when the team
+     * IS the core team (not a sub-group of a hierarchy) and its members are interleaved over hosts / sockets, rings follow the host order */
+    if (ctx->cfg.use_topo != UCC_NO && params->team && params->team->topo && params->size == params->team->size && ucc_ep_map_is_identity(&params->map)) {
+        ucc_sbgp_t *ho = ctx->cfg.ranks_reordering ? ucc_topo_get_sbgp(params->team->topo, UCC_SBGP_FULL_HOST_ORDERED) : NULL;
+        int reordered = 0;
+        if (ho && ho->status == UCC_SBGP_ENABLED && ho->rank_map && ho->group_size == params->size)
+            for (ucc_rank_t r = 0; r < params->size; r++) if (ho->rank_map[r] != r) reordered = 1;
+        if (reordered) {
+            team->ring_order = (ucc_rank_t *)malloc(2 * sizeof(ucc_rank_t) * params->size);
+            if (team->ring_order) {
+                char buf[256]; size_t o = 0;
+                team->ring_pos = team->ring_order + params->size;
+                for (ucc_rank_t r = 0; r < params->size; r++) { team->ring_order[r] = ho->rank_map[r]; team->ring_pos[ho->rank_map[r]] = r; }
+                for (ucc_rank_t r = 0; r < params->size && o + 12 < sizeof(buf); r++) o += (size_t)snprintf(buf + o, sizeof(buf) - o, " %u", team->ring_order[r]);
+                tl_debug(b_ctx->lib, "team %u: ring order by host:%s", (unsigned)params->id, buf);
+            }
+        }
+    } else if (ctx->cfg.use_topo == UCC_YES && !(params->team && params->team->topo)) {
+        tl_debug(b_ctx->lib, "USE_TOPO=y and the team has no topology");
+        free(team->eps); free(team);
+        return UCC_ERR_NOT_SUPPORTED;
+    }
     team->tag_base = ((uint64_t)params->id << 48) | ((uint64_t)(params->scope & 0xf) << 44) | ((uint64_t)(params->scope_id & 0xf) << 40) | ((memb & 0xff) << 32);
     *team_p = &team->super.super;
     return UCC_OK;
 }
 static ucc_status_t shm_team_create_test(ucc_base_team_t *t) { (void)t; return UCC_OK; }
-static ucc_status_t shm_team_destroy(ucc_base_team_t *b) { ucc_tl_shm_team_t *team = ucc_derived_of(b, ucc_tl_shm_team_t); free(team->eps); free(team->svc); free(team); return UCC_OK; }
+static ucc_status_t shm_team_destroy(ucc_base_team_t *b) { ucc_tl_shm_team_t *team = ucc_derived_of(b, ucc_tl_shm_team_t); free(team->eps); free(team->svc); free(team->ring_order); free(team); return UCC_OK; }
 
 static ucc_status_t shm_team_get_scores(ucc_base_team_t *b_team, ucc_coll_score_t **score_p)
 {

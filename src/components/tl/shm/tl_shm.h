@@ -69,6 +69,8 @@ typedef struct ucc_tl_shm_context_config {
     unsigned  fanin_kn_radix, fanout_kn_radix, scatter_kn_radix;   /* 0 / auto: follow BARRIER_KN_RADIX (fanin, fanout) / GATHER_KN_RADIX (scatter) */
     unsigned  alltoall_pairwise_num_posts, alltoallv_pairwise_num_posts, allgather_batched_num_posts, gatherv_linear_num_posts, scatterv_linear_num_posts;
     int       reduce_scatter_ring_bidirectional, reduce_scatterv_ring_bidirectional;
+    int       use_topo;          /* ternary: may the transport look at the team topology */
+    int       ranks_reordering;  /* ring algorithms walk the members host by host (needs the topology) */
     size_t    alltoallv_hybrid_thresh;   /* alltoallv `hybrid`: messages up to this size ride the Bruck rounds */
     int       reduce_avg_pre_op;
     ucc_pipeline_params_t allreduce_sra_kn_pipeline;
@@ -114,6 +116,8 @@ typedef struct ucc_tl_shm_team {
     uint64_t          tag_base;  /* team identity bits of the tag */
     struct shm_svc_cnt { uint64_t hash; uint32_t cnt; } *svc; /* per-subset service collective counters */
     unsigned          n_svc;
+    ucc_rank_t       *ring_order; /* RANKS_REORDERING: ring position -> team rank, members of one host (then socket) adjacent; NULL: rank order */
+    ucc_rank_t       *ring_pos;   /* team rank -> ring position */
 } ucc_tl_shm_team_t;
 
 #define SHM_CTX(_team) ucc_derived_of((_team)->super.super.context, ucc_tl_shm_context_t)

@@ -31,6 +31,10 @@ static unsigned cfg_radix_u(unsigned v, unsigned dflt, ucc_rank_t size)
     if (v > 64) v = 64;
     return v < 2 ? 2 : v;
 }
+/* ring position -> rank: the team's host order (RANKS_REORDERING) for collectives of the whole team, rank order otherwise */
+static inline const ucc_rank_t *ring_order(const ucc_tl_shm_task_t *t)
+{ return (t->team->ring_order && t->vsize == UCC_TL_TEAM_SIZE(t->team) && t->vrank == UCC_TL_TEAM_RANK(t->team) && !UCC_COLL_ARGS_ACTIVE_SET(ARGS(t))) ? t->team->ring_order : NULL; }
+#define RING_AT(_ord, _i, _N) ((_ord) ? (_ord)[(_i) % (_N)] : (_i) % (_N))
 #define NPOSTS(_v) (((_v) == UCC_UUNITS_AUTO) ? 0u : (_v))
 
 /* ================================================================== */
@@ -467,7 +471,8 @@ err:
 /* ================================================================== */
 static ucc_status_t prog_rsv_ring(ucc_tl_shm_task_t *t, char *work, void *scratch, const size_t *cnt, const size_t *off, ucc_memory_type_t mt, int bidir, size_t maxc)
 {
-    ucc_rank_t N = t->vsize, r = t->vrank, next = (r + 1) % N, prev = (r + N - 1) % N;
+    const ucc_rank_t *ord = ring_order(t);
+    ucc_rank_t N = t->vsize, r = t->vrank, p = ord ? t->team->ring_pos[r] : r, next = RING_AT(ord, p + 1, N), prev = RING_AT(ord, p + N - 1, N);
     size_t dts = ucc_dt_size(t->dt); ucc_status_t st = UCC_OK;
     /* bidirectional (reference reduce_scatter_ring.c, REDUCE_SCATTER_RING_BIDIRECTIONAL): the first half of every block is reduced around the
      * ring r -> r+1, the second half around the inverted ring r -> r-1, both at once; a step moves half the bytes per direction */
@@ -475,7 +480,7 @@ static ucc_status_t prog_rsv_ring(ucc_tl_shm_task_t *t, char *work, void *scratc
 #define HI(_b) (cnt[_b] / 2)
     char *scr2 = (char *)scratch + (maxc - maxc / 2) * dts;
     for (ucc_rank_t s = 0; s + 1 < N; s++) {
-        ucc_rank_t sb = (r + 2 * N - s - 1) % N, rb = (r + 2 * N - s - 2) % N, sb2 = (r + s + 1) % N, rb2 = (r + s + 2) % N;
+        ucc_rank_t sb = RING_AT(ord, p + 2 * N - s - 1, N), rb = RING_AT(ord, p + 2 * N - s - 2, N), sb2 = RING_AT(ord, p + s + 1, N), rb2 = RING_AT(ord, p + s + 2, N);
         CHK(shm_prog_send(t, next, work + off[sb] * dts, LO(sb) * dts, mt, 1 + s));
         CHK(shm_prog_recv(t, prev, scratch, LO(rb) * dts, mt, 1 + s));
         if (bidir) {
@@ -575,11 +580,12 @@ static ucc_status_t ag_own_block(ucc_tl_shm_task_t *t, char *dst, const size_t *
 static ucc_status_t allgather_ring_common(ucc_tl_shm_task_t *t, int is_v)
 {
     size_t *cnt, *off, dts; ucc_memory_type_t mt; char *dst; ucc_status_t st;
-    ucc_rank_t N = t->vsize, r = t->vrank, next = (r + 1) % N, prev = (r + N - 1) % N;
+    const ucc_rank_t *ord = ring_order(t);
+    ucc_rank_t N = t->vsize, r = t->vrank, p = ord ? t->team->ring_pos[r] : r, next = RING_AT(ord, p + 1, N), prev = RING_AT(ord, p + N - 1, N);
     CHK(ag_layout(t, is_v, &cnt, &off, &dts, &mt, &dst));
     CHK(ag_own_block(t, dst, cnt, off, mt));
     for (ucc_rank_t s = 0; s + 1 < N; s++) {
-        ucc_rank_t sb = (r + N - s) % N, rb = (r + N - s - 1) % N;
+        ucc_rank_t sb = RING_AT(ord, p + N - s, N), rb = RING_AT(ord, p + N - s - 1, N);
         CHK(shm_prog_send(t, next, dst + off[sb], cnt[sb], mt, 1 + s)); CHK(shm_prog_recv(t, prev, dst + off[rb], cnt[rb], mt, 1 + s)); CHK(shm_prog_wait(t));
     }
 err:

@@ -541,3 +541,32 @@ def test_reduce_scatterv_ring_bidirectional(n, bidir):
             run(team, [coll_args("reduce_scatter", src[r], dst[r], dt="float64", op="avg") for r in range(n)])
             for r in range(n):
                 assert np.allclose(dst[r], np.mean(src, 0)[r * count:(r + 1) * count])
+
+
+@pytest.mark.parametrize("reorder", ["y", "n"])
+def test_ring_ranks_reordering_by_host(reorder, capfd):
+    """RANKS_REORDERING (reference tl_ucp.c:246-249): on a team whose members alternate between two (synthetic) nodes the ring algorithms walk
+    node 0's members first, then node 1's - two node crossings per lap instead of eight; results do not depend on the order"""
+    n = 8
+    env = {"UCC_TL_SHM_RANKS_REORDERING": reorder, "UCC_TLS": "shm,self", "UCC_TL_SHM_LOG_LEVEL": "debug",
+           "UCC_TL_SHM_TUNE": "allgather:inf:@ring#allgatherv:inf:@ring#reduce_scatter:inf:@ring#reduce_scatterv:inf:@ring"}
+    with UccJob(n, ppn=4, env=env) as j:
+        capfd.readouterr()
+        team = j.create_team([0, 4, 1, 5, 2, 6, 3, 7])       # team rank -> context rank: nodes 0 1 0 1 ...
+        log = capfd.readouterr()
+        assert ("ring order by host: 0 2 4 6 1 3 5 7" in log.out + log.err) == (reorder == "y")
+        for count in (1, 37, 3000):
+            check_coll(team, "allgather", n, count)
+            check_coll(team, "allgatherv", n, count)
+            check_coll(team, "reduce_scatter", n, count)
+        rng = np.random.default_rng(1)
+        counts = [5, 0, 11, 2, 8, 1, 64, 3]
+        displs = np.concatenate([[0], np.cumsum(counts)[:-1]]).astype(int)
+        src = [rng.integers(-9, 9, sum(counts)).astype(np.int32) for _ in range(n)]
+        dst = [np.zeros(max(1, counts[r]), np.int32) for r in range(n)]
+        run(team, [coll_args("reduce_scatterv", src[r], dst[r], dt="int32", op="sum", dst_counts=counts, dst_displs=displs) for r in range(n)])
+        for r in range(n):
+            assert np.array_equal(dst[r][:counts[r]], np.sum(src, 0)[displs[r]:displs[r] + counts[r]]), r
+        # a sub-team keeps rank order (the host order belongs to the whole team)
+        sub = j.create_team([0, 4, 1])
+        check_coll(sub, "allgather", 3, 10)
