@@ -24,7 +24,7 @@ static ucc_config_field_t tl_shm_context_config_table[] = {
     {"BCAST_KN_RADIX", "auto", "Radix of the k-nomial tree bcast", ucc_offsetof(ucc_tl_shm_context_config_t, bcast_kn_radix), UCC_CONFIG_TYPE_UINT_RANGED},
     {"REDUCE_KN_RADIX", "auto", "Radix of the k-nomial tree reduce", ucc_offsetof(ucc_tl_shm_context_config_t, reduce_kn_radix), UCC_CONFIG_TYPE_UINT_RANGED},
     {"BARRIER_KN_RADIX", "auto", "Radix of the k-nomial barrier / fanin / fanout", ucc_offsetof(ucc_tl_shm_context_config_t, barrier_kn_radix), UCC_CONFIG_TYPE_UINT_RANGED},
-    {"ALLGATHER_KN_RADIX", "auto", "Radix of the k-nomial allgather", ucc_offsetof(ucc_tl_shm_context_config_t, allgather_kn_radix), UCC_CONFIG_TYPE_UINT_RANGED},
+    {"ALLGATHER_KN_RADIX", "auto", "Radix of the k-nomial allgather(v)", ucc_offsetof(ucc_tl_shm_context_config_t, allgather_kn_radix), UCC_CONFIG_TYPE_UINT_RANGED},
     {"GATHER_KN_RADIX", "auto", "Radix of the k-nomial gather / scatter", ucc_offsetof(ucc_tl_shm_context_config_t, gather_kn_radix), UCC_CONFIG_TYPE_UINT_RANGED},
     {"KN_RADIX", "0", "Radix of every k-nomial algorithm whose own *_KN_RADIX is left on auto (0: built-in defaults)", ucc_offsetof(ucc_tl_shm_context_config_t, kn_radix), UCC_CONFIG_TYPE_UINT},
     {"FANIN_KN_RADIX", "auto", "Radix of the k-nomial fanin (auto: BARRIER_KN_RADIX)", ucc_offsetof(ucc_tl_shm_context_config_t, fanin_kn_radix), UCC_CONFIG_TYPE_UINT},
@@ -62,10 +62,10 @@ typedef struct shm_alg { const char *name; const char *desc; ucc_tl_shm_alg_fn_t
 static const shm_alg_t algs_allreduce[] = {A("knomial", "recursive k-nomial exchange (latency)", allreduce_knomial), A("sra_knomial", "scatter-reduce by vector halving + allgather by doubling (bandwidth)", allreduce_sra),
                                            A("dbt", "double binary tree reduce + bcast", allreduce_dbt), A("ring", "ring reduce-scatter + ring allgather", allreduce_ring),
                                            A("sliding_window", "one-sided: windows of the own slice are read from the peers' buffers (pointer / CMA) and reduced", allreduce_sliding_window), {NULL}};
-static const shm_alg_t algs_allgather[] = {A("knomial", "recursive doubling", allgather_knomial), A("ring", "ring", allgather_ring), A("neighbor", "neighbor exchange (even team size)", allgather_neighbor),
+static const shm_alg_t algs_allgather[] = {A("knomial", "recursive k-ing of block sets (any team size: extra ranks through proxies)", allgather_knomial), A("ring", "ring", allgather_ring), A("neighbor", "neighbor exchange (even team size)", allgather_neighbor),
                                            A("bruck", "O(log N) Bruck allgather", allgather_bruck), A("sparbit", "O(log N) data-locality aware allgather", allgather_sparbit),
                                            A("linear", "everyone sends to everyone", allgather_linear), A("batched", "linear with bounded outstanding messages", allgather_batched), {NULL}};
-static const shm_alg_t algs_allgatherv[] = {A("ring", "ring", allgatherv_ring), A("knomial", "recursive doubling of block sets (extra ranks through proxies)", allgatherv_knomial), A("linear", "everyone sends to everyone", allgatherv_linear), {NULL}};
+static const shm_alg_t algs_allgatherv[] = {A("ring", "ring", allgatherv_ring), A("knomial", "recursive k-ing of block sets (extra ranks through proxies)", allgatherv_knomial), A("linear", "everyone sends to everyone", allgatherv_linear), {NULL}};
 static const shm_alg_t algs_alltoall[] = {A("pairwise", "pairwise exchange", alltoall_pairwise), A("bruck", "O(log N) Bruck alltoall", alltoall_bruck),
                                           A("onesided", "every rank reads its blocks directly from the peers' source buffers (pointer / CMA)", alltoall_onesided), {NULL}};
 static const shm_alg_t algs_alltoallv[] = {A("pairwise", "pairwise exchange", alltoallv_pairwise), A("hybrid", "small messages in fixed slots through Bruck's log2(N) rounds, big ones pairwise", alltoallv_hybrid),

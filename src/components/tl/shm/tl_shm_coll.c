@@ -655,22 +655,6 @@ ucc_status_t ucc_tl_shm_allgather_bruck(ucc_tl_shm_task_t *t)
 err:
     return st;
 }
-/* knomial (recursive doubling over blocks; power-of-two only, others fall back) */
-ucc_status_t ucc_tl_shm_allgather_knomial(ucc_tl_shm_task_t *t)
-{
-    size_t *cnt, *off, dts, blk; ucc_memory_type_t mt; char *dst; ucc_status_t st; ucc_rank_t N = t->vsize, r = t->vrank; unsigned step = 1;
-    if (!ucc_is_pow2(N)) return UCC_ERR_NOT_SUPPORTED;
-    CHK(ag_layout(t, 0, &cnt, &off, &dts, &mt, &dst)); blk = cnt[0];
-    CHK(ag_own_block(t, dst, cnt, off, mt));
-    for (ucc_rank_t d = 1; d < N; d *= 2, step++) {
-        ucc_rank_t peer = r ^ d, peerbase = (peer / d) * d;
-        CHK(shm_prog_send(t, peer, dst + (size_t)((r / d) * d) * blk, (size_t)d * blk, mt, step));
-        CHK(shm_prog_recv(t, peer, dst + (size_t)peerbase * blk, (size_t)d * blk, mt, step));
-        CHK(shm_prog_wait(t));
-    }
-err:
-    return st;
-}
 /* sparbit: log steps with distances N/2, N/4.. ; data locality friendly — same data motion as bruck without rotation for pow2 */
 ucc_status_t ucc_tl_shm_allgather_sparbit(ucc_tl_shm_task_t *t)
 {
@@ -691,17 +675,20 @@ ucc_status_t ucc_tl_shm_allgather_sparbit(ucc_tl_shm_task_t *t)
 err:
     return st;
 }
-/* allgatherv by recursive doubling (radix-2 k-nomial exchange, role of reference tl/ucp allgatherv knomial): log2(N) rounds, in round
- * k a rank swaps everything its group of 2^k ranks has collected so far with the partner group - blocks keep their (arbitrary)
- * displacements, so a round is a set of block-sized messages.  Ranks beyond the largest power of two hand their block to a proxy
- * first and get the complete vector from it at the end (coll_patterns/knomial_tree.h: EXTRA / PROXY). */
-ucc_status_t ucc_tl_shm_allgatherv_knomial(ucc_tl_shm_task_t *t)
+/* allgather(v) by recursive k-ing (role of reference tl/ucp allgather_knomial.c / allgatherv knomial; ALLGATHER_KN_RADIX): log_k(N) rounds over
+ * the digits of the rank, least significant first.  Before the round of weight `dist` a rank holds the blocks of the `dist` ranks that share
+ * its higher digits; it swaps that set with the k-1 ranks that differ in this digit only.  Blocks keep their (arbitrary) displacements, so a
+ * round is a set of block-sized messages.  Ranks beyond the largest power of the radix hand their block to a proxy first and get the complete
+ * vector from it at the end (coll_patterns/knomial_tree.h: EXTRA / PROXY; a proxy serves up to k-1 extras). */
+static ucc_status_t allgather_knomial_common(ucc_tl_shm_task_t *t, int is_v)
 {
-    size_t *cnt, *off, dts; ucc_memory_type_t mt; char *dst; ucc_status_t st;
-    ucc_rank_t N = t->vsize, r = t->vrank; ucc_kn_pattern_t p; unsigned round = 1;
-    ucc_kn_pattern_init(&p, r, N, 2);
+    size_t *cnt, *off, dts, tot = 0; ucc_memory_type_t mt; char *dst; ucc_status_t st;
+    ucc_rank_t N = t->vsize, r = t->vrank, peers[64]; ucc_kn_pattern_t p; unsigned round = 1, radix;
     if ((uint64_t)N * 24 > 65000) return UCC_ERR_NOT_SUPPORTED; /* message ids: (round, block) must fit 16 bits */
-    CHK(ag_layout(t, 1, &cnt, &off, &dts, &mt, &dst));
+    CHK(ag_layout(t, is_v, &cnt, &off, &dts, &mt, &dst));
+    for (ucc_rank_t i = 0; i < N; i++) tot += cnt[i];
+    radix = cfg_radix(&SHM_CTX(t->team)->cfg.allgather_kn_radix, tot, mt, SHM_CTX(t->team)->cfg.kn_radix >= 2 ? SHM_CTX(t->team)->cfg.kn_radix : 2u, N);
+    ucc_kn_pattern_init(&p, r, N, radix);
     CHK(ag_own_block(t, dst, cnt, off, mt));
 #define AGV_ID(_round, _b) ((unsigned)((_round) * N + (_b)))
     if (p.type == UCC_KN_NODE_EXTRA) {
@@ -710,24 +697,36 @@ ucc_status_t ucc_tl_shm_allgatherv_knomial(ucc_tl_shm_task_t *t)
         CHK(shm_prog_wait(t));
         return UCC_OK;
     }
-    if (p.type == UCC_KN_NODE_PROXY) { CHK(shm_prog_recv(t, p.partner, dst + off[p.partner], cnt[p.partner], mt, AGV_ID(0, p.partner))); CHK(shm_prog_wait(t)); }
-    for (ucc_rank_t mask = 1; mask < p.n_full; mask <<= 1, round++) {
-        ucc_rank_t peer = r ^ mask, mine = (r / mask) * mask, theirs = (peer / mask) * mask;
-        for (ucc_rank_t q = 0; q < mask; q++) {
-            /* every base rank q of a group stands for itself and, if it is a proxy, for rank q + n_full */
-            for (ucc_rank_t b = mine + q; b < N; b += p.n_full) CHK(shm_prog_send(t, peer, dst + off[b], cnt[b], mt, AGV_ID(round, b)));
-            for (ucc_rank_t b = theirs + q; b < N; b += p.n_full) CHK(shm_prog_recv(t, peer, dst + off[b], cnt[b], mt, AGV_ID(round, b)));
+    if (p.type == UCC_KN_NODE_PROXY) {
+        for (unsigned j = 0; j < p.n_extras; j++) { ucc_rank_t e = ucc_kn_extra(&p, j); CHK(shm_prog_recv(t, e, dst + off[e], cnt[e], mt, AGV_ID(0, e))); }
+        CHK(shm_prog_wait(t));
+    }
+    for (uint64_t dist = 1; dist < p.n_full; dist *= p.radix, round++) {
+        unsigned np = ucc_kn_round_peers(&p, dist, peers);
+        ucc_rank_t mine = (ucc_rank_t)((r / dist) * dist);
+        for (unsigned i = 0; i < np; i++) {
+            ucc_rank_t peer = peers[i], theirs = (ucc_rank_t)((peer / dist) * dist);
+            for (ucc_rank_t q = 0; q < dist; q++) {
+                /* every base rank of a set stands for itself and for the extras it proxies (rank + j * n_full) */
+                for (ucc_rank_t b = mine + q; b < N; b += p.n_full) CHK(shm_prog_send(t, peer, dst + off[b], cnt[b], mt, AGV_ID(round, b)));
+                for (ucc_rank_t b = theirs + q; b < N; b += p.n_full) CHK(shm_prog_recv(t, peer, dst + off[b], cnt[b], mt, AGV_ID(round, b)));
+            }
         }
         CHK(shm_prog_wait(t));
     }
     if (p.type == UCC_KN_NODE_PROXY) {
-        for (ucc_rank_t b = 0; b < N; b++) if (b != p.partner) CHK(shm_prog_send(t, p.partner, dst + off[b], cnt[b], mt, AGV_ID(23, b)));
+        for (unsigned j = 0; j < p.n_extras; j++) {
+            ucc_rank_t e = ucc_kn_extra(&p, j);
+            for (ucc_rank_t b = 0; b < N; b++) if (b != e) CHK(shm_prog_send(t, e, dst + off[b], cnt[b], mt, AGV_ID(23, b)));
+        }
         CHK(shm_prog_wait(t));
     }
 #undef AGV_ID
 err:
     return st;
 }
+ucc_status_t ucc_tl_shm_allgather_knomial(ucc_tl_shm_task_t *t) { return allgather_knomial_common(t, 0); }
+ucc_status_t ucc_tl_shm_allgatherv_knomial(ucc_tl_shm_task_t *t) { return allgather_knomial_common(t, 1); }
 
 /* ================================================================== */
 /* alltoall(v)                                                         */

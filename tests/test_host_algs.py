@@ -570,3 +570,15 @@ def test_ring_ranks_reordering_by_host(reorder, capfd):
         # a sub-team keeps rank order (the host order belongs to the whole team)
         sub = j.create_team([0, 4, 1])
         check_coll(sub, "allgather", 3, 10)
+
+
+@pytest.mark.parametrize("radix", ["2", "3", "4", "7", "0-1k:2,1k-inf:5"])
+def test_allgather_knomial_radix(radix):
+    """ALLGATHER_KN_RADIX: recursive k-ing on every team size (full powers, one or several extras per proxy), allgather and allgatherv"""
+    with UccJob(13, env={"UCC_TL_SHM_TUNE": "allgather:inf:@knomial#allgatherv:inf:@knomial", "UCC_TL_SHM_ALLGATHER_KN_RADIX": radix, "UCC_TLS": "shm,self"}) as job:
+        for n in (2, 3, 4, 5, 6, 7, 8, 9, 11, 13):
+            team = job.create_team(range(n))
+            for count in (1, 24, 2000):
+                check_coll(team, "allgather", n, count)
+                check_coll(team, "allgatherv", n, count)
+            team.destroy()
