@@ -21,6 +21,7 @@ static ucc_config_field_t tl_shm_context_config_table[] = {
     {"RNDV_THRESH", "16K", "Messages of at least this size are copied directly from the source buffer (same process: always; other processes: through CMA)",
      ucc_offsetof(ucc_tl_shm_context_config_t, rndv_thresh), UCC_CONFIG_TYPE_MEMUNITS},
     {"ALLREDUCE_KN_RADIX", "auto", "Radix of the recursive k-nomial allreduce (per msg range)", ucc_offsetof(ucc_tl_shm_context_config_t, allreduce_kn_radix), UCC_CONFIG_TYPE_UINT_RANGED},
+    {"ALLREDUCE_SRA_KN_RADIX", "auto", "Radix of the scatter-reduce-allgather (SRA) k-nomial allreduce (per msg range)", ucc_offsetof(ucc_tl_shm_context_config_t, allreduce_sra_kn_radix), UCC_CONFIG_TYPE_UINT_RANGED},
     {"BCAST_KN_RADIX", "auto", "Radix of the k-nomial tree bcast", ucc_offsetof(ucc_tl_shm_context_config_t, bcast_kn_radix), UCC_CONFIG_TYPE_UINT_RANGED},
     {"REDUCE_KN_RADIX", "auto", "Radix of the k-nomial tree reduce", ucc_offsetof(ucc_tl_shm_context_config_t, reduce_kn_radix), UCC_CONFIG_TYPE_UINT_RANGED},
     {"BARRIER_KN_RADIX", "auto", "Radix of the k-nomial barrier / fanin / fanout", ucc_offsetof(ucc_tl_shm_context_config_t, barrier_kn_radix), UCC_CONFIG_TYPE_UINT_RANGED},
@@ -59,7 +60,7 @@ static ucc_config_field_t tl_shm_context_config_table[] = {
 /* ------------------------------------------------------------------ */
 typedef struct shm_alg { const char *name; const char *desc; ucc_tl_shm_alg_fn_t fn; } shm_alg_t;
 #define A(_n, _d, _f) {_n, _d, ucc_tl_shm_##_f}
-static const shm_alg_t algs_allreduce[] = {A("knomial", "recursive k-nomial exchange (latency)", allreduce_knomial), A("sra_knomial", "scatter-reduce by vector halving + allgather by doubling (bandwidth)", allreduce_sra),
+static const shm_alg_t algs_allreduce[] = {A("knomial", "recursive k-nomial exchange (latency)", allreduce_knomial), A("sra_knomial", "scatter-reduce by recursive vector splitting + allgather, radix k (bandwidth)", allreduce_sra),
                                            A("dbt", "double binary tree reduce + bcast", allreduce_dbt), A("ring", "ring reduce-scatter + ring allgather", allreduce_ring),
                                            A("sliding_window", "one-sided: windows of the own slice are read from the peers' buffers (pointer / CMA) and reduced", allreduce_sliding_window), {NULL}};
 static const shm_alg_t algs_allgather[] = {A("knomial", "recursive k-ing of block sets (any team size: extra ranks through proxies)", allgather_knomial), A("ring", "ring", allgather_ring), A("neighbor", "neighbor exchange (even team size)", allgather_neighbor),

@@ -304,46 +304,55 @@ ucc_status_t ucc_tl_shm_allreduce_sliding_window(ucc_tl_shm_task_t *t)
 err:
     return st;
 }
-/* scatter-reduce by recursive vector halving + allgather by recursive doubling (radix 2 SRA) */
+/* SRA k-nomial (reference tl/ucp allreduce_sra_knomial.c; ALLREDUCE_SRA_KN_RADIX): scatter-reduce by recursive vector splitting - in the
+ * round of weight d (most significant digit first) the owned segment is cut into k parts, a rank keeps the part its digit selects, sends the
+ * other k-1 to the ranks that differ in this digit only and reduces their k-1 contributions into its part - then an allgather that walks
+ * the rounds backwards.  Ranks beyond the largest power of k add their vector at a proxy first and get the result from it. */
 ucc_status_t ucc_tl_shm_allreduce_sra(ucc_tl_shm_task_t *t)
 {
     ucc_coll_args_t *a = ARGS(t);
     size_t count = a->dst.info.count, dts = ucc_dt_size(a->dst.info.datatype), len = count * dts;
     ucc_memory_type_t mt = a->dst.info.mem_type;
     char *dst = (char *)a->dst.info.buffer; void *scratch;
-    ucc_kn_pattern_t p; ucc_status_t st; unsigned step = 3, nsteps = 0;
-    size_t off[32], cnt[32], soff[32], scnt[32], seg_off = 0, seg_cnt = count;
-    ucc_kn_pattern_init(&p, t->vrank, t->vsize, 2);
+    ucc_kn_pattern_t p; ucc_status_t st; unsigned step = 3, nsteps = 0, radix;
+    ucc_sra_seg_t segs[33]; uint64_t dists[32]; ucc_rank_t peers[64];
+    radix = cfg_radix(&SHM_CTX(t->team)->cfg.allreduce_sra_kn_radix, len, mt, SHM_CTX(t->team)->cfg.kn_radix >= 2 ? SHM_CTX(t->team)->cfg.kn_radix : 2u, t->vsize);
+    ucc_kn_pattern_init(&p, t->vrank, t->vsize, radix);
     if (count < p.n_full) return UCC_ERR_NOT_SUPPORTED;
-    CHK(shm_task_scratch(t, len, mt, &scratch));
+    CHK(shm_task_scratch(t, len + (size_t)p.radix * dts, mt, &scratch)); /* k-1 slots of ceil(cnt / k) elements can exceed cnt by up to k-1 */
     if (!UCC_IS_INPLACE(*a)) CHK(shm_prog_copy(t, dst, a->src.info.buffer, len, mt, a->src.info.mem_type));
     if (p.type == UCC_KN_NODE_EXTRA) {
         CHK(shm_prog_send(t, p.partner, dst, len, mt, 1)); CHK(shm_prog_wait(t));
         CHK(shm_prog_recv(t, p.partner, dst, len, mt, 2)); CHK(shm_prog_wait(t));
         return UCC_OK;
     }
-    if (p.type == UCC_KN_NODE_PROXY) { CHK(shm_prog_recv(t, p.partner, scratch, len, mt, 1)); CHK(shm_prog_wait(t)); CHK(shm_prog_reduce(t, dst, dst, scratch, count, mt, 0)); }
-    for (ucc_rank_t mask = p.n_full >> 1; mask > 0; mask >>= 1, step++, nsteps++) {
-        ucc_rank_t peer = t->vrank ^ mask;
-        /* the round splits the owned segment in two (coll_patterns/sra_knomial.h): I keep the half my digit selects, the peer the other */
-        const ucc_sra_seg_t seg = {seg_off, seg_cnt};
-        const unsigned digit = (t->vrank & mask) ? 1 : 0;
-        const ucc_sra_seg_t keep = ucc_sra_part(seg, 2, digit), give = ucc_sra_part(seg, 2, 1 - digit);
-        off[nsteps] = keep.off; cnt[nsteps] = keep.cnt; soff[nsteps] = give.off; scnt[nsteps] = give.cnt;
-        CHK(shm_prog_send(t, peer, dst + soff[nsteps] * dts, scnt[nsteps] * dts, mt, step));
-        CHK(shm_prog_recv(t, peer, scratch, cnt[nsteps] * dts, mt, step));
+    if (p.type == UCC_KN_NODE_PROXY)
+        for (unsigned j = 0; j < p.n_extras; j++) { CHK(shm_prog_recv(t, ucc_kn_extra(&p, j), scratch, len, mt, 1)); CHK(shm_prog_wait(t)); CHK(shm_prog_reduce(t, dst, dst, scratch, count, mt, 0)); }
+    segs[0].off = 0; segs[0].cnt = count;
+    for (uint64_t d = p.n_full / p.radix; d >= 1; d /= p.radix, step++, nsteps++) {
+        const unsigned np = ucc_kn_round_peers(&p, d, peers), digit = (unsigned)((t->vrank / d) % p.radix);
+        const ucc_sra_seg_t seg = segs[nsteps], keep = ucc_sra_part(seg, p.radix, digit);   /* coll_patterns/sra_knomial.h */
+        const size_t slot = ucc_buffer_block_count(seg.cnt, p.radix, 0) * dts;              /* the largest part */
+        dists[nsteps] = d; segs[nsteps + 1] = keep;
+        for (unsigned i = 0; i < np; i++) {
+            const ucc_sra_seg_t give = ucc_sra_part(seg, p.radix, (unsigned)((peers[i] / d) % p.radix));
+            CHK(shm_prog_send(t, peers[i], dst + give.off * dts, give.cnt * dts, mt, step));
+            CHK(shm_prog_recv(t, peers[i], (char *)scratch + i * slot, keep.cnt * dts, mt, step));
+        }
         CHK(shm_prog_wait(t));
-        CHK(shm_prog_reduce(t, dst + off[nsteps] * dts, dst + off[nsteps] * dts, scratch, cnt[nsteps], mt, 0));
-        seg_off = off[nsteps]; seg_cnt = cnt[nsteps];
+        for (unsigned i = 0; i < np; i++) CHK(shm_prog_reduce(t, dst + keep.off * dts, dst + keep.off * dts, (char *)scratch + i * slot, keep.cnt, mt, 0));
     }
-    if (t->op == UCC_OP_AVG) CHK(shm_prog_reduce(t, dst + seg_off * dts, dst + seg_off * dts, NULL, seg_cnt, mt, 1));
-    for (int i = (int)nsteps - 1; i >= 0; i--, step++) {
-        ucc_rank_t peer = t->vrank ^ (ucc_rank_t)(1u << (nsteps - 1 - (unsigned)i));
-        CHK(shm_prog_send(t, peer, dst + off[i] * dts, cnt[i] * dts, mt, step));
-        CHK(shm_prog_recv(t, peer, dst + soff[i] * dts, scnt[i] * dts, mt, step));
+    if (t->op == UCC_OP_AVG) CHK(shm_prog_reduce(t, dst + segs[nsteps].off * dts, dst + segs[nsteps].off * dts, NULL, segs[nsteps].cnt, mt, 1));
+    for (int i = (int)nsteps - 1; i >= 0; i--, step++) { /* allgather: round i's peers hold the other parts of segs[i] */
+        const unsigned np = ucc_kn_round_peers(&p, dists[i], peers);
+        for (unsigned q = 0; q < np; q++) {
+            const ucc_sra_seg_t theirs = ucc_sra_part(segs[i], p.radix, (unsigned)((peers[q] / dists[i]) % p.radix));
+            CHK(shm_prog_send(t, peers[q], dst + segs[i + 1].off * dts, segs[i + 1].cnt * dts, mt, step));
+            CHK(shm_prog_recv(t, peers[q], dst + theirs.off * dts, theirs.cnt * dts, mt, step));
+        }
         CHK(shm_prog_wait(t));
     }
-    if (p.type == UCC_KN_NODE_PROXY) { CHK(shm_prog_send(t, p.partner, dst, len, mt, 2)); CHK(shm_prog_wait(t)); }
+    if (p.type == UCC_KN_NODE_PROXY) { for (unsigned j = 0; j < p.n_extras; j++) CHK(shm_prog_send(t, ucc_kn_extra(&p, j), dst, len, mt, 2)); CHK(shm_prog_wait(t)); }
 err:
     return st;
 }

@@ -582,3 +582,26 @@ def test_allgather_knomial_radix(radix):
                 check_coll(team, "allgather", n, count)
                 check_coll(team, "allgatherv", n, count)
             team.destroy()
+
+
+@pytest.mark.parametrize("radix", ["2", "3", "4", "8", "0-4k:4,4k-inf:2"])
+def test_allreduce_sra_knomial_radix(radix):
+    """ALLREDUCE_SRA_KN_RADIX: scatter-reduce / allgather over the digits of the rank in base k; every team size (extras through proxies),
+    counts that do not divide, in place, AVG, persistent re-posts"""
+    with UccJob(13, env={"UCC_TL_SHM_TUNE": "allreduce:inf:@sra_knomial", "UCC_TL_SHM_ALLREDUCE_SRA_KN_RADIX": radix, "UCC_TLS": "shm,self"}) as job:
+        rng = np.random.default_rng(5)
+        for n in (2, 3, 4, 5, 7, 8, 9, 12, 13):
+            team = job.create_team(range(n))
+            for count in (n, 17, 1000, 4099):
+                for op in ("sum", "avg"):
+                    for inplace in (False, True):
+                        src = [rng.integers(-1000, 1000, count).astype(np.float64) for _ in range(n)]
+                        exp = np.sum(src, 0) / (n if op == "avg" else 1)
+                        dst = [s.copy() for s in src] if inplace else [np.zeros(count) for _ in range(n)]
+                        req = team.coll([coll_args("allreduce", None if inplace else src[r], dst[r], dt="float64", op=op, inplace=inplace, persistent=not inplace) for r in range(n)])
+                        for rep in range(1 if inplace else 2):
+                            assert req.run() == U.UCC_OK
+                            for r in range(n):
+                                assert np.allclose(dst[r], exp), (n, count, op, inplace, rep, r)
+                        req.finalize()
+            team.destroy()
