@@ -304,55 +304,75 @@ ucc_status_t ucc_tl_shm_allreduce_sliding_window(ucc_tl_shm_task_t *t)
 err:
     return st;
 }
-/* SRA k-nomial (reference tl/ucp allreduce_sra_knomial.c; ALLREDUCE_SRA_KN_RADIX): scatter-reduce by recursive vector splitting - in the
- * round of weight d (most significant digit first) the owned segment is cut into k parts, a rank keeps the part its digit selects, sends the
- * other k-1 to the ranks that differ in this digit only and reduces their k-1 contributions into its part - then an allgather that walks
- * the rounds backwards.  Ranks beyond the largest power of k add their vector at a proxy first and get the result from it. */
-ucc_status_t ucc_tl_shm_allreduce_sra(ucc_tl_shm_task_t *t)
+/* SRA k-nomial (reference tl/ucp allreduce_sra_knomial.c, reduce_srg_knomial.c; ALLREDUCE_SRA_KN_RADIX, REDUCE_SRG_KN_RADIX): scatter-reduce by
+ * recursive vector splitting - in the round of weight d (most significant digit first) the owned segment is cut into k parts, a rank keeps the
+ * part its digit selects, sends the other k-1 to the ranks that differ in this digit only and reduces their k-1 contributions into its part -
+ * then the rounds are walked backwards: as an allgather (allreduce), or as a gather towards the rank whose digits are all zero (reduce: the
+ * root, ranks are rotated so that it is virtual rank 0).  Ranks beyond the largest power of k add their vector at a proxy first (and get the
+ * result from it in the allreduce).  `w` holds the rank's contribution and, where one is due, the result; scratch: count + k elements. */
+static ucc_status_t prog_sra_kn(ucc_tl_shm_task_t *t, char *w, void *scratch, size_t count, size_t dts, ucc_memory_type_t mt, unsigned radix, ucc_rank_t root, int gather_only)
 {
-    ucc_coll_args_t *a = ARGS(t);
-    size_t count = a->dst.info.count, dts = ucc_dt_size(a->dst.info.datatype), len = count * dts;
-    ucc_memory_type_t mt = a->dst.info.mem_type;
-    char *dst = (char *)a->dst.info.buffer; void *scratch;
-    ucc_kn_pattern_t p; ucc_status_t st; unsigned step = 3, nsteps = 0, radix;
+    const ucc_rank_t N = t->vsize, vr = (ucc_rank_t)((t->vrank + N - root) % N);
+    const size_t len = count * dts;
+    ucc_kn_pattern_t p; ucc_status_t st = UCC_OK; unsigned step = 3, nsteps = 0;
     ucc_sra_seg_t segs[33]; uint64_t dists[32]; ucc_rank_t peers[64];
-    radix = cfg_radix(&SHM_CTX(t->team)->cfg.allreduce_sra_kn_radix, len, mt, SHM_CTX(t->team)->cfg.kn_radix >= 2 ? SHM_CTX(t->team)->cfg.kn_radix : 2u, t->vsize);
-    ucc_kn_pattern_init(&p, t->vrank, t->vsize, radix);
-    if (count < p.n_full) return UCC_ERR_NOT_SUPPORTED;
-    CHK(shm_task_scratch(t, len + (size_t)p.radix * dts, mt, &scratch)); /* k-1 slots of ceil(cnt / k) elements can exceed cnt by up to k-1 */
-    if (!UCC_IS_INPLACE(*a)) CHK(shm_prog_copy(t, dst, a->src.info.buffer, len, mt, a->src.info.mem_type));
+#define SRA_RANK(_v) ((ucc_rank_t)(((_v) + root) % N))
+    ucc_kn_pattern_init(&p, vr, N, radix);
     if (p.type == UCC_KN_NODE_EXTRA) {
-        CHK(shm_prog_send(t, p.partner, dst, len, mt, 1)); CHK(shm_prog_wait(t));
-        CHK(shm_prog_recv(t, p.partner, dst, len, mt, 2)); CHK(shm_prog_wait(t));
+        CHK(shm_prog_send(t, SRA_RANK(p.partner), w, len, mt, 1)); CHK(shm_prog_wait(t));
+        if (!gather_only) { CHK(shm_prog_recv(t, SRA_RANK(p.partner), w, len, mt, 2)); CHK(shm_prog_wait(t)); }
         return UCC_OK;
     }
     if (p.type == UCC_KN_NODE_PROXY)
-        for (unsigned j = 0; j < p.n_extras; j++) { CHK(shm_prog_recv(t, ucc_kn_extra(&p, j), scratch, len, mt, 1)); CHK(shm_prog_wait(t)); CHK(shm_prog_reduce(t, dst, dst, scratch, count, mt, 0)); }
+        for (unsigned j = 0; j < p.n_extras; j++) { CHK(shm_prog_recv(t, SRA_RANK(ucc_kn_extra(&p, j)), scratch, len, mt, 1)); CHK(shm_prog_wait(t)); CHK(shm_prog_reduce(t, w, w, scratch, count, mt, 0)); }
     segs[0].off = 0; segs[0].cnt = count;
     for (uint64_t d = p.n_full / p.radix; d >= 1; d /= p.radix, step++, nsteps++) {
-        const unsigned np = ucc_kn_round_peers(&p, d, peers), digit = (unsigned)((t->vrank / d) % p.radix);
+        const unsigned np = ucc_kn_round_peers(&p, d, peers), digit = (unsigned)((vr / d) % p.radix);
         const ucc_sra_seg_t seg = segs[nsteps], keep = ucc_sra_part(seg, p.radix, digit);   /* coll_patterns/sra_knomial.h */
         const size_t slot = ucc_buffer_block_count(seg.cnt, p.radix, 0) * dts;              /* the largest part */
         dists[nsteps] = d; segs[nsteps + 1] = keep;
         for (unsigned i = 0; i < np; i++) {
             const ucc_sra_seg_t give = ucc_sra_part(seg, p.radix, (unsigned)((peers[i] / d) % p.radix));
-            CHK(shm_prog_send(t, peers[i], dst + give.off * dts, give.cnt * dts, mt, step));
-            CHK(shm_prog_recv(t, peers[i], (char *)scratch + i * slot, keep.cnt * dts, mt, step));
+            CHK(shm_prog_send(t, SRA_RANK(peers[i]), w + give.off * dts, give.cnt * dts, mt, step));
+            CHK(shm_prog_recv(t, SRA_RANK(peers[i]), (char *)scratch + i * slot, keep.cnt * dts, mt, step));
         }
         CHK(shm_prog_wait(t));
-        for (unsigned i = 0; i < np; i++) CHK(shm_prog_reduce(t, dst + keep.off * dts, dst + keep.off * dts, (char *)scratch + i * slot, keep.cnt, mt, 0));
+        for (unsigned i = 0; i < np; i++) CHK(shm_prog_reduce(t, w + keep.off * dts, w + keep.off * dts, (char *)scratch + i * slot, keep.cnt, mt, 0));
     }
-    if (t->op == UCC_OP_AVG) CHK(shm_prog_reduce(t, dst + segs[nsteps].off * dts, dst + segs[nsteps].off * dts, NULL, segs[nsteps].cnt, mt, 1));
-    for (int i = (int)nsteps - 1; i >= 0; i--, step++) { /* allgather: round i's peers hold the other parts of segs[i] */
-        const unsigned np = ucc_kn_round_peers(&p, dists[i], peers);
+    if (t->op == UCC_OP_AVG) CHK(shm_prog_reduce(t, w + segs[nsteps].off * dts, w + segs[nsteps].off * dts, NULL, segs[nsteps].cnt, mt, 1));
+    for (int i = (int)nsteps - 1; i >= 0; i--, step++) { /* round i's peers hold the other parts of segs[i] */
+        const unsigned np = ucc_kn_round_peers(&p, dists[i], peers), digit = (unsigned)((vr / dists[i]) % p.radix);
+        if (gather_only && digit) { /* hand the collected segment to the member of the group that is closer to the root; done */
+            CHK(shm_prog_send(t, SRA_RANK((ucc_rank_t)(vr - digit * dists[i])), w + segs[i + 1].off * dts, segs[i + 1].cnt * dts, mt, step));
+            CHK(shm_prog_wait(t));
+            return UCC_OK;
+        }
         for (unsigned q = 0; q < np; q++) {
             const ucc_sra_seg_t theirs = ucc_sra_part(segs[i], p.radix, (unsigned)((peers[q] / dists[i]) % p.radix));
-            CHK(shm_prog_send(t, peers[q], dst + segs[i + 1].off * dts, segs[i + 1].cnt * dts, mt, step));
-            CHK(shm_prog_recv(t, peers[q], dst + theirs.off * dts, theirs.cnt * dts, mt, step));
+            if (!gather_only) CHK(shm_prog_send(t, SRA_RANK(peers[q]), w + segs[i + 1].off * dts, segs[i + 1].cnt * dts, mt, step));
+            CHK(shm_prog_recv(t, SRA_RANK(peers[q]), w + theirs.off * dts, theirs.cnt * dts, mt, step));
         }
         CHK(shm_prog_wait(t));
     }
-    if (p.type == UCC_KN_NODE_PROXY) { for (unsigned j = 0; j < p.n_extras; j++) CHK(shm_prog_send(t, ucc_kn_extra(&p, j), dst, len, mt, 2)); CHK(shm_prog_wait(t)); }
+    if (p.type == UCC_KN_NODE_PROXY && !gather_only) { for (unsigned j = 0; j < p.n_extras; j++) CHK(shm_prog_send(t, SRA_RANK(ucc_kn_extra(&p, j)), w, len, mt, 2)); CHK(shm_prog_wait(t)); }
+#undef SRA_RANK
+err:
+    return st;
+}
+static unsigned sra_radix(ucc_tl_shm_task_t *t, const ucc_mrange_uint_t *r, size_t len, ucc_memory_type_t mt)
+{ return cfg_radix(r, len, mt, SHM_CTX(t->team)->cfg.kn_radix >= 2 ? SHM_CTX(t->team)->cfg.kn_radix : 2u, t->vsize); }
+static int sra_fits(ucc_rank_t N, unsigned radix, size_t count) { uint64_t f = 1; while (f * radix <= N) f *= radix; return count >= f; } /* every rank of the full power gets a part */
+ucc_status_t ucc_tl_shm_allreduce_sra(ucc_tl_shm_task_t *t)
+{
+    ucc_coll_args_t *a = ARGS(t);
+    size_t count = a->dst.info.count, dts = ucc_dt_size(a->dst.info.datatype), len = count * dts;
+    ucc_memory_type_t mt = a->dst.info.mem_type;
+    unsigned radix = sra_radix(t, &SHM_CTX(t->team)->cfg.allreduce_sra_kn_radix, len, mt);
+    void *scratch; ucc_status_t st;
+    if (!sra_fits(t->vsize, radix, count)) return UCC_ERR_NOT_SUPPORTED;
+    CHK(shm_task_scratch(t, len + (size_t)radix * dts, mt, &scratch)); /* k-1 slots of ceil(cnt / k) elements can exceed cnt by up to k-1 */
+    if (!UCC_IS_INPLACE(*a)) CHK(shm_prog_copy(t, a->dst.info.buffer, a->src.info.buffer, len, mt, a->src.info.mem_type));
+    CHK(prog_sra_kn(t, (char *)a->dst.info.buffer, scratch, count, dts, mt, radix, 0, 0));
 err:
     return st;
 }
@@ -415,26 +435,22 @@ ucc_status_t ucc_tl_shm_reduce_knomial(ucc_tl_shm_task_t *t)
 err:
     return st;
 }
-/* scatter-reduce (ring) followed by gather to the root: bandwidth optimal */
+/* scatter-reduce followed by a gather to the root, both k-nomial (reference reduce_srg_knomial.c): bandwidth optimal */
 ucc_status_t ucc_tl_shm_reduce_srg(ucc_tl_shm_task_t *t)
 {
     ucc_coll_args_t *a = ARGS(t);
-    ucc_rank_t root = (ucc_rank_t)a->root, N = t->vsize; int is_root = t->vrank == root;
+    ucc_rank_t root = (ucc_rank_t)a->root; int is_root = t->vrank == root;
     size_t count = is_root ? a->dst.info.count : a->src.info.count;
     ucc_datatype_t dt = is_root ? a->dst.info.datatype : a->src.info.datatype;
     ucc_memory_type_t mt = is_root ? a->dst.info.mem_type : a->src.info.mem_type;
     size_t dts = ucc_dt_size(dt);
-    void *work, *scratch; char *w; ucc_status_t st;
-    if (count < N) return UCC_ERR_NOT_SUPPORTED;
-    CHK(shm_task_scratch(t, ucc_div_round_up(count, N) * dts, mt, &scratch));
+    unsigned radix = sra_radix(t, &SHM_CTX(t->team)->cfg.reduce_srg_kn_radix, count * dts, mt);
+    void *work, *scratch; ucc_status_t st;
+    if (!sra_fits(t->vsize, radix, count)) return UCC_ERR_NOT_SUPPORTED;
+    CHK(shm_task_scratch(t, (count + radix) * dts, mt, &scratch));
     if (is_root) { work = a->dst.info.buffer; if (!UCC_IS_INPLACE(*a)) CHK(shm_prog_copy(t, work, a->src.info.buffer, count * dts, mt, a->src.info.mem_type)); }
     else { CHK(shm_task_scratch(t, count * dts, mt, &work)); CHK(shm_prog_copy(t, work, a->src.info.buffer, count * dts, mt, mt)); }
-    w = (char *)work;
-    CHK(prog_rs_ring(t, w, scratch, count, mt, 1, 1));
-    if (t->op == UCC_OP_AVG) CHK(shm_prog_reduce(t, w + ucc_buffer_block_offset(count, N, t->vrank) * dts, w + ucc_buffer_block_offset(count, N, t->vrank) * dts, NULL, ucc_buffer_block_count(count, N, t->vrank), mt, 1));
-    if (is_root) { for (ucc_rank_t r = 0; r < N; r++) if (r != root) CHK(shm_prog_recv(t, r, w + ucc_buffer_block_offset(count, N, r) * dts, ucc_buffer_block_count(count, N, r) * dts, mt, 1 + N)); }
-    else CHK(shm_prog_send(t, root, w + ucc_buffer_block_offset(count, N, t->vrank) * dts, ucc_buffer_block_count(count, N, t->vrank) * dts, mt, 1 + N));
-    CHK(shm_prog_wait(t));
+    CHK(prog_sra_kn(t, (char *)work, scratch, count, dts, mt, radix, root, 1));
 err:
     return st;
 }

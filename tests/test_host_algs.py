@@ -605,3 +605,26 @@ def test_allreduce_sra_knomial_radix(radix):
                                 assert np.allclose(dst[r], exp), (n, count, op, inplace, rep, r)
                         req.finalize()
             team.destroy()
+
+
+@pytest.mark.parametrize("radix", ["2", "3", "4", "0-4k:5,4k-inf:2"])
+def test_reduce_srg_knomial_radix(radix):
+    """REDUCE_SRG_KN_RADIX: k-nomial scatter-reduce + k-nomial gather towards the root (ranks rotated so that the root has all-zero digits);
+    every root, team sizes with extras, in place at the root, AVG, sources untouched"""
+    with UccJob(11, env={"UCC_TL_SHM_TUNE": "reduce:inf:@srg", "UCC_TL_SHM_REDUCE_SRG_KN_RADIX": radix, "UCC_TLS": "shm,self"}) as job:
+        rng = np.random.default_rng(6)
+        for n in (2, 3, 4, 5, 7, 8, 9, 11):
+            team = job.create_team(range(n))
+            for count in (n, 29, 3001):
+                for root in sorted({0, 1, n // 2, n - 1}):
+                    for op in ("sum", "avg"):
+                        for inplace in (False, True):
+                            src = [rng.integers(-1000, 1000, count).astype(np.float64) for _ in range(n)]
+                            keep = [s_.copy() for s_ in src]
+                            dst = src[root].copy() if inplace else np.zeros(count)
+                            run(team, [coll_args("reduce", None if (inplace and r == root) else src[r], dst if r == root else None, dt="float64", op=op, root=root,
+                                                 count_dst=count, inplace=inplace and r == root) for r in range(n)])
+                            assert np.allclose(dst, np.sum(keep, 0) / (n if op == "avg" else 1)), (n, count, root, op, inplace)
+                            for r in range(n):
+                                assert np.array_equal(src[r], keep[r])
+            team.destroy()
