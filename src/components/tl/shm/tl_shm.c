@@ -23,6 +23,7 @@ static ucc_config_field_t tl_shm_context_config_table[] = {
     {"ALLREDUCE_KN_RADIX", "auto", "Radix of the recursive k-nomial allreduce (per msg range)", ucc_offsetof(ucc_tl_shm_context_config_t, allreduce_kn_radix), UCC_CONFIG_TYPE_UINT_RANGED},
     {"ALLREDUCE_SRA_KN_RADIX", "auto", "Radix of the scatter-reduce-allgather (SRA) k-nomial allreduce (per msg range)", ucc_offsetof(ucc_tl_shm_context_config_t, allreduce_sra_kn_radix), UCC_CONFIG_TYPE_UINT_RANGED},
     {"REDUCE_SRG_KN_RADIX", "auto", "Radix of the scatter-reduce-gather (SRG) k-nomial reduce (per msg range)", ucc_offsetof(ucc_tl_shm_context_config_t, reduce_srg_kn_radix), UCC_CONFIG_TYPE_UINT_RANGED},
+    {"REDUCE_SCATTER_KN_RADIX", "auto", "Radix of the k-nomial reduce_scatter (teams of radix^m ranks; other power-of-two teams use recursive halving)", ucc_offsetof(ucc_tl_shm_context_config_t, reduce_scatter_kn_radix), UCC_CONFIG_TYPE_UINT_RANGED},
     {"BCAST_KN_RADIX", "auto", "Radix of the k-nomial tree bcast", ucc_offsetof(ucc_tl_shm_context_config_t, bcast_kn_radix), UCC_CONFIG_TYPE_UINT_RANGED},
     {"REDUCE_KN_RADIX", "auto", "Radix of the k-nomial tree reduce", ucc_offsetof(ucc_tl_shm_context_config_t, reduce_kn_radix), UCC_CONFIG_TYPE_UINT_RANGED},
     {"BARRIER_KN_RADIX", "auto", "Radix of the k-nomial barrier / fanin / fanout", ucc_offsetof(ucc_tl_shm_context_config_t, barrier_kn_radix), UCC_CONFIG_TYPE_UINT_RANGED},
@@ -79,7 +80,7 @@ static const shm_alg_t algs_fanout[] = {A("knomial", "k-nomial tree", fanout_kno
 static const shm_alg_t algs_gather[] = {A("knomial", "k-nomial tree", gather_knomial), A("linear", "root receives from everyone", gather_linear), {NULL}};
 static const shm_alg_t algs_gatherv[] = {A("linear", "root receives from everyone", gatherv_linear), {NULL}};
 static const shm_alg_t algs_reduce[] = {A("knomial", "k-nomial tree", reduce_knomial), A("dbt", "double binary tree", reduce_dbt), A("srg", "k-nomial scatter-reduce + gather", reduce_srg), {NULL}};
-static const shm_alg_t algs_reduce_scatter[] = {A("ring", "ring", reduce_scatter_ring), A("knomial", "recursive halving (power-of-two teams)", reduce_scatter_knomial), {NULL}};
+static const shm_alg_t algs_reduce_scatter[] = {A("ring", "ring", reduce_scatter_ring), A("knomial", "k-nomial scatter-reduce (teams of radix^m ranks) / recursive halving (power-of-two teams)", reduce_scatter_knomial), {NULL}};
 static const shm_alg_t algs_reduce_scatterv[] = {A("ring", "ring", reduce_scatterv_ring), {NULL}};
 static const shm_alg_t algs_scatter[] = {A("knomial", "k-nomial tree", scatter_knomial), A("linear", "root sends to everyone", scatter_linear), {NULL}};
 static const shm_alg_t algs_scatterv[] = {A("linear", "root sends to everyone", scatterv_linear), {NULL}};

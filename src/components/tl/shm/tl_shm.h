@@ -64,7 +64,7 @@ typedef struct ucc_tl_shm_context_config {
     size_t    cell_payload;      /* eager payload per cell */
     size_t    rndv_thresh;       /* rendezvous (single copy) threshold: same process, or other processes through CMA */
     int       cma;               /* ternary: cross-memory-attach rendezvous between processes */
-    ucc_mrange_uint_t allreduce_kn_radix, allreduce_sra_kn_radix, reduce_srg_kn_radix, bcast_kn_radix, bcast_sag_kn_radix, reduce_kn_radix, barrier_kn_radix, allgather_kn_radix, gather_kn_radix;
+    ucc_mrange_uint_t allreduce_kn_radix, allreduce_sra_kn_radix, reduce_srg_kn_radix, reduce_scatter_kn_radix, bcast_kn_radix, bcast_sag_kn_radix, reduce_kn_radix, barrier_kn_radix, allgather_kn_radix, gather_kn_radix;
     unsigned  kn_radix;          /* > 0: default of every k-nomial radix that is left on auto */
     unsigned  fanin_kn_radix, fanout_kn_radix, scatter_kn_radix;   /* 0 / auto: follow BARRIER_KN_RADIX (fanin, fanout) / GATHER_KN_RADIX (scatter) */
     unsigned  alltoall_pairwise_num_posts, alltoallv_pairwise_num_posts, allgather_batched_num_posts, gatherv_linear_num_posts, scatterv_linear_num_posts;

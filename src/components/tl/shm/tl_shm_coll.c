@@ -310,7 +310,7 @@ err:
  * then the rounds are walked backwards: as an allgather (allreduce), or as a gather towards the rank whose digits are all zero (reduce: the
  * root, ranks are rotated so that it is virtual rank 0).  Ranks beyond the largest power of k add their vector at a proxy first (and get the
  * result from it in the allreduce).  `w` holds the rank's contribution and, where one is due, the result; scratch: count + k elements. */
-static ucc_status_t prog_sra_kn(ucc_tl_shm_task_t *t, char *w, void *scratch, size_t count, size_t dts, ucc_memory_type_t mt, unsigned radix, ucc_rank_t root, int gather_only)
+static ucc_status_t prog_sra_kn(ucc_tl_shm_task_t *t, char *w, void *scratch, size_t count, size_t dts, ucc_memory_type_t mt, unsigned radix, ucc_rank_t root, int gather_only /* 0: allgather, 1: gather to the root, 2: neither */)
 {
     const ucc_rank_t N = t->vsize, vr = (ucc_rank_t)((t->vrank + N - root) % N);
     const size_t len = count * dts;
@@ -340,6 +340,7 @@ static ucc_status_t prog_sra_kn(ucc_tl_shm_task_t *t, char *w, void *scratch, si
         for (unsigned i = 0; i < np; i++) CHK(shm_prog_reduce(t, w + keep.off * dts, w + keep.off * dts, (char *)scratch + i * slot, keep.cnt, mt, 0));
     }
     if (t->op == UCC_OP_AVG) CHK(shm_prog_reduce(t, w + segs[nsteps].off * dts, w + segs[nsteps].off * dts, NULL, segs[nsteps].cnt, mt, 1));
+    if (gather_only == 2) return UCC_OK; /* reduce_scatter: every rank keeps its part */
     for (int i = (int)nsteps - 1; i >= 0; i--, step++) { /* round i's peers hold the other parts of segs[i] */
         const unsigned np = ucc_kn_round_peers(&p, dists[i], peers), digit = (unsigned)((vr / dists[i]) % p.radix);
         if (gather_only && digit) { /* hand the collected segment to the member of the group that is closer to the root; done */
@@ -547,7 +548,8 @@ err:
 }
 ucc_status_t ucc_tl_shm_reduce_scatter_ring(ucc_tl_shm_task_t *t) { return reduce_scatter_common(t, 0); }
 ucc_status_t ucc_tl_shm_reduce_scatterv_ring(ucc_tl_shm_task_t *t) { return reduce_scatter_common(t, 1); }
-/* recursive halving (power-of-two teams): log2(N) steps, each exchanging half of the remaining range */
+/* k-nomial scatter-reduce on teams of k^m ranks; recursive halving (power-of-two teams, any block sizes): log2(N) steps, each exchanging half of
+ * the remaining range */
 ucc_status_t ucc_tl_shm_reduce_scatter_knomial(ucc_tl_shm_task_t *t)
 {
     ucc_coll_args_t *a = ARGS(t);
@@ -555,6 +557,18 @@ ucc_status_t ucc_tl_shm_reduce_scatter_knomial(ucc_tl_shm_task_t *t)
     ucc_memory_type_t mt = a->dst.info.mem_type;
     size_t dts = ucc_dt_size(a->dst.info.datatype), total = inplace ? a->dst.info.count : a->dst.info.count * N;
     void *work, *scratch; char *w; ucc_status_t st; unsigned step = 1;
+    unsigned radix = sra_radix(t, &SHM_CTX(t->team)->cfg.reduce_scatter_kn_radix, total * dts, mt); uint64_t full = 1;
+    while (full * radix <= N) full *= radix;
+    if (full == N && total % N == 0) {
+        /* REDUCE_SCATTER_KN_RADIX (reference reduce_scatter_knomial.c): on a team of k^m ranks with equal blocks the scatter-reduce half of the
+         * SRA program leaves rank r with block r (the digits of r, most significant first, select the part of every round) */
+        CHK(shm_task_scratch(t, (total + radix) * dts, mt, &scratch));
+        if (inplace) work = a->dst.info.buffer;
+        else { CHK(shm_task_scratch(t, total * dts, mt, &work)); CHK(shm_prog_copy(t, work, a->src.info.buffer, total * dts, mt, a->src.info.mem_type)); }
+        CHK(prog_sra_kn(t, (char *)work, scratch, total, dts, mt, radix, 0, 2));
+        if (!inplace) CHK(shm_prog_copy(t, a->dst.info.buffer, (char *)work + (size_t)r * (total / N) * dts, total / N * dts, mt, mt));
+        return UCC_OK;
+    }
     if (!ucc_is_pow2(N)) return UCC_ERR_NOT_SUPPORTED;
     CHK(shm_task_scratch(t, (total / 2 + N) * dts, mt, &scratch));
     if (inplace) work = a->dst.info.buffer;

@@ -628,3 +628,22 @@ def test_reduce_srg_knomial_radix(radix):
                             for r in range(n):
                                 assert np.array_equal(src[r], keep[r])
             team.destroy()
+
+
+@pytest.mark.parametrize("radix", ["2", "3", "4", "8"])
+def test_reduce_scatter_knomial_radix(radix):
+    """REDUCE_SCATTER_KN_RADIX: k-nomial scatter-reduce where the team is a power of the radix, recursive halving on other power-of-two teams, ring
+    (fallback) elsewhere; in place too"""
+    with UccJob(9, env={"UCC_TL_SHM_TUNE": "reduce_scatter:inf:@knomial", "UCC_TL_SHM_REDUCE_SCATTER_KN_RADIX": radix, "UCC_TLS": "shm,self"}) as job:
+        rng = np.random.default_rng(8)
+        for n in (2, 3, 4, 6, 8, 9):
+            team = job.create_team(range(n))
+            for count in (1, 7, 1025):
+                for op in ("sum", "avg"):
+                    check_coll(team, "reduce_scatter", n, count)
+                    buf = [rng.integers(-99, 99, count * n).astype(np.float64) for _ in range(n)]
+                    exp = np.sum(buf, 0) / (n if op == "avg" else 1)
+                    run(team, [coll_args("reduce_scatter", None, buf[r], dt="float64", op=op, inplace=True) for r in range(n)])
+                    for r in range(n):
+                        assert np.allclose(buf[r][r * count:(r + 1) * count], exp[r * count:(r + 1) * count]), (n, count, op, r)
+            team.destroy()
