@@ -24,6 +24,8 @@ static ucc_config_field_t tl_shm_context_config_table[] = {
     {"ALLREDUCE_SRA_KN_RADIX", "auto", "Radix of the scatter-reduce-allgather (SRA) k-nomial allreduce (per msg range)", ucc_offsetof(ucc_tl_shm_context_config_t, allreduce_sra_kn_radix), UCC_CONFIG_TYPE_UINT_RANGED},
     {"REDUCE_SRG_KN_RADIX", "auto", "Radix of the scatter-reduce-gather (SRG) k-nomial reduce (per msg range)", ucc_offsetof(ucc_tl_shm_context_config_t, reduce_srg_kn_radix), UCC_CONFIG_TYPE_UINT_RANGED},
     {"REDUCE_SCATTER_KN_RADIX", "auto", "Radix of the k-nomial reduce_scatter (teams of radix^m ranks; other power-of-two teams use recursive halving)", ucc_offsetof(ucc_tl_shm_context_config_t, reduce_scatter_kn_radix), UCC_CONFIG_TYPE_UINT_RANGED},
+    {"ALLREDUCE_SLIDING_WIN_BUF_SIZE", "512K", "Window of the sliding_window allreduce: bytes of the own slice fetched from each peer and reduced per step",
+     ucc_offsetof(ucc_tl_shm_context_config_t, allreduce_sliding_win_buf_size), UCC_CONFIG_TYPE_MEMUNITS},
     {"BCAST_KN_RADIX", "auto", "Radix of the k-nomial tree bcast", ucc_offsetof(ucc_tl_shm_context_config_t, bcast_kn_radix), UCC_CONFIG_TYPE_UINT_RANGED},
     {"REDUCE_KN_RADIX", "auto", "Radix of the k-nomial tree reduce", ucc_offsetof(ucc_tl_shm_context_config_t, reduce_kn_radix), UCC_CONFIG_TYPE_UINT_RANGED},
     {"BARRIER_KN_RADIX", "auto", "Radix of the k-nomial barrier / fanin / fanout", ucc_offsetof(ucc_tl_shm_context_config_t, barrier_kn_radix), UCC_CONFIG_TYPE_UINT_RANGED},

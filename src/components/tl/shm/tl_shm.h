@@ -71,6 +71,7 @@ typedef struct ucc_tl_shm_context_config {
     int       reduce_scatter_ring_bidirectional, reduce_scatterv_ring_bidirectional;
     int       use_topo;          /* ternary: may the transport look at the team topology */
     int       ranks_reordering;  /* ring algorithms walk the members host by host (needs the topology) */
+    size_t    allreduce_sliding_win_buf_size; /* sliding_window allreduce: bytes fetched from a peer and reduced per step */
     size_t    alltoallv_hybrid_thresh;   /* alltoallv `hybrid`: messages up to this size ride the Bruck rounds */
     int       reduce_avg_pre_op;
     ucc_pipeline_params_t allreduce_sra_kn_pipeline;

@@ -267,7 +267,7 @@ err:
 ucc_status_t ucc_tl_shm_allreduce_sliding_window(ucc_tl_shm_task_t *t)
 {
     ucc_coll_args_t *a = ARGS(t);
-    size_t count = a->dst.info.count, dts = ucc_dt_size(a->dst.info.datatype), win = (512u << 10) / dts, mo, mc;
+    size_t count = a->dst.info.count, dts = ucc_dt_size(a->dst.info.datatype), win = SHM_CTX(t->team)->cfg.allreduce_sliding_win_buf_size / dts, mo, mc;
     ucc_memory_type_t mt = a->dst.info.mem_type; ucc_rank_t N = t->vsize, r = t->vrank;
     char *dst = (char *)a->dst.info.buffer, *src = UCC_IS_INPLACE(*a) ? dst : (char *)a->src.info.buffer, *tok;
     void *sv, *scratch; uint64_t *out, *in; ucc_status_t st;

@@ -147,12 +147,14 @@ def test_tl_coll_plugin_example(monkeypatch):
         assert got == expect, (score, out.stdout)
 
 
+@pytest.mark.parametrize("win,count", [("512K", 400_003), ("4K", 20_011), ("1", 301)])
 @pytest.mark.parametrize("n", [2, 3, 5])
-def test_sliding_window_multi_window_inplace(n):
-    with UccJob(n, env={"UCC_TL_SHM_TUNE": "allreduce:inf:@sliding_window"}) as job:
+def test_sliding_window_multi_window_inplace(n, win, count):
+    """several windows per slice: float64 slices of > 1 MB with the default 512 KB window, small vectors with ALLREDUCE_SLIDING_WIN_BUF_SIZE
+    turned down (a window below one element is one element)"""
+    with UccJob(n, env={"UCC_TL_SHM_TUNE": "allreduce:inf:@sliding_window", "UCC_TL_SHM_ALLREDUCE_SLIDING_WIN_BUF_SIZE": win}) as job:
         team = job.create_team()
         rng = np.random.default_rng(n)
-        count = 400_003                                   # float64: slices of > 1 MB => several 512 KB windows each
         for inplace in (False, True):
             src = [rng.random(count) for _ in range(n)]
             exp = np.sum(src, 0)
