@@ -3,6 +3,7 @@
 #include "tl_shm_coll.h"
 #include "core/ucc_global_opts.h"
 #include "core/ucc_team.h"
+#include "schedule/ucc_schedule_pipelined.h"
 #include "components/topo/ucc_topo.h"
 #include <strings.h>
 
@@ -56,6 +57,7 @@ static ucc_config_field_t tl_shm_context_config_table[] = {
     {"RANKS_REORDERING", "y", "Ring algorithms visit the members host by host (and socket by socket) instead of in rank order; needs USE_TOPO",
      ucc_offsetof(ucc_tl_shm_context_config_t, ranks_reordering), UCC_CONFIG_TYPE_BOOL},
     {"REDUCE_AVG_PRE_OP", "n", "Apply the 1/N scaling of AVG before (y) or after (n) the reduction", ucc_offsetof(ucc_tl_shm_context_config_t, reduce_avg_pre_op), UCC_CONFIG_TYPE_BOOL},
+    {"REDUCE_SRG_KN_PIPELINE", "n", "Pipelining of the SRG reduce: thresh=<size>:fragsize=<size>:nfrags=<n>:pdepth=<n>:<parallel|ordered|sequential>", ucc_offsetof(ucc_tl_shm_context_config_t, reduce_srg_kn_pipeline), UCC_CONFIG_TYPE_PIPELINE_PARAMS},
     {"ALLREDUCE_SRA_KN_PIPELINE", "n", "Pipelining of the SRA allreduce", ucc_offsetof(ucc_tl_shm_context_config_t, allreduce_sra_kn_pipeline), UCC_CONFIG_TYPE_PIPELINE_PARAMS},
     {NULL}};
 
@@ -128,7 +130,7 @@ static ucc_status_t shm_task_setup(ucc_tl_shm_task_t *t)
     return UCC_OK;
 }
 
-static ucc_status_t shm_coll_init_alg(ucc_base_coll_args_t *bargs, ucc_base_team_t *team, ucc_coll_task_t **task_p, ucc_tl_shm_alg_fn_t fn)
+static ucc_status_t shm_coll_init_plain(ucc_base_coll_args_t *bargs, ucc_base_team_t *team, ucc_coll_task_t **task_p, ucc_tl_shm_alg_fn_t fn)
 {
     ucc_tl_shm_task_t *t;
     ucc_status_t st = ucc_tl_shm_task_alloc(bargs, team, &t);
@@ -144,6 +146,83 @@ static ucc_status_t shm_coll_init_alg(ucc_base_coll_args_t *bargs, ucc_base_team
     if (UCC_COLL_ARGS_ACTIVE_SET(&bargs->args)) t->team->seq_num--;
     *task_p = &t->super;
     return UCC_OK;
+}
+
+/* ALLREDUCE_SRA_KN_PIPELINE / REDUCE_SRG_KN_PIPELINE (reference allreduce_sra_knomial.c:175-243, reduce_srg_knomial.c): the vector is cut into
+ * fragments, `pdepth` SRA / SRG tasks are in flight and re-armed round robin by the pipelined schedule - the scatter-reduce of fragment i+1
+ * overlaps the allgather of fragment i, and the scratch of a task is a fragment, not the vector.  A re-armed task rebuilds its step program
+ * from the new arguments at post (UCC_COLL_TASK_FLAG_ARGS_UPDATED). */
+typedef struct shm_pipe { ucc_schedule_pipelined_t super; ucc_tl_shm_alg_fn_t fn; size_t total, dts, fcount; } shm_pipe_t;
+static ucc_status_t shm_frag_post(ucc_coll_task_t *t) { return ucc_schedule_start(t); }
+static ucc_status_t shm_frag_finalize(ucc_coll_task_t *t) { ucc_status_t st = ucc_schedule_finalize(t); free(t); return st; }
+static void shm_frag_args(const ucc_coll_args_t *a, size_t off_bytes, size_t cnt, ucc_coll_args_t *f)
+{
+    *f = *a;
+    if (f->src.info.buffer) f->src.info.buffer = PTR_OFFSET(f->src.info.buffer, off_bytes);
+    if (f->dst.info.buffer) f->dst.info.buffer = PTR_OFFSET(f->dst.info.buffer, off_bytes);
+    f->src.info.count = cnt; f->dst.info.count = cnt;
+}
+static ucc_status_t shm_pipe_frag_init(ucc_base_coll_args_t *b, ucc_schedule_pipelined_t *sp, ucc_base_team_t *team, ucc_schedule_t **frag)
+{
+    shm_pipe_t *pp = (shm_pipe_t *)sp;
+    ucc_base_coll_args_t fb = *b; ucc_coll_task_t *task = NULL; ucc_status_t st;
+    ucc_schedule_t *f = (ucc_schedule_t *)calloc(1, sizeof(*f));
+    if (!f) return UCC_ERR_NO_MEMORY;
+    shm_frag_args(&b->args, 0, pp->fcount, &fb.args); /* the largest fragment */
+    ucc_schedule_init(f, &fb, team);
+    f->super.post = shm_frag_post; f->super.finalize = shm_frag_finalize;
+    st = shm_coll_init_plain(&fb, team, &task, pp->fn);
+    if (st == UCC_OK) st = ucc_schedule_add_task(f, task);
+    if (st == UCC_OK) st = ucc_task_subscribe_dep(&f->super, task, UCC_EVENT_SCHEDULE_STARTED);
+    if (st != UCC_OK) { if (task && !f->n_tasks) task->finalize(task); shm_frag_finalize(&f->super); return st; }
+    *frag = f;
+    return UCC_OK;
+}
+static ucc_status_t shm_pipe_frag_setup(ucc_schedule_pipelined_t *sp, ucc_schedule_t *frag, int frag_num)
+{
+    shm_pipe_t *pp = (shm_pipe_t *)sp;
+    size_t off = (size_t)frag_num * pp->fcount, cnt = ucc_min(pp->fcount, pp->total - off);
+    ucc_coll_args_t fa, *ta = &frag->tasks[0]->bargs.args;
+    shm_frag_args(&sp->super.super.bargs.args, off * pp->dts, cnt, &fa);
+    ta->src = fa.src; ta->dst = fa.dst;
+    frag->tasks[0]->flags |= UCC_COLL_TASK_FLAG_ARGS_UPDATED;
+    return UCC_OK;
+}
+static ucc_status_t shm_pipe_finalize(ucc_coll_task_t *t) { ucc_status_t st = ucc_schedule_pipelined_finalize(t); free(t); return st; }
+/* UCC_ERR_NOT_FOUND: pipelining does not apply, build the plain task */
+static ucc_status_t shm_coll_init_pipelined(ucc_base_coll_args_t *b, ucc_base_team_t *team, ucc_coll_task_t **task_p, ucc_tl_shm_alg_fn_t fn)
+{
+    ucc_tl_shm_context_t *ctx = ucc_derived_of(team->context, ucc_tl_shm_context_t);
+    const ucc_pipeline_params_t *pp = fn == ucc_tl_shm_allreduce_sra ? &ctx->cfg.allreduce_sra_kn_pipeline : &ctx->cfg.reduce_srg_kn_pipeline;
+    const ucc_coll_args_t *a = &b->args;
+    ucc_rank_t N = team->params.size;
+    const ucc_coll_buffer_info_t *info = (a->coll_type == UCC_COLL_TYPE_REDUCE && !((ucc_rank_t)a->root == team->params.rank)) ? &a->src.info : &a->dst.info;
+    size_t count = info->count, dts, fcount; int n_total, depth; shm_pipe_t *sp; ucc_status_t st;
+    if (!pp->n_frags || !pp->pdepth || pp->threshold == UCC_MEMUNITS_INF || pp->threshold == UCC_MEMUNITS_AUTO || UCC_DT_IS_GENERIC(info->datatype)) return UCC_ERR_NOT_FOUND;
+    dts = ucc_dt_size(info->datatype);
+    if (!dts || count * dts < pp->threshold) return UCC_ERR_NOT_FOUND;
+    fcount = (pp->frag_size == UCC_MEMUNITS_INF || pp->frag_size == UCC_MEMUNITS_AUTO) ? ucc_div_round_up(count, pp->n_frags) : ucc_max(1, pp->frag_size / dts);
+    if (fcount < N) fcount = N; /* every rank of a fragment's exchange gets a part */
+    n_total = (int)ucc_div_round_up(count, fcount);
+    if (n_total < 2 || (count % fcount && count % fcount < N)) return UCC_ERR_NOT_FOUND;
+    depth = (int)ucc_min(ucc_min(pp->pdepth, (unsigned)n_total), UCC_SCHEDULE_PIPELINED_MAX_FRAGS);
+    sp = (shm_pipe_t *)calloc(1, sizeof(*sp));
+    if (!sp) return UCC_ERR_NO_MEMORY;
+    sp->fn = fn; sp->total = count; sp->dts = dts; sp->fcount = fcount;
+    st = ucc_schedule_pipelined_init(b, team, shm_pipe_frag_init, shm_pipe_frag_setup, depth, n_total, pp->order, &sp->super);
+    if (st != UCC_OK) { free(sp); return st; }
+    sp->super.super.super.finalize = shm_pipe_finalize;
+    tl_debug(team->context->lib, "%s pipelined: %d fragments of %zu elements, %d in flight", ucc_coll_type_str(a->coll_type), n_total, fcount, depth);
+    *task_p = &sp->super.super.super;
+    return UCC_OK;
+}
+static ucc_status_t shm_coll_init_alg(ucc_base_coll_args_t *bargs, ucc_base_team_t *team, ucc_coll_task_t **task_p, ucc_tl_shm_alg_fn_t fn)
+{
+    if (fn == ucc_tl_shm_allreduce_sra || fn == ucc_tl_shm_reduce_srg) {
+        ucc_status_t st = shm_coll_init_pipelined(bargs, team, task_p, fn);
+        if (st != UCC_ERR_NOT_FOUND) return st;
+    }
+    return shm_coll_init_plain(bargs, team, task_p, fn);
 }
 
 /* one tiny init wrapper per (coll, alg) so that the score map can point at distinct functions */

@@ -74,7 +74,7 @@ typedef struct ucc_tl_shm_context_config {
     size_t    allreduce_sliding_win_buf_size; /* sliding_window allreduce: bytes fetched from a peer and reduced per step */
     size_t    alltoallv_hybrid_thresh;   /* alltoallv `hybrid`: messages up to this size ride the Bruck rounds */
     int       reduce_avg_pre_op;
-    ucc_pipeline_params_t allreduce_sra_kn_pipeline;
+    ucc_pipeline_params_t allreduce_sra_kn_pipeline, reduce_srg_kn_pipeline;
 } ucc_tl_shm_context_config_t;
 
 typedef struct ucc_tl_shm_lib { ucc_tl_lib_t super; } ucc_tl_shm_lib_t;

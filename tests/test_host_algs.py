@@ -649,3 +649,43 @@ def test_reduce_scatter_knomial_radix(radix):
                     for r in range(n):
                         assert np.allclose(buf[r][r * count:(r + 1) * count], exp[r * count:(r + 1) * count]), (n, count, op, r)
             team.destroy()
+
+
+@pytest.mark.parametrize("order", ["parallel", "ordered", "sequential"])
+@pytest.mark.parametrize("n", [2, 5, 8])
+def test_sra_srg_pipelines(n, order, capfd):
+    """ALLREDUCE_SRA_KN_PIPELINE / REDUCE_SRG_KN_PIPELINE: fragments of the vector run as re-armed SRA / SRG tasks (ragged last fragment,
+    vectors below the threshold unpipelined, persistent re-posts, in place)"""
+    pipe = f"thresh=2k:fragsize=4k:nfrags=4:pdepth=2:{order}"
+    env = {"UCC_TL_SHM_TUNE": "allreduce:inf:@sra_knomial#reduce:inf:@srg", "UCC_TL_SHM_ALLREDUCE_SRA_KN_PIPELINE": pipe, "UCC_TL_SHM_REDUCE_SRG_KN_PIPELINE": pipe,
+           "UCC_TL_SHM_ALLREDUCE_SRA_KN_RADIX": "3", "UCC_TLS": "shm,self", "UCC_TL_SHM_LOG_LEVEL": "debug"}
+    with UccJob(n, env=env) as job:
+        team = job.create_team()
+        rng = np.random.default_rng(n)
+        for count in (100, 1024, 2600, 5003):
+            capfd.readouterr()
+            for op in ("sum", "avg"):
+                for inplace in (False, True):
+                    src = [rng.integers(-1000, 1000, count).astype(np.float64) for _ in range(n)]
+                    exp = np.sum(src, 0) / (n if op == "avg" else 1)
+                    dst = [s_.copy() for s_ in src] if inplace else [np.zeros(count) for _ in range(n)]
+                    req = team.coll([coll_args("allreduce", None if inplace else src[r], dst[r], dt="float64", op=op, inplace=inplace, persistent=True) for r in range(n)])
+                    for rep in range(2):
+                        if inplace and rep:
+                            for r in range(n):
+                                dst[r][:] = src[r]
+                        assert req.run() == U.UCC_OK
+                        for r in range(n):
+                            assert np.allclose(dst[r], exp), ("allreduce", count, op, inplace, rep, r)
+                    req.finalize()
+            for root in sorted({0, n - 1}):
+                src = [rng.integers(-1000, 1000, count).astype(np.float64) for _ in range(n)]
+                keep = [s_.copy() for s_ in src]
+                dst = np.zeros(count)
+                run(team, [coll_args("reduce", src[r], dst if r == root else None, dt="float64", op="sum", root=root, count_dst=count) for r in range(n)])
+                assert np.allclose(dst, np.sum(keep, 0)), ("reduce", count, root)
+            log = capfd.readouterr()
+            log = log.out + log.err
+            nf = -(-count // 512)                                        # 4 KB fragments of float64
+            assert (f"allreduce pipelined: {nf} fragments of 512 elements, 2 in flight" in log) == (count * 8 >= 2048), count
+            assert (f"reduce pipelined: {nf} fragments" in log) == (count * 8 >= 2048), count
