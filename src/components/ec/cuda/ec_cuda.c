@@ -264,6 +264,13 @@ static ucc_status_t exec_start(ucc_ee_executor_t *xe, void *ee_context)
         if (!x->wait_state) return UCC_ERR_NO_MEMORY;
         *x->wait_state = 0;
         CUDA_CHECK(cudaHostGetDevicePointer(&dp, (void *)x->wait_state, 0)); x->wait_state_dev = (volatile uint32_t *)dp;
+        /* STREAM_TASK_MODE (reference ec_cuda.c:21-36): memops parks the stream on a stream memory operation - no SM, no thread - when the
+         * driver exports it; kernel (and auto) launch the one-thread wait kernel */
+        if (EC_CFG->stream_task_mode == EC_CUDA_TASK_MEMOPS && ucc_cu_api_load() == UCC_OK && ucc_cu.cuStreamWaitValue32 &&
+            ucc_cu.cuStreamWaitValue32((CUstream)ee_context, (CUdeviceptr)(uintptr_t)x->wait_state_dev, 1, 0 /* CU_STREAM_WAIT_VALUE_GEQ */) == CUDA_SUCCESS) {
+            x->state = EXEC_STARTED;
+            return UCC_OK;
+        }
         if (ec_launch_wait(x->wait_state_dev, (cudaStream_t)ee_context) != cudaSuccess) { (void)cudaGetLastError(); return UCC_ERR_NO_MESSAGE; }
         x->state = EXEC_STARTED;
         return UCC_OK;

@@ -317,7 +317,9 @@ static ucc_status_t prog_sra_kn(ucc_tl_shm_task_t *t, char *w, void *scratch, si
     ucc_kn_pattern_t p; ucc_status_t st = UCC_OK; unsigned step = 3, nsteps = 0;
     ucc_sra_seg_t segs[33]; uint64_t dists[32]; ucc_rank_t peers[64];
 #define SRA_RANK(_v) ((ucc_rank_t)(((_v) + root) % N))
+    const int avg_pre = t->op == UCC_OP_AVG && SHM_CTX(t->team)->cfg.reduce_avg_pre_op; /* REDUCE_AVG_PRE_OP: contributions are scaled, not the sum */
     ucc_kn_pattern_init(&p, vr, N, radix);
+    if (avg_pre) CHK(shm_prog_reduce(t, w, w, NULL, count, mt, 1));
     if (p.type == UCC_KN_NODE_EXTRA) {
         CHK(shm_prog_send(t, SRA_RANK(p.partner), w, len, mt, 1)); CHK(shm_prog_wait(t));
         if (!gather_only) { CHK(shm_prog_recv(t, SRA_RANK(p.partner), w, len, mt, 2)); CHK(shm_prog_wait(t)); }
@@ -339,7 +341,7 @@ static ucc_status_t prog_sra_kn(ucc_tl_shm_task_t *t, char *w, void *scratch, si
         CHK(shm_prog_wait(t));
         for (unsigned i = 0; i < np; i++) CHK(shm_prog_reduce(t, w + keep.off * dts, w + keep.off * dts, (char *)scratch + i * slot, keep.cnt, mt, 0));
     }
-    if (t->op == UCC_OP_AVG) CHK(shm_prog_reduce(t, w + segs[nsteps].off * dts, w + segs[nsteps].off * dts, NULL, segs[nsteps].cnt, mt, 1));
+    if (t->op == UCC_OP_AVG && !avg_pre) CHK(shm_prog_reduce(t, w + segs[nsteps].off * dts, w + segs[nsteps].off * dts, NULL, segs[nsteps].cnt, mt, 1));
     if (gather_only == 2) return UCC_OK; /* reduce_scatter: every rank keeps its part */
     for (int i = (int)nsteps - 1; i >= 0; i--, step++) { /* round i's peers hold the other parts of segs[i] */
         const unsigned np = ucc_kn_round_peers(&p, dists[i], peers), digit = (unsigned)((vr / dists[i]) % p.radix);

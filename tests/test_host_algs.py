@@ -586,6 +586,19 @@ def test_allgather_knomial_radix(radix):
             team.destroy()
 
 
+def test_reduce_avg_pre_op():
+    """REDUCE_AVG_PRE_OP=y (reference tl_ucp.c: scale before the reduction): int8 contributions of 100 on 4 ranks overflow as a sum (400 -> -112, / 4 = -28)
+    but not as a sum of pre-scaled values (4 x 25 = 100)"""
+    for pre, exp in (("y", 100), ("n", -28)):
+        with UccJob(4, env={"UCC_TL_SHM_TUNE": "allreduce:inf:@sra_knomial", "UCC_TL_SHM_REDUCE_AVG_PRE_OP": pre, "UCC_TLS": "shm,self"}) as job:
+            team = job.create_team()
+            src = [np.full(64, 100, np.int8) for _ in range(4)]
+            dst = [np.zeros(64, np.int8) for _ in range(4)]
+            run(team, [coll_args("allreduce", src[r], dst[r], dt="int8", op="avg") for r in range(4)])
+            for r in range(4):
+                assert np.all(dst[r] == exp), (pre, dst[r][:4])
+
+
 @pytest.mark.parametrize("radix", ["2", "3", "4", "8", "0-4k:4,4k-inf:2"])
 def test_allreduce_sra_knomial_radix(radix):
     """ALLREDUCE_SRA_KN_RADIX: scatter-reduce / allgather over the digits of the rank in base k; every team size (extras through proxies),
