@@ -542,7 +542,7 @@ static ucc_status_t reduce_scatter_common(ucc_tl_shm_task_t *t, int is_v)
     CHK(shm_task_scratch(t, maxc * dts, mt, &scratch));
     if (inplace) work = dstbuf;
     else { CHK(shm_task_scratch(t, total * dts, mt, &work)); CHK(shm_prog_copy(t, work, a->src.info.buffer, total * dts, mt, a->src.info.mem_type)); }
-    CHK(prog_rsv_ring(t, (char *)work, scratch, cnt, off, mt, N > 2 && (is_v ? SHM_CTX(t->team)->cfg.reduce_scatterv_ring_bidirectional : SHM_CTX(t->team)->cfg.reduce_scatter_ring_bidirectional), maxc));
+    CHK(prog_rsv_ring(t, (char *)work, scratch, cnt, off, mt, N > 2 && mt == UCC_MEMORY_TYPE_HOST /* device buffers: one reduce launch per step */ && (is_v ? SHM_CTX(t->team)->cfg.reduce_scatterv_ring_bidirectional : SHM_CTX(t->team)->cfg.reduce_scatter_ring_bidirectional), maxc));
     if (t->op == UCC_OP_AVG) CHK(shm_prog_reduce(t, OFF(work, off[r] * dts), OFF(work, off[r] * dts), NULL, cnt[r], mt, 1));
     if (!inplace) CHK(shm_prog_copy(t, dstbuf, OFF(work, off[r] * dts), cnt[r] * dts, mt, mt));
 err:
