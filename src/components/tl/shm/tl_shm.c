@@ -45,9 +45,9 @@ static ucc_config_field_t tl_shm_context_config_table[] = {
      ucc_offsetof(ucc_tl_shm_context_config_t, gatherv_linear_num_posts), UCC_CONFIG_TYPE_UINT},
     {"SCATTERV_LINEAR_NUM_POSTS", "0", "Maximum number of sends the root of a linear scatterv keeps outstanding (0: all)",
      ucc_offsetof(ucc_tl_shm_context_config_t, scatterv_linear_num_posts), UCC_CONFIG_TYPE_UINT},
-    {"REDUCE_SCATTER_RING_BIDIRECTIONAL", "y", "Ring reduce_scatter: the two halves of every block travel around two inverted rings concurrently",
+    {"REDUCE_SCATTER_RING_BIDIRECTIONAL", "n", "Ring reduce_scatter: the two halves of every block travel around two inverted rings concurrently",
      ucc_offsetof(ucc_tl_shm_context_config_t, reduce_scatter_ring_bidirectional), UCC_CONFIG_TYPE_BOOL},
-    {"REDUCE_SCATTERV_RING_BIDIRECTIONAL", "y", "Ring reduce_scatterv: the two halves of every block travel around two inverted rings concurrently",
+    {"REDUCE_SCATTERV_RING_BIDIRECTIONAL", "n", "Ring reduce_scatterv: the two halves of every block travel around two inverted rings concurrently",
      ucc_offsetof(ucc_tl_shm_context_config_t, reduce_scatterv_ring_bidirectional), UCC_CONFIG_TYPE_BOOL},
     {"ALLTOALL_PAIRWISE_NUM_POSTS", "auto", "Maximum number of outstanding send/recv pairs in pairwise alltoall(v) (auto/0: unlimited)",
      ucc_offsetof(ucc_tl_shm_context_config_t, alltoall_pairwise_num_posts), UCC_CONFIG_TYPE_UINT},

@@ -497,7 +497,10 @@ err:
 /* ================================================================== */
 /* reduce_scatter(v)                                                   */
 /* ================================================================== */
-static ucc_status_t prog_rsv_ring(ucc_tl_shm_task_t *t, char *work, void *scratch, const size_t *cnt, const size_t *off, ucc_memory_type_t mt, int bidir, size_t maxc)
+/* ring reduce_scatter(v): a block is reduced into exactly once on every rank (own contribution + the partial sum that arrived), so the
+ * contributions are read where they are (`src`), partial sums live in `work` (touched only for the N-2 blocks that pass through) and the last
+ * step reduces straight into `out` (the place of the rank's result): no staging copy of the whole source, no final copy. */
+static ucc_status_t prog_rsv_ring(ucc_tl_shm_task_t *t, char *work, const char *src, char *out, void *scratch, const size_t *cnt, const size_t *off, ucc_memory_type_t mt, int bidir, size_t maxc)
 {
     const ucc_rank_t *ord = ring_order(t);
     ucc_rank_t N = t->vsize, r = t->vrank, p = ord ? t->team->ring_pos[r] : r, next = RING_AT(ord, p + 1, N), prev = RING_AT(ord, p + N - 1, N);
@@ -509,15 +512,17 @@ static ucc_status_t prog_rsv_ring(ucc_tl_shm_task_t *t, char *work, void *scratc
     char *scr2 = (char *)scratch + (maxc - maxc / 2) * dts;
     for (ucc_rank_t s = 0; s + 1 < N; s++) {
         ucc_rank_t sb = RING_AT(ord, p + 2 * N - s - 1, N), rb = RING_AT(ord, p + 2 * N - s - 2, N), sb2 = RING_AT(ord, p + s + 1, N), rb2 = RING_AT(ord, p + s + 2, N);
-        CHK(shm_prog_send(t, next, work + off[sb] * dts, LO(sb) * dts, mt, 1 + s));
+        const char *from = s == 0 ? src : work;                  /* step 0 forwards an own block, later steps the partial sum of the step before */
+        const int last = s + 2 == N;                             /* rb == rb2 == r */
+        CHK(shm_prog_send(t, next, from + off[sb] * dts, LO(sb) * dts, mt, 1 + s));
         CHK(shm_prog_recv(t, prev, scratch, LO(rb) * dts, mt, 1 + s));
         if (bidir) {
-            CHK(shm_prog_send(t, prev, work + (off[sb2] + LO(sb2)) * dts, HI(sb2) * dts, mt, N + 1 + s));
+            CHK(shm_prog_send(t, prev, from + (off[sb2] + LO(sb2)) * dts, HI(sb2) * dts, mt, N + 1 + s));
             CHK(shm_prog_recv(t, next, scr2, HI(rb2) * dts, mt, N + 1 + s));
         }
         CHK(shm_prog_wait(t));
-        CHK(shm_prog_reduce(t, work + off[rb] * dts, work + off[rb] * dts, scratch, LO(rb), mt, 0));
-        if (bidir && HI(rb2)) CHK(shm_prog_reduce(t, work + (off[rb2] + LO(rb2)) * dts, work + (off[rb2] + LO(rb2)) * dts, scr2, HI(rb2), mt, 0));
+        CHK(shm_prog_reduce(t, last ? out : work + off[rb] * dts, src + off[rb] * dts, scratch, LO(rb), mt, 0));
+        if (bidir && HI(rb2)) CHK(shm_prog_reduce(t, last ? out + LO(rb2) * dts : work + (off[rb2] + LO(rb2)) * dts, src + (off[rb2] + LO(rb2)) * dts, scr2, HI(rb2), mt, 0));
     }
 #undef LO
 #undef HI
@@ -531,7 +536,7 @@ static ucc_status_t reduce_scatter_common(ucc_tl_shm_task_t *t, int is_v)
     ucc_datatype_t dt = is_v ? a->dst.info_v.datatype : a->dst.info.datatype;
     ucc_memory_type_t mt = is_v ? a->dst.info_v.mem_type : a->dst.info.mem_type;
     size_t dts = ucc_dt_size(dt), total = 0, maxc = 0, *cnt, *off;
-    void *work, *scratch, *dstbuf = is_v ? a->dst.info_v.buffer : a->dst.info.buffer; ucc_status_t st;
+    void *work, *scratch, *dstbuf = is_v ? a->dst.info_v.buffer : a->dst.info.buffer; const char *src; char *out; ucc_status_t st;
     cnt = (size_t *)malloc(2 * N * sizeof(size_t)); if (!cnt) return UCC_ERR_NO_MEMORY;
     off = cnt + N; t->host_copy = cnt;
     for (ucc_rank_t i = 0; i < N; i++) {
@@ -540,11 +545,16 @@ static ucc_status_t reduce_scatter_common(ucc_tl_shm_task_t *t, int is_v)
         off[i] = total; total += cnt[i]; if (cnt[i] > maxc) maxc = cnt[i];
     }
     CHK(shm_task_scratch(t, maxc * dts, mt, &scratch));
-    if (inplace) work = dstbuf;
-    else { CHK(shm_task_scratch(t, total * dts, mt, &work)); CHK(shm_prog_copy(t, work, a->src.info.buffer, total * dts, mt, a->src.info.mem_type)); }
-    CHK(prog_rsv_ring(t, (char *)work, scratch, cnt, off, mt, N > 2 && mt == UCC_MEMORY_TYPE_HOST /* device buffers: one reduce launch per step */ && (is_v ? SHM_CTX(t->team)->cfg.reduce_scatterv_ring_bidirectional : SHM_CTX(t->team)->cfg.reduce_scatter_ring_bidirectional), maxc));
-    if (t->op == UCC_OP_AVG) CHK(shm_prog_reduce(t, OFF(work, off[r] * dts), OFF(work, off[r] * dts), NULL, cnt[r], mt, 1));
-    if (!inplace) CHK(shm_prog_copy(t, dstbuf, OFF(work, off[r] * dts), cnt[r] * dts, mt, mt));
+    if (inplace) { work = dstbuf; src = (const char *)dstbuf; out = (char *)dstbuf + off[r] * dts; }
+    else {
+        CHK(shm_task_scratch(t, total * dts, mt, &work));
+        out = (char *)dstbuf;
+        if (a->src.info.mem_type == mt) src = (const char *)a->src.info.buffer;
+        else { CHK(shm_prog_copy(t, work, a->src.info.buffer, total * dts, mt, a->src.info.mem_type)); src = (const char *)work; } /* contributions in another memory type: staged */
+    }
+    CHK(prog_rsv_ring(t, (char *)work, src, out, scratch, cnt, off, mt, N > 2 && mt == UCC_MEMORY_TYPE_HOST /* device buffers: one reduce launch per step */ &&
+                      (is_v ? SHM_CTX(t->team)->cfg.reduce_scatterv_ring_bidirectional : SHM_CTX(t->team)->cfg.reduce_scatter_ring_bidirectional), maxc));
+    if (t->op == UCC_OP_AVG) CHK(shm_prog_reduce(t, out, out, NULL, cnt[r], mt, 1));
 err:
     return st;
 }
