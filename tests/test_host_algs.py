@@ -516,7 +516,7 @@ def test_random_programs_with_random_knobs(seed):
 
 
 @pytest.mark.parametrize("bidir", ["y", "n"])
-@pytest.mark.parametrize("n", [3, 4, 7])
+@pytest.mark.parametrize("n", [2, 3, 4, 7])
 def test_reduce_scatterv_ring_bidirectional(n, bidir):
     """two inverted rings, each carrying one half of every block (reference reduce_scatterv_ring.c); blocks of 0, 1 and odd counts"""
     with UccJob(n, env={"UCC_TL_SHM_REDUCE_SCATTERV_RING_BIDIRECTIONAL": bidir, "UCC_TL_SHM_REDUCE_SCATTER_RING_BIDIRECTIONAL": bidir, "UCC_TLS": "shm,self"}) as j:
@@ -537,12 +537,16 @@ def test_reduce_scatterv_ring_bidirectional(n, bidir):
                 for r in range(n):
                     got = src[r][displs[r]:displs[r] + counts[r]] if inplace else dst[r][:counts[r]]
                     assert np.array_equal(got, exp[displs[r]:displs[r] + counts[r]]), (counts, inplace, r)
+                    # the ring reads the contributions where they are: a non-inplace source must come back untouched
+                    assert inplace or np.array_equal(src[r], keep[r]), (counts, r)
         for count in (1, 5, 4096):
             src = [rng.random(count * n) for _ in range(n)]
             dst = [np.zeros(count) for _ in range(n)]
+            keep = [s_.copy() for s_ in src]
             run(team, [coll_args("reduce_scatter", src[r], dst[r], dt="float64", op="avg") for r in range(n)])
             for r in range(n):
-                assert np.allclose(dst[r], np.mean(src, 0)[r * count:(r + 1) * count])
+                assert np.allclose(dst[r], np.mean(keep, 0)[r * count:(r + 1) * count])
+                assert np.array_equal(src[r], keep[r])
 
 
 @pytest.mark.parametrize("reorder", ["y", "n"])
